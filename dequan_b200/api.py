@@ -1,0 +1,230 @@
+"""ctypes binding of the C ABI (include/dequan_b200.h -> dequan_b200/lib/libdequan_b200.so).
+
+Used by tests/ and bench.py; the product's host side is the C++ drop-in header.  There is no
+fallback: if the CUDA library is missing or no device is present every solve raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+from typing import List, Optional
+
+import numpy as np
+
+from .model import CSP, UNASSIGNED, dq_model_desc
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libdequan_b200.so")
+U64_MAX = 2**64 - 1
+
+DQ_MODE_FIRST, DQ_MODE_COUNT_ALL = 0, 1
+ENGINE = {"auto": 0, "warp": 1, "lane": 2}
+ENGINE_NAME = {v: k for k, v in ENGINE.items()}
+OUTCOME = {0: "unsat", 1: "sat", 2: "budget", 3: "invalid"}
+MODEL_CLASS = {0: "generic", 1: "ne_same", 2: "queens"}
+
+
+class DequanError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"dequan_b200 error {code}: {msg}")
+        self.code = code
+
+
+class dq_tree_opts(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("split_depth", C.c_int32), ("part_rank", C.c_int32), ("part_count", C.c_int32),
+                ("node_budget", C.c_uint64), ("engine", C.c_int32), ("reserved", C.c_int32)]
+
+
+class dq_tree_result(C.Structure):
+    _fields_ = [("outcome", C.c_int32), ("n_prefixes", C.c_int32), ("n_solutions", C.c_uint64), ("n_nodes", C.c_uint64),
+                ("first_key", C.c_uint64), ("nodes_before_first", C.c_uint64), ("kernel_ms", C.c_double),
+                ("engine_used", C.c_int32), ("split_depth_used", C.c_int32), ("kernel_launches", C.c_uint64)]
+
+
+class dq_batch_opts(C.Structure):
+    _fields_ = [("node_budget", C.c_uint64), ("engine", C.c_int32), ("reserved", C.c_int32)]
+
+
+class dq_batch_stats(C.Structure):
+    _fields_ = [("n_sat", C.c_uint64), ("n_unsat", C.c_uint64), ("n_budget", C.c_uint64), ("total_nodes", C.c_uint64),
+                ("kernel_ms", C.c_double), ("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+
+
+EXPORTS = ["dq_device_info", "dq_compile", "dq_free", "dq_model_info", "dq_model_order", "dq_solve_tree",
+           "dq_tree_nodes_upto", "dq_solve_batch_cells", "dq_solve_batch_cells_dev", "dq_solve_batch_graphs",
+           "dq_measure_int_peak", "dq_last_error", "dq_version"]
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise DequanError(-3, f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, i32p, u8p, u64p = C.c_void_p, C.POINTER(C.c_int32), C.c_void_p, C.c_void_p
+    L.dq_device_info.argtypes = [i32p, i32p, C.c_char_p, C.c_size_t]
+    L.dq_compile.argtypes = [C.POINTER(dq_model_desc), C.POINTER(vp)]
+    L.dq_free.argtypes = [vp]
+    L.dq_free.restype = None
+    L.dq_model_info.argtypes = [vp, i32p, i32p, i32p, i32p]
+    L.dq_model_order.argtypes = [vp, i32p]
+    L.dq_solve_tree.argtypes = [vp, C.POINTER(dq_tree_opts), C.POINTER(dq_tree_result), i32p]
+    L.dq_tree_nodes_upto.argtypes = [vp, C.c_uint64, C.POINTER(C.c_uint64)]
+    L.dq_solve_batch_cells.argtypes = [vp, u8p, C.c_int64, C.c_int32, C.POINTER(dq_batch_opts), u8p, u64p, u8p,
+                                       C.POINTER(dq_batch_stats)]
+    L.dq_solve_batch_cells_dev.argtypes = L.dq_solve_batch_cells.argtypes
+    L.dq_solve_batch_graphs.argtypes = [C.c_int32, C.c_int32, C.c_void_p, u8p, C.c_int64, C.POINTER(dq_batch_opts),
+                                        u8p, u64p, u8p, C.POINTER(dq_batch_stats)]
+    L.dq_measure_int_peak.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.dq_last_error.restype = C.c_char_p
+    L.dq_version.restype = C.c_char_p
+    for name in EXPORTS:
+        if name not in ("dq_free", "dq_last_error", "dq_version"):
+            getattr(L, name).restype = C.c_int
+    _lib = L
+    return L
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise DequanError(rc, lib().dq_last_error().decode())
+
+
+def device_info():
+    sm, cc = C.c_int32(), C.c_int32()
+    name = C.create_string_buffer(128)
+    _check(lib().dq_device_info(C.byref(sm), C.byref(cc), name, 128))
+    return {"sm_count": sm.value, "cc": cc.value, "name": name.value.decode()}
+
+
+def measure_int_peak():
+    ops, ms = C.c_double(), C.c_double()
+    _check(lib().dq_measure_int_peak(C.byref(ops), C.byref(ms)))
+    return ops.value, ms.value
+
+
+@dataclass
+class TreeResult:
+    status: str
+    solutions: int
+    nodes: int
+    first: Optional[List[int]]
+    first_key: int
+    n_prefixes: int
+    split_depth: int
+    kernel_ms: float
+    engine: str
+    launches: int
+
+
+@dataclass
+class BatchResult:
+    solution: np.ndarray
+    nodes: np.ndarray
+    status: np.ndarray
+    n_sat: int
+    n_unsat: int
+    n_budget: int
+    total_nodes: int
+    kernel_ms: float
+    launches: int
+    h2d_bytes: int
+    d2h_bytes: int
+
+
+class Model:
+    """A compiled model: `dq_compile` of a CSP (CSP::FinalizeModel + Assignment::Reset)."""
+
+    def __init__(self, csp: CSP):
+        desc, keep = csp.desc()
+        h = C.c_void_p()
+        _check(lib().dq_compile(C.byref(desc), C.byref(h)))
+        del keep
+        self._h = h
+        self.n_vars = len(csp.domains)
+
+    def close(self):
+        if self._h:
+            lib().dq_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def info(self):
+        nv, kd, na, mc = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        _check(lib().dq_model_info(self._h, C.byref(nv), C.byref(kd), C.byref(na), C.byref(mc)))
+        return {"n_vars": nv.value, "max_dom": kd.value, "n_arcs": na.value, "model_class": MODEL_CLASS[mc.value]}
+
+    def order(self) -> List[int]:
+        o = np.zeros(max(self.n_vars, 1), dtype=np.int32)
+        _check(lib().dq_model_order(self._h, o.ctypes.data_as(C.POINTER(C.c_int32))))
+        return o[:self.n_vars].tolist()
+
+    def solve_tree(self, mode: str = "first", split_depth: int = 0, part_rank: int = 0, part_count: int = 1,
+                   engine: str = "auto", node_budget: int = 0) -> TreeResult:
+        o = dq_tree_opts(DQ_MODE_COUNT_ALL if mode == "count" else DQ_MODE_FIRST, split_depth, part_rank, part_count,
+                         node_budget, ENGINE[engine], 0)
+        r = dq_tree_result()
+        first = np.zeros(max(self.n_vars, 1), dtype=np.int32)
+        _check(lib().dq_solve_tree(self._h, C.byref(o), C.byref(r), first.ctypes.data_as(C.POINTER(C.c_int32))))
+        have = r.first_key != U64_MAX and (self.n_vars == 0 or first[0] != UNASSIGNED)
+        return TreeResult(OUTCOME[r.outcome], r.n_solutions, r.n_nodes, first[:self.n_vars].tolist() if have else None,
+                          r.first_key, r.n_prefixes, r.split_depth_used, r.kernel_ms,
+                          ENGINE_NAME.get(r.engine_used, "?"), r.kernel_launches)
+
+    def nodes_upto(self, key: int) -> int:
+        n = C.c_uint64()
+        _check(lib().dq_tree_nodes_upto(self._h, key, C.byref(n)))
+        return n.value
+
+    def solve_batch_cells(self, cells: np.ndarray, node_budget: int = 0, engine: str = "auto",
+                          out: Optional[tuple] = None) -> BatchResult:
+        """cells: uint8[n, stride] host array (0 = keep template domain)."""
+        assert cells.dtype == np.uint8 and cells.ndim == 2 and cells.flags.c_contiguous
+        n, stride = cells.shape
+        if out is None:
+            sol = np.zeros((n, stride), dtype=np.uint8)
+            nodes = np.zeros(n, dtype=np.uint64)
+            status = np.zeros(n, dtype=np.uint8)
+        else:
+            sol, nodes, status = out
+        o = dq_batch_opts(node_budget, ENGINE[engine], 0)
+        st = dq_batch_stats()
+        _check(lib().dq_solve_batch_cells(self._h, cells.ctypes.data, n, stride, C.byref(o), sol.ctypes.data,
+                                          nodes.ctypes.data, status.ctypes.data, C.byref(st)))
+        return BatchResult(sol, nodes, status, st.n_sat, st.n_unsat, st.n_budget, st.total_nodes, st.kernel_ms,
+                           st.kernel_launches, st.h2d_bytes, st.d2h_bytes)
+
+    def solve_batch_cells_ptr(self, cells_ptr: int, n: int, stride: int, sol_ptr: int, nodes_ptr: int, status_ptr: int,
+                              node_budget: int = 0, engine: str = "auto", device: bool = False):
+        """Raw-pointer form (pinned host buffers or, with device=True, HBM-resident buffers)."""
+        o = dq_batch_opts(node_budget, ENGINE[engine], 0)
+        st = dq_batch_stats()
+        fn = lib().dq_solve_batch_cells_dev if device else lib().dq_solve_batch_cells
+        _check(fn(self._h, cells_ptr, n, stride, C.byref(o), sol_ptr, nodes_ptr, status_ptr, C.byref(st)))
+        return st
+
+
+def solve_batch_graphs(n_vertices: int, k: int, edge_off: np.ndarray, edges: np.ndarray, node_budget: int = 0,
+                       engine: str = "auto") -> BatchResult:
+    assert edge_off.dtype == np.int64 and edges.dtype == np.uint8
+    edges = np.ascontiguousarray(edges)
+    n = len(edge_off) - 1
+    col = np.zeros((n, n_vertices), dtype=np.uint8)
+    nodes = np.zeros(n, dtype=np.uint64)
+    status = np.zeros(n, dtype=np.uint8)
+    o = dq_batch_opts(node_budget, ENGINE[engine], 0)
+    st = dq_batch_stats()
+    _check(lib().dq_solve_batch_graphs(n_vertices, k, edge_off.ctypes.data, edges.ctypes.data, n, C.byref(o),
+                                       col.ctypes.data, nodes.ctypes.data, status.ctypes.data, C.byref(st)))
+    return BatchResult(col, nodes, status, st.n_sat, st.n_unsat, st.n_budget, st.total_nodes, st.kernel_ms,
+                       st.kernel_launches, st.h2d_bytes, st.d2h_bytes)

@@ -1,0 +1,561 @@
+// dq_api.cu — the C ABI (include/dequan_b200.h) over the CUDA engines.
+// Host orchestration only: table upload, frontier expansion loop, kernel launches, result
+// gathering.  No search runs on the CPU; every solve needs a CUDA device.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "dequan_b200.h"
+#include "dq_kernels.cuh"
+#include "dq_model.hpp"
+
+namespace dq {
+
+static thread_local std::string g_err;
+
+#define DQ_CUDA(call)                                                                       \
+    do {                                                                                    \
+        cudaError_t e__ = (call);                                                           \
+        if (e__ != cudaSuccess) {                                                           \
+            g_err = std::string(#call) + ": " + cudaGetErrorString(e__);                    \
+            return DQ_ERR_CUDA;                                                             \
+        }                                                                                   \
+    } while (0)
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc((void**)&p, std::max<size_t>(n, 1) * sizeof(T));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct LevelArrays {               // kept per expansion level for FIRST-mode node accounting
+    int n = 0;
+    DevBuf<uint32_t> dmask, surv, child_off, parent_of;   // parent_of indexes the PREVIOUS level
+    DevBuf<unsigned long long> node_off;
+    DevBuf<uint8_t> prefixes;      // [n][depth]
+};
+
+}  // namespace dq
+
+using namespace dq;
+
+struct dq_model {
+    CompiledModel cm;
+    bool uploaded = false;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int sm_count = 0;
+    // model tables in HBM
+    DevBuf<uint32_t> d_ent_off, d_ent_moff, d_masks, d_dom0;
+    DevBuf<uint16_t> d_ent;
+    DevBuf<uint8_t> d_order, d_pos, d_cell_lut;
+    DevBuf<int32_t> d_values, d_sizes;
+    int n_sizes = 0;
+    // tree-solve scratch, retained until the next solve for dq_tree_nodes_upto()
+    std::vector<LevelArrays> levels;
+    DevBuf<unsigned long long> d_ctrl;          // cursor, totals[2], best_key, scan totals[2], misc
+    DevBuf<unsigned long long> d_sub_nodes, d_sol_key;
+    DevBuf<uint8_t> d_sol;
+    int last_depth = 0;
+    unsigned long long last_n_prefix = 0;
+    int last_part_rank = 0, last_part_count = 1;
+    // batch scratch
+    DevBuf<uint8_t> b_cells, b_solution, b_status;
+    DevBuf<unsigned long long> b_nodes;
+};
+
+namespace dq {
+
+static int upload(dq_model* m) {
+    if (m->uploaded) return DQ_OK;
+    int dev = 0;
+    DQ_CUDA(cudaGetDevice(&dev));
+    DQ_CUDA(cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, dev));
+    DQ_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+    DQ_CUDA(cudaEventCreate(&m->ev0));
+    DQ_CUDA(cudaEventCreate(&m->ev1));
+    const CompiledModel& c = m->cm;
+    const int nv = c.nv;
+    auto up = [&](auto& buf, const auto& vec) -> cudaError_t {
+        cudaError_t e = buf.reserve(vec.size());
+        if (e != cudaSuccess) return e;
+        if (vec.empty()) return cudaSuccess;
+        return cudaMemcpy(buf.p, vec.data(), vec.size() * sizeof(vec[0]), cudaMemcpyHostToDevice);
+    };
+    DQ_CUDA(up(m->d_ent_off, c.ent_off));
+    DQ_CUDA(up(m->d_ent, c.ent));
+    DQ_CUDA(up(m->d_ent_moff, c.ent_moff));
+    DQ_CUDA(up(m->d_masks, c.masks));
+    DQ_CUDA(up(m->d_dom0, c.dom0));
+    std::vector<uint8_t> order(nv), pos(nv);
+    for (int i = 0; i < nv; i++) { order[i] = (uint8_t)c.order[i]; pos[i] = (uint8_t)c.pos_of[i]; }
+    DQ_CUDA(up(m->d_order, order));
+    DQ_CUDA(up(m->d_pos, pos));
+    std::vector<int32_t> values((size_t)nv * 32, 0);
+    std::vector<uint8_t> lut((size_t)nv * 256, 0xFF);
+    for (int v = 0; v < nv; v++)
+        for (size_t j = 0; j < c.values[v].size(); j++) {
+            values[(size_t)v * 32 + j] = c.values[v][j];
+            if (c.values[v][j] >= 1 && c.values[v][j] <= 255) lut[(size_t)v * 256 + c.values[v][j]] = (uint8_t)j;
+        }
+    DQ_CUDA(up(m->d_values, values));
+    DQ_CUDA(up(m->d_cell_lut, lut));
+    std::vector<int32_t> sizes = c.distinct_sizes;
+    if (std::find(sizes.begin(), sizes.end(), 1) == sizes.end()) sizes.push_back(1);
+    std::sort(sizes.begin(), sizes.end());
+    m->n_sizes = (int)sizes.size();
+    DQ_CUDA(up(m->d_sizes, sizes));
+    DQ_CUDA(m->d_ctrl.reserve(16));
+    m->uploaded = true;
+    return DQ_OK;
+}
+
+static TreeModelDev dev_model(const dq_model* m) {
+    TreeModelDev M;
+    M.T.nv = m->cm.nv;
+    M.T.ent_off = m->d_ent_off.p;
+    M.T.ent = m->d_ent.p;
+    M.T.ent_moff = m->d_ent_moff.p;
+    M.T.masks = m->d_masks.p;
+    M.dom0 = m->d_dom0.p;
+    M.order = m->d_order.p;
+    M.pos = m->d_pos.p;
+    M.trail = m->cm.trail_bound;
+    return M;
+}
+
+// Picks the template instantiation for the model's feature flags and launches `KERNEL`.
+#define DQ_DISPATCH(m, KERNEL, grid, block, smem, stream, ...)                                            \
+    do {                                                                                                  \
+        if ((m)->cm.has_f) {                                                                              \
+            if ((m)->cm.has_table) KERNEL<true, true><<<grid, block, smem, stream>>>(__VA_ARGS__);        \
+            else KERNEL<true, false><<<grid, block, smem, stream>>>(__VA_ARGS__);                         \
+        } else {                                                                                          \
+            if ((m)->cm.has_table) KERNEL<false, true><<<grid, block, smem, stream>>>(__VA_ARGS__);       \
+            else KERNEL<false, false><<<grid, block, smem, stream>>>(__VA_ARGS__);                        \
+        }                                                                                                 \
+    } while (0)
+
+template <class K>
+static int max_ctas_per_sm(K kernel, int threads, size_t smem, int* out) {
+    if (smem > 48 * 1024) DQ_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, kernel, threads, smem));
+    return DQ_OK;
+}
+
+#define DQ_OCCUPANCY(m, KERNEL, threads, smem, out)                                              \
+    ((m)->cm.has_f ? ((m)->cm.has_table ? max_ctas_per_sm(KERNEL<true, true>, threads, smem, out) \
+                                        : max_ctas_per_sm(KERNEL<true, false>, threads, smem, out)) \
+                   : ((m)->cm.has_table ? max_ctas_per_sm(KERNEL<false, true>, threads, smem, out) \
+                                        : max_ctas_per_sm(KERNEL<false, false>, threads, smem, out)))
+
+}  // namespace dq
+
+extern "C" {
+
+const char* dq_last_error(void) { return g_err.c_str(); }
+const char* dq_version(void) { return "dequan_b200 0.1 (sm_100a)"; }
+
+int dq_device_info(int32_t* sm_count, int32_t* cc, char* name, size_t name_len) {
+    int dev = 0;
+    DQ_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp p;
+    DQ_CUDA(cudaGetDeviceProperties(&p, dev));
+    if (sm_count) *sm_count = p.multiProcessorCount;
+    if (cc) *cc = p.major * 10 + p.minor;
+    if (name && name_len) { strncpy(name, p.name, name_len - 1); name[name_len - 1] = 0; }
+    return DQ_OK;
+}
+
+int dq_compile(const dq_model_desc* desc, dq_model** out) {
+    if (!out) { g_err = "null out"; return DQ_ERR_INVALID; }
+    *out = nullptr;
+    dq_model* m = new (std::nothrow) dq_model();
+    if (!m) return DQ_ERR_NOMEM;
+    std::string err;
+    int rc = compile_model(desc, m->cm, err);
+    if (rc != DQ_OK) { g_err = err; delete m; return rc; }
+    *out = m;
+    return DQ_OK;
+}
+
+void dq_free(dq_model* m) {
+    if (!m) return;
+    if (m->uploaded) {
+        m->d_ent_off.release(); m->d_ent_moff.release(); m->d_masks.release(); m->d_dom0.release();
+        m->d_ent.release(); m->d_order.release(); m->d_pos.release(); m->d_cell_lut.release();
+        m->d_values.release(); m->d_sizes.release(); m->d_ctrl.release();
+        m->d_sub_nodes.release(); m->d_sol_key.release(); m->d_sol.release();
+        m->b_cells.release(); m->b_solution.release(); m->b_status.release(); m->b_nodes.release();
+        for (auto& l : m->levels) {
+            l.dmask.release(); l.surv.release(); l.child_off.release(); l.parent_of.release();
+            l.node_off.release(); l.prefixes.release();
+        }
+        if (m->ev0) cudaEventDestroy(m->ev0);
+        if (m->ev1) cudaEventDestroy(m->ev1);
+        if (m->stream) cudaStreamDestroy(m->stream);
+    }
+    delete m;
+}
+
+int dq_model_info(const dq_model* m, int32_t* n_vars, int32_t* max_dom, int32_t* n_arcs, int32_t* model_class) {
+    if (!m) { g_err = "null model"; return DQ_ERR_INVALID; }
+    if (n_vars) *n_vars = m->cm.nv;
+    if (max_dom) *max_dom = m->cm.kmax;
+    if (n_arcs) *n_arcs = (int32_t)m->cm.ent.size();
+    if (model_class) *model_class = m->cm.model_class;
+    return DQ_OK;
+}
+
+int dq_model_order(const dq_model* m, int32_t* order_out) {
+    if (!m || !order_out) { g_err = "null argument"; return DQ_ERR_INVALID; }
+    for (int i = 0; i < m->cm.nv; i++) order_out[i] = m->cm.order[i];
+    return DQ_OK;
+}
+
+int dq_solve_tree(dq_model* m, const dq_tree_opts* opts, dq_tree_result* res, int32_t* first_solution) {
+    if (!m || !opts || !res) { g_err = "null argument"; return DQ_ERR_INVALID; }
+    if (opts->part_count < 1 || opts->part_rank < 0 || opts->part_rank >= opts->part_count) { g_err = "bad partition"; return DQ_ERR_INVALID; }
+    if (opts->node_budget) { g_err = "node_budget is a batch option; single-tree solves have none"; return DQ_ERR_UNSUPPORTED; }
+    memset(res, 0, sizeof *res);
+    const int nv = m->cm.nv;
+    const int UNASSIGNED = -2147483647;
+    res->first_key = KEY_NONE;
+    res->engine_used = DQ_ENGINE_WARP;
+    if (first_solution) for (int i = 0; i < nv; i++) first_solution[i] = UNASSIGNED;
+    if (nv == 0) { res->outcome = DQ_SAT; res->n_solutions = 1; res->first_key = 0; return DQ_OK; }   // IsComplete at entry
+    int rc = upload(m);
+    if (rc != DQ_OK) return rc;
+    const bool count_all = opts->mode == DQ_MODE_COUNT_ALL;
+    const TreeModelDev M = dev_model(m);
+    const size_t wbytes = warp_state_bytes(nv, M.trail);
+    const size_t smem = wbytes * kWarpsPerCta;
+    if (smem > 200 * 1024) { g_err = "model state exceeds shared memory"; return DQ_ERR_UNSUPPORTED; }
+    int occ = 0;
+    rc = DQ_OCCUPANCY(m, k_tree_dfs, kWarpsPerCta * 32, smem, &occ);
+    if (rc != DQ_OK) return rc;
+    int occ_e = 0;
+    rc = DQ_OCCUPANCY(m, k_expand, kWarpsPerCta * 32, smem, &occ_e);
+    if (rc != DQ_OK) return rc;
+    if (occ < 1 || occ_e < 1) { g_err = "kernel does not fit an SM"; return DQ_ERR_UNSUPPORTED; }
+    const long long resident_warps = (long long)occ * m->sm_count * kWarpsPerCta;
+    const int max_depth = nv - 1;
+    const int want_depth = opts->split_depth > 0 ? std::min(opts->split_depth, max_depth) : -1;
+    const long long want_prefixes = resident_warps * 24 * opts->part_count;
+
+    unsigned long long* ctrl = m->d_ctrl.p;   // [0]=cursor [1]=sols [2]=nodes [3]=best [4]=scan children [5]=scan nodes
+    unsigned long long h_ctrl[8] = {0, 0, 0, KEY_NONE, 0, 0, 0, 0};
+    DQ_CUDA(cudaMemcpyAsync(ctrl, h_ctrl, sizeof h_ctrl, cudaMemcpyHostToDevice, m->stream));
+    DQ_CUDA(cudaEventRecord(m->ev0, m->stream));
+
+    // ---- frontier expansion, level by level, children kept in DFS order ----
+    if (m->levels.empty()) m->levels.resize(1);
+    m->levels[0].n = 1;
+    DQ_CUDA(m->levels[0].prefixes.reserve(1));
+    int depth = 0;
+    unsigned long long shallow_nodes = 0, launches = 0;
+    bool empty = false;
+    while (depth < max_depth && (want_depth >= 0 ? depth < want_depth : m->levels[depth].n < want_prefixes)) {
+        LevelArrays& L = m->levels[depth];
+        const int n = L.n;
+        DQ_CUDA(L.dmask.reserve(n)); DQ_CUDA(L.surv.reserve(n)); DQ_CUDA(L.child_off.reserve(n)); DQ_CUDA(L.node_off.reserve(n));
+        const int grid = (n + kWarpsPerCta - 1) / kWarpsPerCta;
+        DQ_DISPATCH(m, k_expand, grid, kWarpsPerCta * 32, smem, m->stream, M, L.prefixes.p, depth, n, L.dmask.p, L.surv.p);
+        k_scan_level<<<1, 1024, 0, m->stream>>>(L.dmask.p, L.surv.p, n, L.child_off.p, L.node_off.p, ctrl + 4);
+        launches += 2;
+        unsigned long long tot[2];
+        DQ_CUDA(cudaMemcpyAsync(tot, ctrl + 4, sizeof tot, cudaMemcpyDeviceToHost, m->stream));
+        DQ_CUDA(cudaStreamSynchronize(m->stream));
+        shallow_nodes += tot[1];
+        if (tot[0] == 0) { empty = true; depth++; if ((int)m->levels.size() <= depth) m->levels.resize(depth + 1); m->levels[depth].n = 0; break; }
+        if (tot[0] > 0x7FFFFFFFull / (unsigned)(depth + 1)) { g_err = "frontier too large"; return DQ_ERR_NOMEM; }
+        if ((int)m->levels.size() <= depth + 1) m->levels.resize(depth + 2);
+        LevelArrays& C = m->levels[depth + 1];
+        C.n = (int)tot[0];
+        DQ_CUDA(C.prefixes.reserve((size_t)C.n * (depth + 1)));
+        DQ_CUDA(C.parent_of.reserve(C.n));
+        k_write_children<<<(n + 255) / 256, 256, 0, m->stream>>>(L.prefixes.p, depth, n, L.surv.p, L.child_off.p, C.prefixes.p, C.parent_of.p);
+        launches++;
+        depth++;
+    }
+    DQ_CUDA(cudaGetLastError());
+
+    const unsigned long long n_prefix = empty ? 0 : (unsigned long long)m->levels[depth].n;
+    m->last_depth = depth; m->last_n_prefix = n_prefix;
+    m->last_part_rank = opts->part_rank; m->last_part_count = opts->part_count;
+    res->n_prefixes = (int32_t)n_prefix;
+    res->split_depth_used = depth;
+
+    // ---- subtree DFS ----
+    long long n_warps = 0;
+    if (n_prefix) {
+        const unsigned long long mine = (n_prefix + opts->part_count - 1 - opts->part_rank) / opts->part_count;
+        long long ctas = std::min<long long>((long long)((mine + kWarpsPerCta - 1) / kWarpsPerCta), (long long)occ * m->sm_count);
+        if (ctas < 1) ctas = 1;
+        n_warps = ctas * kWarpsPerCta;
+        DQ_CUDA(m->d_sub_nodes.reserve(n_prefix));
+        DQ_CUDA(m->d_sol_key.reserve(n_warps));
+        DQ_CUDA(m->d_sol.reserve((size_t)n_warps * nv));
+        DQ_CUDA(cudaMemsetAsync(m->d_sub_nodes.p, 0, n_prefix * sizeof(unsigned long long), m->stream));
+        DQ_CUDA(cudaMemsetAsync(m->d_sol_key.p, 0xFF, n_warps * sizeof(unsigned long long), m->stream));
+        TreeDfsArgs A;
+        A.prefixes = m->levels[depth].prefixes.p; A.depth = depth; A.n_prefix = n_prefix;
+        A.part_rank = opts->part_rank; A.part_count = opts->part_count; A.count_all = count_all ? 1 : 0;
+        A.cursor = ctrl + 0; A.totals = ctrl + 1; A.best_key = ctrl + 3;
+        A.sub_nodes = m->d_sub_nodes.p; A.sol_key = m->d_sol_key.p; A.sol = m->d_sol.p;
+        DQ_DISPATCH(m, k_tree_dfs, (int)ctas, kWarpsPerCta * 32, smem, m->stream, M, A);
+        launches++;
+        DQ_CUDA(cudaGetLastError());
+    }
+    DQ_CUDA(cudaEventRecord(m->ev1, m->stream));
+    DQ_CUDA(cudaMemcpyAsync(h_ctrl, ctrl, sizeof h_ctrl, cudaMemcpyDeviceToHost, m->stream));
+    DQ_CUDA(cudaStreamSynchronize(m->stream));
+    float ms = 0;
+    DQ_CUDA(cudaEventElapsedTime(&ms, m->ev0, m->ev1));
+    res->kernel_ms = ms;
+    res->kernel_launches = launches;
+
+    const unsigned long long best = h_ctrl[3];
+    res->first_key = best;
+    const unsigned long long my_shallow = opts->part_rank == 0 ? shallow_nodes : 0;
+    if (count_all) {
+        res->n_solutions = h_ctrl[1];
+        res->n_nodes = h_ctrl[2] + my_shallow;
+        res->outcome = res->n_solutions ? DQ_SAT : DQ_UNSAT;
+    } else {
+        res->n_solutions = best != KEY_NONE ? 1 : 0;
+        res->outcome = res->n_solutions ? DQ_SAT : DQ_UNSAT;
+        uint64_t upto = 0;
+        rc = dq_tree_nodes_upto(m, best, &upto);
+        if (rc != DQ_OK) return rc;
+        res->n_nodes = upto;
+        res->nodes_before_first = upto;
+    }
+    if (best != KEY_NONE && first_solution) {
+        std::vector<unsigned long long> keys(n_warps);
+        DQ_CUDA(cudaMemcpy(keys.data(), m->d_sol_key.p, n_warps * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        long long w = -1;
+        for (long long i = 0; i < n_warps; i++) if (keys[i] == best) { w = i; break; }
+        if (w < 0) { g_err = "internal: winning solution not recorded"; return DQ_ERR_INTERNAL; }
+        std::vector<uint8_t> sol(nv);
+        DQ_CUDA(cudaMemcpy(sol.data(), m->d_sol.p + (size_t)w * nv, nv, cudaMemcpyDeviceToHost));
+        for (int v = 0; v < nv; v++) first_solution[v] = m->cm.values[v][sol[v]];
+    }
+    return DQ_OK;
+}
+
+// Nodes the reference's sequential search visits up to and including the solution in prefix `key`,
+// restricted to what THIS partition owns (rank 0 also owns the levels above the split).  With
+// key == UINT64_MAX: everything this partition explored.  Summed over partitions for the global
+// minimum key it equals Assignment::stats.assigned_vars of the reference (dequan.h:421).
+int dq_tree_nodes_upto(dq_model* m, uint64_t key, uint64_t* nodes) {
+    if (!m || !nodes) { g_err = "null argument"; return DQ_ERR_INVALID; }
+    *nodes = 0;
+    if (!m->uploaded) { g_err = "no solve to account for"; return DQ_ERR_INVALID; }
+    const int depth = m->last_depth;
+    const unsigned long long n_prefix = m->last_n_prefix;
+    unsigned long long total = 0;
+    // (a) subtrees with index <= key owned by this partition (the key subtree holds its partial count)
+    if (n_prefix) {
+        const unsigned long long lim = key == KEY_NONE ? n_prefix : std::min<unsigned long long>(key + 1, n_prefix);
+        std::vector<unsigned long long> sub(lim);
+        if (lim) DQ_CUDA(cudaMemcpy(sub.data(), m->d_sub_nodes.p, lim * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        for (unsigned long long i = m->last_part_rank; i < lim; i += m->last_part_count) total += sub[i];
+    }
+    // (b) levels above the split, in DFS order up to the node that creates prefix `key`
+    if (m->last_part_rank == 0) {
+        if (key == KEY_NONE || n_prefix == 0) {
+            for (int l = 0; l < depth; l++) {
+                const LevelArrays& L = m->levels[l];
+                if (L.n == 0) continue;
+                unsigned long long off = 0; uint32_t dm = 0;
+                DQ_CUDA(cudaMemcpy(&off, L.node_off.p + (L.n - 1), sizeof off, cudaMemcpyDeviceToHost));
+                DQ_CUDA(cudaMemcpy(&dm, L.dmask.p + (L.n - 1), sizeof dm, cudaMemcpyDeviceToHost));
+                total += off + __builtin_popcount(dm);
+            }
+        } else {
+            std::vector<uint8_t> pre(std::max(depth, 1));
+            if (depth) DQ_CUDA(cudaMemcpy(pre.data(), m->levels[depth].prefixes.p + key * (size_t)depth, depth, cudaMemcpyDeviceToHost));
+            unsigned long long idx = key;
+            for (int l = depth - 1; l >= 0; l--) {
+                uint32_t par = 0;
+                DQ_CUDA(cudaMemcpy(&par, m->levels[l + 1].parent_of.p + idx, sizeof par, cudaMemcpyDeviceToHost));
+                const LevelArrays& L = m->levels[l];
+                unsigned long long off = 0; uint32_t dm = 0;
+                DQ_CUDA(cudaMemcpy(&off, L.node_off.p + par, sizeof off, cudaMemcpyDeviceToHost));
+                DQ_CUDA(cudaMemcpy(&dm, L.dmask.p + par, sizeof dm, cudaMemcpyDeviceToHost));
+                const uint32_t upto_bit = (2u << pre[l]) - 1u;
+                total += off + __builtin_popcount(dm & upto_bit);
+                idx = par;
+            }
+        }
+    }
+    *nodes = total;
+    return DQ_OK;
+}
+
+static int run_batch_cells(dq_model* m, const uint8_t* cells_dev, int64_t n, int32_t stride, const dq_batch_opts* opts,
+                           uint8_t* sol_dev, unsigned long long* nodes_dev, uint8_t* status_dev, dq_batch_stats* st) {
+    const int nv = m->cm.nv;
+    const TreeModelDev M = dev_model(m);
+    const size_t smem = warp_state_bytes(nv, M.trail) * kWarpsPerCta;
+    if (smem > 200 * 1024) { g_err = "model state exceeds shared memory"; return DQ_ERR_UNSUPPORTED; }
+    int occ = 0;
+    int rc = DQ_OCCUPANCY(m, k_batch_cells, kWarpsPerCta * 32, smem, &occ);
+    if (rc != DQ_OK) return rc;
+    if (occ < 1) { g_err = "kernel does not fit an SM"; return DQ_ERR_UNSUPPORTED; }
+    unsigned long long* ctrl = m->d_ctrl.p;
+    DQ_CUDA(cudaMemsetAsync(ctrl, 0, 8 * sizeof(unsigned long long), m->stream));
+    BatchCellsArgs A;
+    A.cells = cells_dev; A.n = n; A.stride = stride; A.cell_lut = m->d_cell_lut.p; A.values = m->d_values.p;
+    A.sizes = m->d_sizes.p; A.n_sizes = m->n_sizes; A.budget = opts ? opts->node_budget : 0;
+    A.cursor = ctrl; A.solution = sol_dev; A.nodes = nodes_dev; A.status = status_dev; A.totals = ctrl + 1;
+    long long ctas = std::min<long long>((n + kWarpsPerCta - 1) / kWarpsPerCta, (long long)occ * m->sm_count);
+    if (ctas < 1) ctas = 1;
+    DQ_CUDA(cudaEventRecord(m->ev0, m->stream));
+    DQ_DISPATCH(m, k_batch_cells, (int)ctas, kWarpsPerCta * 32, smem, m->stream, M, A);
+    DQ_CUDA(cudaGetLastError());
+    DQ_CUDA(cudaEventRecord(m->ev1, m->stream));
+    unsigned long long h[8];
+    DQ_CUDA(cudaMemcpyAsync(h, ctrl, sizeof h, cudaMemcpyDeviceToHost, m->stream));
+    DQ_CUDA(cudaStreamSynchronize(m->stream));
+    if (st) {
+        float ms = 0;
+        DQ_CUDA(cudaEventElapsedTime(&ms, m->ev0, m->ev1));
+        st->n_sat = h[1]; st->n_unsat = h[2]; st->n_budget = h[3]; st->total_nodes = h[4];
+        st->kernel_ms = ms; st->kernel_launches = 1;
+    }
+    return DQ_OK;
+}
+
+int dq_solve_batch_cells_dev(dq_model* m, const uint8_t* cells_dev, int64_t n, int32_t stride, const dq_batch_opts* opts,
+                             uint8_t* solution_dev, uint64_t* nodes_dev, uint8_t* status_dev, dq_batch_stats* stats) {
+    if (!m || n < 0 || stride < m->cm.nv) { g_err = "bad argument"; return DQ_ERR_INVALID; }
+    if (stats) memset(stats, 0, sizeof *stats);
+    if (n == 0) return DQ_OK;
+    int rc = upload(m);
+    if (rc != DQ_OK) return rc;
+    return run_batch_cells(m, cells_dev, n, stride, opts, solution_dev, (unsigned long long*)nodes_dev, status_dev, stats);
+}
+
+int dq_solve_batch_cells(dq_model* m, const uint8_t* cells, int64_t n, int32_t stride, const dq_batch_opts* opts,
+                         uint8_t* solution, uint64_t* nodes, uint8_t* status, dq_batch_stats* stats) {
+    if (!m || n < 0 || stride < m->cm.nv) { g_err = "bad argument"; return DQ_ERR_INVALID; }
+    if (stats) memset(stats, 0, sizeof *stats);
+    if (n == 0) return DQ_OK;
+    if (!cells || !solution || !nodes || !status) { g_err = "null buffer"; return DQ_ERR_INVALID; }
+    int rc = upload(m);
+    if (rc != DQ_OK) return rc;
+    const size_t bytes = (size_t)n * stride;
+    DQ_CUDA(m->b_cells.reserve(bytes)); DQ_CUDA(m->b_solution.reserve(bytes));
+    DQ_CUDA(m->b_status.reserve(n)); DQ_CUDA(m->b_nodes.reserve(n));
+    DQ_CUDA(cudaMemcpyAsync(m->b_cells.p, cells, bytes, cudaMemcpyHostToDevice, m->stream));
+    rc = run_batch_cells(m, m->b_cells.p, n, stride, opts, m->b_solution.p, m->b_nodes.p, m->b_status.p, stats);
+    if (rc != DQ_OK) return rc;
+    DQ_CUDA(cudaMemcpyAsync(solution, m->b_solution.p, bytes, cudaMemcpyDeviceToHost, m->stream));
+    DQ_CUDA(cudaMemcpyAsync(nodes, m->b_nodes.p, (size_t)n * 8, cudaMemcpyDeviceToHost, m->stream));
+    DQ_CUDA(cudaMemcpyAsync(status, m->b_status.p, (size_t)n, cudaMemcpyDeviceToHost, m->stream));
+    DQ_CUDA(cudaStreamSynchronize(m->stream));
+    if (stats) { stats->h2d_bytes = bytes; stats->d2h_bytes = bytes + (size_t)n * 9; }
+    return DQ_OK;
+}
+
+int dq_solve_batch_graphs(int32_t nv, int32_t k, const int64_t* edge_off, const uint8_t* edges, int64_t n,
+                          const dq_batch_opts* opts, uint8_t* colours, uint64_t* nodes, uint8_t* status,
+                          dq_batch_stats* stats) {
+    if (nv < 1 || nv > kMaxVars || k < 1 || k > kMaxDom || n < 0) { g_err = "bad argument"; return DQ_ERR_INVALID; }
+    if (stats) memset(stats, 0, sizeof *stats);
+    if (n == 0) return DQ_OK;
+    if (!edge_off || !colours || !nodes || !status) { g_err = "null buffer"; return DQ_ERR_INVALID; }
+    const long long total = edge_off[n];
+    for (long long e = 0; e < 2 * total; e++) if (edges[e] >= nv) { g_err = "edge endpoint out of range"; return DQ_ERR_INVALID; }
+    int dev = 0, sms = 0;
+    DQ_CUDA(cudaGetDevice(&dev));
+    DQ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    DevBuf<long long> d_off; DevBuf<uint8_t> d_edges, d_col, d_status; DevBuf<uint32_t> d_ent_off; DevBuf<uint16_t> d_ent;
+    DevBuf<unsigned long long> d_nodes, d_ctrl;
+    auto cleanup = [&]() { d_off.release(); d_edges.release(); d_col.release(); d_status.release(); d_ent_off.release(); d_ent.release(); d_nodes.release(); d_ctrl.release(); };
+    struct Guard { decltype(cleanup)& f; ~Guard() { f(); } } guard{cleanup};
+    DQ_CUDA(d_off.reserve(n + 1)); DQ_CUDA(d_edges.reserve(2 * total)); DQ_CUDA(d_col.reserve((size_t)n * nv));
+    DQ_CUDA(d_status.reserve(n)); DQ_CUDA(d_ent_off.reserve((size_t)n * (nv + 1))); DQ_CUDA(d_ent.reserve(2 * total));
+    DQ_CUDA(d_nodes.reserve(n)); DQ_CUDA(d_ctrl.reserve(8));
+    cudaStream_t s = nullptr;
+    cudaEvent_t e0, e1;
+    DQ_CUDA(cudaEventCreate(&e0)); DQ_CUDA(cudaEventCreate(&e1));
+    DQ_CUDA(cudaMemcpyAsync(d_off.p, edge_off, (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, s));
+    if (total) DQ_CUDA(cudaMemcpyAsync(d_edges.p, edges, 2 * total, cudaMemcpyHostToDevice, s));
+    DQ_CUDA(cudaMemsetAsync(d_ctrl.p, 0, 8 * sizeof(unsigned long long), s));
+    BatchGraphsArgs A;
+    A.nv = nv; A.k = k; A.edge_off = d_off.p; A.edges = d_edges.p; A.n = n; A.ent_off = d_ent_off.p; A.ent = d_ent.p;
+    A.budget = opts ? opts->node_budget : 0; A.cursor = d_ctrl.p; A.colours = d_col.p; A.nodes = d_nodes.p;
+    A.status = d_status.p; A.totals = d_ctrl.p + 1;
+    A.trail = nv * k + 32;
+    const size_t smem = warp_state_bytes(nv, A.trail) * kWarpsPerCta;
+    if (smem > 200 * 1024) { g_err = "instance state exceeds shared memory"; return DQ_ERR_UNSUPPORTED; }
+    int occ = 0;
+    int rc = max_ctas_per_sm(k_batch_graphs, kWarpsPerCta * 32, smem, &occ);
+    if (rc != DQ_OK) return rc;
+    DQ_CUDA(cudaEventRecord(e0, s));
+    k_graphs_build<<<(unsigned)((n + kWarpsPerCta - 1) / kWarpsPerCta), kWarpsPerCta * 32, (size_t)kWarpsPerCta * (nv + 1) * 4, s>>>(A);
+    long long ctas = std::min<long long>((n + kWarpsPerCta - 1) / kWarpsPerCta, (long long)std::max(occ, 1) * sms);
+    k_batch_graphs<<<(unsigned)ctas, kWarpsPerCta * 32, smem, s>>>(A);
+    DQ_CUDA(cudaGetLastError());
+    DQ_CUDA(cudaEventRecord(e1, s));
+    unsigned long long h[8];
+    DQ_CUDA(cudaMemcpyAsync(h, d_ctrl.p, sizeof h, cudaMemcpyDeviceToHost, s));
+    DQ_CUDA(cudaMemcpyAsync(colours, d_col.p, (size_t)n * nv, cudaMemcpyDeviceToHost, s));
+    DQ_CUDA(cudaMemcpyAsync(nodes, d_nodes.p, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
+    DQ_CUDA(cudaMemcpyAsync(status, d_status.p, (size_t)n, cudaMemcpyDeviceToHost, s));
+    DQ_CUDA(cudaStreamSynchronize(s));
+    if (stats) {
+        float ms = 0;
+        DQ_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        stats->n_sat = h[1]; stats->n_unsat = h[2]; stats->n_budget = h[3]; stats->total_nodes = h[4];
+        stats->kernel_ms = ms; stats->kernel_launches = 2;
+        stats->h2d_bytes = (size_t)(n + 1) * 8 + 2 * (size_t)total; stats->d2h_bytes = (size_t)n * (nv + 9);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return DQ_OK;
+}
+
+int dq_measure_int_peak(double* lane_ops_per_s, double* ms_out) {
+    int dev = 0, sms = 0;
+    DQ_CUDA(cudaGetDevice(&dev));
+    DQ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int blocks = sms * 2, threads = 1024, iters = 4096;
+    uint32_t* out = nullptr;
+    DQ_CUDA(cudaMalloc(&out, (size_t)blocks * threads * 4));
+    cudaEvent_t e0, e1;
+    DQ_CUDA(cudaEventCreate(&e0)); DQ_CUDA(cudaEventCreate(&e1));
+    k_int_peak<<<blocks, threads>>>(out, 64);
+    float best = 1e30f;
+    for (int r = 0; r < 5; r++) {
+        DQ_CUDA(cudaEventRecord(e0));
+        k_int_peak<<<blocks, threads>>>(out, iters);
+        DQ_CUDA(cudaEventRecord(e1));
+        DQ_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        DQ_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        best = std::min(best, ms);
+    }
+    DQ_CUDA(cudaGetLastError());
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(out);
+    const double ops = (double)blocks * threads * (double)iters * 16.0 * 8.0;   // one LOP3 per statement (see SASS)
+    if (lane_ops_per_s) *lane_ops_per_s = ops / (best * 1e-3);
+    if (ms_out) *ms_out = best;
+    return DQ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,283 @@
+// dq_compile.cpp — host model compiler: dq_model_desc -> CompiledModel (see dq_model.hpp).
+//
+// Replaces CSP::FinalizeModel + Assignment::Reset (reference dequan.h:484-492, 365-395): the
+// linked-constraint lists and per-constraint virtual AplyArcConsistency calls of the reference
+// become, per ordered variable pair (x -> q), at most a few mask operations.
+#include "dq_model.hpp"
+
+#include <algorithm>
+#include <map>
+#include <set>
+
+namespace dq {
+namespace {
+
+struct PairOp {
+    EntryKind kind;
+    std::vector<uint32_t> m;  // one mask per value index of x
+};
+
+// How assigning x = a filters q through one OpConstraint-style test "y (op) t"
+// (DoCheck, dequan.h:636-669): returns the mask over q's value list.
+uint32_t op_mask(const std::vector<int32_t>& qvals, int op, int64_t t) {
+    uint32_t m = 0;
+    for (size_t j = 0; j < qvals.size(); j++) {
+        int64_t y = qvals[j];
+        bool keep = false;
+        switch (op) {
+            case DQ_OP_EQUAL:    keep = (y == t); break;      // Intersect(t)      (weak, see K_WEQ)
+            case DQ_OP_NOTEQUAL: keep = (y != t); break;      // Exclude(t)
+            case DQ_OP_SUPEQUAL: keep = (y >= t); break;      // ExcludeInf(t)
+            case DQ_OP_SUP:      keep = (y >= t + 1); break;  // ExcludeInf(t+1)
+            case DQ_OP_INFEQUAL: keep = (y < t + 1); break;   // ExcludeSup(t+1)
+            case DQ_OP_INF:      keep = (y < t); break;       // ExcludeSup(t)
+        }
+        if (keep) m |= 1u << j;
+    }
+    return m;
+}
+
+int reverse_op(int op) {  // dequan.h:681-690
+    switch (op) {
+        case DQ_OP_SUPEQUAL: return DQ_OP_INFEQUAL;
+        case DQ_OP_SUP:      return DQ_OP_INF;
+        case DQ_OP_INFEQUAL: return DQ_OP_SUPEQUAL;
+        case DQ_OP_INF:      return DQ_OP_SUP;
+        default:             return op;
+    }
+}
+
+}  // namespace
+
+int compile_model(const dq_model_desc* d, CompiledModel& M, std::string& err) {
+    if (!d || d->n_vars < 0 || d->n_cons < 0) { err = "null or negative-sized descriptor"; return DQ_ERR_INVALID; }
+    const int nv = d->n_vars;
+    if (nv > kMaxVars) { err = "more than 254 variables"; return DQ_ERR_UNSUPPORTED; }
+    M = CompiledModel();
+    M.nv = nv;
+    M.values.resize(nv);
+    M.dom0.resize(nv);
+
+    // ---- domains: expand to iteration-ordered value lists (dequan.h:544-563) ----
+    for (int v = 0; v < nv; v++) {
+        int lo = d->dom_off[v], hi = d->dom_off[v + 1];
+        if (hi < lo) { err = "dom_off not monotone"; return DQ_ERR_INVALID; }
+        std::vector<int32_t>& vals = M.values[v];
+        if (d->dom_type[v] == DQ_DOM_VALUES) {
+            vals.assign(d->dom_vals + lo, d->dom_vals + hi);
+            std::set<int32_t> uniq(vals.begin(), vals.end());
+            if (uniq.size() != vals.size()) { err = "duplicate values in a Values domain (SURVEY Q2) are not supported"; return DQ_ERR_UNSUPPORTED; }
+        } else if (d->dom_type[v] == DQ_DOM_RANGES) {
+            if ((hi - lo) % 2) { err = "odd-length Ranges domain"; return DQ_ERR_INVALID; }
+            int64_t prev_max = INT64_MIN;
+            for (int r = lo; r < hi; r += 2) {
+                int64_t a = d->dom_vals[r], b = d->dom_vals[r + 1];
+                if (a < prev_max) { err = "Ranges domain not ascending/disjoint"; return DQ_ERR_UNSUPPORTED; }
+                prev_max = b > a ? b : a;
+                if (b - a > kMaxDom) { err = "domain larger than 32 values"; return DQ_ERR_UNSUPPORTED; }
+                for (int64_t x = a; x < b; x++) vals.push_back((int32_t)x);
+                if ((int)vals.size() > kMaxDom) { err = "domain larger than 32 values"; return DQ_ERR_UNSUPPORTED; }
+            }
+        } else { err = "bad domain type"; return DQ_ERR_INVALID; }
+        if ((int)vals.size() > kMaxDom) { err = "domain larger than 32 values"; return DQ_ERR_UNSUPPORTED; }
+        M.dom0[v] = vals.size() == 32 ? 0xFFFFFFFFu : ((1u << vals.size()) - 1u);
+        M.kmax = std::max(M.kmax, (int)vals.size());
+    }
+
+    // ---- static order: (initial size asc, id asc), Assignment::Reset dequan.h:384-394 ----
+    M.order.resize(nv);
+    for (int v = 0; v < nv; v++) M.order[v] = v;
+    std::stable_sort(M.order.begin(), M.order.end(), [&](int a, int b) {
+        return M.values[a].size() < M.values[b].size();
+    });
+    M.pos_of.resize(nv);
+    for (int p = 0; p < nv; p++) M.pos_of[M.order[p]] = p;
+    {
+        std::set<int32_t> sz;
+        for (int v = 0; v < nv; v++) sz.insert((int32_t)M.values[v].size());
+        M.distinct_sizes.assign(sz.begin(), sz.end());
+    }
+
+    // ---- link lists in FinalizeModel order (dequan.h:488-491 + each LinkVars) ----
+    struct Con { int kind; const int32_t* data; int n; };
+    std::vector<Con> cons(d->n_cons);
+    std::vector<std::vector<int>> links(nv);
+    for (int c = 0; c < d->n_cons; c++) {
+        cons[c] = {d->con_kind[c], d->con_data + d->con_off[c], d->con_off[c + 1] - d->con_off[c]};
+        const Con& k = cons[c];
+        auto chk = [&](int v) { return v >= 0 && v < nv; };
+        switch (k.kind) {
+            case DQ_CON_OP:      if (k.n != 4) { err = "OP payload"; return DQ_ERR_INVALID; } break;
+            case DQ_CON_EQ:      if (k.n != 2) { err = "EQ payload"; return DQ_ERR_INVALID; } break;
+            case DQ_CON_ORRANGE: if (k.n != 4) { err = "ORRANGE payload"; return DQ_ERR_INVALID; } break;
+            case DQ_CON_TABLE:   if (k.n < 2 || (k.n % 2)) { err = "TABLE payload"; return DQ_ERR_INVALID; } break;
+            case DQ_CON_ALLDIFF: break;
+            default: err = "constraint kind outside the engine's scope (ternary+ constraints are not lowered)"; return DQ_ERR_UNSUPPORTED;
+        }
+        if (k.kind == DQ_CON_ALLDIFF) {
+            std::set<int> seen;
+            for (int i = 0; i < k.n; i++) {
+                if (!chk(k.data[i])) { err = "variable id out of range"; return DQ_ERR_INVALID; }
+                if (!seen.insert(k.data[i]).second) { err = "AllDifferent with a repeated variable"; return DQ_ERR_UNSUPPORTED; }
+                links[k.data[i]].push_back(c);
+            }
+        } else {
+            if (!chk(k.data[0]) || !chk(k.data[1])) { err = "variable id out of range"; return DQ_ERR_INVALID; }
+            if (k.data[0] == k.data[1]) { err = "constraint with v0 == v1"; return DQ_ERR_UNSUPPORTED; }
+            if (k.kind == DQ_CON_OP && (k.data[2] < 0 || k.data[2] > 5)) { err = "bad op"; return DQ_ERR_INVALID; }
+            links[k.data[0]].push_back(c);
+            links[k.data[1]].push_back(c);
+        }
+    }
+
+    // ---- per ordered pair (x -> q): the sequence of filters in x's link order ----
+    M.ent_off.assign(nv + 1, 0);
+    int forced_total = 0;
+    for (int x = 0; x < nv; x++) {
+        const std::vector<int32_t>& xv = M.values[x];
+        const int kx = (int)xv.size();
+        std::vector<int> qorder;                       // neighbours in first-touch order
+        std::map<int, std::vector<PairOp>> ops;
+        auto push = [&](int q, EntryKind kind, std::vector<uint32_t>&& m) {
+            if (!ops.count(q)) qorder.push_back(q);
+            ops[q].push_back(PairOp{kind, std::move(m)});
+        };
+        for (int c : links[x]) {
+            const Con& k = cons[c];
+            if (k.kind == DQ_CON_OP || k.kind == DQ_CON_EQ) {
+                const bool x_is_v0 = (k.data[0] == x);
+                const int q = x_is_v0 ? k.data[1] : k.data[0];
+                int op = k.kind == DQ_CON_EQ ? DQ_OP_EQUAL : k.data[2];
+                const int64_t off = k.kind == DQ_CON_EQ ? 0 : k.data[3];
+                // x==v0 assigned -> q=v1 filtered with reversed op against a-off; x==v1 -> q=v0 with op against a+off
+                if (x_is_v0) op = reverse_op(op);
+                std::vector<uint32_t> m(kx);
+                for (int b = 0; b < kx; b++) {
+                    int64_t t = x_is_v0 ? (int64_t)xv[b] - off : (int64_t)xv[b] + off;
+                    m[b] = op_mask(M.values[q], op, t);
+                }
+                push(q, op == DQ_OP_EQUAL ? K_WEQ : K_AND, std::move(m));
+            } else if (k.kind == DQ_CON_ALLDIFF) {
+                for (int i = 0; i < k.n; i++) {        // AllDifferent::AplyArcConsistency, dequan.h:915-939
+                    int q = k.data[i];
+                    if (q == x) continue;
+                    std::vector<uint32_t> m(kx);
+                    for (int b = 0; b < kx; b++) m[b] = op_mask(M.values[q], DQ_OP_NOTEQUAL, xv[b]);
+                    push(q, K_AND, std::move(m));
+                }
+            } else if (k.kind == DQ_CON_ORRANGE) {     // Evaluate only (dequan.h:844-854); filter compiled out (860-893)
+                const bool x_is_v0 = (k.data[0] == x);
+                const int q = x_is_v0 ? k.data[1] : k.data[0];
+                const int lo = k.data[2], hi = k.data[3];
+                uint32_t q_out = 0;
+                for (size_t j = 0; j < M.values[q].size(); j++)
+                    if (!(M.values[q][j] >= lo && M.values[q][j] < hi)) q_out |= 1u << j;
+                std::vector<uint32_t> m(kx);
+                for (int b = 0; b < kx; b++) m[b] = (xv[b] >= lo && xv[b] < hi) ? 0u : q_out;
+                push(q, K_CHK, std::move(m));
+            } else if (k.kind == DQ_CON_TABLE) {
+                const bool x_is_v0 = (k.data[0] == x);
+                const int q = x_is_v0 ? k.data[1] : k.data[0];
+                std::set<std::pair<int, int>> allowed;
+                for (int i = 2; i + 1 < k.n; i += 2) allowed.insert({k.data[i], k.data[i + 1]});
+                std::vector<uint32_t> m(kx);
+                for (int b = 0; b < kx; b++) {
+                    uint32_t bad = 0;
+                    for (size_t j = 0; j < M.values[q].size(); j++) {
+                        std::pair<int, int> pr = x_is_v0 ? std::make_pair((int)xv[b], (int)M.values[q][j])
+                                                         : std::make_pair((int)M.values[q][j], (int)xv[b]);
+                        if (!allowed.count(pr)) bad |= 1u << j;
+                    }
+                    m[b] = bad;
+                }
+                push(q, K_CHK, std::move(m));
+            }
+        }
+        // normalise each pair: merge adjacent ANDs, gather all CHKs (they commute) at the end
+        std::vector<std::vector<PairOp>> passes;       // passes[p] = p-th op of every pair
+        std::vector<std::vector<int>> pass_q;
+        int multi_pairs = 0;
+        for (int q : qorder) {
+            std::vector<PairOp>& seq = ops[q];
+            std::vector<PairOp> norm;
+            PairOp chk{K_CHK, std::vector<uint32_t>(kx, 0u)};
+            bool have_chk = false;
+            for (PairOp& o : seq) {
+                if (o.kind == K_CHK) { have_chk = true; for (int b = 0; b < kx; b++) chk.m[b] |= o.m[b]; }
+                else if (o.kind == K_AND && !norm.empty() && norm.back().kind == K_AND) { for (int b = 0; b < kx; b++) norm.back().m[b] &= o.m[b]; }
+                else norm.push_back(std::move(o));
+            }
+            if (have_chk) norm.push_back(std::move(chk));
+            // K_AND that is exactly "clear the same bit index" -> K_NE_SAME (no table needed)
+            for (PairOp& o : norm) {
+                if (o.kind != K_AND || M.values[q].size() != (size_t)kx) continue;
+                bool same = true;
+                for (int b = 0; b < kx && same; b++) same = (o.m[b] == (M.dom0[q] & ~(1u << b)));
+                if (same) o.kind = K_NE_SAME;
+            }
+            if (norm.size() > 1) multi_pairs++;
+            for (size_t p = 0; p < norm.size(); p++) {
+                if (passes.size() <= p) { passes.resize(p + 1); pass_q.resize(p + 1); }
+                passes[p].push_back(std::move(norm[p]));
+                pass_q[p].push_back(q);
+            }
+            ops[q].clear();
+            ops[q].resize(norm.size());                // keep the count for flagging below
+        }
+        forced_total += 2 * multi_pairs;
+        for (size_t p = 0; p < passes.size(); p++) {
+            for (size_t i = 0; i < passes[p].size(); i++) {
+                const PairOp& o = passes[p][i];
+                const int q = pass_q[p][i];
+                uint32_t w = (uint32_t)q | ((uint32_t)o.kind << 8);
+                const size_t cnt = ops[q].size();
+                if (cnt > 1) w |= (p == 0) ? (ENT_FORCE_D | ENT_FORCE_F) : (ENT_NOTRAIL_D | ENT_NOTRAIL_F);
+                if (o.kind == K_WEQ || o.kind == K_CHK) M.has_f = true;
+                if (o.kind != K_NE_SAME) {
+                    M.has_table = true;
+                    M.ent_moff.push_back((uint32_t)M.masks.size());
+                    M.masks.insert(M.masks.end(), o.m.begin(), o.m.end());
+                } else M.ent_moff.push_back(0);
+                M.ent.push_back((uint16_t)w);
+            }
+            if (p + 1 < passes.size())                 // next pass must start on a 32-entry boundary
+                while ((M.ent.size() - M.ent_off[x]) % 32) { M.ent.push_back((uint16_t)(ENT_SKIP | 0xFF)); M.ent_moff.push_back(0); }
+        }
+        M.ent_off[x + 1] = (uint32_t)M.ent.size();
+    }
+    if (M.masks.empty()) M.masks.push_back(0);
+
+    int ksum = 0;
+    for (int v = 0; v < nv; v++) ksum += (int)M.values[v].size();
+    M.trail_bound = ksum + (M.has_f ? ksum + nv : 0) + forced_total + 32;
+
+    // ---- model class ----
+    M.model_class = M.has_table ? CLASS_GENERIC : CLASS_NE_SAME;
+    if (M.has_table && !M.has_f && nv >= 1 && nv <= 32) {
+        bool queens = true;
+        const uint32_t full = nv == 32 ? 0xFFFFFFFFu : ((1u << nv) - 1u);
+        for (int v = 0; v < nv && queens; v++) {
+            queens = (int)M.values[v].size() == nv;
+            for (int b = 0; b < nv && queens; b++) queens = M.values[v][b] == b;
+        }
+        for (int x = 0; x < nv && queens; x++) {
+            if ((int)(M.ent_off[x + 1] - M.ent_off[x]) != nv - 1) { queens = false; break; }
+            std::set<int> qs;
+            for (uint32_t e = M.ent_off[x]; e < M.ent_off[x + 1] && queens; e++) {
+                const uint32_t w = M.ent[e];
+                const int q = w & 0xFF, dist = q > x ? q - x : x - q;
+                if (((w >> 8) & 3) != K_AND || (w & 0xFC00) || !qs.insert(q).second) { queens = false; break; }
+                for (int b = 0; b < nv; b++) {
+                    uint32_t rm = 1u << b;
+                    if (b + dist < nv) rm |= 1u << (b + dist);
+                    if (b - dist >= 0) rm |= 1u << (b - dist);
+                    if (M.masks[M.ent_moff[e] + b] != (full & ~rm)) { queens = false; break; }
+                }
+            }
+        }
+        if (queens && nv >= 2) { M.model_class = CLASS_QUEENS; M.queens_n = nv; }
+    }
+    return DQ_OK;
+}
+
+}  // namespace dq

@@ -1,0 +1,376 @@
+// dq_kernels.cuh — kernels around the generic warp engine: frontier (prefix) expansion,
+// the persistent subtree DFS, and the batched-instance kernels.
+#pragma once
+#include "dq_warp_engine.cuh"
+
+namespace dq {
+
+constexpr int kWarpsPerCta = 4;
+constexpr unsigned long long KEY_NONE = 0xFFFFFFFFFFFFFFFFull;
+
+struct TreeModelDev {
+    DevTables T;
+    const uint32_t* __restrict__ dom0;   // [nv] by var id
+    const uint8_t* __restrict__ order;   // [nv]
+    const uint8_t* __restrict__ pos;     // [nv]
+    int trail;                           // trail capacity per warp
+};
+
+__device__ __forceinline__ void load_root_state(const TreeModelDev& M, const WarpState& S, int lane) {
+    for (int v = lane; v < M.T.nv; v += 32) {
+        S.D[v] = __ldg(M.dom0 + v);
+        S.F[v] = 0;
+        S.order[v] = __ldg(M.order + v);
+        S.pos[v] = __ldg(M.pos + v);
+    }
+    __syncwarp();
+}
+
+// Re-apply a prefix (value indices for depths 0..depth-1) to the root state.
+template <bool HAS_F, bool HAS_TABLE>
+__device__ __forceinline__ void replay_prefix(const TreeModelDev& M, const WarpState& S, const uint8_t* __restrict__ prefix,
+                                              int depth, int lane) {
+    load_root_state(M, S, lane);
+    int top = 0;
+    for (int i = 0; i < depth; i++) {
+        const int b = __ldg(prefix + i);
+        if (lane == 0) S.val[i] = (uint8_t)b;
+        fc_apply<HAS_F, HAS_TABLE>(M.T, S, S.order[i], b, i, top, lane);
+        top = 0;                                      // nothing above the split depth is ever undone
+    }
+    __syncwarp();
+}
+
+// ---- frontier expansion, one level: warp per parent state --------------------------------------
+// dmask[i] = current domain of the next variable (each bit is one node, dequan.h:416-423)
+// surv[i]  = values whose validation and forward check succeed (children states)
+template <bool HAS_F, bool HAS_TABLE>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+k_expand(TreeModelDev M, const uint8_t* __restrict__ prefixes, int depth, int n_states,
+         uint32_t* __restrict__ dmask, uint32_t* __restrict__ surv) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int i = blockIdx.x * kWarpsPerCta + wib;
+    if (i >= n_states) return;
+    WarpState S = carve_warp_state(smem + (size_t)wib * warp_state_bytes(M.T.nv, M.trail), M.T.nv, M.trail);
+    replay_prefix<HAS_F, HAS_TABLE>(M, S, prefixes + (size_t)i * depth, depth, lane);
+    const int x = S.order[depth];
+    const uint32_t dm = S.D[x];
+    uint32_t c = HAS_F ? (dm & ~S.F[x]) : dm, sv = 0;
+    while (c) {
+        const int b = __ffs(c) - 1;
+        c &= c - 1;
+        int top = 0;
+        const bool wiped = fc_apply<HAS_F, HAS_TABLE>(M.T, S, x, b, depth, top, lane);
+        trail_undo<HAS_F>(S, 0, top, lane);
+        if (!wiped) sv |= 1u << b;
+    }
+    if (lane == 0) { dmask[i] = dm; surv[i] = sv; }
+}
+
+// Single-CTA exclusive scans of popc(surv) -> child_off and popc(dmask) -> node_off; totals in tot[0..1].
+__global__ void __launch_bounds__(1024)
+k_scan_level(const uint32_t* __restrict__ dmask, const uint32_t* __restrict__ surv, int n,
+             uint32_t* __restrict__ child_off, unsigned long long* __restrict__ node_off,
+             unsigned long long* __restrict__ tot) {
+    __shared__ unsigned long long wsum_c[32], wsum_n[32];
+    __shared__ unsigned long long carry_c, carry_n;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) { carry_c = 0; carry_n = 0; }
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + threadIdx.x;
+        unsigned long long c = i < n ? __popc(surv[i]) : 0, nd = i < n ? __popc(dmask[i]) : 0;
+        unsigned long long ic = c, in = nd;
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned long long tc = __shfl_up_sync(FULL, ic, o), tn = __shfl_up_sync(FULL, in, o);
+            if (lane >= o) { ic += tc; in += tn; }
+        }
+        if (lane == 31) { wsum_c[w] = ic; wsum_n[w] = in; }
+        __syncthreads();
+        if (w == 0) {
+            unsigned long long sc = wsum_c[lane], sn = wsum_n[lane];
+            for (int o = 1; o < 32; o <<= 1) {
+                unsigned long long tc = __shfl_up_sync(FULL, sc, o), tn = __shfl_up_sync(FULL, sn, o);
+                if (lane >= o) { sc += tc; sn += tn; }
+            }
+            wsum_c[lane] = sc; wsum_n[lane] = sn;
+        }
+        __syncthreads();
+        const unsigned long long pc = carry_c + (w ? wsum_c[w - 1] : 0), pn = carry_n + (w ? wsum_n[w - 1] : 0);
+        if (i < n) { child_off[i] = (uint32_t)(pc + ic - c); node_off[i] = pn + in - nd; }
+        __syncthreads();
+        if (threadIdx.x == 1023) { carry_c = pc + ic; carry_n = pn + in; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { tot[0] = carry_c; tot[1] = carry_n; }
+}
+
+// Children prefixes in DFS (lexicographic) order: thread per parent.
+__global__ void k_write_children(const uint8_t* __restrict__ prefixes, int depth, int n_states,
+                                 const uint32_t* __restrict__ surv, const uint32_t* __restrict__ child_off,
+                                 uint8_t* __restrict__ out, uint32_t* __restrict__ parent_of) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_states) return;
+    uint32_t sv = surv[i];
+    size_t o = child_off[i];
+    while (sv) {
+        const int b = __ffs(sv) - 1;
+        sv &= sv - 1;
+        uint8_t* dst = out + o * (size_t)(depth + 1);
+        for (int j = 0; j < depth; j++) dst[j] = prefixes[(size_t)i * depth + j];
+        dst[depth] = (uint8_t)b;
+        parent_of[o] = (uint32_t)i;
+        ++o;
+    }
+}
+
+// ---- persistent subtree DFS: warps pull prefix indices from an atomic cursor -------------------
+struct TreeDfsArgs {
+    const uint8_t* prefixes;            // [n_prefix][depth]
+    int depth;
+    unsigned long long n_prefix;
+    int part_rank, part_count;
+    int count_all;
+    unsigned long long* cursor;         // work counter
+    unsigned long long* totals;         // [0]=solutions [1]=nodes   (COUNT_ALL)
+    unsigned long long* best_key;       // lowest prefix index holding a solution
+    unsigned long long* sub_nodes;      // [n_prefix] nodes per subtree (this partition's)
+    unsigned long long* sol_key;        // [n_warps] key of the solution each warp recorded
+    uint8_t* sol;                       // [n_warps][nv] value index per var id
+};
+
+struct RecordFirst {
+    const TreeDfsArgs& A;
+    unsigned long long key;
+    int gw, nv, lane;
+    __device__ void operator()(const WarpState& S) const {
+        unsigned long long old = 0;
+        if (lane == 0) old = atomicMin(A.best_key, key);
+        old = __shfl_sync(FULL, old, 0);
+        if (key < old) {
+            for (int i = lane; i < nv; i += 32) A.sol[(size_t)gw * nv + S.order[i]] = S.val[i];
+            if (lane == 0) A.sol_key[gw] = key;
+        }
+    }
+};
+
+template <bool HAS_F, bool HAS_TABLE>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+k_tree_dfs(TreeModelDev M, TreeDfsArgs A) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int gw = blockIdx.x * kWarpsPerCta + wib;
+    const int nv = M.T.nv;
+    WarpState S = carve_warp_state(smem + (size_t)wib * warp_state_bytes(nv, M.trail), nv, M.trail);
+    unsigned long long acc_nodes = 0, acc_sols = 0;
+    for (;;) {
+        unsigned long long j = 0;
+        if (lane == 0) j = atomicAdd(A.cursor, 1ull);
+        j = __shfl_sync(FULL, j, 0);
+        const unsigned long long idx = j * (unsigned long long)A.part_count + (unsigned long long)A.part_rank;
+        if (idx >= A.n_prefix) break;
+        if (!A.count_all && *(volatile unsigned long long*)A.best_key < idx) break;   // later prefixes cannot win
+        replay_prefix<HAS_F, HAS_TABLE>(M, S, A.prefixes + idx * (size_t)A.depth, A.depth, lane);
+        RecordFirst rec{A, idx, gw, nv, lane};
+        DfsResult R = warp_dfs<HAS_F, HAS_TABLE>(M.T, S, A.depth, A.count_all != 0, 0ull,
+                                                 A.count_all ? nullptr : A.best_key, idx, lane, rec);
+        if (R.outcome == 3) continue;                                                 // overtaken by an earlier prefix
+        if (lane == 0) A.sub_nodes[idx] = R.nodes;
+        if (A.count_all) { acc_nodes += R.nodes; acc_sols += R.sols; }
+        else if (R.have_first) rec(S);
+    }
+    if (A.count_all && lane == 0) {
+        atomicAdd(A.totals + 0, acc_sols);
+        atomicAdd(A.totals + 1, acc_nodes);
+    }
+}
+
+// ---- batch: one template graph, per-instance initial domains ("cells") -------------------------
+struct BatchCellsArgs {
+    const uint8_t* cells;       // [n][stride]
+    long long n;
+    int stride;
+    const uint8_t* cell_lut;    // [nv][256] byte -> value index (0xFF = not in the template domain)
+    const int32_t* values;      // [nv][32] value index -> value
+    const int32_t* sizes;       // distinct domain sizes after overrides, ascending
+    int n_sizes;
+    unsigned long long budget;
+    unsigned long long* cursor;
+    uint8_t* solution;          // [n][stride]
+    unsigned long long* nodes;  // [n]
+    uint8_t* status;            // [n]
+    unsigned long long* totals; // [0]=sat [1]=unsat [2]=budget [3]=nodes
+};
+
+struct NoFirst { __device__ void operator()(const WarpState&) const {} };
+
+template <bool HAS_F, bool HAS_TABLE>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+k_batch_cells(TreeModelDev M, BatchCellsArgs A) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int nv = M.T.nv;
+    const uint32_t lt = (1u << lane) - 1u;
+    WarpState S = carve_warp_state(smem + (size_t)wib * warp_state_bytes(nv, M.trail), nv, M.trail);
+    unsigned long long t_sat = 0, t_unsat = 0, t_budget = 0, t_nodes = 0;
+    for (;;) {
+        long long i = 0;
+        if (lane == 0) i = (long long)atomicAdd(A.cursor, 1ull);
+        i = __shfl_sync(FULL, i, 0);
+        if (i >= A.n) break;
+        const uint8_t* cell = A.cells + (size_t)i * A.stride;
+        // initial domains: template domain, or the singleton of the given (AddFixedVar, dequan.h:467-471)
+        bool bad = false;
+        for (int v = lane; v < nv; v += 32) {
+            const uint32_t c = cell[v];
+            uint32_t dm = __ldg(M.dom0 + v);
+            if (c) {
+                const uint32_t bi = __ldg(A.cell_lut + v * 256 + c);
+                if (bi == 0xFF) bad = true; else dm = 1u << bi;
+            }
+            S.D[v] = dm;
+            S.F[v] = 0;
+        }
+        bad = __any_sync(FULL, bad);
+        __syncwarp();
+        // static order for THIS instance: (domain size asc, id asc) — Assignment::Reset, dequan.h:384-394
+        int base = 0;
+        for (int s = 0; s < A.n_sizes; s++) {
+            const int sz = __ldg(A.sizes + s);
+            for (int v0 = 0; v0 < nv; v0 += 32) {
+                const int v = v0 + lane;
+                const bool hit = v < nv && __popc(S.D[v]) == sz;
+                const uint32_t m = __ballot_sync(FULL, hit);
+                if (hit) { const int p = base + __popc(m & lt); S.order[p] = (uint8_t)v; S.pos[v] = (uint8_t)p; }
+                base += __popc(m);
+            }
+        }
+        __syncwarp();
+        DfsResult R;
+        if (bad) { R.nodes = 0; R.sols = 0; R.outcome = 0; R.have_first = false; }
+        else R = warp_dfs<HAS_F, HAS_TABLE>(M.T, S, 0, false, A.budget, nullptr, 0ull, lane, NoFirst());
+        uint8_t* out = A.solution + (size_t)i * A.stride;
+        for (int v = lane; v < nv; v += 32)
+            out[v] = R.outcome == 1 ? (uint8_t)__ldg(A.values + v * 32 + S.val[S.pos[v]]) : (uint8_t)0;
+        if (lane == 0) { A.nodes[i] = R.nodes; A.status[i] = bad ? (uint8_t)3 : (uint8_t)R.outcome; }
+        t_nodes += R.nodes;
+        t_sat += R.outcome == 1; t_unsat += R.outcome == 0; t_budget += R.outcome == 2;
+        __syncwarp();
+    }
+    if (lane == 0) {
+        atomicAdd(A.totals + 0, t_sat); atomicAdd(A.totals + 1, t_unsat);
+        atomicAdd(A.totals + 2, t_budget); atomicAdd(A.totals + 3, t_nodes);
+    }
+}
+
+// ---- batch: one graph per instance (k-colouring) ------------------------------------------------
+// Pass 1 builds each instance's entry table in HBM (CSR adjacency in var-id space, both directions);
+// pass 2 runs the generic engine with per-instance tables.
+struct BatchGraphsArgs {
+    int nv, k;
+    const long long* edge_off;  // [n+1]
+    const uint8_t* edges;       // [total][2]
+    long long n;
+    uint32_t* ent_off;          // [n][nv+1]
+    uint16_t* ent;              // [2*total]
+    unsigned long long budget;
+    unsigned long long* cursor;
+    uint8_t* colours;           // [n][nv]
+    unsigned long long* nodes;
+    uint8_t* status;
+    unsigned long long* totals;
+    int trail;
+};
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+k_graphs_build(BatchGraphsArgs A) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const long long i = (long long)blockIdx.x * kWarpsPerCta + wib;
+    if (i >= A.n) return;
+    uint32_t* deg = (uint32_t*)smem + (size_t)wib * (A.nv + 1);
+    const long long e0 = A.edge_off[i], e1 = A.edge_off[i + 1];
+    for (int v = lane; v <= A.nv; v += 32) deg[v] = 0;
+    __syncwarp();
+    for (long long e = e0 + lane; e < e1; e += 32) {
+        atomicAdd(&deg[A.edges[2 * e]], 1u);
+        atomicAdd(&deg[A.edges[2 * e + 1]], 1u);
+    }
+    __syncwarp();
+    // exclusive scan of deg[0..nv) by the warp, 32 at a time
+    uint32_t carry = 0;
+    uint32_t* off = A.ent_off + (size_t)i * (A.nv + 1);
+    for (int v0 = 0; v0 < A.nv; v0 += 32) {
+        const int v = v0 + lane;
+        const uint32_t dv = v < A.nv ? deg[v] : 0;
+        uint32_t inc = dv;
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += t; }
+        if (v < A.nv) { off[v] = carry + inc - dv; deg[v] = carry + inc - dv; }
+        carry += __shfl_sync(FULL, inc, 31);
+    }
+    if (lane == 0) off[A.nv] = carry;
+    __syncwarp();
+    uint16_t* ent = A.ent + 2 * e0;
+    // fill in edge order so that each adjacency list is deterministic: lane 0 walks the edges
+    // (a few hundred per instance; this kernel is <1% of the solve)
+    if (lane == 0)
+        for (long long e = e0; e < e1; e++) {
+            const int u = A.edges[2 * e], v = A.edges[2 * e + 1];
+            ent[deg[u]++] = (uint16_t)(v | (D_K_NE_SAME << 8));
+            ent[deg[v]++] = (uint16_t)(u | (D_K_NE_SAME << 8));
+        }
+}
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+k_batch_graphs(BatchGraphsArgs A) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int nv = A.nv;
+    WarpState S = carve_warp_state(smem + (size_t)wib * warp_state_bytes(nv, A.trail), nv, A.trail);
+    const uint32_t full = A.k >= 32 ? FULL : ((1u << A.k) - 1u);
+    unsigned long long t_sat = 0, t_unsat = 0, t_budget = 0, t_nodes = 0;
+    for (;;) {
+        long long i = 0;
+        if (lane == 0) i = (long long)atomicAdd(A.cursor, 1ull);
+        i = __shfl_sync(FULL, i, 0);
+        if (i >= A.n) break;
+        DevTables T;
+        T.nv = nv;
+        T.ent_off = A.ent_off + (size_t)i * (nv + 1);
+        T.ent = A.ent + 2 * A.edge_off[i];
+        T.ent_moff = nullptr;
+        T.masks = nullptr;
+        for (int v = lane; v < nv; v += 32) { S.D[v] = full; S.F[v] = 0; S.order[v] = (uint8_t)v; S.pos[v] = (uint8_t)v; }
+        __syncwarp();
+        DfsResult R = warp_dfs<false, false>(T, S, 0, false, A.budget, nullptr, 0ull, lane, NoFirst());
+        uint8_t* out = A.colours + (size_t)i * nv;
+        for (int v = lane; v < nv; v += 32) out[v] = R.outcome == 1 ? S.val[v] : (uint8_t)0xFF;
+        if (lane == 0) { A.nodes[i] = R.nodes; A.status[i] = (uint8_t)R.outcome; }
+        t_nodes += R.nodes;
+        t_sat += R.outcome == 1; t_unsat += R.outcome == 0; t_budget += R.outcome == 2;
+        __syncwarp();
+    }
+    if (lane == 0) {
+        atomicAdd(A.totals + 0, t_sat); atomicAdd(A.totals + 1, t_unsat);
+        atomicAdd(A.totals + 2, t_budget); atomicAdd(A.totals + 3, t_nodes);
+    }
+}
+
+// ---- integer-pipe peak: dependent-free LOP3 chains, 8 independent accumulators per lane -----------
+__global__ void __launch_bounds__(1024) k_int_peak(uint32_t* out, int iters) {
+    uint32_t a0 = threadIdx.x, a1 = a0 * 3 + 1, a2 = a0 * 5 + 2, a3 = a0 * 7 + 3, a4 = a0 * 11 + 4, a5 = a0 * 13 + 5,
+             a6 = a0 * 17 + 6, a7 = a0 * 19 + 7;
+    const uint32_t k0 = blockIdx.x * 2654435761u + 1, k1 = ~k0;
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+            a0 = (a0 & k0) ^ a1; a1 = (a1 | k1) ^ a2; a2 = (a2 & k0) ^ a3; a3 = (a3 | k1) ^ a4;
+            a4 = (a4 & k0) ^ a5; a5 = (a5 | k1) ^ a6; a6 = (a6 & k0) ^ a7; a7 = (a7 | k1) ^ a0;
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
+}
+
+}  // namespace dq

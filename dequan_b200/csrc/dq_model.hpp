@@ -1,0 +1,68 @@
+// dq_model.hpp — host-side compiled model ("flat constraint/variable table").
+//
+// dq_compile() lowers a dq_model_desc (the flattened form of dequan::CSP, reference
+// dequan.h:328-355) into var-id-space tables the CUDA engines walk:
+//   * value lists  : per variable, the domain in the reference's ITERATION order
+//                    (Values: list order, Ranges: ascending — dequan.h:544-563); bit b of a
+//                    domain word stands for values[v][b].
+//   * static order : Assignment::Reset's sort (dequan.h:376-394).
+//   * arc entries  : per variable x, what assigning x=values[x][b] does to each neighbour q,
+//                    i.e. the composition of every linked constraint's AplyArcConsistency
+//                    (dequan.h:631-694, 710-743, 915-939) restricted to the pair (x,q), in link
+//                    order, as bit masks (see EntryKind).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+#include "dequan_b200.h"
+
+namespace dq {
+
+constexpr int kMaxVars = 254;      // q fits 8 bits, 0xFF reserved
+constexpr int kMaxDom = 32;        // one 32-bit word per domain
+
+// What one (x -> q) entry does to q's state (D = domain bits, F = "fails validation" bits):
+enum EntryKind : uint32_t {
+    K_NE_SAME = 0,   // D &= ~(1<<b)            NotEqual,0 / AllDifferent between identical value lists
+    K_AND     = 1,   // D &= mask[b]            any composition of Exclude/ExcludeInf/ExcludeSup
+    K_WEQ     = 2,   // if (D & mask[b]) D &= mask[b]; else F = ~0   Domain::Intersect(val) is a no-op when
+                     //                          val is absent (dequan.h:957-984) and Evaluate fails later
+    K_CHK     = 3    // F |= mask[b]            check-only constraints (OrRange, user tables): values of q
+                     //                          that ValidateVarConstraints (dequan.h:573-587) will reject
+};
+// entry word (uint16): q | kind<<8 | flags
+constexpr uint32_t ENT_FORCE_D   = 1u << 10;  // trail D[q] unconditionally (first of several entries on q)
+constexpr uint32_t ENT_FORCE_F   = 1u << 11;
+constexpr uint32_t ENT_NOTRAIL_D = 1u << 12;  // later entry on the same q: the first one already trailed it
+constexpr uint32_t ENT_NOTRAIL_F = 1u << 13;
+constexpr uint32_t ENT_SKIP      = 1u << 14;  // padding so that same-q entries land in different 32-lane passes
+
+enum ModelClass : int32_t {
+    CLASS_GENERIC = 0,     // anything the entry table can express
+    CLASS_NE_SAME = 1,     // only K_NE_SAME entries (Sudoku, graph colouring): no mask table needed
+    CLASS_QUEENS  = 2      // N-Queens structure: dense NotEqual with offsets {0, +-(j-i)} on [0,N)
+};
+
+struct CompiledModel {
+    int nv = 0;
+    int kmax = 0;                              // largest domain size
+    std::vector<std::vector<int32_t>> values;  // [nv][k_v]
+    std::vector<uint32_t> dom0;                // [nv] initial domain bits
+    std::vector<int32_t> order;                // [nv] position -> var id (Reset order)
+    std::vector<int32_t> pos_of;               // [nv] var id -> position
+    std::vector<uint32_t> ent_off;             // [nv+1]
+    std::vector<uint16_t> ent;                 // [n_ent]
+    std::vector<uint32_t> ent_moff;            // [n_ent] index into masks (kinds != K_NE_SAME)
+    std::vector<uint32_t> masks;               // mask tables, kmax words per entry that needs one
+    bool has_f = false;                        // any K_WEQ / K_CHK entry
+    bool has_table = false;                    // any entry other than K_NE_SAME
+    int trail_bound = 0;                       // max live trail entries along one DFS path
+    int model_class = CLASS_GENERIC;
+    int queens_n = 0;
+    std::vector<int32_t> distinct_sizes;       // sorted distinct initial domain sizes (batch re-ordering)
+};
+
+// Returns DQ_OK or a negative dq_status; on failure `err` says why.
+int compile_model(const dq_model_desc* desc, CompiledModel& out, std::string& err);
+
+}  // namespace dq

@@ -1,0 +1,216 @@
+// dq_warp_engine.cuh — generic warp-cooperative forward-checking DFS (sm_100a).
+//
+// One warp owns one search tree (a prefix subtree of a single model, or one instance of a
+// batch).  It replaces, for that tree, the reference's recursive
+//   CSP::ForwardCheckingStep (dequan.h:494-571)  -> explicit stack: cand[]/mark[]/val[] per depth
+//   OpConstraint/AllDifferent/Equality::AplyArcConsistency (631-694, 915-939, 710-743)
+//                                                -> fc_apply(): each lane filters ONE neighbour's
+//                                                   domain word with AND/ANDNOT masks; wipe-out is a
+//                                                   warp vote
+//   Domain::Exclude/Intersect/ExcludeInf/Sup (957-1172) -> bit masks on a 32-bit domain word
+//   EnsureSavedDomain / RestoreSavedDomainStep (431-452) -> warp-appended trail in shared memory
+//   ValidateVarConstraints (573-587)             -> the F ("fails validation") word per variable
+//
+// A node is one AssignVar call (dequan.h:416-423): every value of the current domain of the
+// next variable, including values whose validation or forward check then fails.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace dq {
+
+// entry word layout — keep in sync with dq_model.hpp
+constexpr uint32_t D_K_NE_SAME = 0, D_K_AND = 1, D_K_WEQ = 2, D_K_CHK = 3;
+constexpr uint32_t D_FORCE_D = 1u << 10, D_FORCE_F = 1u << 11, D_NOTRAIL_D = 1u << 12, D_NOTRAIL_F = 1u << 13,
+                   D_SKIP = 1u << 14;
+constexpr uint32_t FULL = 0xFFFFFFFFu;
+constexpr uint32_t TRAIL_F = 0x100;   // trail entry refers to F[q], not D[q]
+
+// Read-only model tables (HBM, read through L1 with ld.global.nc)
+struct DevTables {
+    int nv;
+    const uint32_t* __restrict__ ent_off;   // [nv+1]
+    const uint16_t* __restrict__ ent;       // [n_ent]
+    const uint32_t* __restrict__ ent_moff;  // [n_ent]
+    const uint32_t* __restrict__ masks;
+};
+
+// Per-warp mutable state, all in shared memory
+struct WarpState {
+    uint32_t* D;      // [nv] current domain bits            (Assignment::current_domains)
+    uint32_t* F;      // [nv] values that will fail Evaluate (only if HAS_F)
+    uint32_t* cand;   // [nv] untried values per depth
+    uint32_t* told;   // [trail] saved words                 (Assignment::saved_domains)
+    uint16_t* tq;     // [trail] which word
+    uint16_t* mark;   // [nv] trail height per depth
+    uint8_t* val;     // [nv] chosen value index per depth   (Assignment::inst_vars)
+    uint8_t* order;   // [nv] depth -> var                   (Assignment::assign_order)
+    uint8_t* pos;     // [nv] var -> depth
+};
+
+__host__ __device__ inline size_t warp_state_bytes(int nv, int trail) {
+    size_t nvp = (size_t)((nv + 3) & ~3);
+    size_t tp = (size_t)((trail + 1) & ~1);
+    return nvp * 4 * 3 + tp * 4 + tp * 2 + nvp * 2 + nvp * 3;
+}
+
+__device__ inline WarpState carve_warp_state(unsigned char* base, int nv, int trail) {
+    size_t nvp = (size_t)((nv + 3) & ~3);
+    size_t tp = (size_t)((trail + 1) & ~1);
+    WarpState s;
+    s.D = (uint32_t*)base;           base += nvp * 4;
+    s.F = (uint32_t*)base;           base += nvp * 4;
+    s.cand = (uint32_t*)base;        base += nvp * 4;
+    s.told = (uint32_t*)base;        base += tp * 4;
+    s.tq = (uint16_t*)base;          base += tp * 2;
+    s.mark = (uint16_t*)base;        base += nvp * 2;
+    s.val = base;                    base += nvp;
+    s.order = base;                  base += nvp;
+    s.pos = base;
+    return s;
+}
+
+struct DfsResult {
+    unsigned long long nodes;
+    unsigned long long sols;
+    int outcome;        // dq_outcome
+    bool have_first;    // val[0..nv) holds a solution (value indices by depth)
+};
+
+// Undo the trail down to `mk` (RestoreSavedDomainStep, dequan.h:431-440).
+template <bool HAS_F>
+__device__ __forceinline__ void trail_undo(const WarpState& S, int mk, int& top, int lane) {
+    for (int i = mk + lane; i < top; i += 32) {
+        uint32_t t = S.tq[i];
+        if (HAS_F && (t & TRAIL_F)) S.F[t & 0xFF] = S.told[i];
+        else S.D[t] = S.told[i];
+    }
+    top = mk;
+    __syncwarp();
+}
+
+// Forward-check the assignment x = value index b made at depth d.  Returns true on a domain
+// wipe-out of some unassigned neighbour.  Domain changes are trailed above `top`.
+template <bool HAS_F, bool HAS_TABLE>
+__device__ __forceinline__ bool fc_apply(const DevTables& T, const WarpState& S, int x, int b, int d, int& top, int lane) {
+    const int e0 = (int)__ldg(T.ent_off + x), e1 = (int)__ldg(T.ent_off + x + 1);
+    const uint32_t lt = (1u << lane) - 1u;
+    bool wiped = false;
+    for (int base = e0; base < e1; base += 32) {
+        const int e = base + lane;
+        uint32_t w = e < e1 ? (uint32_t)__ldg(T.ent + e) : D_SKIP;
+        const int q = w & 0xFF;
+        bool act = !(w & D_SKIP);
+        if (act) act = S.pos[q] > d;                      // only unassigned neighbours are filtered
+        uint32_t oldD = 0, newD = 0, oldF = 0, newF = 0;
+        if (act) {
+            oldD = S.D[q];
+            newD = oldD;
+            if (HAS_F) { oldF = S.F[q]; newF = oldF; }
+            const uint32_t kind = (w >> 8) & 3;
+            if (!HAS_TABLE || kind == D_K_NE_SAME) newD = oldD & ~(1u << b);
+            else {
+                const uint32_t m = __ldg(T.masks + __ldg(T.ent_moff + e) + b);
+                if (kind == D_K_AND) newD = oldD & m;
+                else if (HAS_F) {
+                    if (kind == D_K_WEQ) { if (oldD & m) newD = oldD & m; else newF = FULL; }
+                    else newF = oldF | m;
+                }
+            }
+        }
+        const bool tD = act && (newD != oldD || (w & D_FORCE_D)) && !(w & D_NOTRAIL_D);
+        const uint32_t mD = __ballot_sync(FULL, tD);
+        if (tD) { const int i = top + __popc(mD & lt); S.tq[i] = (uint16_t)q; S.told[i] = oldD; }
+        top += __popc(mD);
+        if (act && newD != oldD) S.D[q] = newD;
+        if (HAS_F) {
+            const bool tF = act && (newF != oldF || (w & D_FORCE_F)) && !(w & D_NOTRAIL_F);
+            const uint32_t mF = __ballot_sync(FULL, tF);
+            if (tF) { const int i = top + __popc(mF & lt); S.tq[i] = (uint16_t)(q | TRAIL_F); S.told[i] = oldF; }
+            top += __popc(mF);
+            if (act && newF != oldF) S.F[q] = newF;
+        }
+        wiped |= act && newD == 0;
+        __syncwarp();
+    }
+    return __any_sync(FULL, wiped);
+}
+
+// Explicit-stack DFS from depth d0 (domains already reflect the d0 assignments above it).
+//   count_all : walk the whole subtree (solutions + nodes); else stop at the DFS-first solution.
+//   budget    : stop once more than `budget` nodes have been counted (0 = none), outcome DQ_BUDGET.
+//   abort_key / my_key : FIRST-mode prefix search — give up when another warp has recorded a solution
+//                in an earlier prefix (abort_key may be null).
+template <bool HAS_F, bool HAS_TABLE, class OnFirst>
+__device__ DfsResult warp_dfs(const DevTables& T, const WarpState& S, int d0, bool count_all,
+                              unsigned long long budget, const unsigned long long* abort_key,
+                              unsigned long long my_key, int lane, OnFirst on_first) {
+    const int nv = T.nv;
+    DfsResult R;
+    R.nodes = 0; R.sols = 0; R.outcome = 0; R.have_first = false;
+    if (d0 >= nv) { R.sols = 1; R.outcome = 1; R.have_first = true; return R; }   // IsComplete, dequan.h:496-499
+    int top = 0, d = d0;
+    int x = S.order[d];
+    uint32_t c = S.D[x];
+    unsigned poll = 0;
+    for (;;) {
+        if (c == 0) {                                     // every value tried: return false (dequan.h:569-570)
+            if (d == d0) break;
+            --d;
+            x = S.order[d];
+            trail_undo<HAS_F>(S, S.mark[d], top, lane);
+            c = S.cand[d];
+            continue;
+        }
+        if (abort_key && ((++poll & 63u) == 0) && *(volatile const unsigned long long*)abort_key < my_key) { R.outcome = 3; break; }
+        if (d == nv - 1) {
+            // last variable: each remaining value is a node; valid ones are solutions, no filtering left to do
+            const uint32_t valid = HAS_F ? (c & ~S.F[x]) : c;
+            if (count_all) {
+                R.nodes += __popc(c);
+                R.sols += __popc(valid);
+                if (valid && !R.have_first) {
+                    // first solution of this tree: val[] is the assignment right now (count_all keeps searching)
+                    R.have_first = true;
+                    if (lane == 0) S.val[d] = (uint8_t)(__ffs(valid) - 1);
+                    __syncwarp();
+                    on_first(S);
+                }
+                c = 0;
+                continue;
+            }
+            if (valid) {
+                const int b = __ffs(valid) - 1;
+                unsigned long long n = __popc(c & ((2u << b) - 1u));
+                if (budget && R.nodes + n > budget) {
+                    R.nodes = budget + 1; R.outcome = 2; break;
+                }
+                R.nodes += n;
+                if (lane == 0) S.val[d] = (uint8_t)b;
+                __syncwarp();
+                R.sols = 1; R.outcome = 1; R.have_first = true;
+                break;
+            }
+            if (budget && R.nodes + __popc(c) > budget) { R.nodes = budget + 1; R.outcome = 2; break; }
+            R.nodes += __popc(c);
+            c = 0;
+            continue;
+        }
+        const int b = __ffs(c) - 1;
+        c &= c - 1;
+        ++R.nodes;                                        // AssignVar, dequan.h:416-423
+        if (budget && R.nodes > budget) { R.outcome = 2; break; }
+        if (HAS_F && ((S.F[x] >> b) & 1u)) continue;      // ValidateVarConstraints fails, dequan.h:535-538
+        const int mk = top;
+        if (fc_apply<HAS_F, HAS_TABLE>(T, S, x, b, d, top, lane)) { trail_undo<HAS_F>(S, mk, top, lane); continue; }
+        if (lane == 0) { S.mark[d] = (uint16_t)mk; S.cand[d] = c; S.val[d] = (uint8_t)b; }
+        ++d;
+        __syncwarp();
+        x = S.order[d];
+        c = S.D[x];
+    }
+    if (count_all) R.outcome = R.sols ? 1 : 0;
+    return R;
+}
+
+}  // namespace dq

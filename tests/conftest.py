@@ -1,0 +1,30 @@
+import json
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def golden():
+    with open(os.path.join(ROOT, "tests", "golden", "reference.json")) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="session")
+def product_lib():
+    """The CUDA library must exist (built by __graft_entry__.build()); building needs only nvcc."""
+    from dequan_b200 import api
+    if not os.path.exists(api.LIB_PATH):
+        import __graft_entry__ as g
+        g.build()
+    return api.lib()

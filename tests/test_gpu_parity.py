@@ -1,0 +1,235 @@
+"""GPU: the CUDA engines, through the C ABI, against the CPU oracle and the committed fixtures
+captured from the unmodified reference.  Bit-exact: status, solution count, node count
+(Assignment::AssignVar calls, dequan.h:416-423) and DFS-first solution."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from dequan_b200 import api
+from dequan_b200 import generators as G
+from dequan_b200.model import (CSP, REFERENCE_SUDOKU, Op, OpConstraint, colouring, nqueens, sudoku, sudoku_template)
+from randmodels import model_suite, random_model
+
+pytestmark = pytest.mark.gpu
+
+ENGINES = ["warp"]
+
+
+def _cmp_tree(got, want, what):
+    assert (got.status, got.solutions, got.nodes, got.first) == (want.status, want.solutions, want.nodes, want.first), (what, got, want)
+
+
+def test_device_is_blackwell(product_lib):
+    info = api.device_info()
+    assert info["cc"] >= 100, info
+
+
+def test_reference_scenarios(golden, product_lib):
+    """The three scenarios of /root/reference/test/main-test.cpp plus the boxed variants."""
+    csp = CSP()
+    v = [csp.AddIntVar(0, 10), csp.AddIntVar(0, 10), csp.AddFixedVar(6), csp.AddFixedVar(5)]
+    csp.AddConstraint(OpConstraint(v[0], v[2], Op.Inf, 0))
+    csp.AddConstraint(OpConstraint(v[0], v[3], Op.SupEqual, 0))
+    csp.AddConstraint(OpConstraint(v[1], v[2], Op.InfEqual, 0))
+    csp.AddConstraint(OpConstraint(v[1], v[3], Op.Sup, 0))
+    cases = {
+        "OpInequalityTest": csp,
+        "NQueensTest8": nqueens(8),
+        "SudokuTest_rows_cols_alldiff": sudoku(REFERENCE_SUDOKU, boxes=False, alldiff=True),
+        "Sudoku_rows_cols_binary": sudoku(REFERENCE_SUDOKU, boxes=False, alldiff=False),
+        "Sudoku_boxes_alldiff": sudoku(REFERENCE_SUDOKU, boxes=True, alldiff=True),
+        "Sudoku_boxes_binary": sudoku(REFERENCE_SUDOKU, boxes=True, alldiff=False),
+    }
+    for name, model in cases.items():
+        g = golden["reference_tests"][name]
+        r = api.Model(model).solve_tree("first")
+        assert (r.status, r.nodes, r.first) == (g["status"], g["nodes"], g["first"]), (name, r)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("n", list(range(1, 14)))
+def test_nqueens_count_and_first(golden, product_lib, engine, n):
+    g = golden["nqueens"][str(n)]
+    m = api.Model(nqueens(n))
+    c = m.solve_tree("count", engine=engine)
+    assert (c.solutions, c.nodes, c.first) == (g["count"]["solutions"], g["count"]["nodes"], g["count"]["first"]), c
+    f = m.solve_tree("first", engine=engine)
+    assert (f.status, f.nodes, f.first) == (g["first"]["status"], g["first"]["nodes"], g["first"]["first"]), f
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_nqueens14_config(golden, product_lib, engine):
+    """BASELINE config C2: 365 596 solutions, 19 787 662 nodes, first 0,2,4,6,11,9,12,3,13,8,1,5,7,10."""
+    g = golden["nqueens"]["14"]["count"]
+    c = api.Model(nqueens(14)).solve_tree("count", engine=engine)
+    assert (c.solutions, c.nodes, c.first) == (365596, 19787662, g["first"]) == (g["solutions"], g["nodes"], g["first"])
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("depth", [1, 2, 3, 5])
+def test_split_depth_invariance(golden, product_lib, engine, depth):
+    g = golden["nqueens"]["9"]
+    m = api.Model(nqueens(9))
+    c = m.solve_tree("count", split_depth=depth, engine=engine)
+    assert (c.solutions, c.nodes, c.first) == (g["count"]["solutions"], g["count"]["nodes"], g["count"]["first"])
+    f = m.solve_tree("first", split_depth=depth, engine=engine)
+    assert (f.nodes, f.first) == (g["first"]["nodes"], g["first"]["first"])
+
+
+@pytest.mark.parametrize("mode", ["first", "count"])
+def test_random_suite_vs_golden(golden, product_lib, mode):
+    gs = golden["random_suite"]
+    suite = model_suite(gs["n"], gs["seed0"])
+    for i, (csp, g) in enumerate(zip(suite, gs[mode])):
+        r = api.Model(csp).solve_tree(mode)
+        assert (r.status, r.solutions, r.nodes, r.first) == (g["status"], g["solutions"], g["nodes"], g["first"]), (i, r, g)
+
+
+def test_random_larger_models_vs_oracle(product_lib):
+    for seed in range(5000, 5060):
+        csp = random_model(seed, n_vars=12, n_cons=20, max_dom=7)
+        for mode in ("first", "count"):
+            _cmp_tree(api.Model(csp).solve_tree(mode), O.solve(csp, mode), (seed, mode))
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_partitions_sum_to_whole(golden, product_lib, world):
+    """Multi-GPU split emulated on one device: prefix i -> partition i % world."""
+    g = golden["nqueens"]["10"]
+    m = api.Model(nqueens(10))
+    parts = [m.solve_tree("count", split_depth=3, part_rank=r, part_count=world) for r in range(world)]
+    assert sum(p.solutions for p in parts) == g["count"]["solutions"]
+    assert sum(p.nodes for p in parts) == g["count"]["nodes"]
+    key = min(p.first_key for p in parts)
+    assert [p.first for p in parts if p.first_key == key][0] == g["count"]["first"]
+    # FIRST mode: min key wins; node accounting re-asked for the global key
+    for csp, want in ((nqueens(10), g["first"]), (nqueens(6), golden["nqueens"]["6"]["first"])):
+        models = [api.Model(csp) for _ in range(world)]
+        loc = [mm.solve_tree("first", split_depth=2, part_rank=r, part_count=world) for r, mm in enumerate(models)]
+        key = min(p.first_key for p in loc)
+        assert sum(mm.nodes_upto(key) for mm in models) == want["nodes"]
+        assert [p.first for p in loc if p.first_key == key][0] == want["first"]
+
+
+def test_edge_cases(product_lib):
+    # no variables: IsComplete at entry (dequan.h:496-499)
+    r = api.Model(CSP()).solve_tree("first")
+    assert (r.status, r.nodes) == ("sat", 0)
+    # one variable, empty domain
+    csp = CSP()
+    csp.AddIntVar(3, 3)
+    _cmp_tree(api.Model(csp).solve_tree("first"), O.solve(csp, "first"), "empty domain")
+    # unsat by a wiped-out given: two fixed vars that must differ but are equal
+    csp = CSP()
+    a, b, c = csp.AddFixedVar(2), csp.AddFixedVar(2), csp.AddIntVar(0, 3)
+    csp.AddConstraint(OpConstraint(a, b, Op.NotEqual, 0))
+    csp.AddConstraint(OpConstraint(b, c, Op.Inf, 0))
+    for mode in ("first", "count"):
+        _cmp_tree(api.Model(csp).solve_tree(mode), O.solve(csp, mode), "wiped given")
+    # 32-value domains and 2-queens..3-queens (UNSAT trees)
+    csp = CSP()
+    xs = [csp.AddIntVar(0, 32) for _ in range(3)]
+    csp.AddConstraint(OpConstraint(xs[0], xs[1], Op.Sup, 29))
+    csp.AddConstraint(OpConstraint(xs[2], xs[1], Op.Equal, 1))
+    for mode in ("first", "count"):
+        _cmp_tree(api.Model(csp).solve_tree(mode), O.solve(csp, mode), "32-wide")
+    with pytest.raises(api.DequanError):
+        api.Model(nqueens(4)).solve_tree("first", node_budget=5)
+
+
+@pytest.mark.parametrize("giv", [30, 40, 24])
+def test_sudoku_batch_vs_golden(golden, product_lib, giv):
+    g = golden[f"sudoku_g{giv}"]
+    cells = G.sudoku_batch(g["n"], givens=giv, seed=g["seed"])
+    r = api.Model(sudoku_template()).solve_batch_cells(cells)
+    assert r.nodes.tolist() == g["nodes"]
+    assert [api.OUTCOME[s] for s in r.status] == g["status"]
+    assert ["".join(map(str, row)) for row in r.solution] == g["solution"]
+    assert r.total_nodes == sum(g["nodes"]) and r.n_sat == g["n"]
+
+
+def test_sudoku_batch_budget_and_unsat(product_lib):
+    cells = G.sudoku_batch(64, givens=26)
+    tmpl = api.Model(sudoku_template())
+    full = tmpl.solve_batch_cells(cells)
+    budget = int(np.median(full.nodes))
+    r = tmpl.solve_batch_cells(cells, node_budget=budget)
+    for i in range(64):
+        o = O.solve(sudoku(cells[i]), "first", budget)
+        assert (api.OUTCOME[r.status[i]], int(r.nodes[i])) == (o.status, o.nodes), i
+        if o.status == "sat":
+            assert r.solution[i].tolist() == o.first
+        else:
+            assert not r.solution[i].any()
+    assert 0 < r.n_budget < 64
+    # contradictory givens -> UNSAT with the reference's node count; bytes outside 1..9 -> status 3
+    bad = cells[:4].copy()
+    bad[0, 0], bad[0, 1] = 5, 5
+    bad[1, 0] = 200
+    r = tmpl.solve_batch_cells(bad)
+    o = O.solve(sudoku(bad[0]), "first")
+    assert (api.OUTCOME[r.status[0]], int(r.nodes[0])) == (o.status, o.nodes) and o.status == "unsat"
+    assert r.status[1] == 3
+    assert r.status[2] == 1 and r.status[3] == 1
+
+
+def test_sudoku_batch_large_properties(product_lib):
+    """Size-independent properties at a size the oracle cannot cover."""
+    n = 200_000
+    cells = G.sudoku_batch(n, givens=32, seed=7)
+    r = api.Model(sudoku_template()).solve_batch_cells(cells)
+    assert r.n_sat == n and (r.status == 1).all()
+    sol = r.solution.reshape(n, 9, 9)
+    want = np.arange(1, 10)
+    assert (np.sort(sol, axis=2) == want).all() and (np.sort(sol, axis=1) == want[:, None]).all()
+    boxes = sol.reshape(n, 3, 3, 3, 3).transpose(0, 1, 3, 2, 4).reshape(n, 9, 9)
+    assert (np.sort(boxes, axis=2) == want).all()
+    assert (sol.reshape(n, 81)[cells != 0] == cells[cells != 0]).all()
+    assert (r.nodes >= 81).all() and int(r.nodes.sum()) == r.total_nodes
+    # idempotence: a solved grid is its own solution in exactly 81 nodes
+    again = api.Model(sudoku_template()).solve_batch_cells(np.ascontiguousarray(r.solution[:1000]))
+    assert (again.solution == r.solution[:1000]).all() and (again.nodes == 81).all()
+    # spot-check 50 against the oracle
+    for i in range(0, n, n // 50):
+        o = O.solve(sudoku(cells[i]), "first")
+        assert (int(r.nodes[i]), r.solution[i].tolist()) == (o.nodes, o.first)
+
+
+def test_colouring_batch_vs_golden(golden, product_lib):
+    for case in golden["colouring"]:
+        off, edges = G.colouring_batch(case["count"], case["n_vertices"], case["c"])
+        assert hashlib.sha256(edges.tobytes()).hexdigest() == case["sha256"]
+        r = api.solve_batch_graphs(case["n_vertices"], case["k"], off, edges, node_budget=case["budget"])
+        assert [api.OUTCOME[s] for s in r.status] == case["status"]
+        assert r.nodes.tolist() == case["nodes"]
+        for i, first in enumerate(case["first"]):
+            if first is not None:
+                assert r.solution[i].tolist() == first
+            else:
+                assert (r.solution[i] == 0xFF).all()
+
+
+def test_colouring_200_vs_oracle(product_lib):
+    """BASELINE config C4 shape: G(200, c/199), node budget, tri-state result."""
+    off, edges = G.colouring_batch(24, 200, 3.6, seed=11)
+    r = api.solve_batch_graphs(200, 3, off, edges, node_budget=50_000)
+    for i in range(24):
+        o = O.solve(colouring(200, 3, edges[off[i]:off[i + 1]]), "first", 50_000)
+        assert (api.OUTCOME[r.status[i]], int(r.nodes[i])) == (o.status, o.nodes), i
+        if o.status == "sat":
+            assert r.solution[i].tolist() == o.first
+            e = edges[off[i]:off[i + 1]]
+            assert (r.solution[i][e[:, 0]] != r.solution[i][e[:, 1]]).all()
+    # the same instances as single-tree models through dq_solve_tree agree too (no budget: only the solved ones)
+    for i in range(24):
+        if r.status[i] == 1 and r.nodes[i] < 20000:
+            t = api.Model(colouring(200, 3, edges[off[i]:off[i + 1]])).solve_tree("first")
+            assert (t.nodes, t.first) == (int(r.nodes[i]), r.solution[i].tolist())
+
+
+def test_int_peak_microbenchmark(product_lib):
+    ops, ms = api.measure_int_peak()
+    assert 5e12 < ops < 4e13, ops
