@@ -8,6 +8,6 @@ NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall
        -I"$HERE/../../include" -I"$HERE")
 if [ "${DQ_PTXAS_V:-0}" = "1" ]; then FLAGS+=(-Xptxas -v); fi
-"$NVCC" "${FLAGS[@]}" -shared -o "$OUT/libdequan_b200.so" "$HERE/dq_api.cu" "$HERE/dq_compile.cpp" "$HERE"/dq_lane_*.cu 2>&1 || \
+
 "$NVCC" "${FLAGS[@]}" -shared -o "$OUT/libdequan_b200.so" "$HERE/dq_api.cu" "$HERE/dq_compile.cpp"
 echo "built $OUT/libdequan_b200.so"

@@ -260,7 +260,7 @@ int dq_solve_tree(dq_model* m, const dq_tree_opts* opts, dq_tree_result* res, in
     DQ_CUDA(cudaEventRecord(m->ev0, m->stream));
 
     // ---- frontier expansion, level by level, children kept in DFS order ----
-    if (m->levels.empty()) m->levels.resize(1);
+    if ((int)m->levels.size() < nv + 1) m->levels.resize(nv + 1);   // sized up front: references below stay valid
     m->levels[0].n = 1;
     DQ_CUDA(m->levels[0].prefixes.reserve(1));
     int depth = 0;
@@ -278,9 +278,8 @@ int dq_solve_tree(dq_model* m, const dq_tree_opts* opts, dq_tree_result* res, in
         DQ_CUDA(cudaMemcpyAsync(tot, ctrl + 4, sizeof tot, cudaMemcpyDeviceToHost, m->stream));
         DQ_CUDA(cudaStreamSynchronize(m->stream));
         shallow_nodes += tot[1];
-        if (tot[0] == 0) { empty = true; depth++; if ((int)m->levels.size() <= depth) m->levels.resize(depth + 1); m->levels[depth].n = 0; break; }
+        if (tot[0] == 0) { empty = true; depth++; m->levels[depth].n = 0; break; }
         if (tot[0] > 0x7FFFFFFFull / (unsigned)(depth + 1)) { g_err = "frontier too large"; return DQ_ERR_NOMEM; }
-        if ((int)m->levels.size() <= depth + 1) m->levels.resize(depth + 2);
         LevelArrays& C = m->levels[depth + 1];
         C.n = (int)tot[0];
         DQ_CUDA(C.prefixes.reserve((size_t)C.n * (depth + 1)));
