@@ -51,7 +51,7 @@ class dq_batch_stats(C.Structure):
                 ("kernel_ms", C.c_double), ("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
 
 
-EXPORTS = ["dq_device_info", "dq_compile", "dq_free", "dq_model_info", "dq_model_order", "dq_solve_tree",
+EXPORTS = ["dq_device_info", "dq_set_device", "dq_compile", "dq_free", "dq_model_info", "dq_model_order", "dq_model_table_bytes", "dq_solve_tree",
            "dq_tree_nodes_upto", "dq_solve_batch_cells", "dq_solve_batch_cells_dev", "dq_solve_batch_graphs",
            "dq_measure_int_peak", "dq_last_error", "dq_version"]
 
@@ -68,11 +68,13 @@ def lib():
     L = C.CDLL(LIB_PATH)
     vp, i32p, u8p, u64p = C.c_void_p, C.POINTER(C.c_int32), C.c_void_p, C.c_void_p
     L.dq_device_info.argtypes = [i32p, i32p, C.c_char_p, C.c_size_t]
+    L.dq_set_device.argtypes = [C.c_int32]
     L.dq_compile.argtypes = [C.POINTER(dq_model_desc), C.POINTER(vp)]
     L.dq_free.argtypes = [vp]
     L.dq_free.restype = None
     L.dq_model_info.argtypes = [vp, i32p, i32p, i32p, i32p]
     L.dq_model_order.argtypes = [vp, i32p]
+    L.dq_model_table_bytes.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.dq_solve_tree.argtypes = [vp, C.POINTER(dq_tree_opts), C.POINTER(dq_tree_result), i32p]
     L.dq_tree_nodes_upto.argtypes = [vp, C.c_uint64, C.POINTER(C.c_uint64)]
     L.dq_solve_batch_cells.argtypes = [vp, u8p, C.c_int64, C.c_int32, C.POINTER(dq_batch_opts), u8p, u64p, u8p,
@@ -100,6 +102,10 @@ def device_info():
     name = C.create_string_buffer(128)
     _check(lib().dq_device_info(C.byref(sm), C.byref(cc), name, 128))
     return {"sm_count": sm.value, "cc": cc.value, "name": name.value.decode()}
+
+
+def set_device(ordinal: int):
+    _check(lib().dq_set_device(ordinal))
 
 
 def measure_int_peak():
@@ -180,6 +186,11 @@ class Model:
         return TreeResult(OUTCOME[r.outcome], r.n_solutions, r.n_nodes, first[:self.n_vars].tolist() if have else None,
                           r.first_key, r.n_prefixes, r.split_depth_used, r.kernel_ms,
                           ENGINE_NAME.get(r.engine_used, "?"), r.kernel_launches)
+
+    def table_bytes(self) -> int:
+        n = C.c_uint64()
+        _check(lib().dq_model_table_bytes(self._h, C.byref(n)))
+        return n.value
 
     def nodes_upto(self, key: int) -> int:
         n = C.c_uint64()

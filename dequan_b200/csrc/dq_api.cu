@@ -178,6 +178,11 @@ int dq_device_info(int32_t* sm_count, int32_t* cc, char* name, size_t name_len) 
     return DQ_OK;
 }
 
+int dq_set_device(int32_t ordinal) {
+    DQ_CUDA(cudaSetDevice(ordinal));
+    return DQ_OK;
+}
+
 int dq_compile(const dq_model_desc* desc, dq_model** out) {
     if (!out) { g_err = "null out"; return DQ_ERR_INVALID; }
     *out = nullptr;
@@ -221,6 +226,14 @@ int dq_model_info(const dq_model* m, int32_t* n_vars, int32_t* max_dom, int32_t*
 int dq_model_order(const dq_model* m, int32_t* order_out) {
     if (!m || !order_out) { g_err = "null argument"; return DQ_ERR_INVALID; }
     for (int i = 0; i < m->cm.nv; i++) order_out[i] = m->cm.order[i];
+    return DQ_OK;
+}
+
+int dq_model_table_bytes(const dq_model* m, uint64_t* bytes) {
+    if (!m || !bytes) { g_err = "null argument"; return DQ_ERR_INVALID; }
+    const CompiledModel& c = m->cm;
+    *bytes = c.ent_off.size() * 4 + c.ent.size() * 2 + c.ent_moff.size() * 4 + c.masks.size() * 4 + c.dom0.size() * 4 +
+             (size_t)c.nv * 2 + (size_t)c.nv * 32 * 4 + (size_t)c.nv * 256 + c.distinct_sizes.size() * 4 + 4;
     return DQ_OK;
 }
 
@@ -551,7 +564,7 @@ int dq_measure_int_peak(double* lane_ops_per_s, double* ms_out) {
     DQ_CUDA(cudaGetLastError());
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     cudaFree(out);
-    const double ops = (double)blocks * threads * (double)iters * 16.0 * 8.0;   // one LOP3 per statement (see SASS)
+    const double ops = (double)blocks * threads * (double)iters * 16.0 * 8.0;   // exactly one lop3.b32 per statement
     if (lane_ops_per_s) *lane_ops_per_s = ops / (best * 1e-3);
     if (ms_out) *ms_out = best;
     return DQ_OK;

@@ -357,17 +357,18 @@ k_batch_graphs(BatchGraphsArgs A) {
     }
 }
 
-// ---- integer-pipe peak: dependent-free LOP3 chains, 8 independent accumulators per lane -----------
+// ---- integer-pipe peak: 8 independent lop3.b32 chains per lane, one LOP3 per statement ------------
+#define DQ_LOP3(d, a, b) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(d) : "r"(a), "r"(b))
 __global__ void __launch_bounds__(1024) k_int_peak(uint32_t* out, int iters) {
     uint32_t a0 = threadIdx.x, a1 = a0 * 3 + 1, a2 = a0 * 5 + 2, a3 = a0 * 7 + 3, a4 = a0 * 11 + 4, a5 = a0 * 13 + 5,
              a6 = a0 * 17 + 6, a7 = a0 * 19 + 7;
-    const uint32_t k0 = blockIdx.x * 2654435761u + 1, k1 = ~k0;
+    const uint32_t k0 = blockIdx.x * 2654435761u + 1;
 #pragma unroll 1
     for (int i = 0; i < iters; i++) {
 #pragma unroll
         for (int u = 0; u < 16; u++) {
-            a0 = (a0 & k0) ^ a1; a1 = (a1 | k1) ^ a2; a2 = (a2 & k0) ^ a3; a3 = (a3 | k1) ^ a4;
-            a4 = (a4 & k0) ^ a5; a5 = (a5 | k1) ^ a6; a6 = (a6 & k0) ^ a7; a7 = (a7 | k1) ^ a0;
+            DQ_LOP3(a0, a1, k0); DQ_LOP3(a1, a2, k0); DQ_LOP3(a2, a3, k0); DQ_LOP3(a3, a4, k0);
+            DQ_LOP3(a4, a5, k0); DQ_LOP3(a5, a6, k0); DQ_LOP3(a6, a7, k0); DQ_LOP3(a7, a0, k0);
         }
     }
     out[blockIdx.x * blockDim.x + threadIdx.x] = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;

@@ -148,6 +148,10 @@ typedef struct dq_model dq_model;   /* compiled model: flat tables, host + HBM c
 /* Library / device probe.  Returns DQ_OK and fills *sm_count, *cc (e.g. 100).     */
 int dq_device_info(int32_t *sm_count, int32_t *cc, char *name, size_t name_len);
 
+/* Select the CUDA device this thread's subsequent calls run on (one process per GPU under
+ * torchrun: pass LOCAL_RANK).  Handles are bound to the device current at their first solve. */
+int dq_set_device(int32_t ordinal);
+
 /* Lower a model to the flat position-space table: static assign order
  * (Assignment::Reset, dequan.h:376-394), bitset domains, forward arc programs.
  * Replaces CSP::FinalizeModel + Assignment::Reset.                               */
@@ -158,6 +162,8 @@ void dq_free(dq_model *m);
 int dq_model_info(const dq_model *m, int32_t *n_vars, int32_t *max_dom,
                   int32_t *n_arcs, int32_t *model_class);
 int dq_model_order(const dq_model *m, int32_t *order_out /* [n_vars] */);
+/* Bytes of the flat tables a solve uploads to HBM for this model (h2d accounting). */
+int dq_model_table_bytes(const dq_model *m, uint64_t *bytes);
 
 /* Solve one model (single tree).  Replaces `a.Reset(csp); csp.ForwardCheckingStep(a)`
  * (dequan.h:292, 347).  first_solution[n_vars] receives InstVar values by var id

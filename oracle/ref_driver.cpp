@@ -228,11 +228,12 @@ static void print_out(const SolveOut& o) { std::cout << to_json(o) << std::endl;
 
 // ---------------------------------------------------------------------------------
 // Model builders that follow test/main-test.cpp
-static ModelText nqueens_model(int n, int fix_first /* -1 = none */) {
+static ModelText nqueens_model(int n, const std::vector<int>& fixed /* singleton domains for vars 0..k-1 */) {
     ModelText m;
     m.doms.resize(n);
     for (int i = 0; i < n; i++) { m.doms[i].type = 1; m.doms[i].vals = {0, n}; }   // AddIntVar(0,N) main-test.cpp:36
-    if (fix_first >= 0) { m.doms[0].type = 0; m.doms[0].vals = {fix_first}; }       // depth-1 split (§8c)
+    // prefix split (§8c): fixed vars keep ids 0..k-1 and, being the smallest domains, stay first in assign_order
+    for (size_t i = 0; i < fixed.size(); i++) { m.doms[i].type = 0; m.doms[i].vals = {fixed[i]}; }
     for (int i = 0; i < n; i++)
         for (int j = i + 1; j < n; j++) {                                           // main-test.cpp:39-48
             m.cons.push_back({"op", {i, j, 1, 0}});
@@ -280,7 +281,7 @@ static int cmd_tests() {
         m.cons.push_back({"op", {1, 2, 4, 0}}); m.cons.push_back({"op", {1, 3, 3, 0}});
         std::cout << "{\"test\":\"OpInequalityTest\",\"result\":" << to_json(run_solve(m, false, 0)) << "}" << std::endl;
     }
-    { std::cout << "{\"test\":\"NQueensTest8\",\"result\":" << to_json(run_solve(nqueens_model(8, -1), false, 0)) << "}" << std::endl; }
+    { std::cout << "{\"test\":\"NQueensTest8\",\"result\":" << to_json(run_solve(nqueens_model(8, std::vector<int>()), false, 0)) << "}" << std::endl; }
     const char* grid = "003020600900305001001806400008102900700000008006708200002609500800203009005010300";  // main-test.cpp:92-105
     { std::cout << "{\"test\":\"SudokuTest_rows_cols_alldiff\",\"result\":" << to_json(run_solve(sudoku_model(grid, false, true), false, 0)) << "}" << std::endl; }
     { std::cout << "{\"test\":\"Sudoku_rows_cols_binary\",\"result\":" << to_json(run_solve(sudoku_model(grid, false, false), false, 0)) << "}" << std::endl; }
@@ -307,20 +308,23 @@ static void parallel_for(long n, int threads, F f) {
     for (auto& t : th) t.join();
 }
 
+// nqueens N first|count [THREADS [p0 p1 ...]] : with THREADS>1 (count only) the tree below the fixed
+// prefix p0.. is split on the next variable's values, one task per value, and the results summed.
 static int cmd_nqueens(int argc, char** argv) {
     if (argc < 4) return 2;
     int n = atoi(argv[2]);
     bool count_all = !strcmp(argv[3], "count");
     int threads = argc > 4 ? atoi(argv[4]) : 1;
+    std::vector<int> prefix;
+    for (int i = 5; i < argc; i++) prefix.push_back(atoi(argv[i]));
     auto t0 = std::chrono::steady_clock::now();
-    if (threads <= 1 || !count_all) {
-        SolveOut o = run_solve(nqueens_model(n, -1), count_all, 0);
+    if (threads <= 1 || !count_all || (int)prefix.size() >= n) {
+        SolveOut o = run_solve(nqueens_model(n, prefix), count_all, 0);
         print_out(o);
         return 0;
     }
-    // depth-1 split: var 0 gets a singleton Values domain per task (stays first in assign_order)
     std::vector<SolveOut> outs(n);
-    parallel_for(n, threads, [&](long v) { outs[v] = run_solve(nqueens_model(n, (int)v), true, 0); });
+    parallel_for(n, threads, [&](long v) { std::vector<int> p = prefix; p.push_back((int)v); outs[v] = run_solve(nqueens_model(n, p), true, 0); });
     auto t1 = std::chrono::steady_clock::now();
     SolveOut sum = outs[0];
     for (int v = 1; v < n; v++) {
