@@ -9,6 +9,7 @@
 
 #include "dequan_b200.h"
 #include "dq_kernels.cuh"
+#include "dq_lane_queens.cuh"
 #include "dq_model.hpp"
 
 namespace dq {
@@ -70,6 +71,10 @@ struct dq_model {
     int last_depth = 0;
     unsigned long long last_n_prefix = 0;
     int last_part_rank = 0, last_part_count = 1;
+    // lane engine scratch
+    DevBuf<QueensRecord> q_records;
+    DevBuf<unsigned long long> q_sol_key;
+    DevBuf<uint8_t> q_sol;
     // batch scratch
     DevBuf<uint8_t> b_cells, b_solution, b_status;
     DevBuf<unsigned long long> b_nodes;
@@ -160,6 +165,87 @@ static int max_ctas_per_sm(K kernel, int threads, size_t smem, int* out) {
                    : ((m)->cm.has_table ? max_ctas_per_sm(KERNEL<false, true>, threads, smem, out) \
                                         : max_ctas_per_sm(KERNEL<false, false>, threads, smem, out)))
 
+
+// COUNT_ALL on a CLASS_QUEENS model with the lane-per-subtree engine: two kernels, no host round trip.
+static int solve_queens_lane(dq_model* m, const dq_tree_opts* opts, dq_tree_result* res, int32_t* first_solution) {
+    const int N = m->cm.queens_n;
+    // split depth: as many digits as keep the item space <= 64M (validation stays a small fraction of the search)
+    int K = 0;
+    unsigned long long items = 1;
+    const int kmax = std::min(N - 2, 12);
+    if (opts->split_depth > 0) {
+        K = std::min(opts->split_depth, kmax);
+        for (int i = 0; i < K; i++) items *= (unsigned long long)N;
+        if (items > (1ull << 27)) { g_err = "split_depth too deep for the item index"; return DQ_ERR_INVALID; }
+    } else {
+        while (K < kmax && items * (unsigned long long)N <= (64ull << 20)) { items *= (unsigned long long)N; K++; }
+    }
+    const bool stack128 = (N - 1 - K) > 12;
+    if (N - 1 - K > 25) { g_err = "board too large for the register stack"; return DQ_ERR_UNSUPPORTED; }
+    int occ = 0;
+    if (stack128) DQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_queens_lane<true>, kQueensBlock, 0));
+    else DQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_queens_lane<false>, kQueensBlock, 0));
+    if (occ < 1) { g_err = "kernel does not fit an SM"; return DQ_ERR_UNSUPPORTED; }
+    const unsigned long long mine = (items + opts->part_count - 1 - opts->part_rank) / opts->part_count;
+    const int ctas = occ * m->sm_count;
+    const size_t n_threads = (size_t)ctas * kQueensBlock;
+    DQ_CUDA(m->q_sol_key.reserve(n_threads));
+    DQ_CUDA(m->q_sol.reserve(n_threads * 32 + 32));
+    size_t cap = std::max<size_t>(m->q_records.cap, (size_t)std::min<unsigned long long>(std::max<unsigned long long>(mine, 1), 1ull << 21));
+    unsigned long long h_ctrl[8];
+    unsigned long long* ctrl = m->d_ctrl.p;     // [0]=cursor [1]=sols [2]=nodes [3]=best [4]=n_records
+    uint8_t* out_sol = m->q_sol.p + n_threads * 32;
+    unsigned long long launches = 0;
+    float ms_total = 0;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        DQ_CUDA(m->q_records.reserve(cap));
+        QueensLaneArgs A;
+        A.n = N; A.k = K; A.n_items = items;
+        A.div_magic = (unsigned int)(((1ull << 32) + N - 1) / N);
+        A.part_rank = opts->part_rank; A.part_count = opts->part_count;
+        A.records = m->q_records.p; A.record_cap = m->q_records.cap; A.n_records = ctrl + 4;
+        A.cursor = ctrl + 0; A.totals = ctrl + 1; A.best_key = ctrl + 3;
+        A.sol_key = m->q_sol_key.p; A.sol = m->q_sol.p;
+        const unsigned long long init[8] = {0, 0, 0, KEY_NONE, 0, 0, 0, 0};
+        DQ_CUDA(cudaMemcpyAsync(ctrl, init, sizeof init, cudaMemcpyHostToDevice, m->stream));
+        DQ_CUDA(cudaMemsetAsync(m->q_sol_key.p, 0xFF, n_threads * sizeof(unsigned long long), m->stream));
+        DQ_CUDA(cudaEventRecord(m->ev0, m->stream));
+        const unsigned long long want_ctas = (mine + kQueensBlock - 1) / kQueensBlock;
+        const int grid_items = (int)std::min<unsigned long long>(std::max<unsigned long long>(want_ctas, 1), (unsigned long long)m->sm_count * 16);
+        k_queens_items<<<grid_items, kQueensBlock, 0, m->stream>>>(A);
+        if (stack128) k_queens_lane<true><<<ctas, kQueensBlock, 0, m->stream>>>(A);
+        else k_queens_lane<false><<<ctas, kQueensBlock, 0, m->stream>>>(A);
+        k_queens_pick<<<64, 256, 0, m->stream>>>(ctrl + 3, m->q_sol_key.p, m->q_sol.p, n_threads, N, out_sol);
+        launches += 3;
+        DQ_CUDA(cudaGetLastError());
+        DQ_CUDA(cudaEventRecord(m->ev1, m->stream));
+        DQ_CUDA(cudaMemcpyAsync(h_ctrl, ctrl, sizeof h_ctrl, cudaMemcpyDeviceToHost, m->stream));
+        DQ_CUDA(cudaStreamSynchronize(m->stream));
+        float ms = 0;
+        DQ_CUDA(cudaEventElapsedTime(&ms, m->ev0, m->ev1));
+        ms_total += ms;
+        if (h_ctrl[4] <= m->q_records.cap) break;
+        cap = (size_t)h_ctrl[4];                 // record list overflowed: grow to the exact count and rerun
+        if (attempt == 1) { g_err = "internal: record list overflow persists"; return DQ_ERR_INTERNAL; }
+    }
+    res->kernel_ms = ms_total;
+    res->kernel_launches = launches;
+    res->engine_used = DQ_ENGINE_LANE;
+    res->split_depth_used = K;
+    res->n_prefixes = (int32_t)std::min<unsigned long long>(h_ctrl[4], 0x7FFFFFFF);
+    res->n_solutions = h_ctrl[1];
+    res->n_nodes = h_ctrl[2];
+    res->first_key = h_ctrl[3];
+    res->outcome = res->n_solutions ? DQ_SAT : DQ_UNSAT;
+    m->last_n_prefix = 0; m->last_depth = 0;
+    if (h_ctrl[3] != KEY_NONE && first_solution) {
+        uint8_t sol[32];
+        DQ_CUDA(cudaMemcpy(sol, out_sol, 32, cudaMemcpyDeviceToHost));
+        for (int v = 0; v < N; v++) first_solution[v] = m->cm.values[v][sol[v]];
+    }
+    return DQ_OK;
+}
+
 }  // namespace dq
 
 extern "C" {
@@ -202,6 +288,7 @@ void dq_free(dq_model* m) {
         m->d_ent.release(); m->d_order.release(); m->d_pos.release(); m->d_cell_lut.release();
         m->d_values.release(); m->d_sizes.release(); m->d_ctrl.release();
         m->d_sub_nodes.release(); m->d_sol_key.release(); m->d_sol.release();
+        m->q_records.release(); m->q_sol_key.release(); m->q_sol.release();
         m->b_cells.release(); m->b_solution.release(); m->b_status.release(); m->b_nodes.release();
         for (auto& l : m->levels) {
             l.dmask.release(); l.surv.release(); l.child_off.release(); l.parent_of.release();
@@ -251,6 +338,11 @@ int dq_solve_tree(dq_model* m, const dq_tree_opts* opts, dq_tree_result* res, in
     int rc = upload(m);
     if (rc != DQ_OK) return rc;
     const bool count_all = opts->mode == DQ_MODE_COUNT_ALL;
+    if (opts->engine == DQ_ENGINE_LANE && !(count_all && m->cm.model_class == CLASS_QUEENS)) {
+        g_err = "the lane engine serves COUNT_ALL on N-Queens-class models only"; return DQ_ERR_UNSUPPORTED;
+    }
+    if (count_all && m->cm.model_class == CLASS_QUEENS && opts->engine != DQ_ENGINE_WARP)
+        return solve_queens_lane(m, opts, res, first_solution);
     const TreeModelDev M = dev_model(m);
     const size_t wbytes = warp_state_bytes(nv, M.trail);
     const size_t smem = wbytes * kWarpsPerCta;

@@ -15,7 +15,7 @@ from randmodels import model_suite, random_model
 
 pytestmark = pytest.mark.gpu
 
-ENGINES = ["warp"]
+ENGINES = ["warp", "lane", "auto"]
 
 
 def _cmp_tree(got, want, what):
@@ -56,6 +56,10 @@ def test_nqueens_count_and_first(golden, product_lib, engine, n):
     m = api.Model(nqueens(n))
     c = m.solve_tree("count", engine=engine)
     assert (c.solutions, c.nodes, c.first) == (g["count"]["solutions"], g["count"]["nodes"], g["count"]["first"]), c
+    if engine == "lane":
+        if n >= 2:
+            assert c.engine == "lane"
+        return  # the lane engine serves COUNT_ALL only; FIRST runs on the warp engine
     f = m.solve_tree("first", engine=engine)
     assert (f.status, f.nodes, f.first) == (g["first"]["status"], g["first"]["nodes"], g["first"]["first"]), f
 
@@ -75,8 +79,9 @@ def test_split_depth_invariance(golden, product_lib, engine, depth):
     m = api.Model(nqueens(9))
     c = m.solve_tree("count", split_depth=depth, engine=engine)
     assert (c.solutions, c.nodes, c.first) == (g["count"]["solutions"], g["count"]["nodes"], g["count"]["first"])
-    f = m.solve_tree("first", split_depth=depth, engine=engine)
-    assert (f.nodes, f.first) == (g["first"]["nodes"], g["first"]["first"])
+    if engine != "lane":
+        f = m.solve_tree("first", split_depth=depth, engine=engine)
+        assert (f.nodes, f.first) == (g["first"]["nodes"], g["first"]["first"])
 
 
 @pytest.mark.parametrize("mode", ["first", "count"])
@@ -95,16 +100,19 @@ def test_random_larger_models_vs_oracle(product_lib):
             _cmp_tree(api.Model(csp).solve_tree(mode), O.solve(csp, mode), (seed, mode))
 
 
+@pytest.mark.parametrize("engine", ["warp", "lane"])
 @pytest.mark.parametrize("world", [2, 3, 8])
-def test_partitions_sum_to_whole(golden, product_lib, world):
+def test_partitions_sum_to_whole(golden, product_lib, world, engine):
     """Multi-GPU split emulated on one device: prefix i -> partition i % world."""
     g = golden["nqueens"]["10"]
     m = api.Model(nqueens(10))
-    parts = [m.solve_tree("count", split_depth=3, part_rank=r, part_count=world) for r in range(world)]
+    parts = [m.solve_tree("count", split_depth=3, part_rank=r, part_count=world, engine=engine) for r in range(world)]
     assert sum(p.solutions for p in parts) == g["count"]["solutions"]
     assert sum(p.nodes for p in parts) == g["count"]["nodes"]
     key = min(p.first_key for p in parts)
     assert [p.first for p in parts if p.first_key == key][0] == g["count"]["first"]
+    if engine == "lane":
+        return
     # FIRST mode: min key wins; node accounting re-asked for the global key
     for csp, want in ((nqueens(10), g["first"]), (nqueens(6), golden["nqueens"]["6"]["first"])):
         models = [api.Model(csp) for _ in range(world)]
@@ -228,6 +236,21 @@ def test_colouring_200_vs_oracle(product_lib):
         if r.status[i] == 1 and r.nodes[i] < 20000:
             t = api.Model(colouring(200, 3, edges[off[i]:off[i + 1]])).solve_tree("first")
             assert (t.nodes, t.first) == (int(r.nodes[i]), r.solution[i].tolist())
+
+
+def test_lane_engine_rejects_other_models(product_lib):
+    with pytest.raises(api.DequanError):
+        api.Model(nqueens(6)).solve_tree("first", engine="lane")
+    with pytest.raises(api.DequanError):
+        api.Model(sudoku(REFERENCE_SUDOKU)).solve_tree("count", engine="lane")
+
+
+@pytest.mark.parametrize("n,k", [(15, 0), (16, 0), (12, 1), (12, 7), (13, 10)])
+def test_lane_engine_larger_boards(product_lib, n, k):
+    """N=15/16 counts are OEIS A000170 + the node counts of SURVEY.md section 10 (cross-checked by the warp engine)."""
+    known = {12: (14200, 641974), 13: (73712, 3456855), 15: (2279184, 121498513), 16: (14772512, 795563572)}
+    r = api.Model(nqueens(n)).solve_tree("count", engine="lane", split_depth=k)
+    assert (r.solutions, r.nodes) == known[n] and r.engine == "lane"
 
 
 def test_int_peak_microbenchmark(product_lib):
