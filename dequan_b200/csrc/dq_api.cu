@@ -72,9 +72,9 @@ struct dq_model {
     unsigned long long last_n_prefix = 0;
     int last_part_rank = 0, last_part_count = 1;
     // lane engine scratch
-    DevBuf<QueensRecord> q_records;
-    DevBuf<unsigned long long> q_sol_key;
-    DevBuf<uint8_t> q_sol;
+    DevBuf<uint4> q_records;
+    DevBuf<uint8_t> q_first;
+    uint8_t h_first[32] = {0};
     // batch scratch
     DevBuf<uint8_t> b_cells, b_solution, b_status;
     DevBuf<unsigned long long> b_nodes;
@@ -166,7 +166,7 @@ static int max_ctas_per_sm(K kernel, int threads, size_t smem, int* out) {
                                         : max_ctas_per_sm(KERNEL<false, false>, threads, smem, out)))
 
 
-// COUNT_ALL on a CLASS_QUEENS model with the lane-per-subtree engine: two kernels, no host round trip.
+// COUNT_ALL on a CLASS_QUEENS model with the lane-per-subtree engine: three kernels, no host round trip.
 static int solve_queens_lane(dq_model* m, const dq_tree_opts* opts, dq_tree_result* res, int32_t* first_solution) {
     const int N = m->cm.queens_n;
     // split depth: as many digits as keep the item space <= 64M (validation stays a small fraction of the search)
@@ -180,21 +180,19 @@ static int solve_queens_lane(dq_model* m, const dq_tree_opts* opts, dq_tree_resu
     } else {
         while (K < kmax && items * (unsigned long long)N <= (64ull << 20)) { items *= (unsigned long long)N; K++; }
     }
-    const bool stack128 = (N - 1 - K) > 12;
-    if (N - 1 - K > 25) { g_err = "board too large for the register stack"; return DQ_ERR_UNSUPPORTED; }
+    const int levels = std::max(N - 2 - K, 1);
+    const size_t smem = (size_t)levels * kQueensBlock * sizeof(uint4);
+    if (smem > 200 * 1024) { g_err = "board too large for the shared-memory stack"; return DQ_ERR_UNSUPPORTED; }
     int occ = 0;
-    if (stack128) DQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_queens_lane<true>, kQueensBlock, 0));
-    else DQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_queens_lane<false>, kQueensBlock, 0));
+    int rc = max_ctas_per_sm(k_queens_lane, kQueensBlock, smem, &occ);
+    if (rc != DQ_OK) return rc;
     if (occ < 1) { g_err = "kernel does not fit an SM"; return DQ_ERR_UNSUPPORTED; }
     const unsigned long long mine = (items + opts->part_count - 1 - opts->part_rank) / opts->part_count;
     const int ctas = occ * m->sm_count;
-    const size_t n_threads = (size_t)ctas * kQueensBlock;
-    DQ_CUDA(m->q_sol_key.reserve(n_threads));
-    DQ_CUDA(m->q_sol.reserve(n_threads * 32 + 32));
+    DQ_CUDA(m->q_first.reserve(32));
     size_t cap = std::max<size_t>(m->q_records.cap, (size_t)std::min<unsigned long long>(std::max<unsigned long long>(mine, 1), 1ull << 21));
     unsigned long long h_ctrl[8];
     unsigned long long* ctrl = m->d_ctrl.p;     // [0]=cursor [1]=sols [2]=nodes [3]=best [4]=n_records
-    uint8_t* out_sol = m->q_sol.p + n_threads * 32;
     unsigned long long launches = 0;
     float ms_total = 0;
     for (int attempt = 0; attempt < 2; attempt++) {
@@ -205,21 +203,20 @@ static int solve_queens_lane(dq_model* m, const dq_tree_opts* opts, dq_tree_resu
         A.part_rank = opts->part_rank; A.part_count = opts->part_count;
         A.records = m->q_records.p; A.record_cap = m->q_records.cap; A.n_records = ctrl + 4;
         A.cursor = ctrl + 0; A.totals = ctrl + 1; A.best_key = ctrl + 3;
-        A.sol_key = m->q_sol_key.p; A.sol = m->q_sol.p;
+        A.first_out = m->q_first.p;
         const unsigned long long init[8] = {0, 0, 0, KEY_NONE, 0, 0, 0, 0};
         DQ_CUDA(cudaMemcpyAsync(ctrl, init, sizeof init, cudaMemcpyHostToDevice, m->stream));
-        DQ_CUDA(cudaMemsetAsync(m->q_sol_key.p, 0xFF, n_threads * sizeof(unsigned long long), m->stream));
         DQ_CUDA(cudaEventRecord(m->ev0, m->stream));
         const unsigned long long want_ctas = (mine + kQueensBlock - 1) / kQueensBlock;
         const int grid_items = (int)std::min<unsigned long long>(std::max<unsigned long long>(want_ctas, 1), (unsigned long long)m->sm_count * 16);
         k_queens_items<<<grid_items, kQueensBlock, 0, m->stream>>>(A);
-        if (stack128) k_queens_lane<true><<<ctas, kQueensBlock, 0, m->stream>>>(A);
-        else k_queens_lane<false><<<ctas, kQueensBlock, 0, m->stream>>>(A);
-        k_queens_pick<<<64, 256, 0, m->stream>>>(ctrl + 3, m->q_sol_key.p, m->q_sol.p, n_threads, N, out_sol);
+        k_queens_lane<<<ctas, kQueensBlock, smem, m->stream>>>(A);
+        k_queens_first<<<1, 32, 0, m->stream>>>(A);
         launches += 3;
         DQ_CUDA(cudaGetLastError());
         DQ_CUDA(cudaEventRecord(m->ev1, m->stream));
         DQ_CUDA(cudaMemcpyAsync(h_ctrl, ctrl, sizeof h_ctrl, cudaMemcpyDeviceToHost, m->stream));
+        DQ_CUDA(cudaMemcpyAsync(m->h_first, m->q_first.p, 32, cudaMemcpyDeviceToHost, m->stream));
         DQ_CUDA(cudaStreamSynchronize(m->stream));
         float ms = 0;
         DQ_CUDA(cudaEventElapsedTime(&ms, m->ev0, m->ev1));
@@ -238,11 +235,8 @@ static int solve_queens_lane(dq_model* m, const dq_tree_opts* opts, dq_tree_resu
     res->first_key = h_ctrl[3];
     res->outcome = res->n_solutions ? DQ_SAT : DQ_UNSAT;
     m->last_n_prefix = 0; m->last_depth = 0;
-    if (h_ctrl[3] != KEY_NONE && first_solution) {
-        uint8_t sol[32];
-        DQ_CUDA(cudaMemcpy(sol, out_sol, 32, cudaMemcpyDeviceToHost));
-        for (int v = 0; v < N; v++) first_solution[v] = m->cm.values[v][sol[v]];
-    }
+    if (h_ctrl[3] != KEY_NONE && first_solution)
+        for (int v = 0; v < N; v++) first_solution[v] = m->cm.values[v][m->h_first[v]];
     return DQ_OK;
 }
 
@@ -288,7 +282,7 @@ void dq_free(dq_model* m) {
         m->d_ent.release(); m->d_order.release(); m->d_pos.release(); m->d_cell_lut.release();
         m->d_values.release(); m->d_sizes.release(); m->d_ctrl.release();
         m->d_sub_nodes.release(); m->d_sol_key.release(); m->d_sol.release();
-        m->q_records.release(); m->q_sol_key.release(); m->q_sol.release();
+        m->q_records.release(); m->q_first.release();
         m->b_cells.release(); m->b_solution.release(); m->b_status.release(); m->b_nodes.release();
         for (auto& l : m->levels) {
             l.dmask.release(); l.surv.release(); l.child_off.release(); l.parent_of.release();
@@ -341,7 +335,7 @@ int dq_solve_tree(dq_model* m, const dq_tree_opts* opts, dq_tree_result* res, in
     if (opts->engine == DQ_ENGINE_LANE && !(count_all && m->cm.model_class == CLASS_QUEENS)) {
         g_err = "the lane engine serves COUNT_ALL on N-Queens-class models only"; return DQ_ERR_UNSUPPORTED;
     }
-    if (count_all && m->cm.model_class == CLASS_QUEENS && opts->engine != DQ_ENGINE_WARP)
+    if (count_all && m->cm.model_class == CLASS_QUEENS && m->cm.queens_n <= kQueensMaxN && opts->engine != DQ_ENGINE_WARP)
         return solve_queens_lane(m, opts, res, first_solution);
     const TreeModelDev M = dev_model(m);
     const size_t wbytes = warp_state_bytes(nv, M.trail);

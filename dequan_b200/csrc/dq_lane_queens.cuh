@@ -2,27 +2,32 @@
 // (CLASS_QUEENS: N variables on [0,N), NotEqual with offsets {0, +-(j-i)} for every pair —
 // exactly /root/reference/test/main-test.cpp:36-49, recognised by the model compiler).
 //
-// Every lane owns one subtree and keeps its whole search state in registers:
-//   A            values taken by assigned variables               (column mask)
-//   L, R         the two diagonal masks as 64-bit words, shifted one bit per depth, so the current
-//                domain of the variable at distance j+1 is   full & ~(A | L<<j | R>>j)
-//                i.e. the closed form of what OpConstraint::AplyArcConsistency + Domain::Exclude
-//                (dequan.h:631-694, 985-1031) leave in current_domains[d+1+j]
-//   stk          chosen value per depth below the split, 5 bits each (the explicit DFS stack;
-//                undo = shift the diagonals back and clear the popped bit, no trail memory)
-// Forward checking of a candidate = test every later variable's domain for emptiness (the
-// reference stops at the first wipe-out, dequan.h:514; so does the loop here).
-// Node accounting is the reference's: one node per AssignVar call (dequan.h:416-423), i.e. per
-// value of the current (filtered) domain of the next variable, whether or not its check succeeds.
+// Every lane owns one subtree.  Its search state is three bit masks in registers:
+//   a      values taken by the assigned variables
+//   l, r   the two diagonal masks, shifted one bit per depth, so that the current domain of the
+//          variable at distance j+1 is   full & ~(a | l<<j | r>>j)
+//          — the closed form of what OpConstraint::AplyArcConsistency + Domain::Exclude
+//          (dequan.h:631-694, 985-1031) leave in current_domains[d+1+j].
+// Forward checking of a candidate = test every later variable's domain for emptiness
+// (dequan.h:514-518, 663-668).  Node accounting is the reference's: one node per AssignVar call
+// (dequan.h:416-423), i.e. per value of the current filtered domain of the next variable, whether
+// or not its check then succeeds.
+//
+// The explicit DFS stack (the reference recurses, dequan.h:522) is a frame {a,l,r,untried,depth}
+// per lane per level in shared memory, laid out [level][thread] so that every access is
+// conflict-free.  A frame is written only when the level still has untried values, so a pop always
+// lands on a level with work (the saved-domain restore of dequan.h:431-440 becomes one 16-byte load).
 //
 // Work distribution, two kernels and no host round trip in between:
 //   k_queens_items : item j is the base-N number whose k digits are the values of the first k
 //                    variables.  One lane per item decodes it and replays the k assignments with
 //                    forward checking; a surviving item is appended (warp-aggregated atomic) to a
-//                    record list in HBM {key, A, L, R}.  A node above the split is counted by the
+//                    record list in HBM {key, a, l, r}.  A node above the split is counted by the
 //                    single item that extends it with zeros, so the node total stays exact.
-//   k_queens_lane  : persistent lanes pull records (two coalesced 16-byte loads per lane) and run
-//                    the register-resident DFS below them.
+//   k_queens_lane  : persistent lanes pull records (one coalesced 16-byte load per lane) and run
+//                    the DFS below them.
+//   k_queens_first : one lane re-walks the lowest-keyed item that holds a solution and writes the
+//                    DFS-first solution (keeps solution bookkeeping out of the hot loop).
 // Items are dealt round-robin to partitions (multi-GPU): partition r owns items j = r (mod parts).
 #pragma once
 #include <cstdint>
@@ -30,55 +35,22 @@
 
 namespace dq {
 
-struct __align__(16) QueensRecord {      // one FC-surviving prefix = one subtree to search
-    uint32_t key;                        // item index = DFS order of the prefix
-    uint32_t a, llo, lhi, rlo, rhi;      // search state after the k prefix assignments
-    uint32_t pad0, pad1;
-};
-
 struct QueensLaneArgs {
     int n, k;                         // board size; digits (split depth) per item
     unsigned long long n_items;       // n^k  (<= 2^27)
     unsigned int div_magic;           // ceil(2^32 / n): x / n == umulhi(x, magic) for x < 2^27, 2 <= n <= 32
     int part_rank, part_count;
-    QueensRecord* records;            // [record_cap]
+    uint4* records;                   // [record_cap] {key, a, l, r}: one FC-surviving prefix = one subtree
     unsigned long long record_cap;
     unsigned long long* n_records;    // valid items found (may exceed record_cap: then the host grows and reruns)
     unsigned long long* cursor;       // next record to search
     unsigned long long* totals;       // [0] solutions, [1] nodes
-    unsigned long long* best_key;     // lowest item index that recorded a solution
-    unsigned long long* sol_key;      // [n_threads]
-    uint8_t* sol;                     // [n_threads][32] values by variable
+    unsigned long long* best_key;     // lowest item index that holds a solution
+    uint8_t* first_out;               // [32] DFS-first solution, values by variable
 };
 
 constexpr int kQueensBlock = 256;
-
-// Rare path: this lane just found the DFS-first solution of its item and the item may be the
-// globally first one.  levels 0..k-1 come from the item digits, k..d-1 from the stack.
-__device__ __noinline__ void queens_record_first(unsigned long long* best_key, unsigned long long* sol_key, uint8_t* sol,
-                                                 int n, int k, unsigned int div_magic, unsigned long long key,
-                                                 unsigned long long stk_lo, unsigned long long stk_hi, int d, int v_d,
-                                                 int v_last) {
-    const unsigned long long old = atomicMin(best_key, key);
-    if (key >= old) return;
-    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    uint8_t* out = sol + tid * 32;
-    uint32_t rem = (uint32_t)key;
-    for (int t = k - 1; t >= 0; t--) {
-        const uint32_t q = __umulhi(rem, div_magic);
-        out[t] = (uint8_t)(rem - q * n);
-        rem = q;
-    }
-    for (int lvl = d - 1; lvl >= k; lvl--) {        // top of stack = deepest level
-        out[lvl] = (uint8_t)(stk_lo & 31);
-        stk_lo = (stk_lo >> 5) | (stk_hi << 59);
-        stk_hi >>= 5;
-    }
-    out[d] = (uint8_t)v_d;
-    out[d + 1] = (uint8_t)v_last;
-    __threadfence();
-    sol_key[tid] = key;
-}
+constexpr int kQueensMaxN = 27;       // frame packs the depth above bit 27 of `a`
 
 // Phase A: validate items, count the nodes above the split, emit records.
 __global__ void __launch_bounds__(kQueensBlock)
@@ -86,7 +58,7 @@ k_queens_items(QueensLaneArgs A) {
     const int lane = threadIdx.x & 31;
     const uint32_t lt = (1u << lane) - 1u;
     const int N = A.n, K = A.k;
-    const uint32_t full = N >= 32 ? 0xFFFFFFFFu : ((1u << N) - 1u);
+    const uint32_t full = (1u << N) - 1u;
     const unsigned long long mine = (A.n_items + A.part_count - 1 - A.part_rank) / A.part_count;   // items of this partition
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     unsigned long long tot_nodes = 0;
@@ -95,7 +67,7 @@ k_queens_items(QueensLaneArgs A) {
     for (unsigned long long base = first; base < mine; base += stride) {
         const unsigned long long ord = base + lane;
         bool valid = ord < mine;
-        uint32_t a = 0, llo = 0, lhi = 0, rlo = 0, rhi = 0, nodes = 0;
+        uint32_t a = 0, l = 0, r = 0, nodes = 0;
         const unsigned long long key = ord * (unsigned long long)A.part_count + (unsigned long long)A.part_rank;
         if (valid) {
             // digits of the item, level 0 = most significant, packed 5 bits per level
@@ -108,14 +80,14 @@ k_queens_items(QueensLaneArgs A) {
             }
             for (int i = 0; i < K; i++) {
                 const uint32_t bit = 1u << ((dg >> (5 * i)) & 31);
-                if (!(full & ~(a | llo | rhi) & bit)) { valid = false; break; }      // value not in the current domain: no node
+                if (!(full & ~(a | l | r) & bit)) { valid = false; break; }          // value not in the current domain: no node
                 if ((dg >> (5 * (i + 1))) == 0) ++nodes;                             // this item is the node's representative
-                const uint32_t lb = llo | bit, rb = rhi | bit;
                 a |= bit;
-                lhi = __funnelshift_l(lb, lhi, 1); llo = lb << 1;
-                rlo = __funnelshift_r(rlo, rb, 1); rhi = rb >> 1;
+                l = (l | bit) << 1;
+                r = (r | bit) >> 1;
+                const uint32_t ah = a | ~full;
                 for (int j = 0; j <= N - 2 - i; j++)
-                    if (((a | (llo << j) | (rhi >> j)) & full) == full) { valid = false; break; }   // wipe-out
+                    if ((ah | (l << j) | (r >> j)) == 0xFFFFFFFFu) { valid = false; break; }   // wipe-out
                 if (!valid) break;
             }
             tot_nodes += nodes;
@@ -126,34 +98,30 @@ k_queens_items(QueensLaneArgs A) {
             const int leader = __ffs(m) - 1;
             if (lane == leader) slot = atomicAdd(A.n_records, (unsigned long long)__popc(m));
             slot = __shfl_sync(0xFFFFFFFFu, slot, leader) + __popc(m & lt);
-            if (valid && slot < A.record_cap) {
-                uint4* dst = reinterpret_cast<uint4*>(A.records + slot);
-                dst[0] = make_uint4((uint32_t)key, a, llo, lhi);
-                dst[1] = make_uint4(rlo, rhi, 0u, 0u);
-            }
+            if (valid && slot < A.record_cap) A.records[slot] = make_uint4((uint32_t)key, a, l, r);
         }
     }
     for (int o = 16; o > 0; o >>= 1) tot_nodes += __shfl_down_sync(0xFFFFFFFFu, tot_nodes, o);
     if (lane == 0 && tot_nodes) atomicAdd(A.totals + 1, tot_nodes);
 }
 
-// Phase B: persistent lanes, register-resident DFS below each record.
-template <bool STACK128>
+// Phase B: persistent lanes, DFS below each record.  Dynamic shared memory: uint4[levels][256].
 __global__ void __launch_bounds__(kQueensBlock)
 k_queens_lane(QueensLaneArgs A) {
+    extern __shared__ uint4 frames[];
     const int lane = threadIdx.x & 31;
     const uint32_t lt = (1u << lane) - 1u;
     const int N = A.n, K = A.k;
-    const uint32_t full = N >= 32 ? 0xFFFFFFFFu : ((1u << N) - 1u);
+    const uint32_t full = (1u << N) - 1u;
     const unsigned long long n_found = *A.n_records;
     const unsigned long long n_rec = n_found < A.record_cap ? n_found : A.record_cap;   // overflow: the host grows the list and reruns
+    uint4* const my_frames = frames + threadIdx.x;
     unsigned long long tot_nodes = 0, tot_sols = 0;
 
     // per-lane search state
-    uint32_t a = 0, llo = 0, lhi = 0, rlo = 0, rhi = 0, cand = 0, key = 0;
-    unsigned long long stk = 0, stk_hi = 0;
+    uint32_t a = 0, l = 0, r = 0, cand = 0, key = 0;
     uint32_t nodes = 0, sols = 0;
-    int d = 0;
+    int d = 0, sp = 0;
     bool have = false, done = false, item_found = false;
 
     for (;;) {
@@ -165,72 +133,65 @@ k_queens_lane(QueensLaneArgs A) {
             if (lane == leader) base = atomicAdd(A.cursor, (unsigned long long)__popc(need));
             base = __shfl_sync(0xFFFFFFFFu, base, leader);
             if (!have && !done) {
-                const unsigned long long r = base + __popc(need & lt);
-                if (r >= n_rec) done = true;
+                const unsigned long long rix = base + __popc(need & lt);
+                if (rix >= n_rec) done = true;
                 else {
-                    const uint4* src = reinterpret_cast<const uint4*>(A.records + r);
-                    const uint4 r0 = __ldg(src), r1 = __ldg(src + 1);
-                    key = r0.x; a = r0.y; llo = r0.z; lhi = r0.w; rlo = r1.x; rhi = r1.y;
+                    const uint4 rec = __ldg(A.records + rix);
+                    key = rec.x; a = rec.y; l = rec.z; r = rec.w;
                     nodes = 0; sols = 0; item_found = false;
                     have = true;
-                    d = K;
-                    stk = 0; stk_hi = 0;
-                    cand = full & ~(a | llo | rhi);
+                    d = K; sp = 0;
+                    cand = full & ~(a | l | r);
                 }
             }
             if (__all_sync(0xFFFFFFFFu, done && !have)) break;
         }
 
-        if (have) {
-            if (cand == 0) {
-                // ---- every value tried at this depth: return to the parent (dequan.h:569-570) ----
-                if (d == K) {
-                    have = false;
-                    tot_nodes += nodes; tot_sols += sols;
-                } else {
-                    const uint32_t v = (uint32_t)stk & 31u;
-                    if (STACK128) { stk = (stk >> 5) | (stk_hi << 59); stk_hi >>= 5; } else stk >>= 5;
-                    const uint32_t bit = 1u << v;
-                    --d;
-                    a &= ~bit;
-                    llo = __funnelshift_r(llo, lhi, 1) & ~bit; lhi >>= 1;
-                    rhi = __funnelshift_l(rlo, rhi, 1) & ~bit; rlo <<= 1;
-                    cand = full & ~(a | llo | rhi) & ~((bit << 1) - 1u);     // values after v, ascending order (dequan.h:554-562)
-                }
+        // ---- every value tried at this depth: return to the nearest level with untried values ----
+        if (have && cand == 0) {
+            if (sp == 0) {
+                have = false;                                  // subtree exhausted (dequan.h:569-570 at the split depth)
+                tot_nodes += nodes; tot_sols += sols;
+            } else {
+                --sp;
+                const uint4 f = my_frames[sp * kQueensBlock];
+                a = f.x & 0x07FFFFFFu; d = (int)(f.x >> 27); l = f.y; r = f.z; cand = f.w;
             }
-            if (have && cand) {
-                // ---- AssignVar(next value) + forward check ----
-                const uint32_t bit = cand & (0u - cand);
-                cand ^= bit;
-                ++nodes;
-                const uint32_t lb = llo | bit, rb = rhi | bit;
-                const uint32_t na = a | bit, nllo = lb << 1, nrhi = rb >> 1;
-                bool ok = true;
-                const int last = N - 2 - d;
-                for (int j = 0; j <= last; j++)
-                    if (((na | (nllo << j) | (nrhi >> j)) & full) == full) { ok = false; break; }
-                if (ok) {
-                    if (last == 0) {
-                        // the child is the last variable: its whole domain is nodes, each one a solution
-                        const uint32_t c = full & ~(na | nllo | nrhi);
-                        const int pc = __popc(c);
-                        nodes += pc;
-                        if (!item_found) {
-                            item_found = true;
-                            if ((unsigned long long)key < *(volatile unsigned long long*)A.best_key)
-                                queens_record_first(A.best_key, A.sol_key, A.sol, N, K, A.div_magic, key, stk, stk_hi, d, __ffs(bit) - 1, __ffs(c) - 1);
-                        }
-                        sols += pc;
-                    } else {
-                        const uint32_t v = __ffs(bit) - 1;
-                        if (STACK128) { stk_hi = (stk_hi << 5) | (stk >> 59); }
-                        stk = (stk << 5) | v;
-                        a = na;
-                        lhi = __funnelshift_l(lb, lhi, 1); llo = nllo;
-                        rlo = __funnelshift_r(rlo, rb, 1); rhi = nrhi;
-                        ++d;
-                        cand = full & ~(a | llo | rhi);
+        }
+
+        // ---- AssignVar(next value) + forward check, all lanes converged ----
+        // The loop runs a warp-uniform number of rows (the deepest requirement among the lanes; a lane
+        // that needs fewer re-tests its last row) so the lanes leave it together.
+        const bool trying = have && cand != 0;
+        const uint32_t bit = cand & (0u - cand);
+        const uint32_t na = a | bit, nl = (l | bit) << 1, nr = (r | bit) >> 1;
+        const int last = trying ? N - 2 - d : 0;
+        const int tmax = __reduce_max_sync(0xFFFFFFFFu, last);
+        const uint32_t na_hi = na | ~full;                     // bits >= N pre-set: "row empty" <=> word is all ones
+        bool wipe = false;
+#pragma unroll 2
+        for (int j = 0; j <= tmax; j++) {
+            const int je = min(j, last);
+            wipe |= (na_hi | (nl << je) | (nr >> je)) == 0xFFFFFFFFu;
+        }
+        if (trying) {
+            cand ^= bit;
+            ++nodes;
+            if (!wipe) {
+                if (last == 0) {
+                    // the child is the last variable: its whole domain is nodes, each one a solution
+                    const int pc = __popc(full & ~(na | nl | nr));
+                    nodes += pc;
+                    sols += pc;
+                    if (!item_found) {
+                        item_found = true;
+                        if ((unsigned long long)key < *(volatile unsigned long long*)A.best_key) atomicMin(A.best_key, (unsigned long long)key);
                     }
+                } else {
+                    if (cand) { my_frames[sp * kQueensBlock] = make_uint4(a | ((uint32_t)d << 27), l, r, cand); ++sp; }
+                    a = na; l = nl; r = nr;
+                    ++d;
+                    cand = full & ~(a | l | r);
                 }
             }
         }
@@ -246,13 +207,41 @@ k_queens_lane(QueensLaneArgs A) {
     }
 }
 
-// Copies the solution recorded under `best_key` (if any) to out[0..n).
-__global__ void k_queens_pick(const unsigned long long* __restrict__ best_key, const unsigned long long* __restrict__ sol_key,
-                              const uint8_t* __restrict__ sol, size_t n_threads, int n, uint8_t* __restrict__ out) {
-    const unsigned long long best = *best_key;
-    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_threads; t += (size_t)gridDim.x * blockDim.x)
-        if (sol_key[t] == best && best != 0xFFFFFFFFFFFFFFFFull)
-            for (int i = 0; i < n; i++) out[i] = sol[t * 32 + i];
+// Phase C: the DFS-first solution lives in the lowest-keyed item that holds any solution; one lane
+// walks that item in value order until its first solution (ForwardCheckingStep's own order).
+__global__ void k_queens_first(QueensLaneArgs A) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const unsigned long long best = *A.best_key;
+    if (best == 0xFFFFFFFFFFFFFFFFull) return;
+    const int N = A.n, K = A.k;
+    const uint32_t full = (1u << N) - 1u;
+    uint32_t sa[32], sl[32], sr[32], sc[32];
+    uint8_t* out = A.first_out;
+    uint32_t a = 0, l = 0, r = 0, rem = (uint32_t)best;
+    for (int t = K - 1; t >= 0; t--) {
+        const uint32_t q = __umulhi(rem, A.div_magic);
+        out[t] = (uint8_t)(rem - q * N);
+        rem = q;
+    }
+    for (int i = 0; i < K; i++) {
+        const uint32_t bit = 1u << out[i];
+        a |= bit; l = (l | bit) << 1; r = (r | bit) >> 1;
+    }
+    int d = K;
+    sa[d] = a; sl[d] = l; sr[d] = r; sc[d] = full & ~(a | l | r);
+    while (d >= K) {
+        if (sc[d] == 0) { --d; continue; }
+        const uint32_t bit = sc[d] & (0u - sc[d]);
+        sc[d] ^= bit;
+        const uint32_t na = sa[d] | bit, nl = (sl[d] | bit) << 1, nr = (sr[d] | bit) >> 1;
+        bool wipe = false;
+        for (int j = 0; j <= N - 2 - d; j++) wipe |= ((na | ~full) | (nl << j) | (nr >> j)) == 0xFFFFFFFFu;
+        if (wipe) continue;
+        out[d] = (uint8_t)(__ffs(bit) - 1);
+        if (d == N - 2) { out[N - 1] = (uint8_t)(__ffs(full & ~(na | nl | nr)) - 1); return; }
+        ++d;
+        sa[d] = na; sl[d] = nl; sr[d] = nr; sc[d] = full & ~(na | nl | nr);
+    }
 }
 
 }  // namespace dq
