@@ -50,7 +50,7 @@ struct QueensLaneArgs {
 };
 
 constexpr int kQueensBlock = 256;
-constexpr int kQueensMaxN = 27;       // frame packs the depth above bit 27 of `a`
+constexpr int kQueensMaxN = 31;       // one spare bit so that ~(a|l|r) of a full board is still distinguishable
 
 // Phase A: validate items, count the nodes above the split, emit records.
 __global__ void __launch_bounds__(kQueensBlock)
@@ -105,23 +105,46 @@ k_queens_items(QueensLaneArgs A) {
     if (lane == 0 && tot_nodes) atomicAdd(A.totals + 1, tot_nodes);
 }
 
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+// PTX shifts clamp the amount (>= 32 gives 0), unlike C++ where it is undefined.
+__device__ __forceinline__ uint32_t shl_clamp(uint32_t x, uint32_t n) { uint32_t r; asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(n)); return r; }
+__device__ __forceinline__ uint32_t shr_clamp(uint32_t x, uint32_t n) { uint32_t r; asm("shr.u32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(n)); return r; }
+
 // Phase B: persistent lanes, DFS below each record.  Dynamic shared memory: uint4[levels][256].
+//
+// Register conventions in the hot loop:
+//   a   has every bit >= N permanently set, so a domain is a single ~(a|l|r) with no masking and the
+//       depth is popc(a) - (32 - N);
+//   the forward check walks the later variables from the LAST one backwards (t = 0 is variable N-1):
+//       its distance from the next variable is j = last - t, which goes "negative" for lanes that are
+//       deeper than the warp's shallowest lane; as an unsigned shift amount that clamps both diagonal
+//       terms to 0, so those extra rows see the non-empty ~a and pass — no per-row bounds test;
+//   the wipe-out test is an unsigned max over the rows' occupied masks (all ones <=> some domain is empty).
 __global__ void __launch_bounds__(kQueensBlock)
 k_queens_lane(QueensLaneArgs A) {
     extern __shared__ uint4 frames[];
     const int lane = threadIdx.x & 31;
     const uint32_t lt = (1u << lane) - 1u;
-    const int N = A.n, K = A.k;
-    const uint32_t full = (1u << N) - 1u;
+    const int N = A.n;
+    const uint32_t hi = ~((1u << N) - 1u);                       // bits >= N
+    const int dbias = 32 - N;
     const unsigned long long n_found = *A.n_records;
     const unsigned long long n_rec = n_found < A.record_cap ? n_found : A.record_cap;   // overflow: the host grows the list and reruns
-    uint4* const my_frames = frames + threadIdx.x;
+    const uint32_t fbase = (uint32_t)__cvta_generic_to_shared(frames + threadIdx.x);
+    constexpr uint32_t kLevelBytes = kQueensBlock * sizeof(uint4);
     unsigned long long tot_nodes = 0, tot_sols = 0;
 
     // per-lane search state
-    uint32_t a = 0, l = 0, r = 0, cand = 0, key = 0;
+    uint32_t a = 0xFFFFFFFFu, l = 0, r = 0, cand = 0, key = 0;
     uint32_t nodes = 0, sols = 0;
-    int d = 0, sp = 0;
+    uint32_t sp = fbase;                                         // shared-memory address of the next free frame
     bool have = false, done = false, item_found = false;
 
     for (;;) {
@@ -137,11 +160,11 @@ k_queens_lane(QueensLaneArgs A) {
                 if (rix >= n_rec) done = true;
                 else {
                     const uint4 rec = __ldg(A.records + rix);
-                    key = rec.x; a = rec.y; l = rec.z; r = rec.w;
+                    key = rec.x; a = rec.y | hi; l = rec.z; r = rec.w;
                     nodes = 0; sols = 0; item_found = false;
                     have = true;
-                    d = K; sp = 0;
-                    cand = full & ~(a | l | r);
+                    sp = fbase;
+                    cand = ~(a | l | r);
                 }
             }
             if (__all_sync(0xFFFFFFFFu, done && !have)) break;
@@ -149,38 +172,36 @@ k_queens_lane(QueensLaneArgs A) {
 
         // ---- every value tried at this depth: return to the nearest level with untried values ----
         if (have && cand == 0) {
-            if (sp == 0) {
+            if (sp == fbase) {
                 have = false;                                  // subtree exhausted (dequan.h:569-570 at the split depth)
                 tot_nodes += nodes; tot_sols += sols;
             } else {
-                --sp;
-                const uint4 f = my_frames[sp * kQueensBlock];
-                a = f.x & 0x07FFFFFFu; d = (int)(f.x >> 27); l = f.y; r = f.z; cand = f.w;
+                sp -= kLevelBytes;
+                const uint4 f = lds128(sp);
+                a = f.x; l = f.y; r = f.z; cand = f.w;
             }
         }
 
         // ---- AssignVar(next value) + forward check, all lanes converged ----
-        // The loop runs a warp-uniform number of rows (the deepest requirement among the lanes; a lane
-        // that needs fewer re-tests its last row) so the lanes leave it together.
         const bool trying = have && cand != 0;
         const uint32_t bit = cand & (0u - cand);
         const uint32_t na = a | bit, nl = (l | bit) << 1, nr = (r | bit) >> 1;
-        const int last = trying ? N - 2 - d : 0;
-        const int tmax = __reduce_max_sync(0xFFFFFFFFu, last);
-        const uint32_t na_hi = na | ~full;                     // bits >= N pre-set: "row empty" <=> word is all ones
-        bool wipe = false;
-#pragma unroll 2
-        for (int j = 0; j <= tmax; j++) {
-            const int je = min(j, last);
-            wipe |= (na_hi | (nl << je) | (nr >> je)) == 0xFFFFFFFFu;
+        const int last = N - 2 + dbias - __popc(a);              // later variables to check, minus one (d = popc(a) - dbias)
+        const int tmax = __reduce_max_sync(0xFFFFFFFFu, trying ? last : 0);
+        uint32_t occ_max = 0;                                    // max over rows of the occupied mask; all ones <=> an empty domain
+        uint32_t j = (uint32_t)last;
+#pragma unroll 4
+        for (int t = 0; t <= tmax; t++) {
+            occ_max = max(occ_max, na | shl_clamp(nl, j) | shr_clamp(nr, j));
+            --j;
         }
         if (trying) {
             cand ^= bit;
             ++nodes;
-            if (!wipe) {
+            if (occ_max != 0xFFFFFFFFu) {
                 if (last == 0) {
                     // the child is the last variable: its whole domain is nodes, each one a solution
-                    const int pc = __popc(full & ~(na | nl | nr));
+                    const int pc = __popc(~(na | nl | nr));
                     nodes += pc;
                     sols += pc;
                     if (!item_found) {
@@ -188,10 +209,9 @@ k_queens_lane(QueensLaneArgs A) {
                         if ((unsigned long long)key < *(volatile unsigned long long*)A.best_key) atomicMin(A.best_key, (unsigned long long)key);
                     }
                 } else {
-                    if (cand) { my_frames[sp * kQueensBlock] = make_uint4(a | ((uint32_t)d << 27), l, r, cand); ++sp; }
+                    if (cand) { sts128(sp, a, l, r, cand); sp += kLevelBytes; }
                     a = na; l = nl; r = nr;
-                    ++d;
-                    cand = full & ~(a | l | r);
+                    cand = ~(a | l | r);
                 }
             }
         }
