@@ -72,7 +72,7 @@ struct dq_model {
     unsigned long long last_n_prefix = 0;
     int last_part_rank = 0, last_part_count = 1;
     // lane engine scratch
-    DevBuf<uint4> q_records;
+    DevBuf<uint4> q_records, q_records2;
     DevBuf<uint8_t> q_first;
     uint8_t h_first[32] = {0};
     // batch scratch
@@ -121,7 +121,7 @@ static int upload(dq_model* m) {
     std::sort(sizes.begin(), sizes.end());
     m->n_sizes = (int)sizes.size();
     DQ_CUDA(up(m->d_sizes, sizes));
-    DQ_CUDA(m->d_ctrl.reserve(16));
+    DQ_CUDA(m->d_ctrl.reserve(32));
     m->uploaded = true;
     return DQ_OK;
 }
@@ -166,53 +166,61 @@ static int max_ctas_per_sm(K kernel, int threads, size_t smem, int* out) {
                                         : max_ctas_per_sm(KERNEL<false, false>, threads, smem, out)))
 
 
-// COUNT_ALL on a CLASS_QUEENS model with the lane-per-subtree engine: three kernels, no host round trip.
+// COUNT_ALL on a CLASS_QUEENS model with the lane-per-subtree engine: K level kernels + DFS + first-solution
+// kernel queued back to back, one host synchronisation at the end.
 static int solve_queens_lane(dq_model* m, const dq_tree_opts* opts, dq_tree_result* res, int32_t* first_solution) {
     const int N = m->cm.queens_n;
-    // split depth: as many digits as keep the item space <= 64M (validation stays a small fraction of the search)
+    // Split depth.  Measured on B200 (scripts/sweep_k.py, profiles/r1_queens_split_depth.txt): subtrees of a few
+    // hundred nodes keep the lanes busy without flooding the record list; that is depth 6 up to N=15 and 7 above.
     int K = 0;
-    unsigned long long items = 1;
-    const int kmax = std::min(N - 2, 12);
-    if (opts->split_depth > 0) {
-        K = std::min(opts->split_depth, kmax);
-        for (int i = 0; i < K; i++) items *= (unsigned long long)N;
-        if (items > (1ull << 27)) { g_err = "split_depth too deep for the item index"; return DQ_ERR_INVALID; }
-    } else {
-        while (K < kmax && items * (unsigned long long)N <= (64ull << 20)) { items *= (unsigned long long)N; K++; }
-    }
-    const int levels = std::max(N - 2 - K, 1);
-    const size_t smem = (size_t)levels * kQueensBlock * sizeof(uint4);
-    if (smem > 200 * 1024) { g_err = "board too large for the shared-memory stack"; return DQ_ERR_UNSUPPORTED; }
+    auto dfs_smem = [&](int k) { return (size_t)std::max(N - 2 - k, 1) * kQueensBlock * sizeof(uint4); };
+    // estimated FC-surviving prefixes per depth (sizes the record lists): each level multiplies by about N - 2.2*depth
+    auto estimate = [&](int k) { double e = 1; for (int i = 0; i < k; i++) e *= std::max(N - 2.2 * i, 2.0); return e; };
     int occ = 0;
-    int rc = max_ctas_per_sm(k_queens_lane, kQueensBlock, smem, &occ);
+    int rc = DQ_OK;
+    if (opts->split_depth > 0) K = std::min(opts->split_depth, std::min(N - 2, 12));
+    else K = std::max(std::min(N - 7, N <= 15 ? 6 : 7), 0);
+    auto key_space = [&](int k) { double keys = 1; for (int i = 0; i < k; i++) keys *= N; return keys; };
+    while (K > 0 && key_space(K) > 4.0e9) K--;               // prefix keys are 32-bit (res->split_depth_used reports K)
+    const size_t smem = dfs_smem(K);
+    if (smem > 200 * 1024) { g_err = "board too large for the shared-memory stack"; return DQ_ERR_UNSUPPORTED; }
+    rc = max_ctas_per_sm(k_queens_lane, kQueensBlock, smem, &occ);
     if (rc != DQ_OK) return rc;
     if (occ < 1) { g_err = "kernel does not fit an SM"; return DQ_ERR_UNSUPPORTED; }
-    const unsigned long long mine = (items + opts->part_count - 1 - opts->part_rank) / opts->part_count;
     const int ctas = occ * m->sm_count;
     DQ_CUDA(m->q_first.reserve(32));
-    size_t cap = std::max<size_t>(m->q_records.cap, (size_t)std::min<unsigned long long>(std::max<unsigned long long>(mine, 1), 1ull << 21));
-    unsigned long long h_ctrl[8];
-    unsigned long long* ctrl = m->d_ctrl.p;     // [0]=cursor [1]=sols [2]=nodes [3]=best [4]=n_records
+    DQ_CUDA(m->d_ctrl.reserve(32));
+    size_t cap = std::max<size_t>(m->q_records.cap, (size_t)std::min(std::max(2.0 * estimate(K), 1024.0), 64.0 * 1024 * 1024));
+    unsigned long long h_ctrl[32];
+    unsigned long long* ctrl = m->d_ctrl.p;     // [0]=cursor [1]=sols [2]=nodes [3]=best [8+l]=frontier size at depth l
     unsigned long long launches = 0;
     float ms_total = 0;
-    for (int attempt = 0; attempt < 2; attempt++) {
+    for (int attempt = 0; attempt < 3; attempt++) {
         DQ_CUDA(m->q_records.reserve(cap));
+        DQ_CUDA(m->q_records2.reserve(m->q_records.cap));
+        const size_t rcap = std::min(m->q_records.cap, m->q_records2.cap);
+        uint4* buf[2] = {m->q_records.p, m->q_records2.p};
         QueensLaneArgs A;
-        A.n = N; A.k = K; A.n_items = items;
-        A.div_magic = (unsigned int)(((1ull << 32) + N - 1) / N);
+        A.n = N; A.k = K;
         A.part_rank = opts->part_rank; A.part_count = opts->part_count;
-        A.records = m->q_records.p; A.record_cap = m->q_records.cap; A.n_records = ctrl + 4;
+        A.records = buf[K & 1]; A.record_cap = rcap; A.n_records = ctrl + 8 + K;
         A.cursor = ctrl + 0; A.totals = ctrl + 1; A.best_key = ctrl + 3;
         A.first_out = m->q_first.p;
-        const unsigned long long init[8] = {0, 0, 0, KEY_NONE, 0, 0, 0, 0};
+        unsigned long long init[32] = {0};
+        init[3] = KEY_NONE;
+        init[8] = (K > 0 || opts->part_rank == 0) ? 1 : 0;   // the root prefix (key 0) belongs to partition 0
+        const uint4 root = make_uint4(0, 0, 0, 0);
         DQ_CUDA(cudaMemcpyAsync(ctrl, init, sizeof init, cudaMemcpyHostToDevice, m->stream));
+        DQ_CUDA(cudaMemcpyAsync(buf[0], &root, sizeof root, cudaMemcpyHostToDevice, m->stream));
         DQ_CUDA(cudaEventRecord(m->ev0, m->stream));
-        const unsigned long long want_ctas = (mine + kQueensBlock - 1) / kQueensBlock;
-        const int grid_items = (int)std::min<unsigned long long>(std::max<unsigned long long>(want_ctas, 1), (unsigned long long)m->sm_count * 16);
-        k_queens_items<<<grid_items, kQueensBlock, 0, m->stream>>>(A);
+        for (int l = 0; l < K; l++) {
+            const int grid = (int)std::min<double>(std::max(estimate(l) * N / kQueensBlock, 1.0), (double)m->sm_count * 8);
+            k_queens_level<<<grid, kQueensBlock, 0, m->stream>>>(A, l, buf[l & 1], ctrl + 8 + l, buf[(l + 1) & 1], ctrl + 8 + l + 1,
+                                                                   opts->part_rank == 0 ? 1 : 0, (l == K - 1 && opts->part_count > 1) ? 1 : 0);
+        }
         k_queens_lane<<<ctas, kQueensBlock, smem, m->stream>>>(A);
         k_queens_first<<<1, 32, 0, m->stream>>>(A);
-        launches += 3;
+        launches += K + 2;
         DQ_CUDA(cudaGetLastError());
         DQ_CUDA(cudaEventRecord(m->ev1, m->stream));
         DQ_CUDA(cudaMemcpyAsync(h_ctrl, ctrl, sizeof h_ctrl, cudaMemcpyDeviceToHost, m->stream));
@@ -221,15 +229,18 @@ static int solve_queens_lane(dq_model* m, const dq_tree_opts* opts, dq_tree_resu
         float ms = 0;
         DQ_CUDA(cudaEventElapsedTime(&ms, m->ev0, m->ev1));
         ms_total += ms;
-        if (h_ctrl[4] <= m->q_records.cap) break;
-        cap = (size_t)h_ctrl[4];                 // record list overflowed: grow to the exact count and rerun
-        if (attempt == 1) { g_err = "internal: record list overflow persists"; return DQ_ERR_INTERNAL; }
+        unsigned long long biggest = 0;
+        for (int l = 0; l <= K; l++) biggest = std::max(biggest, h_ctrl[8 + l]);
+        if (biggest <= rcap) break;
+        // a frontier overflowed its list: grow (the last level's count is exact only if the earlier ones fitted) and rerun
+        cap = (size_t)std::max<unsigned long long>(biggest, 2 * rcap);
+        if (attempt == 2) { g_err = "internal: record list overflow persists"; return DQ_ERR_INTERNAL; }
     }
     res->kernel_ms = ms_total;
     res->kernel_launches = launches;
     res->engine_used = DQ_ENGINE_LANE;
     res->split_depth_used = K;
-    res->n_prefixes = (int32_t)std::min<unsigned long long>(h_ctrl[4], 0x7FFFFFFF);
+    res->n_prefixes = (int32_t)std::min<unsigned long long>(h_ctrl[8 + K], 0x7FFFFFFF);
     res->n_solutions = h_ctrl[1];
     res->n_nodes = h_ctrl[2];
     res->first_key = h_ctrl[3];
@@ -282,7 +293,7 @@ void dq_free(dq_model* m) {
         m->d_ent.release(); m->d_order.release(); m->d_pos.release(); m->d_cell_lut.release();
         m->d_values.release(); m->d_sizes.release(); m->d_ctrl.release();
         m->d_sub_nodes.release(); m->d_sol_key.release(); m->d_sol.release();
-        m->q_records.release(); m->q_first.release();
+        m->q_records.release(); m->q_records2.release(); m->q_first.release();
         m->b_cells.release(); m->b_solution.release(); m->b_status.release(); m->b_nodes.release();
         for (auto& l : m->levels) {
             l.dmask.release(); l.surv.release(); l.child_off.release(); l.parent_of.release();

@@ -18,17 +18,18 @@
 // conflict-free.  A frame is written only when the level still has untried values, so a pop always
 // lands on a level with work (the saved-domain restore of dequan.h:431-440 becomes one 16-byte load).
 //
-// Work distribution, two kernels and no host round trip in between:
-//   k_queens_items : item j is the base-N number whose k digits are the values of the first k
-//                    variables.  One lane per item decodes it and replays the k assignments with
-//                    forward checking; a surviving item is appended (warp-aggregated atomic) to a
-//                    record list in HBM {key, a, l, r}.  A node above the split is counted by the
-//                    single item that extends it with zeros, so the node total stays exact.
-//   k_queens_lane  : persistent lanes pull records (one coalesced 16-byte load per lane) and run
-//                    the DFS below them.
+// Work distribution, a queue of kernels with no host round trip in between:
+//   k_queens_level : one launch per level above the split depth k.  The frontier is a record list
+//                    in HBM {key, a, l, r}; key is the base-N number formed by the prefix values,
+//                    i.e. the DFS order of the prefix.  One lane per (record, value) pair: a value
+//                    of the current domain is a node; a surviving child is appended to the next
+//                    frontier with a warp-aggregated atomic.
+//   k_queens_lane  : persistent lanes pull depth-k records (one coalesced 16-byte load per lane)
+//                    and run the DFS below them.
 //   k_queens_first : one lane re-walks the lowest-keyed item that holds a solution and writes the
 //                    DFS-first solution (keeps solution bookkeeping out of the hot loop).
-// Items are dealt round-robin to partitions (multi-GPU): partition r owns items j = r (mod parts).
+// Depth-k prefixes are dealt to partitions (multi-GPU) by key: partition r owns keys = r (mod parts);
+// the levels above the split are expanded by every partition and counted by partition 0 only.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -36,13 +37,11 @@
 namespace dq {
 
 struct QueensLaneArgs {
-    int n, k;                         // board size; digits (split depth) per item
-    unsigned long long n_items;       // n^k  (<= 2^27)
-    unsigned int div_magic;           // ceil(2^32 / n): x / n == umulhi(x, magic) for x < 2^27, 2 <= n <= 32
+    int n, k;                         // board size; split depth
     int part_rank, part_count;
     uint4* records;                   // [record_cap] {key, a, l, r}: one FC-surviving prefix = one subtree
     unsigned long long record_cap;
-    unsigned long long* n_records;    // valid items found (may exceed record_cap: then the host grows and reruns)
+    unsigned long long* n_records;    // depth-k records found (may exceed record_cap: then the host grows and reruns)
     unsigned long long* cursor;       // next record to search
     unsigned long long* totals;       // [0] solutions, [1] nodes
     unsigned long long* best_key;     // lowest item index that holds a solution
@@ -52,57 +51,58 @@ struct QueensLaneArgs {
 constexpr int kQueensBlock = 256;
 constexpr int kQueensMaxN = 31;       // one spare bit so that ~(a|l|r) of a full board is still distinguishable
 
-// Phase A: validate items, count the nodes above the split, emit records.
+// Phase A, one launch per level above the split: every lane takes one (record, value) pair of the
+// current frontier, and if the value is in the record's current domain it is a node (AssignVar);
+// if its forward check leaves no later domain empty the child record is appended (warp-aggregated
+// atomic) to the next frontier.  The launches are queued back to back: the frontier sizes never
+// come back to the host.  On the last level only the children this partition owns are kept.
 __global__ void __launch_bounds__(kQueensBlock)
-k_queens_items(QueensLaneArgs A) {
+k_queens_level(QueensLaneArgs A, int level, const uint4* __restrict__ in, const unsigned long long* __restrict__ n_in_ptr,
+               uint4* __restrict__ out, unsigned long long* __restrict__ n_out_ptr, int count_nodes, int filter_partition) {
     const int lane = threadIdx.x & 31;
     const uint32_t lt = (1u << lane) - 1u;
-    const int N = A.n, K = A.k;
+    const int N = A.n;
     const uint32_t full = (1u << N) - 1u;
-    const unsigned long long mine = (A.n_items + A.part_count - 1 - A.part_rank) / A.part_count;   // items of this partition
+    const unsigned long long n_in = min(*n_in_ptr, A.record_cap);
+    const unsigned long long pairs = n_in * (unsigned long long)N;
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     unsigned long long tot_nodes = 0;
-    // uniform trip count per warp so the warp-aggregated append below stays convergent
     const unsigned long long first = (unsigned long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31);
-    for (unsigned long long base = first; base < mine; base += stride) {
-        const unsigned long long ord = base + lane;
-        bool valid = ord < mine;
-        uint32_t a = 0, l = 0, r = 0, nodes = 0;
-        const unsigned long long key = ord * (unsigned long long)A.part_count + (unsigned long long)A.part_rank;
+    for (unsigned long long base = first; base < pairs; base += stride) {      // warp-uniform trip count
+        const unsigned long long p = base + lane;
+        bool valid = p < pairs;
+        uint32_t key = 0, a = 0, l = 0, r = 0;
         if (valid) {
-            // digits of the item, level 0 = most significant, packed 5 bits per level
-            uint32_t rem = (uint32_t)key;
-            unsigned long long dg = 0;
-            for (int t = K - 1; t >= 0; t--) {
-                const uint32_t q = __umulhi(rem, A.div_magic);
-                dg |= (unsigned long long)(rem - q * N) << (5 * t);
-                rem = q;
-            }
-            for (int i = 0; i < K; i++) {
-                const uint32_t bit = 1u << ((dg >> (5 * i)) & 31);
-                if (!(full & ~(a | l | r) & bit)) { valid = false; break; }          // value not in the current domain: no node
-                if ((dg >> (5 * (i + 1))) == 0) ++nodes;                             // this item is the node's representative
-                a |= bit;
-                l = (l | bit) << 1;
-                r = (r | bit) >> 1;
+            const uint32_t rix = (uint32_t)p / (uint32_t)N;                    // pairs < 2^32 (host caps the record list)
+            const uint32_t v = (uint32_t)p - rix * N;
+            const uint4 rec = __ldg(in + rix);
+            const uint32_t bit = 1u << v;
+            valid = (full & ~(rec.y | rec.z | rec.w) & bit) != 0;               // value in the current domain
+            if (valid) {
+                ++tot_nodes;
+                key = rec.x * N + v;
+                a = rec.y | bit;
+                l = (rec.z | bit) << 1;
+                r = (rec.w | bit) >> 1;
                 const uint32_t ah = a | ~full;
-                for (int j = 0; j <= N - 2 - i; j++)
+                for (int j = 0; j <= N - 2 - level; j++)
                     if ((ah | (l << j) | (r >> j)) == 0xFFFFFFFFu) { valid = false; break; }   // wipe-out
-                if (!valid) break;
+                if (valid && filter_partition) valid = (key % (uint32_t)A.part_count) == (uint32_t)A.part_rank;
             }
-            tot_nodes += nodes;
         }
         const uint32_t m = __ballot_sync(0xFFFFFFFFu, valid);
         if (m) {
             unsigned long long slot = 0;
             const int leader = __ffs(m) - 1;
-            if (lane == leader) slot = atomicAdd(A.n_records, (unsigned long long)__popc(m));
+            if (lane == leader) slot = atomicAdd(n_out_ptr, (unsigned long long)__popc(m));
             slot = __shfl_sync(0xFFFFFFFFu, slot, leader) + __popc(m & lt);
-            if (valid && slot < A.record_cap) A.records[slot] = make_uint4((uint32_t)key, a, l, r);
+            if (valid && slot < A.record_cap) out[slot] = make_uint4(key, a, l, r);
         }
     }
-    for (int o = 16; o > 0; o >>= 1) tot_nodes += __shfl_down_sync(0xFFFFFFFFu, tot_nodes, o);
-    if (lane == 0 && tot_nodes) atomicAdd(A.totals + 1, tot_nodes);
+    if (count_nodes) {
+        for (int o = 16; o > 0; o >>= 1) tot_nodes += __shfl_down_sync(0xFFFFFFFFu, tot_nodes, o);
+        if (lane == 0 && tot_nodes) atomicAdd(A.totals + 1, tot_nodes);
+    }
 }
 
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
@@ -146,27 +146,48 @@ k_queens_lane(QueensLaneArgs A) {
     uint32_t nodes = 0, sols = 0;
     uint32_t sp = fbase;                                         // shared-memory address of the next free frame
     bool have = false, done = false, item_found = false;
+    // warp-uniform work-distribution state
+    unsigned long long chunk_pos = 0, chunk_end = 0;
+    bool exhausted = false;
+    const unsigned long long total_warps = (unsigned long long)gridDim.x * (kQueensBlock / 32);
 
     for (;;) {
         // ---- refill: lanes without a subtree take the next records ----
+        // The warp owns a chunk [chunk_pos, chunk_end) of the record list and hands it out lane by lane;
+        // an empty chunk is refilled with ONE atomic whose size follows guided self-scheduling
+        // (remaining / (4 * warps), at most 256), so the shared cursor sees thousands of atomics instead
+        // of one per record while the tail stays balanced.
         const uint32_t need = __ballot_sync(0xFFFFFFFFu, !have && !done);
         if (need) {
-            unsigned long long base = 0;
-            const int leader = __ffs(need) - 1;
-            if (lane == leader) base = atomicAdd(A.cursor, (unsigned long long)__popc(need));
-            base = __shfl_sync(0xFFFFFFFFu, base, leader);
+            const uint32_t n_need = __popc(need);
+            if (chunk_pos >= chunk_end && !exhausted) {
+                unsigned long long base = 0;
+                uint32_t size = 0;
+                if (lane == 0) {
+                    const unsigned long long cur = *(volatile unsigned long long*)A.cursor;
+                    const unsigned long long remaining = cur < n_rec ? n_rec - cur : 0;
+                    size = (uint32_t)min(max(remaining / (4ull * total_warps), (unsigned long long)n_need), 256ull);
+                    base = atomicAdd(A.cursor, (unsigned long long)size);
+                }
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                size = __shfl_sync(0xFFFFFFFFu, size, 0);
+                chunk_pos = base;
+                chunk_end = min(base + size, n_rec);
+                if (base >= n_rec) { exhausted = true; chunk_end = chunk_pos; }
+            }
+            const unsigned long long avail = chunk_end - chunk_pos;
             if (!have && !done) {
-                const unsigned long long rix = base + __popc(need & lt);
-                if (rix >= n_rec) done = true;
-                else {
-                    const uint4 rec = __ldg(A.records + rix);
+                const uint32_t rank = __popc(need & lt);
+                if (rank < avail) {
+                    const uint4 rec = __ldg(A.records + chunk_pos + rank);
                     key = rec.x; a = rec.y | hi; l = rec.z; r = rec.w;
                     nodes = 0; sols = 0; item_found = false;
                     have = true;
                     sp = fbase;
                     cand = ~(a | l | r);
-                }
+                } else if (exhausted) done = true;
             }
+            chunk_pos += min((unsigned long long)n_need, avail);
             if (__all_sync(0xFFFFFFFFu, done && !have)) break;
         }
 
@@ -239,7 +260,7 @@ __global__ void k_queens_first(QueensLaneArgs A) {
     uint8_t* out = A.first_out;
     uint32_t a = 0, l = 0, r = 0, rem = (uint32_t)best;
     for (int t = K - 1; t >= 0; t--) {
-        const uint32_t q = __umulhi(rem, A.div_magic);
+        const uint32_t q = rem / (uint32_t)N;
         out[t] = (uint8_t)(rem - q * N);
         rem = q;
     }

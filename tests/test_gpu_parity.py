@@ -54,6 +54,10 @@ def test_reference_scenarios(golden, product_lib):
 def test_nqueens_count_and_first(golden, product_lib, engine, n):
     g = golden["nqueens"][str(n)]
     m = api.Model(nqueens(n))
+    if engine == "lane" and n < 2:
+        with pytest.raises(api.DequanError):   # a single variable has no queens structure to recognise
+            m.solve_tree("count", engine=engine)
+        return
     c = m.solve_tree("count", engine=engine)
     assert (c.solutions, c.nodes, c.first) == (g["count"]["solutions"], g["count"]["nodes"], g["count"]["first"]), c
     if engine == "lane":
