@@ -90,6 +90,15 @@ int compile_model(const dq_model_desc* d, CompiledModel& M, std::string& err) {
     std::stable_sort(M.order.begin(), M.order.end(), [&](int a, int b) {
         return M.values[a].size() < M.values[b].size();
     });
+    if (d->assign_order) {                                // caller-supplied Assignment::assign_order (dequan.h:316)
+        std::vector<char> seen(nv, 0);
+        for (int p = 0; p < nv; p++) {
+            const int v = d->assign_order[p];
+            if (v < 0 || v >= nv || seen[v]) { err = "assign_order is not a permutation of the variable ids"; return DQ_ERR_INVALID; }
+            seen[v] = 1;
+            M.order[p] = v;
+        }
+    }
     M.pos_of.resize(nv);
     for (int p = 0; p < nv; p++) M.pos_of[M.order[p]] = p;
     {

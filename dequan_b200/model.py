@@ -126,6 +126,7 @@ class dq_model_desc(C.Structure):  # include/dequan_b200.h
         ("con_kind", C.POINTER(C.c_int32)),
         ("con_off", C.POINTER(C.c_int32)),
         ("con_data", C.POINTER(C.c_int32)),
+        ("assign_order", C.POINTER(C.c_int32)),
     ]
 
 
@@ -133,6 +134,7 @@ class dq_model_desc(C.Structure):  # include/dequan_b200.h
 class CSP:  # dequan.h:328-355
     domains: List[Domain] = field(default_factory=list)
     constraints: list = field(default_factory=list)
+    assign_order: List[int] = None  # explicit Assignment::assign_order (dequan.h:316); None = Reset's sort
 
     def AddIntVar(self, a, b=None) -> int:  # dequan.h:454-466
         if b is None:
@@ -180,8 +182,13 @@ class CSP:  # dequan.h:328-355
         """Returns (dq_model_desc, keepalive) — keepalive owns the numpy buffers."""
         arrs = self.arrays()
         p = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+        order = None
+        if self.assign_order is not None:
+            order = np.array(self.assign_order, dtype=np.int32)
+            arrs = arrs + (order,)
         d = dq_model_desc(len(self.domains), p(arrs[0]), p(arrs[1]), p(arrs[2]),
-                          len(self.constraints), p(arrs[3]), p(arrs[4]), p(arrs[5]))
+                          len(self.constraints), p(arrs[3]), p(arrs[4]), p(arrs[5]),
+                          p(order) if order is not None else None)
         return d, arrs
 
     def to_text(self) -> str:

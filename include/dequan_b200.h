@@ -85,6 +85,10 @@ typedef struct dq_model_desc {
     const int32_t *con_kind;   /* [n_cons]   dq_con_kind                          */
     const int32_t *con_off;    /* [n_cons+1] offsets into con_data                */
     const int32_t *con_data;   /* flat constraint payloads, see dq_con_kind       */
+    const int32_t *assign_order; /* optional [n_vars] permutation of the var ids =
+                                  Assignment::assign_order (dequan.h:316) when the
+                                  caller supplies its own; NULL = the order
+                                  Assignment::Reset computes (dequan.h:376-394)      */
 } dq_model_desc;
 
 /* ---- options / results ---------------------------------------------------- */

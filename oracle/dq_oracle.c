@@ -415,6 +415,8 @@ int dqo_solve(const dq_model_desc *m, const dqo_opts *o, dqo_result *res,
     }
     link_vars(&s);
     reset_assignment(&s);
+    if (m->assign_order)   /* a caller-edited Assignment::assign_order (public field, dequan.h:316) */
+        for (int i = 0; i < s.nv; i++) s.order[i] = m->assign_order[i];
     s.count_all = o->mode == DQ_MODE_COUNT_ALL;
     s.budget = o->node_budget;
     s.first = first;

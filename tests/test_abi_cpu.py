@@ -100,3 +100,16 @@ def test_product_does_not_touch_oracle():
                 txt = open(os.path.join(dirpath, f)).read()
                 for needle in ("libdq_oracle", "oracle_lib", "dqo_solve", "dequan_ref", "dq_oracle.c", "import oracle"):
                     assert needle not in txt, (f, needle)
+
+
+def test_explicit_assign_order_is_validated_and_kept():
+    from dequan_b200 import api
+    from dequan_b200.model import nqueens
+    csp = nqueens(5)
+    csp.assign_order = [4, 3, 2, 1, 0]
+    assert api.Model(csp).order() == [4, 3, 2, 1, 0]
+    assert O.solve(csp, "count").order == [4, 3, 2, 1, 0]
+    assert O.solve(csp, "count").solutions == 10
+    csp.assign_order = [0, 1, 1, 2, 3]
+    with pytest.raises(api.DequanError):
+        api.Model(csp)

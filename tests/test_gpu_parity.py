@@ -260,3 +260,17 @@ def test_lane_engine_larger_boards(product_lib, n, k):
 def test_int_peak_microbenchmark(product_lib):
     ops, ms = api.measure_int_peak()
     assert 5e12 < ops < 4e13, ops
+
+
+def test_caller_supplied_assign_order_vs_oracle(product_lib):
+    """Assignment::assign_order is a public field (dequan.h:316): a caller-edited order reaches the engine."""
+    import random
+    for seed in range(7000, 7040):
+        csp = random_model(seed, n_vars=9, n_cons=14, max_dom=6)
+        order = list(range(9))
+        random.Random(seed).shuffle(order)
+        csp.assign_order = order
+        m = api.Model(csp)
+        assert m.order() == order
+        for mode in ("first", "count"):
+            _cmp_tree(m.solve_tree(mode), O.solve(csp, mode), (seed, mode))
