@@ -22,7 +22,7 @@ DQ_MODE_FIRST, DQ_MODE_COUNT_ALL = 0, 1
 ENGINE = {"auto": 0, "warp": 1, "lane": 2}
 ENGINE_NAME = {v: k for k, v in ENGINE.items()}
 OUTCOME = {0: "unsat", 1: "sat", 2: "budget", 3: "invalid"}
-MODEL_CLASS = {0: "generic", 1: "ne_same", 2: "queens"}
+MODEL_CLASS = {0: "generic", 1: "ne_same", 2: "queens", 3: "sudoku9"}
 
 
 class DequanError(RuntimeError):
@@ -43,7 +43,7 @@ class dq_tree_result(C.Structure):
 
 
 class dq_batch_opts(C.Structure):
-    _fields_ = [("node_budget", C.c_uint64), ("engine", C.c_int32), ("reserved", C.c_int32)]
+    _fields_ = [("node_budget", C.c_uint64), ("engine", C.c_int32), ("task_nodes", C.c_int32)]
 
 
 class dq_batch_stats(C.Structure):
@@ -198,7 +198,7 @@ class Model:
         return n.value
 
     def solve_batch_cells(self, cells: np.ndarray, node_budget: int = 0, engine: str = "auto",
-                          out: Optional[tuple] = None) -> BatchResult:
+                          out: Optional[tuple] = None, task_nodes: int = 0) -> BatchResult:
         """cells: uint8[n, stride] host array (0 = keep template domain)."""
         assert cells.dtype == np.uint8 and cells.ndim == 2 and cells.flags.c_contiguous
         n, stride = cells.shape
@@ -208,7 +208,7 @@ class Model:
             status = np.zeros(n, dtype=np.uint8)
         else:
             sol, nodes, status = out
-        o = dq_batch_opts(node_budget, ENGINE[engine], 0)
+        o = dq_batch_opts(node_budget, ENGINE[engine], task_nodes)
         st = dq_batch_stats()
         _check(lib().dq_solve_batch_cells(self._h, cells.ctypes.data, n, stride, C.byref(o), sol.ctypes.data,
                                           nodes.ctypes.data, status.ctypes.data, C.byref(st)))
@@ -216,9 +216,9 @@ class Model:
                            st.kernel_launches, st.h2d_bytes, st.d2h_bytes)
 
     def solve_batch_cells_ptr(self, cells_ptr: int, n: int, stride: int, sol_ptr: int, nodes_ptr: int, status_ptr: int,
-                              node_budget: int = 0, engine: str = "auto", device: bool = False):
+                              node_budget: int = 0, engine: str = "auto", device: bool = False, task_nodes: int = 0):
         """Raw-pointer form (pinned host buffers or, with device=True, HBM-resident buffers)."""
-        o = dq_batch_opts(node_budget, ENGINE[engine], 0)
+        o = dq_batch_opts(node_budget, ENGINE[engine], task_nodes)
         st = dq_batch_stats()
         fn = lib().dq_solve_batch_cells_dev if device else lib().dq_solve_batch_cells
         _check(fn(self._h, cells_ptr, n, stride, C.byref(o), sol_ptr, nodes_ptr, status_ptr, C.byref(st)))

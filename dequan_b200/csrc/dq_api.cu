@@ -3,6 +3,7 @@
 // gathering.  No search runs on the CPU; every solve needs a CUDA device.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -10,6 +11,7 @@
 #include "dequan_b200.h"
 #include "dq_kernels.cuh"
 #include "dq_lane_queens.cuh"
+#include "dq_lane_sudoku.cuh"
 #include "dq_model.hpp"
 
 namespace dq {
@@ -78,6 +80,13 @@ struct dq_model {
     // batch scratch
     DevBuf<uint8_t> b_cells, b_solution, b_status;
     DevBuf<unsigned long long> b_nodes;
+    // sudoku lane engine scratch (task pool)
+    DevBuf<SudokuDigest> s_digest;
+    DevBuf<unsigned long long> s_best, s_piece_nodes, s_ctrl;
+    DevBuf<SudokuPiece> s_pieces;
+    DevBuf<uint4> s_snaps;
+    DevBuf<uint8_t> s_piece_sol, s_piece_found;
+    DevBuf<int> s_deferred;
 };
 
 namespace dq {
@@ -295,6 +304,9 @@ void dq_free(dq_model* m) {
         m->d_sub_nodes.release(); m->d_sol_key.release(); m->d_sol.release();
         m->q_records.release(); m->q_records2.release(); m->q_first.release();
         m->b_cells.release(); m->b_solution.release(); m->b_status.release(); m->b_nodes.release();
+        m->s_digest.release(); m->s_best.release(); m->s_piece_nodes.release(); m->s_ctrl.release();
+        m->s_pieces.release(); m->s_snaps.release(); m->s_piece_sol.release(); m->s_piece_found.release();
+        m->s_deferred.release();
         for (auto& l : m->levels) {
             l.dmask.release(); l.surv.release(); l.child_off.release(); l.parent_of.release();
             l.node_off.release(); l.prefixes.release();
@@ -514,8 +526,17 @@ int dq_tree_nodes_upto(dq_model* m, uint64_t key, uint64_t* nodes) {
     return DQ_OK;
 }
 
+static int run_batch_sudoku(dq_model* m, const uint8_t* cells_dev, int64_t n, int32_t stride, const dq_batch_opts* opts,
+                            uint8_t* sol_dev, unsigned long long* nodes_dev, uint8_t* status_dev, dq_batch_stats* st);
+
 static int run_batch_cells(dq_model* m, const uint8_t* cells_dev, int64_t n, int32_t stride, const dq_batch_opts* opts,
-                           uint8_t* sol_dev, unsigned long long* nodes_dev, uint8_t* status_dev, dq_batch_stats* st) {
+                           uint8_t* sol_dev, unsigned long long* nodes_dev, uint8_t* status_dev, dq_batch_stats* st,
+                           const int* idx_list = nullptr, bool timed = true) {
+    if (!idx_list && m->cm.model_class == CLASS_SUDOKU9 && !(opts && opts->engine == DQ_ENGINE_WARP))
+        return run_batch_sudoku(m, cells_dev, n, stride, opts, sol_dev, nodes_dev, status_dev, st);
+    if (opts && opts->engine == DQ_ENGINE_LANE && m->cm.model_class != CLASS_SUDOKU9) {
+        g_err = "the lane batch engine serves the 9x9 Sudoku class only"; return DQ_ERR_UNSUPPORTED;
+    }
     const int nv = m->cm.nv;
     const TreeModelDev M = dev_model(m);
     const size_t smem = warp_state_bytes(nv, M.trail) * kWarpsPerCta;
@@ -527,14 +548,16 @@ static int run_batch_cells(dq_model* m, const uint8_t* cells_dev, int64_t n, int
     unsigned long long* ctrl = m->d_ctrl.p;
     DQ_CUDA(cudaMemsetAsync(ctrl, 0, 8 * sizeof(unsigned long long), m->stream));
     BatchCellsArgs A;
+    A.idx_list = idx_list;
     A.cells = cells_dev; A.n = n; A.stride = stride; A.cell_lut = m->d_cell_lut.p; A.values = m->d_values.p;
     A.sizes = m->d_sizes.p; A.n_sizes = m->n_sizes; A.budget = opts ? opts->node_budget : 0;
     A.cursor = ctrl; A.solution = sol_dev; A.nodes = nodes_dev; A.status = status_dev; A.totals = ctrl + 1;
     long long ctas = std::min<long long>((n + kWarpsPerCta - 1) / kWarpsPerCta, (long long)occ * m->sm_count);
     if (ctas < 1) ctas = 1;
-    DQ_CUDA(cudaEventRecord(m->ev0, m->stream));
+    if (timed) DQ_CUDA(cudaEventRecord(m->ev0, m->stream));
     DQ_DISPATCH(m, k_batch_cells, (int)ctas, kWarpsPerCta * 32, smem, m->stream, M, A);
     DQ_CUDA(cudaGetLastError());
+    if (!timed) return DQ_OK;
     DQ_CUDA(cudaEventRecord(m->ev1, m->stream));
     unsigned long long h[8];
     DQ_CUDA(cudaMemcpyAsync(h, ctrl, sizeof h, cudaMemcpyDeviceToHost, m->stream));
@@ -544,6 +567,84 @@ static int run_batch_cells(dq_model* m, const uint8_t* cells_dev, int64_t n, int
         DQ_CUDA(cudaEventElapsedTime(&ms, m->ev0, m->ev1));
         st->n_sat = h[1]; st->n_unsat = h[2]; st->n_budget = h[3]; st->total_nodes = h[4];
         st->kernel_ms = ms; st->kernel_launches = 1;
+    }
+    return DQ_OK;
+}
+
+// Batch of 9x9 Sudoku on the lane-per-instance engine (dq_lane_sudoku.cuh): digest pass, search rounds until the
+// task pool is drained, accounting passes; instances the digest cannot take (clashing givens, foreign bytes) go
+// through the generic warp engine.
+static int run_batch_sudoku(dq_model* m, const uint8_t* cells_dev, int64_t n, int32_t stride, const dq_batch_opts* opts,
+                            uint8_t* sol_dev, unsigned long long* nodes_dev, uint8_t* status_dev, dq_batch_stats* st) {
+    const size_t smem = sizeof(SudokuSmem);
+    int occ = 0;
+    int rc = max_ctas_per_sm(k_sudoku_lane, kSudokuBlock, smem, &occ);
+    if (rc != DQ_OK) return rc;
+    if (occ < 1) { g_err = "kernel does not fit an SM"; return DQ_ERR_UNSUPPORTED; }
+    const unsigned long long piece_cap = std::max<unsigned long long>(1u << 16, std::min<unsigned long long>(4ull * n, 1ull << 24));
+    const unsigned long long snap_cap = piece_cap / 2;
+    DQ_CUDA(m->s_digest.reserve(n)); DQ_CUDA(m->s_best.reserve(n)); DQ_CUDA(m->s_ctrl.reserve(16));
+    DQ_CUDA(m->s_pieces.reserve(piece_cap)); DQ_CUDA(m->s_snaps.reserve(snap_cap * kSnapWords));
+    DQ_CUDA(m->s_piece_nodes.reserve(piece_cap)); DQ_CUDA(m->s_piece_found.reserve(piece_cap));
+    DQ_CUDA(m->s_piece_sol.reserve(piece_cap * 81));
+    unsigned long long* ctrl = m->s_ctrl.p;       // [0] cursor [1] piece tail [2] snapshot tail [3] round begin [4] round end [8..11] totals [12] deferred
+    DQ_CUDA(cudaMemsetAsync(ctrl, 0, 16 * sizeof(unsigned long long), m->stream));
+    SudokuArgs A;
+    A.digest = m->s_digest.p; A.n = n; A.stride = stride; A.cells = cells_dev; A.solution = sol_dev; A.nodes = nodes_dev;
+    A.status = status_dev; A.best_key = m->s_best.p; A.pieces = m->s_pieces.p; A.piece_cap = piece_cap;
+    A.snaps = m->s_snaps.p; A.snap_cap = snap_cap; A.piece_nodes = m->s_piece_nodes.p; A.piece_sol = m->s_piece_sol.p;
+    A.piece_found = m->s_piece_found.p; A.ctrl = ctrl; A.user_budget = opts ? opts->node_budget : 0;
+    const unsigned budget0 = opts && opts->task_nodes > 0 ? (unsigned)opts->task_nodes : 8192u;
+    unsigned long long launches = 0;
+    DQ_CUDA(cudaEventRecord(m->ev0, m->stream));
+    k_sudoku_digest<<<(unsigned)((n + 127) / 128), 128, 128 * 81, m->stream>>>(cells_dev, n, stride, m->s_digest.p, m->s_best.p);
+    launches++;
+    const long long resident = (long long)occ * m->sm_count;
+    unsigned long long seg_begin = 0, seg_end = 0;
+    for (int round = 0; round < 4096; round++) {
+        const unsigned long long tasks = round == 0 ? (unsigned long long)n : seg_end - seg_begin;
+        A.round = round;
+        A.budget = round < 64 ? budget0 : 0xFFFFFFFFu;            // past 64 rounds: stop splitting, run the leftovers out
+        const long long ctas = std::max<long long>(1, std::min<long long>(resident, (long long)((tasks + kSudokuBlock - 1) / kSudokuBlock)));
+        k_sudoku_lane<<<(unsigned)ctas, kSudokuBlock, smem, m->stream>>>(A);
+        launches++;
+        DQ_CUDA(cudaGetLastError());
+        unsigned long long h[3];
+        DQ_CUDA(cudaMemcpyAsync(h, ctrl, sizeof h, cudaMemcpyDeviceToHost, m->stream));
+        DQ_CUDA(cudaStreamSynchronize(m->stream));
+        const unsigned long long tail = std::min(h[1], piece_cap);
+        if (tail == seg_end) break;                                 // no new pieces: every task ran to its end
+        seg_begin = seg_end; seg_end = tail;
+        const unsigned long long next[5] = {0, h[1], h[2], seg_begin, seg_end};
+        DQ_CUDA(cudaMemcpyAsync(ctrl, next, sizeof next, cudaMemcpyHostToDevice, m->stream));
+    }
+    if (seg_end) { k_sudoku_account<<<(unsigned)((seg_end + 255) / 256), 256, 0, m->stream>>>(A, seg_end); launches++; }
+    k_sudoku_finish<<<(unsigned)((n + 255) / 256), 256, 0, m->stream>>>(A, ctrl + 8);
+    DQ_CUDA(m->s_deferred.reserve(n));
+    k_sudoku_collect_deferred<<<(unsigned)((n + 255) / 256), 256, 0, m->stream>>>(status_dev, n, m->s_deferred.p, ctrl + 12);
+    launches += 2;
+    DQ_CUDA(cudaGetLastError());
+    unsigned long long n_def = 0;
+    DQ_CUDA(cudaMemcpyAsync(&n_def, ctrl + 12, sizeof n_def, cudaMemcpyDeviceToHost, m->stream));
+    DQ_CUDA(cudaStreamSynchronize(m->stream));
+    unsigned long long hw[8] = {0};
+    if (n_def) {
+        dq_batch_opts o2 = opts ? *opts : dq_batch_opts{0, 0, 0};
+        o2.engine = DQ_ENGINE_WARP;
+        rc = run_batch_cells(m, cells_dev, (int64_t)n_def, stride, &o2, sol_dev, nodes_dev, status_dev, nullptr, m->s_deferred.p, false);
+        if (rc != DQ_OK) return rc;
+        launches++;
+    }
+    DQ_CUDA(cudaEventRecord(m->ev1, m->stream));
+    unsigned long long ht[4];
+    DQ_CUDA(cudaMemcpyAsync(ht, ctrl + 8, sizeof ht, cudaMemcpyDeviceToHost, m->stream));
+    if (n_def) DQ_CUDA(cudaMemcpyAsync(hw, m->d_ctrl.p, sizeof hw, cudaMemcpyDeviceToHost, m->stream));
+    DQ_CUDA(cudaStreamSynchronize(m->stream));
+    if (st) {
+        float ms = 0;
+        DQ_CUDA(cudaEventElapsedTime(&ms, m->ev0, m->ev1));
+        st->n_sat = ht[0] + hw[1]; st->n_unsat = ht[1] + hw[2]; st->n_budget = ht[2] + hw[3]; st->total_nodes = ht[3] + hw[4];
+        st->kernel_ms = ms; st->kernel_launches = launches;
     }
     return DQ_OK;
 }

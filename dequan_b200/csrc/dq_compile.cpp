@@ -286,6 +286,30 @@ int compile_model(const dq_model_desc* d, CompiledModel& M, std::string& err) {
         }
         if (queens && nv >= 2) { M.model_class = CLASS_QUEENS; M.queens_n = nv; }
     }
+    // 9x9 Sudoku template: every variable on 1..9 (ascending), every arc a plain "different value", and the
+    // neighbours of cell (r,c) exactly its row, column and box — whichever mix of binary NotEqual and
+    // AllDifferent rows the user wrote (test/main-test.cpp:130-148 plus the boxes).
+    if (M.model_class == CLASS_NE_SAME && nv == 81 && !d->assign_order) {
+        bool sudoku = true;
+        for (int v = 0; v < nv && sudoku; v++) {
+            sudoku = M.values[v].size() == 9;
+            for (int b = 0; b < 9 && sudoku; b++) sudoku = M.values[v][b] == b + 1;
+        }
+        for (int x = 0; x < nv && sudoku; x++) {
+            std::set<int> want, got;
+            const int r = x / 9, c = x % 9;
+            for (int i = 0; i < 9; i++) {
+                want.insert(r * 9 + i);
+                want.insert(i * 9 + c);
+                want.insert((r / 3 * 3 + i / 3) * 9 + (c / 3 * 3 + i % 3));
+            }
+            want.erase(x);
+            for (uint32_t e = M.ent_off[x]; e < M.ent_off[x + 1]; e++)
+                if (!(M.ent[e] & ENT_SKIP)) got.insert(M.ent[e] & 0xFF);
+            sudoku = want == got;
+        }
+        if (sudoku) M.model_class = CLASS_SUDOKU9;
+    }
     return DQ_OK;
 }
 

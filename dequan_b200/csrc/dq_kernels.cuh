@@ -201,6 +201,7 @@ struct BatchCellsArgs {
     unsigned long long* nodes;  // [n]
     uint8_t* status;            // [n]
     unsigned long long* totals; // [0]=sat [1]=unsat [2]=budget [3]=nodes
+    const int* idx_list;        // optional: the n instance ids to solve (null = 0..n-1)
 };
 
 struct NoFirst { __device__ void operator()(const WarpState&) const {} };
@@ -219,6 +220,7 @@ k_batch_cells(TreeModelDev M, BatchCellsArgs A) {
         if (lane == 0) i = (long long)atomicAdd(A.cursor, 1ull);
         i = __shfl_sync(FULL, i, 0);
         if (i >= A.n) break;
+        if (A.idx_list) i = A.idx_list[i];
         const uint8_t* cell = A.cells + (size_t)i * A.stride;
         // initial domains: template domain, or the singleton of the given (AddFixedVar, dequan.h:467-471)
         bool bad = false;

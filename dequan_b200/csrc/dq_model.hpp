@@ -40,7 +40,8 @@ constexpr uint32_t ENT_SKIP      = 1u << 14;  // padding so that same-q entries 
 enum ModelClass : int32_t {
     CLASS_GENERIC = 0,     // anything the entry table can express
     CLASS_NE_SAME = 1,     // only K_NE_SAME entries (Sudoku, graph colouring): no mask table needed
-    CLASS_QUEENS  = 2      // N-Queens structure: dense NotEqual with offsets {0, +-(j-i)} on [0,N)
+    CLASS_QUEENS  = 2,     // N-Queens structure: dense NotEqual with offsets {0, +-(j-i)} on [0,N)
+    CLASS_SUDOKU9 = 3      // 81 variables on 1..9, pairwise different over the 27 rows / columns / boxes
 };
 
 struct CompiledModel {

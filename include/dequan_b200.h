@@ -102,7 +102,8 @@ enum dq_mode {
 enum dq_engine {
     DQ_ENGINE_AUTO  = 0,     /* fastest engine the compiled model qualifies for     */
     DQ_ENGINE_WARP  = 1,     /* generic warp-cooperative DFS (any supported model)  */
-    DQ_ENGINE_LANE  = 2      /* lane-per-subtree bitboard DFS (ne-offset models)    */
+    DQ_ENGINE_LANE  = 2      /* lane-per-subtree / lane-per-instance closed-form DFS
+                                (N-Queens class trees, 9x9 Sudoku class batches)    */
 };
 
 typedef struct dq_tree_opts {
@@ -134,7 +135,9 @@ typedef struct dq_tree_result {
 typedef struct dq_batch_opts {
     uint64_t node_budget;    /* per instance, 0 = unlimited                         */
     int32_t  engine;         /* dq_engine                                           */
-    int32_t  reserved;
+    int32_t  task_nodes;     /* lane engine: nodes one lane spends on a search before
+                                handing the rest of its stack to the task pool;
+                                0 = default (8192)                                  */
 } dq_batch_opts;
 
 typedef struct dq_batch_stats {

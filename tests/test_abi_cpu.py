@@ -47,7 +47,7 @@ def test_model_classes(product_lib):
     assert api.Model(nqueens(8)).info()["model_class"] == "queens"
     assert api.Model(nqueens(17)).info() == {"n_vars": 17, "max_dom": 17, "n_arcs": 17 * 16, "model_class": "queens"}
     s = api.Model(sudoku_template()).info()
-    assert s["model_class"] == "ne_same" and s["n_arcs"] == 1620 and s["n_vars"] == 81
+    assert s["model_class"] == "sudoku9" and s["n_arcs"] == 1620 and s["n_vars"] == 81
     assert api.Model(sudoku(REFERENCE_SUDOKU, alldiff=True)).info()["model_class"] == "generic"  # givens have other value lists
     assert api.Model(colouring(5, 3, [(0, 1), (1, 2)])).info()["model_class"] == "ne_same"
     csp = CSP()

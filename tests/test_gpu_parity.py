@@ -274,3 +274,71 @@ def test_caller_supplied_assign_order_vs_oracle(product_lib):
         assert m.order() == order
         for mode in ("first", "count"):
             _cmp_tree(m.solve_tree(mode), O.solve(csp, mode), (seed, mode))
+
+
+# ---- lane-per-instance Sudoku engine (dq_lane_sudoku.cuh): task splitting must not change any result ----
+
+def _same_batch(a, b, what):
+    assert (a.status == b.status).all(), what
+    assert (a.nodes == b.nodes).all(), (what, np.nonzero(a.nodes != b.nodes)[0][:5])
+    assert (a.solution == b.solution).all(), what
+    assert (a.n_sat, a.n_unsat, a.n_budget, a.total_nodes) == (b.n_sat, b.n_unsat, b.n_budget, b.total_nodes), what
+
+
+def test_sudoku_template_is_recognised(product_lib):
+    assert api.Model(sudoku_template()).info()["model_class"] == "sudoku9"
+    assert api.Model(sudoku([0] * 81, alldiff=True)).info()["model_class"] == "sudoku9"
+    assert api.Model(sudoku_template(boxes=False)).info()["model_class"] == "ne_same"      # a Latin square is not a Sudoku
+    assert api.Model(sudoku(REFERENCE_SUDOKU)).info()["model_class"] == "generic"          # givens baked into the template
+
+
+@pytest.mark.parametrize("task_nodes", [16, 200, 3000, 0])
+@pytest.mark.parametrize("giv", [24, 28, 36])
+def test_sudoku_lane_engine_equals_warp_engine(product_lib, giv, task_nodes):
+    """Whatever the split granularity, the lane engine reproduces the generic warp engine (itself pinned to the
+    reference by the golden vectors) on every instance: status, node count, solution."""
+    n = 1500 if giv == 24 else 6000
+    cells = G.sudoku_batch(n, givens=giv, seed=99 + giv)
+    tmpl = api.Model(sudoku_template())
+    want = tmpl.solve_batch_cells(cells, engine="warp")
+    got = tmpl.solve_batch_cells(cells, engine="lane", task_nodes=task_nodes)
+    _same_batch(got, want, (giv, task_nodes))
+
+
+def test_sudoku_lane_engine_unsat_budget_and_odd_inputs(product_lib):
+    rng = np.random.default_rng(5)
+    cells = G.sudoku_batch(3000, givens=27, seed=123)
+    # no solution, but no two givens clash: overwrite one given with another value that is still free in its units
+    broken = 0
+    for i in range(0, 3000, 3):
+        g = cells[i].reshape(9, 9)
+        rs, cs = np.nonzero(g)
+        for j in rng.permutation(len(rs)):
+            r, c = rs[j], cs[j]
+            used = set(g[r]) | set(g[:, c]) | set(g[r // 3 * 3:r // 3 * 3 + 3, c // 3 * 3:c // 3 * 3 + 3].ravel())
+            free = [v for v in range(1, 10) if v not in used]
+            if free:
+                g[r, c] = free[0]
+                broken += 1
+                break
+    assert broken > 900
+    cells[1] = 0                                   # all blank
+    cells[4] = G.sudoku_batch(1, givens=81, seed=4)[0]   # nothing blank
+    cells[7, 0], cells[7, 1] = 5, 5                # clashing givens -> generic engine, exact node count
+    cells[10, 3] = 77                              # a byte outside the template domain -> status 3
+    tmpl = api.Model(sudoku_template())
+    want = tmpl.solve_batch_cells(cells, engine="warp")
+    assert want.n_unsat > 300 and want.status[10] == 3
+    for tn in (32, 700, 0):
+        _same_batch(tmpl.solve_batch_cells(cells, engine="lane", task_nodes=tn), want, tn)
+    for budget in (60, 81, 300, 5000):
+        wb = tmpl.solve_batch_cells(cells, engine="warp", node_budget=budget)
+        for tn in (50, 0):
+            _same_batch(tmpl.solve_batch_cells(cells, engine="lane", node_budget=budget, task_nodes=tn), wb, (budget, tn))
+    # padded rows (stride > 81)
+    wide = np.zeros((500, 96), dtype=np.uint8)
+    wide[:, :81] = cells[:500]
+    gw = tmpl.solve_batch_cells(wide, engine="lane", task_nodes=100)
+    assert (gw.nodes == want.nodes[:500]).all() and (gw.solution[:, :81] == want.solution[:500]).all()
+    with pytest.raises(api.DequanError):
+        api.Model(sudoku_template(boxes=False)).solve_batch_cells(cells[:8], engine="lane")
