@@ -82,11 +82,12 @@ struct dq_model {
     DevBuf<unsigned long long> b_nodes;
     // sudoku lane engine scratch (task pool)
     DevBuf<SudokuDigest> s_digest;
-    DevBuf<unsigned long long> s_best, s_piece_nodes, s_ctrl;
-    DevBuf<SudokuPiece> s_pieces;
+    DevBuf<unsigned long long> s_ctrl;
+    DevBuf<uint32_t> s_hard;
+    DevBuf<SudokuTask> s_tasks;
     DevBuf<uint4> s_snaps;
-    DevBuf<uint8_t> s_piece_sol, s_piece_found;
     DevBuf<int> s_deferred;
+    unsigned long long s_tasks_used = 0;
 };
 
 namespace dq {
@@ -304,8 +305,7 @@ void dq_free(dq_model* m) {
         m->d_sub_nodes.release(); m->d_sol_key.release(); m->d_sol.release();
         m->q_records.release(); m->q_records2.release(); m->q_first.release();
         m->b_cells.release(); m->b_solution.release(); m->b_status.release(); m->b_nodes.release();
-        m->s_digest.release(); m->s_best.release(); m->s_piece_nodes.release(); m->s_ctrl.release();
-        m->s_pieces.release(); m->s_snaps.release(); m->s_piece_sol.release(); m->s_piece_found.release();
+        m->s_digest.release(); m->s_ctrl.release(); m->s_hard.release(); m->s_tasks.release(); m->s_snaps.release();
         m->s_deferred.release();
         for (auto& l : m->levels) {
             l.dmask.release(); l.surv.release(); l.child_off.release(); l.parent_of.release();
@@ -571,62 +571,80 @@ static int run_batch_cells(dq_model* m, const uint8_t* cells_dev, int64_t n, int
     return DQ_OK;
 }
 
-// Batch of 9x9 Sudoku on the lane-per-instance engine (dq_lane_sudoku.cuh): digest pass, search rounds until the
-// task pool is drained, accounting passes; instances the digest cannot take (clashing givens, foreign bytes) go
-// through the generic warp engine.
+// Batch of 9x9 Sudoku (dq_lane_sudoku.cuh): digest -> first (lane per instance, bounded) -> strong (warp per hard
+// instance: the solution) -> walk + count (the reference's node total, exhaustive subtree tasks) -> finish, queued back
+// to back on one stream; instances the digest cannot take (clashing givens, foreign bytes) go through the generic warp
+// engine afterwards.
 static int run_batch_sudoku(dq_model* m, const uint8_t* cells_dev, int64_t n, int32_t stride, const dq_batch_opts* opts,
                             uint8_t* sol_dev, unsigned long long* nodes_dev, uint8_t* status_dev, dq_batch_stats* st) {
-    const size_t smem = sizeof(SudokuSmem);
-    int occ = 0;
-    int rc = max_ctas_per_sm(k_sudoku_lane, kSudokuBlock, smem, &occ);
+    const size_t smem = sizeof(SudokuSmem), smem_strong = sizeof(StrongSmem);
+    int occ_first = 0, occ_count = 0, occ_walk = 0, occ_strong = 0;
+    int rc = max_ctas_per_sm(k_sudoku_first, kSudokuBlock, smem, &occ_first);
+    if (rc == DQ_OK) rc = max_ctas_per_sm(k_sudoku_count, kSudokuBlock, smem, &occ_count);
+    if (rc == DQ_OK) rc = max_ctas_per_sm(k_sudoku_walk, kSudokuBlock, smem, &occ_walk);
+    if (rc == DQ_OK) rc = max_ctas_per_sm(k_sudoku_strong, 128, smem_strong, &occ_strong);
     if (rc != DQ_OK) return rc;
-    if (occ < 1) { g_err = "kernel does not fit an SM"; return DQ_ERR_UNSUPPORTED; }
-    const unsigned long long piece_cap = std::max<unsigned long long>(1u << 16, std::min<unsigned long long>(4ull * n, 1ull << 24));
-    const unsigned long long snap_cap = piece_cap / 2;
-    DQ_CUDA(m->s_digest.reserve(n)); DQ_CUDA(m->s_best.reserve(n)); DQ_CUDA(m->s_ctrl.reserve(16));
-    DQ_CUDA(m->s_pieces.reserve(piece_cap)); DQ_CUDA(m->s_snaps.reserve(snap_cap * kSnapWords));
-    DQ_CUDA(m->s_piece_nodes.reserve(piece_cap)); DQ_CUDA(m->s_piece_found.reserve(piece_cap));
-    DQ_CUDA(m->s_piece_sol.reserve(piece_cap * 81));
-    unsigned long long* ctrl = m->s_ctrl.p;       // [0] cursor [1] piece tail [2] snapshot tail [3] round begin [4] round end [8..11] totals [12] deferred
+    if (occ_first < 1 || occ_count < 1 || occ_walk < 1 || occ_strong < 1) { g_err = "kernel does not fit an SM"; return DQ_ERR_UNSUPPORTED; }
+    const unsigned long long task_cap = std::max<unsigned long long>(1u << 20, std::min<unsigned long long>(8ull * n, 1ull << 25));
+    const unsigned long long snap_cap = std::max<unsigned long long>(1u << 18, std::min<unsigned long long>(2ull * n, 1ull << 23));
+    const bool fresh_pool = m->s_tasks.cap < task_cap;
+    DQ_CUDA(m->s_digest.reserve(n)); DQ_CUDA(m->s_hard.reserve(n)); DQ_CUDA(m->s_ctrl.reserve(16));
+    DQ_CUDA(m->s_tasks.reserve(task_cap)); DQ_CUDA(m->s_snaps.reserve(snap_cap * kSnapWords));
+    unsigned long long* ctrl = m->s_ctrl.p;       // SkCtrl words
     DQ_CUDA(cudaMemsetAsync(ctrl, 0, 16 * sizeof(unsigned long long), m->stream));
+    // task records double as "published" flags: the part the previous call used must read zero again
+    const unsigned long long dirty = fresh_pool ? m->s_tasks.cap : std::min<unsigned long long>(m->s_tasks_used, m->s_tasks.cap);
+    if (dirty) DQ_CUDA(cudaMemsetAsync(m->s_tasks.p, 0, dirty * sizeof(SudokuTask), m->stream));
     SudokuArgs A;
     A.digest = m->s_digest.p; A.n = n; A.stride = stride; A.cells = cells_dev; A.solution = sol_dev; A.nodes = nodes_dev;
-    A.status = status_dev; A.best_key = m->s_best.p; A.pieces = m->s_pieces.p; A.piece_cap = piece_cap;
-    A.snaps = m->s_snaps.p; A.snap_cap = snap_cap; A.piece_nodes = m->s_piece_nodes.p; A.piece_sol = m->s_piece_sol.p;
-    A.piece_found = m->s_piece_found.p; A.ctrl = ctrl; A.user_budget = opts ? opts->node_budget : 0;
-    const unsigned budget0 = opts && opts->task_nodes > 0 ? (unsigned)opts->task_nodes : 8192u;
-    unsigned long long launches = 0;
+    A.status = status_dev; A.hard = m->s_hard.p; A.tasks = m->s_tasks.p; A.task_cap = task_cap;
+    A.snaps = m->s_snaps.p; A.snap_cap = snap_cap; A.ctrl = ctrl; A.user_budget = opts ? opts->node_budget : 0;
+    A.force_donate = opts && opts->task_nodes > 0 ? (unsigned)opts->task_nodes : 0u;
+    const char* env_fb = getenv("DQ_SUDOKU_FIRST_BUDGET");
+    A.first_budget = env_fb ? (unsigned)atoi(env_fb) : 2048u;
+    if (A.force_donate) A.first_budget = std::min(A.first_budget, 4u * A.force_donate);       // tests: push work through the task path
+    const bool trace = getenv("DQ_TRACE") != nullptr;
+    cudaEvent_t ev[7] = {nullptr};
+    if (trace) for (auto& e : ev) cudaEventCreate(&e);
+    auto mark = [&](int i) { if (trace) cudaEventRecord(ev[i], m->stream); };
+    const long long sms = m->sm_count;
     DQ_CUDA(cudaEventRecord(m->ev0, m->stream));
-    k_sudoku_digest<<<(unsigned)((n + 127) / 128), 128, 128 * 81, m->stream>>>(cells_dev, n, stride, m->s_digest.p, m->s_best.p);
-    launches++;
-    const long long resident = (long long)occ * m->sm_count;
-    unsigned long long seg_begin = 0, seg_end = 0;
-    for (int round = 0; round < 4096; round++) {
-        const unsigned long long tasks = round == 0 ? (unsigned long long)n : seg_end - seg_begin;
-        A.round = round;
-        A.budget = round < 64 ? budget0 : 0xFFFFFFFFu;            // past 64 rounds: stop splitting, run the leftovers out
-        const long long ctas = std::max<long long>(1, std::min<long long>(resident, (long long)((tasks + kSudokuBlock - 1) / kSudokuBlock)));
-        k_sudoku_lane<<<(unsigned)ctas, kSudokuBlock, smem, m->stream>>>(A);
-        launches++;
-        DQ_CUDA(cudaGetLastError());
-        unsigned long long h[3];
-        DQ_CUDA(cudaMemcpyAsync(h, ctrl, sizeof h, cudaMemcpyDeviceToHost, m->stream));
-        DQ_CUDA(cudaStreamSynchronize(m->stream));
-        const unsigned long long tail = std::min(h[1], piece_cap);
-        if (tail == seg_end) break;                                 // no new pieces: every task ran to its end
-        seg_begin = seg_end; seg_end = tail;
-        const unsigned long long next[5] = {0, h[1], h[2], seg_begin, seg_end};
-        DQ_CUDA(cudaMemcpyAsync(ctrl, next, sizeof next, cudaMemcpyHostToDevice, m->stream));
-    }
-    if (seg_end) { k_sudoku_account<<<(unsigned)((seg_end + 255) / 256), 256, 0, m->stream>>>(A, seg_end); launches++; }
-    k_sudoku_finish<<<(unsigned)((n + 255) / 256), 256, 0, m->stream>>>(A, ctrl + 8);
+    mark(0);
+    k_sudoku_digest<<<(unsigned)((n + 127) / 128), 128, 128 * 81, m->stream>>>(cells_dev, n, stride, m->s_digest.p);
+    mark(1);
+    const long long ctas_first = std::max<long long>(1, std::min<long long>(occ_first * sms, (long long)((n + kSudokuBlock - 1) / kSudokuBlock)));
+    k_sudoku_first<<<(unsigned)ctas_first, kSudokuBlock, smem, m->stream>>>(A);
+    mark(2);
+    // the hard list's length stays on the device: the next three kernels are sized for the machine and find it in ctrl
+    k_sudoku_strong<<<(unsigned)(occ_strong * sms), 128, smem_strong, m->stream>>>(A);
+    mark(3);
+    k_sudoku_walk<<<(unsigned)std::min<long long>(occ_walk * sms, (long long)((n + kSudokuBlock - 1) / kSudokuBlock)), kSudokuBlock, smem, m->stream>>>(A);
+    mark(4);
+    k_sudoku_count<<<(unsigned)(occ_count * sms), kSudokuBlock, smem, m->stream>>>(A);
+    mark(5);
+    k_sudoku_finish<<<(unsigned)((n + 255) / 256), 256, 0, m->stream>>>(A, ctrl + SKC_TOTALS);
     DQ_CUDA(m->s_deferred.reserve(n));
-    k_sudoku_collect_deferred<<<(unsigned)((n + 255) / 256), 256, 0, m->stream>>>(status_dev, n, m->s_deferred.p, ctrl + 12);
-    launches += 2;
+    k_sudoku_collect_deferred<<<(unsigned)((n + 255) / 256), 256, 0, m->stream>>>(status_dev, n, m->s_deferred.p, ctrl + 10);
+    mark(6);
+    unsigned long long launches = 7;
     DQ_CUDA(cudaGetLastError());
-    unsigned long long n_def = 0;
-    DQ_CUDA(cudaMemcpyAsync(&n_def, ctrl + 12, sizeof n_def, cudaMemcpyDeviceToHost, m->stream));
+    unsigned long long hc[16];
+    DQ_CUDA(cudaMemcpyAsync(hc, ctrl, sizeof hc, cudaMemcpyDeviceToHost, m->stream));
     DQ_CUDA(cudaStreamSynchronize(m->stream));
+    m->s_tasks_used = std::min(hc[SKC_RESERVE], task_cap);
+    if (trace) {
+        float ms[6];
+        for (int i = 0; i < 6; i++) cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]);
+        fprintf(stderr, "[dq] sudoku: n=%lld hard=%llu tasks=%llu snaps=%llu err=%llu | ms digest %.3f first %.3f strong %.3f walk %.3f count %.3f finish %.3f\n",
+                (long long)n, hc[SKC_HARD], hc[SKC_RESERVE], hc[SKC_SNAP], hc[SKC_ERROR], ms[0], ms[1], ms[2], ms[3], ms[4], ms[5]);
+        for (auto& e : ev) cudaEventDestroy(e);
+    }
+    if (hc[SKC_ERROR] & 2) { g_err = "sudoku task pool overflow"; return DQ_ERR_NOMEM; }
+    if (hc[SKC_ERROR] || hc[SKC_OUTSTANDING]) {
+        g_err = "internal: sudoku counting pipeline inconsistent (error bits " + std::to_string(hc[SKC_ERROR]) + ")";
+        return DQ_ERR_INTERNAL;
+    }
+    const unsigned long long n_def = hc[10];
     unsigned long long hw[8] = {0};
     if (n_def) {
         dq_batch_opts o2 = opts ? *opts : dq_batch_opts{0, 0, 0};
@@ -636,13 +654,12 @@ static int run_batch_sudoku(dq_model* m, const uint8_t* cells_dev, int64_t n, in
         launches++;
     }
     DQ_CUDA(cudaEventRecord(m->ev1, m->stream));
-    unsigned long long ht[4];
-    DQ_CUDA(cudaMemcpyAsync(ht, ctrl + 8, sizeof ht, cudaMemcpyDeviceToHost, m->stream));
     if (n_def) DQ_CUDA(cudaMemcpyAsync(hw, m->d_ctrl.p, sizeof hw, cudaMemcpyDeviceToHost, m->stream));
     DQ_CUDA(cudaStreamSynchronize(m->stream));
     if (st) {
         float ms = 0;
         DQ_CUDA(cudaEventElapsedTime(&ms, m->ev0, m->ev1));
+        const unsigned long long* ht = hc + SKC_TOTALS;
         st->n_sat = ht[0] + hw[1]; st->n_unsat = ht[1] + hw[2]; st->n_budget = ht[2] + hw[3]; st->total_nodes = ht[3] + hw[4];
         st->kernel_ms = ms; st->kernel_launches = launches;
     }

@@ -1,7 +1,6 @@
-// dq_lane_sudoku.cuh — lane-per-instance forward-checking DFS for batches of 9x9 Sudoku
-// (CLASS_SUDOKU9: 81 variables on 1..9, NotEqual/AllDifferent over the 27 rows, columns and boxes
-// — BASELINE config C3, recognised by the model compiler whatever mix of binary != and
-// AllDifferent rows produced it).
+// dq_lane_sudoku.cuh — batches of 9x9 Sudoku on B200 (CLASS_SUDOKU9: 81 variables on 1..9,
+// NotEqual/AllDifferent over the 27 rows, columns and boxes — BASELINE config C3, recognised by
+// the model compiler whatever mix of binary != and AllDifferent rows produced it).
 //
 // What the reference does per node (CSP::ForwardCheckingStep dequan.h:494-571 with
 // OpConstraint/AllDifferent::AplyArcConsistency 631-694, 915-939 and Domain::Exclude 985-1031)
@@ -12,23 +11,37 @@
 //
 // Static order (Assignment::Reset, dequan.h:376-394): givens first (domain size 1) by id, then the
 // blanks by id.  A node is an AssignVar call (dequan.h:416-423): one per given, then one per value
-// tried at a blank.  The forward check after assigning value v at cell p asks whether any LATER
-// blank peer q is left with no value: used(q) | v == all nine.  Cells are packed three to a word
-// (10-bit fields, one word per (row, stack) = one box-row), so a check is one OR/AND/ADD per word:
-// adding 1 to every field carries into the field's spare bit exactly when the field is all ones.
+// tried at a blank.  Assigning value v at cell p passes its forward check unless some LATER blank
+// peer q is left with no value, i.e. unless dom(q) == {v}.  Cells are packed three to a word
+// (10-bit fields, one word per (row, stack) = one box-row), so "which values of p are forbidden by
+// a later peer" is a handful of packed-field operations per peer word (sk_singletons).
 //
-// Layout: every lane owns one instance; its masks, blank-field masks and DFS stack live in shared
-// memory as [word][thread], which is bank-conflict-free whatever each lane indexes.
+// Lane engine: every lane owns one search; its masks, blank-field masks and DFS stack live in
+// shared memory as [word][thread], bank-conflict-free whatever each lane indexes.  A level is
+// entered once (domain + forbidden values in one pass); failing values are never stepped through,
+// only counted when the search moves past them.
 //
-// Work distribution.  Node counts per puzzle are heavy-tailed (30 givens: median 363, max > 1e6), and a
-// lane is slow, so long searches are cut into TASKS: a lane that has spent its node budget on a
-// task stops, and hands every untried candidate set left on its stack to the task pool as an
-// independent subtree ("piece"), each with a sub-interval of the parent's 64-bit DFS-order key
-// range.  Pieces are searched by any lane in a later round.  Exactness of the per-puzzle node count
-// (the reference's sequential count up to its first solution) comes from the keys: the first
-// solution in DFS order is the found piece with the smallest key, and the puzzle's node count is
-// the sum over its tasks with key <= that key.  Tasks with larger keys are speculative; they are
-// skipped or abandoned as soon as a smaller-keyed solution is known.
+// Pipeline for a batch (all on one stream, no host round trip in between):
+//   k_sudoku_digest  one thread per instance: working tables of the givens, coalesced.
+//   k_sudoku_first   lane per instance: the reference's search, up to `first_budget` nodes.  Node
+//                    counts are heavy-tailed (30 givens: median 363, max > 1e6) and a lane is slow,
+//                    so an instance that is not done by then is put on the HARD list instead.
+//   k_sudoku_strong  warp per hard instance: finds the solution the reference would return — the
+//                    lexicographically first one in (blank order, ascending values), SURVEY.md §9
+//                    S5 — by the same static-order DFS with naked-single propagation to a fixed
+//                    point.  Sound extra pruning never changes WHICH solution is first, only how
+//                    many nodes it takes to get there (a few hundred instead of up to 1e6).
+//   k_sudoku_walk    lane per hard instance: walks the solution path and counts what the
+//                    reference's plain forward-checking search visits on the way: at every path
+//                    level the values tried up to the solution's (nodes), and for each of those
+//                    that passes its forward check a ROOT TASK = "count the whole subtree below it".
+//   k_sudoku_count   lanes take root tasks from a queue and count their subtrees exhaustively.
+//                    Every one of those nodes is a node of the reference's search, so there is no
+//                    speculative work; lanes that run dry raise a hunger count and busy lanes hand
+//                    over their shallowest stack level with untried values (the largest subtree
+//                    they own) as a new task.  Sums go to nodes[instance] with atomicAdd.
+//   k_sudoku_finish  API node budget on the exact totals, batch totals.
+// Instances with clashing givens or foreign bytes are handed to the generic warp engine.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -39,54 +52,67 @@ constexpr int kSudokuBlock = 128;               // threads per CTA
 constexpr uint32_t SK_ONES = 0x00100401u;       // 1 in each of the three 10-bit fields
 constexpr uint32_t SK_SPARE = 0x20080200u;      // bit 9 of each field
 constexpr uint32_t SK_FULL3 = 0x1FF7FDFFu;      // 0x1FF in each field
-constexpr unsigned long long SK_KEY_END = 0x7FFFFFFFFFFFFFFFull;
-constexpr uint8_t SK_STATUS_SPLIT = 0xFD;       // interim: the puzzle's tasks are still being accounted
+constexpr uint8_t SK_STATUS_HARD = 0xFD;        // interim: on the hard list
 constexpr uint8_t SK_STATUS_DEFER = 0xFE;       // interim: handed to the generic warp engine
 
-// 48-byte digest of one instance, written by k_sudoku_digest and read by the lanes.
-//   w[0..2]  rows' used masks, three rows per word (10-bit fields)
-//   w[3..5]  columns' used masks, three columns per word
-//   w[6..8]  boxes' used masks, three boxes (one band) per word
-//   w[9..11] blank bitmap by cell id (81 bits); w[11] bit 31 = deferred to the generic engine
-struct SudokuDigest { uint32_t w[12]; };
+// Per-instance record written by k_sudoku_digest and copied into shared memory by the lane that
+// takes the instance: everything the search needs, already in its working layout (19 x uint4).
+//   w[0..2]   blank bitmap by cell id (81 bits)
+//   w[3]      bit 31 = deferred to the generic engine; low byte = number of blanks
+//   w[4..12]  rows' used masks, replicated in the three 10-bit fields
+//   w[13..15] columns' used masks, one stack per word, one column per field
+//   w[16..24] boxes' used masks, replicated
+//   w[25..51] per (row, stack): 0x1FF in the fields of blank cells
+//   w[52..72] the blank cells' ids in search order, one byte per level
+constexpr int kDigestVec = 19;
+struct SudokuDigest { uint4 v[kDigestVec]; };
 
-struct SudokuPiece {           // 32 bytes: one part of a split task's remaining search
+// One unit of counting work (16 bytes).
+//   root task : count the subtree below "path values at levels < level, then `value` at `level`"
+//   piece     : a range of stack levels [lo, hi] of a donor's snapshot
+// `info` is written LAST by whoever publishes the task; 0 = not published yet.
+struct SudokuTask {
     uint32_t puzzle;
-    uint32_t snap_id;          // which stack snapshot it resumes from
-    uint32_t levels;           // lo | hi << 8: the snapshot's stack levels [lo, hi] whose untried values it owns;
-                               // 0xFFFFFFFF = null piece (pool overflow filler)
+    uint32_t snap_id;          // piece: which stack snapshot it resumes from
+    uint32_t info;             // bit 31 valid | bit 30 root | bit 29 null ; root: level | value << 8 ; piece: lo | hi << 8
     uint32_t pad;
-    unsigned long long key_lo, key_hi;
 };
-constexpr int kSnapWords = 12;                  // uint4 per stack snapshot: 96 u16 entries (untried | value << 9) per level
+constexpr uint32_t SKT_VALID = 0x80000000u, SKT_ROOT = 0x40000000u, SKT_NULL = 0x20000000u;
+constexpr int kSnapWords = 12;                  // uint4 per stack snapshot: 96 u16 entries (passing untried | value << 9) per level
+
+// Control block (unsigned long long words)
+enum SkCtrl { SKC_FRESH = 0,        // k_sudoku_first: next fresh instance
+              SKC_HARD = 1,         // instances on the hard list
+              SKC_HARD_CUR = 2,     // k_sudoku_strong / k_sudoku_walk cursors over the hard list
+              SKC_WALK_CUR = 3,
+              SKC_RESERVE = 4,      // tasks reserved (root tasks by the walker, pieces by donors)
+              SKC_SNAP = 5,         // snapshots reserved
+              SKC_HEAD = 6,         // tickets drawn by consumers (may run ahead of SKC_RESERVE: lanes waiting for work)
+              SKC_OUTSTANDING = 7,  // tasks published and not finished yet
+              SKC_ERROR = 9,        // bit 0: a warp gave up waiting; bit 1: task pool overflow; bit 2: a counted subtree held a solution
+              SKC_TOTALS = 12 };    // [12..15] sat, unsat, budget, nodes
 
 struct SudokuArgs {
     const SudokuDigest* digest;
     long long n;                           // instances
     int stride;
-    const uint8_t* cells;                  // [n][stride] givens (for writing solutions)
+    const uint8_t* cells;                  // [n][stride] givens
     uint8_t* solution;                     // [n][stride]
     unsigned long long* nodes;             // [n]
     uint8_t* status;                       // [n]
-    unsigned long long* best_key;          // [n] smallest key of a task that found a solution
-    // task pool
-    SudokuPiece* pieces;  unsigned long long piece_cap;
+    uint32_t* hard;                        // [n] ids of the instances k_sudoku_first did not finish
+    SudokuTask* tasks;    unsigned long long task_cap;
     uint4* snaps;         unsigned long long snap_cap;       // kSnapWords x uint4 per snapshot
-    unsigned long long* piece_nodes;       // [piece_cap]
-    uint8_t* piece_sol;                    // [piece_cap][81], valid where piece_found
-    uint8_t* piece_found;                  // [piece_cap]
-    // control block: [0] cursor  [1] piece tail  [2] snapshot tail  [3] round begin  [4] round end
-    unsigned long long* ctrl;
-    unsigned budget;                       // nodes per task before it is split
+    unsigned long long* ctrl;              // control block, see SkCtrl
     unsigned long long user_budget;        // per-instance node budget of the API (0 = none)
-    int round;                             // 0: fresh instances, >0: pool pieces [ctrl[3], ctrl[4])
+    unsigned first_budget;                 // nodes k_sudoku_first spends on an instance before calling it hard
+    unsigned force_donate;                 // test knob: donate whenever a task is this many nodes old, hungry lanes or not (0 = off)
 };
 
 // ---------------------------------------------------------------------------------------------
 // Pass 0: one thread per instance, inputs staged through shared memory so that HBM reads coalesce.
 __global__ void __launch_bounds__(128)
-k_sudoku_digest(const uint8_t* __restrict__ cells, long long n, int stride, SudokuDigest* __restrict__ out,
-                unsigned long long* __restrict__ best_key) {
+k_sudoku_digest(const uint8_t* __restrict__ cells, long long n, int stride, SudokuDigest* __restrict__ out) {
     extern __shared__ uint8_t stage[];                       // [128][81]
     const long long first = (long long)blockIdx.x * 128;
     const int here = (int)min((long long)128, n - first);
@@ -116,27 +142,33 @@ k_sudoku_digest(const uint8_t* __restrict__ cells, long long n, int stride, Sudo
             if ((row[r] | col[c] | box[b]) & bit) defer = true;   // two givens clash: the exact node count is the generic engine's job
             row[r] |= bit; col[c] |= bit; box[b] |= bit;
         }
+    uint32_t w[kDigestVec * 4];
+#pragma unroll
+    for (int i = 0; i < kDigestVec * 4; i++) w[i] = 0;
+    int level = 0;
 #pragma unroll
     for (int r = 0; r < 9; r++)
 #pragma unroll
         for (int c = 0; c < 9; c++) {
             const int p = r * 9 + c;
-            if (((blank[p >> 5] >> (p & 31)) & 1u) && (row[r] | col[c] | box[(r / 3) * 3 + c / 3]) == 0x1FFu) defer = true;  // a blank wiped out by the givens
-        }
-    SudokuDigest d;
+            if (!((blank[p >> 5] >> (p & 31)) & 1u)) continue;
+            if ((row[r] | col[c] | box[(r / 3) * 3 + c / 3]) == 0x1FFu) defer = true;  // a blank wiped out by the givens
+            w[25 + r * 3 + c / 3] |= 0x1FFu << (10 * (c % 3));
+            // cell id of this search level, one byte per level (dynamic index: the only non-static store of the pass)
+            const uint32_t sh = (uint32_t)(level & 3) * 8;
 #pragma unroll
-    for (int t = 0; t < 3; t++) {
-        d.w[t] = row[3 * t] | (row[3 * t + 1] << 10) | (row[3 * t + 2] << 20);
-        d.w[3 + t] = col[3 * t] | (col[3 * t + 1] << 10) | (col[3 * t + 2] << 20);
-        d.w[6 + t] = box[3 * t] | (box[3 * t + 1] << 10) | (box[3 * t + 2] << 20);
-        d.w[9 + t] = blank[t];
-    }
-    if (defer) d.w[11] |= 0x80000000u;
+            for (int q = 0; q < 21; q++) if ((level >> 2) == q) w[52 + q] |= (uint32_t)p << sh;
+            ++level;
+        }
+    w[0] = blank[0]; w[1] = blank[1]; w[2] = blank[2];
+    w[3] = (uint32_t)level | (defer ? 0x80000000u : 0u);
+#pragma unroll
+    for (int i = 0; i < 9; i++) { w[4 + i] = row[i] * SK_ONES; w[16 + i] = box[i] * SK_ONES; }
+#pragma unroll
+    for (int i = 0; i < 3; i++) w[13 + i] = col[3 * i] | (col[3 * i + 1] << 10) | (col[3 * i + 2] << 20);
     uint4* o = reinterpret_cast<uint4*>(out + first + threadIdx.x);
-    o[0] = make_uint4(d.w[0], d.w[1], d.w[2], d.w[3]);
-    o[1] = make_uint4(d.w[4], d.w[5], d.w[6], d.w[7]);
-    o[2] = make_uint4(d.w[8], d.w[9], d.w[10], d.w[11]);
-    best_key[first + threadIdx.x] = 0xFFFFFFFFFFFFFFFFull;
+#pragma unroll
+    for (int i = 0; i < kDigestVec; i++) o[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -146,7 +178,8 @@ struct SudokuSmem {
     uint32_t colp[3][kSudokuBlock];     // column used masks of one stack, one per field
     uint32_t boxr[9][kSudokuBlock];     // box used mask, replicated
     uint32_t blk[27][kSudokuBlock];     // (row, stack) -> 0x1FF in the fields of blank cells
-    uint16_t stk[81][kSudokuBlock];     // per level: untried candidates | value index << 9
+    uint32_t cellw[21][kSudokuBlock];   // blank cell ids in search order, four levels per word
+    uint16_t stk[81][kSudokuBlock];     // per level: passing values not tried yet | chosen value index << 9
 };
 
 __device__ __forceinline__ uint32_t sk_rep(uint32_t x9) { return x9 * SK_ONES; }
@@ -163,394 +196,690 @@ __device__ __forceinline__ SkCell sk_decode(int p) {
     return c;
 }
 
-// next / previous blank cell in id order from the 81-bit bitmap (b0: cells 0-31, b1: 32-63, b2: 64-80)
-__device__ __forceinline__ int sk_next_blank(uint32_t b0, uint32_t b1, uint32_t b2, int p) {
-    // p in [-1, 80]; returns 81 if none
-    const int q = p + 1;
-    const uint32_t m0 = q < 32 ? (b0 >> q) << q : 0u;
-    const uint32_t m1 = q < 32 ? b1 : (q < 64 ? (b1 >> (q - 32)) << (q - 32) : 0u);
-    const uint32_t m2 = q < 64 ? b2 : (b2 >> (q - 64)) << (q - 64);
-    if (m0) return __ffs(m0) - 1;
-    if (m1) return 32 + __ffs(m1) - 1;
-    if (m2) return 64 + __ffs(m2) - 1;
-    return 81;
-}
-__device__ __forceinline__ int sk_prev_blank(uint32_t b0, uint32_t b1, uint32_t b2, int p) {
-    // largest blank id < p (p in [0,81]); -1 if none
-    const uint32_t m2 = p > 64 ? b2 & ((1u << (p - 64)) - 1u) : 0u;
-    const uint32_t m1 = p >= 64 ? b1 : (p > 32 ? b1 & ((1u << (p - 32)) - 1u) : 0u);
-    const uint32_t m0 = p >= 32 ? b0 : (p > 0 ? b0 & ((1u << p) - 1u) : 0u);
-    if (m2) return 64 + 31 - __clz(m2);
-    if (m1) return 32 + 31 - __clz(m1);
-    if (m0) return 31 - __clz(m0);
-    return -1;
+// Packed fields x (three 9-bit sets): keeps the fields that hold exactly one value, clears the rest.
+// A later blank peer whose domain is a single value forbids that value here: taking it would wipe
+// the peer out (the wipe-out test of OpConstraint::AplyArcConsistency, dequan.h:663-668).
+__device__ __forceinline__ uint32_t sk_singletons(uint32_t x) {
+    const uint32_t y = x + (SK_SPARE - SK_ONES);            // per field x - 1, the spare bit absorbs the borrow of an empty field
+    const uint32_t z = x & y;                               // x & (x - 1): zero iff the field holds at most one value
+    const uint32_t tt = z + (SK_SPARE - SK_ONES);           // spare bit survives iff z != 0
+    const uint32_t nz = ~tt & SK_SPARE;
+    return x & (nz - (nz >> 9));                            // 0x1FF in the fields with z == 0
 }
 
-// The search kernel: one launch per round.  Round 0 walks the fresh instances; later rounds walk
-// the pieces the previous round produced.
+// ---------------------------------------------------------------------------------------------
+// Per-lane search state (registers) and the three steps every lane kernel is built from.
+struct SkLane {
+    bool have, enter;
+    uint32_t puzzle;
+    int p;                      // current cell
+    SkCell c;                   // ... decoded
+    int sp, base_sp, nblank;    // stack level of the current cell; the task's root level; blanks in the instance
+    uint32_t passrem;           // values of the current cell that pass the forward check and are not tried yet
+    uint32_t dom_rem;           // values of the current cell not tried yet, passing or not
+    uint32_t nodes;             // nodes counted by this task
+    unsigned long long nodes_hi;
+};
+
+__device__ __forceinline__ int sk_cell_at(const SudokuSmem& S, int t, int l) { return (int)((S.cellw[l >> 2][t] >> ((l & 3) * 8)) & 0xFF); }
+__device__ __forceinline__ uint32_t sk_used_at(const SudokuSmem& S, int t, const SkCell& k) {
+    return (S.rowr[k.r][t] | (S.colp[k.s][t] >> (10 * k.f)) | S.boxr[k.box][t]) & 0x1FF;
+}
+__device__ __forceinline__ void sk_commit(SudokuSmem& S, int t, const SkCell& k, uint32_t bit) {
+    S.rowr[k.r][t] |= sk_rep(bit);
+    S.boxr[k.box][t] |= sk_rep(bit);
+    S.colp[k.s][t] |= bit << (10 * k.f);
+}
+
+// words 4..72 of the digest record -> rowr, colp, boxr, blk, cellw (contiguous in S)
+__device__ __forceinline__ void sk_load_tables(SudokuSmem& S, int t, const uint4* __restrict__ dg) {
+    uint32_t* dst = &S.rowr[0][t];
+#pragma unroll
+    for (int q = 1; q < kDigestVec; q++) {
+        const uint4 x = __ldg(dg + q);
+        const int wbase = 4 * q - 4;
+        if (wbase + 0 < 69) dst[(wbase + 0) * kSudokuBlock] = x.x;
+        if (wbase + 1 < 69) dst[(wbase + 1) * kSudokuBlock] = x.y;
+        if (wbase + 2 < 69) dst[(wbase + 2) * kSudokuBlock] = x.z;
+        if (wbase + 3 < 69) dst[(wbase + 3) * kSudokuBlock] = x.w;
+    }
+}
+
+// Enter a level: the cell's current domain and the subset that passes the forward check, i.e. is
+// not the only value left to some later blank peer (row to the right, box-rows below inside the
+// band, the column cell below the band).
+__device__ __forceinline__ void sk_enter(const SudokuSmem& S, int t, const SkCell& c, uint32_t& dom, uint32_t& pass) {
+    const uint32_t rowv = S.rowr[c.r][t];
+    const uint32_t colw = S.colp[c.s][t];
+    const uint32_t boxv = S.boxr[c.box][t];
+    dom = ~(rowv | (colw >> (10 * c.f)) | boxv) & 0x1FF;
+    uint32_t kill3 = 0;
+    {
+        const uint32_t sel = (0xFFFFFFFFu << (10 * c.f + 10)) & SK_FULL3;
+        kill3 |= sk_singletons(~(rowv | colw | boxv) & S.blk[c.r * 3 + c.s][t] & sel);
+        for (int s2 = c.s + 1; s2 < 3; s2++)
+            kill3 |= sk_singletons(~(rowv | S.colp[s2][t] | S.boxr[c.band * 3 + s2][t]) & S.blk[c.r * 3 + s2][t]);
+    }
+    {
+        const int in_band_last = c.band * 3 + 2;
+        for (int r2 = c.r + 1; r2 <= in_band_last; r2++)
+            kill3 |= sk_singletons(~(S.rowr[r2][t] | colw | boxv) & S.blk[r2 * 3 + c.s][t]);
+        const uint32_t fsel = 0x1FFu << (10 * c.f);
+        for (int r2 = in_band_last + 1; r2 < 9; r2++) {
+            const int box2 = ((r2 * 11) >> 5) * 3 + c.s;
+            kill3 |= sk_singletons(~(S.rowr[r2][t] | colw | S.boxr[box2][t]) & S.blk[r2 * 3 + c.s][t] & fsel);
+        }
+    }
+    const uint32_t kill = (kill3 | (kill3 >> 10) | (kill3 >> 20)) & 0x1FF;
+    pass = dom & ~kill;
+}
+
+// Step back one level (RestoreSavedDomainStep, dequan.h:431-440).  Returns true when the task's
+// own root level is exhausted — the caller closes the task.
+__device__ __forceinline__ bool sk_pop(SudokuSmem& S, int t, SkLane& L) {
+    L.nodes += __popc(L.dom_rem);            // the leftover values here all fail their check: tried, counted, gone
+    if (L.sp == L.base_sp) return true;
+    --L.sp;
+    const uint32_t e = S.stk[L.sp][t];
+    const uint32_t v = e >> 9, bit = 1u << v;
+    L.p = sk_cell_at(S, t, L.sp);
+    L.c = sk_decode(L.p);
+    S.rowr[L.c.r][t] ^= sk_rep(bit);
+    S.boxr[L.c.box][t] ^= sk_rep(bit);
+    S.colp[L.c.s][t] ^= bit << (10 * L.c.f);
+    L.passrem = e & 0x1FF;
+    L.dom_rem = ~sk_used_at(S, t, L.c) & 0x1FF & ~((2u << v) - 1u);
+    return false;
+}
+
+// AssignVar(next passing value) (dequan.h:416-423).  Returns true when that was the last blank
+// (a solution); otherwise the value is committed and the lane stands before the next level.
+__device__ __forceinline__ bool sk_choose(SudokuSmem& S, int t, SkLane& L) {
+    const uint32_t nxt = L.passrem & (0u - L.passrem);
+    L.nodes += __popc(L.dom_rem & (nxt | (nxt - 1u)));          // the failing values skipped on the way, and this one
+    L.passrem ^= nxt;
+    const uint32_t v = __ffs(nxt) - 1;
+    S.stk[L.sp][t] = (uint16_t)(L.passrem | (v << 9));
+    if (L.sp == L.nblank - 1) return true;
+    sk_commit(S, t, L.c, nxt);
+    ++L.sp;
+    L.p = sk_cell_at(S, t, L.sp);
+    L.enter = true;
+    return false;
+}
+
+constexpr int kPopQuorum = 6;           // extra pop rounds run while at least this many lanes still stand on an exhausted level
+
+// The warp writes the solutions of its finished lanes, one lane at a time, coalesced.
+__device__ __forceinline__ void sk_store_solutions(const SudokuSmem& S, const SudokuArgs& A, int t, bool fin, uint32_t puzzle,
+                                                   uint32_t b0, uint32_t b1, uint32_t b2) {
+    const int lane = t & 31;
+    const uint32_t lt = (1u << lane) - 1u;
+    __syncwarp();
+    uint32_t fm = __ballot_sync(0xFFFFFFFFu, fin);
+    while (fm) {
+        const int Ls = __ffs(fm) - 1;
+        fm &= fm - 1;
+        const uint32_t x0 = __shfl_sync(0xFFFFFFFFu, b0, Ls), x1 = __shfl_sync(0xFFFFFFFFu, b1, Ls), x2 = __shfl_sync(0xFFFFFFFFu, b2, Ls);
+        const uint32_t pz = __shfl_sync(0xFFFFFFFFu, puzzle, Ls);
+        uint8_t* out = A.solution + (size_t)pz * A.stride;
+        const uint8_t* in = A.cells + (size_t)pz * A.stride;
+        const int tL = (t & ~31) + Ls;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const int cell = lane + 32 * k;
+            if (cell < 81) {
+                const uint32_t bw = k == 0 ? x0 : (k == 1 ? x1 : x2);
+                uint8_t val;
+                if ((bw >> lane) & 1u) {
+                    const int level = __popc(bw & lt) + (k > 0 ? __popc(x0) : 0) + (k > 1 ? __popc(x1) : 0);
+                    val = (uint8_t)((S.stk[level][tL] >> 9) + 1);
+                } else val = in[cell];
+                out[cell] = val;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_sudoku_first: lane per instance, the reference's search as it is, up to first_budget nodes.
 __global__ void __launch_bounds__(kSudokuBlock)
-k_sudoku_lane(SudokuArgs A) {
+k_sudoku_first(SudokuArgs A) {
     extern __shared__ __align__(16) unsigned char sk_raw[];
     SudokuSmem& S = *reinterpret_cast<SudokuSmem*>(sk_raw);
     const int t = threadIdx.x;
     const int lane = t & 31;
     const uint32_t lt = (1u << lane) - 1u;
-
-    const unsigned long long q_begin = A.round == 0 ? 0ull : A.ctrl[3];
-    const unsigned long long q_end = A.round == 0 ? (unsigned long long)A.n : A.ctrl[4];
     const unsigned long long total_warps = (unsigned long long)gridDim.x * (kSudokuBlock / 32);
 
-    // per-lane task state
-    bool have = false, done = false;
-    unsigned long long task = 0;            // round 0: instance id; else piece id
-    uint32_t puzzle = 0;
+    SkLane L = {};
     uint32_t b0 = 0, b1 = 0, b2 = 0;        // blank bitmap
-    int p = 0;                              // current cell
-    int sp = 0, base_sp = 0, nblank = 0;    // stack level of the current cell, the task's root level, blanks in the puzzle
-    uint32_t cand = 0;                      // untried values at the current cell
-    uint32_t nodes = 0, limit = 0;          // nodes tried by this task; split / stop threshold
-    unsigned long long nodes_hi = 0;        // overflow of `nodes` for unlimited tasks
-    bool stop_is_budget = false;            // reaching `limit` means the API node budget ran out (no split)
-    unsigned long long key_lo = 0, key_hi = 0;
-    unsigned poll = 0;
-    // warp-uniform queue state
+    uint32_t limit = 0;
+    bool limit_is_api = false, done = false;
     unsigned long long chunk_pos = 0, chunk_end = 0;
     bool exhausted = false;
 
     for (;;) {
         // ---------------- refill ----------------
-        const uint32_t need = __ballot_sync(0xFFFFFFFFu, !have && !done);
+        const uint32_t need = __ballot_sync(0xFFFFFFFFu, !L.have && !done);
         if (need) {
             const uint32_t n_need = __popc(need);
             if (chunk_pos >= chunk_end && !exhausted) {
                 unsigned long long base = 0;
                 uint32_t size = 0;
                 if (lane == 0) {
-                    const unsigned long long cur = *(volatile unsigned long long*)(A.ctrl + 0);
-                    const unsigned long long at = q_begin + cur;
-                    const unsigned long long remaining = at < q_end ? q_end - at : 0;
+                    const unsigned long long cur = *(volatile unsigned long long*)(A.ctrl + SKC_FRESH);
+                    const unsigned long long remaining = cur < (unsigned long long)A.n ? (unsigned long long)A.n - cur : 0;
                     size = (uint32_t)min(max(remaining / (8ull * total_warps), (unsigned long long)n_need), 64ull);
-                    base = q_begin + atomicAdd(A.ctrl + 0, (unsigned long long)size);
+                    base = atomicAdd(A.ctrl + SKC_FRESH, (unsigned long long)size);
                 }
                 base = __shfl_sync(0xFFFFFFFFu, base, 0);
                 size = __shfl_sync(0xFFFFFFFFu, size, 0);
                 chunk_pos = base;
-                chunk_end = min(base + size, q_end);
-                if (base >= q_end) { exhausted = true; chunk_end = chunk_pos; }
+                chunk_end = min(base + size, (unsigned long long)A.n);
+                if (base >= (unsigned long long)A.n) { exhausted = true; chunk_end = chunk_pos; }
             }
             const unsigned long long avail = chunk_end - chunk_pos;
-            if (!have && !done) {
+            if (!L.have && !done) {
                 const uint32_t rank = __popc(need & lt);
                 if (rank < avail) {
-                    task = chunk_pos + rank;
-                    // ---- load the task ----
-                    uint32_t levels = 0, snap_id = 0;
-                    if (A.round == 0) {
-                        puzzle = (uint32_t)task;
-                        key_lo = 0; key_hi = SK_KEY_END;
-                    } else {
-                        const uint4* pr = reinterpret_cast<const uint4*>(A.pieces + task);
-                        const uint4 x = pr[0], y = pr[1];
-                        puzzle = x.x; snap_id = x.y; levels = x.z;
-                        key_lo = (unsigned long long)y.x | ((unsigned long long)y.y << 32);
-                        key_hi = (unsigned long long)y.z | ((unsigned long long)y.w << 32);
-                    }
-                    const uint4* dg = reinterpret_cast<const uint4*>(A.digest + puzzle);
-                    const uint4 d0 = __ldg(dg), d1 = __ldg(dg + 1), d2 = __ldg(dg + 2);
-                    const uint32_t w[12] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w, d2.x, d2.y, d2.z, d2.w};
-                    b0 = w[9]; b1 = w[10]; b2 = w[11] & 0x0001FFFFu;
-                    nblank = __popc(b0) + __popc(b1) + __popc(b2);
-                    have = true;
-                    nodes = 0; nodes_hi = 0; poll = 0;
-                    stop_is_budget = false;
-                    limit = A.budget;
+                    L.puzzle = (uint32_t)(chunk_pos + rank);
+                    const uint4* dg = A.digest[L.puzzle].v;
+                    const uint4 head = __ldg(dg);
+                    b0 = head.x; b1 = head.y; b2 = head.z;
+                    L.nblank = (int)(head.w & 0xFF);
+                    L.nodes = 0; L.nodes_hi = 0;
+                    limit = A.first_budget; limit_is_api = false;
                     bool skip = false;
-                    if (A.round == 0) {
-                        if (w[11] & 0x80000000u) { A.status[puzzle] = SK_STATUS_DEFER; skip = true; }
-                        else if (A.user_budget) {
-                            const unsigned long long givens = 81 - nblank;
-                            if (A.user_budget < givens) {        // the budget runs out among the givens
-                                A.nodes[puzzle] = A.user_budget + 1; A.status[puzzle] = 2; skip = true;
-                                uint8_t* out = A.solution + (size_t)puzzle * A.stride;
-                                for (int i = 0; i < 81; i++) out[i] = 0;
-                            } else if (A.user_budget - givens + 1 <= (unsigned long long)limit) {
-                                limit = (uint32_t)(A.user_budget - givens + 1);
-                                stop_is_budget = true;
-                            }
+                    if (head.w & 0x80000000u) { A.status[L.puzzle] = SK_STATUS_DEFER; skip = true; }
+                    else if (A.user_budget) {
+                        const unsigned long long givens = 81 - L.nblank;
+                        if (A.user_budget < givens) {        // the budget runs out among the givens
+                            A.nodes[L.puzzle] = A.user_budget + 1; A.status[L.puzzle] = 2; skip = true;
+                            uint8_t* out = A.solution + (size_t)L.puzzle * A.stride;
+                            for (int i = 0; i < 81; i++) out[i] = 0;
+                        } else if (A.user_budget - givens + 1 <= (unsigned long long)limit) {
+                            limit = (uint32_t)(A.user_budget - givens + 1);
+                            limit_is_api = true;
                         }
-                    } else if (levels == 0xFFFFFFFFu || *(volatile unsigned long long*)(A.best_key + puzzle) < key_lo) {
-                        A.piece_nodes[task] = 0; A.piece_found[task] = 0; skip = true;   // null, or an earlier subtree already holds a solution
                     }
-                    if (skip) have = false;
-                    else {
-#pragma unroll
-                        for (int i = 0; i < 3; i++) {
-                            S.rowr[3 * i][t] = sk_rep(w[i] & 0x1FF);
-                            S.rowr[3 * i + 1][t] = sk_rep((w[i] >> 10) & 0x1FF);
-                            S.rowr[3 * i + 2][t] = sk_rep((w[i] >> 20) & 0x1FF);
-                            S.colp[i][t] = w[3 + i];
-                            S.boxr[3 * i][t] = sk_rep(w[6 + i] & 0x1FF);
-                            S.boxr[3 * i + 1][t] = sk_rep((w[6 + i] >> 10) & 0x1FF);
-                            S.boxr[3 * i + 2][t] = sk_rep((w[6 + i] >> 20) & 0x1FF);
-                        }
-#pragma unroll
-                        for (int rs = 0; rs < 27; rs++) {
-                            const int cell0 = (rs / 3) * 9 + (rs % 3) * 3;       // compile-time
-                            uint32_t m = 0;
-#pragma unroll
-                            for (int f = 0; f < 3; f++) {
-                                const int c = cell0 + f;
-                                const uint32_t bw = c < 32 ? b0 : (c < 64 ? b1 : b2);
-                                if ((bw >> (c & 31)) & 1u) m |= 0x1FFu << (10 * f);
-                            }
-                            S.blk[rs][t] = m;
-                        }
-                        sp = 0; base_sp = 0;
-                        p = sk_next_blank(b0, b1, b2, -1);
-                        if (A.round != 0) {
-                            // resume from the snapshot: re-assign the values chosen at levels 0..hi-1; the untried
-                            // values of levels [lo, hi] are this piece's, everything shallower belongs to other pieces
-                            const int lo = (int)(levels & 0xFF), hi = (int)((levels >> 8) & 0xFF);
-                            const uint4* sb = A.snaps + (size_t)snap_id * kSnapWords;
-                            uint4 cur = make_uint4(0, 0, 0, 0);
-                            for (int l = 0; l <= hi; l++) {
-                                if ((l & 7) == 0) cur = __ldg(sb + (l >> 3));
-                                const uint32_t word = (l & 4) ? ((l & 2) ? cur.w : cur.z) : ((l & 2) ? cur.y : cur.x);
-                                const uint32_t e = (l & 1) ? (word >> 16) : (word & 0xFFFF);
-                                if (l == hi) { cand = e & 0x1FF; break; }
-                                const uint32_t v = e >> 9;
-                                const SkCell c = sk_decode(p);
-                                const uint32_t bit = 1u << v;
-                                S.rowr[c.r][t] |= sk_rep(bit);
-                                S.boxr[c.box][t] |= sk_rep(bit);
-                                S.colp[c.s][t] |= bit << (10 * c.f);
-                                S.stk[l][t] = (uint16_t)(l >= lo ? e : (e & 0xFE00u));
-                                p = sk_next_blank(b0, b1, b2, p);
-                            }
-                            sp = hi; base_sp = lo;
-                        } else if (nblank == 0) {
-                            // nothing to search: the givens are the solution (81 nodes)
-                            A.nodes[puzzle] = 81; A.status[puzzle] = 1;
-                            uint8_t* out = A.solution + (size_t)puzzle * A.stride;
-                            const uint8_t* in = A.cells + (size_t)puzzle * A.stride;
-                            for (int i = 0; i < 81; i++) out[i] = in[i];
-                            have = false;
-                        } else {
-                            const SkCell c = sk_decode(p);
-                            cand = ~(S.rowr[c.r][t] | (S.colp[c.s][t] >> (10 * c.f)) | S.boxr[c.box][t]) & 0x1FF;
-                        }
+                    if (!skip && L.nblank == 0) {
+                        // nothing to search: the givens are the solution (81 nodes); k_sudoku_finish applies the budget
+                        A.nodes[L.puzzle] = 81; A.status[L.puzzle] = 1;
+                        uint8_t* out = A.solution + (size_t)L.puzzle * A.stride;
+                        const uint8_t* in = A.cells + (size_t)L.puzzle * A.stride;
+                        for (int i = 0; i < 81; i++) out[i] = in[i];
+                        skip = true;
+                    }
+                    if (!skip) {
+                        sk_load_tables(S, t, dg);
+                        L.sp = 0; L.base_sp = 0; L.passrem = 0; L.dom_rem = 0;
+                        L.p = sk_cell_at(S, t, 0);
+                        L.enter = true;
+                        L.have = true;
                     }
                 } else if (exhausted) done = true;
             }
             chunk_pos += min((unsigned long long)n_need, avail);
-            if (__all_sync(0xFFFFFFFFu, done && !have)) break;
+            if (__all_sync(0xFFFFFFFFu, done && !L.have)) break;
         }
 
-        // ---------------- speculative tasks give up when an earlier subtree has the solution ----------------
-        if (A.round != 0 && ((++poll & 255u) == 0)) {
-            if (have && *(volatile unsigned long long*)(A.best_key + puzzle) < key_lo) {
-                A.piece_nodes[task] = 0; A.piece_found[task] = 0; have = false;
+        // ---------------- exhausted levels: step back ----------------
+        for (int rep = 0;; rep++) {
+            const bool popping = L.have && !L.enter && L.passrem == 0;
+            const uint32_t pm = __ballot_sync(0xFFFFFFFFu, popping);
+            if (pm == 0 || (rep > 0 && __popc(pm) < kPopQuorum)) break;
+            if (popping && sk_pop(S, t, L)) {
+                // the whole tree is exhausted: ForwardCheckingStep returns false
+                A.nodes[L.puzzle] = (81 - L.nblank) + L.nodes_hi + L.nodes;
+                A.status[L.puzzle] = 0;
+                uint8_t* out = A.solution + (size_t)L.puzzle * A.stride;
+                for (int i = 0; i < 81; i++) out[i] = 0;
+                L.have = false;
             }
         }
 
-        // ---------------- every value tried at this level: step back one level ----------------
-        if (have && cand == 0) {
-            if (sp == base_sp) {
-                // the task's subtree is exhausted without a solution
-                const unsigned long long tot = nodes_hi + nodes;
-                if (A.round == 0) {
-                    A.nodes[puzzle] = (81 - nblank) + tot;
-                    A.status[puzzle] = 0;
-                    uint8_t* out = A.solution + (size_t)puzzle * A.stride;
-                    for (int i = 0; i < 81; i++) out[i] = 0;
-                } else { A.piece_nodes[task] = tot; A.piece_found[task] = 0; }
-                have = false;
+        // ---------------- next passing value ----------------
+        bool fin = false;
+        if (L.have && !L.enter && L.passrem != 0 && sk_choose(S, t, L)) {
+            A.nodes[L.puzzle] = (81 - L.nblank) + L.nodes_hi + L.nodes;
+            A.status[L.puzzle] = 1;
+            fin = true;
+            L.have = false;
+        }
+
+        // ---------------- enter the next level ----------------
+        if (L.have && L.enter) {
+            L.c = sk_decode(L.p);
+            uint32_t dom, pass;
+            sk_enter(S, t, L.c, dom, pass);
+            L.dom_rem = dom; L.passrem = pass; L.enter = false;
+        }
+
+        // ---------------- node budgets ----------------
+        if (L.have && L.nodes >= limit) {
+            if (limit_is_api) {
+                A.nodes[L.puzzle] = A.user_budget + 1; A.status[L.puzzle] = 2;
+                uint8_t* out = A.solution + (size_t)L.puzzle * A.stride;
+                for (int i = 0; i < 81; i++) out[i] = 0;
             } else {
-                --sp;
-                const uint32_t e = S.stk[sp][t];
-                cand = e & 0x1FF;
-                const uint32_t bit = 1u << (e >> 9);
-                p = sk_prev_blank(b0, b1, b2, p);
-                const SkCell c = sk_decode(p);
-                S.rowr[c.r][t] ^= sk_rep(bit);
-                S.boxr[c.box][t] ^= sk_rep(bit);
-                S.colp[c.s][t] ^= bit << (10 * c.f);
+                A.status[L.puzzle] = SK_STATUS_HARD;
+                A.hard[atomicAdd(A.ctrl + SKC_HARD, 1ull)] = L.puzzle;
             }
+            L.have = false;
         }
 
-        // ---------------- AssignVar(next value) + forward check ----------------
-        if (have && cand != 0) {
-            const uint32_t bit = cand & (0u - cand);
-            cand ^= bit;
-            ++nodes;
-            const SkCell c = sk_decode(p);
-            const uint32_t rb = sk_rep(bit);
-            const uint32_t rowv = S.rowr[c.r][t] | rb;
-            uint32_t acc = 0;
-            // later cells of the same row: own word (fields above f), then the stacks to the right
-            {
-                const uint32_t sel = (0xFFFFFFFFu << (10 * c.f + 10)) & SK_FULL3;
-                const uint32_t u = rowv | S.colp[c.s][t] | S.boxr[c.box][t];
-                acc |= (u & S.blk[c.r * 3 + c.s][t] & sel) + SK_ONES;
-                for (int s2 = c.s + 1; s2 < 3; s2++) {
-                    const uint32_t u2 = rowv | S.colp[s2][t] | S.boxr[c.band * 3 + s2][t];
-                    acc |= (u2 & S.blk[c.r * 3 + s2][t]) + SK_ONES;
+        sk_store_solutions(S, A, t, fin, L.puzzle, b0, b1, b2);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_sudoku_strong: warp per hard instance.  Lane j holds cells j, j+32, j+64 in the three fields
+// of one register: bits 0-8 the cell's domain, bit 9 "this cell's single value has been
+// propagated to its peers".  Same static order, same ascending value order as the reference, plus
+// naked-single propagation to a fixed point after every assignment, so the first solution it
+// reaches is the reference's first solution.
+struct StrongSmem {
+    uint32_t peer[81][32];               // peer[x][lane]: bit 10*f set iff cell lane+32f is a peer of x
+    uint32_t saved[4][81][32];           // per warp, per level: the registers before the level's first value
+    uint16_t rest[4][81];                // per warp, per level: values still to try (0: forced level)
+};
+
+__device__ __forceinline__ bool sk_propagate(uint32_t& D, const StrongSmem& M, int lane, uint32_t valid3) {
+    for (;;) {
+        const uint32_t x3 = D & SK_FULL3;
+        const uint32_t zero = ~(x3 + (SK_SPARE - SK_ONES)) & SK_SPARE & (valid3 << 9);    // spare bit of the EMPTY fields
+        if (__any_sync(0xFFFFFFFFu, zero != 0)) return false;
+        const uint32_t unfl = ~D & SK_SPARE & (valid3 << 9);
+        const uint32_t sing = sk_singletons(x3 & ((unfl >> 9) * 0x1FFu));
+        const uint32_t b = __ballot_sync(0xFFFFFFFFu, sing != 0);
+        if (!b) return true;
+        const int j = __ffs(b) - 1;
+        const uint32_t sj = __shfl_sync(0xFFFFFFFFu, sing, j);
+        const int f = (sj & 0x1FF) ? 0 : (((sj >> 10) & 0x1FF) ? 1 : 2);
+        const uint32_t bit = (sj >> (10 * f)) & 0x1FF;
+        if (lane == j) D |= 0x200u << (10 * f);
+        D &= ~(M.peer[j + 32 * f][lane] * bit);
+    }
+}
+
+__global__ void __launch_bounds__(128)
+k_sudoku_strong(SudokuArgs A) {
+    extern __shared__ __align__(16) unsigned char sk_raw[];
+    StrongSmem& M = *reinterpret_cast<StrongSmem*>(sk_raw);
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    // peer table, once per CTA
+    for (int i = threadIdx.x; i < 81 * 32; i += blockDim.x) {
+        const int x = i >> 5, l = i & 31;
+        const int xr = x / 9, xc = x % 9;
+        uint32_t m = 0;
+        for (int f = 0; f < 3; f++) {
+            const int q = l + 32 * f;
+            if (q >= 81 || q == x) continue;
+            const int qr = q / 9, qc = q % 9;
+            if (qr == xr || qc == xc || (qr / 3 == xr / 3 && qc / 3 == xc / 3)) m |= 1u << (10 * f);
+        }
+        M.peer[x][l] = m;
+    }
+    __syncthreads();
+    const uint32_t valid3 = lane < 17 ? SK_ONES : 0x00000401u;      // lanes 17..31 hold two cells
+    const unsigned long long n_hard = A.ctrl[SKC_HARD];
+    for (;;) {
+        unsigned long long idx = 0;
+        if (lane == 0) idx = atomicAdd(A.ctrl + SKC_HARD_CUR, 1ull);
+        idx = __shfl_sync(0xFFFFFFFFu, idx, 0);
+        if (idx >= n_hard) break;
+        const uint32_t puzzle = A.hard[idx];
+        const uint8_t* in = A.cells + (size_t)puzzle * A.stride;
+        const uint32_t* dw = reinterpret_cast<const uint32_t*>(A.digest[puzzle].v);
+        const int nblank = (int)(__ldg(dw + 3) & 0xFF);
+        const uint32_t cw = lane < 21 ? __ldg(dw + 52 + lane) : 0u;          // cell ids per level, four per word
+        // initial domains from the digest's used masks; givens are singletons already propagated
+        uint32_t D = 0;
+#pragma unroll
+        for (int f = 0; f < 3; f++) {
+            const int q = lane + 32 * f;
+            if (q < 81) {
+                const uint32_t g = in[q];
+                uint32_t field;
+                if (g) field = (1u << (g - 1)) | 0x200u;
+                else {
+                    const SkCell k = sk_decode(q);
+                    field = ~(__ldg(dw + 4 + k.r) | (__ldg(dw + 13 + k.s) >> (10 * k.f)) | __ldg(dw + 16 + k.box)) & 0x1FF;
                 }
+                D |= field << (10 * f);
             }
-            // later rows: inside the band the whole box-row is a peer, below it only the column cell
-            {
-                const uint32_t colv = S.colp[c.s][t] | rb;
-                const int in_band_last = c.band * 3 + 2;
-                const uint32_t boxv = S.boxr[c.box][t] | rb;
-                for (int r2 = c.r + 1; r2 <= in_band_last; r2++) {
-                    const uint32_t u = S.rowr[r2][t] | colv | boxv;
-                    acc |= (u & S.blk[r2 * 3 + c.s][t]) + SK_ONES;
+        }
+        // explicit-stack DFS over the blank levels; `back` = the level was reached by stepping back
+        int l = sk_propagate(D, M, lane, valid3) ? 0 : -1;
+        bool back = false;
+        while (l >= 0 && l < nblank) {
+            const int p = (int)((__shfl_sync(0xFFFFFFFFu, cw, l >> 2) >> ((l & 3) * 8)) & 0xFF);
+            const int owner = p & 31, f = p >> 5;
+            uint32_t d;
+            if (!back) {
+                const uint32_t w = __shfl_sync(0xFFFFFFFFu, D, owner) >> (10 * f);
+                if (w & 0x200u) {                          // forced: its single value is already everywhere
+                    if (lane == 0) M.rest[wib][l] = 0;
+                    __syncwarp();
+                    ++l;
+                    continue;
                 }
-                const uint32_t fsel = 0x1FFu << (10 * c.f);
-                for (int r2 = in_band_last + 1; r2 < 9; r2++) {
-                    const int box2 = ((r2 * 11) >> 5) * 3 + c.s;
-                    const uint32_t u = S.rowr[r2][t] | colv | S.boxr[box2][t];
-                    acc |= (u & S.blk[r2 * 3 + c.s][t] & fsel) + SK_ONES;
-                }
+                d = w & 0x1FF;
+                M.saved[wib][l][lane] = D;
+            } else d = M.rest[wib][l];
+            bool ok = false;
+            while (d) {                                    // the level's values in ascending order, each from the saved state
+                const uint32_t v = d & (0u - d);
+                d ^= v;
+                D = M.saved[wib][l][lane];
+                if (lane == owner) D = (D & ~(0x3FFu << (10 * f))) | ((v | 0x200u) << (10 * f));
+                D &= ~(M.peer[p][lane] * v);
+                if (sk_propagate(D, M, lane, valid3)) { ok = true; break; }
             }
-            if ((acc & SK_SPARE) == 0) {
-                // no wipe-out: the value stands
-                const uint32_t v = __ffs(bit) - 1;
-                if (sp == nblank - 1) {
-                    // last blank assigned: the DFS-first solution of this subtree
-                    S.stk[sp][t] = (uint16_t)(v << 9);
-                    const unsigned long long tot = nodes_hi + nodes;
-                    uint8_t* out;
-                    if (A.round == 0) {
-                        const unsigned long long all = (81 - nblank) + tot;
-                        const bool over = A.user_budget && all > A.user_budget;
-                        A.nodes[puzzle] = over ? A.user_budget + 1 : all;
-                        A.status[puzzle] = over ? 2 : 1;
-                        out = A.solution + (size_t)puzzle * A.stride;
-                        if (over) { for (int i = 0; i < 81; i++) out[i] = 0; out = nullptr; }
-                    } else {
-                        A.piece_nodes[task] = tot; A.piece_found[task] = 1;
-                        atomicMin(A.best_key + puzzle, key_lo);
-                        out = A.piece_sol + (size_t)task * 81;
+            __syncwarp();
+            if (lane == 0) M.rest[wib][l] = (uint16_t)d;
+            __syncwarp();
+            if (ok) { ++l; back = false; }
+            else {
+                --l;
+                while (l >= 0 && M.rest[wib][l] == 0) --l;
+                back = true;
+            }
+        }
+        const bool sat = l == nblank;
+        // result: the reference's first solution, or none
+        uint8_t* out = A.solution + (size_t)puzzle * A.stride;
+#pragma unroll
+        for (int f = 0; f < 3; f++) {
+            const int q = lane + 32 * f;
+            if (q < 81) out[q] = sat ? (uint8_t)__ffs((D >> (10 * f)) & 0x1FF) : (uint8_t)0;
+        }
+        if (lane == 0) A.status[puzzle] = sat ? 1 : 0;
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_sudoku_walk: lane per hard instance.  Follows the solution k_sudoku_strong found (or, for an
+// instance without one, stands at the root) and accounts for the reference's plain
+// forward-checking search: nodes[instance] = givens + the values tried at each path level up to
+// the solution's; every earlier value that passes its forward check becomes a root task whose
+// whole subtree k_sudoku_count adds.
+__global__ void __launch_bounds__(kSudokuBlock)
+k_sudoku_walk(SudokuArgs A) {
+    extern __shared__ __align__(16) unsigned char sk_raw[];
+    SudokuSmem& S = *reinterpret_cast<SudokuSmem*>(sk_raw);
+    const int t = threadIdx.x;
+    const int lane = t & 31;
+    const unsigned long long n_hard = A.ctrl[SKC_HARD];
+    for (;;) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(A.ctrl + SKC_WALK_CUR, 32ull);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (base >= n_hard) break;
+        const bool active = base + lane < n_hard;
+        const uint32_t puzzle = active ? A.hard[base + lane] : 0u;
+        int nblank = 0;
+        bool sat = false;
+        if (active) {
+            const uint4* dg = A.digest[puzzle].v;
+            nblank = (int)(__ldg(dg).w & 0xFF);
+            sk_load_tables(S, t, dg);
+            sat = A.status[puzzle] == 1;
+        }
+        const uint8_t* sol = A.solution + (size_t)puzzle * A.stride;
+        unsigned long long direct = 0;
+        int levels = active ? (sat ? nblank : 1) : 0;
+        const int max_levels = __reduce_max_sync(0xFFFFFFFFu, levels);
+        for (int l = 0; l < max_levels; l++) {
+            if (l < levels) {
+                const int p = sk_cell_at(S, t, l);
+                const SkCell c = sk_decode(p);
+                uint32_t dom, pass;
+                sk_enter(S, t, c, dom, pass);
+                uint32_t V, bit = 0;
+                if (sat) {
+                    bit = 1u << (sol[p] - 1);
+                    direct += __popc(dom & (bit | (bit - 1u)));      // tried in ascending order up to the solution's value
+                    V = pass & (bit - 1u);
+                    if (!(pass & bit)) atomicOr(A.ctrl + SKC_ERROR, 8ull);
+                } else {
+                    direct += __popc(dom);                           // no solution: every value of the first blank is tried
+                    V = pass;
+                }
+                if (V) {
+                    const unsigned k = __popc(V);
+                    unsigned long long slot = atomicAdd(A.ctrl + SKC_RESERVE, (unsigned long long)k);
+                    const unsigned long long room = slot < A.task_cap ? A.task_cap - slot : 0;
+                    const unsigned kk = (unsigned)min((unsigned long long)k, room);
+                    if (kk < k) atomicOr(A.ctrl + SKC_ERROR, 2ull);
+                    if (kk) atomicAdd(A.ctrl + SKC_OUTSTANDING, (unsigned long long)kk);
+                    uint32_t vv = V;
+                    for (unsigned i = 0; i < kk; i++) {
+                        const uint32_t v = __ffs(vv) - 1;
+                        vv &= vv - 1;
+                        *reinterpret_cast<uint4*>(A.tasks + slot + i) = make_uint4(puzzle, 0u, SKT_VALID | SKT_ROOT | (uint32_t)l | (v << 8), 0u);
                     }
-                    if (out) {
-                        const uint8_t* in = A.cells + (size_t)puzzle * A.stride;
-                        int l = 0;
-                        for (int i = 0; i < 81; i++) {
-                            const uint32_t bw = i < 32 ? b0 : (i < 64 ? b1 : b2);
-                            if ((bw >> (i & 31)) & 1u) { out[i] = (uint8_t)((S.stk[l][t] >> 9) + 1); ++l; }
-                            else out[i] = in[i];
+                }
+                if (sat) sk_commit(S, t, c, bit);
+            }
+        }
+        if (active) A.nodes[puzzle] = (unsigned long long)(81 - nblank) + direct;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_sudoku_count: ONE persistent launch.  Lanes take tasks from the queue and count their subtrees
+// exhaustively; a warp leaves when no task is outstanding.  Load balance is demand driven: idle
+// lanes draw tickets for queue slots that are not published yet; busy lanes look every
+// kDonatePeriod steps and, while tickets are waiting, hand over the SHALLOWEST stack level that
+// still has untried passing values as a new task (a "piece").  A piece owns stack levels [lo, hi] of the
+// donor's snapshot; the donor keeps the deeper ones.  Every level is owned by exactly one task,
+// which also counts the level's failing leftovers when it steps back through it.
+constexpr int kDonatePeriod = 32;
+constexpr uint32_t kDonateMinNodes = 128;   // a task younger than this keeps its stack to itself
+constexpr uint32_t kDonateGap = 256;        // ... and so does one that gave a level away fewer nodes ago than this
+
+__global__ void __launch_bounds__(kSudokuBlock)
+k_sudoku_count(SudokuArgs A) {
+    extern __shared__ __align__(16) unsigned char sk_raw[];
+    SudokuSmem& S = *reinterpret_cast<SudokuSmem*>(sk_raw);
+    const int t = threadIdx.x;
+    const int lane = t & 31;
+    const uint32_t lt = (1u << lane) - 1u;
+    const unsigned long long total_warps = (unsigned long long)gridDim.x * (kSudokuBlock / 32);
+    volatile unsigned long long* vctrl = A.ctrl;
+
+    SkLane L = {};
+    uint32_t donate_at = 0;                 // node count from which the task may give a level away
+    bool waiting = false, poll_now = false; // holds a ticket for a queue slot that is not published yet
+    unsigned long long ticket = 0;
+    int iter = 0;
+    unsigned spins = 0;
+
+    for (;;) {
+        // ---------------- refill from the task queue ----------------
+        // An idle lane draws a TICKET (the next queue slot, atomicAdd — no contention window) and waits for that slot
+        // to be published.  Slots already written (the walker's root tasks) are there at once; a ticket beyond the
+        // published end is a standing order that the next donor fills: tickets drawn minus tasks reserved IS the
+        // number of hungry lanes.
+        {
+            const uint32_t need = __ballot_sync(0xFFFFFFFFu, !L.have && !waiting);
+            if (need) {
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(A.ctrl + SKC_HEAD, (unsigned long long)__popc(need));
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                if (!L.have && !waiting) { ticket = base + __popc(need & lt); waiting = true; poll_now = true; }
+            }
+        }
+        unsigned closed_now = 0;                // tasks this lane took and closed on the spot
+        if (waiting && (poll_now || (iter & 7) == 0) && ticket < A.task_cap) {
+            volatile uint32_t* rec = reinterpret_cast<volatile uint32_t*>(A.tasks + ticket);
+            const uint32_t info = rec[2];       // the publisher writes `info` last
+            if (info) {
+                __threadfence();
+                waiting = false;
+                L.puzzle = rec[0];
+                const uint32_t snap_id = rec[1];
+                if (info & SKT_NULL) closed_now = 1;
+                else {
+                    const uint4* dg = A.digest[L.puzzle].v;
+                    L.nblank = (int)(__ldg(dg).w & 0xFF);
+                    sk_load_tables(S, t, dg);
+                    L.nodes = 0; L.nodes_hi = 0;
+                    L.passrem = 0; L.dom_rem = 0;
+                    L.have = true;
+                    donate_at = A.force_donate ? A.force_donate : kDonateMinNodes;
+                    if (info & SKT_ROOT) {
+                        // path values at the levels above, then the task's own value at its level
+                        const int l0 = (int)(info & 0xFF);
+                        const uint32_t v0 = (info >> 8) & 0xF;
+                        const uint8_t* sol = A.solution + (size_t)L.puzzle * A.stride;
+                        for (int l = 0; l <= l0; l++) {
+                            const int q = sk_cell_at(S, t, l);
+                            const uint32_t v = l < l0 ? (uint32_t)sol[q] - 1u : v0;
+                            sk_commit(S, t, sk_decode(q), 1u << v);
+                            S.stk[l][t] = (uint16_t)(v << 9);
                         }
+                        L.sp = l0 + 1; L.base_sp = l0 + 1;
+                        if (L.sp >= L.nblank) { atomicOr(A.ctrl + SKC_ERROR, 4ull); L.have = false; closed_now = 1; }
+                        else { L.p = sk_cell_at(S, t, L.sp); L.enter = true; }
+                    } else {
+                        // resume from the donor's snapshot: re-assign the values chosen at levels 0..hi-1; the untried
+                        // values of levels [lo, hi] are this piece's, everything shallower belongs to other tasks
+                        const int lo = (int)(info & 0xFF), hi = (int)((info >> 8) & 0xFF);
+                        const uint4* sb = A.snaps + (size_t)snap_id * kSnapWords;
+                        auto entry = [&](int l) -> uint32_t {
+                            const uint4 cur = __ldcg(sb + (l >> 3));
+                            const uint32_t word = (l & 4) ? ((l & 2) ? cur.w : cur.z) : ((l & 2) ? cur.y : cur.x);
+                            return (l & 1) ? (word >> 16) : (word & 0xFFFF);
+                        };
+                        for (int l = 0; l < hi; l++) {
+                            const uint32_t e = entry(l);
+                            sk_commit(S, t, sk_decode(sk_cell_at(S, t, l)), 1u << (e >> 9));
+                            S.stk[l][t] = (uint16_t)(l >= lo ? e : (e & 0xFE00u));
+                        }
+                        L.sp = hi; L.base_sp = lo;
+                        L.p = sk_cell_at(S, t, hi);
+                        L.c = sk_decode(L.p);
+                        const uint32_t e = entry(hi);
+                        L.passrem = e & 0x1FF;
+                        L.dom_rem = ~sk_used_at(S, t, L.c) & 0x1FF & ~((2u << (e >> 9)) - 1u);   // the values above the one the donor took here
+                        L.enter = false;
                     }
-                    have = false;
-                } else {
-                    S.rowr[c.r][t] = rowv;
-                    S.boxr[c.box][t] |= rb;
-                    S.colp[c.s][t] |= bit << (10 * c.f);
-                    S.stk[sp][t] = (uint16_t)(cand | (v << 9));
-                    ++sp;
-                    p = sk_next_blank(b0, b1, b2, p);
-                    const SkCell n = sk_decode(p);
-                    cand = ~(S.rowr[n.r][t] | (S.colp[n.s][t] >> (10 * n.f)) | S.boxr[n.box][t]) & 0x1FF;
                 }
             }
-            // ---------------- node budget of the task ----------------
-            if (nodes >= 0x80000000u) { nodes_hi += nodes; nodes = 0; }      // only unlimited tasks get here
-            if (have && nodes >= limit) {
-                if (stop_is_budget) {
-                    A.nodes[puzzle] = A.user_budget + 1; A.status[puzzle] = 2;
-                    uint8_t* out = A.solution + (size_t)puzzle * A.stride;
-                    for (int i = 0; i < 81; i++) out[i] = 0;
-                    have = false;
-                } else {
-                    // Split: the untried values left on the stack, levels [base_sp, sp], are cut into up to four
-                    // contiguous level groups.  DFS order is deepest first, so the deepest group continues this
-                    // task's own search and gets the lowest key interval; the shallowest levels — the largest
-                    // subtrees — get a group each.
-                    int m = cand ? 1 : 0;
-                    for (int l = base_sp; l < sp; l++) m += (S.stk[l][t] & 0x1FF) ? 1 : 0;
-                    const int groups = m < 4 ? m : 4;
-                    const unsigned long long width = (key_hi - key_lo) / (unsigned long long)(groups + 1);
-                    unsigned long long slot = 0, sslot = 0;
-                    bool ok = m > 0 && width > 0;
-                    if (ok) {
-                        slot = atomicAdd(A.ctrl + 1, (unsigned long long)groups);
-                        sslot = atomicAdd(A.ctrl + 2, 1ull);
-                        ok = slot + groups <= A.piece_cap && sslot < A.snap_cap;
-                        if (!ok)                                                 // pool full: fill what was reserved with null pieces
-                            for (unsigned long long i = slot; i < slot + groups && i < A.piece_cap; i++) {
-                                uint4* pr = reinterpret_cast<uint4*>(A.pieces + i);
-                                pr[0] = make_uint4(puzzle, 0u, 0xFFFFFFFFu, 0u);
-                                pr[1] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
-                            }
-                    }
-                    if (!ok) limit = 0xFFFFFFFFu;          // nothing to hand over, or key space / pool exhausted: finish unsplit
-                    else {
-                        // stack snapshot: levels 0..sp, entry sp = the current cell's untried values
+        }
+        poll_now = false;
+        {
+            const uint32_t cm = __ballot_sync(0xFFFFFFFFu, closed_now != 0);
+            if (cm && lane == 0) atomicAdd(A.ctrl + SKC_OUTSTANDING, 0ull - (unsigned long long)__popc(cm));
+            if (cm) continue;                   // the lanes that closed a task on the spot draw again
+        }
+        if (__ballot_sync(0xFFFFFFFFu, L.have) == 0) {
+            // nobody in the warp has work: leave when nothing is outstanding anywhere, else wait on the tickets
+            unsigned long long out = 0;
+            if (lane == 0) out = vctrl[SKC_OUTSTANDING];
+            out = __shfl_sync(0xFFFFFFFFu, out, 0);
+            if (out == 0) break;
+            __nanosleep(200);
+            if (++spins > 8000000u) { if (lane == 0) atomicOr(A.ctrl + SKC_ERROR, 1ull); break; }
+            poll_now = true;
+            continue;
+        }
+        spins = 0;
+        ++iter;
+
+        // ---------------- donate work while lanes elsewhere are hungry ----------------
+        if ((iter & (kDonatePeriod - 1)) == 0) {
+            long long demand = 0;
+            if (lane == 0) {
+                const unsigned long long h = vctrl[SKC_HEAD], r = vctrl[SKC_RESERVE];
+                demand = h > r ? (long long)(h - r) : 0;                       // tickets waiting for a task to be published
+                if (A.force_donate) demand = (long long)total_warps * 8;
+            }
+            demand = __shfl_sync(0xFFFFFFFFu, demand, 0);
+            if (demand > 0) {
+                // eligible: an established task with an untried passing value on a level below the current one
+                int hl = -1;
+                if (L.have && !L.enter && L.nodes >= donate_at) {
+                    int l = L.base_sp;
+                    while (l < L.sp && (S.stk[l][t] & 0x1FF) == 0) ++l;
+                    if (l < L.sp) hl = l;
+                }
+                const uint32_t elig = __ballot_sync(0xFFFFFFFFu, hl >= 0);
+                const long long quota = min((long long)8, demand / (long long)total_warps + 1);
+                if (hl >= 0 && (long long)__popc(elig & lt) < quota) {
+                    atomicAdd(A.ctrl + SKC_OUTSTANDING, 1ull);                 // the piece exists from here on
+                    const unsigned long long slot = atomicAdd(A.ctrl + SKC_RESERVE, 1ull);
+                    const unsigned long long sslot = atomicAdd(A.ctrl + SKC_SNAP, 1ull);
+                    if (slot >= A.task_cap) atomicAdd(A.ctrl + SKC_OUTSTANDING, 0ull - 1ull);      // pool full: nobody will ever claim it
+                    else if (sslot >= A.snap_cap) {
+                        // publish a null task: whoever claims it closes it
+                        volatile uint32_t* rec = reinterpret_cast<volatile uint32_t*>(A.tasks + slot);
+                        rec[0] = L.puzzle; rec[1] = 0;
+                        __threadfence();
+                        rec[2] = SKT_VALID | SKT_NULL;
+                    } else {
+                        // stack snapshot, levels 0..hl
                         uint4* sb = A.snaps + (size_t)sslot * kSnapWords;
-                        for (int q = 0; q * 8 <= sp; q++) {
+                        for (int q = 0; q * 8 <= hl; q++) {
                             uint32_t w4[4];
 #pragma unroll
                             for (int i = 0; i < 4; i++) {
                                 const int l0 = q * 8 + 2 * i, l1 = l0 + 1;
-                                const uint32_t e0 = l0 < sp ? (uint32_t)S.stk[l0][t] : (l0 == sp ? cand : 0u);
-                                const uint32_t e1 = l1 < sp ? (uint32_t)S.stk[l1][t] : (l1 == sp ? cand : 0u);
+                                const uint32_t e0 = l0 <= hl ? (uint32_t)S.stk[l0][t] : 0u;
+                                const uint32_t e1 = l1 <= hl ? (uint32_t)S.stk[l1][t] : 0u;
                                 w4[i] = e0 | (e1 << 16);
                             }
-                            sb[q] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+                            __stcg(sb + q, make_uint4(w4[0], w4[1], w4[2], w4[3]));
                         }
-                        // group g (0 = shallowest) takes 1, 1, 2 non-empty levels; the deepest group takes the rest
-                        unsigned long long k = key_lo + width * (unsigned long long)groups;   // shallowest = last in DFS order
-                        int l = base_sp;
-                        int left = m;
-                        for (int g = 0; g < groups; g++) {
-                            int take = g == groups - 1 ? left : (g == 2 ? 2 : 1);
-                            if (take > left - (groups - 1 - g)) take = left - (groups - 1 - g);
-                            int lo_l = -1, hi_l = -1;
-                            while (take > 0) {
-                                const uint32_t cl = l == sp ? cand : (uint32_t)(S.stk[l][t] & 0x1FF);
-                                if (cl) { if (lo_l < 0) lo_l = l; hi_l = l; --take; --left; }
-                                ++l;
-                            }
-                            uint4* pr = reinterpret_cast<uint4*>(A.pieces + slot + g);
-                            pr[0] = make_uint4(puzzle, (uint32_t)sslot, (uint32_t)lo_l | ((uint32_t)hi_l << 8), 0u);
-                            pr[1] = make_uint4((uint32_t)k, (uint32_t)(k >> 32), (uint32_t)(k + width), (uint32_t)((k + width) >> 32));
-                            k -= width;
-                        }
-                        const unsigned long long tot = nodes_hi + nodes;
-                        if (A.round == 0) {
-                            A.nodes[puzzle] = (81 - nblank) + tot;          // the part before every piece; pieces add to it
-                            A.status[puzzle] = SK_STATUS_SPLIT;
-                        } else { A.piece_nodes[task] = tot; A.piece_found[task] = 0; }
-                        have = false;
+                        volatile uint32_t* rec = reinterpret_cast<volatile uint32_t*>(A.tasks + slot);
+                        rec[0] = L.puzzle; rec[1] = (uint32_t)sslot;
+                        __threadfence();
+                        rec[2] = SKT_VALID | (uint32_t)L.base_sp | ((uint32_t)hl << 8);
+                        L.base_sp = hl + 1;                                      // this task keeps the deeper levels
+                        donate_at = L.nodes + (A.force_donate ? A.force_donate : kDonateGap);
                     }
                 }
             }
         }
+
+        // ---------------- exhausted levels: step back ----------------
+        unsigned closed = 0;
+        for (int rep = 0;; rep++) {
+            const bool popping = L.have && !L.enter && L.passrem == 0;
+            const uint32_t pm = __ballot_sync(0xFFFFFFFFu, popping);
+            if (pm == 0 || (rep > 0 && __popc(pm) < kPopQuorum)) break;
+            if (popping && sk_pop(S, t, L)) {
+                atomicAdd(A.nodes + L.puzzle, L.nodes_hi + L.nodes);             // every node of the subtree is a node of the reference
+                L.have = false; closed = 1;
+            }
+        }
+
+        // ---------------- next passing value ----------------
+        if (L.have && !L.enter && L.passrem != 0 && sk_choose(S, t, L))
+            atomicOr(A.ctrl + SKC_ERROR, 4ull);                                  // a subtree left of the first solution cannot hold one
+
+        // ---------------- enter the next level ----------------
+        if (L.have && L.enter) {
+            L.c = sk_decode(L.p);
+            uint32_t dom, pass;
+            sk_enter(S, t, L.c, dom, pass);
+            L.dom_rem = dom; L.passrem = pass; L.enter = false;
+        }
+        if (L.nodes >= 0x80000000u) { L.nodes_hi += L.nodes; L.nodes = 0; donate_at = 0; }
+
+        // ---------------- closed tasks leave the outstanding count ----------------
+        {
+            const uint32_t cm = __ballot_sync(0xFFFFFFFFu, closed != 0);
+            if (cm && lane == 0) atomicAdd(A.ctrl + SKC_OUTSTANDING, 0ull - (unsigned long long)__popc(cm));
+        }
     }
 }
 
-// After the last round.  Pass 1: every piece that holds a solution has already lowered best_key
-// (atomicMin in the search).  Pass 2, one thread per piece: add its nodes if it lies at or before
-// the puzzle's first solution in DFS order; the piece AT the first solution writes it out.
-__global__ void k_sudoku_account(SudokuArgs A, unsigned long long n_pieces) {
-    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_pieces) return;
-    const SudokuPiece pc = A.pieces[i];
-    if (pc.levels == 0xFFFFFFFFu) return;
-    const unsigned long long best = A.best_key[pc.puzzle];
-    if (pc.key_lo > best) return;
-    atomicAdd(A.nodes + pc.puzzle, A.piece_nodes[i]);
-    if (pc.key_lo == best && A.piece_found[i]) {
-        uint8_t* out = A.solution + (size_t)pc.puzzle * A.stride;
-        const uint8_t* in = A.piece_sol + (size_t)i * 81;
-        for (int c = 0; c < 81; c++) out[c] = in[c];
-        A.status[pc.puzzle] = 1;
-    }
-}
-
-// Pass 3, one thread per instance: split puzzles without a winner are UNSAT; the API node budget is
-// applied to the exact totals; batch totals.
+// Last pass, one thread per instance: the API node budget applied to the exact totals; batch totals.
 __global__ void k_sudoku_finish(SudokuArgs A, unsigned long long* totals) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned sat = 0, unsat = 0, budget = 0;
@@ -558,11 +887,6 @@ __global__ void k_sudoku_finish(SudokuArgs A, unsigned long long* totals) {
     if (i < A.n) {
         uint8_t st = A.status[i];
         if (st != SK_STATUS_DEFER) {
-            if (st == SK_STATUS_SPLIT) {
-                st = 0;
-                uint8_t* out = A.solution + (size_t)i * A.stride;
-                for (int c = 0; c < 81; c++) out[c] = 0;
-            }
             if (A.user_budget && A.nodes[i] > A.user_budget && st != 2) {
                 st = 2;
                 A.nodes[i] = A.user_budget + 1;

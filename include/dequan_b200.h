@@ -135,9 +135,10 @@ typedef struct dq_tree_result {
 typedef struct dq_batch_opts {
     uint64_t node_budget;    /* per instance, 0 = unlimited                         */
     int32_t  engine;         /* dq_engine                                           */
-    int32_t  task_nodes;     /* lane engine: nodes one lane spends on a search before
-                                handing the rest of its stack to the task pool;
-                                0 = default (8192)                                  */
+    int32_t  task_nodes;     /* lane engine test knob: > 0 makes every search older than
+                                this many nodes hand stack levels to the task pool
+                                whether or not other lanes are idle; 0 = demand
+                                driven (production)                                 */
 } dq_batch_opts;
 
 typedef struct dq_batch_stats {
