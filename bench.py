@@ -11,8 +11,8 @@ One "step" = one complete solve of the workload through the C ABI:
   N  > 1 : BASELINE config C5, 17-Queens all-solutions, FC-surviving prefixes dealt round-robin
            to the ranks, {solutions, nodes} summed with NCCL (strong scaling).
 `value`  : inputs/tables already resident in HBM (compiled model re-used), whole-job nodes/s.
-`e2e`    : the same through the host-facing calls with host buffers: dq_compile (CSP::FinalizeModel
-           + Assignment::Reset) + table upload + solve + result read-back, every step.
+`e2e`    : the same through the host-facing C-ABI calls with HOST buffers, every step: dq_compile of the flat
+           model descriptor (CSP::FinalizeModel + Assignment::Reset), table upload, solve, result read-back, dq_free.
 Every result of every step is checked against the known answers; a mismatch aborts the bench.
 """
 from __future__ import annotations
@@ -246,8 +246,10 @@ def main():
         sampler.start()
     tot, kern_ms, launches = timed_steps(lambda: solve_step(model), args.steps, args.warmup)
 
+    desc_keep = csp.desc()          # the host-side flat descriptor: the input buffers of the C-ABI call
+
     def e2e_step():
-        m = api.Model(csp)          # dq_compile: FinalizeModel + Reset on the host, tables uploaded by the solve
+        m = api.Model(csp, desc_keep)   # dq_compile: FinalizeModel + Reset on the host, tables uploaded by the solve
         r = solve_step(m)
         m.close()
         return r
@@ -356,7 +358,7 @@ def sudoku_section(args, torch, api, dev, hbm_peak, peak_src, int_peak):
                       "l2": "inputs+outputs 171 MB per step > 126 MB L2"},
            "e2e": {"value": n * steps / e_tot, "unit": "puzzles/s", "h2d_bytes_per_step": n * 81, "d2h_bytes_per_step": n * 90,
                    "ms_per_step": 1e3 * e_tot / steps},
-           "gpu_launches": launches,
+           "gpu_launches": launches, "engine": "lane pipeline (digest, first, strong, walk, count, finish)",
            "roofline": {"bound": "hbm", "achieved": kpps * 174 / 1e9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": kpps * 174 / 1e9 / hbm_peak, "traffic": None, "bytes_per_puzzle": 174, "peak_source": peak_src,
                         "note": "instance stream only; the search itself is integer-issue bound (see roofline_int)"},
@@ -370,6 +372,9 @@ def sudoku_section(args, torch, api, dev, hbm_peak, peak_src, int_peak):
             f.write("\n".join(G.sudoku_lines(cells[:sample])) + "\n")
         thr = cpu_threads()
         o = run_ref(["sudoku", path, "boxes", thr, sample, "quiet"])[-1]
+        # parity at scale against the unmodified reference: the node total of the sample must be the reference's
+        assert int(h_nodes.numpy()[:sample].sum()) == int(o["nodes"]), ("sudoku node total differs from the reference",
+                                                                      int(h_nodes.numpy()[:sample].sum()), o["nodes"])
         out["cpu_baseline"] = {"value": o["puzzles"] / o["wall_seconds"], "unit": "puzzles/s", "cores": thr, "kind": "reference",
                                "sample": f"first {sample} puzzles of the same batch, one puzzle per thread, model build included "
                                          f"(solve-only {o['puzzles'] / o['solve_seconds_sum'] * thr:.0f} puzzles/s)",

@@ -146,8 +146,10 @@ class BatchResult:
 class Model:
     """A compiled model: `dq_compile` of a CSP (CSP::FinalizeModel + Assignment::Reset)."""
 
-    def __init__(self, csp: CSP):
-        desc, keep = csp.desc()
+    def __init__(self, csp: CSP, desc_keep=None):
+        """`desc_keep` = a (dq_model_desc, keepalive) pair from an earlier `csp.desc()`: compile straight from the
+        host arrays (what the C++ drop-in header hands to dq_compile) without rebuilding them in Python."""
+        desc, keep = desc_keep if desc_keep is not None else csp.desc()
         h = C.c_void_p()
         _check(lib().dq_compile(C.byref(desc), C.byref(h)))
         del keep

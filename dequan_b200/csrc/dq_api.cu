@@ -27,20 +27,89 @@ static thread_local std::string g_err;
         }                                                                                   \
     } while (0)
 
+// Device memory comes from a per-thread cache of freed blocks: compiling and solving a fresh model per call (the
+// drop-in header's pattern: one CSP, one ForwardCheckingStep) must not pay cudaMalloc/cudaFree (each a device-wide
+// synchronisation) every time.  Blocks are handed back to the driver only by dq_trim() or at thread exit.
+struct BlockCache {
+    struct Block { void* p; size_t bytes; int dev; };
+    std::vector<Block> free_blocks;
+    size_t cached_bytes = 0;
+    cudaError_t take(size_t bytes, void** out) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        size_t best = free_blocks.size();
+        for (size_t i = 0; i < free_blocks.size(); i++) {
+            const Block& b = free_blocks[i];
+            if (b.dev != dev || b.bytes < bytes || b.bytes > 2 * bytes + (1u << 20)) continue;
+            if (best == free_blocks.size() || b.bytes < free_blocks[best].bytes) best = i;
+        }
+        if (best != free_blocks.size()) {
+            *out = free_blocks[best].p;
+            cached_bytes -= free_blocks[best].bytes;
+            free_blocks.erase(free_blocks.begin() + best);
+            return cudaSuccess;
+        }
+        cudaError_t e = cudaMalloc(out, bytes);
+        if (e != cudaSuccess && !free_blocks.empty()) {          // make room and try once more
+            trim();
+            e = cudaMalloc(out, bytes);
+        }
+        return e;
+    }
+    void give(void* p, size_t bytes) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        free_blocks.push_back(Block{p, bytes, dev});
+        cached_bytes += bytes;
+        if (cached_bytes > (size_t)8 << 30) trim();               // keep at most 8 GiB parked
+    }
+    void trim() {
+        for (const Block& b : free_blocks) cudaFree(b.p);
+        free_blocks.clear();
+        cached_bytes = 0;
+    }
+    ~BlockCache() { /* the context may already be gone at thread exit: leave the blocks to the driver */ }
+};
+static thread_local BlockCache g_cache;
+
 template <class T>
 struct DevBuf {
     T* p = nullptr;
-    size_t cap = 0;
+    size_t cap = 0, bytes = 0;
     cudaError_t reserve(size_t n) {
         if (n <= cap) return cudaSuccess;
-        if (p) cudaFree(p);
-        p = nullptr; cap = 0;
-        cudaError_t e = cudaMalloc((void**)&p, std::max<size_t>(n, 1) * sizeof(T));
-        if (e == cudaSuccess) cap = n;
+        release();
+        const size_t want = std::max<size_t>(n, 1) * sizeof(T);
+        cudaError_t e = g_cache.take(want, (void**)&p);
+        if (e == cudaSuccess) { cap = n; bytes = want; }
+        else p = nullptr;
         return e;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    void release() { if (p) g_cache.give(p, bytes); p = nullptr; cap = 0; bytes = 0; }
 };
+
+// Stream + timing events are per thread and device, shared by every handle.
+struct DeviceCtx {
+    int dev = -1, sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+static thread_local std::vector<DeviceCtx> g_ctx;
+static cudaError_t device_ctx(DeviceCtx** out) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    for (DeviceCtx& c : g_ctx) if (c.dev == dev) { *out = &c; return cudaSuccess; }
+    DeviceCtx c;
+    c.dev = dev;
+    if ((e = cudaDeviceGetAttribute(&c.sm_count, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+    if ((e = cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking)) != cudaSuccess) return e;
+    if ((e = cudaEventCreate(&c.ev0)) != cudaSuccess) return e;
+    if ((e = cudaEventCreate(&c.ev1)) != cudaSuccess) return e;
+    g_ctx.push_back(c);
+    *out = &g_ctx.back();
+    return cudaSuccess;
+}
 
 struct LevelArrays {               // kept per expansion level for FIRST-mode node accounting
     int n = 0;
@@ -60,10 +129,12 @@ struct dq_model {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int sm_count = 0;
     // model tables in HBM
-    DevBuf<uint32_t> d_ent_off, d_ent_moff, d_masks, d_dom0;
-    DevBuf<uint16_t> d_ent;
-    DevBuf<uint8_t> d_order, d_pos, d_cell_lut;
-    DevBuf<int32_t> d_values, d_sizes;
+    DevBuf<uint8_t> d_blob;                     // all tables, one block
+    std::vector<uint8_t> h_blob;                // its host image (kept while the copy may be in flight)
+    uint32_t *t_ent_off = nullptr, *t_ent_moff = nullptr, *t_masks = nullptr, *t_dom0 = nullptr;
+    uint16_t* t_ent = nullptr;
+    uint8_t *t_order = nullptr, *t_pos = nullptr, *t_cell_lut = nullptr;
+    int32_t *t_values = nullptr, *t_sizes = nullptr;
     int n_sizes = 0;
     // tree-solve scratch, retained until the next solve for dq_tree_nodes_upto()
     std::vector<LevelArrays> levels;
@@ -96,27 +167,14 @@ static int upload(dq_model* m) {
     if (m->uploaded) return DQ_OK;
     int dev = 0;
     DQ_CUDA(cudaGetDevice(&dev));
-    DQ_CUDA(cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, dev));
-    DQ_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
-    DQ_CUDA(cudaEventCreate(&m->ev0));
-    DQ_CUDA(cudaEventCreate(&m->ev1));
+    DeviceCtx* ctx = nullptr;
+    DQ_CUDA(device_ctx(&ctx));
+    m->sm_count = ctx->sm_count; m->stream = ctx->stream; m->ev0 = ctx->ev0; m->ev1 = ctx->ev1;
     const CompiledModel& c = m->cm;
     const int nv = c.nv;
-    auto up = [&](auto& buf, const auto& vec) -> cudaError_t {
-        cudaError_t e = buf.reserve(vec.size());
-        if (e != cudaSuccess) return e;
-        if (vec.empty()) return cudaSuccess;
-        return cudaMemcpy(buf.p, vec.data(), vec.size() * sizeof(vec[0]), cudaMemcpyHostToDevice);
-    };
-    DQ_CUDA(up(m->d_ent_off, c.ent_off));
-    DQ_CUDA(up(m->d_ent, c.ent));
-    DQ_CUDA(up(m->d_ent_moff, c.ent_moff));
-    DQ_CUDA(up(m->d_masks, c.masks));
-    DQ_CUDA(up(m->d_dom0, c.dom0));
+    // every table goes into ONE device block with ONE stream-ordered copy (the solve's kernels follow on the same stream)
     std::vector<uint8_t> order(nv), pos(nv);
     for (int i = 0; i < nv; i++) { order[i] = (uint8_t)c.order[i]; pos[i] = (uint8_t)c.pos_of[i]; }
-    DQ_CUDA(up(m->d_order, order));
-    DQ_CUDA(up(m->d_pos, pos));
     std::vector<int32_t> values((size_t)nv * 32, 0);
     std::vector<uint8_t> lut((size_t)nv * 256, 0xFF);
     for (int v = 0; v < nv; v++)
@@ -124,13 +182,27 @@ static int upload(dq_model* m) {
             values[(size_t)v * 32 + j] = c.values[v][j];
             if (c.values[v][j] >= 1 && c.values[v][j] <= 255) lut[(size_t)v * 256 + c.values[v][j]] = (uint8_t)j;
         }
-    DQ_CUDA(up(m->d_values, values));
-    DQ_CUDA(up(m->d_cell_lut, lut));
     std::vector<int32_t> sizes = c.distinct_sizes;
     if (std::find(sizes.begin(), sizes.end(), 1) == sizes.end()) sizes.push_back(1);
     std::sort(sizes.begin(), sizes.end());
     m->n_sizes = (int)sizes.size();
-    DQ_CUDA(up(m->d_sizes, sizes));
+    std::vector<uint8_t>& blob = m->h_blob;
+    blob.clear();
+    auto put = [&](const auto& vec) -> size_t {
+        const size_t off = (blob.size() + 255) & ~(size_t)255;
+        blob.resize(off + std::max<size_t>(vec.size() * sizeof(vec[0]), 4), 0);
+        if (!vec.empty()) memcpy(blob.data() + off, vec.data(), vec.size() * sizeof(vec[0]));
+        return off;
+    };
+    const size_t o_ent_off = put(c.ent_off), o_ent = put(c.ent), o_ent_moff = put(c.ent_moff), o_masks = put(c.masks),
+                 o_dom0 = put(c.dom0), o_order = put(order), o_pos = put(pos), o_values = put(values), o_lut = put(lut),
+                 o_sizes = put(sizes);
+    DQ_CUDA(m->d_blob.reserve(blob.size()));
+    DQ_CUDA(cudaMemcpyAsync(m->d_blob.p, blob.data(), blob.size(), cudaMemcpyHostToDevice, m->stream));
+    uint8_t* base = m->d_blob.p;
+    m->t_ent_off = (uint32_t*)(base + o_ent_off); m->t_ent = (uint16_t*)(base + o_ent); m->t_ent_moff = (uint32_t*)(base + o_ent_moff);
+    m->t_masks = (uint32_t*)(base + o_masks); m->t_dom0 = (uint32_t*)(base + o_dom0); m->t_order = base + o_order; m->t_pos = base + o_pos;
+    m->t_values = (int32_t*)(base + o_values); m->t_cell_lut = base + o_lut; m->t_sizes = (int32_t*)(base + o_sizes);
     DQ_CUDA(m->d_ctrl.reserve(32));
     m->uploaded = true;
     return DQ_OK;
@@ -139,13 +211,13 @@ static int upload(dq_model* m) {
 static TreeModelDev dev_model(const dq_model* m) {
     TreeModelDev M;
     M.T.nv = m->cm.nv;
-    M.T.ent_off = m->d_ent_off.p;
-    M.T.ent = m->d_ent.p;
-    M.T.ent_moff = m->d_ent_moff.p;
-    M.T.masks = m->d_masks.p;
-    M.dom0 = m->d_dom0.p;
-    M.order = m->d_order.p;
-    M.pos = m->d_pos.p;
+    M.T.ent_off = m->t_ent_off;
+    M.T.ent = m->t_ent;
+    M.T.ent_moff = m->t_ent_moff;
+    M.T.masks = m->t_masks;
+    M.dom0 = m->t_dom0;
+    M.order = m->t_order;
+    M.pos = m->t_pos;
     M.trail = m->cm.trail_bound;
     return M;
 }
@@ -299,9 +371,7 @@ int dq_compile(const dq_model_desc* desc, dq_model** out) {
 void dq_free(dq_model* m) {
     if (!m) return;
     if (m->uploaded) {
-        m->d_ent_off.release(); m->d_ent_moff.release(); m->d_masks.release(); m->d_dom0.release();
-        m->d_ent.release(); m->d_order.release(); m->d_pos.release(); m->d_cell_lut.release();
-        m->d_values.release(); m->d_sizes.release(); m->d_ctrl.release();
+        m->d_blob.release(); m->d_ctrl.release();
         m->d_sub_nodes.release(); m->d_sol_key.release(); m->d_sol.release();
         m->q_records.release(); m->q_records2.release(); m->q_first.release();
         m->b_cells.release(); m->b_solution.release(); m->b_status.release(); m->b_nodes.release();
@@ -311,9 +381,6 @@ void dq_free(dq_model* m) {
             l.dmask.release(); l.surv.release(); l.child_off.release(); l.parent_of.release();
             l.node_off.release(); l.prefixes.release();
         }
-        if (m->ev0) cudaEventDestroy(m->ev0);
-        if (m->ev1) cudaEventDestroy(m->ev1);
-        if (m->stream) cudaStreamDestroy(m->stream);
     }
     delete m;
 }
@@ -549,8 +616,8 @@ static int run_batch_cells(dq_model* m, const uint8_t* cells_dev, int64_t n, int
     DQ_CUDA(cudaMemsetAsync(ctrl, 0, 8 * sizeof(unsigned long long), m->stream));
     BatchCellsArgs A;
     A.idx_list = idx_list;
-    A.cells = cells_dev; A.n = n; A.stride = stride; A.cell_lut = m->d_cell_lut.p; A.values = m->d_values.p;
-    A.sizes = m->d_sizes.p; A.n_sizes = m->n_sizes; A.budget = opts ? opts->node_budget : 0;
+    A.cells = cells_dev; A.n = n; A.stride = stride; A.cell_lut = m->t_cell_lut; A.values = m->t_values;
+    A.sizes = m->t_sizes; A.n_sizes = m->n_sizes; A.budget = opts ? opts->node_budget : 0;
     A.cursor = ctrl; A.solution = sol_dev; A.nodes = nodes_dev; A.status = status_dev; A.totals = ctrl + 1;
     long long ctas = std::min<long long>((n + kWarpsPerCta - 1) / kWarpsPerCta, (long long)occ * m->sm_count);
     if (ctas < 1) ctas = 1;
