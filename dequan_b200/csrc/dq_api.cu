@@ -655,7 +655,7 @@ static int run_batch_sudoku(dq_model* m, const uint8_t* cells_dev, int64_t n, in
     const unsigned long long task_cap = std::max<unsigned long long>(1u << 20, std::min<unsigned long long>(8ull * n, 1ull << 25));
     const unsigned long long snap_cap = std::max<unsigned long long>(1u << 18, std::min<unsigned long long>(2ull * n, 1ull << 23));
     const bool fresh_pool = m->s_tasks.cap < task_cap;
-    DQ_CUDA(m->s_digest.reserve(n)); DQ_CUDA(m->s_hard.reserve(n)); DQ_CUDA(m->s_ctrl.reserve(16));
+    DQ_CUDA(m->s_digest.reserve(n)); DQ_CUDA(m->s_hard.reserve(2 * (size_t)n)); DQ_CUDA(m->s_ctrl.reserve(16));
     DQ_CUDA(m->s_tasks.reserve(task_cap)); DQ_CUDA(m->s_snaps.reserve(snap_cap * kSnapWords));
     unsigned long long* ctrl = m->s_ctrl.p;       // SkCtrl words
     DQ_CUDA(cudaMemsetAsync(ctrl, 0, 16 * sizeof(unsigned long long), m->stream));

@@ -74,10 +74,11 @@ struct SudokuDigest { uint4 v[kDigestVec]; };
 struct SudokuTask {
     uint32_t puzzle;
     uint32_t snap_id;          // piece: which stack snapshot it resumes from
-    uint32_t info;             // bit 31 valid | bit 30 root | bit 29 null ; root: level | value << 8 ; piece: lo | hi << 8
+    uint32_t info;             // bit 31 valid | bit 30 root | bit 29 null | bit 28 top ; root: level | value << 8 ; piece: lo | hi << 8
+                               // (top: hi is the level the snapshot's search stood on; its untried sets are entries hi, hi+1)
     uint32_t pad;
 };
-constexpr uint32_t SKT_VALID = 0x80000000u, SKT_ROOT = 0x40000000u, SKT_NULL = 0x20000000u;
+constexpr uint32_t SKT_VALID = 0x80000000u, SKT_ROOT = 0x40000000u, SKT_NULL = 0x20000000u, SKT_TOP = 0x10000000u;
 constexpr int kSnapWords = 12;                  // uint4 per stack snapshot: 96 u16 entries (passing untried | value << 9) per level
 
 // Control block (unsigned long long words)
@@ -100,7 +101,7 @@ struct SudokuArgs {
     uint8_t* solution;                     // [n][stride]
     unsigned long long* nodes;             // [n]
     uint8_t* status;                       // [n]
-    uint32_t* hard;                        // [n] ids of the instances k_sudoku_first did not finish
+    uint32_t* hard;                        // [n][2] instances k_sudoku_first did not finish: {id, snapshot slot | stack level << 24}
     SudokuTask* tasks;    unsigned long long task_cap;
     uint4* snaps;         unsigned long long snap_cap;       // kSnapWords x uint4 per snapshot
     unsigned long long* ctrl;              // control block, see SkCtrl
@@ -308,6 +309,27 @@ __device__ __forceinline__ bool sk_choose(SudokuSmem& S, int t, SkLane& L) {
     return false;
 }
 
+// Stack snapshot in HBM: u16 per level (passing untried | value << 9), eight levels per uint4.
+__device__ __forceinline__ uint32_t sk_snap_entry(const uint4* __restrict__ sb, int l) {
+    const uint4 cur = __ldcg(sb + (l >> 3));
+    const uint32_t word = (l & 4) ? ((l & 2) ? cur.w : cur.z) : ((l & 2) ? cur.y : cur.x);
+    return (l & 1) ? (word >> 16) : (word & 0xFFFF);
+}
+// levels 0..upto-1 from the stack, then `extra0`, `extra1` as entries upto and upto+1
+__device__ __forceinline__ void sk_snap_write(uint4* __restrict__ sb, const SudokuSmem& S, int t, int upto, uint32_t extra0, uint32_t extra1) {
+    for (int q = 0; q * 8 <= upto + 1; q++) {
+        uint32_t w4[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int l0 = q * 8 + 2 * i, l1 = l0 + 1;
+            const uint32_t e0 = l0 < upto ? (uint32_t)S.stk[l0][t] : (l0 == upto ? extra0 : (l0 == upto + 1 ? extra1 : 0u));
+            const uint32_t e1 = l1 < upto ? (uint32_t)S.stk[l1][t] : (l1 == upto ? extra0 : (l1 == upto + 1 ? extra1 : 0u));
+            w4[i] = e0 | (e1 << 16);
+        }
+        __stcg(sb + q, make_uint4(w4[0], w4[1], w4[2], w4[3]));
+    }
+}
+
 constexpr int kPopQuorum = 6;           // extra pop rounds run while at least this many lanes still stand on an exhausted level
 
 // The warp writes the solutions of its finished lanes, one lane at a time, coalesced.
@@ -463,8 +485,16 @@ k_sudoku_first(SudokuArgs A) {
                 uint8_t* out = A.solution + (size_t)L.puzzle * A.stride;
                 for (int i = 0; i < 81; i++) out[i] = 0;
             } else {
+                // not done within the budget: park the search (stack snapshot + nodes so far) on the hard list; the
+                // counting pipeline picks it up exactly where it stands
+                const unsigned long long sslot = atomicAdd(A.ctrl + SKC_SNAP, 1ull);
+                const unsigned long long idx = atomicAdd(A.ctrl + SKC_HARD, 1ull);
+                if (sslot < A.snap_cap) sk_snap_write(A.snaps + (size_t)sslot * kSnapWords, S, t, L.sp, L.passrem, L.dom_rem);
+                else atomicOr(A.ctrl + SKC_ERROR, 2ull);
+                A.hard[2 * idx] = L.puzzle;
+                A.hard[2 * idx + 1] = (uint32_t)sslot | ((uint32_t)L.sp << 24);
+                A.nodes[L.puzzle] = (81 - L.nblank) + L.nodes_hi + L.nodes;
                 A.status[L.puzzle] = SK_STATUS_HARD;
-                A.hard[atomicAdd(A.ctrl + SKC_HARD, 1ull)] = L.puzzle;
             }
             L.have = false;
         }
@@ -529,7 +559,7 @@ k_sudoku_strong(SudokuArgs A) {
         if (lane == 0) idx = atomicAdd(A.ctrl + SKC_HARD_CUR, 1ull);
         idx = __shfl_sync(0xFFFFFFFFu, idx, 0);
         if (idx >= n_hard) break;
-        const uint32_t puzzle = A.hard[idx];
+        const uint32_t puzzle = A.hard[2 * idx];
         const uint8_t* in = A.cells + (size_t)puzzle * A.stride;
         const uint32_t* dw = reinterpret_cast<const uint32_t*>(A.digest[puzzle].v);
         const int nblank = (int)(__ldg(dw + 3) & 0xFF);
@@ -601,11 +631,15 @@ k_sudoku_strong(SudokuArgs A) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_sudoku_walk: lane per hard instance.  Follows the solution k_sudoku_strong found (or, for an
-// instance without one, stands at the root) and accounts for the reference's plain
-// forward-checking search: nodes[instance] = givens + the values tried at each path level up to
-// the solution's; every earlier value that passes its forward check becomes a root task whose
-// whole subtree k_sudoku_count adds.
+// k_sudoku_walk: lane per hard instance.  k_sudoku_first parked the reference's search at some
+// point P of its DFS (stack snapshot, nodes so far); k_sudoku_strong found the solution S the
+// search ends at (or that there is none).  What the reference still visits between P and S:
+//   * everything left on the parked stack BELOW the level d where P's path leaves S's path — one
+//     task: "count the snapshot's levels (d, sp] exhaustively";
+//   * at level d the values between the parked one and S's: nodes; the passing ones are root tasks
+//     ("count the whole subtree under path-prefix + value");
+//   * at every deeper path level the values up to S's: nodes, passing earlier ones root tasks.
+// No solution: everything left on the parked stack, one task.
 __global__ void __launch_bounds__(kSudokuBlock)
 k_sudoku_walk(SudokuArgs A) {
     extern __shared__ __align__(16) unsigned char sk_raw[];
@@ -613,13 +647,23 @@ k_sudoku_walk(SudokuArgs A) {
     const int t = threadIdx.x;
     const int lane = t & 31;
     const unsigned long long n_hard = A.ctrl[SKC_HARD];
+    auto emit = [&](uint32_t puzzle, uint32_t snap, uint32_t info) {
+        const unsigned long long slot = atomicAdd(A.ctrl + SKC_RESERVE, 1ull);
+        if (slot >= A.task_cap) { atomicOr(A.ctrl + SKC_ERROR, 2ull); return; }
+        atomicAdd(A.ctrl + SKC_OUTSTANDING, 1ull);
+        *reinterpret_cast<uint4*>(A.tasks + slot) = make_uint4(puzzle, snap, SKT_VALID | info, 0u);
+    };
     for (;;) {
         unsigned long long base = 0;
         if (lane == 0) base = atomicAdd(A.ctrl + SKC_WALK_CUR, 32ull);
         base = __shfl_sync(0xFFFFFFFFu, base, 0);
         if (base >= n_hard) break;
         const bool active = base + lane < n_hard;
-        const uint32_t puzzle = active ? A.hard[base + lane] : 0u;
+        const uint32_t puzzle = active ? A.hard[2 * (base + lane)] : 0u;
+        const uint32_t hinfo = active ? A.hard[2 * (base + lane) + 1] : 0u;
+        const uint32_t snap = hinfo & 0xFFFFFFu;
+        const int psp = (int)(hinfo >> 24);                        // the level the parked search stands on
+        const uint4* sb = A.snaps + (size_t)snap * kSnapWords;
         int nblank = 0;
         bool sat = false;
         if (active) {
@@ -629,43 +673,53 @@ k_sudoku_walk(SudokuArgs A) {
             sat = A.status[puzzle] == 1;
         }
         const uint8_t* sol = A.solution + (size_t)puzzle * A.stride;
+        if (active && !sat) emit(puzzle, snap, SKT_TOP | 0u | ((uint32_t)psp << 8));      // the whole parked stack
         unsigned long long direct = 0;
-        int levels = active ? (sat ? nblank : 1) : 0;
+        bool on_parked_path = true;                                 // levels so far: parked path == solution path
+        const int levels = active && sat ? nblank : 0;
         const int max_levels = __reduce_max_sync(0xFFFFFFFFu, levels);
         for (int l = 0; l < max_levels; l++) {
             if (l < levels) {
                 const int p = sk_cell_at(S, t, l);
                 const SkCell c = sk_decode(p);
-                uint32_t dom, pass;
-                sk_enter(S, t, c, dom, pass);
-                uint32_t V, bit = 0;
-                if (sat) {
-                    bit = 1u << (sol[p] - 1);
-                    direct += __popc(dom & (bit | (bit - 1u)));      // tried in ascending order up to the solution's value
-                    V = pass & (bit - 1u);
-                    if (!(pass & bit)) atomicOr(A.ctrl + SKC_ERROR, 8ull);
+                const uint32_t bit = 1u << (sol[p] - 1);
+                uint32_t dom_rem, passrem;                          // what the reference still tries at this level
+                bool charge = true;
+                if (on_parked_path && l < psp) {
+                    const uint32_t e = sk_snap_entry(sb, l);
+                    const uint32_t v = e >> 9;
+                    if ((1u << v) == bit) charge = false;           // the parked search already stands on the solution's value here
+                    else {
+                        // d: the parked path leaves the solution path.  Below d the parked stack is solution-free
+                        if ((1u << v) > bit) atomicOr(A.ctrl + SKC_ERROR, 8ull);
+                        emit(puzzle, snap, SKT_TOP | (uint32_t)(l + 1) | ((uint32_t)psp << 8));
+                        passrem = e & 0x1FF;
+                        dom_rem = ~sk_used_at(S, t, c) & 0x1FF & ~((2u << v) - 1u);
+                        on_parked_path = false;
+                    }
+                } else if (on_parked_path && l == psp) {
+                    passrem = sk_snap_entry(sb, l) & 0x1FF;         // parked exactly on the solution path: its untried sets
+                    dom_rem = sk_snap_entry(sb, l + 1) & 0x1FF;
+                    on_parked_path = false;
                 } else {
-                    direct += __popc(dom);                           // no solution: every value of the first blank is tried
-                    V = pass;
+                    uint32_t dom, pass;
+                    sk_enter(S, t, c, dom, pass);
+                    dom_rem = dom; passrem = pass;
                 }
-                if (V) {
-                    const unsigned k = __popc(V);
-                    unsigned long long slot = atomicAdd(A.ctrl + SKC_RESERVE, (unsigned long long)k);
-                    const unsigned long long room = slot < A.task_cap ? A.task_cap - slot : 0;
-                    const unsigned kk = (unsigned)min((unsigned long long)k, room);
-                    if (kk < k) atomicOr(A.ctrl + SKC_ERROR, 2ull);
-                    if (kk) atomicAdd(A.ctrl + SKC_OUTSTANDING, (unsigned long long)kk);
-                    uint32_t vv = V;
-                    for (unsigned i = 0; i < kk; i++) {
-                        const uint32_t v = __ffs(vv) - 1;
-                        vv &= vv - 1;
-                        *reinterpret_cast<uint4*>(A.tasks + slot + i) = make_uint4(puzzle, 0u, SKT_VALID | SKT_ROOT | (uint32_t)l | (v << 8), 0u);
+                if (charge) {
+                    direct += __popc(dom_rem & (bit | (bit - 1u)));          // tried in ascending order up to the solution's value
+                    if (!(passrem & bit)) atomicOr(A.ctrl + SKC_ERROR, 8ull);
+                    uint32_t V = passrem & (bit - 1u);                       // earlier passing values: whole subtrees to count
+                    while (V) {
+                        const uint32_t v = __ffs(V) - 1;
+                        V &= V - 1;
+                        emit(puzzle, 0u, SKT_ROOT | (uint32_t)l | (v << 8));
                     }
                 }
-                if (sat) sk_commit(S, t, c, bit);
+                sk_commit(S, t, c, bit);
             }
         }
-        if (active) A.nodes[puzzle] = (unsigned long long)(81 - nblank) + direct;
+        if (active && direct) atomicAdd(A.nodes + puzzle, direct);
     }
 }
 
@@ -680,6 +734,7 @@ k_sudoku_walk(SudokuArgs A) {
 constexpr int kDonatePeriod = 32;
 constexpr uint32_t kDonateMinNodes = 128;   // a task younger than this keeps its stack to itself
 constexpr uint32_t kDonateGap = 256;        // ... and so does one that gave a level away fewer nodes ago than this
+constexpr uint32_t kSplitGap = 4096;        // a task splits unasked every time it has counted this many nodes
 
 __global__ void __launch_bounds__(kSudokuBlock)
 k_sudoku_count(SudokuArgs A) {
@@ -693,6 +748,7 @@ k_sudoku_count(SudokuArgs A) {
 
     SkLane L = {};
     uint32_t donate_at = 0;                 // node count from which the task may give a level away
+    uint32_t split_at = 0;                  // node count from which it does so unasked
     bool waiting = false, poll_now = false; // holds a ticket for a queue slot that is not published yet
     unsigned long long ticket = 0;
     int iter = 0;
@@ -731,6 +787,7 @@ k_sudoku_count(SudokuArgs A) {
                     L.passrem = 0; L.dom_rem = 0;
                     L.have = true;
                     donate_at = A.force_donate ? A.force_donate : kDonateMinNodes;
+                    split_at = kSplitGap;
                     if (info & SKT_ROOT) {
                         // path values at the levels above, then the task's own value at its level
                         const int l0 = (int)(info & 0xFF);
@@ -750,22 +807,18 @@ k_sudoku_count(SudokuArgs A) {
                         // values of levels [lo, hi] are this piece's, everything shallower belongs to other tasks
                         const int lo = (int)(info & 0xFF), hi = (int)((info >> 8) & 0xFF);
                         const uint4* sb = A.snaps + (size_t)snap_id * kSnapWords;
-                        auto entry = [&](int l) -> uint32_t {
-                            const uint4 cur = __ldcg(sb + (l >> 3));
-                            const uint32_t word = (l & 4) ? ((l & 2) ? cur.w : cur.z) : ((l & 2) ? cur.y : cur.x);
-                            return (l & 1) ? (word >> 16) : (word & 0xFFFF);
-                        };
                         for (int l = 0; l < hi; l++) {
-                            const uint32_t e = entry(l);
+                            const uint32_t e = sk_snap_entry(sb, l);
                             sk_commit(S, t, sk_decode(sk_cell_at(S, t, l)), 1u << (e >> 9));
                             S.stk[l][t] = (uint16_t)(l >= lo ? e : (e & 0xFE00u));
                         }
                         L.sp = hi; L.base_sp = lo;
                         L.p = sk_cell_at(S, t, hi);
                         L.c = sk_decode(L.p);
-                        const uint32_t e = entry(hi);
+                        const uint32_t e = sk_snap_entry(sb, hi);
                         L.passrem = e & 0x1FF;
-                        L.dom_rem = ~sk_used_at(S, t, L.c) & 0x1FF & ~((2u << (e >> 9)) - 1u);   // the values above the one the donor took here
+                        if (info & SKT_TOP) L.dom_rem = sk_snap_entry(sb, hi + 1) & 0x1FF;
+                        else L.dom_rem = ~sk_used_at(S, t, L.c) & 0x1FF & ~((2u << (e >> 9)) - 1u);   // the values above the one the donor took here
                         L.enter = false;
                     }
                 }
@@ -800,17 +853,20 @@ k_sudoku_count(SudokuArgs A) {
                 if (A.force_donate) demand = (long long)total_warps * 8;
             }
             demand = __shfl_sync(0xFFFFFFFFu, demand, 0);
-            if (demand > 0) {
-                // eligible: an established task with an untried passing value on a level below the current one
+            // eligible: an established task with an untried passing value on a level below the current one.  A task that
+            // has grown large splits whether or not anybody is waiting, so that no giant subtree is left for the end.
+            const bool want = L.have && !L.enter && (L.nodes >= split_at || (demand > 0 && L.nodes >= donate_at));
+            if (__any_sync(0xFFFFFFFFu, want)) {
                 int hl = -1;
-                if (L.have && !L.enter && L.nodes >= donate_at) {
+                if (want) {
                     int l = L.base_sp;
                     while (l < L.sp && (S.stk[l][t] & 0x1FF) == 0) ++l;
                     if (l < L.sp) hl = l;
+                    else if (L.nodes >= split_at) split_at = L.nodes + kSplitGap / 4;     // nothing to give right now: look again soon
                 }
                 const uint32_t elig = __ballot_sync(0xFFFFFFFFu, hl >= 0);
                 const long long quota = min((long long)8, demand / (long long)total_warps + 1);
-                if (hl >= 0 && (long long)__popc(elig & lt) < quota) {
+                if (hl >= 0 && (L.nodes >= split_at || (long long)__popc(elig & lt) < quota)) {
                     atomicAdd(A.ctrl + SKC_OUTSTANDING, 1ull);                 // the piece exists from here on
                     const unsigned long long slot = atomicAdd(A.ctrl + SKC_RESERVE, 1ull);
                     const unsigned long long sslot = atomicAdd(A.ctrl + SKC_SNAP, 1ull);
@@ -823,24 +879,14 @@ k_sudoku_count(SudokuArgs A) {
                         rec[2] = SKT_VALID | SKT_NULL;
                     } else {
                         // stack snapshot, levels 0..hl
-                        uint4* sb = A.snaps + (size_t)sslot * kSnapWords;
-                        for (int q = 0; q * 8 <= hl; q++) {
-                            uint32_t w4[4];
-#pragma unroll
-                            for (int i = 0; i < 4; i++) {
-                                const int l0 = q * 8 + 2 * i, l1 = l0 + 1;
-                                const uint32_t e0 = l0 <= hl ? (uint32_t)S.stk[l0][t] : 0u;
-                                const uint32_t e1 = l1 <= hl ? (uint32_t)S.stk[l1][t] : 0u;
-                                w4[i] = e0 | (e1 << 16);
-                            }
-                            __stcg(sb + q, make_uint4(w4[0], w4[1], w4[2], w4[3]));
-                        }
+                        sk_snap_write(A.snaps + (size_t)sslot * kSnapWords, S, t, hl + 1, 0u, 0u);
                         volatile uint32_t* rec = reinterpret_cast<volatile uint32_t*>(A.tasks + slot);
                         rec[0] = L.puzzle; rec[1] = (uint32_t)sslot;
                         __threadfence();
                         rec[2] = SKT_VALID | (uint32_t)L.base_sp | ((uint32_t)hl << 8);
                         L.base_sp = hl + 1;                                      // this task keeps the deeper levels
                         donate_at = L.nodes + (A.force_donate ? A.force_donate : kDonateGap);
+                        split_at = L.nodes + kSplitGap;
                     }
                 }
             }
@@ -869,7 +915,7 @@ k_sudoku_count(SudokuArgs A) {
             sk_enter(S, t, L.c, dom, pass);
             L.dom_rem = dom; L.passrem = pass; L.enter = false;
         }
-        if (L.nodes >= 0x80000000u) { L.nodes_hi += L.nodes; L.nodes = 0; donate_at = 0; }
+        if (L.nodes >= 0x80000000u) { L.nodes_hi += L.nodes; L.nodes = 0; donate_at = 0; split_at = kSplitGap; }
 
         // ---------------- closed tasks leave the outstanding count ----------------
         {
