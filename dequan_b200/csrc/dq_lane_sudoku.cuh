@@ -56,15 +56,17 @@ constexpr uint8_t SK_STATUS_HARD = 0xFD;        // interim: on the hard list
 constexpr uint8_t SK_STATUS_DEFER = 0xFE;       // interim: handed to the generic warp engine
 
 // Per-instance record written by k_sudoku_digest and copied into shared memory by the lane that
-// takes the instance: everything the search needs, already in its working layout (19 x uint4).
-//   w[0..2]   blank bitmap by cell id (81 bits)
+// takes the instance: everything the search needs, already in its working layout (18 x uint4).
+//   w[0..2]   blank bitmap by cell id (81 bits, row-major)
 //   w[3]      bit 31 = deferred to the generic engine; low byte = number of blanks
-//   w[4..12]  rows' used masks, replicated in the three 10-bit fields
-//   w[13..15] columns' used masks, one stack per word, one column per field
-//   w[16..24] boxes' used masks, replicated
-//   w[25..51] per (row, stack): 0x1FF in the fields of blank cells
-//   w[52..72] the blank cells' ids in search order, one byte per level
-constexpr int kDigestVec = 19;
+//   w[4..6]   rows' used masks, one band per word, one row per 10-bit field
+//   w[7..9]   columns' used masks, one stack per word, one column per field
+//   w[10..18] boxes' used masks, replicated in the three fields
+//   w[19..45] per (row, stack): 0x1FF in the fields of blank cells
+//   w[46..66] the blank cells' ids in search order, one byte per level
+//   w[67..69] blank bitmap transposed (bit 9*column + row)
+constexpr int kDigestVec = 18;
+constexpr int kTableWords = 63;                 // w[4..66]: copied verbatim into the lane's shared-memory tables
 struct SudokuDigest { uint4 v[kDigestVec]; };
 
 // One unit of counting work (16 bytes).
@@ -154,19 +156,23 @@ k_sudoku_digest(const uint8_t* __restrict__ cells, long long n, int stride, Sudo
             const int p = r * 9 + c;
             if (!((blank[p >> 5] >> (p & 31)) & 1u)) continue;
             if ((row[r] | col[c] | box[(r / 3) * 3 + c / 3]) == 0x1FFu) defer = true;  // a blank wiped out by the givens
-            w[25 + r * 3 + c / 3] |= 0x1FFu << (10 * (c % 3));
+            w[19 + r * 3 + c / 3] |= 0x1FFu << (10 * (c % 3));
+            w[67 + (c * 9 + r) / 32] |= 1u << ((c * 9 + r) % 32);
             // cell id of this search level, one byte per level (dynamic index: the only non-static store of the pass)
             const uint32_t sh = (uint32_t)(level & 3) * 8;
 #pragma unroll
-            for (int q = 0; q < 21; q++) if ((level >> 2) == q) w[52 + q] |= (uint32_t)p << sh;
+            for (int q = 0; q < 21; q++) if ((level >> 2) == q) w[46 + q] |= (uint32_t)p << sh;
             ++level;
         }
     w[0] = blank[0]; w[1] = blank[1]; w[2] = blank[2];
     w[3] = (uint32_t)level | (defer ? 0x80000000u : 0u);
 #pragma unroll
-    for (int i = 0; i < 9; i++) { w[4 + i] = row[i] * SK_ONES; w[16 + i] = box[i] * SK_ONES; }
+    for (int i = 0; i < 9; i++) w[10 + i] = box[i] * SK_ONES;
 #pragma unroll
-    for (int i = 0; i < 3; i++) w[13 + i] = col[3 * i] | (col[3 * i + 1] << 10) | (col[3 * i + 2] << 20);
+    for (int i = 0; i < 3; i++) {
+        w[4 + i] = row[3 * i] | (row[3 * i + 1] << 10) | (row[3 * i + 2] << 20);
+        w[7 + i] = col[3 * i] | (col[3 * i + 1] << 10) | (col[3 * i + 2] << 20);
+    }
     uint4* o = reinterpret_cast<uint4*>(out + first + threadIdx.x);
 #pragma unroll
     for (int i = 0; i < kDigestVec; i++) o[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
@@ -175,8 +181,8 @@ k_sudoku_digest(const uint8_t* __restrict__ cells, long long n, int stride, Sudo
 // ---------------------------------------------------------------------------------------------
 // Per-lane shared-memory state, all arrays [word][thread].
 struct SudokuSmem {
-    uint32_t rowr[9][kSudokuBlock];     // row used mask, replicated in the three fields
-    uint32_t colp[3][kSudokuBlock];     // column used masks of one stack, one per field
+    uint32_t rowp[3][kSudokuBlock];     // row used masks of one band, one row per field
+    uint32_t colp[3][kSudokuBlock];     // column used masks of one stack, one column per field
     uint32_t boxr[9][kSudokuBlock];     // box used mask, replicated
     uint32_t blk[27][kSudokuBlock];     // (row, stack) -> 0x1FF in the fields of blank cells
     uint32_t cellw[21][kSudokuBlock];   // blank cell ids in search order, four levels per word
@@ -185,7 +191,7 @@ struct SudokuSmem {
 
 __device__ __forceinline__ uint32_t sk_rep(uint32_t x9) { return x9 * SK_ONES; }
 
-struct SkCell { int r, s, f, band, box; };
+struct SkCell { int r, s, f, band, box, rm; };    // row, stack, column in stack, band, box, row in band
 __device__ __forceinline__ SkCell sk_decode(int p) {
     SkCell c;
     c.r = (p * 57) >> 9;                 // p / 9 for p < 81
@@ -194,6 +200,7 @@ __device__ __forceinline__ SkCell sk_decode(int p) {
     c.f = col - 3 * c.s;
     c.band = (c.r * 11) >> 5;            // r / 3
     c.box = c.band * 3 + c.s;
+    c.rm = c.r - 3 * c.band;
     return c;
 }
 
@@ -224,51 +231,90 @@ struct SkLane {
 
 __device__ __forceinline__ int sk_cell_at(const SudokuSmem& S, int t, int l) { return (int)((S.cellw[l >> 2][t] >> ((l & 3) * 8)) & 0xFF); }
 __device__ __forceinline__ uint32_t sk_used_at(const SudokuSmem& S, int t, const SkCell& k) {
-    return (S.rowr[k.r][t] | (S.colp[k.s][t] >> (10 * k.f)) | S.boxr[k.box][t]) & 0x1FF;
+    return ((S.rowp[k.band][t] >> (10 * k.rm)) | (S.colp[k.s][t] >> (10 * k.f)) | S.boxr[k.box][t]) & 0x1FF;
 }
 __device__ __forceinline__ void sk_commit(SudokuSmem& S, int t, const SkCell& k, uint32_t bit) {
-    S.rowr[k.r][t] |= sk_rep(bit);
+    S.rowp[k.band][t] |= bit << (10 * k.rm);
     S.boxr[k.box][t] |= sk_rep(bit);
     S.colp[k.s][t] |= bit << (10 * k.f);
 }
 
-// words 4..72 of the digest record -> rowr, colp, boxr, blk, cellw (contiguous in S)
+// words 4..66 of the digest record -> rowp, colp, boxr, blk, cellw (contiguous in S)
 __device__ __forceinline__ void sk_load_tables(SudokuSmem& S, int t, const uint4* __restrict__ dg) {
-    uint32_t* dst = &S.rowr[0][t];
+    uint32_t* dst = &S.rowp[0][t];
 #pragma unroll
     for (int q = 1; q < kDigestVec; q++) {
         const uint4 x = __ldg(dg + q);
         const int wbase = 4 * q - 4;
-        if (wbase + 0 < 69) dst[(wbase + 0) * kSudokuBlock] = x.x;
-        if (wbase + 1 < 69) dst[(wbase + 1) * kSudokuBlock] = x.y;
-        if (wbase + 2 < 69) dst[(wbase + 2) * kSudokuBlock] = x.z;
-        if (wbase + 3 < 69) dst[(wbase + 3) * kSudokuBlock] = x.w;
+        if (wbase + 0 < kTableWords) dst[(wbase + 0) * kSudokuBlock] = x.x;
+        if (wbase + 1 < kTableWords) dst[(wbase + 1) * kSudokuBlock] = x.y;
+        if (wbase + 2 < kTableWords) dst[(wbase + 2) * kSudokuBlock] = x.z;
+        if (wbase + 3 < kTableWords) dst[(wbase + 3) * kSudokuBlock] = x.w;
     }
+}
+// the transposed blank bitmap (w[67..69]) stays in registers
+struct SkBlankT { uint32_t t0, t1, t2; };
+__device__ __forceinline__ SkBlankT sk_load_blank_t(const uint4* __restrict__ dg) {
+    const uint4 a = __ldg(dg + 16), b = __ldg(dg + 17);
+    SkBlankT x; x.t0 = a.w; x.t1 = b.x; x.t2 = b.y;
+    return x;
 }
 
 // Enter a level: the cell's current domain and the subset that passes the forward check, i.e. is
-// not the only value left to some later blank peer (row to the right, box-rows below inside the
-// band, the column cell below the band).
-__device__ __forceinline__ void sk_enter(const SudokuSmem& S, int t, const SkCell& c, uint32_t& dom, uint32_t& pass) {
-    const uint32_t rowv = S.rowr[c.r][t];
+// not the only value left to some later blank peer.  Seven packed words cover every later peer, all
+// straight-line code (a lane whose cell has fewer later peers runs the same instructions on empty
+// selections): the rest of the row (own word above the cell's field + two stacks to the right), the
+// box-rows below inside the band (two), and the column below the band as two TRANSPOSED words —
+// three rows of one column each — built from the band-packed row masks.
+__device__ __forceinline__ void sk_enter(const SudokuSmem& S, int t, const SkCell& c, const SkBlankT& bt, uint32_t& dom, uint32_t& pass) {
+    const uint32_t rowband = S.rowp[c.band][t];
     const uint32_t colw = S.colp[c.s][t];
     const uint32_t boxv = S.boxr[c.box][t];
-    dom = ~(rowv | (colw >> (10 * c.f)) | boxv) & 0x1FF;
-    uint32_t kill3 = 0;
+    const uint32_t rowv = sk_rep((rowband >> (10 * c.rm)) & 0x1FF);
+    const uint32_t colv = (colw >> (10 * c.f)) & 0x1FF;
+    dom = ~(rowv | colv | boxv) & 0x1FF;
+    // own word: the fields above the cell's
+    uint32_t kill3 = sk_singletons(~(rowv | colw | boxv) & S.blk[c.r * 3 + c.s][t] & (0xFFFFFFFFu << (10 * c.f + 10)) & SK_FULL3);
+    // stacks to the right
     {
-        const uint32_t sel = (0xFFFFFFFFu << (10 * c.f + 10)) & SK_FULL3;
-        kill3 |= sk_singletons(~(rowv | colw | boxv) & S.blk[c.r * 3 + c.s][t] & sel);
-        for (int s2 = c.s + 1; s2 < 3; s2++)
-            kill3 |= sk_singletons(~(rowv | S.colp[s2][t] | S.boxr[c.band * 3 + s2][t]) & S.blk[c.r * 3 + s2][t]);
+        const uint32_t* colp = &S.colp[c.s][t];
+        const uint32_t* boxp = &S.boxr[c.box][t];
+        const uint32_t* blkp = &S.blk[c.r * 3 + c.s][t];
+#pragma unroll
+        for (int k = 1; k <= 2; k++) {
+            const bool on = c.s + k < 3;
+            const uint32_t u = on ? (rowv | colp[k * kSudokuBlock] | boxp[k * kSudokuBlock]) : 0xFFFFFFFFu;
+            const uint32_t b = on ? blkp[k * kSudokuBlock] : 0u;
+            kill3 |= sk_singletons(~u & b);
+        }
     }
+    // box-rows below, inside the band
     {
-        const int in_band_last = c.band * 3 + 2;
-        for (int r2 = c.r + 1; r2 <= in_band_last; r2++)
-            kill3 |= sk_singletons(~(S.rowr[r2][t] | colw | boxv) & S.blk[r2 * 3 + c.s][t]);
-        const uint32_t fsel = 0x1FFu << (10 * c.f);
-        for (int r2 = in_band_last + 1; r2 < 9; r2++) {
-            const int box2 = ((r2 * 11) >> 5) * 3 + c.s;
-            kill3 |= sk_singletons(~(S.rowr[r2][t] | colw | S.boxr[box2][t]) & S.blk[r2 * 3 + c.s][t] & fsel);
+        const uint32_t* blkp = &S.blk[c.r * 3 + c.s][t];
+#pragma unroll
+        for (int k = 1; k <= 2; k++) {
+            const bool on = c.rm + k < 3;
+            const uint32_t rv = sk_rep((rowband >> (on ? 10 * (c.rm + k) : 0)) & 0x1FF);
+            const uint32_t b = on ? blkp[3 * k * kSudokuBlock] : 0u;
+            kill3 |= sk_singletons(~(rv | colw | boxv) & b);
+        }
+    }
+    // the column below the band: bands band+1, band+2, three rows per word
+    {
+        const uint32_t crep = sk_rep(colv);
+        const uint32_t* rowp = &S.rowp[c.band][t];
+        const uint32_t* boxp = &S.boxr[c.box][t];
+        const int q0 = 9 * (3 * c.s + c.f) + 3 * c.band;            // transposed bit index of (row 3*band, this column)
+#pragma unroll
+        for (int k = 1; k <= 2; k++) {
+            const bool on = c.band + k < 3;
+            const int q = q0 + 3 * k;
+            const uint32_t lo = q < 32 ? bt.t0 : (q < 64 ? bt.t1 : bt.t2);
+            const uint32_t hi = q < 32 ? bt.t1 : (q < 64 ? bt.t2 : 0u);
+            const uint32_t m3 = on ? (__funnelshift_r(lo, hi, q & 31) & 7u) : 0u;
+            const uint32_t b = ((m3 * 0x00040201u) & SK_ONES) * 0x1FFu;           // 0x1FF in the fields of the blank rows
+            const uint32_t u = on ? (crep | rowp[k * kSudokuBlock] | boxp[3 * k * kSudokuBlock]) : 0xFFFFFFFFu;
+            kill3 |= sk_singletons(~u & b);
         }
     }
     const uint32_t kill = (kill3 | (kill3 >> 10) | (kill3 >> 20)) & 0x1FF;
@@ -285,7 +331,7 @@ __device__ __forceinline__ bool sk_pop(SudokuSmem& S, int t, SkLane& L) {
     const uint32_t v = e >> 9, bit = 1u << v;
     L.p = sk_cell_at(S, t, L.sp);
     L.c = sk_decode(L.p);
-    S.rowr[L.c.r][t] ^= sk_rep(bit);
+    S.rowp[L.c.band][t] ^= bit << (10 * L.c.rm);
     S.boxr[L.c.box][t] ^= sk_rep(bit);
     S.colp[L.c.s][t] ^= bit << (10 * L.c.f);
     L.passrem = e & 0x1FF;
@@ -375,6 +421,7 @@ k_sudoku_first(SudokuArgs A) {
     const unsigned long long total_warps = (unsigned long long)gridDim.x * (kSudokuBlock / 32);
 
     SkLane L = {};
+    SkBlankT bt = {0, 0, 0};
     uint32_t b0 = 0, b1 = 0, b2 = 0;        // blank bitmap
     uint32_t limit = 0;
     bool limit_is_api = false, done = false;
@@ -435,6 +482,7 @@ k_sudoku_first(SudokuArgs A) {
                     }
                     if (!skip) {
                         sk_load_tables(S, t, dg);
+                        bt = sk_load_blank_t(dg);
                         L.sp = 0; L.base_sp = 0; L.passrem = 0; L.dom_rem = 0;
                         L.p = sk_cell_at(S, t, 0);
                         L.enter = true;
@@ -474,7 +522,7 @@ k_sudoku_first(SudokuArgs A) {
         if (L.have && L.enter) {
             L.c = sk_decode(L.p);
             uint32_t dom, pass;
-            sk_enter(S, t, L.c, dom, pass);
+            sk_enter(S, t, L.c, bt, dom, pass);
             L.dom_rem = dom; L.passrem = pass; L.enter = false;
         }
 
@@ -563,7 +611,7 @@ k_sudoku_strong(SudokuArgs A) {
         const uint8_t* in = A.cells + (size_t)puzzle * A.stride;
         const uint32_t* dw = reinterpret_cast<const uint32_t*>(A.digest[puzzle].v);
         const int nblank = (int)(__ldg(dw + 3) & 0xFF);
-        const uint32_t cw = lane < 21 ? __ldg(dw + 52 + lane) : 0u;          // cell ids per level, four per word
+        const uint32_t cw = lane < 21 ? __ldg(dw + 46 + lane) : 0u;          // cell ids per level, four per word
         // initial domains from the digest's used masks; givens are singletons already propagated
         uint32_t D = 0;
 #pragma unroll
@@ -575,7 +623,7 @@ k_sudoku_strong(SudokuArgs A) {
                 if (g) field = (1u << (g - 1)) | 0x200u;
                 else {
                     const SkCell k = sk_decode(q);
-                    field = ~(__ldg(dw + 4 + k.r) | (__ldg(dw + 13 + k.s) >> (10 * k.f)) | __ldg(dw + 16 + k.box)) & 0x1FF;
+                    field = ~((__ldg(dw + 4 + k.band) >> (10 * k.rm)) | (__ldg(dw + 7 + k.s) >> (10 * k.f)) | __ldg(dw + 10 + k.box)) & 0x1FF;
                 }
                 D |= field << (10 * f);
             }
@@ -666,10 +714,12 @@ k_sudoku_walk(SudokuArgs A) {
         const uint4* sb = A.snaps + (size_t)snap * kSnapWords;
         int nblank = 0;
         bool sat = false;
+        SkBlankT bt = {0, 0, 0};
         if (active) {
             const uint4* dg = A.digest[puzzle].v;
             nblank = (int)(__ldg(dg).w & 0xFF);
             sk_load_tables(S, t, dg);
+            bt = sk_load_blank_t(dg);
             sat = A.status[puzzle] == 1;
         }
         const uint8_t* sol = A.solution + (size_t)puzzle * A.stride;
@@ -703,7 +753,7 @@ k_sudoku_walk(SudokuArgs A) {
                     on_parked_path = false;
                 } else {
                     uint32_t dom, pass;
-                    sk_enter(S, t, c, dom, pass);
+                    sk_enter(S, t, c, bt, dom, pass);
                     dom_rem = dom; passrem = pass;
                 }
                 if (charge) {
@@ -747,6 +797,7 @@ k_sudoku_count(SudokuArgs A) {
     volatile unsigned long long* vctrl = A.ctrl;
 
     SkLane L = {};
+    SkBlankT bt = {0, 0, 0};
     uint32_t donate_at = 0;                 // node count from which the task may give a level away
     uint32_t split_at = 0;                  // node count from which it does so unasked
     bool waiting = false, poll_now = false; // holds a ticket for a queue slot that is not published yet
@@ -783,6 +834,7 @@ k_sudoku_count(SudokuArgs A) {
                     const uint4* dg = A.digest[L.puzzle].v;
                     L.nblank = (int)(__ldg(dg).w & 0xFF);
                     sk_load_tables(S, t, dg);
+                    bt = sk_load_blank_t(dg);
                     L.nodes = 0; L.nodes_hi = 0;
                     L.passrem = 0; L.dom_rem = 0;
                     L.have = true;
@@ -912,7 +964,7 @@ k_sudoku_count(SudokuArgs A) {
         if (L.have && L.enter) {
             L.c = sk_decode(L.p);
             uint32_t dom, pass;
-            sk_enter(S, t, L.c, dom, pass);
+            sk_enter(S, t, L.c, bt, dom, pass);
             L.dom_rem = dom; L.passrem = pass; L.enter = false;
         }
         if (L.nodes >= 0x80000000u) { L.nodes_hi += L.nodes; L.nodes = 0; donate_at = 0; split_at = kSplitGap; }
