@@ -109,6 +109,7 @@ struct SudokuArgs {
     unsigned long long* ctrl;              // control block, see SkCtrl
     unsigned long long user_budget;        // per-instance node budget of the API (0 = none)
     unsigned first_budget;                 // nodes k_sudoku_first spends on an instance before calling it hard
+    int pop_quorum;                        // extra step-back rounds run while at least this many lanes still stand on an exhausted level
     unsigned force_donate;                 // test knob: donate whenever a task is this many nodes old, hungry lanes or not (0 = off)
 };
 
@@ -376,7 +377,7 @@ __device__ __forceinline__ void sk_snap_write(uint4* __restrict__ sb, const Sudo
     }
 }
 
-constexpr int kPopQuorum = 6;           // extra pop rounds run while at least this many lanes still stand on an exhausted level
+constexpr int kPopQuorum = 10;          // extra pop rounds run while at least this many lanes still stand on an exhausted level
 
 // The warp writes the solutions of its finished lanes, one lane at a time, coalesced.
 __device__ __forceinline__ void sk_store_solutions(const SudokuSmem& S, const SudokuArgs& A, int t, bool fin, uint32_t puzzle,
@@ -498,7 +499,7 @@ k_sudoku_first(SudokuArgs A) {
         for (int rep = 0;; rep++) {
             const bool popping = L.have && !L.enter && L.passrem == 0;
             const uint32_t pm = __ballot_sync(0xFFFFFFFFu, popping);
-            if (pm == 0 || (rep > 0 && __popc(pm) < kPopQuorum)) break;
+            if (pm == 0 || (rep > 0 && __popc(pm) < A.pop_quorum)) break;
             if (popping && sk_pop(S, t, L)) {
                 // the whole tree is exhausted: ForwardCheckingStep returns false
                 A.nodes[L.puzzle] = (81 - L.nblank) + L.nodes_hi + L.nodes;
@@ -949,7 +950,7 @@ k_sudoku_count(SudokuArgs A) {
         for (int rep = 0;; rep++) {
             const bool popping = L.have && !L.enter && L.passrem == 0;
             const uint32_t pm = __ballot_sync(0xFFFFFFFFu, popping);
-            if (pm == 0 || (rep > 0 && __popc(pm) < kPopQuorum)) break;
+            if (pm == 0 || (rep > 0 && __popc(pm) < A.pop_quorum)) break;
             if (popping && sk_pop(S, t, L)) {
                 atomicAdd(A.nodes + L.puzzle, L.nodes_hi + L.nodes);             // every node of the subtree is a node of the reference
                 L.have = false; closed = 1;
