@@ -221,8 +221,11 @@ def main():
         g = multi.reduce_tree(loc, m.nodes_upto, "count", n, device=dev)
         return loc, g.solutions, g.nodes
 
+    dom = {"ms": 0.0, "frontier_nodes": 0, "records": 0}
+
     def timed_steps(step_fn, k, w):
         tot, kern, launches = 0.0, 0.0, 0
+        dom["ms"] = 0.0
         for i in range(w + k):
             flush.fill_(i & 0xFF)
             sync_all()
@@ -235,6 +238,8 @@ def main():
                 tot += dt
                 kern += loc.kernel_ms
                 launches += loc.launches
+                dom["ms"] += loc.search_kernel_ms
+                dom["frontier_nodes"], dom["records"] = loc.frontier_nodes, loc.n_prefixes
         if world > 1:
             t = torch.tensor([tot, kern], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -245,6 +250,7 @@ def main():
     if rank == 0:
         sampler.start()
     tot, kern_ms, launches = timed_steps(lambda: solve_step(model), args.steps, args.warmup)
+    dom_ms, dom_frontier, dom_records = dom["ms"], dom["frontier_nodes"], dom["records"]
 
     desc_keep = csp.desc()          # the host-side flat descriptor: the input buffers of the C-ABI call
 
@@ -254,7 +260,6 @@ def main():
         m.close()
         return r
     e_tot, _, _ = timed_steps(e2e_step, args.steps, args.warmup)
-    clocks = sampler.stop() if rank == 0 else None
     table_bytes = model.table_bytes()
     engine_used = model.solve_tree("count", part_rank=rank, part_count=world, engine=args.engine).engine
 
@@ -264,6 +269,10 @@ def main():
             dist.destroy_process_group()
         return
 
+    sudoku = None
+    if world == 1 and not args.no_sudoku:
+        sudoku = sudoku_section(args, torch, api, dev)          # still inside the clock-sampling window
+    clocks = sampler.stop()
     int_peak, _ = api.measure_int_peak()
     value = want_nodes * args.steps / tot
     kernel_nodes_per_s = want_nodes * args.steps / (kern_ms * 1e-3)
@@ -279,11 +288,7 @@ def main():
         "gpu_launches": launches,
         "engine": engine_used,
         "kernel_ms_per_step": kern_ms / args.steps,
-        "roofline": {"bound": "int32-alu", "achieved": kernel_nodes_per_s * ops_per_node / 1e12 / world,
-                     "peak": int_peak / 1e12, "unit": "Tlane-op/s per GPU",
-                     "frac": kernel_nodes_per_s * ops_per_node / world / int_peak, "traffic": None,
-                     "ops_per_node": ops_per_node, "peak_source": "LOP3 microbenchmark (dq_measure_int_peak), this run",
-                     "note": "search kernel is integer-issue bound, not HBM or tensor (SURVEY.md §8d)"},
+        "roofline": roofline_queens(n, world, want_nodes, dom_frontier, dom_records, dom_ms / args.steps, int_peak, hbm_peak, peak_src),
     }
     if not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline_queens(world)
@@ -296,9 +301,16 @@ def main():
         extra["nqueens17_1gpu"] = {"nodes_per_sec_kernel": r.nodes / (r.kernel_ms * 1e-3), "kernel_ms": r.kernel_ms,
                                    "solutions": r.solutions, "nodes": r.nodes, "engine": r.engine,
                                    "roofline_frac": r.nodes / (r.kernel_ms * 1e-3) * (5 * QUEENS_A[17] + 4) / int_peak}
-    if world == 1:
-        if not args.no_sudoku:
-            line["sudoku"] = sudoku_section(args, torch, api, dev, hbm_peak, peak_src, int_peak)
+        # BASELINE config C4: G(200, c/199) 3-colouring near the phase transition, batched, node budget per instance
+        from dequan_b200 import generators as G
+        off, edges = G.colouring_batch(1024, 200, 4.2)
+        cr = api.solve_batch_graphs(200, 3, off, edges, node_budget=100_000)
+        cr = api.solve_batch_graphs(200, 3, off, edges, node_budget=100_000)
+        extra["colouring_g200_c4.2_k3"] = {"instances": 1024, "node_budget": 100_000, "kernel_ms": cr.kernel_ms,
+                                           "instances_per_sec": 1024 / (cr.kernel_ms * 1e-3), "nodes_per_sec": cr.total_nodes / (cr.kernel_ms * 1e-3),
+                                           "sat": cr.n_sat, "unsat": cr.n_unsat, "budget": cr.n_budget, "engine": "warp"}
+    if sudoku is not None:
+        line["sudoku"] = sudoku_rooflines(sudoku, hbm_peak, peak_src, int_peak)
     line["extra"] = extra
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -306,7 +318,41 @@ def main():
         dist.destroy_process_group()
 
 
-def sudoku_section(args, torch, api, dev, hbm_peak, peak_src, int_peak):
+# ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of k_queens_lane (profiles/r1_ncu_queens14.txt, r1_ncu_queens17_lane.txt)
+NCU_TRAFFIC = {(14, 1): 3869696, (17, 1): 127958784 + 3989760}
+
+
+def roofline_queens(n, world, nodes, frontier_nodes, records, lane_ms, int_peak, hbm_peak, peak_src):
+    """Roofline of the dominant kernel, k_queens_lane (subtree DFS; ~80 % of the step, profiles/r1_launches_bench.csv).
+    It is integer-issue bound: algorithmic work = (5A+4) lane-ops per node, A = forward-checking domain
+    updates per node; the peak is the LOP3 rate measured in this run.  Its HBM side is shown next to it: one 16-byte
+    record read per subtree."""
+    ops_per_node = 5 * QUEENS_A[n] + 4
+    lane_nodes = (nodes - frontier_nodes) if world == 1 else None          # N>1: this rank's share is not split out
+    per_gpu_nodes = (nodes / world) if lane_nodes is None else lane_nodes
+    achieved = per_gpu_nodes * ops_per_node / (lane_ms * 1e-3) if lane_ms else 0.0
+    algo_bytes = records * 16 if world == 1 else None
+    return {"bound": "int32-alu", "kernel": "k_queens_lane", "achieved": achieved / 1e12, "peak": int_peak / 1e12,
+            "unit": "Tlane-op/s per GPU", "frac": achieved / int_peak, "kernel_ms": lane_ms,
+            "nodes_per_launch": per_gpu_nodes, "ops_per_node": ops_per_node,
+            "peak_source": "LOP3 microbenchmark (dq_measure_int_peak), this run",
+            "traffic": NCU_TRAFFIC.get((n, world)), "algorithmic_bytes": algo_bytes,
+            "hbm": {"achieved": (algo_bytes / (lane_ms * 1e-3) / 1e9) if algo_bytes and lane_ms else None, "peak": hbm_peak,
+                    "unit": "GB/s", "peak_source": peak_src},
+            "note": "not HBM- or tensor-bound: no dense contraction on this path, one 16 B record per subtree from HBM"}
+
+
+def sudoku_rooflines(out, hbm_peak, peak_src, int_peak):
+    kpps, nps = out.pop("_kernel_pps"), out["nodes_per_sec"]
+    out["roofline"] = {"bound": "hbm", "achieved": kpps * 174 / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                       "frac": kpps * 174 / 1e9 / hbm_peak, "traffic": None, "bytes_per_puzzle": 174, "peak_source": peak_src,
+                       "note": "instance stream only; the search itself is integer-issue bound (see roofline_int)"}
+    out["roofline_int"] = {"ops_per_node": 2 * 10 + 4, "achieved": nps * 24 / 1e12, "peak": int_peak / 1e12, "unit": "Tlane-op/s",
+                           "frac": nps * 24 / int_peak}
+    return out
+
+
+def sudoku_section(args, torch, api, dev):
     """BASELINE config C3: batch of synthetic 9x9 Sudoku (810 binary != arcs), first solution each."""
     from dequan_b200 import generators as G
     from dequan_b200.model import sudoku_template
@@ -359,12 +405,7 @@ def sudoku_section(args, torch, api, dev, hbm_peak, peak_src, int_peak):
            "e2e": {"value": n * steps / e_tot, "unit": "puzzles/s", "h2d_bytes_per_step": n * 81, "d2h_bytes_per_step": n * 90,
                    "ms_per_step": 1e3 * e_tot / steps},
            "gpu_launches": launches, "engine": "lane pipeline (digest, first, strong, walk, count, finish)",
-           "roofline": {"bound": "hbm", "achieved": kpps * 174 / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": kpps * 174 / 1e9 / hbm_peak, "traffic": None, "bytes_per_puzzle": 174, "peak_source": peak_src,
-                        "note": "instance stream only; the search itself is integer-issue bound (see roofline_int)"},
-           "roofline_int": {"ops_per_node": 2 * 10 + 4, "achieved": total_nodes * steps / (kern * 1e-3) * 24 / 1e12,
-                            "peak": int_peak / 1e12, "unit": "Tlane-op/s",
-                            "frac": total_nodes * steps / (kern * 1e-3) * 24 / int_peak}}
+           "_kernel_pps": kpps}
     if not args.no_cpu and os.path.exists(REF_BIN):
         sample = min(n, 16000)
         path = "/tmp/dq_bench_sudoku.txt"

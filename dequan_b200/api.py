@@ -39,7 +39,8 @@ class dq_tree_opts(C.Structure):
 class dq_tree_result(C.Structure):
     _fields_ = [("outcome", C.c_int32), ("n_prefixes", C.c_int32), ("n_solutions", C.c_uint64), ("n_nodes", C.c_uint64),
                 ("first_key", C.c_uint64), ("nodes_before_first", C.c_uint64), ("kernel_ms", C.c_double),
-                ("engine_used", C.c_int32), ("split_depth_used", C.c_int32), ("kernel_launches", C.c_uint64)]
+                ("engine_used", C.c_int32), ("split_depth_used", C.c_int32), ("kernel_launches", C.c_uint64),
+                ("search_kernel_ms", C.c_double), ("frontier_nodes", C.c_uint64)]
 
 
 class dq_batch_opts(C.Structure):
@@ -126,6 +127,8 @@ class TreeResult:
     kernel_ms: float
     engine: str
     launches: int
+    search_kernel_ms: float = 0.0
+    frontier_nodes: int = 0
 
 
 @dataclass
@@ -187,7 +190,7 @@ class Model:
         have = r.first_key != U64_MAX and (self.n_vars == 0 or first[0] != UNASSIGNED)
         return TreeResult(OUTCOME[r.outcome], r.n_solutions, r.n_nodes, first[:self.n_vars].tolist() if have else None,
                           r.first_key, r.n_prefixes, r.split_depth_used, r.kernel_ms,
-                          ENGINE_NAME.get(r.engine_used, "?"), r.kernel_launches)
+                          ENGINE_NAME.get(r.engine_used, "?"), r.kernel_launches, r.search_kernel_ms, r.frontier_nodes)
 
     def table_bytes(self) -> int:
         n = C.c_uint64()

@@ -92,7 +92,7 @@ struct DevBuf {
 struct DeviceCtx {
     int dev = -1, sm_count = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
 };
 static thread_local std::vector<DeviceCtx> g_ctx;
 static cudaError_t device_ctx(DeviceCtx** out) {
@@ -106,6 +106,8 @@ static cudaError_t device_ctx(DeviceCtx** out) {
     if ((e = cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking)) != cudaSuccess) return e;
     if ((e = cudaEventCreate(&c.ev0)) != cudaSuccess) return e;
     if ((e = cudaEventCreate(&c.ev1)) != cudaSuccess) return e;
+    if ((e = cudaEventCreate(&c.ev2)) != cudaSuccess) return e;
+    if ((e = cudaEventCreate(&c.ev3)) != cudaSuccess) return e;
     g_ctx.push_back(c);
     *out = &g_ctx.back();
     return cudaSuccess;
@@ -126,7 +128,7 @@ struct dq_model {
     CompiledModel cm;
     bool uploaded = false;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     int sm_count = 0;
     // model tables in HBM
     DevBuf<uint8_t> d_blob;                     // all tables, one block
@@ -169,7 +171,7 @@ static int upload(dq_model* m) {
     DQ_CUDA(cudaGetDevice(&dev));
     DeviceCtx* ctx = nullptr;
     DQ_CUDA(device_ctx(&ctx));
-    m->sm_count = ctx->sm_count; m->stream = ctx->stream; m->ev0 = ctx->ev0; m->ev1 = ctx->ev1;
+    m->sm_count = ctx->sm_count; m->stream = ctx->stream; m->ev0 = ctx->ev0; m->ev1 = ctx->ev1; m->ev2 = ctx->ev2; m->ev3 = ctx->ev3;
     const CompiledModel& c = m->cm;
     const int nv = c.nv;
     // every table goes into ONE device block with ONE stream-ordered copy (the solve's kernels follow on the same stream)
@@ -275,8 +277,8 @@ static int solve_queens_lane(dq_model* m, const dq_tree_opts* opts, dq_tree_resu
     size_t cap = std::max<size_t>(m->q_records.cap, (size_t)std::min(std::max(2.0 * estimate(K), 1024.0), 64.0 * 1024 * 1024));
     unsigned long long h_ctrl[32];
     unsigned long long* ctrl = m->d_ctrl.p;     // [0]=cursor [1]=sols [2]=nodes [3]=best [8+l]=frontier size at depth l
-    unsigned long long launches = 0;
-    float ms_total = 0;
+    unsigned long long launches = 0, h_frontier_nodes = 0;
+    float ms_total = 0, ms_search = 0;
     for (int attempt = 0; attempt < 3; attempt++) {
         DQ_CUDA(m->q_records.reserve(cap));
         DQ_CUDA(m->q_records2.reserve(m->q_records.cap));
@@ -300,7 +302,10 @@ static int solve_queens_lane(dq_model* m, const dq_tree_opts* opts, dq_tree_resu
             k_queens_level<<<grid, kQueensBlock, 0, m->stream>>>(A, l, buf[l & 1], ctrl + 8 + l, buf[(l + 1) & 1], ctrl + 8 + l + 1,
                                                                    opts->part_rank == 0 ? 1 : 0, (l == K - 1 && opts->part_count > 1) ? 1 : 0);
         }
+        DQ_CUDA(cudaMemcpyAsync(&h_frontier_nodes, ctrl + 2, sizeof h_frontier_nodes, cudaMemcpyDeviceToHost, m->stream));
+        DQ_CUDA(cudaEventRecord(m->ev2, m->stream));
         k_queens_lane<<<ctas, kQueensBlock, smem, m->stream>>>(A);
+        DQ_CUDA(cudaEventRecord(m->ev3, m->stream));
         k_queens_first<<<1, 32, 0, m->stream>>>(A);
         launches += K + 2;
         DQ_CUDA(cudaGetLastError());
@@ -311,6 +316,7 @@ static int solve_queens_lane(dq_model* m, const dq_tree_opts* opts, dq_tree_resu
         float ms = 0;
         DQ_CUDA(cudaEventElapsedTime(&ms, m->ev0, m->ev1));
         ms_total += ms;
+        DQ_CUDA(cudaEventElapsedTime(&ms_search, m->ev2, m->ev3));
         unsigned long long biggest = 0;
         for (int l = 0; l <= K; l++) biggest = std::max(biggest, h_ctrl[8 + l]);
         if (biggest <= rcap) break;
@@ -319,6 +325,8 @@ static int solve_queens_lane(dq_model* m, const dq_tree_opts* opts, dq_tree_resu
         if (attempt == 2) { g_err = "internal: record list overflow persists"; return DQ_ERR_INTERNAL; }
     }
     res->kernel_ms = ms_total;
+    res->search_kernel_ms = ms_search;
+    res->frontier_nodes = h_frontier_nodes;
     res->kernel_launches = launches;
     res->engine_used = DQ_ENGINE_LANE;
     res->split_depth_used = K;

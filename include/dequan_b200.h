@@ -130,6 +130,9 @@ typedef struct dq_tree_result {
     int32_t  engine_used;    /* dq_engine actually run                              */
     int32_t  split_depth_used;
     uint64_t kernel_launches;/* number of engine kernels launched by this call      */
+    double   search_kernel_ms;/* device time of the dominant (subtree DFS) kernel alone */
+    uint64_t frontier_nodes; /* nodes counted by the frontier-expansion kernels above
+                                the split depth (the DFS kernel counted the rest)     */
 } dq_tree_result;
 
 typedef struct dq_batch_opts {
