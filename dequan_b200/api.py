@@ -54,7 +54,7 @@ class dq_batch_stats(C.Structure):
 
 EXPORTS = ["dq_device_info", "dq_set_device", "dq_compile", "dq_free", "dq_model_info", "dq_model_order", "dq_model_table_bytes", "dq_solve_tree",
            "dq_tree_nodes_upto", "dq_solve_batch_cells", "dq_solve_batch_cells_dev", "dq_solve_batch_graphs",
-           "dq_measure_int_peak", "dq_last_error", "dq_version"]
+           "dq_measure_int_peak", "dq_last_error", "dq_version", "dq_parse_sudoku_lines", "dq_parse_dimacs_col"]
 
 _lib = None
 
@@ -84,6 +84,8 @@ def lib():
     L.dq_solve_batch_graphs.argtypes = [C.c_int32, C.c_int32, C.c_void_p, u8p, C.c_int64, C.POINTER(dq_batch_opts),
                                         u8p, u64p, u8p, C.POINTER(dq_batch_stats)]
     L.dq_measure_int_peak.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.dq_parse_sudoku_lines.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
+    L.dq_parse_dimacs_col.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_int32), C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
     L.dq_last_error.restype = C.c_char_p
     L.dq_version.restype = C.c_char_p
     for name in EXPORTS:
@@ -244,3 +246,23 @@ def solve_batch_graphs(n_vertices: int, k: int, edge_off: np.ndarray, edges: np.
                                        col.ctypes.data, nodes.ctypes.data, status.ctypes.data, C.byref(st)))
     return BatchResult(col, nodes, status, st.n_sat, st.n_unsat, st.n_budget, st.total_nodes, st.kernel_ms,
                        st.kernel_launches, st.h2d_bytes, st.d2h_bytes)
+
+
+def parse_sudoku_lines(text: str) -> np.ndarray:
+    """81-character lines -> uint8[n, 81] (0 = blank), the input layout of `Model.solve_batch_cells`."""
+    raw = text.encode()
+    cap = raw.count(b"\n") + 1
+    cells = np.zeros((cap, 81), dtype=np.uint8)
+    n = C.c_int64()
+    _check(lib().dq_parse_sudoku_lines(raw, len(raw), cells.ctypes.data, cap, C.byref(n)))
+    return np.ascontiguousarray(cells[:n.value])
+
+
+def parse_dimacs_col(text: str):
+    """DIMACS .col -> (n_vertices, uint8[m, 2] edges, 0-based), the per-instance input of `solve_batch_graphs`."""
+    raw = text.encode()
+    cap = raw.count(b"\ne ") + raw.startswith(b"e ") + 1
+    edges = np.zeros((cap, 2), dtype=np.uint8)
+    nv, m = C.c_int32(), C.c_int64()
+    _check(lib().dq_parse_dimacs_col(raw, len(raw), C.byref(nv), edges.ctypes.data, cap, C.byref(m)))
+    return nv.value, np.ascontiguousarray(edges[:m.value])

@@ -9,5 +9,5 @@ FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompil
        -I"$HERE/../../include" -I"$HERE")
 if [ "${DQ_PTXAS_V:-0}" = "1" ]; then FLAGS+=(-Xptxas -v); fi
 
-"$NVCC" "${FLAGS[@]}" -shared -o "$OUT/libdequan_b200.so" "$HERE/dq_api.cu" "$HERE/dq_compile.cpp"
+"$NVCC" "${FLAGS[@]}" -shared -o "$OUT/libdequan_b200.so" "$HERE/dq_api.cu" "$HERE/dq_compile.cpp" "$HERE/dq_formats.cpp"
 echo "built $OUT/libdequan_b200.so"

@@ -17,6 +17,7 @@
 namespace dq {
 
 static thread_local std::string g_err;
+void set_last_error(const std::string& s) { g_err = s; }
 
 #define DQ_CUDA(call)                                                                       \
     do {                                                                                    \

@@ -213,6 +213,16 @@ int dq_solve_batch_graphs(int32_t n_vertices, int32_t k, const int64_t *edge_off
                           uint8_t *colours, uint64_t *nodes, uint8_t *status,
                           dq_batch_stats *stats);
 
+/* On-disk instance formats for the batch entry points (host-side parsing only).
+ * Sudoku: one puzzle per line, 81 characters, '1'..'9' givens, '0' '.' '_' '*' blank; blank
+ * lines and lines starting with '#' are skipped.  cells[i*81 + c] as dq_solve_batch_cells
+ * expects (stride 81).  *n_out = puzzles parsed.                                          */
+int dq_parse_sudoku_lines(const char *text, size_t len, uint8_t *cells, int64_t cap, int64_t *n_out);
+/* DIMACS .col: "c" comments, one "p edge N M", then "e u v" (1-based).  edges[2*e] = (u-1, v-1)
+ * as dq_solve_batch_graphs expects; N <= 254.                                               */
+int dq_parse_dimacs_col(const char *text, size_t len, int32_t *n_vertices, uint8_t *edges,
+                        int64_t cap_edges, int64_t *n_edges);
+
 /* Integer-pipe microbenchmark (LOP3 issue rate) used as the search roofline
  * denominator: returns measured lane-ops/s on the current device.                */
 int dq_measure_int_peak(double *lane_ops_per_s, double *ms);

@@ -113,3 +113,21 @@ def test_explicit_assign_order_is_validated_and_kept():
     csp.assign_order = [0, 1, 1, 2, 3]
     with pytest.raises(api.DequanError):
         api.Model(csp)
+
+
+def test_on_disk_formats():
+    from dequan_b200 import api, generators as G
+    cells = G.sudoku_batch(5, givens=30)
+    text = "# five puzzles\n" + "\n".join(G.sudoku_lines(cells)).replace("0", ".", 7) + "\n\n"
+    assert (api.parse_sudoku_lines(text) == cells).all()
+    assert api.parse_sudoku_lines("").shape == (0, 81)
+    with pytest.raises(api.DequanError):
+        api.parse_sudoku_lines("123\n")
+    with pytest.raises(api.DequanError):
+        api.parse_sudoku_lines("x" * 81 + "\n")
+    nv, edges = api.parse_dimacs_col("c triangle plus a tail\np edge 4 4\ne 1 2\ne 2 3\ne 1 3\ne 3 4\n")
+    assert nv == 4 and edges.tolist() == [[0, 1], [1, 2], [0, 2], [2, 3]]
+    with pytest.raises(api.DequanError):
+        api.parse_dimacs_col("p edge 3 1\ne 1 4\n")
+    with pytest.raises(api.DequanError):
+        api.parse_dimacs_col("e 1 2\n")

@@ -342,3 +342,18 @@ def test_sudoku_lane_engine_unsat_budget_and_odd_inputs(product_lib):
     assert (gw.nodes == want.nodes[:500]).all() and (gw.solution[:, :81] == want.solution[:500]).all()
     with pytest.raises(api.DequanError):
         api.Model(sudoku_template(boxes=False)).solve_batch_cells(cells[:8], engine="lane")
+
+
+def test_batches_from_on_disk_formats(product_lib):
+    """81-character Sudoku lines and DIMACS .col text go through the parsers into the batch entry points."""
+    cells = G.sudoku_batch(300, givens=31, seed=77)
+    parsed = api.parse_sudoku_lines("\n".join(G.sudoku_lines(cells)) + "\n")
+    tmpl = api.Model(sudoku_template())
+    _same_batch(tmpl.solve_batch_cells(parsed), tmpl.solve_batch_cells(cells), "sudoku lines")
+    edges = G.colouring_instance(60, 3.0, 20261018, 3)
+    text = f"c G(60, 3/59)\np edge 60 {len(edges)}\n" + "".join(f"e {u + 1} {v + 1}\n" for u, v in edges)
+    nv, pe = api.parse_dimacs_col(text)
+    off = np.array([0, len(pe)], dtype=np.int64)
+    r = api.solve_batch_graphs(nv, 3, off, pe, node_budget=20000)
+    o = O.solve(colouring(60, 3, [tuple(e) for e in edges.tolist()]), "first", 20000)
+    assert (api.OUTCOME[r.status[0]], int(r.nodes[0])) == (o.status, o.nodes)
