@@ -289,7 +289,7 @@ static int solve_queens_lane(dq_model* m, const dq_tree_opts* opts, dq_tree_resu
         A.n = N; A.k = K;
         A.part_rank = opts->part_rank; A.part_count = opts->part_count;
         A.records = buf[K & 1]; A.record_cap = rcap; A.n_records = ctrl + 8 + K;
-        A.cursor = ctrl + 0; A.totals = ctrl + 1; A.best_key = ctrl + 3;
+        A.cursor = ctrl + 0; A.totals = ctrl + 1; A.best_key = ctrl + 3; A.dfs_nodes = ctrl + 24;
         A.first_out = m->q_first.p;
         unsigned long long init[32] = {0};
         init[3] = KEY_NONE;
@@ -303,7 +303,6 @@ static int solve_queens_lane(dq_model* m, const dq_tree_opts* opts, dq_tree_resu
             k_queens_level<<<grid, kQueensBlock, 0, m->stream>>>(A, l, buf[l & 1], ctrl + 8 + l, buf[(l + 1) & 1], ctrl + 8 + l + 1,
                                                                    opts->part_rank == 0 ? 1 : 0, (l == K - 1 && opts->part_count > 1) ? 1 : 0);
         }
-        DQ_CUDA(cudaMemcpyAsync(&h_frontier_nodes, ctrl + 2, sizeof h_frontier_nodes, cudaMemcpyDeviceToHost, m->stream));
         DQ_CUDA(cudaEventRecord(m->ev2, m->stream));
         k_queens_lane<<<ctas, kQueensBlock, smem, m->stream>>>(A);
         DQ_CUDA(cudaEventRecord(m->ev3, m->stream));
@@ -318,6 +317,7 @@ static int solve_queens_lane(dq_model* m, const dq_tree_opts* opts, dq_tree_resu
         DQ_CUDA(cudaEventElapsedTime(&ms, m->ev0, m->ev1));
         ms_total += ms;
         DQ_CUDA(cudaEventElapsedTime(&ms_search, m->ev2, m->ev3));
+        h_frontier_nodes = h_ctrl[2];
         unsigned long long biggest = 0;
         for (int l = 0; l <= K; l++) biggest = std::max(biggest, h_ctrl[8 + l]);
         if (biggest <= rcap) break;
@@ -333,7 +333,7 @@ static int solve_queens_lane(dq_model* m, const dq_tree_opts* opts, dq_tree_resu
     res->split_depth_used = K;
     res->n_prefixes = (int32_t)std::min<unsigned long long>(h_ctrl[8 + K], 0x7FFFFFFF);
     res->n_solutions = h_ctrl[1];
-    res->n_nodes = h_ctrl[2];
+    res->n_nodes = h_ctrl[2] + h_ctrl[24];
     res->first_key = h_ctrl[3];
     res->outcome = res->n_solutions ? DQ_SAT : DQ_UNSAT;
     m->last_n_prefix = 0; m->last_depth = 0;

@@ -43,7 +43,8 @@ struct QueensLaneArgs {
     unsigned long long record_cap;
     unsigned long long* n_records;    // depth-k records found (may exceed record_cap: then the host grows and reruns)
     unsigned long long* cursor;       // next record to search
-    unsigned long long* totals;       // [0] solutions, [1] nodes
+    unsigned long long* totals;       // [0] solutions, [1] nodes counted by the frontier (level) kernels
+    unsigned long long* dfs_nodes;    // nodes counted by the subtree DFS kernel
     unsigned long long* best_key;     // lowest item index that holds a solution
     uint8_t* first_out;               // [32] DFS-first solution, values by variable
 };
@@ -164,6 +165,8 @@ k_queens_lane(QueensLaneArgs A) {
     unsigned long long chunk_pos = 0, chunk_end = 0;
     bool exhausted = false;
     const unsigned long long total_warps = (unsigned long long)gridDim.x * (kQueensBlock / 32);
+    // fewer records than lanes: a warp takes no more than its share, its other lanes get work from their mates
+    const uint32_t fair_share = (uint32_t)min((n_rec + total_warps - 1) / total_warps, 32ull);
 
     for (;;) {
         // ---- refill: lanes without a subtree take the next records ----
@@ -180,7 +183,7 @@ k_queens_lane(QueensLaneArgs A) {
                 if (lane == 0) {
                     const unsigned long long cur = *(volatile unsigned long long*)A.cursor;
                     const unsigned long long remaining = cur < n_rec ? n_rec - cur : 0;
-                    size = (uint32_t)min(max(remaining / (4ull * total_warps), (unsigned long long)n_need), 256ull);
+                    size = (uint32_t)min(max(remaining / (4ull * total_warps), (unsigned long long)min(n_need, fair_share)), 256ull);
                     base = atomicAdd(A.cursor, (unsigned long long)size);
                 }
                 base = __shfl_sync(0xFFFFFFFFu, base, 0);
@@ -285,7 +288,7 @@ k_queens_lane(QueensLaneArgs A) {
     }
     if (lane == 0) {
         atomicAdd(A.totals + 0, tot_sols);
-        atomicAdd(A.totals + 1, tot_nodes);
+        atomicAdd(A.dfs_nodes, tot_nodes);
     }
 }
 
