@@ -215,6 +215,7 @@ k_queens_lane(QueensLaneArgs A) {
                 const uint32_t donors = __ballot_sync(0xFFFFFFFFu, have && sp != fb);
                 if (idle == 0xFFFFFFFFu) break;                      // nobody has anything left
                 if (idle && donors) {
+                    __syncwarp();                                    // the donors' frame stores are visible to the takers
                     const int n_pairs = min(__popc(idle), __popc(donors));
                     const int my_idle_rank = __popc(idle & lt), my_donor_rank = __popc(donors & lt);
                     const bool take = !have && my_idle_rank < n_pairs;
