@@ -358,7 +358,8 @@ def sudoku_section(args, torch, api, dev, world=1, rank=0, dist=None, flush=None
     from dequan_b200 import generators as G
     from dequan_b200.model import sudoku_template
     n_total = args.sudoku_n
-    lo, hi = rank * n_total // world, (rank + 1) * n_total // world
+    from dequan_b200 import multi
+    lo, hi = multi.shard_range(n_total, rank, world)
     n = hi - lo
     cells = G.sudoku_batch(n, givens=args.givens, start=lo)
     tmpl = api.Model(sudoku_template())
@@ -412,10 +413,9 @@ def sudoku_section(args, torch, api, dev, world=1, rank=0, dist=None, flush=None
             e_tot += dt
     e_tot = reduce_max(e_tot)
     if world > 1:      # the one collective of a sharded batch: totals
-        acc = torch.tensor([st.n_sat, total_nodes], dtype=torch.int64, device=dev)
-        dist.all_reduce(acc, op=dist.ReduceOp.SUM)
-        assert int(acc[0]) == n_total
-        total_nodes = int(acc[1])
+        g = multi.reduce_batch(st.n_sat, st.n_unsat, st.n_budget, total_nodes, device=dev)
+        assert g.n_sat == n_total
+        total_nodes = g.nodes
     # checks: device and host legs agree; solutions are valid grids consistent with the givens
     sol = h_sol.numpy()
     assert (d_sol.cpu().numpy() == sol).all() and (d_nodes.cpu().numpy() == h_nodes.numpy()).all()

@@ -54,3 +54,24 @@ def reduce_tree(local, nodes_upto: Callable[[int], int], mode: str, n_vars: int,
     solutions = int(acc[0].item()) if mode == "count" else (1 if have else 0)
     return GlobalTreeResult("sat" if solutions else "unsat", solutions, int(acc[1].item()),
                             sol[:n_vars].tolist() if have else None, gkey if have else U64_MAX)
+
+
+def shard_range(n: int, rank: int, world: int):
+    """Contiguous instance range of `rank` when a batch of n instances is cut into `world` shards."""
+    return rank * n // world, (rank + 1) * n // world
+
+
+@dataclass
+class GlobalBatchTotals:
+    n_sat: int
+    n_unsat: int
+    n_budget: int
+    nodes: int
+
+
+def reduce_batch(n_sat: int, n_unsat: int, n_budget: int, nodes: int, device="cpu", group=None) -> GlobalBatchTotals:
+    """The one collective of a sharded batch: every rank solved its own contiguous shard (outputs stay local);
+    the totals are summed."""
+    acc = torch.tensor([int(n_sat), int(n_unsat), int(n_budget), int(nodes)], dtype=torch.int64, device=device)
+    dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=group)
+    return GlobalBatchTotals(*[int(x) for x in acc.tolist()])

@@ -55,3 +55,38 @@ def test_reduce_tree_matches_unsplit(world):
         csp = nqueens(arg) if kind == "q" else random_model(arg, 7, 9, 5, "ne")
         want = O.solve(csp, mode)
         assert g == (want.status, want.solutions, want.nodes, want.first), (kind, arg, mode, depth, g, want)
+
+
+def _batch_worker(rank, world, port, n, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from dequan_b200 import generators as G
+    from dequan_b200.model import sudoku
+    lo, hi = multi.shard_range(n, rank, world)
+    cells = G.sudoku_batch(hi - lo, givens=36, seed=5, start=lo)          # each rank generates and solves only its shard
+    outs = [O.solve(sudoku(c), "first") for c in cells]
+    g = multi.reduce_batch(sum(o.status == "sat" for o in outs), sum(o.status == "unsat" for o in outs), 0, sum(o.nodes for o in outs))
+    if rank == 0:
+        out.put((g.n_sat, g.n_unsat, g.n_budget, g.nodes))
+    dist.destroy_process_group()
+
+
+def test_sharded_batch_totals():
+    """Batches shard by contiguous instance ranges; shards regenerate the same instances the whole batch holds."""
+    from dequan_b200 import generators as G
+    from dequan_b200.model import sudoku
+    n, world = 24, 2
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_batch_worker, args=(r, world, port, n, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = out.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    whole = [O.solve(sudoku(c), "first") for c in G.sudoku_batch(n, givens=36, seed=5)]
+    assert got == (sum(o.status == "sat" for o in whole), 0, 0, sum(o.nodes for o in whole))
+    assert [multi.shard_range(10, r, 3) for r in range(3)] == [(0, 3), (3, 6), (6, 10)]
