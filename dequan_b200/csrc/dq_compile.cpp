@@ -37,6 +37,23 @@ uint32_t op_mask(const std::vector<int32_t>& qvals, int op, int64_t t) {
     return m;
 }
 
+// Same mask in O(1) when q's value list is one ascending run minv, minv+1, ... (every Ranges domain with a single
+// range — AddIntVar(min, max) — which is what the BASELINE models use).
+inline uint32_t low_bits(int64_t n, int k) { return n <= 0 ? 0u : (n >= k ? (k == 32 ? 0xFFFFFFFFu : (1u << k) - 1u) : (1u << n) - 1u); }
+uint32_t op_mask_run(int64_t minv, int k, int op, int64_t t) {
+    const uint32_t full = low_bits(k, k);
+    const int64_t i = t - minv;                                   // index of value t
+    switch (op) {
+        case DQ_OP_EQUAL:    return (i >= 0 && i < k) ? 1u << i : 0u;
+        case DQ_OP_NOTEQUAL: return (i >= 0 && i < k) ? full & ~(1u << i) : full;
+        case DQ_OP_SUPEQUAL: return full & ~low_bits(i, k);       // y >= t
+        case DQ_OP_SUP:      return full & ~low_bits(i + 1, k);   // y >= t + 1
+        case DQ_OP_INFEQUAL: return low_bits(i + 1, k);           // y <  t + 1
+        case DQ_OP_INF:      return low_bits(i, k);               // y <  t
+    }
+    return 0;
+}
+
 int reverse_op(int op) {  // dequan.h:681-690
     switch (op) {
         case DQ_OP_SUPEQUAL: return DQ_OP_INFEQUAL;
@@ -83,6 +100,17 @@ int compile_model(const dq_model_desc* d, CompiledModel& M, std::string& err) {
         M.dom0[v] = vals.size() == 32 ? 0xFFFFFFFFu : ((1u << vals.size()) - 1u);
         M.kmax = std::max(M.kmax, (int)vals.size());
     }
+
+    std::vector<char> is_run(nv, 0);                      // value list is minv, minv+1, ...
+    for (int v = 0; v < nv; v++) {
+        const std::vector<int32_t>& vals = M.values[v];
+        bool run = !vals.empty();
+        for (size_t j = 1; j < vals.size() && run; j++) run = (int64_t)vals[j] == (int64_t)vals[j - 1] + 1;
+        is_run[v] = run;
+    }
+    auto mask_of = [&](int q, int op, int64_t t) -> uint32_t {
+        return is_run[q] ? op_mask_run(M.values[q][0], (int)M.values[q].size(), op, t) : op_mask(M.values[q], op, t);
+    };
 
     // ---- static order: (initial size asc, id asc), Assignment::Reset dequan.h:384-394 ----
     M.order.resize(nv);
@@ -142,13 +170,24 @@ int compile_model(const dq_model_desc* d, CompiledModel& M, std::string& err) {
     // ---- per ordered pair (x -> q): the sequence of filters in x's link order ----
     M.ent_off.assign(nv + 1, 0);
     int forced_total = 0;
+    std::vector<int> qorder_buf;
+    std::vector<std::vector<PairOp>> ops_buf(nv);
+    std::vector<size_t> op_count(nv, 0);
     for (int x = 0; x < nv; x++) {
         const std::vector<int32_t>& xv = M.values[x];
         const int kx = (int)xv.size();
-        std::vector<int> qorder;                       // neighbours in first-touch order
-        std::map<int, std::vector<PairOp>> ops;
+        std::vector<int>& qorder = qorder_buf;         // neighbours in first-touch order
+        std::vector<std::vector<PairOp>>& ops = ops_buf;
+        for (int q : qorder) ops[q].clear();           // left over from the previous x
+        qorder.clear();
         auto push = [&](int q, EntryKind kind, std::vector<uint32_t>&& m) {
-            if (!ops.count(q)) qorder.push_back(q);
+            if (ops[q].empty()) qorder.push_back(q);
+            // consecutive AND filters on the same pair compose into one (the normalisation below would do it anyway)
+            if (kind == K_AND && !ops[q].empty() && ops[q].back().kind == K_AND) {
+                std::vector<uint32_t>& acc = ops[q].back().m;
+                for (int b = 0; b < kx; b++) acc[b] &= m[b];
+                return;
+            }
             ops[q].push_back(PairOp{kind, std::move(m)});
         };
         for (int c : links[x]) {
@@ -160,18 +199,25 @@ int compile_model(const dq_model_desc* d, CompiledModel& M, std::string& err) {
                 const int64_t off = k.kind == DQ_CON_EQ ? 0 : k.data[3];
                 // x==v0 assigned -> q=v1 filtered with reversed op against a-off; x==v1 -> q=v0 with op against a+off
                 if (x_is_v0) op = reverse_op(op);
-                std::vector<uint32_t> m(kx);
-                for (int b = 0; b < kx; b++) {
-                    int64_t t = x_is_v0 ? (int64_t)xv[b] - off : (int64_t)xv[b] + off;
-                    m[b] = op_mask(M.values[q], op, t);
+                const EntryKind kind = op == DQ_OP_EQUAL ? K_WEQ : K_AND;
+                auto mask_at = [&](int b) {
+                    const int64_t t = x_is_v0 ? (int64_t)xv[b] - off : (int64_t)xv[b] + off;
+                    return mask_of(q, op, t);
+                };
+                if (kind == K_AND && !ops[q].empty() && ops[q].back().kind == K_AND) {
+                    std::vector<uint32_t>& acc = ops[q].back().m;          // compose in place, no temporary
+                    for (int b = 0; b < kx; b++) acc[b] &= mask_at(b);
+                } else {
+                    std::vector<uint32_t> m(kx);
+                    for (int b = 0; b < kx; b++) m[b] = mask_at(b);
+                    push(q, kind, std::move(m));
                 }
-                push(q, op == DQ_OP_EQUAL ? K_WEQ : K_AND, std::move(m));
             } else if (k.kind == DQ_CON_ALLDIFF) {
                 for (int i = 0; i < k.n; i++) {        // AllDifferent::AplyArcConsistency, dequan.h:915-939
                     int q = k.data[i];
                     if (q == x) continue;
                     std::vector<uint32_t> m(kx);
-                    for (int b = 0; b < kx; b++) m[b] = op_mask(M.values[q], DQ_OP_NOTEQUAL, xv[b]);
+                    for (int b = 0; b < kx; b++) m[b] = mask_of(q, DQ_OP_NOTEQUAL, xv[b]);
                     push(q, K_AND, std::move(m));
                 }
             } else if (k.kind == DQ_CON_ORRANGE) {     // Evaluate only (dequan.h:844-854); filter compiled out (860-893)
@@ -230,8 +276,7 @@ int compile_model(const dq_model_desc* d, CompiledModel& M, std::string& err) {
                 passes[p].push_back(std::move(norm[p]));
                 pass_q[p].push_back(q);
             }
-            ops[q].clear();
-            ops[q].resize(norm.size());                // keep the count for flagging below
+            op_count[q] = norm.size();                 // for flagging below
         }
         forced_total += 2 * multi_pairs;
         for (size_t p = 0; p < passes.size(); p++) {
@@ -239,7 +284,7 @@ int compile_model(const dq_model_desc* d, CompiledModel& M, std::string& err) {
                 const PairOp& o = passes[p][i];
                 const int q = pass_q[p][i];
                 uint32_t w = (uint32_t)q | ((uint32_t)o.kind << 8);
-                const size_t cnt = ops[q].size();
+                const size_t cnt = op_count[q];
                 if (cnt > 1) w |= (p == 0) ? (ENT_FORCE_D | ENT_FORCE_F) : (ENT_NOTRAIL_D | ENT_NOTRAIL_F);
                 if (o.kind == K_WEQ || o.kind == K_CHK) M.has_f = true;
                 if (o.kind != K_NE_SAME) {
