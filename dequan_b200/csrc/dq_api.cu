@@ -298,10 +298,15 @@ static int solve_queens_lane(dq_model* m, const dq_tree_opts* opts, dq_tree_resu
         DQ_CUDA(cudaMemcpyAsync(ctrl, init, sizeof init, cudaMemcpyHostToDevice, m->stream));
         DQ_CUDA(cudaMemcpyAsync(buf[0], &root, sizeof root, cudaMemcpyHostToDevice, m->stream));
         DQ_CUDA(cudaEventRecord(m->ev0, m->stream));
+        // Multi-GPU: the frontier is dealt to the partitions (key mod parts) as soon as it is wide enough to balance —
+        // below that level every partition expands only its own records, above it all of them expand the same few
+        // thousand records and partition 0 alone counts their nodes.
+        const int part_level = std::min(K - 1, 3);
         for (int l = 0; l < K; l++) {
             const int grid = (int)std::min<double>(std::max(estimate(l) * N / kQueensBlock, 1.0), (double)m->sm_count * 8);
+            const int count_nodes = (l > part_level || opts->part_rank == 0) ? 1 : 0;
             k_queens_level<<<grid, kQueensBlock, 0, m->stream>>>(A, l, buf[l & 1], ctrl + 8 + l, buf[(l + 1) & 1], ctrl + 8 + l + 1,
-                                                                   opts->part_rank == 0 ? 1 : 0, (l == K - 1 && opts->part_count > 1) ? 1 : 0);
+                                                                   count_nodes, (l == part_level && opts->part_count > 1) ? 1 : 0);
         }
         DQ_CUDA(cudaEventRecord(m->ev2, m->stream));
         k_queens_lane<<<ctas, kQueensBlock, smem, m->stream>>>(A);
