@@ -681,6 +681,8 @@ static int run_batch_sudoku(dq_model* m, const uint8_t* cells_dev, int64_t n, in
     A.status = status_dev; A.hard = m->s_hard.p; A.tasks = m->s_tasks.p; A.task_cap = task_cap;
     A.snaps = m->s_snaps.p; A.snap_cap = snap_cap; A.ctrl = ctrl; A.user_budget = opts ? opts->node_budget : 0;
     A.force_donate = opts && opts->task_nodes > 0 ? (unsigned)opts->task_nodes : 0u;
+    const char* env_h = getenv("DQ_SUDOKU_HIDDEN_AFTER");
+    A.strong_hidden_after = env_h ? (unsigned)atoi(env_h) : kStrongHiddenAfter;
     const char* env_q = getenv("DQ_SUDOKU_POP_QUORUM");
     A.pop_quorum = env_q ? atoi(env_q) : kPopQuorum;
     const char* env_fb = getenv("DQ_SUDOKU_FIRST_BUDGET");

@@ -109,6 +109,7 @@ struct SudokuArgs {
     unsigned long long* ctrl;              // control block, see SkCtrl
     unsigned long long user_budget;        // per-instance node budget of the API (0 = none)
     unsigned first_budget;                 // nodes k_sudoku_first spends on an instance before calling it hard
+    unsigned strong_hidden_after;          // k_sudoku_strong: value tries after which hidden-single propagation joins in
     int pop_quorum;                        // extra step-back rounds run while at least this many lanes still stand on an exhausted level
     unsigned force_donate;                 // test knob: donate whenever a task is this many nodes old, hungry lanes or not (0 = off)
 };
@@ -558,13 +559,49 @@ k_sudoku_first(SudokuArgs A) {
 // propagated to its peers".  Same static order, same ascending value order as the reference, plus
 // naked-single propagation to a fixed point after every assignment, so the first solution it
 // reaches is the reference's first solution.
+constexpr unsigned kStrongHiddenAfter = 400;   // value tries after which an instance also gets hidden-single propagation
+
 struct StrongSmem {
     uint32_t peer[81][32];               // peer[x][lane]: bit 10*f set iff cell lane+32f is a peer of x
     uint32_t saved[4][81][32];           // per warp, per level: the registers before the level's first value
     uint16_t rest[4][81];                // per warp, per level: values still to try (0: forced level)
 };
 
-__device__ __forceinline__ bool sk_propagate(uint32_t& D, const StrongSmem& M, int lane, uint32_t valid3) {
+// Hidden singles: a value that only one cell of a row, column or box can still take goes to that cell; a value no
+// cell of the unit can take is a contradiction.  Lane u < 27 owns unit u (its three 32-bit cell masks u0..u2 in the
+// lane/field numbering); per value, three ballots give the 81-bit "cells that can hold it" mask.
+// Returns false on a contradiction; `changed` reports whether any domain was cut.
+__device__ __forceinline__ bool sk_hidden_singles(uint32_t& D, int lane, uint32_t u0, uint32_t u1, uint32_t u2, bool& changed) {
+    bool mine = false;
+#pragma unroll 1
+    for (int v = 0; v < 9; v++) {
+        const uint32_t w0 = __ballot_sync(0xFFFFFFFFu, (D >> v) & 1u) & u0;
+        const uint32_t w1 = __ballot_sync(0xFFFFFFFFu, (D >> (10 + v)) & 1u) & u1;
+        const uint32_t w2 = __ballot_sync(0xFFFFFFFFu, (D >> (20 + v)) & 1u) & u2;
+        const int cnt = __popc(w0) + __popc(w1) + __popc(w2);
+        if (__any_sync(0xFFFFFFFFu, lane < 27 && cnt == 0)) return false;
+        uint32_t hs = __ballot_sync(0xFFFFFFFFu, lane < 27 && cnt == 1);
+        const int cell = w0 ? __ffs(w0) - 1 : (w1 ? 32 + __ffs(w1) - 1 : 64 + __ffs(w2) - 1);
+        while (hs) {
+            const int u = __ffs(hs) - 1;
+            hs &= hs - 1;
+            const int c = __shfl_sync(0xFFFFFFFFu, cell, u);
+            if (lane == (c & 31)) {
+                const int f = c >> 5;
+                if (((D >> (10 * f)) & 0x1FF) != (1u << v)) {             // more than this value left: cut (flag stays clear)
+                    D = (D & ~(0x3FFu << (10 * f))) | ((1u << v) << (10 * f));
+                    mine = true;
+                }
+            }
+        }
+    }
+    changed = __any_sync(0xFFFFFFFFu, mine);
+    return true;
+}
+
+// Naked singles to a fixed point; with `hidden`, hidden singles as well.
+__device__ __forceinline__ bool sk_propagate(uint32_t& D, const StrongSmem& M, int lane, uint32_t valid3,
+                                             bool hidden, uint32_t u0, uint32_t u1, uint32_t u2) {
     for (;;) {
         const uint32_t x3 = D & SK_FULL3;
         const uint32_t zero = ~(x3 + (SK_SPARE - SK_ONES)) & SK_SPARE & (valid3 << 9);    // spare bit of the EMPTY fields
@@ -572,7 +609,13 @@ __device__ __forceinline__ bool sk_propagate(uint32_t& D, const StrongSmem& M, i
         const uint32_t unfl = ~D & SK_SPARE & (valid3 << 9);
         const uint32_t sing = sk_singletons(x3 & ((unfl >> 9) * 0x1FFu));
         const uint32_t b = __ballot_sync(0xFFFFFFFFu, sing != 0);
-        if (!b) return true;
+        if (!b) {
+            if (!hidden) return true;
+            bool changed = false;
+            if (!sk_hidden_singles(D, lane, u0, u1, u2, changed)) return false;
+            if (!changed) return true;
+            continue;
+        }
         const int j = __ffs(b) - 1;
         const uint32_t sj = __shfl_sync(0xFFFFFFFFu, sing, j);
         const int f = (sj & 0x1FF) ? 0 : (((sj >> 10) & 0x1FF) ? 1 : 2);
@@ -602,6 +645,15 @@ k_sudoku_strong(SudokuArgs A) {
     }
     __syncthreads();
     const uint32_t valid3 = lane < 17 ? SK_ONES : 0x00000401u;      // lanes 17..31 hold two cells
+    // lane u < 27 owns unit u (rows 0-8, columns 9-17, boxes 18-26): its cells as bit (cell & 31) of word (cell >> 5)
+    uint32_t u0 = 0, u1 = 0, u2 = 0;
+    if (lane < 27)
+        for (int k = 0; k < 9; k++) {
+            const int cell = lane < 9 ? lane * 9 + k : (lane < 18 ? k * 9 + (lane - 9)
+                                                                  : ((lane - 18) / 3 * 3 + k / 3) * 9 + ((lane - 18) % 3 * 3 + k % 3));
+            const uint32_t bit = 1u << (cell & 31);
+            if (cell < 32) u0 |= bit; else if (cell < 64) u1 |= bit; else u2 |= bit;
+        }
     const unsigned long long n_hard = A.ctrl[SKC_HARD];
     for (;;) {
         unsigned long long idx = 0;
@@ -630,7 +682,10 @@ k_sudoku_strong(SudokuArgs A) {
             }
         }
         // explicit-stack DFS over the blank levels; `back` = the level was reached by stepping back
-        int l = sk_propagate(D, M, lane, valid3) ? 0 : -1;
+        // Instances that stay hard under naked singles alone (a few per thousand) switch hidden singles on as well: any
+        // sound pruning leaves the first solution in DFS order where it is.
+        unsigned tries = 0;
+        int l = sk_propagate(D, M, lane, valid3, false, u0, u1, u2) ? 0 : -1;
         bool back = false;
         while (l >= 0 && l < nblank) {
             const int p = (int)((__shfl_sync(0xFFFFFFFFu, cw, l >> 2) >> ((l & 3) * 8)) & 0xFF);
@@ -654,7 +709,8 @@ k_sudoku_strong(SudokuArgs A) {
                 D = M.saved[wib][l][lane];
                 if (lane == owner) D = (D & ~(0x3FFu << (10 * f))) | ((v | 0x200u) << (10 * f));
                 D &= ~(M.peer[p][lane] * v);
-                if (sk_propagate(D, M, lane, valid3)) { ok = true; break; }
+                ++tries;
+                if (sk_propagate(D, M, lane, valid3, tries > A.strong_hidden_after, u0, u1, u2)) { ok = true; break; }
             }
             __syncwarp();
             if (lane == 0) M.rest[wib][l] = (uint16_t)d;
