@@ -666,8 +666,9 @@ static int run_batch_sudoku(dq_model* m, const uint8_t* cells_dev, int64_t n, in
     if (rc == DQ_OK) rc = max_ctas_per_sm(k_sudoku_strong, 128, smem_strong, &occ_strong);
     if (rc != DQ_OK) return rc;
     if (occ_first < 1 || occ_count < 1 || occ_walk < 1 || occ_strong < 1) { g_err = "kernel does not fit an SM"; return DQ_ERR_UNSUPPORTED; }
-    const unsigned long long task_cap = std::max<unsigned long long>(1u << 20, std::min<unsigned long long>(8ull * n, 1ull << 25));
-    const unsigned long long snap_cap = std::max<unsigned long long>(1u << 18, std::min<unsigned long long>(2ull * n, 1ull << 23));
+    // the number of pieces handed over at the tail does not shrink with the batch: generous floors (64 MB + 192 MB)
+    const unsigned long long task_cap = std::max<unsigned long long>(1u << 22, std::min<unsigned long long>(8ull * n, 1ull << 25));
+    const unsigned long long snap_cap = std::max<unsigned long long>(1u << 20, std::min<unsigned long long>(2ull * n, 1ull << 23));
     const bool fresh_pool = m->s_tasks.cap < task_cap;
     DQ_CUDA(m->s_digest.reserve(n)); DQ_CUDA(m->s_hard.reserve(2 * (size_t)n)); DQ_CUDA(m->s_ctrl.reserve(16));
     DQ_CUDA(m->s_tasks.reserve(task_cap)); DQ_CUDA(m->s_snaps.reserve(snap_cap * kSnapWords));
@@ -681,6 +682,10 @@ static int run_batch_sudoku(dq_model* m, const uint8_t* cells_dev, int64_t n, in
     A.status = status_dev; A.hard = m->s_hard.p; A.tasks = m->s_tasks.p; A.task_cap = task_cap;
     A.snaps = m->s_snaps.p; A.snap_cap = snap_cap; A.ctrl = ctrl; A.user_budget = opts ? opts->node_budget : 0;
     A.force_donate = opts && opts->task_nodes > 0 ? (unsigned)opts->task_nodes : 0u;
+    const char* env_dm = getenv("DQ_SUDOKU_DONATE_MIN");
+    const char* env_dg = getenv("DQ_SUDOKU_DONATE_GAP");
+    A.donate_min = env_dm ? (unsigned)atoi(env_dm) : kDonateMinNodes;
+    A.donate_gap = env_dg ? (unsigned)atoi(env_dg) : kDonateGap;
     const char* env_h = getenv("DQ_SUDOKU_HIDDEN_AFTER");
     A.strong_hidden_after = env_h ? (unsigned)atoi(env_h) : kStrongHiddenAfter;
     const char* env_q = getenv("DQ_SUDOKU_POP_QUORUM");

@@ -109,6 +109,7 @@ struct SudokuArgs {
     unsigned long long* ctrl;              // control block, see SkCtrl
     unsigned long long user_budget;        // per-instance node budget of the API (0 = none)
     unsigned first_budget;                 // nodes k_sudoku_first spends on an instance before calling it hard
+    unsigned donate_min, donate_gap;       // k_sudoku_count: a task gives a level away only when it is this old / this long after the last time
     unsigned strong_hidden_after;          // k_sudoku_strong: value tries after which hidden-single propagation joins in
     int pop_quorum;                        // extra step-back rounds run while at least this many lanes still stand on an exhausted level
     unsigned force_donate;                 // test knob: donate whenever a task is this many nodes old, hungry lanes or not (0 = off)
@@ -839,8 +840,8 @@ k_sudoku_walk(SudokuArgs A) {
 // donor's snapshot; the donor keeps the deeper ones.  Every level is owned by exactly one task,
 // which also counts the level's failing leftovers when it steps back through it.
 constexpr int kDonatePeriod = 32;
-constexpr uint32_t kDonateMinNodes = 128;   // a task younger than this keeps its stack to itself
-constexpr uint32_t kDonateGap = 256;        // ... and so does one that gave a level away fewer nodes ago than this
+constexpr uint32_t kDonateMinNodes = 48;    // a task younger than this keeps its stack to itself
+constexpr uint32_t kDonateGap = 96;         // ... and so does one that gave a level away fewer nodes ago than this
 constexpr uint32_t kSplitGap = 4096;        // a task splits unasked every time it has counted this many nodes
 
 __global__ void __launch_bounds__(kSudokuBlock)
@@ -895,7 +896,7 @@ k_sudoku_count(SudokuArgs A) {
                     L.nodes = 0; L.nodes_hi = 0;
                     L.passrem = 0; L.dom_rem = 0;
                     L.have = true;
-                    donate_at = A.force_donate ? A.force_donate : kDonateMinNodes;
+                    donate_at = A.force_donate ? A.force_donate : A.donate_min;
                     split_at = kSplitGap;
                     if (info & SKT_ROOT) {
                         // path values at the levels above, then the task's own value at its level
@@ -979,8 +980,11 @@ k_sudoku_count(SudokuArgs A) {
                     atomicAdd(A.ctrl + SKC_OUTSTANDING, 1ull);                 // the piece exists from here on
                     const unsigned long long slot = atomicAdd(A.ctrl + SKC_RESERVE, 1ull);
                     const unsigned long long sslot = atomicAdd(A.ctrl + SKC_SNAP, 1ull);
-                    if (slot >= A.task_cap) atomicAdd(A.ctrl + SKC_OUTSTANDING, 0ull - 1ull);      // pool full: nobody will ever claim it
-                    else if (sslot >= A.snap_cap) {
+                    if (slot >= A.task_cap) {                                  // pool full: nobody will ever claim it
+                        atomicAdd(A.ctrl + SKC_OUTSTANDING, 0ull - 1ull);
+                        donate_at = 0xFFFFFFFFu; split_at = 0xFFFFFFFFu;       // ... and this task stops offering
+                    } else if (sslot >= A.snap_cap) {
+                        donate_at = 0xFFFFFFFFu; split_at = 0xFFFFFFFFu;
                         // publish a null task: whoever claims it closes it
                         volatile uint32_t* rec = reinterpret_cast<volatile uint32_t*>(A.tasks + slot);
                         rec[0] = L.puzzle; rec[1] = 0;
@@ -994,7 +998,7 @@ k_sudoku_count(SudokuArgs A) {
                         __threadfence();
                         rec[2] = SKT_VALID | (uint32_t)L.base_sp | ((uint32_t)hl << 8);
                         L.base_sp = hl + 1;                                      // this task keeps the deeper levels
-                        donate_at = L.nodes + (A.force_donate ? A.force_donate : kDonateGap);
+                        donate_at = L.nodes + (A.force_donate ? A.force_donate : A.donate_gap);
                         split_at = L.nodes + kSplitGap;
                     }
                 }
