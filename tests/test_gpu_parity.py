@@ -357,3 +357,39 @@ def test_batches_from_on_disk_formats(product_lib):
     r = api.solve_batch_graphs(nv, 3, off, pe, node_budget=20000)
     o = O.solve(colouring(60, 3, [tuple(e) for e in edges.tolist()]), "first", 20000)
     assert (api.OUTCOME[r.status[0]], int(r.nodes[0])) == (o.status, o.nodes)
+
+
+def test_maximum_sizes_and_limits(product_lib):
+    """254 variables (the engine's limit) with 32-value and 2-value domains; the first size beyond each limit is
+    refused with an error, not approximated; empty batches are no-ops."""
+    import random
+    rng = random.Random(3)
+    csp = CSP()
+    n = 254
+    for i in range(n):
+        csp.AddIntVar(0, 32 if i % 50 == 0 else 2)
+    for i in range(n - 1):
+        csp.AddConstraint(OpConstraint(i, i + 1, Op.NotEqual, 0))
+    for _ in range(40):
+        a, b = rng.sample(range(n), 2)
+        csp.AddConstraint(OpConstraint(a, b, Op.NotEqual, rng.choice([0, 1])))
+    _cmp_tree(api.Model(csp).solve_tree("first"), O.solve(csp, "first"), "254 variables")
+    big = CSP()
+    for _ in range(255):
+        big.AddIntVar(0, 2)
+    with pytest.raises(api.DequanError):
+        api.Model(big)
+    wide = CSP()
+    wide.AddIntVar(0, 33)
+    with pytest.raises(api.DequanError):
+        api.Model(wide)
+    tmpl = api.Model(sudoku_template())
+    r = tmpl.solve_batch_cells(np.zeros((0, 81), dtype=np.uint8))
+    assert (r.n_sat, r.n_unsat, r.total_nodes, len(r.nodes)) == (0, 0, 0, 0)
+    r = api.solve_batch_graphs(5, 3, np.zeros(1, dtype=np.int64), np.zeros((0, 2), dtype=np.uint8))
+    assert len(r.status) == 0
+    # a single instance, and a batch smaller than a warp
+    one = G.sudoku_batch(1, givens=30, seed=9)
+    _same_batch(tmpl.solve_batch_cells(one), tmpl.solve_batch_cells(one, engine="warp"), "single instance")
+    few = G.sudoku_batch(7, givens=26, seed=10)
+    _same_batch(tmpl.solve_batch_cells(few), tmpl.solve_batch_cells(few, engine="warp"), "seven instances")
