@@ -12,6 +12,7 @@
 #include "dq_kernels.cuh"
 #include "dq_lane_queens.cuh"
 #include "dq_lane_sudoku.cuh"
+#include "dq_reg_graphs.cuh"
 #include "dq_model.hpp"
 
 namespace dq {
@@ -797,6 +798,9 @@ int dq_solve_batch_graphs(int32_t nv, int32_t k, const int64_t* edge_off, const 
     if (!edge_off || !colours || !nodes || !status) { g_err = "null buffer"; return DQ_ERR_INVALID; }
     const long long total = edge_off[n];
     for (long long e = 0; e < 2 * total; e++) if (edges[e] >= nv) { g_err = "edge endpoint out of range"; return DQ_ERR_INVALID; }
+    for (long long e = 0; e < total; e++) if (edges[2 * e] == edges[2 * e + 1]) { g_err = "edge with u == v"; return DQ_ERR_UNSUPPORTED; }
+    const bool reg_engine = k <= 4 && !(opts && opts->engine == DQ_ENGINE_WARP);       // register-resident warp engine (dq_reg_graphs.cuh)
+    if (opts && opts->engine == DQ_ENGINE_LANE) { g_err = "no lane engine for graph batches"; return DQ_ERR_UNSUPPORTED; }
     int dev = 0, sms = 0;
     DQ_CUDA(cudaGetDevice(&dev));
     DQ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -824,9 +828,21 @@ int dq_solve_batch_graphs(int32_t nv, int32_t k, const int64_t* edge_off, const 
     int rc = max_ctas_per_sm(k_batch_graphs, kWarpsPerCta * 32, smem, &occ);
     if (rc != DQ_OK) return rc;
     DQ_CUDA(cudaEventRecord(e0, s));
-    k_graphs_build<<<(unsigned)((n + kWarpsPerCta - 1) / kWarpsPerCta), kWarpsPerCta * 32, (size_t)kWarpsPerCta * (nv + 1) * 4, s>>>(A);
-    long long ctas = std::min<long long>((n + kWarpsPerCta - 1) / kWarpsPerCta, (long long)std::max(occ, 1) * sms);
-    k_batch_graphs<<<(unsigned)ctas, kWarpsPerCta * 32, smem, s>>>(A);
+    if (reg_engine) {
+        RegGraphsArgs R;
+        R.nv = nv; R.k = k; R.edge_off = d_off.p; R.edges = d_edges.p; R.n = n; R.budget = A.budget; R.cursor = d_ctrl.p;
+        R.colours = d_col.p; R.nodes = d_nodes.p; R.status = d_status.p; R.totals = d_ctrl.p + 1;
+        const size_t rsmem = reg_graphs_warp_bytes(nv, k) * kRegWarpsPerCta;
+        int rocc = 0;
+        rc = max_ctas_per_sm(k_batch_graphs_reg, kRegWarpsPerCta * 32, rsmem, &rocc);
+        if (rc != DQ_OK) return rc;
+        const long long rctas = std::min<long long>((n + kRegWarpsPerCta - 1) / kRegWarpsPerCta, (long long)std::max(rocc, 1) * sms);
+        k_batch_graphs_reg<<<(unsigned)rctas, kRegWarpsPerCta * 32, rsmem, s>>>(R);
+    } else {
+        k_graphs_build<<<(unsigned)((n + kWarpsPerCta - 1) / kWarpsPerCta), kWarpsPerCta * 32, (size_t)kWarpsPerCta * (nv + 1) * 4, s>>>(A);
+        long long ctas = std::min<long long>((n + kWarpsPerCta - 1) / kWarpsPerCta, (long long)std::max(occ, 1) * sms);
+        k_batch_graphs<<<(unsigned)ctas, kWarpsPerCta * 32, smem, s>>>(A);
+    }
     DQ_CUDA(cudaGetLastError());
     DQ_CUDA(cudaEventRecord(e1, s));
     unsigned long long h[8];
@@ -839,7 +855,7 @@ int dq_solve_batch_graphs(int32_t nv, int32_t k, const int64_t* edge_off, const 
         float ms = 0;
         DQ_CUDA(cudaEventElapsedTime(&ms, e0, e1));
         stats->n_sat = h[1]; stats->n_unsat = h[2]; stats->n_budget = h[3]; stats->total_nodes = h[4];
-        stats->kernel_ms = ms; stats->kernel_launches = 2;
+        stats->kernel_ms = ms; stats->kernel_launches = reg_engine ? 1 : 2;
         stats->h2d_bytes = (size_t)(n + 1) * 8 + 2 * (size_t)total; stats->d2h_bytes = (size_t)n * (nv + 9);
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1);

@@ -393,3 +393,20 @@ def test_maximum_sizes_and_limits(product_lib):
     _same_batch(tmpl.solve_batch_cells(one), tmpl.solve_batch_cells(one, engine="warp"), "single instance")
     few = G.sudoku_batch(7, givens=26, seed=10)
     _same_batch(tmpl.solve_batch_cells(few), tmpl.solve_batch_cells(few, engine="warp"), "seven instances")
+
+
+@pytest.mark.parametrize("nv,k,c,budget", [(200, 3, 4.2, 30000), (200, 4, 7.0, 30000), (60, 3, 3.5, 0), (33, 2, 1.2, 0), (1, 3, 0.0, 0),
+                                           (254, 4, 6.0, 5000), (64, 1, 0.5, 0)])
+def test_colouring_register_engine_equals_warp_engine(product_lib, nv, k, c, budget):
+    """dq_reg_graphs.cuh (one register per lane) against the generic warp engine, itself pinned to the reference."""
+    lists = [G.colouring_instance(nv, c, 4242, i) if nv > 1 else np.zeros((0, 2), dtype=np.uint8) for i in range(96)]
+    off = np.zeros(len(lists) + 1, dtype=np.int64)
+    for i, e in enumerate(lists):
+        off[i + 1] = off[i] + len(e)
+    edges = np.ascontiguousarray(np.concatenate(lists, axis=0).astype(np.uint8)) if off[-1] else np.zeros((0, 2), dtype=np.uint8)
+    a = api.solve_batch_graphs(nv, k, off, edges, node_budget=budget)
+    b = api.solve_batch_graphs(nv, k, off, edges, node_budget=budget, engine="warp")
+    _same_batch(a, b, (nv, k, c, budget))
+    assert a.launches == 1 and b.launches == 2
+    with pytest.raises(api.DequanError):        # a self-loop has no lowering (the reference would fail every value of that vertex)
+        api.solve_batch_graphs(3, 3, np.array([0, 1], dtype=np.int64), np.array([[1, 1]], dtype=np.uint8))
