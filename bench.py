@@ -308,7 +308,8 @@ def main():
         cr = api.solve_batch_graphs(200, 3, off, edges, node_budget=100_000)
         extra["colouring_g200_c4.2_k3"] = {"instances": 1024, "node_budget": 100_000, "kernel_ms": cr.kernel_ms,
                                            "instances_per_sec": 1024 / (cr.kernel_ms * 1e-3), "nodes_per_sec": cr.total_nodes / (cr.kernel_ms * 1e-3),
-                                           "sat": cr.n_sat, "unsat": cr.n_unsat, "budget": cr.n_budget, "engine": "warp"}
+                                           "sat": cr.n_sat, "unsat": cr.n_unsat, "budget": cr.n_budget,
+                                           "engine": "register-resident warp engine (dq_reg_graphs.cuh)"}
     if sudoku is not None:
         line["sudoku"] = sudoku_rooflines(sudoku, hbm_peak, peak_src, int_peak)
     line["extra"] = extra
