@@ -139,6 +139,15 @@ int compile_model(const dq_model_desc* d, CompiledModel& M, std::string& err) {
     struct Con { int kind; const int32_t* data; int n; };
     std::vector<Con> cons(d->n_cons);
     std::vector<std::vector<int>> links(nv);
+    {   // size the link lists once
+        std::vector<int> deg(nv, 0);
+        for (int c = 0; c < d->n_cons; c++) {
+            const int32_t* p = d->con_data + d->con_off[c];
+            const int cnt = d->con_kind[c] == DQ_CON_ALLDIFF ? d->con_off[c + 1] - d->con_off[c] : std::min(2, d->con_off[c + 1] - d->con_off[c]);
+            for (int i = 0; i < cnt; i++) if (p[i] >= 0 && p[i] < nv) deg[p[i]]++;
+        }
+        for (int v = 0; v < nv; v++) links[v].reserve(deg[v]);
+    }
     for (int c = 0; c < d->n_cons; c++) {
         cons[c] = {d->con_kind[c], d->con_data + d->con_off[c], d->con_off[c + 1] - d->con_off[c]};
         const Con& k = cons[c];
@@ -173,6 +182,8 @@ int compile_model(const dq_model_desc* d, CompiledModel& M, std::string& err) {
     std::vector<int> qorder_buf;
     std::vector<std::vector<PairOp>> ops_buf(nv);
     std::vector<size_t> op_count(nv, 0);
+    std::vector<std::vector<PairOp>> passes_buf;
+    std::vector<std::vector<int>> pass_q_buf;
     for (int x = 0; x < nv; x++) {
         const std::vector<int32_t>& xv = M.values[x];
         const int kx = (int)xv.size();
@@ -249,9 +260,12 @@ int compile_model(const dq_model_desc* d, CompiledModel& M, std::string& err) {
             }
         }
         // normalise each pair: merge adjacent ANDs, gather all CHKs (they commute) at the end
-        std::vector<std::vector<PairOp>> passes;       // passes[p] = p-th op of every pair
-        std::vector<std::vector<int>> pass_q;
+        std::vector<std::vector<PairOp>>& passes = passes_buf;       // passes[p] = p-th op of every pair
+        std::vector<std::vector<int>>& pass_q = pass_q_buf;
+        for (auto& v : passes) v.clear();
+        for (auto& v : pass_q) v.clear();
         int multi_pairs = 0;
+        size_t n_pass = 0;                             // passes in use for this x (the buffers keep their length)
         for (int q : qorder) {
             std::vector<PairOp>& seq = ops[q];
             std::vector<PairOp> norm;
@@ -271,6 +285,7 @@ int compile_model(const dq_model_desc* d, CompiledModel& M, std::string& err) {
                 if (same) o.kind = K_NE_SAME;
             }
             if (norm.size() > 1) multi_pairs++;
+            n_pass = std::max(n_pass, norm.size());
             for (size_t p = 0; p < norm.size(); p++) {
                 if (passes.size() <= p) { passes.resize(p + 1); pass_q.resize(p + 1); }
                 passes[p].push_back(std::move(norm[p]));
@@ -279,7 +294,7 @@ int compile_model(const dq_model_desc* d, CompiledModel& M, std::string& err) {
             op_count[q] = norm.size();                 // for flagging below
         }
         forced_total += 2 * multi_pairs;
-        for (size_t p = 0; p < passes.size(); p++) {
+        for (size_t p = 0; p < n_pass; p++) {
             for (size_t i = 0; i < passes[p].size(); i++) {
                 const PairOp& o = passes[p][i];
                 const int q = pass_q[p][i];
@@ -294,7 +309,7 @@ int compile_model(const dq_model_desc* d, CompiledModel& M, std::string& err) {
                 } else M.ent_moff.push_back(0);
                 M.ent.push_back((uint16_t)w);
             }
-            if (p + 1 < passes.size())                 // next pass must start on a 32-entry boundary
+            if (p + 1 < n_pass)                        // next pass must start on a 32-entry boundary
                 while ((M.ent.size() - M.ent_off[x]) % 32) { M.ent.push_back((uint16_t)(ENT_SKIP | 0xFF)); M.ent_moff.push_back(0); }
         }
         M.ent_off[x + 1] = (uint32_t)M.ent.size();
