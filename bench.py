@@ -5,11 +5,12 @@ puzzles/sec, on 1/2/4/8 B200, next to the reference dequan timed on the host cor
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     torchrun ... bench.py --gpus N ...                      (N > 1, one rank per GPU, NCCL)
 
-One "step" = one complete solve of the workload through the C ABI:
-  N == 1 : BASELINE config C2, 14-Queens all-solutions (365 596 solutions / 19 787 662 nodes);
-           the line also carries `sudoku` (config C3, 1M puzzles) and `extra.nqueens17_1gpu`.
-  N  > 1 : BASELINE config C5, 17-Queens all-solutions, FC-surviving prefixes dealt round-robin
-           to the ranks, {solutions, nodes} summed with NCCL (strong scaling).
+One "step" = one complete solve of the workload through the C ABI.  The workload is the same at every N, so that the
+1/2/4/8-GPU series is a strong-scaling series of ONE job: BASELINE config C5, 17-Queens all-solutions (95 815 104
+solutions / 5 474 619 051 nodes; 24 ms on one B200 — the largest single-tree configuration and the one the north star
+names), FC-surviving prefixes dealt to the ranks by key, {solutions, nodes} summed with NCCL.  The line also carries
+`sudoku` (config C3, 1M puzzles, sharded over the ranks), and at N == 1 `extra.nqueens14_1gpu` (config C2, 14-Queens:
+value, e2e and roofline of its own) and `extra.colouring_*` (config C4).
 `value`  : inputs/tables already resident in HBM (compiled model re-used), whole-job nodes/s.
 `e2e`    : the same through the host-facing C-ABI calls with HOST buffers, every step: dq_compile of the flat
            model descriptor (CSP::FinalizeModel + Assignment::Reset), table upload, solve, result read-back, dq_free.
@@ -101,13 +102,6 @@ def cpu_baseline_queens(n_gpus: int):
     thr = cpu_threads()
     if not os.path.exists(REF_BIN):
         return cpu_baseline_port_queens(n_gpus)
-    if n_gpus == 1:
-        t = time.time()
-        o = run_ref(["nqueens", 14, "count", thr])[0]
-        wall = time.time() - t
-        assert (o["solutions"], ) == (QUEENS[14][0], )
-        return {"value": o["nodes"] / o["seconds"], "unit": "nodes/s", "cores": min(thr, 14), "kind": "reference",
-                "sample": f"whole 14-Queens tree, depth-1 split, one first-row subtree per thread ({o['nodes']} nodes, {wall:.1f}s wall)"}
     t = time.time()
     o = run_ref(["nqueens", 17, "count", thr, 8, 3])[0]
     wall = time.time() - t
@@ -133,8 +127,8 @@ def reference_arm(args):
     if rank != 0:
         return
     thr = cpu_threads()
-    n = 14 if args.gpus == 1 else 17
-    cmd = ["nqueens", 14, "count", thr] if args.gpus == 1 else ["nqueens", 17, "count", thr, 8, 3]
+    n = 17
+    cmd = ["nqueens", 17, "count", thr, 8, 3]
     times, nodes = [], 0
     kind = "reference" if os.path.exists(REF_BIN) else "port"
     for i in range(args.warmup + args.steps):
@@ -150,8 +144,7 @@ def reference_arm(args):
             nodes += nd
     total = sum(times)
     val = nodes / total
-    sample = ("whole 14-Queens tree, depth-1 split over the host threads" if args.gpus == 1 else
-              "17-Queens subtree under prefix (8,3) split over the host threads (bounded sample of the 5.47e9-node tree)")
+    sample = "17-Queens subtree under prefix (8,3) split over the host threads (bounded sample of the 5.47e9-node tree)"
     line = {"impl": "reference", "metric": "search_nodes_per_sec", "value": val, "unit": "nodes/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / max(len(times), 1),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
@@ -163,8 +156,11 @@ def reference_arm(args):
 
 
 def workload_config(n_gpus, n):
-    return {"workload": f"nqueens{n}_count_all", "model": "N vars AddIntVar(0,N), 3 OpConstraint NotEqual per pair (main-test.cpp:36-49)",
-            "parallelism": "single tree, FC-surviving prefixes in DFS order" + (f", dealt round-robin to {n_gpus} GPUs, NCCL sum" if n_gpus > 1 else ""),
+    which = {17: "BASELINE config C5 (the same job at every N: strong scaling; C2 = 14-Queens is reported in extra.nqueens14_1gpu)",
+             14: "BASELINE config C2"}.get(n, "")
+    return {"workload": f"nqueens{n}_count_all", "baseline_config": which,
+            "model": "N vars AddIntVar(0,N), 3 OpConstraint NotEqual per pair (main-test.cpp:36-49)",
+            "parallelism": "single tree, FC-surviving prefixes in DFS order" + (f", dealt by key to {n_gpus} GPUs, NCCL sum" if n_gpus > 1 else ""),
             "l2": "flushed between steps (256 MiB write, untimed)"}
 
 
@@ -209,59 +205,66 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    n = 14 if world == 1 else 17
-    want_sols, want_nodes = QUEENS[n]
-    csp = nqueens(n)
-    model = api.Model(csp)
+    def measure_queens(n, steps, warmup):
+        """value / e2e legs of the N-Queens all-solutions workload; every step's result is checked."""
+        want_sols, want_nodes = QUEENS[n]
+        csp = nqueens(n)
+        model = api.Model(csp)
 
-    def solve_step(m):
-        loc = m.solve_tree("count", part_rank=rank, part_count=world, engine=args.engine)
-        if world == 1:
-            return loc, loc.solutions, loc.nodes
-        g = multi.reduce_tree(loc, m.nodes_upto, "count", n, device=dev)
-        return loc, g.solutions, g.nodes
+        def solve_step(m):
+            loc = m.solve_tree("count", part_rank=rank, part_count=world, engine=args.engine)
+            if world == 1:
+                return loc, loc.solutions, loc.nodes
+            g = multi.reduce_tree(loc, m.nodes_upto, "count", n, device=dev)
+            return loc, g.solutions, g.nodes
 
-    dom = {"ms": 0.0, "frontier_nodes": 0, "records": 0}
+        dom = {"ms": 0.0, "frontier_nodes": 0, "records": 0}
 
-    def timed_steps(step_fn, k, w):
-        tot, kern, launches = 0.0, 0.0, 0
-        dom["ms"] = 0.0
-        for i in range(w + k):
-            flush.fill_(i & 0xFF)
-            sync_all()
-            t0 = time.perf_counter()
-            loc, sols, nodes = step_fn()
-            sync_all()
-            dt = time.perf_counter() - t0
-            assert (sols, nodes) == (want_sols, want_nodes), f"parity failure in bench step: {(sols, nodes)}"
-            if i >= w:
-                tot += dt
-                kern += loc.kernel_ms
-                launches += loc.launches
-                dom["ms"] += loc.search_kernel_ms
-                dom["frontier_nodes"], dom["records"] = loc.frontier_nodes, loc.n_prefixes
-        if world > 1:
-            t = torch.tensor([tot, kern], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            tot, kern = float(t[0]), float(t[1])
-        return tot, kern, launches
+        def timed_steps(step_fn, k, w):
+            tot, kern, launches = 0.0, 0.0, 0
+            dom["ms"] = 0.0
+            for i in range(w + k):
+                flush.fill_(i & 0xFF)
+                sync_all()
+                t0 = time.perf_counter()
+                loc, sols, nodes = step_fn()
+                sync_all()
+                dt = time.perf_counter() - t0
+                assert (sols, nodes) == (want_sols, want_nodes), f"parity failure in bench step: {(sols, nodes)}"
+                if i >= w:
+                    tot += dt
+                    kern += loc.kernel_ms
+                    launches += loc.launches
+                    dom["ms"] += loc.search_kernel_ms
+                    dom["frontier_nodes"], dom["records"] = loc.frontier_nodes, loc.n_prefixes
+            if world > 1:
+                t = torch.tensor([tot, kern], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                tot, kern = float(t[0]), float(t[1])
+            return tot, kern, launches
+
+        tot, kern_ms, launches = timed_steps(lambda: solve_step(model), steps, warmup)
+        dom_ms, dom_frontier, dom_records = dom["ms"], dom["frontier_nodes"], dom["records"]
+        desc_keep = csp.desc()          # the host-side flat descriptor: the input buffers of the C-ABI call
+
+        def e2e_step():
+            m = api.Model(csp, desc_keep)   # dq_compile: FinalizeModel + Reset on the host, tables uploaded by the solve
+            r = solve_step(m)
+            m.close()
+            return r
+        e_tot, _, _ = timed_steps(e2e_step, steps, warmup)
+        return {"n": n, "nodes": want_nodes, "steps": steps, "tot": tot, "kern_ms": kern_ms, "launches": launches, "e_tot": e_tot,
+                "dom_ms": dom_ms, "dom_frontier": dom_frontier, "dom_records": dom_records, "table_bytes": model.table_bytes(),
+                "engine": model.solve_tree("count", part_rank=rank, part_count=world, engine=args.engine).engine}
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    tot, kern_ms, launches = timed_steps(lambda: solve_step(model), args.steps, args.warmup)
-    dom_ms, dom_frontier, dom_records = dom["ms"], dom["frontier_nodes"], dom["records"]
-
-    desc_keep = csp.desc()          # the host-side flat descriptor: the input buffers of the C-ABI call
-
-    def e2e_step():
-        m = api.Model(csp, desc_keep)   # dq_compile: FinalizeModel + Reset on the host, tables uploaded by the solve
-        r = solve_step(m)
-        m.close()
-        return r
-    e_tot, _, _ = timed_steps(e2e_step, args.steps, args.warmup)
-    table_bytes = model.table_bytes()
-    engine_used = model.solve_tree("count", part_rank=rank, part_count=world, engine=args.engine).engine
+    n = 17
+    Q = measure_queens(n, args.steps, args.warmup)
+    want_nodes, tot, kern_ms, launches, e_tot = Q["nodes"], Q["tot"], Q["kern_ms"], Q["launches"], Q["e_tot"]
+    dom_ms, dom_frontier, dom_records, table_bytes, engine_used = Q["dom_ms"], Q["dom_frontier"], Q["dom_records"], Q["table_bytes"], Q["engine"]
+    Q14 = measure_queens(14, max(args.steps, 10), args.warmup) if world == 1 and not args.no_extra else None
 
     sudoku = None
     if not args.no_sudoku:
@@ -294,13 +297,15 @@ def main():
         line["cpu_baseline"] = cpu_baseline_queens(world)
     extra = {}
     if world == 1 and not args.no_extra:
-        m17 = api.Model(nqueens(17))
-        r = m17.solve_tree("count", engine=args.engine)
-        r = m17.solve_tree("count", engine=args.engine)
-        assert (r.solutions, r.nodes) == QUEENS[17]
-        extra["nqueens17_1gpu"] = {"nodes_per_sec_kernel": r.nodes / (r.kernel_ms * 1e-3), "kernel_ms": r.kernel_ms,
-                                   "solutions": r.solutions, "nodes": r.nodes, "engine": r.engine,
-                                   "roofline_frac": r.nodes / (r.kernel_ms * 1e-3) * (5 * QUEENS_A[17] + 4) / int_peak}
+        # BASELINE config C2: 14-Queens all-solutions on one B200 (365 596 solutions / 19 787 662 nodes)
+        q = Q14
+        extra["nqueens14_1gpu"] = {
+            "config": workload_config(1, 14), "value": q["nodes"] * q["steps"] / q["tot"], "unit": "nodes/s",
+            "ms_per_step": 1e3 * q["tot"] / q["steps"], "kernel_ms_per_step": q["kern_ms"] / q["steps"], "steps": q["steps"],
+            "e2e": {"value": q["nodes"] * q["steps"] / q["e_tot"], "unit": "nodes/s", "ms_per_step": 1e3 * q["e_tot"] / q["steps"],
+                    "h2d_bytes_per_step": q["table_bytes"] + 64, "d2h_bytes_per_step": 64 + 4 * 14 + 8 * 64},
+            "gpu_launches": q["launches"], "engine": q["engine"],
+            "roofline": roofline_queens(14, 1, q["nodes"], q["dom_frontier"], q["dom_records"], q["dom_ms"] / q["steps"], int_peak, hbm_peak, peak_src)}
         # BASELINE config C4: G(200, c/199) 3-colouring near the phase transition, batched, node budget per instance
         from dequan_b200 import generators as G
         off, edges = G.colouring_batch(1024, 200, 4.2)
