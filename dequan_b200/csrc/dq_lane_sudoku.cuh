@@ -109,6 +109,7 @@ struct SudokuArgs {
     unsigned long long* ctrl;              // control block, see SkCtrl
     unsigned long long user_budget;        // per-instance node budget of the API (0 = none)
     unsigned first_budget;                 // nodes k_sudoku_first spends on an instance before calling it hard
+    int donate_depth;                      // ... and only levels at least this far above the current one
     unsigned donate_min, donate_gap;       // k_sudoku_count: a task gives a level away only when it is this old / this long after the last time
     unsigned strong_hidden_after;          // k_sudoku_strong: value tries after which hidden-single propagation joins in
     int pop_quorum;                        // extra step-back rounds run while at least this many lanes still stand on an exhausted level
@@ -971,7 +972,7 @@ k_sudoku_count(SudokuArgs A) {
                 if (want) {
                     int l = L.base_sp;
                     while (l < L.sp && (S.stk[l][t] & 0x1FF) == 0) ++l;
-                    if (l < L.sp) hl = l;
+                    if (l + A.donate_depth <= L.sp) hl = l;                               // a level close to the current one roots a tiny subtree
                     else if (L.nodes >= split_at) split_at = L.nodes + kSplitGap / 4;     // nothing to give right now: look again soon
                 }
                 const uint32_t elig = __ballot_sync(0xFFFFFFFFu, hl >= 0);
