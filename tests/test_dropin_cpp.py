@@ -20,7 +20,7 @@ GOLD = os.path.join(ROOT, "tests", "golden")
 def scen_bin(product_lib, tmp_path_factory):
     out = str(tmp_path_factory.mktemp("dropin") / "dropin_scen")
     libdir = os.path.join(ROOT, "dequan_b200", "lib")
-    subprocess.check_call(["g++", "-std=c++14", "-O2", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), "-o", out,
+    subprocess.check_call(["g++", "-std=c++11", "-O2", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), "-o", out,
                            os.path.join(ROOT, "tests", "cpp", "dropin_scenarios.cpp"), "-L" + libdir, "-ldequan_b200",
                            "-Wl,-rpath," + libdir])
     return out
