@@ -19,7 +19,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libdequan_b200.so")
 U64_MAX = 2**64 - 1
 
 DQ_MODE_FIRST, DQ_MODE_COUNT_ALL = 0, 1
-ENGINE = {"auto": 0, "warp": 1, "lane": 2}
+ENGINE = {"auto": 0, "warp": 1, "lane": 2, "reg": 3}
 ENGINE_NAME = {v: k for k, v in ENGINE.items()}
 OUTCOME = {0: "unsat", 1: "sat", 2: "budget", 3: "invalid"}
 MODEL_CLASS = {0: "generic", 1: "ne_same", 2: "queens", 3: "sudoku9"}

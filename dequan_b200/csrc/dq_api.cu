@@ -13,6 +13,7 @@
 #include "dq_lane_queens.cuh"
 #include "dq_lane_sudoku.cuh"
 #include "dq_reg_graphs.cuh"
+#include "dq_small_tree.cuh"
 #include "dq_model.hpp"
 
 namespace dq {
@@ -139,6 +140,7 @@ struct dq_model {
     uint16_t* t_ent = nullptr;
     uint8_t *t_order = nullptr, *t_pos = nullptr, *t_cell_lut = nullptr;
     int32_t *t_values = nullptr, *t_sizes = nullptr;
+    uint32_t *t_s_and = nullptr, *t_s_weq = nullptr, *t_s_weq_on = nullptr, *t_s_chk = nullptr, *t_s_dom0 = nullptr;
     int n_sizes = 0;
     // tree-solve scratch, retained until the next solve for dq_tree_nodes_upto()
     std::vector<LevelArrays> levels;
@@ -201,12 +203,18 @@ static int upload(dq_model* m) {
     const size_t o_ent_off = put(c.ent_off), o_ent = put(c.ent), o_ent_moff = put(c.ent_moff), o_masks = put(c.masks),
                  o_dom0 = put(c.dom0), o_order = put(order), o_pos = put(pos), o_values = put(values), o_lut = put(lut),
                  o_sizes = put(sizes);
+    std::vector<uint32_t> dom0_pos(32, 0xFFFFFFFFu);
+    for (int p = 0; p < nv && p < 32; p++) dom0_pos[p] = c.dom0[c.order[p]];
+    const size_t o_s_and = put(c.small_and), o_s_weq = put(c.small_weq), o_s_weq_on = put(c.small_weq_on), o_s_chk = put(c.small_chk),
+                 o_s_dom0 = put(dom0_pos);
     DQ_CUDA(m->d_blob.reserve(blob.size()));
     DQ_CUDA(cudaMemcpyAsync(m->d_blob.p, blob.data(), blob.size(), cudaMemcpyHostToDevice, m->stream));
     uint8_t* base = m->d_blob.p;
     m->t_ent_off = (uint32_t*)(base + o_ent_off); m->t_ent = (uint16_t*)(base + o_ent); m->t_ent_moff = (uint32_t*)(base + o_ent_moff);
     m->t_masks = (uint32_t*)(base + o_masks); m->t_dom0 = (uint32_t*)(base + o_dom0); m->t_order = base + o_order; m->t_pos = base + o_pos;
     m->t_values = (int32_t*)(base + o_values); m->t_cell_lut = base + o_lut; m->t_sizes = (int32_t*)(base + o_sizes);
+    m->t_s_and = (uint32_t*)(base + o_s_and); m->t_s_weq = (uint32_t*)(base + o_s_weq); m->t_s_weq_on = (uint32_t*)(base + o_s_weq_on);
+    m->t_s_chk = (uint32_t*)(base + o_s_chk); m->t_s_dom0 = (uint32_t*)(base + o_s_dom0);
     DQ_CUDA(m->d_ctrl.reserve(32));
     m->uploaded = true;
     return DQ_OK;
@@ -518,7 +526,28 @@ int dq_solve_tree(dq_model* m, const dq_tree_opts* opts, dq_tree_result* res, in
         A.part_rank = opts->part_rank; A.part_count = opts->part_count; A.count_all = count_all ? 1 : 0;
         A.cursor = ctrl + 0; A.totals = ctrl + 1; A.best_key = ctrl + 3;
         A.sub_nodes = m->d_sub_nodes.p; A.sol_key = m->d_sol_key.p; A.sol = m->d_sol.p;
-        DQ_DISPATCH(m, k_tree_dfs, (int)ctas, kWarpsPerCta * 32, smem, m->stream, M, A);
+        // small models run the subtree DFS with their domains in registers (dq_small_tree.cuh)
+        if (opts->engine == DQ_ENGINE_REG && !m->cm.small_ok) { g_err = "the register engine serves models of at most 32 variables with simple pair filters"; return DQ_ERR_UNSUPPORTED; }
+        const bool small = m->cm.small_ok && opts->engine != DQ_ENGINE_WARP;
+        if (small) {
+            SmallTablesDev ST;
+            ST.nv = nv; ST.kmax = m->cm.kmax; ST.t_and = m->t_s_and; ST.t_weq = m->t_s_weq; ST.t_weq_on = m->t_s_weq_on;
+            ST.t_chk = m->t_s_chk; ST.dom0_pos = m->t_s_dom0; ST.order = m->t_order;
+            const size_t ssm = small_tree_smem(nv, m->cm.kmax, m->cm.has_f, kWarpsPerCta);
+            int socc = 0;
+            rc = m->cm.has_f ? max_ctas_per_sm(k_tree_small<true>, kWarpsPerCta * 32, ssm, &socc)
+                             : max_ctas_per_sm(k_tree_small<false>, kWarpsPerCta * 32, ssm, &socc);
+            if (rc != DQ_OK) return rc;
+            if (socc < 1) { g_err = "kernel does not fit an SM"; return DQ_ERR_UNSUPPORTED; }
+            const long long sctas = std::max<long long>(1, std::min<long long>((long long)((mine + kWarpsPerCta - 1) / kWarpsPerCta), (long long)socc * m->sm_count));
+            // sol / sol_key are indexed by global warp id: the buffers above were sized for `ctas` of the generic kernel
+            if (sctas > ctas) { DQ_CUDA(m->d_sol_key.reserve(sctas * kWarpsPerCta)); DQ_CUDA(m->d_sol.reserve((size_t)sctas * kWarpsPerCta * nv));
+                                DQ_CUDA(cudaMemsetAsync(m->d_sol_key.p, 0xFF, sctas * kWarpsPerCta * sizeof(unsigned long long), m->stream));
+                                A.sol_key = m->d_sol_key.p; A.sol = m->d_sol.p; n_warps = sctas * kWarpsPerCta; }
+            if (m->cm.has_f) k_tree_small<true><<<(int)sctas, kWarpsPerCta * 32, ssm, m->stream>>>(ST, A);
+            else k_tree_small<false><<<(int)sctas, kWarpsPerCta * 32, ssm, m->stream>>>(ST, A);
+            res->engine_used = DQ_ENGINE_REG;
+        } else DQ_DISPATCH(m, k_tree_dfs, (int)ctas, kWarpsPerCta * 32, smem, m->stream, M, A);
         launches++;
         DQ_CUDA(cudaGetLastError());
     }

@@ -179,6 +179,12 @@ int compile_model(const dq_model_desc* d, CompiledModel& M, std::string& err) {
     // ---- per ordered pair (x -> q): the sequence of filters in x's link order ----
     M.ent_off.assign(nv + 1, 0);
     int forced_total = 0;
+    // small-model tables (filled while the pairs are normalised below; dropped if some pair does not fit the pattern)
+    bool small_try = nv >= 1 && nv <= 32 && (size_t)nv * M.kmax * 32 * 4 * 3 + 40 * 1024 <= 200 * 1024;   // three tables + four warps of frames fit one CTA
+    if (small_try) {
+        M.small_and.assign((size_t)nv * M.kmax * 32, 0xFFFFFFFFu);
+        M.small_weq_on.assign((size_t)nv * M.kmax, 0u);       // the WEQ / CHK tables are created when the first such op shows up
+    }
     std::vector<int> qorder_buf;
     std::vector<std::vector<PairOp>> ops_buf(nv);
     std::vector<size_t> op_count(nv, 0);
@@ -286,6 +292,25 @@ int compile_model(const dq_model_desc* d, CompiledModel& M, std::string& err) {
             }
             if (norm.size() > 1) multi_pairs++;
             n_pass = std::max(n_pass, norm.size());
+            if (small_try) {
+                size_t i = 0;
+                const PairOp *pa = nullptr, *pw = nullptr, *pc = nullptr;
+                if (i < norm.size() && (norm[i].kind == K_AND || norm[i].kind == K_NE_SAME)) pa = &norm[i++];
+                if (i < norm.size() && norm[i].kind == K_WEQ) pw = &norm[i++];
+                if (i < norm.size() && norm[i].kind == K_CHK) pc = &norm[i++];
+                if (i != norm.size()) small_try = false;
+                else {
+                    const int px = M.pos_of[x], pq = M.pos_of[q];
+                    if (pw && M.small_weq.empty()) M.small_weq.assign((size_t)nv * M.kmax * 32, 0u);
+                    if (pc && M.small_chk.empty()) M.small_chk.assign((size_t)nv * M.kmax * 32, 0u);
+                    for (int b = 0; b < kx; b++) {
+                        const size_t at = ((size_t)px * M.kmax + b) * 32 + pq;
+                        if (pa) M.small_and[at] = pa->m[b];
+                        if (pw) { M.small_weq[at] = pw->m[b]; M.small_weq_on[(size_t)px * M.kmax + b] |= 1u << pq; }
+                        if (pc) M.small_chk[at] = pc->m[b];
+                    }
+                }
+            }
             for (size_t p = 0; p < norm.size(); p++) {
                 if (passes.size() <= p) { passes.resize(p + 1); pass_q.resize(p + 1); }
                 passes[p].push_back(std::move(norm[p]));
@@ -315,6 +340,12 @@ int compile_model(const dq_model_desc* d, CompiledModel& M, std::string& err) {
         M.ent_off[x + 1] = (uint32_t)M.ent.size();
     }
     if (M.masks.empty()) M.masks.push_back(0);
+    M.small_ok = small_try;
+    if (!small_try) { M.small_and.clear(); M.small_weq.clear(); M.small_chk.clear(); M.small_weq_on.clear(); }
+    else if (M.has_f) {                                   // the device kernel indexes both tables when the model has an F word
+        if (M.small_weq.empty()) M.small_weq.assign((size_t)nv * M.kmax * 32, 0u);
+        if (M.small_chk.empty()) M.small_chk.assign((size_t)nv * M.kmax * 32, 0u);
+    }
 
     int ksum = 0;
     for (int v = 0; v < nv; v++) ksum += (int)M.values[v].size();

@@ -61,6 +61,13 @@ struct CompiledModel {
     int model_class = CLASS_GENERIC;
     int queens_n = 0;
     std::vector<int32_t> distinct_sizes;       // sorted distinct initial domain sizes (batch re-ordering)
+    // Small-model tables for the register-resident tree engine (nv <= 32, every pair at most AND -> WEQ -> CHK):
+    // position space, [pos(x)][value index][pos(q)]: what x = value does to q.  Empty when the model does not qualify.
+    bool small_ok = false;
+    std::vector<uint32_t> small_and;           // AND mask (all ones: q untouched)
+    std::vector<uint32_t> small_weq;           // weak-equal mask, valid where the bit of pos(q) is set in small_weq_on[pos(x)][value]
+    std::vector<uint32_t> small_weq_on;        // [pos(x)][value index]
+    std::vector<uint32_t> small_chk;           // values of q that will fail validation
 };
 
 // Returns DQ_OK or a negative dq_status; on failure `err` says why.

@@ -102,8 +102,10 @@ enum dq_mode {
 enum dq_engine {
     DQ_ENGINE_AUTO  = 0,     /* fastest engine the compiled model qualifies for     */
     DQ_ENGINE_WARP  = 1,     /* generic warp-cooperative DFS (any supported model)  */
-    DQ_ENGINE_LANE  = 2      /* lane-per-subtree / lane-per-instance closed-form DFS
+    DQ_ENGINE_LANE  = 2,     /* lane-per-subtree / lane-per-instance closed-form DFS
                                 (N-Queens class trees, 9x9 Sudoku class batches)    */
+    DQ_ENGINE_REG   = 3      /* register-resident warp DFS: trees of models with at
+                                most 32 variables, colouring batches with k <= 4     */
 };
 
 typedef struct dq_tree_opts {

@@ -410,3 +410,45 @@ def test_colouring_register_engine_equals_warp_engine(product_lib, nv, k, c, bud
     assert a.launches == 1 and b.launches == 2
     with pytest.raises(api.DequanError):        # a self-loop has no lowering (the reference would fail every value of that vertex)
         api.solve_batch_graphs(3, 3, np.array([0, 1], dtype=np.int64), np.array([[1, 1]], dtype=np.uint8))
+
+
+def test_register_tree_engine_equals_generic_engine(product_lib):
+    """dq_small_tree.cuh (domains in registers, models of at most 32 variables) against the generic warp engine and the
+    oracle: random models with every constraint kind, both modes, several split depths and partitions."""
+    used = 0
+    for seed in range(9000, 9120):
+        csp = random_model(seed, n_vars=5 + seed % 9, n_cons=6 + seed % 13, max_dom=3 + seed % 5)
+        m = api.Model(csp)
+        for mode in ("first", "count"):
+            want = O.solve(csp, mode)
+            a = m.solve_tree(mode, engine="warp")
+            _cmp_tree(a, want, (seed, mode, "warp"))
+            b = m.solve_tree(mode)
+            _cmp_tree(b, want, (seed, mode, "auto"))
+            used += b.engine == "reg"
+            if b.engine == "reg":
+                for depth in (1, 3):
+                    _cmp_tree(m.solve_tree(mode, split_depth=depth, engine="reg"), want, (seed, mode, depth))
+    assert used > 15            # most of these tiny models are decided during frontier expansion and never reach a DFS kernel
+    used = 0
+    for seed in range(9200, 9260):             # not-equal models: many solutions, the DFS kernel always runs
+        csp = random_model(seed, n_vars=7 + seed % 4, n_cons=10 + seed % 9, max_dom=4 + seed % 2, kinds="ne")
+        m = api.Model(csp)
+        for mode in ("first", "count"):
+            want = O.solve(csp, mode)
+            b = m.solve_tree(mode)
+            _cmp_tree(b, want, (seed, mode, "auto"))
+            _cmp_tree(m.solve_tree(mode, engine="warp"), want, (seed, mode, "warp"))
+            used += b.engine == "reg"
+    assert used > 80
+    m = api.Model(nqueens(11))
+    g = O.solve(nqueens(11), "count")
+    parts = [m.solve_tree("count", split_depth=3, part_rank=r, part_count=3, engine="reg") for r in range(3)]
+    assert (sum(p.solutions for p in parts), sum(p.nodes for p in parts)) == (g.solutions, g.nodes)
+    f = m.solve_tree("first")
+    assert f.engine == "reg" and (f.nodes, f.first) == (O.solve(nqueens(11), "first").nodes, O.solve(nqueens(11), "first").first)
+    big = CSP()
+    for _ in range(40):
+        big.AddIntVar(0, 3)
+    with pytest.raises(api.DequanError):
+        api.Model(big).solve_tree("first", engine="reg")
