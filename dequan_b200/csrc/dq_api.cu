@@ -432,6 +432,13 @@ int dq_model_table_bytes(const dq_model* m, uint64_t* bytes) {
     return DQ_OK;
 }
 
+// node budget of the root probe of dq_solve_tree (DQ_PROBE_NODES overrides it, 0 switches the probe off)
+constexpr unsigned long long kProbeNodes = 512;
+static unsigned long long env_ull(const char* name, unsigned long long dflt) {
+    const char* e = getenv(name);
+    return e ? strtoull(e, nullptr, 10) : dflt;
+}
+
 int dq_solve_tree(dq_model* m, const dq_tree_opts* opts, dq_tree_result* res, int32_t* first_solution) {
     if (!m || !opts || !res) { g_err = "null argument"; return DQ_ERR_INVALID; }
     if (opts->part_count < 1 || opts->part_rank < 0 || opts->part_rank >= opts->part_count) { g_err = "bad partition"; return DQ_ERR_INVALID; }
@@ -472,13 +479,77 @@ int dq_solve_tree(dq_model* m, const dq_tree_opts* opts, dq_tree_result* res, in
     DQ_CUDA(cudaMemcpyAsync(ctrl, h_ctrl, sizeof h_ctrl, cudaMemcpyHostToDevice, m->stream));
     DQ_CUDA(cudaEventRecord(m->ev0, m->stream));
 
-    // ---- frontier expansion, level by level, children kept in DFS order ----
     if ((int)m->levels.size() < nv + 1) m->levels.resize(nv + 1);   // sized up front: references below stay valid
     m->levels[0].n = 1;
     DQ_CUDA(m->levels[0].prefixes.reserve(1));
     int depth = 0;
     unsigned long long shallow_nodes = 0, launches = 0;
     bool empty = false;
+    long long n_warps = 0;
+
+    // One launch of the subtree DFS over the prefixes of level `depth`: the register engine for small models
+    // (dq_small_tree.cuh), the generic warp engine otherwise.  Sizes and clears the per-run buffers.
+    if (opts->engine == DQ_ENGINE_REG && !m->cm.small_ok) { g_err = "the register engine serves models of at most 32 variables with simple pair filters"; return DQ_ERR_UNSUPPORTED; }
+    const bool small = m->cm.small_ok && opts->engine != DQ_ENGINE_WARP;
+    const size_t ssm = small ? small_tree_smem(nv, m->cm.kmax, m->cm.has_f, kWarpsPerCta) : 0;
+    int socc = 0;
+    if (small) {
+        rc = m->cm.has_f ? max_ctas_per_sm(k_tree_small<true>, kWarpsPerCta * 32, ssm, &socc)
+                         : max_ctas_per_sm(k_tree_small<false>, kWarpsPerCta * 32, ssm, &socc);
+        if (rc != DQ_OK) return rc;
+        if (socc < 1) { g_err = "kernel does not fit an SM"; return DQ_ERR_UNSUPPORTED; }
+    }
+    auto launch_dfs = [&](int at_depth, unsigned long long n_prefix, int part_rank, int part_count, unsigned long long node_budget) -> int {
+        const unsigned long long mine = (n_prefix + part_count - 1 - part_rank) / part_count;
+        const long long per_sm = small ? socc : occ;
+        const long long ctas = std::max<long long>(1, std::min<long long>((long long)((mine + kWarpsPerCta - 1) / kWarpsPerCta), per_sm * m->sm_count));
+        n_warps = ctas * kWarpsPerCta;
+        DQ_CUDA(m->d_sub_nodes.reserve(n_prefix));
+        DQ_CUDA(m->d_sol_key.reserve(n_warps));
+        DQ_CUDA(m->d_sol.reserve((size_t)n_warps * nv));
+        DQ_CUDA(cudaMemsetAsync(m->d_sub_nodes.p, 0, n_prefix * sizeof(unsigned long long), m->stream));
+        DQ_CUDA(cudaMemsetAsync(m->d_sol_key.p, 0xFF, n_warps * sizeof(unsigned long long), m->stream));
+        TreeDfsArgs A;
+        A.prefixes = m->levels[at_depth].prefixes.p; A.depth = at_depth; A.n_prefix = n_prefix;
+        A.part_rank = part_rank; A.part_count = part_count; A.count_all = count_all ? 1 : 0;
+        A.cursor = ctrl + 0; A.totals = ctrl + 1; A.best_key = ctrl + 3;
+        A.sub_nodes = m->d_sub_nodes.p; A.sol_key = m->d_sol_key.p; A.sol = m->d_sol.p;
+        A.node_budget = node_budget; A.gave_up = ctrl + 6;
+        if (small) {
+            SmallTablesDev ST;
+            ST.nv = nv; ST.kmax = m->cm.kmax; ST.t_and = m->t_s_and; ST.t_weq = m->t_s_weq; ST.t_weq_on = m->t_s_weq_on;
+            ST.t_chk = m->t_s_chk; ST.dom0_pos = m->t_s_dom0; ST.order = m->t_order;
+            if (m->cm.has_f) k_tree_small<true><<<(int)ctas, kWarpsPerCta * 32, ssm, m->stream>>>(ST, A);
+            else k_tree_small<false><<<(int)ctas, kWarpsPerCta * 32, ssm, m->stream>>>(ST, A);
+            res->engine_used = DQ_ENGINE_REG;
+        } else DQ_DISPATCH(m, k_tree_dfs, (int)ctas, kWarpsPerCta * 32, smem, m->stream, M, A);
+        launches++;
+        DQ_CUDA(cudaGetLastError());
+        return DQ_OK;
+    };
+
+    // ---- root probe: ONE warp walks the whole tree under a small node budget ----
+    // Most ForwardCheckingStep calls of a modelling session are small (the reference's own scenarios take 88-193
+    // nodes): one launch and one synchronisation answer them, instead of a synchronisation per frontier level.
+    // Past the budget the probe's counts are dropped and the split search below starts over.
+    static const unsigned long long probe_nodes = env_ull("DQ_PROBE_NODES", kProbeNodes);
+    bool probed = false;
+    if (probe_nodes && want_depth < 0 && opts->part_count == 1) {
+        rc = launch_dfs(0, 1, 0, 1, probe_nodes);
+        if (rc != DQ_OK) return rc;
+        DQ_CUDA(cudaEventRecord(m->ev1, m->stream));
+        DQ_CUDA(cudaMemcpyAsync(h_ctrl, ctrl, sizeof h_ctrl, cudaMemcpyDeviceToHost, m->stream));
+        DQ_CUDA(cudaStreamSynchronize(m->stream));
+        if (h_ctrl[6] == 0) probed = true;
+        else {
+            const unsigned long long z[8] = {0, 0, 0, KEY_NONE, 0, 0, 0, 0};
+            memcpy(h_ctrl, z, sizeof z);
+            DQ_CUDA(cudaMemcpyAsync(ctrl, h_ctrl, sizeof h_ctrl, cudaMemcpyHostToDevice, m->stream));
+        }
+    }
+
+    // ---- frontier expansion, level by level, children kept in DFS order ----
+  if (!probed) {
     while (depth < max_depth && (want_depth >= 0 ? depth < want_depth : m->levels[depth].n < want_prefixes)) {
         LevelArrays& L = m->levels[depth];
         const int n = L.n;
@@ -503,6 +574,7 @@ int dq_solve_tree(dq_model* m, const dq_tree_opts* opts, dq_tree_result* res, in
     }
     DQ_CUDA(cudaGetLastError());
 
+  }
     const unsigned long long n_prefix = empty ? 0 : (unsigned long long)m->levels[depth].n;
     m->last_depth = depth; m->last_n_prefix = n_prefix;
     m->last_part_rank = opts->part_rank; m->last_part_count = opts->part_count;
@@ -510,50 +582,15 @@ int dq_solve_tree(dq_model* m, const dq_tree_opts* opts, dq_tree_result* res, in
     res->split_depth_used = depth;
 
     // ---- subtree DFS ----
-    long long n_warps = 0;
-    if (n_prefix) {
-        const unsigned long long mine = (n_prefix + opts->part_count - 1 - opts->part_rank) / opts->part_count;
-        long long ctas = std::min<long long>((long long)((mine + kWarpsPerCta - 1) / kWarpsPerCta), (long long)occ * m->sm_count);
-        if (ctas < 1) ctas = 1;
-        n_warps = ctas * kWarpsPerCta;
-        DQ_CUDA(m->d_sub_nodes.reserve(n_prefix));
-        DQ_CUDA(m->d_sol_key.reserve(n_warps));
-        DQ_CUDA(m->d_sol.reserve((size_t)n_warps * nv));
-        DQ_CUDA(cudaMemsetAsync(m->d_sub_nodes.p, 0, n_prefix * sizeof(unsigned long long), m->stream));
-        DQ_CUDA(cudaMemsetAsync(m->d_sol_key.p, 0xFF, n_warps * sizeof(unsigned long long), m->stream));
-        TreeDfsArgs A;
-        A.prefixes = m->levels[depth].prefixes.p; A.depth = depth; A.n_prefix = n_prefix;
-        A.part_rank = opts->part_rank; A.part_count = opts->part_count; A.count_all = count_all ? 1 : 0;
-        A.cursor = ctrl + 0; A.totals = ctrl + 1; A.best_key = ctrl + 3;
-        A.sub_nodes = m->d_sub_nodes.p; A.sol_key = m->d_sol_key.p; A.sol = m->d_sol.p;
-        // small models run the subtree DFS with their domains in registers (dq_small_tree.cuh)
-        if (opts->engine == DQ_ENGINE_REG && !m->cm.small_ok) { g_err = "the register engine serves models of at most 32 variables with simple pair filters"; return DQ_ERR_UNSUPPORTED; }
-        const bool small = m->cm.small_ok && opts->engine != DQ_ENGINE_WARP;
-        if (small) {
-            SmallTablesDev ST;
-            ST.nv = nv; ST.kmax = m->cm.kmax; ST.t_and = m->t_s_and; ST.t_weq = m->t_s_weq; ST.t_weq_on = m->t_s_weq_on;
-            ST.t_chk = m->t_s_chk; ST.dom0_pos = m->t_s_dom0; ST.order = m->t_order;
-            const size_t ssm = small_tree_smem(nv, m->cm.kmax, m->cm.has_f, kWarpsPerCta);
-            int socc = 0;
-            rc = m->cm.has_f ? max_ctas_per_sm(k_tree_small<true>, kWarpsPerCta * 32, ssm, &socc)
-                             : max_ctas_per_sm(k_tree_small<false>, kWarpsPerCta * 32, ssm, &socc);
-            if (rc != DQ_OK) return rc;
-            if (socc < 1) { g_err = "kernel does not fit an SM"; return DQ_ERR_UNSUPPORTED; }
-            const long long sctas = std::max<long long>(1, std::min<long long>((long long)((mine + kWarpsPerCta - 1) / kWarpsPerCta), (long long)socc * m->sm_count));
-            // sol / sol_key are indexed by global warp id: the buffers above were sized for `ctas` of the generic kernel
-            if (sctas > ctas) { DQ_CUDA(m->d_sol_key.reserve(sctas * kWarpsPerCta)); DQ_CUDA(m->d_sol.reserve((size_t)sctas * kWarpsPerCta * nv));
-                                DQ_CUDA(cudaMemsetAsync(m->d_sol_key.p, 0xFF, sctas * kWarpsPerCta * sizeof(unsigned long long), m->stream));
-                                A.sol_key = m->d_sol_key.p; A.sol = m->d_sol.p; n_warps = sctas * kWarpsPerCta; }
-            if (m->cm.has_f) k_tree_small<true><<<(int)sctas, kWarpsPerCta * 32, ssm, m->stream>>>(ST, A);
-            else k_tree_small<false><<<(int)sctas, kWarpsPerCta * 32, ssm, m->stream>>>(ST, A);
-            res->engine_used = DQ_ENGINE_REG;
-        } else DQ_DISPATCH(m, k_tree_dfs, (int)ctas, kWarpsPerCta * 32, smem, m->stream, M, A);
-        launches++;
-        DQ_CUDA(cudaGetLastError());
+    if (n_prefix && !probed) {
+        rc = launch_dfs(depth, n_prefix, opts->part_rank, opts->part_count, 0ull);
+        if (rc != DQ_OK) return rc;
     }
-    DQ_CUDA(cudaEventRecord(m->ev1, m->stream));
-    DQ_CUDA(cudaMemcpyAsync(h_ctrl, ctrl, sizeof h_ctrl, cudaMemcpyDeviceToHost, m->stream));
-    DQ_CUDA(cudaStreamSynchronize(m->stream));
+    if (!probed) {
+        DQ_CUDA(cudaEventRecord(m->ev1, m->stream));
+        DQ_CUDA(cudaMemcpyAsync(h_ctrl, ctrl, sizeof h_ctrl, cudaMemcpyDeviceToHost, m->stream));
+        DQ_CUDA(cudaStreamSynchronize(m->stream));
+    }
     float ms = 0;
     DQ_CUDA(cudaEventElapsedTime(&ms, m->ev0, m->ev1));
     res->kernel_ms = ms;

@@ -138,6 +138,8 @@ struct TreeDfsArgs {
     unsigned long long* sub_nodes;      // [n_prefix] nodes per subtree (this partition's)
     unsigned long long* sol_key;        // [n_warps] key of the solution each warp recorded
     uint8_t* sol;                       // [n_warps][nv] value index per var id
+    unsigned long long node_budget;     // root probe only: give up past this many nodes (0 = none) ...
+    unsigned long long* gave_up;        // ... and say so here
 };
 
 struct RecordFirst {
@@ -173,9 +175,10 @@ k_tree_dfs(TreeModelDev M, TreeDfsArgs A) {
         if (!A.count_all && *(volatile unsigned long long*)A.best_key < idx) break;   // later prefixes cannot win
         replay_prefix<HAS_F, HAS_TABLE>(M, S, A.prefixes + idx * (size_t)A.depth, A.depth, lane);
         RecordFirst rec{A, idx, gw, nv, lane};
-        DfsResult R = warp_dfs<HAS_F, HAS_TABLE>(M.T, S, A.depth, A.count_all != 0, 0ull,
+        DfsResult R = warp_dfs<HAS_F, HAS_TABLE>(M.T, S, A.depth, A.count_all != 0, A.node_budget,
                                                  A.count_all ? nullptr : A.best_key, idx, lane, rec);
         if (R.outcome == 3) continue;                                                 // overtaken by an earlier prefix
+        if (R.outcome == 2) { if (lane == 0) *A.gave_up = 1ull; break; }              // root probe over budget: the host runs the split search
         if (lane == 0) A.sub_nodes[idx] = R.nodes;
         if (A.count_all) { acc_nodes += R.nodes; acc_sols += R.sols; }
         else if (R.have_first) rec(S);

@@ -128,6 +128,7 @@ k_tree_small(SmallTablesDev T, TreeDfsArgs A) {
                     continue;
                 }
                 if (!A.count_all && ((++poll & 63u) == 0) && *(volatile const unsigned long long*)A.best_key < idx) { outcome = 3; break; }
+                if (A.node_budget && nodes > A.node_budget) { outcome = 2; break; }   // root probe: the host runs the split search instead
                 const uint32_t Fx = HAS_F ? __shfl_sync(FULL, F, d) : 0u;
                 if (d == nv - 1) {
                     // last variable: each remaining value is a node; valid ones are solutions, nothing left to filter
@@ -170,9 +171,10 @@ k_tree_small(SmallTablesDev T, TreeDfsArgs A) {
                 __syncwarp();
                 c = __shfl_sync(FULL, D, d);
             }
-            if (A.count_all) outcome = sols ? 1 : 0;
+            if (A.count_all && outcome != 2) outcome = sols ? 1 : 0;
         }
         if (outcome == 3) continue;                                                    // overtaken by an earlier prefix
+        if (outcome == 2) { if (lane == 0) *A.gave_up = 1ull; break; }
         if (lane == 0) A.sub_nodes[idx] = nodes;
         if (A.count_all) { acc_nodes += nodes; acc_sols += sols; }
         else if (have_first) record_first();

@@ -168,6 +168,7 @@ __device__ DfsResult warp_dfs(const DevTables& T, const WarpState& S, int d0, bo
             const uint32_t valid = HAS_F ? (c & ~S.F[x]) : c;
             if (count_all) {
                 R.nodes += __popc(c);
+                if (budget && R.nodes > budget) { R.outcome = 2; break; }
                 R.sols += __popc(valid);
                 if (valid && !R.have_first) {
                     // first solution of this tree: val[] is the assignment right now (count_all keeps searching)
@@ -209,7 +210,7 @@ __device__ DfsResult warp_dfs(const DevTables& T, const WarpState& S, int d0, bo
         x = S.order[d];
         c = S.D[x];
     }
-    if (count_all) R.outcome = R.sols ? 1 : 0;
+    if (count_all && R.outcome != 2) R.outcome = R.sols ? 1 : 0;
     return R;
 }
 

@@ -1,5 +1,5 @@
 """Register small-tree engine (dq_small_tree.cuh) against the generic warp engine on models of at most 32 variables."""
-import json, sys, os
+import json, sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 from dequan_b200 import api
@@ -35,3 +35,14 @@ for name, csp, mode in cases:
         row[eng] = {"ms": round(best.kernel_ms, 3), "nodes": best.nodes, "Mnodes_s": round(best.nodes / best.kernel_ms / 1e3, 1), "sol": best.solutions}
     assert row["warp"]["nodes"] == row["reg"]["nodes"] and row["warp"]["sol"] == row["reg"]["sol"]
     print(json.dumps(row))
+
+# wall-clock latency of one call, the way the drop-in header makes it (engine left to the library)
+for name, csp, mode in [("queens8_first", nqueens(8), "first"), ("queens8_count_generic", nqueens(8), "count"), ("queens12_first", nqueens(12), "first"),
+                        ("colour24_k4_c5_first", colouring(24, 4, 5.0, 3), "first"), ("colour30_k3_c3.0_count", colouring(30, 3, 3.0, 1), "count")]:
+    m = api.Model(csp)
+    eng = "warp" if "generic" in name else "auto"
+    best = 1e9
+    for _ in range(20):
+        t0 = time.perf_counter(); r = m.solve_tree(mode, engine=eng); dt = time.perf_counter() - t0
+        best = min(best, dt)
+    print(json.dumps({"case": name, "wall_us": round(best * 1e6, 1), "kernel_ms": round(r.kernel_ms, 3), "nodes": r.nodes, "engine": r.engine, "launches": r.launches}))
