@@ -2,13 +2,15 @@
 
 One process per GPU (torch.distributed, NCCL over NVLink on the GPU box, gloo in the CPU tests).
 Prefix i of the DFS-ordered frontier belongs to rank i % world; the search itself needs no
-exchange.  The only collectives are the ones the north star names:
-  * all_reduce(SUM)  of {solutions, nodes}
-  * all_reduce(MIN)  of the DFS index of the prefix holding each rank's first solution
-  * all_reduce(MAX)  of the owner's solution vector (everyone else contributes INT64_MIN),
-    which is a broadcast from the owner without a second round to discover who the owner is.
-In FIRST mode the node count is re-asked per rank for the GLOBAL minimum key
-(`nodes_upto`), so the sum equals the reference's sequential stats.assigned_vars.
+exchange.  What the north star names — the solution-count / node-count sum and the
+lexicographic-min first-solution reduction — is one small record per rank:
+    {DFS key of the rank's first solution, solutions, nodes, solution vector}
+COUNT mode: ONE all_gather of the records and one device->host read; every rank then takes
+the sum of the counts and the solution of the lowest key (= a MIN reduction whose payload
+rides along, so no second round is needed to find and broadcast from the owner).
+FIRST mode: the node count of the reference's sequential search depends on the GLOBAL
+minimum key (`nodes_upto`), so the keys are MIN-reduced first and the records gathered
+second; the sum then equals the reference's stats.assigned_vars.
 """
 from __future__ import annotations
 
@@ -36,24 +38,32 @@ def _key_to_i64(k: int) -> int:
     return I64_MAX if k >= I64_MAX else int(k)
 
 
+def _gather_rows(rec: torch.Tensor, group) -> torch.Tensor:
+    world = dist.get_world_size(group)
+    out = [torch.empty_like(rec) for _ in range(world)]
+    dist.all_gather(out, rec, group=group)
+    return torch.stack(out).cpu()                      # the one device->host read
+
+
 def reduce_tree(local, nodes_upto: Callable[[int], int], mode: str, n_vars: int, device="cpu", group=None) -> GlobalTreeResult:
     """`local` needs .solutions .nodes .first .first_key; nodes_upto(key) -> this rank's share."""
-    key = torch.tensor([_key_to_i64(local.first_key if local.first is not None else U64_MAX)], dtype=torch.int64, device=device)
-    dist.all_reduce(key, op=dist.ReduceOp.MIN, group=group)
-    gkey = int(key.item())
-    have = gkey != I64_MAX
+    my_key = _key_to_i64(local.first_key if local.first is not None else U64_MAX)
     if mode == "count":
-        acc = torch.tensor([int(local.solutions), int(local.nodes)], dtype=torch.int64, device=device)
+        nodes = int(local.nodes)
     else:
-        acc = torch.tensor([0, int(nodes_upto(gkey if have else U64_MAX))], dtype=torch.int64, device=device)
-    dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=group)
-    sol = torch.full((max(n_vars, 1),), I64_MIN, dtype=torch.int64, device=device)
-    if have and local.first is not None and _key_to_i64(local.first_key) == gkey:
-        sol[:n_vars] = torch.tensor(local.first, dtype=torch.int64, device=device)
-    dist.all_reduce(sol, op=dist.ReduceOp.MAX, group=group)
-    solutions = int(acc[0].item()) if mode == "count" else (1 if have else 0)
-    return GlobalTreeResult("sat" if solutions else "unsat", solutions, int(acc[1].item()),
-                            sol[:n_vars].tolist() if have else None, gkey if have else U64_MAX)
+        key = torch.tensor([my_key], dtype=torch.int64, device=device)
+        dist.all_reduce(key, op=dist.ReduceOp.MIN, group=group)
+        gk = int(key.item())
+        nodes = int(nodes_upto(gk if gk != I64_MAX else U64_MAX))
+    rec = [my_key, int(local.solutions) if mode == "count" else 0, nodes]
+    rec += [int(v) for v in local.first] if local.first is not None else [I64_MIN] * n_vars
+    rows = _gather_rows(torch.tensor(rec, dtype=torch.int64, device=device), group)
+    owner = int(torch.argmin(rows[:, 0]).item())        # lowest DFS key; keys of different ranks never tie
+    gkey = int(rows[owner, 0].item())
+    have = gkey != I64_MAX
+    solutions = int(rows[:, 1].sum().item()) if mode == "count" else (1 if have else 0)
+    return GlobalTreeResult("sat" if solutions else "unsat", solutions, int(rows[:, 2].sum().item()),
+                            rows[owner, 3:3 + n_vars].tolist() if have else None, gkey if have else U64_MAX)
 
 
 def shard_range(n: int, rank: int, world: int):
