@@ -94,8 +94,9 @@ struct DevBuf {
 // Stream + timing events are per thread and device, shared by every handle.
 struct DeviceCtx {
     int dev = -1, sm_count = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, stream2 = nullptr;          // stream2: side work that overlaps the main queue
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;          // ordering only (no timing)
 };
 static thread_local std::vector<DeviceCtx> g_ctx;
 static cudaError_t device_ctx(DeviceCtx** out) {
@@ -111,6 +112,9 @@ static cudaError_t device_ctx(DeviceCtx** out) {
     if ((e = cudaEventCreate(&c.ev1)) != cudaSuccess) return e;
     if ((e = cudaEventCreate(&c.ev2)) != cudaSuccess) return e;
     if ((e = cudaEventCreate(&c.ev3)) != cudaSuccess) return e;
+    if ((e = cudaStreamCreateWithFlags(&c.stream2, cudaStreamNonBlocking)) != cudaSuccess) return e;
+    if ((e = cudaEventCreateWithFlags(&c.ev_fork, cudaEventDisableTiming)) != cudaSuccess) return e;
+    if ((e = cudaEventCreateWithFlags(&c.ev_join, cudaEventDisableTiming)) != cudaSuccess) return e;
     g_ctx.push_back(c);
     *out = &g_ctx.back();
     return cudaSuccess;
@@ -130,8 +134,8 @@ using namespace dq;
 struct dq_model {
     CompiledModel cm;
     bool uploaded = false;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    cudaStream_t stream = nullptr, stream2 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, ev_fork = nullptr, ev_join = nullptr;
     int sm_count = 0;
     // model tables in HBM
     DevBuf<uint8_t> d_blob;                     // all tables, one block
@@ -176,6 +180,7 @@ static int upload(dq_model* m) {
     DeviceCtx* ctx = nullptr;
     DQ_CUDA(device_ctx(&ctx));
     m->sm_count = ctx->sm_count; m->stream = ctx->stream; m->ev0 = ctx->ev0; m->ev1 = ctx->ev1; m->ev2 = ctx->ev2; m->ev3 = ctx->ev3;
+    m->stream2 = ctx->stream2; m->ev_fork = ctx->ev_fork; m->ev_join = ctx->ev_join;
     const CompiledModel& c = m->cm;
     const int nv = c.nv;
     // every table goes into ONE device block with ONE stream-ordered copy (the solve's kernels follow on the same stream)
@@ -276,9 +281,11 @@ static int solve_queens_lane(dq_model* m, const dq_tree_opts* opts, dq_tree_resu
     else K = std::max(std::min(N - 7, N <= 15 ? 6 : 7), 0);
     auto key_space = [&](int k) { double keys = 1; for (int i = 0; i < k; i++) keys *= N; return keys; };
     while (K > 0 && key_space(K) > 4.0e9) K--;               // prefix keys are 32-bit (res->split_depth_used reports K)
-    const size_t smem = dfs_smem(K);
+    // the search kernel: depth-bucketed warp pools (default) or the older lane-per-subtree stacks (DQ_QUEENS_ENGINE=lane)
+    static const bool use_buckets = !(getenv("DQ_QUEENS_ENGINE") && !strcmp(getenv("DQ_QUEENS_ENGINE"), "lane"));
+    const size_t smem = use_buckets ? (size_t)(kQueensBucketBlock / 32) * (N - 1 - K) * kQueensBucketCap * sizeof(uint4) : dfs_smem(K);
     if (smem > 200 * 1024) { g_err = "board too large for the shared-memory stack"; return DQ_ERR_UNSUPPORTED; }
-    rc = max_ctas_per_sm(k_queens_lane, kQueensBlock, smem, &occ);
+    rc = use_buckets ? max_ctas_per_sm(k_queens_bucket, kQueensBucketBlock, smem, &occ) : max_ctas_per_sm(k_queens_lane, kQueensBlock, smem, &occ);
     if (rc != DQ_OK) return rc;
     if (occ < 1) { g_err = "kernel does not fit an SM"; return DQ_ERR_UNSUPPORTED; }
     const int ctas = occ * m->sm_count;
@@ -312,6 +319,14 @@ static int solve_queens_lane(dq_model* m, const dq_tree_opts* opts, dq_tree_resu
         // hundred thousand records and partition 0 alone counts their nodes.
         const char* env_pl = getenv("DQ_QUEENS_PART_LEVEL");
         const int part_level = std::min(K - 1, env_pl ? atoi(env_pl) : 4);     // measured: depth-5 keys balance 2/4/8 partitions within 3 %
+        A.part_level = part_level;
+        if (use_buckets) {
+            // the DFS-first solution needs nothing from the frontier: one warp looks for it on the side stream
+            DQ_CUDA(cudaEventRecord(m->ev_fork, m->stream));
+            DQ_CUDA(cudaStreamWaitEvent(m->stream2, m->ev_fork, 0));
+            k_queens_first_warp<<<1, 32, 0, m->stream2>>>(A);
+            DQ_CUDA(cudaEventRecord(m->ev_join, m->stream2));
+        }
         for (int l = 0; l < K; l++) {
             const int grid = (int)std::min<double>(std::max(estimate(l) * N / kQueensBlock, 1.0), (double)m->sm_count * 8);
             const int count_nodes = (l > part_level || opts->part_rank == 0) ? 1 : 0;
@@ -319,10 +334,17 @@ static int solve_queens_lane(dq_model* m, const dq_tree_opts* opts, dq_tree_resu
                                                                    count_nodes, (l == part_level && opts->part_count > 1) ? 1 : 0);
         }
         DQ_CUDA(cudaEventRecord(m->ev2, m->stream));
-        k_queens_lane<<<ctas, kQueensBlock, smem, m->stream>>>(A);
-        DQ_CUDA(cudaEventRecord(m->ev3, m->stream));
-        k_queens_first<<<1, 32, 0, m->stream>>>(A);
-        launches += K + 2;
+        if (use_buckets) {
+            k_queens_bucket<<<ctas, kQueensBucketBlock, smem, m->stream>>>(A);
+            DQ_CUDA(cudaEventRecord(m->ev3, m->stream));
+            DQ_CUDA(cudaStreamWaitEvent(m->stream, m->ev_join, 0));
+            launches += K + 2;
+        } else {
+            k_queens_lane<<<ctas, kQueensBlock, smem, m->stream>>>(A);
+            DQ_CUDA(cudaEventRecord(m->ev3, m->stream));
+            k_queens_first<<<1, 32, 0, m->stream>>>(A);
+            launches += K + 2;
+        }
         DQ_CUDA(cudaGetLastError());
         DQ_CUDA(cudaEventRecord(m->ev1, m->stream));
         DQ_CUDA(cudaMemcpyAsync(h_ctrl, ctrl, sizeof h_ctrl, cudaMemcpyDeviceToHost, m->stream));

@@ -40,6 +40,7 @@ namespace dq {
 struct QueensLaneArgs {
     int n, k;                         // board size; split depth
     int part_rank, part_count;
+    int part_level;                   // children of this level are dealt to the partitions by key (multi-GPU); -1: the root
     uint4* records;                   // [record_cap] {key, a, l, r}: one FC-surviving prefix = one subtree
     unsigned long long record_cap;
     unsigned long long* n_records;    // depth-k records found (may exceed record_cap: then the host grows and reruns)
@@ -328,6 +329,170 @@ __global__ void k_queens_first(QueensLaneArgs A) {
         if (d == N - 2) { out[N - 1] = (uint8_t)(__ffs(full & ~(na | nl | nr)) - 1); return; }
         ++d;
         sa[d] = na; sl[d] = nl; sr[d] = nr; sc[d] = full & ~(na | nl | nr);
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Depth-bucketed warp search (COUNT_ALL).  The lane-per-subtree kernel above pays for SIMT twice: its forward-check
+// loop runs to the row count of the SHALLOWEST lane of the warp (about 9 rows per trip when a node needs 4.3 on
+// average, N=17), and lanes idle while their mates finish a subtree.  Here a warp owns a pool of open frames
+// {a, l, r, untried} in shared memory, bucketed by depth, and every trip takes up to 32 frames of ONE depth:
+//   * the row count of the forward check is warp-uniform and exact (no max over lanes, uniform shift amounts);
+//   * each lane tries the lowest untried value of its frame (one node, dequan.h:416-423); frames that still hold
+//     untried values go back to the bucket, surviving children go to the next bucket, both compacted with a ballot;
+//   * the bucket is chosen deepest-first among those holding a full warp of frames, which bounds every bucket below
+//     64 frames (a bucket is only fed while it holds fewer than 32); with no full bucket the warp pulls 32 more
+//     records from the frontier list, and once that is empty widens from the shallowest bucket.
+// Node and solution counts do not depend on the visiting order; the DFS-first solution is found separately by
+// queens_first_owned.  Bucket sizes live in registers, lane i holding the size of bucket i.
+constexpr int kQueensBucketBlock = 128;
+constexpr int kQueensBucketCap = 64;
+
+// DFS-first solution of the part of the tree this partition owns, and the depth-k key of its prefix
+// (ForwardCheckingStep's own order, dequan.h:494-571).  Run by one warp in a kernel of its own, on a second stream
+// next to the level and bucket kernels (inside the bucket kernel the call costs the compiler its proof that the
+// search loop is warp-uniform, and with it the uniform datapath: 18.0 -> 21.6 ms on 17-Queens).  The search state is
+// warp-uniform, lane j tests the domain of the j-th later variable (one vote per
+// node), and lane d keeps the frame of depth d in its registers (a pop is four shuffles, nothing touches memory).
+__device__ __forceinline__ void queens_first_owned(const QueensLaneArgs& A, int lane) {
+    const int N = A.n, K = A.k;
+    const uint32_t full = (1u << N) - 1u;
+    const int own_depth = A.part_level + 1;              // prefixes of this depth are dealt to the partitions by key
+    if (A.part_count > 1 && own_depth <= 0 && A.part_rank != 0) return;
+    uint32_t fa = 0, fl = 0, fr = 0, fc = 0, fkey = 0, fv = 0;
+    uint32_t a = 0, l = 0, r = 0, cand = full, key = 0;
+    int d = 0;
+    for (;;) {
+        if (cand == 0) {                                 // every value tried at this depth
+            if (d == 0) return;                          // no solution in this partition's share
+            --d;
+            a = __shfl_sync(0xFFFFFFFFu, fa, d); l = __shfl_sync(0xFFFFFFFFu, fl, d); r = __shfl_sync(0xFFFFFFFFu, fr, d);
+            cand = __shfl_sync(0xFFFFFFFFu, fc, d); key = __shfl_sync(0xFFFFFFFFu, fkey, d);
+            continue;
+        }
+        const uint32_t bit = cand & (0u - cand);
+        cand ^= bit;
+        const uint32_t v = (uint32_t)__ffs((int)bit) - 1u;
+        const uint32_t na = a | bit, nl = (l | bit) << 1, nr = (r | bit) >> 1;
+        const bool wiped = lane < N - 1 - d && ((na | ~full) | (nl << lane) | (nr >> lane)) == 0xFFFFFFFFu;
+        if (__any_sync(0xFFFFFFFFu, wiped)) continue;
+        const uint32_t kchild = d < K ? key * (uint32_t)N + v : key;      // the key stops growing at depth k
+        if (A.part_count > 1 && d + 1 == own_depth && (kchild % (uint32_t)A.part_count) != (uint32_t)A.part_rank) continue;
+        if (lane == d) { fa = a; fl = l; fr = r; fc = cand; fkey = key; fv = v; }
+        if (d == N - 2) {
+            if (lane == N - 1) fv = (uint32_t)__ffs((int)(full & ~(na | nl | nr))) - 1u;
+            if (lane < N) A.first_out[lane] = (uint8_t)fv;
+            if (lane == 0) *A.best_key = (unsigned long long)kchild;
+            return;
+        }
+        a = na; l = nl; r = nr; cand = full & ~(na | nl | nr); key = kchild;
+        ++d;
+    }
+}
+
+__global__ void __launch_bounds__(32) k_queens_first_warp(QueensLaneArgs A) { queens_first_owned(A, (int)threadIdx.x); }
+
+__global__ void __launch_bounds__(kQueensBucketBlock)
+k_queens_bucket(QueensLaneArgs A) {
+    extern __shared__ uint4 qb_frames[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint32_t lt = (1u << lane) - 1u;
+    const int N = A.n;
+    const int L = N - 1 - A.k;                                   // buckets: depth k .. N-2
+    const uint32_t hi = ~((1u << N) - 1u);
+    const uint32_t bbase = (uint32_t)__cvta_generic_to_shared(qb_frames + (size_t)wib * L * kQueensBucketCap);
+    const unsigned long long n_found = *A.n_records;
+    const unsigned long long n_rec = n_found < A.record_cap ? n_found : A.record_cap;   // overflow: the host grows the list and reruns
+    const unsigned long long total_warps = (unsigned long long)gridDim.x * (kQueensBucketBlock / 32);
+    const uint32_t fair_share = (uint32_t)min((n_rec + total_warps - 1) / total_warps, 32ull);
+
+
+    uint32_t cnt = 0;                                            // lane i: frames in bucket i
+    uint32_t nodes = 0, sols = 0;
+    unsigned long long tot_nodes = 0, tot_sols = 0;
+    unsigned long long chunk_pos = 0, chunk_end = 0;
+    bool exhausted = false;
+
+    for (;;) {
+        const uint32_t big = __ballot_sync(0xFFFFFFFFu, cnt >= 32u);
+        int lvl;
+        if (big) lvl = 31 - __clz((int)big);
+        else {
+            if (!exhausted) {
+                if (chunk_pos >= chunk_end) {
+                    unsigned long long base = 0;
+                    uint32_t size = 0;
+                    if (lane == 0) {
+                        const unsigned long long cur = *(volatile unsigned long long*)A.cursor;
+                        const unsigned long long remaining = cur < n_rec ? n_rec - cur : 0;
+                        size = (uint32_t)min(max(remaining / (4ull * total_warps), (unsigned long long)max(fair_share, 1u)), 256ull);
+                        base = atomicAdd(A.cursor, (unsigned long long)size);
+                    }
+                    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                    size = __shfl_sync(0xFFFFFFFFu, size, 0);
+                    chunk_pos = base;
+                    chunk_end = min(base + size, n_rec);
+                    if (base >= n_rec) { exhausted = true; chunk_end = chunk_pos; }
+                }
+                if (!exhausted) {
+                    const uint32_t c0 = __shfl_sync(0xFFFFFFFFu, cnt, 0);
+                    const uint32_t n_take = (uint32_t)min(chunk_end - chunk_pos, 32ull);
+                    if ((uint32_t)lane < n_take) {
+                        const uint4 rec = __ldg(A.records + chunk_pos + lane);
+                        const uint32_t a = rec.y | hi;
+                        sts128(bbase + ((c0 + lane) << 4), a, rec.z, rec.w, ~(a | rec.z | rec.w));
+                    }
+                    if (lane == 0) cnt = c0 + n_take;
+                    chunk_pos += n_take;
+                    if (nodes >= 0x40000000u) { tot_nodes += nodes; tot_sols += sols; nodes = 0; sols = 0; }
+                    __syncwarp();
+                    continue;
+                }
+            }
+            const uint32_t any = __ballot_sync(0xFFFFFFFFu, cnt != 0u);
+            if (!any) break;
+            lvl = __ffs((int)any) - 1;
+        }
+        const uint32_t c = __shfl_sync(0xFFFFFFFFu, cnt, lvl);
+        const uint32_t n = min(c, 32u);
+        const uint32_t keep_base = c - n;
+        const bool act = (uint32_t)lane < n;
+        const uint32_t row = bbase + (uint32_t)lvl * (kQueensBucketCap * 16u);
+        uint32_t a = 0xFFFFFFFFu, l = 0, r = 0, cand = 0;
+        if (act) { const uint4 f = lds128(row + ((keep_base + lane) << 4)); a = f.x; l = f.y; r = f.z; cand = f.w; }
+        const uint32_t bit = cand & (0u - cand);
+        cand ^= bit;
+        const uint32_t na = a | bit, nl = (l | bit) << 1, nr = (r | bit) >> 1;
+        const int last = L - 1 - lvl;
+        uint32_t occ_max = 0;
+#pragma unroll 4
+        for (int j = 0; j <= last; j++) occ_max = max(occ_max, na | (nl << j) | (nr >> j));
+        const bool pass = act && occ_max != 0xFFFFFFFFu;
+        nodes += act ? 1u : 0u;
+        const uint32_t keep = __ballot_sync(0xFFFFFFFFu, cand != 0u);
+        if (cand) sts128(row + ((keep_base + __popc(keep & lt)) << 4), a, l, r, cand);
+        const uint32_t c_new = keep_base + __popc(keep);
+        if (last == 0) {
+            if (pass) { const uint32_t pc = __popc(~(na | nl | nr)); nodes += pc; sols += pc; }
+            if (lane == lvl) cnt = c_new;
+        } else {
+            const uint32_t kids = __ballot_sync(0xFFFFFFFFu, pass);
+            const uint32_t c1 = __shfl_sync(0xFFFFFFFFu, cnt, lvl + 1);
+            if (pass) sts128(row + kQueensBucketCap * 16u + ((c1 + __popc(kids & lt)) << 4), na, nl, nr, ~(na | nl | nr));
+            if (lane == lvl) cnt = c_new;
+            if (lane == lvl + 1) cnt = c1 + __popc(kids);
+        }
+        __syncwarp();
+    }
+    tot_nodes += nodes; tot_sols += sols;
+    for (int o = 16; o > 0; o >>= 1) {
+        tot_nodes += __shfl_down_sync(0xFFFFFFFFu, tot_nodes, o);
+        tot_sols += __shfl_down_sync(0xFFFFFFFFu, tot_sols, o);
+    }
+    if (lane == 0) {
+        atomicAdd(A.totals + 0, tot_sols);
+        atomicAdd(A.dfs_nodes, tot_nodes);
     }
 }
 
