@@ -391,6 +391,15 @@ __device__ __forceinline__ void queens_first_owned(const QueensLaneArgs& A, int 
     }
 }
 
+// Unsigned max over the next ROWS variables of their occupied masks (all ones <=> that domain is empty).
+template <int ROWS>
+__device__ __forceinline__ uint32_t queens_rows_occupied(uint32_t na, uint32_t nl, uint32_t nr) {
+    uint32_t m = 0;
+#pragma unroll
+    for (int j = 0; j < ROWS; j++) m = max(m, na | (nl << j) | (nr >> j));
+    return m;
+}
+
 __global__ void __launch_bounds__(32) k_queens_first_warp(QueensLaneArgs A) { queens_first_owned(A, (int)threadIdx.x); }
 
 __global__ void __launch_bounds__(kQueensBucketBlock)
@@ -465,9 +474,16 @@ k_queens_bucket(QueensLaneArgs A) {
         cand ^= bit;
         const uint32_t na = a | bit, nl = (l | bit) << 1, nr = (r | bit) >> 1;
         const int last = L - 1 - lvl;
-        uint32_t occ_max = 0;
-#pragma unroll 4
-        for (int j = 0; j <= last; j++) occ_max = max(occ_max, na | (nl << j) | (nr >> j));
+        // the row count is warp-uniform: one jump into straight-line code with immediate shift amounts
+        uint32_t occ_max = 0;                                    // all ones <=> some later domain is empty
+        switch (last) {
+#define DQ_QROWS(J) case J: occ_max = queens_rows_occupied<J + 1>(na, nl, nr); break;
+            DQ_QROWS(0) DQ_QROWS(1) DQ_QROWS(2) DQ_QROWS(3) DQ_QROWS(4) DQ_QROWS(5) DQ_QROWS(6) DQ_QROWS(7) DQ_QROWS(8) DQ_QROWS(9)
+            DQ_QROWS(10) DQ_QROWS(11) DQ_QROWS(12) DQ_QROWS(13) DQ_QROWS(14) DQ_QROWS(15) DQ_QROWS(16) DQ_QROWS(17) DQ_QROWS(18) DQ_QROWS(19)
+            DQ_QROWS(20) DQ_QROWS(21) DQ_QROWS(22) DQ_QROWS(23) DQ_QROWS(24) DQ_QROWS(25) DQ_QROWS(26) DQ_QROWS(27) DQ_QROWS(28)
+#undef DQ_QROWS
+            default: occ_max = queens_rows_occupied<30>(na, nl, nr); break;
+        }
         const bool pass = act && occ_max != 0xFFFFFFFFu;
         nodes += act ? 1u : 0u;
         const uint32_t keep = __ballot_sync(0xFFFFFFFFu, cand != 0u);

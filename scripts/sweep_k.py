@@ -3,13 +3,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from dequan_b200 import api
 from dequan_b200.model import nqueens
-for n in (13, 14, 15, 16, 17, 18):
+for n in (10, 12, 13, 14, 15, 16, 17, 18):
     m = api.Model(nqueens(n))
-    for k in (4, 5, 6, 7, 8):
-        if n == 18 and k < 5: continue
+    for k in (2, 3, 4, 5, 6, 7, 8):
+        if (n >= 17 and k < 4) or k > n - 3: continue
         try:
             r = m.solve_tree("count", engine="lane", split_depth=k)
             r = m.solve_tree("count", engine="lane", split_depth=k)
-            print(f"N={n} K={k} records={r.n_prefixes} ms={r.kernel_ms:.3f} Gnodes/s={r.nodes/r.kernel_ms/1e6:.1f} sols={r.solutions} nodes={r.nodes}", flush=True)
+            print(f"N={n} K={k} records={r.n_prefixes} ms={r.kernel_ms:.3f} search_ms={r.search_kernel_ms:.3f} Gnodes/s={r.nodes/r.kernel_ms/1e6:.1f} sols={r.solutions} nodes={r.nodes}", flush=True)
         except Exception as e:
             print(n, k, "EXC", e, flush=True)
