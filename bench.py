@@ -324,12 +324,12 @@ def main():
         dist.destroy_process_group()
 
 
-# ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of k_queens_lane (profiles/r1_ncu_queens14.txt, r1_ncu_queens17_lane.txt)
-NCU_TRAFFIC = {(14, 1): 3869696, (17, 1): 127958784 + 3989760}
+# ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of k_queens_bucket (profiles/r1_ncu_queens14_bucket.txt, r1_ncu_queens17_bucket.txt)
+NCU_TRAFFIC = {(14, 1): 3895040, (17, 1): 127105792 + 6686464}
 
 
 def roofline_queens(n, world, nodes, frontier_nodes, records, lane_ms, int_peak, hbm_peak, peak_src):
-    """Roofline of the dominant kernel, k_queens_lane (subtree DFS; ~80 % of the step, profiles/r1_launches_bench.csv).
+    """Roofline of the dominant kernel, k_queens_bucket (depth-bucketed subtree search; profiles/r1_launch_shares.txt).
     It is integer-issue bound: algorithmic work = (5A+4) lane-ops per node, A = forward-checking domain
     updates per node; the peak is the LOP3 rate measured in this run.  Its HBM side is shown next to it: one 16-byte
     record read per subtree."""
@@ -338,7 +338,7 @@ def roofline_queens(n, world, nodes, frontier_nodes, records, lane_ms, int_peak,
     per_gpu_nodes = (nodes / world) if lane_nodes is None else lane_nodes
     achieved = per_gpu_nodes * ops_per_node / (lane_ms * 1e-3) if lane_ms else 0.0
     algo_bytes = records * 16 if world == 1 else None
-    return {"bound": "int32-alu", "kernel": "k_queens_lane", "achieved": achieved / 1e12, "peak": int_peak / 1e12,
+    return {"bound": "int32-alu", "kernel": "k_queens_bucket", "achieved": achieved / 1e12, "peak": int_peak / 1e12,
             "unit": "Tlane-op/s per GPU", "frac": achieved / int_peak, "kernel_ms": lane_ms,
             "nodes_per_launch": per_gpu_nodes, "ops_per_node": ops_per_node,
             "peak_source": "LOP3 microbenchmark (dq_measure_int_peak), this run",
