@@ -53,7 +53,7 @@ class dq_batch_stats(C.Structure):
 
 
 EXPORTS = ["dq_device_info", "dq_set_device", "dq_compile", "dq_free", "dq_model_info", "dq_model_order", "dq_model_table_bytes", "dq_solve_tree",
-           "dq_tree_nodes_upto", "dq_solve_batch_cells", "dq_solve_batch_cells_dev", "dq_solve_batch_graphs",
+           "dq_tree_nodes_upto", "dq_enumerate_solutions", "dq_solve_batch_cells", "dq_solve_batch_cells_dev", "dq_solve_batch_graphs",
            "dq_measure_int_peak", "dq_last_error", "dq_version", "dq_parse_sudoku_lines", "dq_parse_dimacs_col"]
 
 _lib = None
@@ -78,6 +78,7 @@ def lib():
     L.dq_model_table_bytes.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.dq_solve_tree.argtypes = [vp, C.POINTER(dq_tree_opts), C.POINTER(dq_tree_result), i32p]
     L.dq_tree_nodes_upto.argtypes = [vp, C.c_uint64, C.POINTER(C.c_uint64)]
+    L.dq_enumerate_solutions.argtypes = [vp, C.POINTER(dq_tree_opts), C.POINTER(dq_tree_result), i32p, C.c_uint64, C.POINTER(C.c_uint64)]
     L.dq_solve_batch_cells.argtypes = [vp, u8p, C.c_int64, C.c_int32, C.POINTER(dq_batch_opts), u8p, u64p, u8p,
                                        C.POINTER(dq_batch_stats)]
     L.dq_solve_batch_cells_dev.argtypes = L.dq_solve_batch_cells.argtypes
@@ -193,6 +194,20 @@ class Model:
         return TreeResult(OUTCOME[r.outcome], r.n_solutions, r.n_nodes, first[:self.n_vars].tolist() if have else None,
                           r.first_key, r.n_prefixes, r.split_depth_used, r.kernel_ms,
                           ENGINE_NAME.get(r.engine_used, "?"), r.kernel_launches, r.search_kernel_ms, r.frontier_nodes)
+
+    def enumerate_solutions(self, cap: int, split_depth: int = 0, part_rank: int = 0, part_count: int = 1,
+                            engine: str = "auto"):
+        """All solutions in the reference's DFS order -> (int32[n, n_vars], TreeResult).  Raises DequanError
+        (DQ_ERR_NOMEM) when there are more than `cap`."""
+        o = dq_tree_opts(DQ_MODE_COUNT_ALL, split_depth, part_rank, part_count, 0, ENGINE[engine], 0)
+        r = dq_tree_result()
+        out = np.zeros((max(cap, 1), max(self.n_vars, 1)), dtype=np.int32)
+        n = C.c_uint64()
+        _check(lib().dq_enumerate_solutions(self._h, C.byref(o), C.byref(r), out.ctypes.data_as(C.POINTER(C.c_int32)),
+                                            cap, C.byref(n)))
+        res = TreeResult(OUTCOME[r.outcome], r.n_solutions, r.n_nodes, None, r.first_key, r.n_prefixes, r.split_depth_used,
+                         r.kernel_ms, ENGINE_NAME.get(r.engine_used, "?"), r.kernel_launches, r.search_kernel_ms, r.frontier_nodes)
+        return out[:n.value, :self.n_vars].copy(), res
 
     def table_bytes(self) -> int:
         n = C.c_uint64()

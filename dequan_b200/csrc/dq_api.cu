@@ -151,6 +151,8 @@ struct dq_model {
     DevBuf<unsigned long long> d_ctrl;          // cursor, totals[2], best_key, scan totals[2], misc
     DevBuf<unsigned long long> d_sub_nodes, d_sol_key;
     DevBuf<uint8_t> d_sol;
+    DevBuf<uint8_t> e_out;                      // dq_enumerate_solutions: [cap][nv] value indices
+    DevBuf<unsigned long long> e_prefix, e_seq; // ... and their place in the DFS order
     int last_depth = 0;
     unsigned long long last_n_prefix = 0;
     int last_part_rank = 0, last_part_count = 1;
@@ -419,6 +421,7 @@ void dq_free(dq_model* m) {
     if (m->uploaded) {
         m->d_blob.release(); m->d_ctrl.release();
         m->d_sub_nodes.release(); m->d_sol_key.release(); m->d_sol.release();
+        m->e_out.release(); m->e_prefix.release(); m->e_seq.release();
         m->q_records.release(); m->q_records2.release(); m->q_first.release();
         m->b_cells.release(); m->b_solution.release(); m->b_status.release(); m->b_nodes.release();
         m->s_digest.release(); m->s_ctrl.release(); m->s_hard.release(); m->s_tasks.release(); m->s_snaps.release();
@@ -461,7 +464,14 @@ static unsigned long long env_ull(const char* name, unsigned long long dflt) {
     return e ? strtoull(e, nullptr, 10) : dflt;
 }
 
-int dq_solve_tree(dq_model* m, const dq_tree_opts* opts, dq_tree_result* res, int32_t* first_solution) {
+// enumeration request of dq_enumerate_solutions (null for a plain solve)
+struct EnumRequest {
+    int32_t* out;                    // [cap][nv] values by var id, DFS order
+    uint64_t cap;
+    uint64_t written;
+};
+
+static int solve_tree_impl(dq_model* m, const dq_tree_opts* opts, dq_tree_result* res, int32_t* first_solution, EnumRequest* er) {
     if (!m || !opts || !res) { g_err = "null argument"; return DQ_ERR_INVALID; }
     if (opts->part_count < 1 || opts->part_rank < 0 || opts->part_rank >= opts->part_count) { g_err = "bad partition"; return DQ_ERR_INVALID; }
     if (opts->node_budget) { g_err = "node_budget is a batch option; single-tree solves have none"; return DQ_ERR_UNSUPPORTED; }
@@ -471,14 +481,16 @@ int dq_solve_tree(dq_model* m, const dq_tree_opts* opts, dq_tree_result* res, in
     res->first_key = KEY_NONE;
     res->engine_used = DQ_ENGINE_WARP;
     if (first_solution) for (int i = 0; i < nv; i++) first_solution[i] = UNASSIGNED;
-    if (nv == 0) { res->outcome = DQ_SAT; res->n_solutions = 1; res->first_key = 0; return DQ_OK; }   // IsComplete at entry
+    if (nv == 0) { res->outcome = DQ_SAT; res->n_solutions = 1; res->first_key = 0; if (er) er->written = er->cap ? 1 : 0; return DQ_OK; }   // IsComplete at entry
     int rc = upload(m);
     if (rc != DQ_OK) return rc;
     const bool count_all = opts->mode == DQ_MODE_COUNT_ALL;
+    if (er && !count_all) { g_err = "enumeration is a COUNT_ALL solve"; return DQ_ERR_INVALID; }
+    if (er && opts->engine == DQ_ENGINE_LANE) { g_err = "the lane engine counts; enumeration runs on the warp or register engine"; return DQ_ERR_UNSUPPORTED; }
     if (opts->engine == DQ_ENGINE_LANE && !(count_all && m->cm.model_class == CLASS_QUEENS)) {
         g_err = "the lane engine serves COUNT_ALL on N-Queens-class models only"; return DQ_ERR_UNSUPPORTED;
     }
-    if (count_all && m->cm.model_class == CLASS_QUEENS && m->cm.queens_n <= kQueensMaxN && opts->engine != DQ_ENGINE_WARP)
+    if (!er && count_all && m->cm.model_class == CLASS_QUEENS && m->cm.queens_n <= kQueensMaxN && opts->engine != DQ_ENGINE_WARP && opts->engine != DQ_ENGINE_REG)
         return solve_queens_lane(m, opts, res, first_solution);
     const TreeModelDev M = dev_model(m);
     const size_t wbytes = warp_state_bytes(nv, M.trail);
@@ -496,7 +508,12 @@ int dq_solve_tree(dq_model* m, const dq_tree_opts* opts, dq_tree_result* res, in
     const int want_depth = opts->split_depth > 0 ? std::min(opts->split_depth, max_depth) : -1;
     const long long want_prefixes = resident_warps * 24 * opts->part_count;
 
-    unsigned long long* ctrl = m->d_ctrl.p;   // [0]=cursor [1]=sols [2]=nodes [3]=best [4]=scan children [5]=scan nodes
+    if (er) {
+        DQ_CUDA(m->e_out.reserve(std::max<size_t>((size_t)er->cap * nv, 1)));
+        DQ_CUDA(m->e_prefix.reserve(std::max<size_t>(er->cap, 1)));
+        DQ_CUDA(m->e_seq.reserve(std::max<size_t>(er->cap, 1)));
+    }
+    unsigned long long* ctrl = m->d_ctrl.p;   // [0]=cursor [1]=sols [2]=nodes [3]=best [4]=scan children [5]=scan nodes [6]=probe gave up [7]=enumerated
     unsigned long long h_ctrl[8] = {0, 0, 0, KEY_NONE, 0, 0, 0, 0};
     DQ_CUDA(cudaMemcpyAsync(ctrl, h_ctrl, sizeof h_ctrl, cudaMemcpyHostToDevice, m->stream));
     DQ_CUDA(cudaEventRecord(m->ev0, m->stream));
@@ -537,6 +554,8 @@ int dq_solve_tree(dq_model* m, const dq_tree_opts* opts, dq_tree_result* res, in
         A.cursor = ctrl + 0; A.totals = ctrl + 1; A.best_key = ctrl + 3;
         A.sub_nodes = m->d_sub_nodes.p; A.sol_key = m->d_sol_key.p; A.sol = m->d_sol.p;
         A.node_budget = node_budget; A.gave_up = ctrl + 6;
+        A.enum_out = er ? m->e_out.p : nullptr; A.enum_prefix = m->e_prefix.p; A.enum_seq = m->e_seq.p;
+        A.enum_count = ctrl + 7; A.enum_cap = er ? er->cap : 0;
         if (small) {
             SmallTablesDev ST;
             ST.nv = nv; ST.kmax = m->cm.kmax; ST.t_and = m->t_s_and; ST.t_weq = m->t_s_weq; ST.t_weq_on = m->t_s_weq_on;
@@ -556,7 +575,7 @@ int dq_solve_tree(dq_model* m, const dq_tree_opts* opts, dq_tree_result* res, in
     // Past the budget the probe's counts are dropped and the split search below starts over.
     static const unsigned long long probe_nodes = env_ull("DQ_PROBE_NODES", kProbeNodes);
     bool probed = false;
-    if (probe_nodes && want_depth < 0 && opts->part_count == 1) {
+    if (probe_nodes && want_depth < 0 && opts->part_count == 1 && !er) {
         rc = launch_dfs(0, 1, 0, 1, probe_nodes);
         if (rc != DQ_OK) return rc;
         DQ_CUDA(cudaEventRecord(m->ev1, m->stream));
@@ -644,7 +663,45 @@ int dq_solve_tree(dq_model* m, const dq_tree_opts* opts, dq_tree_result* res, in
         DQ_CUDA(cudaMemcpy(sol.data(), m->d_sol.p + (size_t)w * nv, nv, cudaMemcpyDeviceToHost));
         for (int v = 0; v < nv; v++) first_solution[v] = m->cm.values[v][sol[v]];
     }
+    if (er) {
+        // solutions arrive in the order the warps found them; (prefix index, rank inside the subtree) is their DFS order
+        const uint64_t found = h_ctrl[7];
+        if (found != res->n_solutions) { g_err = "internal: enumeration count differs from the solution count"; return DQ_ERR_INTERNAL; }
+        if (found > er->cap) { er->written = 0; g_err = "solution buffer too small (n_solutions holds the number needed)"; return DQ_ERR_NOMEM; }
+        std::vector<uint8_t> raw((size_t)found * nv);
+        std::vector<unsigned long long> pre(found), seq(found);
+        if (found) {
+            DQ_CUDA(cudaMemcpy(raw.data(), m->e_out.p, raw.size(), cudaMemcpyDeviceToHost));
+            DQ_CUDA(cudaMemcpy(pre.data(), m->e_prefix.p, found * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+            DQ_CUDA(cudaMemcpy(seq.data(), m->e_seq.p, found * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        }
+        std::vector<uint64_t> idx(found);
+        for (uint64_t i = 0; i < found; i++) idx[i] = i;
+        std::sort(idx.begin(), idx.end(), [&](uint64_t x, uint64_t y) { return pre[x] != pre[y] ? pre[x] < pre[y] : seq[x] < seq[y]; });
+        for (uint64_t i = 0; i < found; i++)
+            for (int v = 0; v < nv; v++) er->out[i * nv + v] = m->cm.values[v][raw[idx[i] * nv + v]];
+        er->written = found;
+    }
     return DQ_OK;
+}
+
+int dq_solve_tree(dq_model* m, const dq_tree_opts* opts, dq_tree_result* res, int32_t* first_solution) {
+    return solve_tree_impl(m, opts, res, first_solution, nullptr);
+}
+
+// All solutions in the reference's DFS order: what a counting Constraint that snapshots inst_vars on every hit sees
+// (SURVEY.md §8c).  DQ_ERR_NOMEM when there are more than `cap` (res->n_solutions then holds the number).
+int dq_enumerate_solutions(dq_model* m, const dq_tree_opts* opts, dq_tree_result* res, int32_t* solutions, uint64_t cap,
+                           uint64_t* n_written) {
+    if (!solutions && cap) { g_err = "null solution buffer"; return DQ_ERR_INVALID; }
+    if (n_written) *n_written = 0;
+    if (!opts) { g_err = "null argument"; return DQ_ERR_INVALID; }
+    dq_tree_opts o = *opts;
+    o.mode = DQ_MODE_COUNT_ALL;
+    EnumRequest er{solutions, cap, 0};
+    const int rc = solve_tree_impl(m, &o, res, nullptr, &er);
+    if (n_written) *n_written = er.written;
+    return rc;
 }
 
 // Nodes the reference's sequential search visits up to and including the solution in prefix `key`,

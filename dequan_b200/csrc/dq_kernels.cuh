@@ -140,7 +140,33 @@ struct TreeDfsArgs {
     uint8_t* sol;                       // [n_warps][nv] value index per var id
     unsigned long long node_budget;     // root probe only: give up past this many nodes (0 = none) ...
     unsigned long long* gave_up;        // ... and say so here
+    // dq_enumerate_solutions (COUNT_ALL): every solution is appended here, tagged with its place in the DFS order
+    uint8_t* enum_out;                  // [enum_cap][nv] value index per var id (null: not enumerating)
+    unsigned long long* enum_prefix;    // [enum_cap] prefix index of the subtree that holds the solution
+    unsigned long long* enum_seq;       // [enum_cap] rank of the solution inside that subtree
+    unsigned long long* enum_count;     // solutions appended (may exceed enum_cap: the host reports the overflow)
+    unsigned long long enum_cap;
 };
+
+// Append the solutions formed by the current assignment of depths 0..nv-2 (value index per depth in `val`, depth ->
+// var id in `order`) and each value of `valid` for the last variable; the first one has rank `seq` in its subtree.
+template <class ValT, class OrdT>
+__device__ __forceinline__ void enum_append(const TreeDfsArgs& A, unsigned long long prefix_idx, int nv, const ValT* val,
+                                            const OrdT* order, uint32_t valid, unsigned long long seq, int lane) {
+    while (valid) {
+        const int b = __ffs((int)valid) - 1;
+        valid &= valid - 1;
+        unsigned long long slot = 0;
+        if (lane == 0) slot = atomicAdd(A.enum_count, 1ull);
+        slot = __shfl_sync(FULL, slot, 0);
+        if (slot < A.enum_cap) {
+            uint8_t* dst = A.enum_out + slot * (size_t)nv;
+            for (int i = lane; i < nv - 1; i += 32) dst[order[i]] = (uint8_t)val[i];
+            if (lane == 0) { dst[order[nv - 1]] = (uint8_t)b; A.enum_prefix[slot] = prefix_idx; A.enum_seq[slot] = seq; }
+        }
+        ++seq;
+    }
+}
 
 struct RecordFirst {
     const TreeDfsArgs& A;
@@ -154,6 +180,10 @@ struct RecordFirst {
             for (int i = lane; i < nv; i += 32) A.sol[(size_t)gw * nv + S.order[i]] = S.val[i];
             if (lane == 0) A.sol_key[gw] = key;
         }
+    }
+    // COUNT_ALL, last variable: `valid` are its solution values (warp_dfs calls this for every such node)
+    __device__ void solutions(const WarpState& S, uint32_t valid, unsigned long long seq) const {
+        if (A.enum_out) enum_append(A, key, nv, S.val, S.order, valid, seq, lane);
     }
 };
 
@@ -207,7 +237,10 @@ struct BatchCellsArgs {
     const int* idx_list;        // optional: the n instance ids to solve (null = 0..n-1)
 };
 
-struct NoFirst { __device__ void operator()(const WarpState&) const {} };
+struct NoFirst {
+    __device__ void operator()(const WarpState&) const {}
+    __device__ void solutions(const WarpState&, uint32_t, unsigned long long) const {}
+};
 
 template <bool HAS_F, bool HAS_TABLE>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)

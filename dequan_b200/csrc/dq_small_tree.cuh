@@ -135,6 +135,7 @@ k_tree_small(SmallTablesDev T, TreeDfsArgs A) {
                     const uint32_t valid = c & ~Fx;
                     if (A.count_all) {
                         nodes += __popc(c);
+                        if (valid && A.enum_out) enum_append(A, idx, nv, val, T.order, valid, sols, lane);
                         sols += __popc(valid);
                         if (valid && !have_first) {
                             have_first = true;

@@ -169,6 +169,7 @@ __device__ DfsResult warp_dfs(const DevTables& T, const WarpState& S, int d0, bo
             if (count_all) {
                 R.nodes += __popc(c);
                 if (budget && R.nodes > budget) { R.outcome = 2; break; }
+                if (valid) on_first.solutions(S, valid, R.sols);
                 R.sols += __popc(valid);
                 if (valid && !R.have_first) {
                     // first solution of this tree: val[] is the assignment right now (count_all keeps searching)

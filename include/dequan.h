@@ -575,8 +575,12 @@ public:
 
     /* ---- extensions (namespace b200 has the free-function forms) ---- */
     bool SolveB200(Assignment& a, int mode, const b200::SolveOptions& opt, b200::SolveReport* rep) const;
+    /* b200::EnumerateAll: every solution in the search's visiting order, values by var id. */
+    void EnumerateB200(const Assignment& a, const b200::SolveOptions& opt, b200::SolveReport* rep,
+                       std::vector<std::vector<int> >& out, unsigned long long max_solutions) const;
 
 private:
+    bool CompileB200(const Assignment& a) const;
     void Flatten(const Assignment& a, b200::Lowering& low, std::vector<int32_t>& dom_type, std::vector<int32_t>& dom_off,
                  std::vector<int32_t>& dom_vals) const;
     void TabulateUserConstraint(size_t c, b200::Lowering& low) const;
@@ -681,13 +685,10 @@ inline void CSP::Flatten(const Assignment& a, b200::Lowering& low, std::vector<i
         }
 }
 
-inline bool CSP::SolveB200(Assignment& a, int mode, const b200::SolveOptions& opt, b200::SolveReport* rep) const {
+/* Lowers the CSP with the Assignment's domains and order and compiles it, unless the cached handle was built from the
+ * identical descriptor.  Returns whether it compiled afresh. */
+inline bool CSP::CompileB200(const Assignment& a) const {
     const int nv = (int)vars.size();
-    if ((int)a.inst_vars.size() != nv || (int)a.current_domains.size() != nv || (int)a.assign_order.size() != nv)
-        throw b200::Error(DQ_ERR_INVALID, "Assignment does not belong to this CSP: call a.Reset(csp) first");
-    if (a.assigned_var_count != 0)
-        throw b200::Error(DQ_ERR_UNSUPPORTED, "resuming a partially assigned Assignment is not supported; Reset() it");
-
     b200::Lowering low;
     std::vector<int32_t> dom_type, dom_off, dom_vals, order(a.assign_order.begin(), a.assign_order.end());
     Flatten(a, low, dom_type, dom_off, dom_vals);
@@ -717,6 +718,17 @@ inline bool CSP::SolveB200(Assignment& a, int mode, const b200::SolveOptions& op
         if (rc != DQ_OK) throw b200::Error(rc, dq_last_error());
         cache_.key.swap(key);
     }
+    return fresh;
+}
+
+inline bool CSP::SolveB200(Assignment& a, int mode, const b200::SolveOptions& opt, b200::SolveReport* rep) const {
+    const int nv = (int)vars.size();
+    if ((int)a.inst_vars.size() != nv || (int)a.current_domains.size() != nv || (int)a.assign_order.size() != nv)
+        throw b200::Error(DQ_ERR_INVALID, "Assignment does not belong to this CSP: call a.Reset(csp) first");
+    if (a.assigned_var_count != 0)
+        throw b200::Error(DQ_ERR_UNSUPPORTED, "resuming a partially assigned Assignment is not supported; Reset() it");
+
+    const bool fresh = CompileB200(a);
 
     dq_tree_opts o{};
     o.mode = mode;
@@ -753,6 +765,39 @@ inline bool CSP::SolveB200(Assignment& a, int mode, const b200::SolveOptions& op
     return true;
 }
 
+inline void CSP::EnumerateB200(const Assignment& a, const b200::SolveOptions& opt, b200::SolveReport* rep,
+                               std::vector<std::vector<int> >& out, unsigned long long max_solutions) const {
+    const int nv = (int)vars.size();
+    if ((int)a.inst_vars.size() != nv || (int)a.current_domains.size() != nv || (int)a.assign_order.size() != nv)
+        throw b200::Error(DQ_ERR_INVALID, "Assignment does not belong to this CSP: call a.Reset(csp) first");
+    if (a.assigned_var_count != 0)
+        throw b200::Error(DQ_ERR_UNSUPPORTED, "resuming a partially assigned Assignment is not supported; Reset() it");
+    const bool fresh = CompileB200(a);
+    dq_tree_opts o{};
+    o.mode = DQ_MODE_COUNT_ALL;
+    o.split_depth = opt.split_depth;
+    o.part_rank = opt.part_rank;
+    o.part_count = opt.part_count;
+    o.engine = opt.engine;
+    dq_tree_result r{};
+    // count first when the caller's bound is generous: the buffer is sized by what the tree holds
+    unsigned long long cap = max_solutions;
+    if (cap > 4096) {
+        const int rc0 = dq_solve_tree(cache_.handle, &o, &r, nullptr);
+        if (rc0 != DQ_OK) throw b200::Error(rc0, dq_last_error());
+        if (r.n_solutions > max_solutions) throw b200::Error(DQ_ERR_NOMEM, "more solutions than max_solutions");
+        cap = r.n_solutions;
+    }
+    std::vector<int32_t> flat((size_t)std::max<unsigned long long>(cap, 1) * (size_t)std::max(nv, 1));
+    uint64_t n = 0;
+    const int rc = dq_enumerate_solutions(cache_.handle, &o, &r, flat.data(), cap, &n);
+    if (rc != DQ_OK) throw b200::Error(rc, dq_last_error());
+    if (rep) { rep->tree = r; rep->compiled_fresh = fresh; }
+    out.clear();
+    out.reserve((size_t)n);
+    for (uint64_t i = 0; i < n; i++) out.emplace_back(flat.begin() + (size_t)i * nv, flat.begin() + (size_t)(i + 1) * nv);
+}
+
 inline bool CSP::ForwardCheckingStep(Assignment& a) const {
     if (a.IsComplete()) return true;                 // also the reference's answer for a second call after success
     return SolveB200(a, DQ_MODE_FIRST, b200::SolveOptions(), nullptr);
@@ -776,6 +821,16 @@ inline unsigned long long CountAll(const CSP& csp, Assignment& a, const SolveOpt
     SolveReport* r = rep ? rep : &local;
     csp.SolveB200(a, DQ_MODE_COUNT_ALL, opt, r);
     return r->tree.n_solutions;
+}
+
+/* Every solution, in the order the search visits them (the reference's static variable order and domain value
+ * order): out[i][v] = value of variable v in the i-th solution.  On the reference the equivalent is a counting
+ * Constraint linked last to the last variable that snapshots inst_vars on every Evaluate.  Throws
+ * Error(DQ_ERR_NOMEM) when the tree holds more than max_solutions.  `a` is left untouched. */
+inline void EnumerateAll(const CSP& csp, const Assignment& a, std::vector<std::vector<int> >& out,
+                         unsigned long long max_solutions = 1000000ULL, const SolveOptions& opt = SolveOptions(),
+                         SolveReport* rep = nullptr) {
+    csp.EnumerateB200(a, opt, rep, out, max_solutions);
 }
 
 }  // namespace b200

@@ -192,6 +192,15 @@ int dq_solve_tree(dq_model *m, const dq_tree_opts *opts,
  * reference.  key == UINT64_MAX: everything this partition explored.                       */
 int dq_tree_nodes_upto(dq_model *m, uint64_t key, uint64_t *nodes);
 
+/* Every solution of the model, in the reference's DFS order (static variable order, domain value order): what a
+ * counting Constraint linked last to the last variable sees when it snapshots Assignment::inst_vars on every
+ * Evaluate (SURVEY.md par. 8c; the reference has no enumeration mode of its own, dequan.h:494-571 stops at the first
+ * solution).  solutions[i * n_vars + v] = value of variable v in the i-th solution.  opts->mode is ignored (the
+ * solve is COUNT_ALL); res is filled as by dq_solve_tree.  With opts->part_count > 1: this partition's solutions.
+ * More than `cap` solutions: returns DQ_ERR_NOMEM, res->n_solutions holds the number, nothing is written.        */
+int dq_enumerate_solutions(dq_model *m, const dq_tree_opts *opts, dq_tree_result *res,
+                           int32_t *solutions /* [cap][n_vars] */, uint64_t cap, uint64_t *n_written);
+
 /* Batch of independent instances sharing the template's constraint graph but with
  * per-instance initial domains: cells[i*stride + v] == 0 keeps variable v's template
  * domain, any other byte c fixes it to the single value c (AddFixedVar, dequan.h:467).

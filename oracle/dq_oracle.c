@@ -143,6 +143,7 @@ typedef struct {
     /* harness extensions (mirror oracle/ref_driver.cpp's Counting/Budget constraints) */
     int count_all; uint64_t budget, evals, solutions; int busted;
     int32_t *first; int have_first;
+    int32_t *all_out; uint64_t all_cap;      /* dqo_enumerate: inst_vars of every counted solution, in visiting order */
     /* prefix-partition emulation of the multi-GPU split (DESIGN.md "multi-GPU") */
     int split_depth, part_rank, part_count; uint64_t upto_key, prefix_counter, cur_prefix, first_key; int stop_all;
 } search_t;
@@ -321,6 +322,8 @@ static int validate(search_t *s, int vid) {
     if (s->count_all && vid == s->order[s->nv - 1]) {
         s->validated++;
         if (!s->have_first) { for (int i = 0; i < s->nv; i++) s->first[i] = s->inst[i]; s->have_first = 1; s->first_key = s->cur_prefix; }
+        if (s->all_out && s->solutions < s->all_cap)
+            for (int i = 0; i < s->nv; i++) s->all_out[s->solutions * (uint64_t)s->nv + i] = s->inst[i];
         s->solutions++;
         return 0;
     }
@@ -392,10 +395,12 @@ typedef struct dqo_opts {
     uint64_t upto_key;       /* UINT64_MAX = no cut-off */
 } dqo_opts;
 
-int dqo_solve(const dq_model_desc *m, const dqo_opts *o, dqo_result *res,
-              int32_t *first /* [n_vars] */, int32_t *order_out /* [n_vars] or NULL */) {
+static int dqo_run(const dq_model_desc *m, const dqo_opts *o, dqo_result *res,
+                   int32_t *first /* [n_vars] */, int32_t *order_out /* [n_vars] or NULL */,
+                   int32_t *all_out, uint64_t all_cap) {
     search_t s;
     memset(&s, 0, sizeof s);
+    s.all_out = all_out; s.all_cap = all_cap;
     s.nv = m->n_vars; s.nc = m->n_cons;
     s.cons = (con_t *)calloc((size_t)(s.nc ? s.nc : 1), sizeof(con_t));
     s.links = (ivec *)calloc((size_t)(s.nv ? s.nv : 1), sizeof(ivec));
@@ -444,6 +449,24 @@ int dqo_solve(const dq_model_desc *m, const dqo_opts *o, dqo_result *res,
     for (int i = 0; i <= s.nv; i++) { for (int j = 0; j < s.frames[i].cap; j++) free(s.frames[i].e[j].saved.vals.v); free(s.frames[i].e); }
     free(s.cons); free(s.links); free(s.dom0); free(s.cur); free(s.inst); free(s.order); free(s.frames);
     return 0;
+}
+
+int dqo_solve(const dq_model_desc *m, const dqo_opts *o, dqo_result *res,
+              int32_t *first /* [n_vars] */, int32_t *order_out /* [n_vars] or NULL */) {
+    return dqo_run(m, o, res, first, order_out, NULL, 0);
+}
+
+/* Every solution in visiting order: the harness's Counting constraint (oracle/ref_driver.cpp, SURVEY.md par. 8c)
+ * snapshotting Assignment::inst_vars on each hit.  out[i * n_vars + v]; at most `cap` are kept, res->solutions
+ * counts them all. */
+int dqo_enumerate(const dq_model_desc *m, dqo_result *res, int32_t *out /* [cap][n_vars] */, uint64_t cap) {
+    dqo_opts o;
+    memset(&o, 0, sizeof o);
+    o.mode = DQ_MODE_COUNT_ALL; o.part_count = 1; o.upto_key = UINT64_MAX;
+    int32_t *first = (int32_t *)calloc((size_t)(m->n_vars ? m->n_vars : 1), sizeof(int32_t));
+    int rc = dqo_run(m, &o, res, first, NULL, out, cap);
+    free(first);
+    return rc;
 }
 
 const char *dqo_version(void) { return "dq_oracle 1 (restatement of nsweb/dequan dequan.h)"; }

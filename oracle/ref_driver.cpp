@@ -54,6 +54,8 @@ struct SolveCounters {
     u64 budget = 0;          // 0 = unlimited
     u64 evals = 0;           // BudgetConstraint evaluate calls
     std::vector<int> first;  // inst_vars snapshot at first counted solution
+    u64 keep_all = 0;        // `enumerate`: snapshot up to this many counted solutions, in visiting order
+    std::vector<std::vector<int> > all;
 };
 
 struct BudgetExceeded {};
@@ -67,6 +69,11 @@ struct CountingConstraint : public Constraint {
         if (ctr->solutions == 0) {
             ctr->first.resize(inst_vars.size());
             for (size_t i = 0; i < inst_vars.size(); i++) ctr->first[i] = inst_vars[i].value;
+        }
+        if (ctr->all.size() < ctr->keep_all) {
+            std::vector<int> snap(inst_vars.size());
+            for (size_t i = 0; i < inst_vars.size(); i++) snap[i] = inst_vars[i].value;
+            ctr->all.push_back(snap);
         }
         ctr->solutions++;
         return Eval::Failed;
@@ -290,6 +297,30 @@ static int cmd_tests() {
     return 0;
 }
 
+// enumerate CAP : models on stdin as for `solve`; one JSON line per model with every counted solution in visiting order
+static int cmd_enumerate(int argc, char** argv) {
+    if (argc < 3) return 2;
+    u64 cap = strtoull(argv[2], 0, 10);
+    ModelText m;
+    while (read_model(std::cin, m)) {
+        SolveCounters ctr;
+        ctr.keep_all = cap;
+        BuiltModel b;
+        build_model(m, b, ctr, true);
+        Assignment a;
+        a.Reset(b.csp);
+        b.csp.ForwardCheckingStep(a);
+        std::cout << "{\"solutions\":" << ctr.solutions << ",\"nodes\":" << a.stats.assigned_vars << ",\"all\":[";
+        for (size_t i = 0; i < ctr.all.size(); i++) {
+            std::cout << (i ? "," : "") << "[";
+            for (size_t j = 0; j < ctr.all[i].size(); j++) std::cout << (j ? "," : "") << ctr.all[i][j];
+            std::cout << "]";
+        }
+        std::cout << "]}" << std::endl;
+    }
+    return 0;
+}
+
 static int cmd_solve(int argc, char** argv) {
     if (argc < 4) return 2;
     bool count_all = !strcmp(argv[2], "count");
@@ -390,9 +421,10 @@ static int cmd_color(int argc, char** argv) {
 int main(int argc, char** argv) {
     std::ios::sync_with_stdio(false);
     try {
-        if (argc < 2) { fprintf(stderr, "usage: dequan_ref tests|solve|nqueens|sudoku|color ...\n"); return 2; }
+        if (argc < 2) { fprintf(stderr, "usage: dequan_ref tests|solve|enumerate|nqueens|sudoku|color ...\n"); return 2; }
         if (!strcmp(argv[1], "tests")) return cmd_tests();
         if (!strcmp(argv[1], "solve")) return cmd_solve(argc, argv);
+        if (!strcmp(argv[1], "enumerate")) return cmd_enumerate(argc, argv);
         if (!strcmp(argv[1], "nqueens")) return cmd_nqueens(argc, argv);
         if (!strcmp(argv[1], "sudoku")) return cmd_sudoku(argc, argv);
         if (!strcmp(argv[1], "color")) return cmd_color(argc, argv);

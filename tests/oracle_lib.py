@@ -79,3 +79,17 @@ def solve(csp: CSP, mode: str = "first", budget: int = 0, split_depth: int = 0, 
     have = r.solutions > 0
     return OracleOut(STATUS[r.outcome], r.solutions, r.nodes, first[:nv].tolist() if have else None,
                      order[:nv].tolist(), r.validated_constraints, r.applied_arcs, r.first_key, r.n_prefixes)
+
+
+def enumerate_solutions(csp: CSP, cap: int = 100000):
+    """All solutions in the reference's visiting order -> (list of value lists by var id, total count)."""
+    desc, keep = csp.desc()
+    nv = len(csp.domains)
+    out = np.zeros((max(cap, 1), max(nv, 1)), dtype=np.int32)
+    r = dqo_result()
+    L = lib()
+    L.dqo_enumerate.argtypes = [C.c_void_p, C.POINTER(dqo_result), C.POINTER(C.c_int32), C.c_uint64]
+    rc = L.dqo_enumerate(C.byref(desc), C.byref(r), out.ctypes.data_as(C.POINTER(C.c_int32)), cap)
+    assert rc == 0
+    del keep
+    return out[:min(r.solutions, cap), :nv].tolist(), r.solutions

@@ -52,3 +52,20 @@ def test_scenarios_match_reference(scen_bin):
     assert [g["name"] for g in got] == [w["name"] for w in want]
     for g, w in zip(got, want):
         assert g == w, f"scenario {w['name']} differs from the reference"
+
+
+@pytest.mark.gpu
+def test_b200_extensions(product_lib, tmp_path):
+    """dequan::b200::CountAll / EnumerateAll (no reference counterpart): counts, node counts and the full solution
+    lists in visiting order against the enumeration goldens recorded from the unmodified reference."""
+    out = str(tmp_path / "ext")
+    libdir = os.path.join(ROOT, "dequan_b200", "lib")
+    subprocess.check_call(["g++", "-std=c++11", "-O2", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), "-o", out,
+                           os.path.join(ROOT, "tests", "cpp", "extensions.cpp"), "-L" + libdir, "-ldequan_b200", "-Wl,-rpath," + libdir])
+    got = {g["name"]: g for g in _lines(subprocess.run([out], capture_output=True, text=True, check=True, timeout=300).stdout)}
+    gold = json.load(open(os.path.join(GOLD, "enumerate_reference.json")))["models"]
+    for name in ("nqueens6", "nqueens8", "ordered_values"):
+        g, w = got[name], gold[name]
+        assert (g["count"], g["nodes"], g["enum_nodes"]) == (w["solutions"], w["nodes"], w["nodes"]), name
+        assert g["all"] == w["all"] and g["first_in_a"] and g["small_refused"], name
+    assert got["nqueens3"]["count"] == 0 and got["nqueens3"]["all"] == [] and not got["nqueens3"]["first_in_a"]

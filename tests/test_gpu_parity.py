@@ -453,3 +453,38 @@ def test_register_tree_engine_equals_generic_engine(product_lib):
         big.AddIntVar(0, 3)
     with pytest.raises(api.DequanError):
         api.Model(big).solve_tree("first", engine="reg")
+
+
+def test_enumeration_in_reference_order(product_lib):
+    """dq_enumerate_solutions: every solution, in the order the reference's search visits them — against the golden
+    lists recorded from the unmodified reference and against the oracle, on both tree engines, split and partitioned."""
+    import json
+    from enum_models import enum_models
+    with open(os.path.join(os.path.dirname(__file__), "golden", "enumerate_reference.json")) as f:
+        gold = json.load(f)
+    used_reg = 0
+    for name, csp in enum_models():
+        g = gold["models"][name]
+        want, total = O.enumerate_solutions(csp, 100000)
+        assert total == g["solutions"] and want[:gold["cap"]] == g["all"], name
+        m = api.Model(csp)
+        for engine in ("warp", "auto"):
+            for depth in (0, 1, 2):
+                got, r = m.enumerate_solutions(max(total, 1), split_depth=depth, engine=engine)
+                assert got.tolist() == want, (name, engine, depth)
+                assert (r.solutions, r.nodes) == (g["solutions"], g["nodes"]), (name, engine, depth)
+                used_reg += r.engine == "reg"
+        if total > 1:
+            with pytest.raises(api.DequanError):
+                m.enumerate_solutions(total - 1)
+            parts = [m.enumerate_solutions(total, split_depth=2, part_rank=k, part_count=3)[0].tolist() for k in range(3)]
+            assert sorted(sum(parts, [])) == sorted(want), name
+            pos = {tuple(s): i for i, s in enumerate(want)}
+            for p in parts:                                   # each partition's list keeps the global order
+                idx = [pos[tuple(s)] for s in p]
+                assert idx == sorted(idx), name
+    assert used_reg > 100
+    csp = nqueens(10)
+    want, total = O.enumerate_solutions(csp, 1000)
+    got, r = api.Model(csp).enumerate_solutions(1000)
+    assert total == 724 and got.tolist() == want and r.nodes == O.solve(csp, "count").nodes

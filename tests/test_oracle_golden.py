@@ -104,3 +104,18 @@ def test_partition_emulation_sums():
             assert sum(p.nodes for p in again) == first.nodes
             owner = [p for p in again if p.first_key == key][0]
             assert owner.first == first.first
+
+
+def test_oracle_enumeration_matches_reference():
+    """Every solution, in visiting order, as recorded by the unmodified reference (tests/golden/make_enumerate_golden.py)."""
+    import json
+    import os
+    from enum_models import enum_models
+    with open(os.path.join(os.path.dirname(__file__), "golden", "enumerate_reference.json")) as f:
+        gold = json.load(f)
+    for name, csp in enum_models():
+        g = gold["models"][name]
+        sols, total = O.enumerate_solutions(csp, gold["cap"])
+        assert total == g["solutions"], name
+        assert sols == g["all"], name
+        assert O.solve(csp, "count").nodes == g["nodes"], name
