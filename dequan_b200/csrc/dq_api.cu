@@ -123,6 +123,7 @@ static cudaError_t device_ctx(DeviceCtx** out) {
 struct LevelArrays {               // kept per expansion level for FIRST-mode node accounting
     int n = 0;
     DevBuf<uint32_t> dmask, surv, child_off, parent_of;   // parent_of indexes the PREVIOUS level
+    DevBuf<unsigned long long> dmask64, surv64;           // dmask / surv of models with 64-bit domain words
     DevBuf<unsigned long long> node_off;
     DevBuf<uint8_t> prefixes;      // [n][depth]
 };
@@ -140,7 +141,8 @@ struct dq_model {
     // model tables in HBM
     DevBuf<uint8_t> d_blob;                     // all tables, one block
     std::vector<uint8_t> h_blob;                // its host image (kept while the copy may be in flight)
-    uint32_t *t_ent_off = nullptr, *t_ent_moff = nullptr, *t_masks = nullptr, *t_dom0 = nullptr;
+    uint32_t *t_ent_off = nullptr, *t_ent_moff = nullptr, *t_masks = nullptr, *t_dom0 = nullptr;   // masks / dom0: 64-bit words when cm.wide()
+    bool last_wide = false;
     uint16_t* t_ent = nullptr;
     uint8_t *t_order = nullptr, *t_pos = nullptr, *t_cell_lut = nullptr;
     int32_t *t_values = nullptr, *t_sizes = nullptr;
@@ -192,7 +194,7 @@ static int upload(dq_model* m) {
     std::vector<uint8_t> lut((size_t)nv * 256, 0xFF);
     for (int v = 0; v < nv; v++)
         for (size_t j = 0; j < c.values[v].size(); j++) {
-            values[(size_t)v * 32 + j] = c.values[v][j];
+            if (j < 32) values[(size_t)v * 32 + j] = c.values[v][j];     // (batch kernels: 32-bit models only)
             if (c.values[v][j] >= 1 && c.values[v][j] <= 255) lut[(size_t)v * 256 + c.values[v][j]] = (uint8_t)j;
         }
     std::vector<int32_t> sizes = c.distinct_sizes;
@@ -207,11 +209,14 @@ static int upload(dq_model* m) {
         if (!vec.empty()) memcpy(blob.data() + off, vec.data(), vec.size() * sizeof(vec[0]));
         return off;
     };
-    const size_t o_ent_off = put(c.ent_off), o_ent = put(c.ent), o_ent_moff = put(c.ent_moff), o_masks = put(c.masks),
-                 o_dom0 = put(c.dom0), o_order = put(order), o_pos = put(pos), o_values = put(values), o_lut = put(lut),
+    // domain words on the device: 32 bits unless some domain has more than 32 values
+    std::vector<uint32_t> masks32, dom032;
+    if (!c.wide()) { masks32.assign(c.masks.begin(), c.masks.end()); dom032.assign(c.dom0.begin(), c.dom0.end()); }
+    const size_t o_ent_off = put(c.ent_off), o_ent = put(c.ent), o_ent_moff = put(c.ent_moff),
+                 o_masks = c.wide() ? put(c.masks) : put(masks32), o_dom0 = c.wide() ? put(c.dom0) : put(dom032), o_order = put(order), o_pos = put(pos), o_values = put(values), o_lut = put(lut),
                  o_sizes = put(sizes);
     std::vector<uint32_t> dom0_pos(32, 0xFFFFFFFFu);
-    for (int p = 0; p < nv && p < 32; p++) dom0_pos[p] = c.dom0[c.order[p]];
+    for (int p = 0; p < nv && p < 32; p++) dom0_pos[p] = (uint32_t)c.dom0[c.order[p]];
     const size_t o_s_and = put(c.small_and), o_s_weq = put(c.small_weq), o_s_weq_on = put(c.small_weq_on), o_s_chk = put(c.small_chk),
                  o_s_dom0 = put(dom0_pos);
     DQ_CUDA(m->d_blob.reserve(blob.size()));
@@ -227,19 +232,50 @@ static int upload(dq_model* m) {
     return DQ_OK;
 }
 
-static TreeModelDev dev_model(const dq_model* m) {
-    TreeModelDev M;
+typedef unsigned long long W64;     // the device's 64-bit domain word
+
+template <typename W>
+static TreeModelDevT<W> dev_model_t(const dq_model* m) {
+    TreeModelDevT<W> M;
     M.T.nv = m->cm.nv;
     M.T.ent_off = m->t_ent_off;
     M.T.ent = m->t_ent;
     M.T.ent_moff = m->t_ent_moff;
-    M.T.masks = m->t_masks;
-    M.dom0 = m->t_dom0;
+    M.T.masks = reinterpret_cast<const W*>(m->t_masks);
+    M.dom0 = reinterpret_cast<const W*>(m->t_dom0);
     M.order = m->t_order;
     M.pos = m->t_pos;
     M.trail = m->cm.trail_bound;
     return M;
 }
+static TreeModelDev dev_model(const dq_model* m) { return dev_model_t<uint32_t>(m); }
+
+template <typename W> struct LevelWords;
+template <> struct LevelWords<uint32_t> {
+    static DevBuf<uint32_t>& dmask(LevelArrays& L) { return L.dmask; }
+    static DevBuf<uint32_t>& surv(LevelArrays& L) { return L.surv; }
+};
+template <> struct LevelWords<W64> {
+    static DevBuf<W64>& dmask(LevelArrays& L) { return L.dmask64; }
+    static DevBuf<W64>& surv(LevelArrays& L) { return L.surv64; }
+};
+
+// Same, for the kernels that are also templated on the domain word type.
+#define DQ_DISPATCH_W(m, W, KERNEL, grid, block, smem, stream, ...)                                       \
+    do {                                                                                                  \
+        if ((m)->cm.has_f) {                                                                              \
+            if ((m)->cm.has_table) KERNEL<true, true, W><<<grid, block, smem, stream>>>(__VA_ARGS__);     \
+            else KERNEL<true, false, W><<<grid, block, smem, stream>>>(__VA_ARGS__);                      \
+        } else {                                                                                          \
+            if ((m)->cm.has_table) KERNEL<false, true, W><<<grid, block, smem, stream>>>(__VA_ARGS__);    \
+            else KERNEL<false, false, W><<<grid, block, smem, stream>>>(__VA_ARGS__);                     \
+        }                                                                                                 \
+    } while (0)
+#define DQ_OCCUPANCY_W(m, W, KERNEL, threads, smem, out)                                               \
+    ((m)->cm.has_f ? ((m)->cm.has_table ? max_ctas_per_sm(KERNEL<true, true, W>, threads, smem, out)  \
+                                        : max_ctas_per_sm(KERNEL<true, false, W>, threads, smem, out)) \
+                   : ((m)->cm.has_table ? max_ctas_per_sm(KERNEL<false, true, W>, threads, smem, out) \
+                                        : max_ctas_per_sm(KERNEL<false, false, W>, threads, smem, out)))
 
 // Picks the template instantiation for the model's feature flags and launches `KERNEL`.
 #define DQ_DISPATCH(m, KERNEL, grid, block, smem, stream, ...)                                            \
@@ -427,7 +463,7 @@ void dq_free(dq_model* m) {
         m->s_digest.release(); m->s_ctrl.release(); m->s_hard.release(); m->s_tasks.release(); m->s_snaps.release();
         m->s_deferred.release();
         for (auto& l : m->levels) {
-            l.dmask.release(); l.surv.release(); l.child_off.release(); l.parent_of.release();
+            l.dmask.release(); l.surv.release(); l.dmask64.release(); l.surv64.release(); l.child_off.release(); l.parent_of.release();
             l.node_off.release(); l.prefixes.release();
         }
     }
@@ -457,6 +493,8 @@ int dq_model_table_bytes(const dq_model* m, uint64_t* bytes) {
     return DQ_OK;
 }
 
+}  // extern "C" (templates follow)
+
 // node budget of the root probe of dq_solve_tree (DQ_PROBE_NODES overrides it, 0 switches the probe off)
 constexpr unsigned long long kProbeNodes = 512;
 static unsigned long long env_ull(const char* name, unsigned long long dflt) {
@@ -471,36 +509,22 @@ struct EnumRequest {
     uint64_t written;
 };
 
-static int solve_tree_impl(dq_model* m, const dq_tree_opts* opts, dq_tree_result* res, int32_t* first_solution, EnumRequest* er) {
-    if (!m || !opts || !res) { g_err = "null argument"; return DQ_ERR_INVALID; }
-    if (opts->part_count < 1 || opts->part_rank < 0 || opts->part_rank >= opts->part_count) { g_err = "bad partition"; return DQ_ERR_INVALID; }
-    if (opts->node_budget) { g_err = "node_budget is a batch option; single-tree solves have none"; return DQ_ERR_UNSUPPORTED; }
-    memset(res, 0, sizeof *res);
+// The generic path (any compiled model): frontier expansion level by level, then the subtree DFS.  W = domain word type.
+template <typename W>
+static int solve_tree_generic(dq_model* m, const dq_tree_opts* opts, dq_tree_result* res, int32_t* first_solution, EnumRequest* er,
+                              const bool count_all) {
     const int nv = m->cm.nv;
-    const int UNASSIGNED = -2147483647;
-    res->first_key = KEY_NONE;
-    res->engine_used = DQ_ENGINE_WARP;
-    if (first_solution) for (int i = 0; i < nv; i++) first_solution[i] = UNASSIGNED;
-    if (nv == 0) { res->outcome = DQ_SAT; res->n_solutions = 1; res->first_key = 0; if (er) er->written = er->cap ? 1 : 0; return DQ_OK; }   // IsComplete at entry
-    int rc = upload(m);
-    if (rc != DQ_OK) return rc;
-    const bool count_all = opts->mode == DQ_MODE_COUNT_ALL;
-    if (er && !count_all) { g_err = "enumeration is a COUNT_ALL solve"; return DQ_ERR_INVALID; }
-    if (er && opts->engine == DQ_ENGINE_LANE) { g_err = "the lane engine counts; enumeration runs on the warp or register engine"; return DQ_ERR_UNSUPPORTED; }
-    if (opts->engine == DQ_ENGINE_LANE && !(count_all && m->cm.model_class == CLASS_QUEENS)) {
-        g_err = "the lane engine serves COUNT_ALL on N-Queens-class models only"; return DQ_ERR_UNSUPPORTED;
-    }
-    if (!er && count_all && m->cm.model_class == CLASS_QUEENS && m->cm.queens_n <= kQueensMaxN && opts->engine != DQ_ENGINE_WARP && opts->engine != DQ_ENGINE_REG)
-        return solve_queens_lane(m, opts, res, first_solution);
-    const TreeModelDev M = dev_model(m);
-    const size_t wbytes = warp_state_bytes(nv, M.trail);
+    int rc = DQ_OK;
+    const TreeModelDevT<W> M = dev_model_t<W>(m);
+    m->last_wide = sizeof(W) == 8;
+    const size_t wbytes = warp_state_bytes(nv, M.trail, sizeof(W));
     const size_t smem = wbytes * kWarpsPerCta;
     if (smem > 200 * 1024) { g_err = "model state exceeds shared memory"; return DQ_ERR_UNSUPPORTED; }
     int occ = 0;
-    rc = DQ_OCCUPANCY(m, k_tree_dfs, kWarpsPerCta * 32, smem, &occ);
+    rc = DQ_OCCUPANCY_W(m, W, k_tree_dfs, kWarpsPerCta * 32, smem, &occ);
     if (rc != DQ_OK) return rc;
     int occ_e = 0;
-    rc = DQ_OCCUPANCY(m, k_expand, kWarpsPerCta * 32, smem, &occ_e);
+    rc = DQ_OCCUPANCY_W(m, W, k_expand, kWarpsPerCta * 32, smem, &occ_e);
     if (rc != DQ_OK) return rc;
     if (occ < 1 || occ_e < 1) { g_err = "kernel does not fit an SM"; return DQ_ERR_UNSUPPORTED; }
     const long long resident_warps = (long long)occ * m->sm_count * kWarpsPerCta;
@@ -529,7 +553,7 @@ static int solve_tree_impl(dq_model* m, const dq_tree_opts* opts, dq_tree_result
     // One launch of the subtree DFS over the prefixes of level `depth`: the register engine for small models
     // (dq_small_tree.cuh), the generic warp engine otherwise.  Sizes and clears the per-run buffers.
     if (opts->engine == DQ_ENGINE_REG && !m->cm.small_ok) { g_err = "the register engine serves models of at most 32 variables with simple pair filters"; return DQ_ERR_UNSUPPORTED; }
-    const bool small = m->cm.small_ok && opts->engine != DQ_ENGINE_WARP;
+    const bool small = sizeof(W) == 4 && m->cm.small_ok && opts->engine != DQ_ENGINE_WARP;
     const size_t ssm = small ? small_tree_smem(nv, m->cm.kmax, m->cm.has_f, kWarpsPerCta) : 0;
     int socc = 0;
     if (small) {
@@ -563,7 +587,7 @@ static int solve_tree_impl(dq_model* m, const dq_tree_opts* opts, dq_tree_result
             if (m->cm.has_f) k_tree_small<true><<<(int)ctas, kWarpsPerCta * 32, ssm, m->stream>>>(ST, A);
             else k_tree_small<false><<<(int)ctas, kWarpsPerCta * 32, ssm, m->stream>>>(ST, A);
             res->engine_used = DQ_ENGINE_REG;
-        } else DQ_DISPATCH(m, k_tree_dfs, (int)ctas, kWarpsPerCta * 32, smem, m->stream, M, A);
+        } else DQ_DISPATCH_W(m, W, k_tree_dfs, (int)ctas, kWarpsPerCta * 32, smem, m->stream, M, A);
         launches++;
         DQ_CUDA(cudaGetLastError());
         return DQ_OK;
@@ -594,10 +618,12 @@ static int solve_tree_impl(dq_model* m, const dq_tree_opts* opts, dq_tree_result
     while (depth < max_depth && (want_depth >= 0 ? depth < want_depth : m->levels[depth].n < want_prefixes)) {
         LevelArrays& L = m->levels[depth];
         const int n = L.n;
-        DQ_CUDA(L.dmask.reserve(n)); DQ_CUDA(L.surv.reserve(n)); DQ_CUDA(L.child_off.reserve(n)); DQ_CUDA(L.node_off.reserve(n));
+        DevBuf<W>& Ldmask = LevelWords<W>::dmask(L);
+        DevBuf<W>& Lsurv = LevelWords<W>::surv(L);
+        DQ_CUDA(Ldmask.reserve(n)); DQ_CUDA(Lsurv.reserve(n)); DQ_CUDA(L.child_off.reserve(n)); DQ_CUDA(L.node_off.reserve(n));
         const int grid = (n + kWarpsPerCta - 1) / kWarpsPerCta;
-        DQ_DISPATCH(m, k_expand, grid, kWarpsPerCta * 32, smem, m->stream, M, L.prefixes.p, depth, n, L.dmask.p, L.surv.p);
-        k_scan_level<<<1, 1024, 0, m->stream>>>(L.dmask.p, L.surv.p, n, L.child_off.p, L.node_off.p, ctrl + 4);
+        DQ_DISPATCH_W(m, W, k_expand, grid, kWarpsPerCta * 32, smem, m->stream, M, L.prefixes.p, depth, n, Ldmask.p, Lsurv.p);
+        k_scan_level<W><<<1, 1024, 0, m->stream>>>(Ldmask.p, Lsurv.p, n, L.child_off.p, L.node_off.p, ctrl + 4);
         launches += 2;
         unsigned long long tot[2];
         DQ_CUDA(cudaMemcpyAsync(tot, ctrl + 4, sizeof tot, cudaMemcpyDeviceToHost, m->stream));
@@ -609,7 +635,7 @@ static int solve_tree_impl(dq_model* m, const dq_tree_opts* opts, dq_tree_result
         C.n = (int)tot[0];
         DQ_CUDA(C.prefixes.reserve((size_t)C.n * (depth + 1)));
         DQ_CUDA(C.parent_of.reserve(C.n));
-        k_write_children<<<(n + 255) / 256, 256, 0, m->stream>>>(L.prefixes.p, depth, n, L.surv.p, L.child_off.p, C.prefixes.p, C.parent_of.p);
+        k_write_children<W><<<(n + 255) / 256, 256, 0, m->stream>>>(L.prefixes.p, depth, n, Lsurv.p, L.child_off.p, C.prefixes.p, C.parent_of.p);
         launches++;
         depth++;
     }
@@ -685,6 +711,36 @@ static int solve_tree_impl(dq_model* m, const dq_tree_opts* opts, dq_tree_result
     return DQ_OK;
 }
 
+static int solve_tree_impl(dq_model* m, const dq_tree_opts* opts, dq_tree_result* res, int32_t* first_solution, EnumRequest* er) {
+    if (!m || !opts || !res) { g_err = "null argument"; return DQ_ERR_INVALID; }
+    if (opts->part_count < 1 || opts->part_rank < 0 || opts->part_rank >= opts->part_count) { g_err = "bad partition"; return DQ_ERR_INVALID; }
+    if (opts->node_budget) { g_err = "node_budget is a batch option; single-tree solves have none"; return DQ_ERR_UNSUPPORTED; }
+    memset(res, 0, sizeof *res);
+    const int nv = m->cm.nv;
+    const int UNASSIGNED = -2147483647;
+    res->first_key = KEY_NONE;
+    res->engine_used = DQ_ENGINE_WARP;
+    if (first_solution) for (int i = 0; i < nv; i++) first_solution[i] = UNASSIGNED;
+    if (nv == 0) { res->outcome = DQ_SAT; res->n_solutions = 1; res->first_key = 0; if (er) er->written = er->cap ? 1 : 0; return DQ_OK; }   // IsComplete at entry
+    int rc = upload(m);
+    if (rc != DQ_OK) return rc;
+    const bool count_all = opts->mode == DQ_MODE_COUNT_ALL;
+    if (er && !count_all) { g_err = "enumeration is a COUNT_ALL solve"; return DQ_ERR_INVALID; }
+    if (er && opts->engine == DQ_ENGINE_LANE) { g_err = "the lane engine counts; enumeration runs on the warp or register engine"; return DQ_ERR_UNSUPPORTED; }
+    if (opts->engine == DQ_ENGINE_LANE && !(count_all && m->cm.model_class == CLASS_QUEENS)) {
+        g_err = "the lane engine serves COUNT_ALL on N-Queens-class models only"; return DQ_ERR_UNSUPPORTED;
+    }
+    if (!er && count_all && m->cm.model_class == CLASS_QUEENS && m->cm.queens_n <= kQueensMaxN && opts->engine != DQ_ENGINE_WARP && opts->engine != DQ_ENGINE_REG)
+        return solve_queens_lane(m, opts, res, first_solution);
+    if (m->cm.wide()) {
+        if (opts->engine == DQ_ENGINE_REG || opts->engine == DQ_ENGINE_LANE) { g_err = "domains of more than 32 values run on the generic warp engine only"; return DQ_ERR_UNSUPPORTED; }
+        return solve_tree_generic<W64>(m, opts, res, first_solution, er, count_all);
+    }
+    return solve_tree_generic<uint32_t>(m, opts, res, first_solution, er, count_all);
+}
+
+extern "C" {
+
 int dq_solve_tree(dq_model* m, const dq_tree_opts* opts, dq_tree_result* res, int32_t* first_solution) {
     return solve_tree_impl(m, opts, res, first_solution, nullptr);
 }
@@ -715,6 +771,14 @@ int dq_tree_nodes_upto(dq_model* m, uint64_t key, uint64_t* nodes) {
     const int depth = m->last_depth;
     const unsigned long long n_prefix = m->last_n_prefix;
     unsigned long long total = 0;
+    const bool wide = m->last_wide;
+    auto read_dmask = [&](const LevelArrays& L, size_t i, unsigned long long* out) -> cudaError_t {
+        if (wide) return cudaMemcpy(out, L.dmask64.p + i, 8, cudaMemcpyDeviceToHost);
+        uint32_t w = 0;
+        const cudaError_t e = cudaMemcpy(&w, L.dmask.p + i, 4, cudaMemcpyDeviceToHost);
+        *out = w;
+        return e;
+    };
     // (a) subtrees with index <= key owned by this partition (the key subtree holds its partial count)
     if (n_prefix) {
         const unsigned long long lim = key == KEY_NONE ? n_prefix : std::min<unsigned long long>(key + 1, n_prefix);
@@ -728,10 +792,10 @@ int dq_tree_nodes_upto(dq_model* m, uint64_t key, uint64_t* nodes) {
             for (int l = 0; l < depth; l++) {
                 const LevelArrays& L = m->levels[l];
                 if (L.n == 0) continue;
-                unsigned long long off = 0; uint32_t dm = 0;
+                unsigned long long off = 0, dm = 0;
                 DQ_CUDA(cudaMemcpy(&off, L.node_off.p + (L.n - 1), sizeof off, cudaMemcpyDeviceToHost));
-                DQ_CUDA(cudaMemcpy(&dm, L.dmask.p + (L.n - 1), sizeof dm, cudaMemcpyDeviceToHost));
-                total += off + __builtin_popcount(dm);
+                DQ_CUDA(read_dmask(L, (size_t)L.n - 1, &dm));
+                total += off + __builtin_popcountll(dm);
             }
         } else {
             std::vector<uint8_t> pre(std::max(depth, 1));
@@ -741,11 +805,11 @@ int dq_tree_nodes_upto(dq_model* m, uint64_t key, uint64_t* nodes) {
                 uint32_t par = 0;
                 DQ_CUDA(cudaMemcpy(&par, m->levels[l + 1].parent_of.p + idx, sizeof par, cudaMemcpyDeviceToHost));
                 const LevelArrays& L = m->levels[l];
-                unsigned long long off = 0; uint32_t dm = 0;
+                unsigned long long off = 0, dm = 0;
                 DQ_CUDA(cudaMemcpy(&off, L.node_off.p + par, sizeof off, cudaMemcpyDeviceToHost));
-                DQ_CUDA(cudaMemcpy(&dm, L.dmask.p + par, sizeof dm, cudaMemcpyDeviceToHost));
-                const uint32_t upto_bit = (2u << pre[l]) - 1u;
-                total += off + __builtin_popcount(dm & upto_bit);
+                DQ_CUDA(read_dmask(L, par, &dm));
+                const unsigned long long upto_bit = pre[l] >= 63 ? ~0ull : (2ull << pre[l]) - 1ull;
+                total += off + __builtin_popcountll(dm & upto_bit);
                 idx = par;
             }
         }
@@ -760,6 +824,7 @@ static int run_batch_sudoku(dq_model* m, const uint8_t* cells_dev, int64_t n, in
 static int run_batch_cells(dq_model* m, const uint8_t* cells_dev, int64_t n, int32_t stride, const dq_batch_opts* opts,
                            uint8_t* sol_dev, unsigned long long* nodes_dev, uint8_t* status_dev, dq_batch_stats* st,
                            const int* idx_list = nullptr, bool timed = true) {
+    if (m->cm.wide()) { g_err = "batches take template domains of at most 32 values"; return DQ_ERR_UNSUPPORTED; }
     if (!idx_list && m->cm.model_class == CLASS_SUDOKU9 && !(opts && opts->engine == DQ_ENGINE_WARP))
         return run_batch_sudoku(m, cells_dev, n, stride, opts, sol_dev, nodes_dev, status_dev, st);
     if (opts && opts->engine == DQ_ENGINE_LANE && m->cm.model_class != CLASS_SUDOKU9) {

@@ -14,13 +14,13 @@ namespace {
 
 struct PairOp {
     EntryKind kind;
-    std::vector<uint32_t> m;  // one mask per value index of x
+    std::vector<Mask> m;      // one mask per value index of x
 };
 
 // How assigning x = a filters q through one OpConstraint-style test "y (op) t"
 // (DoCheck, dequan.h:636-669): returns the mask over q's value list.
-uint32_t op_mask(const std::vector<int32_t>& qvals, int op, int64_t t) {
-    uint32_t m = 0;
+Mask op_mask(const std::vector<int32_t>& qvals, int op, int64_t t) {
+    Mask m = 0;
     for (size_t j = 0; j < qvals.size(); j++) {
         int64_t y = qvals[j];
         bool keep = false;
@@ -32,20 +32,20 @@ uint32_t op_mask(const std::vector<int32_t>& qvals, int op, int64_t t) {
             case DQ_OP_INFEQUAL: keep = (y < t + 1); break;   // ExcludeSup(t+1)
             case DQ_OP_INF:      keep = (y < t); break;       // ExcludeSup(t)
         }
-        if (keep) m |= 1u << j;
+        if (keep) m |= Mask(1) << j;
     }
     return m;
 }
 
 // Same mask in O(1) when q's value list is one ascending run minv, minv+1, ... (every Ranges domain with a single
 // range — AddIntVar(min, max) — which is what the BASELINE models use).
-inline uint32_t low_bits(int64_t n, int k) { return n <= 0 ? 0u : (n >= k ? (k == 32 ? 0xFFFFFFFFu : (1u << k) - 1u) : (1u << n) - 1u); }
-uint32_t op_mask_run(int64_t minv, int k, int op, int64_t t) {
-    const uint32_t full = low_bits(k, k);
+inline Mask low_bits(int64_t n, int k) { const int64_t c = n <= 0 ? 0 : (n >= k ? k : n); return c >= 64 ? ~Mask(0) : (Mask(1) << c) - 1; }
+Mask op_mask_run(int64_t minv, int k, int op, int64_t t) {
+    const Mask full = low_bits(k, k);
     const int64_t i = t - minv;                                   // index of value t
     switch (op) {
-        case DQ_OP_EQUAL:    return (i >= 0 && i < k) ? 1u << i : 0u;
-        case DQ_OP_NOTEQUAL: return (i >= 0 && i < k) ? full & ~(1u << i) : full;
+        case DQ_OP_EQUAL:    return (i >= 0 && i < k) ? Mask(1) << i : Mask(0);
+        case DQ_OP_NOTEQUAL: return (i >= 0 && i < k) ? full & ~(Mask(1) << i) : full;
         case DQ_OP_SUPEQUAL: return full & ~low_bits(i, k);       // y >= t
         case DQ_OP_SUP:      return full & ~low_bits(i + 1, k);   // y >= t + 1
         case DQ_OP_INFEQUAL: return low_bits(i + 1, k);           // y <  t + 1
@@ -91,13 +91,13 @@ int compile_model(const dq_model_desc* d, CompiledModel& M, std::string& err) {
                 int64_t a = d->dom_vals[r], b = d->dom_vals[r + 1];
                 if (a < prev_max) { err = "Ranges domain not ascending/disjoint"; return DQ_ERR_UNSUPPORTED; }
                 prev_max = b > a ? b : a;
-                if (b - a > kMaxDom) { err = "domain larger than 32 values"; return DQ_ERR_UNSUPPORTED; }
+                if (b - a > kMaxDom) { err = "domain larger than 64 values"; return DQ_ERR_UNSUPPORTED; }
                 for (int64_t x = a; x < b; x++) vals.push_back((int32_t)x);
-                if ((int)vals.size() > kMaxDom) { err = "domain larger than 32 values"; return DQ_ERR_UNSUPPORTED; }
+                if ((int)vals.size() > kMaxDom) { err = "domain larger than 64 values"; return DQ_ERR_UNSUPPORTED; }
             }
         } else { err = "bad domain type"; return DQ_ERR_INVALID; }
-        if ((int)vals.size() > kMaxDom) { err = "domain larger than 32 values"; return DQ_ERR_UNSUPPORTED; }
-        M.dom0[v] = vals.size() == 32 ? 0xFFFFFFFFu : ((1u << vals.size()) - 1u);
+        if ((int)vals.size() > kMaxDom) { err = "domain larger than 64 values"; return DQ_ERR_UNSUPPORTED; }
+        M.dom0[v] = low_bits((int64_t)vals.size(), (int)vals.size());
         M.kmax = std::max(M.kmax, (int)vals.size());
     }
 
@@ -108,7 +108,7 @@ int compile_model(const dq_model_desc* d, CompiledModel& M, std::string& err) {
         for (size_t j = 1; j < vals.size() && run; j++) run = (int64_t)vals[j] == (int64_t)vals[j - 1] + 1;
         is_run[v] = run;
     }
-    auto mask_of = [&](int q, int op, int64_t t) -> uint32_t {
+    auto mask_of = [&](int q, int op, int64_t t) -> Mask {
         return is_run[q] ? op_mask_run(M.values[q][0], (int)M.values[q].size(), op, t) : op_mask(M.values[q], op, t);
     };
 
@@ -180,7 +180,7 @@ int compile_model(const dq_model_desc* d, CompiledModel& M, std::string& err) {
     M.ent_off.assign(nv + 1, 0);
     int forced_total = 0;
     // small-model tables (filled while the pairs are normalised below; dropped if some pair does not fit the pattern)
-    bool small_try = nv >= 1 && nv <= 32 && (size_t)nv * M.kmax * 32 * 4 * 3 + 40 * 1024 <= 200 * 1024;   // three tables + four warps of frames fit one CTA
+    bool small_try = nv >= 1 && nv <= 32 && M.kmax <= 32 && (size_t)nv * M.kmax * 32 * 4 * 3 + 40 * 1024 <= 200 * 1024;   // three tables + four warps of frames fit one CTA
     if (small_try) {
         M.small_and.assign((size_t)nv * M.kmax * 32, 0xFFFFFFFFu);
         M.small_weq_on.assign((size_t)nv * M.kmax, 0u);       // the WEQ / CHK tables are created when the first such op shows up
@@ -197,11 +197,11 @@ int compile_model(const dq_model_desc* d, CompiledModel& M, std::string& err) {
         std::vector<std::vector<PairOp>>& ops = ops_buf;
         for (int q : qorder) ops[q].clear();           // left over from the previous x
         qorder.clear();
-        auto push = [&](int q, EntryKind kind, std::vector<uint32_t>&& m) {
+        auto push = [&](int q, EntryKind kind, std::vector<Mask>&& m) {
             if (ops[q].empty()) qorder.push_back(q);
             // consecutive AND filters on the same pair compose into one (the normalisation below would do it anyway)
             if (kind == K_AND && !ops[q].empty() && ops[q].back().kind == K_AND) {
-                std::vector<uint32_t>& acc = ops[q].back().m;
+                std::vector<Mask>& acc = ops[q].back().m;
                 for (int b = 0; b < kx; b++) acc[b] &= m[b];
                 return;
             }
@@ -222,10 +222,10 @@ int compile_model(const dq_model_desc* d, CompiledModel& M, std::string& err) {
                     return mask_of(q, op, t);
                 };
                 if (kind == K_AND && !ops[q].empty() && ops[q].back().kind == K_AND) {
-                    std::vector<uint32_t>& acc = ops[q].back().m;          // compose in place, no temporary
+                    std::vector<Mask>& acc = ops[q].back().m;              // compose in place, no temporary
                     for (int b = 0; b < kx; b++) acc[b] &= mask_at(b);
                 } else {
-                    std::vector<uint32_t> m(kx);
+                    std::vector<Mask> m(kx);
                     for (int b = 0; b < kx; b++) m[b] = mask_at(b);
                     push(q, kind, std::move(m));
                 }
@@ -233,7 +233,7 @@ int compile_model(const dq_model_desc* d, CompiledModel& M, std::string& err) {
                 for (int i = 0; i < k.n; i++) {        // AllDifferent::AplyArcConsistency, dequan.h:915-939
                     int q = k.data[i];
                     if (q == x) continue;
-                    std::vector<uint32_t> m(kx);
+                    std::vector<Mask> m(kx);
                     for (int b = 0; b < kx; b++) m[b] = mask_of(q, DQ_OP_NOTEQUAL, xv[b]);
                     push(q, K_AND, std::move(m));
                 }
@@ -241,10 +241,10 @@ int compile_model(const dq_model_desc* d, CompiledModel& M, std::string& err) {
                 const bool x_is_v0 = (k.data[0] == x);
                 const int q = x_is_v0 ? k.data[1] : k.data[0];
                 const int lo = k.data[2], hi = k.data[3];
-                uint32_t q_out = 0;
+                Mask q_out = 0;
                 for (size_t j = 0; j < M.values[q].size(); j++)
-                    if (!(M.values[q][j] >= lo && M.values[q][j] < hi)) q_out |= 1u << j;
-                std::vector<uint32_t> m(kx);
+                    if (!(M.values[q][j] >= lo && M.values[q][j] < hi)) q_out |= Mask(1) << j;
+                std::vector<Mask> m(kx);
                 for (int b = 0; b < kx; b++) m[b] = (xv[b] >= lo && xv[b] < hi) ? 0u : q_out;
                 push(q, K_CHK, std::move(m));
             } else if (k.kind == DQ_CON_TABLE) {
@@ -252,13 +252,13 @@ int compile_model(const dq_model_desc* d, CompiledModel& M, std::string& err) {
                 const int q = x_is_v0 ? k.data[1] : k.data[0];
                 std::set<std::pair<int, int>> allowed;
                 for (int i = 2; i + 1 < k.n; i += 2) allowed.insert({k.data[i], k.data[i + 1]});
-                std::vector<uint32_t> m(kx);
+                std::vector<Mask> m(kx);
                 for (int b = 0; b < kx; b++) {
-                    uint32_t bad = 0;
+                    Mask bad = 0;
                     for (size_t j = 0; j < M.values[q].size(); j++) {
                         std::pair<int, int> pr = x_is_v0 ? std::make_pair((int)xv[b], (int)M.values[q][j])
                                                          : std::make_pair((int)M.values[q][j], (int)xv[b]);
-                        if (!allowed.count(pr)) bad |= 1u << j;
+                        if (!allowed.count(pr)) bad |= Mask(1) << j;
                     }
                     m[b] = bad;
                 }
@@ -275,7 +275,7 @@ int compile_model(const dq_model_desc* d, CompiledModel& M, std::string& err) {
         for (int q : qorder) {
             std::vector<PairOp>& seq = ops[q];
             std::vector<PairOp> norm;
-            PairOp chk{K_CHK, std::vector<uint32_t>(kx, 0u)};
+            PairOp chk{K_CHK, std::vector<Mask>(kx, Mask(0))};
             bool have_chk = false;
             for (PairOp& o : seq) {
                 if (o.kind == K_CHK) { have_chk = true; for (int b = 0; b < kx; b++) chk.m[b] |= o.m[b]; }
@@ -287,7 +287,7 @@ int compile_model(const dq_model_desc* d, CompiledModel& M, std::string& err) {
             for (PairOp& o : norm) {
                 if (o.kind != K_AND || M.values[q].size() != (size_t)kx) continue;
                 bool same = true;
-                for (int b = 0; b < kx && same; b++) same = (o.m[b] == (M.dom0[q] & ~(1u << b)));
+                for (int b = 0; b < kx && same; b++) same = (o.m[b] == (M.dom0[q] & ~(Mask(1) << b)));
                 if (same) o.kind = K_NE_SAME;
             }
             if (norm.size() > 1) multi_pairs++;
@@ -305,9 +305,9 @@ int compile_model(const dq_model_desc* d, CompiledModel& M, std::string& err) {
                     if (pc && M.small_chk.empty()) M.small_chk.assign((size_t)nv * M.kmax * 32, 0u);
                     for (int b = 0; b < kx; b++) {
                         const size_t at = ((size_t)px * M.kmax + b) * 32 + pq;
-                        if (pa) M.small_and[at] = pa->m[b];
-                        if (pw) { M.small_weq[at] = pw->m[b]; M.small_weq_on[(size_t)px * M.kmax + b] |= 1u << pq; }
-                        if (pc) M.small_chk[at] = pc->m[b];
+                        if (pa) M.small_and[at] = (uint32_t)pa->m[b];
+                        if (pw) { M.small_weq[at] = (uint32_t)pw->m[b]; M.small_weq_on[(size_t)px * M.kmax + b] |= 1u << pq; }
+                        if (pc) M.small_chk[at] = (uint32_t)pc->m[b];
                     }
                 }
             }

@@ -8,15 +8,18 @@ namespace dq {
 constexpr int kWarpsPerCta = 4;
 constexpr unsigned long long KEY_NONE = 0xFFFFFFFFFFFFFFFFull;
 
-struct TreeModelDev {
-    DevTables T;
-    const uint32_t* __restrict__ dom0;   // [nv] by var id
+template <typename W>
+struct TreeModelDevT {
+    DevTablesT<W> T;
+    const W* __restrict__ dom0;          // [nv] by var id
     const uint8_t* __restrict__ order;   // [nv]
     const uint8_t* __restrict__ pos;     // [nv]
     int trail;                           // trail capacity per warp
 };
+typedef TreeModelDevT<uint32_t> TreeModelDev;
 
-__device__ __forceinline__ void load_root_state(const TreeModelDev& M, const WarpState& S, int lane) {
+template <typename W>
+__device__ __forceinline__ void load_root_state(const TreeModelDevT<W>& M, const WarpStateT<W>& S, int lane) {
     for (int v = lane; v < M.T.nv; v += 32) {
         S.D[v] = __ldg(M.dom0 + v);
         S.F[v] = 0;
@@ -27,8 +30,8 @@ __device__ __forceinline__ void load_root_state(const TreeModelDev& M, const War
 }
 
 // Re-apply a prefix (value indices for depths 0..depth-1) to the root state.
-template <bool HAS_F, bool HAS_TABLE>
-__device__ __forceinline__ void replay_prefix(const TreeModelDev& M, const WarpState& S, const uint8_t* __restrict__ prefix,
+template <bool HAS_F, bool HAS_TABLE, typename W>
+__device__ __forceinline__ void replay_prefix(const TreeModelDevT<W>& M, const WarpStateT<W>& S, const uint8_t* __restrict__ prefix,
                                               int depth, int lane) {
     load_root_state(M, S, lane);
     int top = 0;
@@ -44,33 +47,34 @@ __device__ __forceinline__ void replay_prefix(const TreeModelDev& M, const WarpS
 // ---- frontier expansion, one level: warp per parent state --------------------------------------
 // dmask[i] = current domain of the next variable (each bit is one node, dequan.h:416-423)
 // surv[i]  = values whose validation and forward check succeed (children states)
-template <bool HAS_F, bool HAS_TABLE>
+template <bool HAS_F, bool HAS_TABLE, typename W = uint32_t>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
-k_expand(TreeModelDev M, const uint8_t* __restrict__ prefixes, int depth, int n_states,
-         uint32_t* __restrict__ dmask, uint32_t* __restrict__ surv) {
+k_expand(TreeModelDevT<W> M, const uint8_t* __restrict__ prefixes, int depth, int n_states,
+         W* __restrict__ dmask, W* __restrict__ surv) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int i = blockIdx.x * kWarpsPerCta + wib;
     if (i >= n_states) return;
-    WarpState S = carve_warp_state(smem + (size_t)wib * warp_state_bytes(M.T.nv, M.trail), M.T.nv, M.trail);
+    WarpStateT<W> S = carve_warp_state_t<W>(smem + (size_t)wib * warp_state_bytes(M.T.nv, M.trail, sizeof(W)), M.T.nv, M.trail);
     replay_prefix<HAS_F, HAS_TABLE>(M, S, prefixes + (size_t)i * depth, depth, lane);
     const int x = S.order[depth];
-    const uint32_t dm = S.D[x];
-    uint32_t c = HAS_F ? (dm & ~S.F[x]) : dm, sv = 0;
+    const W dm = S.D[x];
+    W c = HAS_F ? (dm & ~S.F[x]) : dm, sv = 0;
     while (c) {
-        const int b = __ffs(c) - 1;
+        const int b = dq_ffs(c) - 1;
         c &= c - 1;
         int top = 0;
         const bool wiped = fc_apply<HAS_F, HAS_TABLE>(M.T, S, x, b, depth, top, lane);
         trail_undo<HAS_F>(S, 0, top, lane);
-        if (!wiped) sv |= 1u << b;
+        if (!wiped) sv |= W(1) << b;
     }
     if (lane == 0) { dmask[i] = dm; surv[i] = sv; }
 }
 
 // Single-CTA exclusive scans of popc(surv) -> child_off and popc(dmask) -> node_off; totals in tot[0..1].
+template <typename W>
 __global__ void __launch_bounds__(1024)
-k_scan_level(const uint32_t* __restrict__ dmask, const uint32_t* __restrict__ surv, int n,
+k_scan_level(const W* __restrict__ dmask, const W* __restrict__ surv, int n,
              uint32_t* __restrict__ child_off, unsigned long long* __restrict__ node_off,
              unsigned long long* __restrict__ tot) {
     __shared__ unsigned long long wsum_c[32], wsum_n[32];
@@ -80,7 +84,7 @@ k_scan_level(const uint32_t* __restrict__ dmask, const uint32_t* __restrict__ su
     __syncthreads();
     for (int base = 0; base < n; base += 1024) {
         const int i = base + threadIdx.x;
-        unsigned long long c = i < n ? __popc(surv[i]) : 0, nd = i < n ? __popc(dmask[i]) : 0;
+        unsigned long long c = i < n ? dq_popc(surv[i]) : 0, nd = i < n ? dq_popc(dmask[i]) : 0;
         unsigned long long ic = c, in = nd;
         for (int o = 1; o < 32; o <<= 1) {
             unsigned long long tc = __shfl_up_sync(FULL, ic, o), tn = __shfl_up_sync(FULL, in, o);
@@ -107,15 +111,16 @@ k_scan_level(const uint32_t* __restrict__ dmask, const uint32_t* __restrict__ su
 }
 
 // Children prefixes in DFS (lexicographic) order: thread per parent.
+template <typename W>
 __global__ void k_write_children(const uint8_t* __restrict__ prefixes, int depth, int n_states,
-                                 const uint32_t* __restrict__ surv, const uint32_t* __restrict__ child_off,
+                                 const W* __restrict__ surv, const uint32_t* __restrict__ child_off,
                                  uint8_t* __restrict__ out, uint32_t* __restrict__ parent_of) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_states) return;
-    uint32_t sv = surv[i];
+    W sv = surv[i];
     size_t o = child_off[i];
     while (sv) {
-        const int b = __ffs(sv) - 1;
+        const int b = dq_ffs(sv) - 1;
         sv &= sv - 1;
         uint8_t* dst = out + o * (size_t)(depth + 1);
         for (int j = 0; j < depth; j++) dst[j] = prefixes[(size_t)i * depth + j];
@@ -150,11 +155,11 @@ struct TreeDfsArgs {
 
 // Append the solutions formed by the current assignment of depths 0..nv-2 (value index per depth in `val`, depth ->
 // var id in `order`) and each value of `valid` for the last variable; the first one has rank `seq` in its subtree.
-template <class ValT, class OrdT>
+template <class ValT, class OrdT, typename W>
 __device__ __forceinline__ void enum_append(const TreeDfsArgs& A, unsigned long long prefix_idx, int nv, const ValT* val,
-                                            const OrdT* order, uint32_t valid, unsigned long long seq, int lane) {
+                                            const OrdT* order, W valid, unsigned long long seq, int lane) {
     while (valid) {
-        const int b = __ffs((int)valid) - 1;
+        const int b = dq_ffs(valid) - 1;
         valid &= valid - 1;
         unsigned long long slot = 0;
         if (lane == 0) slot = atomicAdd(A.enum_count, 1ull);
@@ -172,7 +177,8 @@ struct RecordFirst {
     const TreeDfsArgs& A;
     unsigned long long key;
     int gw, nv, lane;
-    __device__ void operator()(const WarpState& S) const {
+    template <typename W>
+    __device__ void operator()(const WarpStateT<W>& S) const {
         unsigned long long old = 0;
         if (lane == 0) old = atomicMin(A.best_key, key);
         old = __shfl_sync(FULL, old, 0);
@@ -182,19 +188,20 @@ struct RecordFirst {
         }
     }
     // COUNT_ALL, last variable: `valid` are its solution values (warp_dfs calls this for every such node)
-    __device__ void solutions(const WarpState& S, uint32_t valid, unsigned long long seq) const {
+    template <typename W>
+    __device__ void solutions(const WarpStateT<W>& S, W valid, unsigned long long seq) const {
         if (A.enum_out) enum_append(A, key, nv, S.val, S.order, valid, seq, lane);
     }
 };
 
-template <bool HAS_F, bool HAS_TABLE>
+template <bool HAS_F, bool HAS_TABLE, typename W = uint32_t>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
-k_tree_dfs(TreeModelDev M, TreeDfsArgs A) {
+k_tree_dfs(TreeModelDevT<W> M, TreeDfsArgs A) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int gw = blockIdx.x * kWarpsPerCta + wib;
     const int nv = M.T.nv;
-    WarpState S = carve_warp_state(smem + (size_t)wib * warp_state_bytes(nv, M.trail), nv, M.trail);
+    WarpStateT<W> S = carve_warp_state_t<W>(smem + (size_t)wib * warp_state_bytes(nv, M.trail, sizeof(W)), nv, M.trail);
     unsigned long long acc_nodes = 0, acc_sols = 0;
     for (;;) {
         unsigned long long j = 0;

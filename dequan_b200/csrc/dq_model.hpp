@@ -19,7 +19,8 @@
 namespace dq {
 
 constexpr int kMaxVars = 254;      // q fits 8 bits, 0xFF reserved
-constexpr int kMaxDom = 32;        // one 32-bit word per domain
+constexpr int kMaxDom = 64;        // one domain word: 32 bits, or 64 for models whose largest domain has 33..64 values
+typedef uint64_t Mask;             // host-side masks are always 64-bit; the upload narrows them for 32-bit models
 
 // What one (x -> q) entry does to q's state (D = domain bits, F = "fails validation" bits):
 enum EntryKind : uint32_t {
@@ -47,14 +48,15 @@ enum ModelClass : int32_t {
 struct CompiledModel {
     int nv = 0;
     int kmax = 0;                              // largest domain size
+    bool wide() const { return kmax > 32; }    // 64-bit domain words on the device (generic tree engine only)
     std::vector<std::vector<int32_t>> values;  // [nv][k_v]
-    std::vector<uint32_t> dom0;                // [nv] initial domain bits
+    std::vector<Mask> dom0;                    // [nv] initial domain bits
     std::vector<int32_t> order;                // [nv] position -> var id (Reset order)
     std::vector<int32_t> pos_of;               // [nv] var id -> position
     std::vector<uint32_t> ent_off;             // [nv+1]
     std::vector<uint16_t> ent;                 // [n_ent]
     std::vector<uint32_t> ent_moff;            // [n_ent] index into masks (kinds != K_NE_SAME)
-    std::vector<uint32_t> masks;               // mask tables, kmax words per entry that needs one
+    std::vector<Mask> masks;                   // mask tables, kmax words per entry that needs one
     bool has_f = false;                        // any K_WEQ / K_CHK entry
     bool has_table = false;                    // any entry other than K_NE_SAME
     int trail_bound = 0;                       // max live trail entries along one DFS path

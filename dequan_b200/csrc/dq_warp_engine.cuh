@@ -26,42 +26,53 @@ constexpr uint32_t D_FORCE_D = 1u << 10, D_FORCE_F = 1u << 11, D_NOTRAIL_D = 1u 
 constexpr uint32_t FULL = 0xFFFFFFFFu;
 constexpr uint32_t TRAIL_F = 0x100;   // trail entry refers to F[q], not D[q]
 
+// Domain word: 32 bits, or 64 for models whose largest domain has 33..64 values (single-tree solves only).
+__device__ __forceinline__ int dq_ffs(uint32_t x) { return __ffs((int)x); }
+__device__ __forceinline__ int dq_ffs(unsigned long long x) { return __ffsll((long long)x); }
+__device__ __forceinline__ int dq_popc(uint32_t x) { return __popc(x); }
+__device__ __forceinline__ int dq_popc(unsigned long long x) { return __popcll(x); }
+
 // Read-only model tables (HBM, read through L1 with ld.global.nc)
-struct DevTables {
+template <typename W>
+struct DevTablesT {
     int nv;
     const uint32_t* __restrict__ ent_off;   // [nv+1]
     const uint16_t* __restrict__ ent;       // [n_ent]
     const uint32_t* __restrict__ ent_moff;  // [n_ent]
-    const uint32_t* __restrict__ masks;
+    const W* __restrict__ masks;
 };
+typedef DevTablesT<uint32_t> DevTables;
 
 // Per-warp mutable state, all in shared memory
-struct WarpState {
-    uint32_t* D;      // [nv] current domain bits            (Assignment::current_domains)
-    uint32_t* F;      // [nv] values that will fail Evaluate (only if HAS_F)
-    uint32_t* cand;   // [nv] untried values per depth
-    uint32_t* told;   // [trail] saved words                 (Assignment::saved_domains)
+template <typename W>
+struct WarpStateT {
+    W* D;             // [nv] current domain bits            (Assignment::current_domains)
+    W* F;             // [nv] values that will fail Evaluate (only if HAS_F)
+    W* cand;          // [nv] untried values per depth
+    W* told;          // [trail] saved words                 (Assignment::saved_domains)
     uint16_t* tq;     // [trail] which word
     uint16_t* mark;   // [nv] trail height per depth
     uint8_t* val;     // [nv] chosen value index per depth   (Assignment::inst_vars)
     uint8_t* order;   // [nv] depth -> var                   (Assignment::assign_order)
     uint8_t* pos;     // [nv] var -> depth
 };
+typedef WarpStateT<uint32_t> WarpState;
 
-__host__ __device__ inline size_t warp_state_bytes(int nv, int trail) {
+__host__ __device__ inline size_t warp_state_bytes(int nv, int trail, int word_bytes = 4) {
     size_t nvp = (size_t)((nv + 3) & ~3);
-    size_t tp = (size_t)((trail + 1) & ~1);
-    return nvp * 4 * 3 + tp * 4 + tp * 2 + nvp * 2 + nvp * 3;
+    size_t tp = (size_t)((trail + 3) & ~3);
+    return (nvp * word_bytes * 3 + tp * word_bytes + tp * 2 + nvp * 2 + nvp * 3 + 15) & ~(size_t)15;   // the next warp's block stays 16-byte aligned
 }
 
-__device__ inline WarpState carve_warp_state(unsigned char* base, int nv, int trail) {
+template <typename W>
+__device__ inline WarpStateT<W> carve_warp_state_t(unsigned char* base, int nv, int trail) {
     size_t nvp = (size_t)((nv + 3) & ~3);
-    size_t tp = (size_t)((trail + 1) & ~1);
-    WarpState s;
-    s.D = (uint32_t*)base;           base += nvp * 4;
-    s.F = (uint32_t*)base;           base += nvp * 4;
-    s.cand = (uint32_t*)base;        base += nvp * 4;
-    s.told = (uint32_t*)base;        base += tp * 4;
+    size_t tp = (size_t)((trail + 3) & ~3);
+    WarpStateT<W> s;
+    s.D = (W*)base;                  base += nvp * sizeof(W);
+    s.F = (W*)base;                  base += nvp * sizeof(W);
+    s.cand = (W*)base;               base += nvp * sizeof(W);
+    s.told = (W*)base;               base += tp * sizeof(W);
     s.tq = (uint16_t*)base;          base += tp * 2;
     s.mark = (uint16_t*)base;        base += nvp * 2;
     s.val = base;                    base += nvp;
@@ -69,6 +80,7 @@ __device__ inline WarpState carve_warp_state(unsigned char* base, int nv, int tr
     s.pos = base;
     return s;
 }
+__device__ inline WarpState carve_warp_state(unsigned char* base, int nv, int trail) { return carve_warp_state_t<uint32_t>(base, nv, trail); }
 
 struct DfsResult {
     unsigned long long nodes;
@@ -78,8 +90,8 @@ struct DfsResult {
 };
 
 // Undo the trail down to `mk` (RestoreSavedDomainStep, dequan.h:431-440).
-template <bool HAS_F>
-__device__ __forceinline__ void trail_undo(const WarpState& S, int mk, int& top, int lane) {
+template <bool HAS_F, typename W>
+__device__ __forceinline__ void trail_undo(const WarpStateT<W>& S, int mk, int& top, int lane) {
     for (int i = mk + lane; i < top; i += 32) {
         uint32_t t = S.tq[i];
         if (HAS_F && (t & TRAIL_F)) S.F[t & 0xFF] = S.told[i];
@@ -91,8 +103,8 @@ __device__ __forceinline__ void trail_undo(const WarpState& S, int mk, int& top,
 
 // Forward-check the assignment x = value index b made at depth d.  Returns true on a domain
 // wipe-out of some unassigned neighbour.  Domain changes are trailed above `top`.
-template <bool HAS_F, bool HAS_TABLE>
-__device__ __forceinline__ bool fc_apply(const DevTables& T, const WarpState& S, int x, int b, int d, int& top, int lane) {
+template <bool HAS_F, bool HAS_TABLE, typename W>
+__device__ __forceinline__ bool fc_apply(const DevTablesT<W>& T, const WarpStateT<W>& S, int x, int b, int d, int& top, int lane) {
     const int e0 = (int)__ldg(T.ent_off + x), e1 = (int)__ldg(T.ent_off + x + 1);
     const uint32_t lt = (1u << lane) - 1u;
     bool wiped = false;
@@ -102,18 +114,18 @@ __device__ __forceinline__ bool fc_apply(const DevTables& T, const WarpState& S,
         const int q = w & 0xFF;
         bool act = !(w & D_SKIP);
         if (act) act = S.pos[q] > d;                      // only unassigned neighbours are filtered
-        uint32_t oldD = 0, newD = 0, oldF = 0, newF = 0;
+        W oldD = 0, newD = 0, oldF = 0, newF = 0;
         if (act) {
             oldD = S.D[q];
             newD = oldD;
             if (HAS_F) { oldF = S.F[q]; newF = oldF; }
             const uint32_t kind = (w >> 8) & 3;
-            if (!HAS_TABLE || kind == D_K_NE_SAME) newD = oldD & ~(1u << b);
+            if (!HAS_TABLE || kind == D_K_NE_SAME) newD = oldD & ~(W(1) << b);
             else {
-                const uint32_t m = __ldg(T.masks + __ldg(T.ent_moff + e) + b);
+                const W m = __ldg(T.masks + __ldg(T.ent_moff + e) + b);
                 if (kind == D_K_AND) newD = oldD & m;
                 else if (HAS_F) {
-                    if (kind == D_K_WEQ) { if (oldD & m) newD = oldD & m; else newF = FULL; }
+                    if (kind == D_K_WEQ) { if (oldD & m) newD = oldD & m; else newF = ~W(0); }
                     else newF = oldF | m;
                 }
             }
@@ -141,8 +153,8 @@ __device__ __forceinline__ bool fc_apply(const DevTables& T, const WarpState& S,
 //   budget    : stop once more than `budget` nodes have been counted (0 = none), outcome DQ_BUDGET.
 //   abort_key / my_key : FIRST-mode prefix search — give up when another warp has recorded a solution
 //                in an earlier prefix (abort_key may be null).
-template <bool HAS_F, bool HAS_TABLE, class OnFirst>
-__device__ DfsResult warp_dfs(const DevTables& T, const WarpState& S, int d0, bool count_all,
+template <bool HAS_F, bool HAS_TABLE, typename W, class OnFirst>
+__device__ DfsResult warp_dfs(const DevTablesT<W>& T, const WarpStateT<W>& S, int d0, bool count_all,
                               unsigned long long budget, const unsigned long long* abort_key,
                               unsigned long long my_key, int lane, OnFirst on_first) {
     const int nv = T.nv;
@@ -151,7 +163,7 @@ __device__ DfsResult warp_dfs(const DevTables& T, const WarpState& S, int d0, bo
     if (d0 >= nv) { R.sols = 1; R.outcome = 1; R.have_first = true; return R; }   // IsComplete, dequan.h:496-499
     int top = 0, d = d0;
     int x = S.order[d];
-    uint32_t c = S.D[x];
+    W c = S.D[x];
     unsigned poll = 0;
     for (;;) {
         if (c == 0) {                                     // every value tried: return false (dequan.h:569-570)
@@ -165,16 +177,16 @@ __device__ DfsResult warp_dfs(const DevTables& T, const WarpState& S, int d0, bo
         if (abort_key && ((++poll & 63u) == 0) && *(volatile const unsigned long long*)abort_key < my_key) { R.outcome = 3; break; }
         if (d == nv - 1) {
             // last variable: each remaining value is a node; valid ones are solutions, no filtering left to do
-            const uint32_t valid = HAS_F ? (c & ~S.F[x]) : c;
+            const W valid = HAS_F ? (c & ~S.F[x]) : c;
             if (count_all) {
-                R.nodes += __popc(c);
+                R.nodes += dq_popc(c);
                 if (budget && R.nodes > budget) { R.outcome = 2; break; }
                 if (valid) on_first.solutions(S, valid, R.sols);
-                R.sols += __popc(valid);
+                R.sols += dq_popc(valid);
                 if (valid && !R.have_first) {
                     // first solution of this tree: val[] is the assignment right now (count_all keeps searching)
                     R.have_first = true;
-                    if (lane == 0) S.val[d] = (uint8_t)(__ffs(valid) - 1);
+                    if (lane == 0) S.val[d] = (uint8_t)(dq_ffs(valid) - 1);
                     __syncwarp();
                     on_first(S);
                 }
@@ -182,8 +194,8 @@ __device__ DfsResult warp_dfs(const DevTables& T, const WarpState& S, int d0, bo
                 continue;
             }
             if (valid) {
-                const int b = __ffs(valid) - 1;
-                unsigned long long n = __popc(c & ((2u << b) - 1u));
+                const int b = dq_ffs(valid) - 1;
+                unsigned long long n = dq_popc(c & ((W(2) << b) - W(1)));
                 if (budget && R.nodes + n > budget) {
                     R.nodes = budget + 1; R.outcome = 2; break;
                 }
@@ -193,12 +205,12 @@ __device__ DfsResult warp_dfs(const DevTables& T, const WarpState& S, int d0, bo
                 R.sols = 1; R.outcome = 1; R.have_first = true;
                 break;
             }
-            if (budget && R.nodes + __popc(c) > budget) { R.nodes = budget + 1; R.outcome = 2; break; }
-            R.nodes += __popc(c);
+            if (budget && R.nodes + dq_popc(c) > budget) { R.nodes = budget + 1; R.outcome = 2; break; }
+            R.nodes += dq_popc(c);
             c = 0;
             continue;
         }
-        const int b = __ffs(c) - 1;
+        const int b = dq_ffs(c) - 1;
         c &= c - 1;
         ++R.nodes;                                        // AssignVar, dequan.h:416-423
         if (budget && R.nodes > budget) { R.outcome = 2; break; }

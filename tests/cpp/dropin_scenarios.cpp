@@ -178,6 +178,32 @@ static void mixed_ops(const char* name, int r3_gap_lo) {
     report(name, ok, csp, a);
 }
 
+// Domains of more than 32 values: six queens on a 48-column board with an ordering chain on top, and a 60-value
+// Values domain listed in descending order.
+static void wide_domains(const char* name, int shift, bool contradict) {
+    CSP csp;
+    const int n = 6, cols = 48;
+    for (int i = 0; i < n; i++) csp.AddIntVar(0, cols);
+    for (int i = 0; i < n; i++)
+        for (int j = i + 1; j < n; j++) {
+            csp.AddConstraint(OpConstraint(i, j, OpConstraint::Op::NotEqual, 0));
+            csp.AddConstraint(OpConstraint(i, j, OpConstraint::Op::NotEqual, j - i));
+            csp.AddConstraint(OpConstraint(i, j, OpConstraint::Op::NotEqual, i - j));
+        }
+    Array<int> desc;
+    for (int v = 59; v >= 0; v--) desc.push_back(v + shift);
+    VarId w = csp.AddIntVar(Domain(DomainType::Values, desc));
+    csp.AddConstraint(OpConstraint(w, 0, OpConstraint::Op::Sup, 40));           // w > q0 + 40
+    csp.AddConstraint(OpConstraint(5, w, OpConstraint::Op::Equal, -30));        // q5 == w - 30
+    csp.AddConstraint(OpConstraint(2, 3, OpConstraint::Op::InfEqual, -20));     // q2 <= q3 - 20
+    if (contradict) csp.AddConstraint(OpConstraint(1, 0, OpConstraint::Op::Equal, 0));   // q1 == q0 against q0 != q1
+    csp.FinalizeModel();
+    Assignment a;
+    a.Reset(csp);
+    bool ok = csp.ForwardCheckingStep(a);
+    report(name, ok, csp, a);
+}
+
 // 7 variables on [0,7), pairwise different, plus the user-defined gap constraint between neighbours.
 static void user_constraint(const char* name, int gap) {
     CSP csp;
@@ -262,5 +288,8 @@ int main(int argc, char** argv) {
     user_constraint("user_gap1", 1);
     user_constraint("user_gap2", 2);
     empty_model();
+    wide_domains("wide_domains_sat", 10, false);
+    wide_domains("wide_domains_shift40", 40, false);
+    wide_domains("wide_domains_unsat", 10, true);
     return 0;
 }

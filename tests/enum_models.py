@@ -11,6 +11,8 @@ def enum_models():
         out.append((f"random{seed}", random_model(seed, n_vars=3 + seed % 4, n_cons=1 + seed % 4, max_dom=3 + seed % 3)))
     for seed in range(7100, 7120):                      # not-equal models with offsets
         out.append((f"ne{seed}", random_model(seed, n_vars=4 + seed % 4, n_cons=5 + seed % 6, max_dom=3 + seed % 2, kinds="ne")))
+    for seed in range(7200, 7212):                      # domains of 33..64 values (64-bit domain words on the device)
+        out.append((f"wide{seed}", random_model(seed, n_vars=3 + seed % 2, n_cons=4 + seed % 3, max_dom=40 + 2 * (seed % 12))))
     edges = np.array([[0, 1], [1, 2], [2, 3], [3, 0], [0, 2], [4, 0], [4, 3], [5, 1]], dtype=np.uint8)
     out.append(("colour6_k3", colouring(6, 3, edges)))
     ordered = CSP()                                      # unsorted Values domains: enumeration follows the list order

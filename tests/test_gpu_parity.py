@@ -360,8 +360,8 @@ def test_batches_from_on_disk_formats(product_lib):
 
 
 def test_maximum_sizes_and_limits(product_lib):
-    """254 variables (the engine's limit) with 32-value and 2-value domains; the first size beyond each limit is
-    refused with an error, not approximated; empty batches are no-ops."""
+    """254 variables (the engine's limit) with 32-value and 2-value domains; the first size beyond each limit (255
+    variables, 65 values) is refused with an error, not approximated; empty batches are no-ops."""
     import random
     rng = random.Random(3)
     csp = CSP()
@@ -380,7 +380,7 @@ def test_maximum_sizes_and_limits(product_lib):
     with pytest.raises(api.DequanError):
         api.Model(big)
     wide = CSP()
-    wide.AddIntVar(0, 33)
+    wide.AddIntVar(0, 65)
     with pytest.raises(api.DequanError):
         api.Model(wide)
     tmpl = api.Model(sudoku_template())
@@ -488,3 +488,63 @@ def test_enumeration_in_reference_order(product_lib):
     want, total = O.enumerate_solutions(csp, 1000)
     got, r = api.Model(csp).enumerate_solutions(1000)
     assert total == 724 and got.tolist() == want and r.nodes == O.solve(csp, "count").nodes
+
+
+def _max_dom(csp):
+    return max(len(d.values) if d.type.name == "Values" else sum(d.values[i + 1] - d.values[i] for i in range(0, len(d.values), 2))
+               for d in csp.domains)
+
+
+def test_domains_up_to_64_values(product_lib):
+    """Models whose largest domain has 33..64 values run the generic engine on 64-bit domain words: same counts,
+    node counts and first solutions as the oracle, through every split depth and partition count."""
+    wide = 0
+    for seed in range(9500, 9580):
+        csp = random_model(seed, n_vars=3 + seed % 3, n_cons=3 + seed % 5, max_dom=40 + seed % 25)
+        m = api.Model(csp)
+        is_wide = _max_dom(csp) > 32
+        wide += is_wide
+        for mode in ("first", "count"):
+            want = O.solve(csp, mode)
+            _cmp_tree(m.solve_tree(mode), want, (seed, mode))
+            for depth in (1, 2):
+                _cmp_tree(m.solve_tree(mode, split_depth=depth), want, (seed, mode, depth))
+            if is_wide:
+                assert m.solve_tree(mode).engine == "warp"
+                with pytest.raises(api.DequanError):
+                    m.solve_tree(mode, engine="reg")
+        if is_wide and seed % 4 == 0:
+            g = O.solve(csp, "count")
+            parts = [m.solve_tree("count", split_depth=2, part_rank=r, part_count=3) for r in range(3)]
+            assert (sum(p.solutions for p in parts), sum(p.nodes for p in parts)) == (g.solutions, g.nodes), seed
+    assert wide > 25
+    # seven queens on a 50-column board (test/main-test.cpp:36-49 with a wider domain): first solution, node count, and
+    # the count of the tree below a fixed first queen
+    board = CSP()
+    for _ in range(7):
+        board.AddIntVar(0, 50)
+    for i in range(7):
+        for j in range(i + 1, 7):
+            for off in (0, j - i, i - j):
+                board.AddConstraint(OpConstraint(i, j, Op.NotEqual, off))
+    board.FinalizeModel()
+    _cmp_tree(api.Model(board).solve_tree("first"), O.solve(board, "first"), "board first")
+    # 64 values exactly, and one more is refused
+    edge = CSP()
+    a = edge.AddIntVar(0, 64); b = edge.AddIntVar(-10, 54); c = edge.AddIntVar(5, 20)
+    edge.AddConstraint(OpConstraint(a, b, Op.Equal, 3)); edge.AddConstraint(OpConstraint(c, a, Op.Sup, 40)); edge.AddConstraint(OpConstraint(b, c, Op.NotEqual, -7))
+    edge.FinalizeModel()
+    for mode in ("first", "count"):
+        _cmp_tree(api.Model(edge).solve_tree(mode), O.solve(edge, mode), ("edge", mode))
+    big = CSP()
+    big.AddIntVar(0, 65); big.AddIntVar(0, 3)
+    big.FinalizeModel()
+    with pytest.raises(api.DequanError):
+        api.Model(big)
+    tmpl = CSP()
+    for _ in range(4):
+        tmpl.AddIntVar(1, 41)
+    tmpl.AddConstraint(OpConstraint(0, 1, Op.NotEqual, 0))
+    tmpl.FinalizeModel()
+    with pytest.raises(api.DequanError):            # batches take 32-bit templates
+        api.Model(tmpl).solve_batch_cells(np.zeros((2, 4), dtype=np.uint8))
