@@ -58,7 +58,7 @@ def test_model_classes(product_lib):
 
 def test_compile_rejects_out_of_scope(product_lib):
     csp = CSP()
-    csp.AddIntVar(0, 40)  # > 32 values
+    csp.AddIntVar(0, 70)  # > 64 values
     with pytest.raises(api.DequanError) as e:
         api.Model(csp)
     assert e.value.code == -2
