@@ -1,8 +1,8 @@
-// dq_lane_queens.cuh — lane-per-subtree forward-checking DFS for the N-Queens model class
+// dq_lane_queens.cuh — forward-checking search for the N-Queens model class
 // (CLASS_QUEENS: N variables on [0,N), NotEqual with offsets {0, +-(j-i)} for every pair —
 // exactly /root/reference/test/main-test.cpp:36-49, recognised by the model compiler).
 //
-// Every lane owns one subtree.  Its search state is three bit masks in registers:
+// The search state of a node is three bit masks:
 //   a      values taken by the assigned variables
 //   l, r   the two diagonal masks, shifted one bit per depth, so that the current domain of the
 //          variable at distance j+1 is   full & ~(a | l<<j | r>>j)
@@ -13,21 +13,21 @@
 // (dequan.h:416-423), i.e. per value of the current filtered domain of the next variable, whether
 // or not its check then succeeds.
 //
-// The explicit DFS stack (the reference recurses, dequan.h:522) is a frame {a,l,r,untried,depth}
-// per lane per level in shared memory, laid out [level][thread] so that every access is
-// conflict-free.  A frame is written only when the level still has untried values, so a pop always
-// lands on a level with work (the saved-domain restore of dequan.h:431-440 becomes one 16-byte load).
-//
-// Work distribution, a queue of kernels with no host round trip in between:
-//   k_queens_level : one launch per level above the split depth k.  The frontier is a record list
-//                    in HBM {key, a, l, r}; key is the base-N number formed by the prefix values,
-//                    i.e. the DFS order of the prefix.  One lane per (record, value) pair: a value
-//                    of the current domain is a node; a surviving child is appended to the next
-//                    frontier with a warp-aggregated atomic.
-//   k_queens_lane  : persistent lanes pull depth-k records (one coalesced 16-byte load per lane)
-//                    and run the DFS below them.
-//   k_queens_first : one lane re-walks the lowest-keyed item that holds a solution and writes the
-//                    DFS-first solution (keeps solution bookkeeping out of the hot loop).
+// A queue of kernels with no host round trip in between:
+//   k_queens_level      : one launch per level above the split depth k.  The frontier is a record list
+//                         in HBM {key, a, l, r}; key is the base-N number formed by the prefix values,
+//                         i.e. the DFS order of the prefix.  One lane per (record, value) pair: a value
+//                         of the current domain is a node; a surviving child is appended to the next
+//                         frontier with a CTA-aggregated atomic.
+//   k_queens_bucket     : the search below the depth-k records: per-warp pools of open frames
+//                         {a, l, r, untried} in shared memory, bucketed by depth, 32 nodes of ONE depth
+//                         per trip (see the comment above the kernel).  DEFAULT.
+//   k_queens_first_warp : one warp, on a side stream, walks the tree in the reference's order to the
+//                         DFS-first solution of this partition (solution bookkeeping stays out of the
+//                         counting kernel).
+//   k_queens_lane / k_queens_first : the earlier lane-per-subtree search (explicit stack per lane,
+//                         [level][thread] frames in shared memory), kept for comparison
+//                         (DQ_QUEENS_ENGINE=lane; profiles/r1_ncu_queens17_lane_old.txt).
 // Prefixes are dealt to partitions (multi-GPU) by key at depth min(k, 5): partition r owns keys = r (mod parts);
 // the levels above that depth are expanded by every partition and counted by partition 0 only, the levels below
 // it by the owner alone.
