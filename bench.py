@@ -308,13 +308,17 @@ def main():
             "roofline": roofline_queens(14, 1, q["nodes"], q["dom_frontier"], q["dom_records"], q["dom_ms"] / q["steps"], int_peak, hbm_peak, peak_src)}
         # BASELINE config C4: G(200, c/199) 3-colouring near the phase transition, batched, node budget per instance
         from dequan_b200 import generators as G
-        off, edges = G.colouring_batch(1024, 200, 4.2)
-        cr = api.solve_batch_graphs(200, 3, off, edges, node_budget=100_000)
-        cr = api.solve_batch_graphs(200, 3, off, edges, node_budget=100_000)
-        extra["colouring_g200_c4.2_k3"] = {"instances": 1024, "node_budget": 100_000, "kernel_ms": cr.kernel_ms,
-                                           "instances_per_sec": 1024 / (cr.kernel_ms * 1e-3), "nodes_per_sec": cr.total_nodes / (cr.kernel_ms * 1e-3),
-                                           "sat": cr.n_sat, "unsat": cr.n_unsat, "budget": cr.n_budget,
-                                           "engine": "register-resident warp engine (dq_reg_graphs.cuh)"}
+        # 1 024 instances leave 7 warps per SM (one warp per instance): a latency-bound launch; 8 192 fill the machine
+        off_all, edges_all = G.colouring_batch(8192, 200, 4.2)
+        for count in (1024, 8192):
+            off, edges = off_all[:count + 1], edges_all[:off_all[count]]
+            cr = api.solve_batch_graphs(200, 3, off, edges, node_budget=100_000)
+            cr = api.solve_batch_graphs(200, 3, off, edges, node_budget=100_000)
+            extra[f"colouring_g200_c4.2_k3_{count}"] = {"instances": count, "node_budget": 100_000, "kernel_ms": cr.kernel_ms,
+                                                        "instances_per_sec": count / (cr.kernel_ms * 1e-3),
+                                                        "nodes_per_sec": cr.total_nodes / (cr.kernel_ms * 1e-3),
+                                                        "sat": cr.n_sat, "unsat": cr.n_unsat, "budget": cr.n_budget,
+                                                        "engine": "register-resident warp engine (dq_reg_graphs.cuh)"}
     if sudoku is not None:
         line["sudoku"] = sudoku_rooflines(sudoku, hbm_peak, peak_src, int_peak)
     line["extra"] = extra
