@@ -143,8 +143,9 @@ struct dq_model {
     std::vector<uint8_t> h_blob;                // its host image (kept while the copy may be in flight)
     uint32_t *t_ent_off = nullptr, *t_ent_moff = nullptr, *t_masks = nullptr, *t_dom0 = nullptr;   // masks / dom0: 64-bit words when cm.wide()
     bool last_wide = false;
-    uint16_t* t_ent = nullptr;
-    uint8_t *t_order = nullptr, *t_pos = nullptr, *t_cell_lut = nullptr;
+    uint32_t* t_ent = nullptr;
+    uint16_t *t_order = nullptr, *t_pos = nullptr;
+    uint8_t* t_cell_lut = nullptr;
     int32_t *t_values = nullptr, *t_sizes = nullptr;
     uint32_t *t_s_and = nullptr, *t_s_weq = nullptr, *t_s_weq_on = nullptr, *t_s_chk = nullptr, *t_s_dom0 = nullptr;
     int n_sizes = 0;
@@ -188,8 +189,8 @@ static int upload(dq_model* m) {
     const CompiledModel& c = m->cm;
     const int nv = c.nv;
     // every table goes into ONE device block with ONE stream-ordered copy (the solve's kernels follow on the same stream)
-    std::vector<uint8_t> order(nv), pos(nv);
-    for (int i = 0; i < nv; i++) { order[i] = (uint8_t)c.order[i]; pos[i] = (uint8_t)c.pos_of[i]; }
+    std::vector<uint16_t> order(nv), pos(nv);
+    for (int i = 0; i < nv; i++) { order[i] = (uint16_t)c.order[i]; pos[i] = (uint16_t)c.pos_of[i]; }
     std::vector<int32_t> values((size_t)nv * 32, 0);
     std::vector<uint8_t> lut((size_t)nv * 256, 0xFF);
     for (int v = 0; v < nv; v++)
@@ -222,8 +223,8 @@ static int upload(dq_model* m) {
     DQ_CUDA(m->d_blob.reserve(blob.size()));
     DQ_CUDA(cudaMemcpyAsync(m->d_blob.p, blob.data(), blob.size(), cudaMemcpyHostToDevice, m->stream));
     uint8_t* base = m->d_blob.p;
-    m->t_ent_off = (uint32_t*)(base + o_ent_off); m->t_ent = (uint16_t*)(base + o_ent); m->t_ent_moff = (uint32_t*)(base + o_ent_moff);
-    m->t_masks = (uint32_t*)(base + o_masks); m->t_dom0 = (uint32_t*)(base + o_dom0); m->t_order = base + o_order; m->t_pos = base + o_pos;
+    m->t_ent_off = (uint32_t*)(base + o_ent_off); m->t_ent = (uint32_t*)(base + o_ent); m->t_ent_moff = (uint32_t*)(base + o_ent_moff);
+    m->t_masks = (uint32_t*)(base + o_masks); m->t_dom0 = (uint32_t*)(base + o_dom0); m->t_order = (uint16_t*)(base + o_order); m->t_pos = (uint16_t*)(base + o_pos);
     m->t_values = (int32_t*)(base + o_values); m->t_cell_lut = base + o_lut; m->t_sizes = (int32_t*)(base + o_sizes);
     m->t_s_and = (uint32_t*)(base + o_s_and); m->t_s_weq = (uint32_t*)(base + o_s_weq); m->t_s_weq_on = (uint32_t*)(base + o_s_weq_on);
     m->t_s_chk = (uint32_t*)(base + o_s_chk); m->t_s_dom0 = (uint32_t*)(base + o_s_dom0);
@@ -488,7 +489,7 @@ int dq_model_order(const dq_model* m, int32_t* order_out) {
 int dq_model_table_bytes(const dq_model* m, uint64_t* bytes) {
     if (!m || !bytes) { g_err = "null argument"; return DQ_ERR_INVALID; }
     const CompiledModel& c = m->cm;
-    *bytes = c.ent_off.size() * 4 + c.ent.size() * 2 + c.ent_moff.size() * 4 + c.masks.size() * 4 + c.dom0.size() * 4 +
+    *bytes = c.ent_off.size() * 4 + c.ent.size() * 4 + c.ent_moff.size() * 4 + c.masks.size() * (c.wide() ? 8 : 4) + c.dom0.size() * (c.wide() ? 8 : 4) +
              (size_t)c.nv * 2 + (size_t)c.nv * 32 * 4 + (size_t)c.nv * 256 + c.distinct_sizes.size() * 4 + 4;
     return DQ_OK;
 }
@@ -518,16 +519,18 @@ static int solve_tree_generic(dq_model* m, const dq_tree_opts* opts, dq_tree_res
     const TreeModelDevT<W> M = dev_model_t<W>(m);
     m->last_wide = sizeof(W) == 8;
     const size_t wbytes = warp_state_bytes(nv, M.trail, sizeof(W));
-    const size_t smem = wbytes * kWarpsPerCta;
-    if (smem > 200 * 1024) { g_err = "model state exceeds shared memory"; return DQ_ERR_UNSUPPORTED; }
+    // warps per CTA: four, fewer when the per-warp state (domains + trail) of a large model would not fit a CTA
+    const int wpc = (int)std::min<size_t>(kWarpsPerCta, (200 * 1024) / wbytes);
+    if (wpc < 1) { g_err = "model state exceeds shared memory"; return DQ_ERR_UNSUPPORTED; }
+    const size_t smem = wbytes * wpc;
     int occ = 0;
-    rc = DQ_OCCUPANCY_W(m, W, k_tree_dfs, kWarpsPerCta * 32, smem, &occ);
+    rc = DQ_OCCUPANCY_W(m, W, k_tree_dfs, wpc * 32, smem, &occ);
     if (rc != DQ_OK) return rc;
     int occ_e = 0;
-    rc = DQ_OCCUPANCY_W(m, W, k_expand, kWarpsPerCta * 32, smem, &occ_e);
+    rc = DQ_OCCUPANCY_W(m, W, k_expand, wpc * 32, smem, &occ_e);
     if (rc != DQ_OK) return rc;
     if (occ < 1 || occ_e < 1) { g_err = "kernel does not fit an SM"; return DQ_ERR_UNSUPPORTED; }
-    const long long resident_warps = (long long)occ * m->sm_count * kWarpsPerCta;
+    const long long resident_warps = (long long)occ * m->sm_count * wpc;
     const int max_depth = nv - 1;
     const int want_depth = opts->split_depth > 0 ? std::min(opts->split_depth, max_depth) : -1;
     const long long want_prefixes = resident_warps * 24 * opts->part_count;
@@ -565,8 +568,9 @@ static int solve_tree_generic(dq_model* m, const dq_tree_opts* opts, dq_tree_res
     auto launch_dfs = [&](int at_depth, unsigned long long n_prefix, int part_rank, int part_count, unsigned long long node_budget) -> int {
         const unsigned long long mine = (n_prefix + part_count - 1 - part_rank) / part_count;
         const long long per_sm = small ? socc : occ;
-        const long long ctas = std::max<long long>(1, std::min<long long>((long long)((mine + kWarpsPerCta - 1) / kWarpsPerCta), per_sm * m->sm_count));
-        n_warps = ctas * kWarpsPerCta;
+        const int w_cta = small ? kWarpsPerCta : wpc;
+        const long long ctas = std::max<long long>(1, std::min<long long>((long long)((mine + w_cta - 1) / w_cta), per_sm * m->sm_count));
+        n_warps = ctas * w_cta;
         DQ_CUDA(m->d_sub_nodes.reserve(n_prefix));
         DQ_CUDA(m->d_sol_key.reserve(n_warps));
         DQ_CUDA(m->d_sol.reserve((size_t)n_warps * nv));
@@ -587,7 +591,7 @@ static int solve_tree_generic(dq_model* m, const dq_tree_opts* opts, dq_tree_res
             if (m->cm.has_f) k_tree_small<true><<<(int)ctas, kWarpsPerCta * 32, ssm, m->stream>>>(ST, A);
             else k_tree_small<false><<<(int)ctas, kWarpsPerCta * 32, ssm, m->stream>>>(ST, A);
             res->engine_used = DQ_ENGINE_REG;
-        } else DQ_DISPATCH_W(m, W, k_tree_dfs, (int)ctas, kWarpsPerCta * 32, smem, m->stream, M, A);
+        } else DQ_DISPATCH_W(m, W, k_tree_dfs, (int)ctas, wpc * 32, smem, m->stream, M, A);
         launches++;
         DQ_CUDA(cudaGetLastError());
         return DQ_OK;
@@ -621,8 +625,8 @@ static int solve_tree_generic(dq_model* m, const dq_tree_opts* opts, dq_tree_res
         DevBuf<W>& Ldmask = LevelWords<W>::dmask(L);
         DevBuf<W>& Lsurv = LevelWords<W>::surv(L);
         DQ_CUDA(Ldmask.reserve(n)); DQ_CUDA(Lsurv.reserve(n)); DQ_CUDA(L.child_off.reserve(n)); DQ_CUDA(L.node_off.reserve(n));
-        const int grid = (n + kWarpsPerCta - 1) / kWarpsPerCta;
-        DQ_DISPATCH_W(m, W, k_expand, grid, kWarpsPerCta * 32, smem, m->stream, M, L.prefixes.p, depth, n, Ldmask.p, Lsurv.p);
+        const int grid = (n + wpc - 1) / wpc;
+        DQ_DISPATCH_W(m, W, k_expand, grid, wpc * 32, smem, m->stream, M, L.prefixes.p, depth, n, Ldmask.p, Lsurv.p);
         k_scan_level<W><<<1, 1024, 0, m->stream>>>(Ldmask.p, Lsurv.p, n, L.child_off.p, L.node_off.p, ctrl + 4);
         launches += 2;
         unsigned long long tot[2];
@@ -1005,7 +1009,7 @@ int dq_solve_batch_cells(dq_model* m, const uint8_t* cells, int64_t n, int32_t s
 int dq_solve_batch_graphs(int32_t nv, int32_t k, const int64_t* edge_off, const uint8_t* edges, int64_t n,
                           const dq_batch_opts* opts, uint8_t* colours, uint64_t* nodes, uint8_t* status,
                           dq_batch_stats* stats) {
-    if (nv < 1 || nv > kMaxVars || k < 1 || k > kMaxDom || n < 0) { g_err = "bad argument"; return DQ_ERR_INVALID; }
+    if (nv < 1 || nv > kMaxGraphVertices || k < 1 || k > 32 || n < 0) { g_err = "bad argument"; return DQ_ERR_INVALID; }
     if (stats) memset(stats, 0, sizeof *stats);
     if (n == 0) return DQ_OK;
     if (!edge_off || !colours || !nodes || !status) { g_err = "null buffer"; return DQ_ERR_INVALID; }
@@ -1017,7 +1021,7 @@ int dq_solve_batch_graphs(int32_t nv, int32_t k, const int64_t* edge_off, const 
     int dev = 0, sms = 0;
     DQ_CUDA(cudaGetDevice(&dev));
     DQ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    DevBuf<long long> d_off; DevBuf<uint8_t> d_edges, d_col, d_status; DevBuf<uint32_t> d_ent_off; DevBuf<uint16_t> d_ent;
+    DevBuf<long long> d_off; DevBuf<uint8_t> d_edges, d_col, d_status; DevBuf<uint32_t> d_ent_off; DevBuf<uint32_t> d_ent;
     DevBuf<unsigned long long> d_nodes, d_ctrl;
     auto cleanup = [&]() { d_off.release(); d_edges.release(); d_col.release(); d_status.release(); d_ent_off.release(); d_ent.release(); d_nodes.release(); d_ctrl.release(); };
     struct Guard { decltype(cleanup)& f; ~Guard() { f(); } } guard{cleanup};

@@ -69,7 +69,7 @@ int reverse_op(int op) {  // dequan.h:681-690
 int compile_model(const dq_model_desc* d, CompiledModel& M, std::string& err) {
     if (!d || d->n_vars < 0 || d->n_cons < 0) { err = "null or negative-sized descriptor"; return DQ_ERR_INVALID; }
     const int nv = d->n_vars;
-    if (nv > kMaxVars) { err = "more than 254 variables"; return DQ_ERR_UNSUPPORTED; }
+    if (nv > kMaxVars) { err = "more than 1022 variables"; return DQ_ERR_UNSUPPORTED; }
     M = CompiledModel();
     M.nv = nv;
     M.values.resize(nv);
@@ -323,7 +323,7 @@ int compile_model(const dq_model_desc* d, CompiledModel& M, std::string& err) {
             for (size_t i = 0; i < passes[p].size(); i++) {
                 const PairOp& o = passes[p][i];
                 const int q = pass_q[p][i];
-                uint32_t w = (uint32_t)q | ((uint32_t)o.kind << 8);
+                uint32_t w = (uint32_t)q | ((uint32_t)o.kind << ENT_KIND_SHIFT);
                 const size_t cnt = op_count[q];
                 if (cnt > 1) w |= (p == 0) ? (ENT_FORCE_D | ENT_FORCE_F) : (ENT_NOTRAIL_D | ENT_NOTRAIL_F);
                 if (o.kind == K_WEQ || o.kind == K_CHK) M.has_f = true;
@@ -332,10 +332,10 @@ int compile_model(const dq_model_desc* d, CompiledModel& M, std::string& err) {
                     M.ent_moff.push_back((uint32_t)M.masks.size());
                     M.masks.insert(M.masks.end(), o.m.begin(), o.m.end());
                 } else M.ent_moff.push_back(0);
-                M.ent.push_back((uint16_t)w);
+                M.ent.push_back(w);
             }
             if (p + 1 < n_pass)                        // next pass must start on a 32-entry boundary
-                while ((M.ent.size() - M.ent_off[x]) % 32) { M.ent.push_back((uint16_t)(ENT_SKIP | 0xFF)); M.ent_moff.push_back(0); }
+                while ((M.ent.size() - M.ent_off[x]) % 32) { M.ent.push_back(ENT_SKIP | ENT_Q_MASK); M.ent_moff.push_back(0); }
         }
         M.ent_off[x + 1] = (uint32_t)M.ent.size();
     }
@@ -365,8 +365,8 @@ int compile_model(const dq_model_desc* d, CompiledModel& M, std::string& err) {
             std::set<int> qs;
             for (uint32_t e = M.ent_off[x]; e < M.ent_off[x + 1] && queens; e++) {
                 const uint32_t w = M.ent[e];
-                const int q = w & 0xFF, dist = q > x ? q - x : x - q;
-                if (((w >> 8) & 3) != K_AND || (w & 0xFC00) || !qs.insert(q).second) { queens = false; break; }
+                const int q = (int)(w & ENT_Q_MASK), dist = q > x ? q - x : x - q;
+                if (((w >> ENT_KIND_SHIFT) & 3) != K_AND || (w & ENT_FLAGS) || !qs.insert(q).second) { queens = false; break; }
                 for (int b = 0; b < nv; b++) {
                     uint32_t rm = 1u << b;
                     if (b + dist < nv) rm |= 1u << (b + dist);
@@ -396,7 +396,7 @@ int compile_model(const dq_model_desc* d, CompiledModel& M, std::string& err) {
             }
             want.erase(x);
             for (uint32_t e = M.ent_off[x]; e < M.ent_off[x + 1]; e++)
-                if (!(M.ent[e] & ENT_SKIP)) got.insert(M.ent[e] & 0xFF);
+                if (!(M.ent[e] & ENT_SKIP)) got.insert((int)(M.ent[e] & ENT_Q_MASK));
             sudoku = want == got;
         }
         if (sudoku) M.model_class = CLASS_SUDOKU9;

@@ -12,8 +12,8 @@ template <typename W>
 struct TreeModelDevT {
     DevTablesT<W> T;
     const W* __restrict__ dom0;          // [nv] by var id
-    const uint8_t* __restrict__ order;   // [nv]
-    const uint8_t* __restrict__ pos;     // [nv]
+    const uint16_t* __restrict__ order;  // [nv]
+    const uint16_t* __restrict__ pos;    // [nv]
     int trail;                           // trail capacity per warp
 };
 typedef TreeModelDevT<uint32_t> TreeModelDev;
@@ -53,7 +53,7 @@ k_expand(TreeModelDevT<W> M, const uint8_t* __restrict__ prefixes, int depth, in
          W* __restrict__ dmask, W* __restrict__ surv) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int i = blockIdx.x * kWarpsPerCta + wib;
+    const int i = blockIdx.x * (blockDim.x >> 5) + wib;       // (large models run fewer warps per CTA)
     if (i >= n_states) return;
     WarpStateT<W> S = carve_warp_state_t<W>(smem + (size_t)wib * warp_state_bytes(M.T.nv, M.trail, sizeof(W)), M.T.nv, M.trail);
     replay_prefix<HAS_F, HAS_TABLE>(M, S, prefixes + (size_t)i * depth, depth, lane);
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32)
 k_tree_dfs(TreeModelDevT<W> M, TreeDfsArgs A) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int gw = blockIdx.x * kWarpsPerCta + wib;
+    const int gw = blockIdx.x * (blockDim.x >> 5) + wib;
     const int nv = M.T.nv;
     WarpStateT<W> S = carve_warp_state_t<W>(smem + (size_t)wib * warp_state_bytes(nv, M.trail, sizeof(W)), nv, M.trail);
     unsigned long long acc_nodes = 0, acc_sols = 0;
@@ -287,7 +287,7 @@ k_batch_cells(TreeModelDev M, BatchCellsArgs A) {
                 const int v = v0 + lane;
                 const bool hit = v < nv && __popc(S.D[v]) == sz;
                 const uint32_t m = __ballot_sync(FULL, hit);
-                if (hit) { const int p = base + __popc(m & lt); S.order[p] = (uint8_t)v; S.pos[v] = (uint8_t)p; }
+                if (hit) { const int p = base + __popc(m & lt); S.order[p] = (uint16_t)v; S.pos[v] = (uint16_t)p; }
                 base += __popc(m);
             }
         }
@@ -318,7 +318,7 @@ struct BatchGraphsArgs {
     const uint8_t* edges;       // [total][2]
     long long n;
     uint32_t* ent_off;          // [n][nv+1]
-    uint16_t* ent;              // [2*total]
+    uint32_t* ent;              // [2*total]
     unsigned long long budget;
     unsigned long long* cursor;
     uint8_t* colours;           // [n][nv]
@@ -356,14 +356,14 @@ k_graphs_build(BatchGraphsArgs A) {
     }
     if (lane == 0) off[A.nv] = carry;
     __syncwarp();
-    uint16_t* ent = A.ent + 2 * e0;
+    uint32_t* ent = A.ent + 2 * e0;
     // fill in edge order so that each adjacency list is deterministic: lane 0 walks the edges
     // (a few hundred per instance; this kernel is <1% of the solve)
     if (lane == 0)
         for (long long e = e0; e < e1; e++) {
             const int u = A.edges[2 * e], v = A.edges[2 * e + 1];
-            ent[deg[u]++] = (uint16_t)(v | (D_K_NE_SAME << 8));
-            ent[deg[v]++] = (uint16_t)(u | (D_K_NE_SAME << 8));
+            ent[deg[u]++] = (uint32_t)v | (D_K_NE_SAME << D_KIND_SHIFT);
+            ent[deg[v]++] = (uint32_t)u | (D_K_NE_SAME << D_KIND_SHIFT);
         }
 }
 
@@ -386,7 +386,7 @@ k_batch_graphs(BatchGraphsArgs A) {
         T.ent = A.ent + 2 * A.edge_off[i];
         T.ent_moff = nullptr;
         T.masks = nullptr;
-        for (int v = lane; v < nv; v += 32) { S.D[v] = full; S.F[v] = 0; S.order[v] = (uint8_t)v; S.pos[v] = (uint8_t)v; }
+        for (int v = lane; v < nv; v += 32) { S.D[v] = full; S.F[v] = 0; S.order[v] = (uint16_t)v; S.pos[v] = (uint16_t)v; }
         __syncwarp();
         DfsResult R = warp_dfs<false, false>(T, S, 0, false, A.budget, nullptr, 0ull, lane, NoFirst());
         uint8_t* out = A.colours + (size_t)i * nv;

@@ -18,7 +18,8 @@
 
 namespace dq {
 
-constexpr int kMaxVars = 254;      // q fits 8 bits, 0xFF reserved
+constexpr int kMaxVars = 1022;     // q fits 10 bits with room to spare in the 16-bit id field; 0xFFFF reserved
+constexpr int kMaxGraphVertices = 254;   // batch graphs: vertex ids are bytes in the edge list
 constexpr int kMaxDom = 64;        // one domain word: 32 bits, or 64 for models whose largest domain has 33..64 values
 typedef uint64_t Mask;             // host-side masks are always 64-bit; the upload narrows them for 32-bit models
 
@@ -31,12 +32,15 @@ enum EntryKind : uint32_t {
     K_CHK     = 3    // F |= mask[b]            check-only constraints (OrRange, user tables): values of q
                      //                          that ValidateVarConstraints (dequan.h:573-587) will reject
 };
-// entry word (uint16): q | kind<<8 | flags
-constexpr uint32_t ENT_FORCE_D   = 1u << 10;  // trail D[q] unconditionally (first of several entries on q)
-constexpr uint32_t ENT_FORCE_F   = 1u << 11;
-constexpr uint32_t ENT_NOTRAIL_D = 1u << 12;  // later entry on the same q: the first one already trailed it
-constexpr uint32_t ENT_NOTRAIL_F = 1u << 13;
-constexpr uint32_t ENT_SKIP      = 1u << 14;  // padding so that same-q entries land in different 32-lane passes
+// entry word (uint32): q (16 bits) | kind<<16 | flags
+constexpr uint32_t ENT_Q_MASK    = 0xFFFFu;
+constexpr int      ENT_KIND_SHIFT = 16;
+constexpr uint32_t ENT_FORCE_D   = 1u << 18;  // trail D[q] unconditionally (first of several entries on q)
+constexpr uint32_t ENT_FORCE_F   = 1u << 19;
+constexpr uint32_t ENT_NOTRAIL_D = 1u << 20;  // later entry on the same q: the first one already trailed it
+constexpr uint32_t ENT_NOTRAIL_F = 1u << 21;
+constexpr uint32_t ENT_SKIP      = 1u << 22;  // padding so that same-q entries land in different 32-lane passes
+constexpr uint32_t ENT_FLAGS     = ENT_FORCE_D | ENT_FORCE_F | ENT_NOTRAIL_D | ENT_NOTRAIL_F | ENT_SKIP;
 
 enum ModelClass : int32_t {
     CLASS_GENERIC = 0,     // anything the entry table can express
@@ -54,7 +58,7 @@ struct CompiledModel {
     std::vector<int32_t> order;                // [nv] position -> var id (Reset order)
     std::vector<int32_t> pos_of;               // [nv] var id -> position
     std::vector<uint32_t> ent_off;             // [nv+1]
-    std::vector<uint16_t> ent;                 // [n_ent]
+    std::vector<uint32_t> ent;                 // [n_ent]
     std::vector<uint32_t> ent_moff;            // [n_ent] index into masks (kinds != K_NE_SAME)
     std::vector<Mask> masks;                   // mask tables, kmax words per entry that needs one
     bool has_f = false;                        // any K_WEQ / K_CHK entry

@@ -25,7 +25,7 @@ struct SmallTablesDev {
     const uint32_t* __restrict__ t_weq_on;   // [nv][kmax]       (HAS_F)
     const uint32_t* __restrict__ t_chk;      // [nv][kmax][32]   (HAS_F)
     const uint32_t* __restrict__ dom0_pos;   // [32] initial domain by position (all ones beyond nv)
-    const uint8_t* __restrict__ order;       // [nv] position -> var id
+    const uint16_t* __restrict__ order;      // [nv] position -> var id
 };
 
 __host__ __device__ inline size_t small_tree_smem(int nv, int kmax, bool has_f, int warps) {

@@ -21,10 +21,12 @@ namespace dq {
 
 // entry word layout — keep in sync with dq_model.hpp
 constexpr uint32_t D_K_NE_SAME = 0, D_K_AND = 1, D_K_WEQ = 2, D_K_CHK = 3;
-constexpr uint32_t D_FORCE_D = 1u << 10, D_FORCE_F = 1u << 11, D_NOTRAIL_D = 1u << 12, D_NOTRAIL_F = 1u << 13,
-                   D_SKIP = 1u << 14;
+constexpr uint32_t D_Q_MASK = 0xFFFFu;
+constexpr int D_KIND_SHIFT = 16;
+constexpr uint32_t D_FORCE_D = 1u << 18, D_FORCE_F = 1u << 19, D_NOTRAIL_D = 1u << 20, D_NOTRAIL_F = 1u << 21,
+                   D_SKIP = 1u << 22;
 constexpr uint32_t FULL = 0xFFFFFFFFu;
-constexpr uint32_t TRAIL_F = 0x100;   // trail entry refers to F[q], not D[q]
+constexpr uint32_t TRAIL_F = 0x8000;  // trail entry refers to F[q], not D[q]
 
 // Domain word: 32 bits, or 64 for models whose largest domain has 33..64 values (single-tree solves only).
 __device__ __forceinline__ int dq_ffs(uint32_t x) { return __ffs((int)x); }
@@ -37,7 +39,7 @@ template <typename W>
 struct DevTablesT {
     int nv;
     const uint32_t* __restrict__ ent_off;   // [nv+1]
-    const uint16_t* __restrict__ ent;       // [n_ent]
+    const uint32_t* __restrict__ ent;       // [n_ent]
     const uint32_t* __restrict__ ent_moff;  // [n_ent]
     const W* __restrict__ masks;
 };
@@ -53,15 +55,15 @@ struct WarpStateT {
     uint16_t* tq;     // [trail] which word
     uint16_t* mark;   // [nv] trail height per depth
     uint8_t* val;     // [nv] chosen value index per depth   (Assignment::inst_vars)
-    uint8_t* order;   // [nv] depth -> var                   (Assignment::assign_order)
-    uint8_t* pos;     // [nv] var -> depth
+    uint16_t* order;  // [nv] depth -> var                   (Assignment::assign_order)
+    uint16_t* pos;    // [nv] var -> depth
 };
 typedef WarpStateT<uint32_t> WarpState;
 
 __host__ __device__ inline size_t warp_state_bytes(int nv, int trail, int word_bytes = 4) {
     size_t nvp = (size_t)((nv + 3) & ~3);
     size_t tp = (size_t)((trail + 3) & ~3);
-    return (nvp * word_bytes * 3 + tp * word_bytes + tp * 2 + nvp * 2 + nvp * 3 + 15) & ~(size_t)15;   // the next warp's block stays 16-byte aligned
+    return (nvp * word_bytes * 3 + tp * word_bytes + tp * 2 + nvp * 2 + nvp * 5 + 15) & ~(size_t)15;   // the next warp's block stays 16-byte aligned
 }
 
 template <typename W>
@@ -75,9 +77,9 @@ __device__ inline WarpStateT<W> carve_warp_state_t(unsigned char* base, int nv, 
     s.told = (W*)base;               base += tp * sizeof(W);
     s.tq = (uint16_t*)base;          base += tp * 2;
     s.mark = (uint16_t*)base;        base += nvp * 2;
-    s.val = base;                    base += nvp;
-    s.order = base;                  base += nvp;
-    s.pos = base;
+    s.order = (uint16_t*)base;       base += nvp * 2;
+    s.pos = (uint16_t*)base;         base += nvp * 2;
+    s.val = base;
     return s;
 }
 __device__ inline WarpState carve_warp_state(unsigned char* base, int nv, int trail) { return carve_warp_state_t<uint32_t>(base, nv, trail); }
@@ -94,7 +96,7 @@ template <bool HAS_F, typename W>
 __device__ __forceinline__ void trail_undo(const WarpStateT<W>& S, int mk, int& top, int lane) {
     for (int i = mk + lane; i < top; i += 32) {
         uint32_t t = S.tq[i];
-        if (HAS_F && (t & TRAIL_F)) S.F[t & 0xFF] = S.told[i];
+        if (HAS_F && (t & TRAIL_F)) S.F[t & 0x7FFF] = S.told[i];
         else S.D[t] = S.told[i];
     }
     top = mk;
@@ -110,8 +112,8 @@ __device__ __forceinline__ bool fc_apply(const DevTablesT<W>& T, const WarpState
     bool wiped = false;
     for (int base = e0; base < e1; base += 32) {
         const int e = base + lane;
-        uint32_t w = e < e1 ? (uint32_t)__ldg(T.ent + e) : D_SKIP;
-        const int q = w & 0xFF;
+        uint32_t w = e < e1 ? __ldg(T.ent + e) : D_SKIP;
+        const int q = (int)(w & D_Q_MASK);
         bool act = !(w & D_SKIP);
         if (act) act = S.pos[q] > d;                      // only unassigned neighbours are filtered
         W oldD = 0, newD = 0, oldF = 0, newF = 0;
@@ -119,7 +121,7 @@ __device__ __forceinline__ bool fc_apply(const DevTablesT<W>& T, const WarpState
             oldD = S.D[q];
             newD = oldD;
             if (HAS_F) { oldF = S.F[q]; newF = oldF; }
-            const uint32_t kind = (w >> 8) & 3;
+            const uint32_t kind = (w >> D_KIND_SHIFT) & 3;
             if (!HAS_TABLE || kind == D_K_NE_SAME) newD = oldD & ~(W(1) << b);
             else {
                 const W m = __ldg(T.masks + __ldg(T.ent_moff + e) + b);

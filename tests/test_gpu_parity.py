@@ -10,7 +10,8 @@ import pytest
 import oracle_lib as O
 from dequan_b200 import api
 from dequan_b200 import generators as G
-from dequan_b200.model import (CSP, REFERENCE_SUDOKU, Op, OpConstraint, colouring, nqueens, sudoku, sudoku_template)
+from dequan_b200.model import (CSP, AllDifferentConstraint, REFERENCE_SUDOKU, Op, OpConstraint, colouring, nqueens, sudoku,
+                               sudoku_template)
 from randmodels import model_suite, random_model
 
 pytestmark = pytest.mark.gpu
@@ -360,8 +361,8 @@ def test_batches_from_on_disk_formats(product_lib):
 
 
 def test_maximum_sizes_and_limits(product_lib):
-    """254 variables (the engine's limit) with 32-value and 2-value domains; the first size beyond each limit (255
-    variables, 65 values) is refused with an error, not approximated; empty batches are no-ops."""
+    """254 variables (the widest batch template) and 1022 (the engine's limit) with mixed domain sizes; the first size
+    beyond each limit (1023 variables, 65 values) is refused with an error, not approximated; empty batches are no-ops."""
     import random
     rng = random.Random(3)
     csp = CSP()
@@ -374,8 +375,40 @@ def test_maximum_sizes_and_limits(product_lib):
         a, b = rng.sample(range(n), 2)
         csp.AddConstraint(OpConstraint(a, b, Op.NotEqual, rng.choice([0, 1])))
     _cmp_tree(api.Model(csp).solve_tree("first"), O.solve(csp, "first"), "254 variables")
+    # 1022 variables: a ring of different-neighbour constraints with 1100 chords, domains of 3..5 values
+    csp = CSP()
+    n = 1022
+    rng = random.Random(4)
+    for i in range(n):
+        csp.AddIntVar(0, 3 + (i * 7) % 3)
+    for i in range(n):
+        csp.AddConstraint(OpConstraint(i, (i + 1) % n, Op.NotEqual, 0))
+    for _ in range(1100):
+        a, b = rng.sample(range(n), 2)
+        csp.AddConstraint(OpConstraint(a, b, Op.NotEqual, rng.choice([0, 1, -1])))
+    m = api.Model(csp)
+    want = O.solve(csp, "first")
+    _cmp_tree(m.solve_tree("first"), want, "1022 variables")
+    _cmp_tree(m.solve_tree("first", split_depth=5), want, "1022 variables, split")
+    # a 16x16 Sudoku (256 variables on 1..16), 4 of every 7 cells blank: 514 140 nodes to the first solution
+    base = [[(4 * (r % 4) + r // 4 + c) % 16 + 1 for c in range(16)] for r in range(16)]
+    s16 = CSP()
+    for r in range(16):
+        for c in range(16):
+            if (r * 16 + c) % 7 < 4:
+                s16.AddIntVar(1, 17)
+            else:
+                s16.AddFixedVar(base[r][c])
+    groups = [[r * 16 + c for c in range(16)] for r in range(16)] + [[r * 16 + c for r in range(16)] for c in range(16)]
+    groups += [[(4 * (b // 4) + i // 4) * 16 + 4 * (b % 4) + i % 4 for i in range(16)] for b in range(16)]
+    for g in groups:
+        s16.AddConstraint(AllDifferentConstraint(g))
+    s16.FinalizeModel()
+    want = O.solve(s16, "first")
+    assert want.status == "sat" and want.first == [base[r][c] for r in range(16) for c in range(16)]
+    _cmp_tree(api.Model(s16).solve_tree("first"), want, "16x16 sudoku")
     big = CSP()
-    for _ in range(255):
+    for _ in range(1023):
         big.AddIntVar(0, 2)
     with pytest.raises(api.DequanError):
         api.Model(big)
