@@ -54,6 +54,9 @@ enum dq_outcome {
 /* ---- model descriptor ------------------------------------------------------
  * Mirrors CSP::vars / CSP::domains / CSP::constraints (dequan.h:349-354) as
  * flat int32 arrays.  Variable ids are dense 0..n_vars-1 in AddIntVar order.
+ * Device scope: n_vars <= 1022, every domain <= 64 values (templates of the batch entry
+ * points: <= 32 values), binary constraints; beyond it dq_compile / the solve returns
+ * DQ_ERR_UNSUPPORTED.
  */
 enum dq_domain_type {           /* dequan::DomainType (dequan.h:70-74)           */
     DQ_DOM_VALUES = 0,          /* explicit list, iteration = list order          */
