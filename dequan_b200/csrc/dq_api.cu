@@ -366,7 +366,13 @@ static int solve_queens_lane(dq_model* m, const dq_tree_opts* opts, dq_tree_resu
             k_queens_first_warp<<<1, 32, 0, m->stream2>>>(A);
             DQ_CUDA(cudaEventRecord(m->ev_join, m->stream2));
         }
-        for (int l = 0; l < K; l++) {
+        // levels 0 .. head-1 in one single-CTA launch (a few hundred records at most, all above the partition level)
+        const int head = use_buckets ? std::max(0, std::min(std::min(K, part_level), 3)) : 0;
+        if (head > 0) {
+            k_queens_levels_head<<<1, kQueensBlock, 0, m->stream>>>(A, head, buf[0], buf[1], ctrl + 8, opts->part_rank == 0 ? 1 : 0);
+            launches++;
+        }
+        for (int l = head; l < K; l++) {
             const int grid = (int)std::min<double>(std::max(estimate(l) * N / kQueensBlock, 1.0), (double)m->sm_count * 8);
             const int count_nodes = (l > part_level || opts->part_rank == 0) ? 1 : 0;
             k_queens_level<<<grid, kQueensBlock, 0, m->stream>>>(A, l, buf[l & 1], ctrl + 8 + l, buf[(l + 1) & 1], ctrl + 8 + l + 1,
@@ -377,7 +383,7 @@ static int solve_queens_lane(dq_model* m, const dq_tree_opts* opts, dq_tree_resu
             k_queens_bucket<<<ctas, kQueensBucketBlock, smem, m->stream>>>(A);
             DQ_CUDA(cudaEventRecord(m->ev3, m->stream));
             DQ_CUDA(cudaStreamWaitEvent(m->stream, m->ev_join, 0));
-            launches += K + 2;
+            launches += (K - head) + 2;
         } else {
             k_queens_lane<<<ctas, kQueensBlock, smem, m->stream>>>(A);
             DQ_CUDA(cudaEventRecord(m->ev3, m->stream));

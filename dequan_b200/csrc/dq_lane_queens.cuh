@@ -59,19 +59,19 @@ constexpr int kQueensMaxN = 31;       // one spare bit so that ~(a|l|r) of a ful
 // if its forward check leaves no later domain empty the child record is appended (warp-aggregated
 // atomic) to the next frontier.  The launches are queued back to back: the frontier sizes never
 // come back to the host.  On the last level only the children this partition owns are kept.
-__global__ void __launch_bounds__(kQueensBlock)
-k_queens_level(QueensLaneArgs A, int level, const uint4* __restrict__ in, const unsigned long long* __restrict__ n_in_ptr,
-               uint4* __restrict__ out, unsigned long long* __restrict__ n_out_ptr, int count_nodes, int filter_partition) {
+template <bool IN_IS_READ_ONLY>
+__device__ __forceinline__ void queens_level_body(const QueensLaneArgs& A, int level, const uint4* __restrict__ in, unsigned long long n_found,
+                                                  uint4* __restrict__ out, unsigned long long* __restrict__ n_out_ptr, int count_nodes,
+                                                  int filter_partition, uint32_t* s_cnt, unsigned long long* s_base_p) {
     const int lane = threadIdx.x & 31;
     const uint32_t lt = (1u << lane) - 1u;
     const int N = A.n;
     const uint32_t full = (1u << N) - 1u;
-    const unsigned long long n_in = min(*n_in_ptr, A.record_cap);
+    const unsigned long long n_in = min(n_found, A.record_cap);
     const unsigned long long pairs = n_in * (unsigned long long)N;
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     unsigned long long tot_nodes = 0;
-    __shared__ uint32_t s_cnt[kQueensBlock / 32];
-    __shared__ unsigned long long s_base;
+    unsigned long long& s_base = *s_base_p;
     const unsigned long long first = (unsigned long long)blockIdx.x * blockDim.x;
     for (unsigned long long tile = first; tile < pairs; tile += stride) {      // CTA-uniform trip count
         const unsigned long long base = tile + (threadIdx.x & ~31);
@@ -81,7 +81,8 @@ k_queens_level(QueensLaneArgs A, int level, const uint4* __restrict__ in, const 
         if (valid) {
             const uint32_t rix = (uint32_t)p / (uint32_t)N;                    // pairs < 2^32 (host caps the record list)
             const uint32_t v = (uint32_t)p - rix * N;
-            const uint4 rec = __ldg(in + rix);
+            // (the fused head kernel reads records it wrote itself one level earlier: no read-only cache path there)
+            const uint4 rec = IN_IS_READ_ONLY ? __ldg(in + rix) : __ldcg(in + rix);
             const uint32_t bit = 1u << v;
             valid = (full & ~(rec.y | rec.z | rec.w) & bit) != 0;               // value in the current domain
             if (valid) {
@@ -118,6 +119,30 @@ k_queens_level(QueensLaneArgs A, int level, const uint4* __restrict__ in, const 
     if (count_nodes) {
         for (int o = 16; o > 0; o >>= 1) tot_nodes += __shfl_down_sync(0xFFFFFFFFu, tot_nodes, o);
         if (lane == 0 && tot_nodes) atomicAdd(A.totals + 1, tot_nodes);
+    }
+}
+
+__global__ void __launch_bounds__(kQueensBlock)
+k_queens_level(QueensLaneArgs A, int level, const uint4* __restrict__ in, const unsigned long long* __restrict__ n_in_ptr,
+               uint4* __restrict__ out, unsigned long long* __restrict__ n_out_ptr, int count_nodes, int filter_partition) {
+    __shared__ uint32_t s_cnt[kQueensBlock / 32];
+    __shared__ unsigned long long s_base;
+    queens_level_body<true>(A, level, in, *n_in_ptr, out, n_out_ptr, count_nodes, filter_partition, s_cnt, &s_base);
+}
+
+// The first levels hold a handful of records (1, N, about N^2 / 1.2): ONE CTA walks levels 0 .. n_levels-1 back to back
+// instead of one launch each (a launch costs more than these levels' work).  buf0 / buf1 alternate as in the host loop,
+// sizes[l] is the frontier size at depth l.
+__global__ void __launch_bounds__(kQueensBlock)
+k_queens_levels_head(QueensLaneArgs A, int n_levels, uint4* __restrict__ buf0, uint4* __restrict__ buf1,
+                     unsigned long long* __restrict__ sizes, int count_nodes) {
+    __shared__ uint32_t s_cnt[kQueensBlock / 32];
+    __shared__ unsigned long long s_base;
+    for (int l = 0; l < n_levels; l++) {
+        const unsigned long long n_in = *(volatile unsigned long long*)(sizes + l);
+        queens_level_body<false>(A, l, (l & 1) ? buf1 : buf0, n_in, (l & 1) ? buf0 : buf1, sizes + l + 1, count_nodes, 0, s_cnt, &s_base);
+        __threadfence();
+        __syncthreads();                                 // the children and their count are visible to the whole CTA
     }
 }
 
