@@ -235,8 +235,6 @@ def main():
                     tot += dt
                     kern += loc.kernel_ms
                     launches += loc.launches
-                    dom["ms"] += loc.search_kernel_ms
-                    dom["frontier_nodes"], dom["records"] = loc.frontier_nodes, loc.n_prefixes
             if world > 1:
                 t = torch.tensor([tot, kern], dtype=torch.float64, device=dev)
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -244,6 +242,16 @@ def main():
             return tot, kern, launches
 
         tot, kern_ms, launches = timed_steps(lambda: solve_step(model), steps, warmup)
+        # roofline leg: the search kernel's own duration from CUDA events on its stream (DQ_TREE_TIME_KERNELS; the steps
+        # above replay the solve as one CUDA graph, whose inner events cannot be read back)
+        dom["ms"] = 0.0
+        for i in range(steps):
+            flush.fill_(i & 0xFF)
+            sync_all()
+            loc = model.solve_tree("count", part_rank=rank, part_count=world, engine=args.engine, time_kernels=True)
+            assert (loc.solutions, loc.nodes) == (want_sols, want_nodes) or world > 1
+            dom["ms"] += loc.search_kernel_ms
+            dom["frontier_nodes"], dom["records"] = loc.frontier_nodes, loc.n_prefixes
         dom_ms, dom_frontier, dom_records = dom["ms"], dom["frontier_nodes"], dom["records"]
         desc_keep = csp.desc()          # the host-side flat descriptor: the input buffers of the C-ABI call
 

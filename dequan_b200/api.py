@@ -33,7 +33,7 @@ class DequanError(RuntimeError):
 
 class dq_tree_opts(C.Structure):
     _fields_ = [("mode", C.c_int32), ("split_depth", C.c_int32), ("part_rank", C.c_int32), ("part_count", C.c_int32),
-                ("node_budget", C.c_uint64), ("engine", C.c_int32), ("reserved", C.c_int32)]
+                ("node_budget", C.c_uint64), ("engine", C.c_int32), ("flags", C.c_int32)]
 
 
 class dq_tree_result(C.Structure):
@@ -184,9 +184,10 @@ class Model:
         return o[:self.n_vars].tolist()
 
     def solve_tree(self, mode: str = "first", split_depth: int = 0, part_rank: int = 0, part_count: int = 1,
-                   engine: str = "auto", node_budget: int = 0) -> TreeResult:
+                   engine: str = "auto", node_budget: int = 0, time_kernels: bool = False) -> TreeResult:
+        """time_kernels: DQ_TREE_TIME_KERNELS (search_kernel_ms from CUDA events; the queue is not replayed as a graph)."""
         o = dq_tree_opts(DQ_MODE_COUNT_ALL if mode == "count" else DQ_MODE_FIRST, split_depth, part_rank, part_count,
-                         node_budget, ENGINE[engine], 0)
+                         node_budget, ENGINE[engine], 1 if time_kernels else 0)
         r = dq_tree_result()
         first = np.zeros(max(self.n_vars, 1), dtype=np.int32)
         _check(lib().dq_solve_tree(self._h, C.byref(o), C.byref(r), first.ctypes.data_as(C.POINTER(C.c_int32))))

@@ -97,6 +97,7 @@ struct DeviceCtx {
     cudaStream_t stream = nullptr, stream2 = nullptr;          // stream2: side work that overlaps the main queue
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;          // ordering only (no timing)
+    unsigned long long* pin = nullptr;                         // 1 KB of pinned host memory: control words of the queued solves
 };
 static thread_local std::vector<DeviceCtx> g_ctx;
 static cudaError_t device_ctx(DeviceCtx** out) {
@@ -115,6 +116,7 @@ static cudaError_t device_ctx(DeviceCtx** out) {
     if ((e = cudaStreamCreateWithFlags(&c.stream2, cudaStreamNonBlocking)) != cudaSuccess) return e;
     if ((e = cudaEventCreateWithFlags(&c.ev_fork, cudaEventDisableTiming)) != cudaSuccess) return e;
     if ((e = cudaEventCreateWithFlags(&c.ev_join, cudaEventDisableTiming)) != cudaSuccess) return e;
+    if ((e = cudaHostAlloc((void**)&c.pin, 1024, cudaHostAllocDefault)) != cudaSuccess) return e;
     g_ctx.push_back(c);
     *out = &g_ctx.back();
     return cudaSuccess;
@@ -137,6 +139,10 @@ struct dq_model {
     bool uploaded = false;
     cudaStream_t stream = nullptr, stream2 = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, ev_fork = nullptr, ev_join = nullptr;
+    unsigned long long* pin = nullptr;          // pinned control words (DeviceCtx)
+    // the queue of one N-Queens solve (copies, level kernels, search, first solution) as an instantiated CUDA graph
+    cudaGraphExec_t q_exec = nullptr;
+    unsigned long long q_exec_key[6] = {0, 0, 0, 0, 0, 0}, q_seen_key[6] = {0, 0, 0, 0, 0, 0};
     int sm_count = 0;
     // model tables in HBM
     DevBuf<uint8_t> d_blob;                     // all tables, one block
@@ -162,7 +168,6 @@ struct dq_model {
     // lane engine scratch
     DevBuf<uint4> q_records, q_records2;
     DevBuf<uint8_t> q_first;
-    uint8_t h_first[32] = {0};
     // batch scratch
     DevBuf<uint8_t> b_cells, b_solution, b_status;
     DevBuf<unsigned long long> b_nodes;
@@ -186,6 +191,7 @@ static int upload(dq_model* m) {
     DQ_CUDA(device_ctx(&ctx));
     m->sm_count = ctx->sm_count; m->stream = ctx->stream; m->ev0 = ctx->ev0; m->ev1 = ctx->ev1; m->ev2 = ctx->ev2; m->ev3 = ctx->ev3;
     m->stream2 = ctx->stream2; m->ev_fork = ctx->ev_fork; m->ev_join = ctx->ev_join;
+    m->pin = ctx->pin;
     const CompiledModel& c = m->cm;
     const int nv = c.nv;
     // every table goes into ONE device block with ONE stream-ordered copy (the solve's kernels follow on the same stream)
@@ -331,10 +337,19 @@ static int solve_queens_lane(dq_model* m, const dq_tree_opts* opts, dq_tree_resu
     DQ_CUDA(m->q_first.reserve(32));
     DQ_CUDA(m->d_ctrl.reserve(32));
     size_t cap = std::max<size_t>(m->q_records.cap, (size_t)std::min(std::max(2.0 * estimate(K), 1024.0), 64.0 * 1024 * 1024));
-    unsigned long long h_ctrl[32];
+    // control words live in pinned host memory that outlives the call: the queue below may be replayed as a CUDA graph
+    unsigned long long* h_init = m->pin;              // [32] initial control block
+    uint4* h_root = reinterpret_cast<uint4*>(m->pin + 32);
+    unsigned long long* h_ctrl = m->pin + 40;         // [32] control block read back
+    uint8_t* h_first = reinterpret_cast<uint8_t*>(m->pin + 72);   // [32]
     unsigned long long* ctrl = m->d_ctrl.p;     // [0]=cursor [1]=sols [2]=nodes [3]=best [8+l]=frontier size at depth l
     unsigned long long launches = 0, h_frontier_nodes = 0;
     float ms_total = 0, ms_search = 0;
+    const char* env_pl = getenv("DQ_QUEENS_PART_LEVEL");
+    const int part_level = std::min(K - 1, env_pl ? atoi(env_pl) : 4);     // measured: depth-5 keys balance 2/4/8 partitions within 3 %
+    // levels 0 .. head-1 in one single-CTA launch (a few hundred records at most, all above the partition level)
+    const int head = use_buckets ? std::max(0, std::min(std::min(K, part_level), 3)) : 0;
+    static const bool use_graph = getenv("DQ_NO_GRAPH") == nullptr;
     for (int attempt = 0; attempt < 3; attempt++) {
         DQ_CUDA(m->q_records.reserve(cap));
         DQ_CUDA(m->q_records2.reserve(m->q_records.cap));
@@ -343,62 +358,98 @@ static int solve_queens_lane(dq_model* m, const dq_tree_opts* opts, dq_tree_resu
         QueensLaneArgs A;
         A.n = N; A.k = K;
         A.part_rank = opts->part_rank; A.part_count = opts->part_count;
+        A.part_level = part_level;
         A.records = buf[K & 1]; A.record_cap = rcap; A.n_records = ctrl + 8 + K;
         A.cursor = ctrl + 0; A.totals = ctrl + 1; A.best_key = ctrl + 3; A.dfs_nodes = ctrl + 24;
         A.first_out = m->q_first.p;
-        unsigned long long init[32] = {0};
-        init[3] = KEY_NONE;
-        init[8] = (K > 0 || opts->part_rank == 0) ? 1 : 0;   // the root prefix (key 0) belongs to partition 0
-        const uint4 root = make_uint4(0, 0, 0, 0);
-        DQ_CUDA(cudaMemcpyAsync(ctrl, init, sizeof init, cudaMemcpyHostToDevice, m->stream));
-        DQ_CUDA(cudaMemcpyAsync(buf[0], &root, sizeof root, cudaMemcpyHostToDevice, m->stream));
-        DQ_CUDA(cudaEventRecord(m->ev0, m->stream));
+        for (int i = 0; i < 32; i++) h_init[i] = 0;
+        h_init[3] = KEY_NONE;
+        h_init[8] = (K > 0 || opts->part_rank == 0) ? 1 : 0;   // the root prefix (key 0) belongs to partition 0
+        *h_root = make_uint4(0, 0, 0, 0);
+
+        // The queue of one solve: nothing in it comes back to the host before the end.
         // Multi-GPU: the frontier is dealt to the partitions (key mod parts) as soon as it is wide enough to balance —
         // below that level every partition expands only its own records, above it all of them expand the same few
         // hundred thousand records and partition 0 alone counts their nodes.
-        const char* env_pl = getenv("DQ_QUEENS_PART_LEVEL");
-        const int part_level = std::min(K - 1, env_pl ? atoi(env_pl) : 4);     // measured: depth-5 keys balance 2/4/8 partitions within 3 %
-        A.part_level = part_level;
-        if (use_buckets) {
-            // the DFS-first solution needs nothing from the frontier: one warp looks for it on the side stream
-            DQ_CUDA(cudaEventRecord(m->ev_fork, m->stream));
-            DQ_CUDA(cudaStreamWaitEvent(m->stream2, m->ev_fork, 0));
-            k_queens_first_warp<<<1, 32, 0, m->stream2>>>(A);
-            DQ_CUDA(cudaEventRecord(m->ev_join, m->stream2));
+        // (timing events cannot be read back from inside a graph: the graph is bracketed by ev0 / ev1 from outside, and the
+        // per-kernel pair ev2 / ev3 exists only in the call-by-call queue, DQ_TREE_TIME_KERNELS)
+        auto enqueue = [&](const bool with_events) -> int {
+            if (with_events) DQ_CUDA(cudaEventRecord(m->ev0, m->stream));
+            DQ_CUDA(cudaMemcpyAsync(ctrl, h_init, 32 * sizeof(unsigned long long), cudaMemcpyHostToDevice, m->stream));
+            DQ_CUDA(cudaMemcpyAsync(buf[0], h_root, sizeof(uint4), cudaMemcpyHostToDevice, m->stream));
+            if (use_buckets) {
+                // the DFS-first solution needs nothing from the frontier: one warp looks for it on the side stream
+                DQ_CUDA(cudaEventRecord(m->ev_fork, m->stream));
+                DQ_CUDA(cudaStreamWaitEvent(m->stream2, m->ev_fork, 0));
+                k_queens_first_warp<<<1, 32, 0, m->stream2>>>(A);
+                DQ_CUDA(cudaEventRecord(m->ev_join, m->stream2));
+            }
+            if (head > 0)
+                k_queens_levels_head<<<1, kQueensBlock, 0, m->stream>>>(A, head, buf[0], buf[1], ctrl + 8, opts->part_rank == 0 ? 1 : 0);
+            for (int l = head; l < K; l++) {
+                const int grid = (int)std::min<double>(std::max(estimate(l) * N / kQueensBlock, 1.0), (double)m->sm_count * 8);
+                const int count_nodes = (l > part_level || opts->part_rank == 0) ? 1 : 0;
+                k_queens_level<<<grid, kQueensBlock, 0, m->stream>>>(A, l, buf[l & 1], ctrl + 8 + l, buf[(l + 1) & 1], ctrl + 8 + l + 1,
+                                                                       count_nodes, (l == part_level && opts->part_count > 1) ? 1 : 0);
+            }
+            if (with_events) DQ_CUDA(cudaEventRecord(m->ev2, m->stream));
+            if (use_buckets) {
+                k_queens_bucket<<<ctas, kQueensBucketBlock, smem, m->stream>>>(A);
+                if (with_events) DQ_CUDA(cudaEventRecord(m->ev3, m->stream));
+                DQ_CUDA(cudaStreamWaitEvent(m->stream, m->ev_join, 0));
+            } else {
+                k_queens_lane<<<ctas, kQueensBlock, smem, m->stream>>>(A);
+                if (with_events) DQ_CUDA(cudaEventRecord(m->ev3, m->stream));
+                k_queens_first<<<1, 32, 0, m->stream>>>(A);
+            }
+            DQ_CUDA(cudaGetLastError());
+            DQ_CUDA(cudaMemcpyAsync(h_ctrl, ctrl, 32 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, m->stream));
+            DQ_CUDA(cudaMemcpyAsync(h_first, m->q_first.p, 32, cudaMemcpyDeviceToHost, m->stream));
+            if (with_events) DQ_CUDA(cudaEventRecord(m->ev1, m->stream));
+            return DQ_OK;
+        };
+        launches += (use_buckets ? (K - head) + (head > 0 ? 1 : 0) + 2 : K + 2);
+
+        // One graph launch instead of ~20 API calls (a 14-Queens solve is 0.16 ms of kernels): the queue is captured once
+        // per (model, split, partition, buffers) and replayed; anything that changes one of those re-captures it.
+        bool queued = false;
+        const bool time_kernels = (opts->flags & DQ_TREE_TIME_KERNELS) != 0;
+        if (use_graph && use_buckets && !time_kernels) {
+            const unsigned long long key[6] = {(unsigned long long)K | ((unsigned long long)opts->part_rank << 16) | ((unsigned long long)opts->part_count << 32),
+                                               (unsigned long long)rcap, (unsigned long long)(uintptr_t)buf[0], (unsigned long long)(uintptr_t)buf[1],
+                                               (unsigned long long)(uintptr_t)ctrl, (unsigned long long)(uintptr_t)m->q_first.p};
+            // a model solved once (the drop-in path compiles, solves, frees) is not worth a capture: the graph is built when
+            // the same queue comes round a second time
+            const bool seen = memcmp(key, m->q_seen_key, sizeof key) == 0;
+            memcpy(m->q_seen_key, key, sizeof key);
+            if (seen && (!m->q_exec || memcmp(key, m->q_exec_key, sizeof key) != 0)) {
+                if (m->q_exec) { cudaGraphExecDestroy(m->q_exec); m->q_exec = nullptr; }
+                cudaGraph_t graph = nullptr;
+                if (cudaStreamBeginCapture(m->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+                    const int qrc = enqueue(false);
+                    const cudaError_t ce = cudaStreamEndCapture(m->stream, &graph);
+                    if (qrc == DQ_OK && ce == cudaSuccess && graph && cudaGraphInstantiate(&m->q_exec, graph, 0) == cudaSuccess)
+                        memcpy(m->q_exec_key, key, sizeof key);
+                    else m->q_exec = nullptr;
+                    if (graph) cudaGraphDestroy(graph);
+                }
+                (void)cudaGetLastError();                      // a failed capture falls back to the plain queue below
+            }
+            if (m->q_exec && memcmp(key, m->q_exec_key, sizeof key) == 0) {
+                DQ_CUDA(cudaEventRecord(m->ev0, m->stream));
+                if (cudaGraphLaunch(m->q_exec, m->stream) == cudaSuccess) { queued = true; DQ_CUDA(cudaEventRecord(m->ev1, m->stream)); }
+                else (void)cudaGetLastError();
+            }
         }
-        // levels 0 .. head-1 in one single-CTA launch (a few hundred records at most, all above the partition level)
-        const int head = use_buckets ? std::max(0, std::min(std::min(K, part_level), 3)) : 0;
-        if (head > 0) {
-            k_queens_levels_head<<<1, kQueensBlock, 0, m->stream>>>(A, head, buf[0], buf[1], ctrl + 8, opts->part_rank == 0 ? 1 : 0);
-            launches++;
+        if (!queued) {
+            rc = enqueue(true);
+            if (rc != DQ_OK) return rc;
         }
-        for (int l = head; l < K; l++) {
-            const int grid = (int)std::min<double>(std::max(estimate(l) * N / kQueensBlock, 1.0), (double)m->sm_count * 8);
-            const int count_nodes = (l > part_level || opts->part_rank == 0) ? 1 : 0;
-            k_queens_level<<<grid, kQueensBlock, 0, m->stream>>>(A, l, buf[l & 1], ctrl + 8 + l, buf[(l + 1) & 1], ctrl + 8 + l + 1,
-                                                                   count_nodes, (l == part_level && opts->part_count > 1) ? 1 : 0);
-        }
-        DQ_CUDA(cudaEventRecord(m->ev2, m->stream));
-        if (use_buckets) {
-            k_queens_bucket<<<ctas, kQueensBucketBlock, smem, m->stream>>>(A);
-            DQ_CUDA(cudaEventRecord(m->ev3, m->stream));
-            DQ_CUDA(cudaStreamWaitEvent(m->stream, m->ev_join, 0));
-            launches += (K - head) + 2;
-        } else {
-            k_queens_lane<<<ctas, kQueensBlock, smem, m->stream>>>(A);
-            DQ_CUDA(cudaEventRecord(m->ev3, m->stream));
-            k_queens_first<<<1, 32, 0, m->stream>>>(A);
-            launches += K + 2;
-        }
-        DQ_CUDA(cudaGetLastError());
-        DQ_CUDA(cudaEventRecord(m->ev1, m->stream));
-        DQ_CUDA(cudaMemcpyAsync(h_ctrl, ctrl, sizeof h_ctrl, cudaMemcpyDeviceToHost, m->stream));
-        DQ_CUDA(cudaMemcpyAsync(m->h_first, m->q_first.p, 32, cudaMemcpyDeviceToHost, m->stream));
         DQ_CUDA(cudaStreamSynchronize(m->stream));
         float ms = 0;
         DQ_CUDA(cudaEventElapsedTime(&ms, m->ev0, m->ev1));
         ms_total += ms;
-        DQ_CUDA(cudaEventElapsedTime(&ms_search, m->ev2, m->ev3));
+        if (!queued) DQ_CUDA(cudaEventElapsedTime(&ms_search, m->ev2, m->ev3));
         h_frontier_nodes = h_ctrl[2];
         unsigned long long biggest = 0;
         for (int l = 0; l <= K; l++) biggest = std::max(biggest, h_ctrl[8 + l]);
@@ -420,7 +471,7 @@ static int solve_queens_lane(dq_model* m, const dq_tree_opts* opts, dq_tree_resu
     res->outcome = res->n_solutions ? DQ_SAT : DQ_UNSAT;
     m->last_n_prefix = 0; m->last_depth = 0;
     if (h_ctrl[3] != KEY_NONE && first_solution)
-        for (int v = 0; v < N; v++) first_solution[v] = m->cm.values[v][m->h_first[v]];
+        for (int v = 0; v < N; v++) first_solution[v] = m->cm.values[v][h_first[v]];
     return DQ_OK;
 }
 
@@ -461,6 +512,7 @@ int dq_compile(const dq_model_desc* desc, dq_model** out) {
 
 void dq_free(dq_model* m) {
     if (!m) return;
+    if (m->q_exec) { cudaGraphExecDestroy(m->q_exec); m->q_exec = nullptr; }
     if (m->uploaded) {
         m->d_blob.release(); m->d_ctrl.release();
         m->d_sub_nodes.release(); m->d_sol_key.release(); m->d_sol.release();

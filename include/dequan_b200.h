@@ -118,8 +118,13 @@ typedef struct dq_tree_opts {
     int32_t  part_count;     /* number of partitions         (1 for single GPU)     */
     uint64_t node_budget;    /* 0 = unlimited (FIRST mode only)                     */
     int32_t  engine;         /* dq_engine                                           */
-    int32_t  reserved;
+    int32_t  flags;          /* DQ_TREE_* bits                                      */
 } dq_tree_opts;
+
+/* dq_tree_opts.flags: fill dq_tree_result.search_kernel_ms (CUDA events around the search kernel).  The solve is then
+ * queued call by call; without the flag the N-Queens engine replays its queue as one CUDA graph and reports only
+ * kernel_ms, measured around the graph.                                                                         */
+#define DQ_TREE_TIME_KERNELS 1
 
 typedef struct dq_tree_result {
     int32_t  outcome;        /* dq_outcome (COUNT_ALL: SAT iff n_solutions>0)       */

@@ -8,8 +8,8 @@ for n in (10, 12, 13, 14, 15, 16, 17, 18):
     for k in (2, 3, 4, 5, 6, 7, 8):
         if (n >= 17 and k < 4) or k > n - 3: continue
         try:
-            r = m.solve_tree("count", engine="lane", split_depth=k)
-            r = m.solve_tree("count", engine="lane", split_depth=k)
+            r = m.solve_tree("count", engine="lane", split_depth=k, time_kernels=True)
+            r = m.solve_tree("count", engine="lane", split_depth=k, time_kernels=True)
             print(f"N={n} K={k} records={r.n_prefixes} ms={r.kernel_ms:.3f} search_ms={r.search_kernel_ms:.3f} Gnodes/s={r.nodes/r.kernel_ms/1e6:.1f} sols={r.solutions} nodes={r.nodes}", flush=True)
         except Exception as e:
             print(n, k, "EXC", e, flush=True)
