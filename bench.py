@@ -360,10 +360,18 @@ def roofline_queens(n, world, nodes, frontier_nodes, records, lane_ms, int_peak,
             "note": "not HBM- or tensor-bound: no dense contraction on this path, one 16 B record per subtree from HBM"}
 
 
+# ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum summed over the seven kernels of one 1 M-puzzle pipeline pass
+# (profiles/r1_ncu_sudoku_1M.txt): 869 MB read + 687 MB written, of which 288 B per puzzle are the digest (written once, a
+# local-memory spill in k_sudoku_digest doubles that write) and the rest task / snapshot records of the counting stage
+NCU_SUDOKU_TRAFFIC_1M = 869624832 + 687312384
+
+
 def sudoku_rooflines(out, hbm_peak, peak_src, int_peak):
     kpps, nps = out.pop("_kernel_pps"), out["nodes_per_sec"]
     out["roofline"] = {"bound": "hbm", "achieved": kpps * 174 / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                       "frac": kpps * 174 / 1e9 / hbm_peak, "traffic": None, "bytes_per_puzzle": 174, "peak_source": peak_src,
+                       "frac": kpps * 174 / 1e9 / hbm_peak,
+                       "traffic": NCU_SUDOKU_TRAFFIC_1M if out.get("shard", out["n"]) == 1_000_000 else None,
+                       "algorithmic_bytes": 174 * out.get("shard", out["n"]), "bytes_per_puzzle": 174, "peak_source": peak_src,
                        "note": "instance stream only; the search itself is integer-issue bound (see roofline_int)"}
     out["roofline_int"] = {"ops_per_node": 2 * 10 + 4, "achieved": nps * 24 / 1e12, "peak": int_peak / 1e12, "unit": "Tlane-op/s",
                            "frac": nps * 24 / int_peak}
