@@ -602,3 +602,26 @@ def test_previous_queens_engine_still_agrees(product_lib):
         n = int(line.split()[0])
         g = O.solve(nqueens(n), "count")
         assert line.startswith(f"{n} {g.solutions} {g.nodes} {g.first}"), line
+
+
+def test_queens_graph_replay_and_recapture(product_lib):
+    """The N-Queens solve queue is replayed as a CUDA graph from the second identical solve on; a change of split depth
+    or partition re-captures it.  Every call returns the same exact counts."""
+    csp = nqueens(12)
+    g = O.solve(csp, "count")
+    m = api.Model(csp)
+    for _ in range(4):                                          # call-by-call, capture, replay, replay
+        r = m.solve_tree("count")
+        assert (r.solutions, r.nodes, r.first) == (g.solutions, g.nodes, g.first)
+    for rounds in range(2):
+        parts = [m.solve_tree("count", part_rank=k, part_count=2) for k in (0, 1, 0, 1)]
+        assert (parts[0].solutions + parts[1].solutions, parts[0].nodes + parts[1].nodes) == (g.solutions, g.nodes)
+        assert (parts[2].solutions, parts[2].nodes, parts[3].solutions, parts[3].nodes) == \
+               (parts[0].solutions, parts[0].nodes, parts[1].solutions, parts[1].nodes)
+        for depth in (4, 6, 4, 4):
+            r = m.solve_tree("count", split_depth=depth)
+            assert (r.solutions, r.nodes, r.first) == (g.solutions, g.nodes, g.first), depth
+    t = m.solve_tree("count", time_kernels=True)
+    assert (t.solutions, t.nodes) == (g.solutions, g.nodes) and t.search_kernel_ms > 0
+    m.solve_tree("count")                                        # first time round for this queue again: call by call
+    assert m.solve_tree("count").search_kernel_ms == 0          # replayed: the graph is timed from outside only
