@@ -323,9 +323,17 @@ static int solve_queens_lane(dq_model* m, const dq_tree_opts* opts, dq_tree_resu
     int occ = 0;
     int rc = DQ_OK;
     if (opts->split_depth > 0) K = std::min(opts->split_depth, std::min(N - 2, 12));
-    else K = std::max(std::min(N - 7, N <= 15 ? 6 : 7), 0);
+    else {
+        K = std::max(std::min(N - 7, N <= 15 ? 6 : 7), 0);
+        // a partition of a strongly scaled solve (multi-GPU) holds 1/parts of the records: one level deeper keeps the
+        // bucket pools fed to the end (17-Queens, 8 partitions: 2.57 -> 2.46 ms each; scripts/parts_k.py)
+        if (opts->part_count >= 4 && N >= 17 && !(getenv("DQ_QUEENS_ENGINE") && !strcmp(getenv("DQ_QUEENS_ENGINE"), "lane"))) K = 8;
+    }
     auto key_space = [&](int k) { double keys = 1; for (int i = 0; i < k; i++) keys *= N; return keys; };
-    while (K > 0 && key_space(K) > 4.0e9) K--;               // prefix keys are 32-bit (res->split_depth_used reports K)
+    // the lane engine reads 32-bit prefix keys from its records; the bucket search reads none (its first-solution warp
+    // computes 64-bit keys, and the partition deal happens at depth <= 5), so its split may go deeper
+    const bool deep_ok = !(getenv("DQ_QUEENS_ENGINE") && !strcmp(getenv("DQ_QUEENS_ENGINE"), "lane"));
+    while (K > 0 && !deep_ok && key_space(K) > 4.0e9) K--;   // (res->split_depth_used reports K)
     // the search kernel: depth-bucketed warp pools (default) or the older lane-per-subtree stacks (DQ_QUEENS_ENGINE=lane)
     static const bool use_buckets = !(getenv("DQ_QUEENS_ENGINE") && !strcmp(getenv("DQ_QUEENS_ENGINE"), "lane"));
     const size_t smem = use_buckets ? (size_t)(kQueensBucketBlock / 32) * (N - 1 - K) * kQueensBucketCap * sizeof(uint4) : dfs_smem(K);

@@ -385,8 +385,9 @@ __device__ __forceinline__ void queens_first_owned(const QueensLaneArgs& A, int 
     const uint32_t full = (1u << N) - 1u;
     const int own_depth = A.part_level + 1;              // prefixes of this depth are dealt to the partitions by key
     if (A.part_count > 1 && own_depth <= 0 && A.part_rank != 0) return;
-    uint32_t fa = 0, fl = 0, fr = 0, fc = 0, fkey = 0, fv = 0;
-    uint32_t a = 0, l = 0, r = 0, cand = full, key = 0;
+    uint32_t fa = 0, fl = 0, fr = 0, fc = 0, fv = 0;
+    unsigned long long fkey = 0, key = 0;                // 64-bit: N^k outgrows 32 bits from k = 8 on (N = 17)
+    uint32_t a = 0, l = 0, r = 0, cand = full;
     int d = 0;
     for (;;) {
         if (cand == 0) {                                 // every value tried at this depth
@@ -402,13 +403,13 @@ __device__ __forceinline__ void queens_first_owned(const QueensLaneArgs& A, int 
         const uint32_t na = a | bit, nl = (l | bit) << 1, nr = (r | bit) >> 1;
         const bool wiped = lane < N - 1 - d && ((na | ~full) | (nl << lane) | (nr >> lane)) == 0xFFFFFFFFu;
         if (__any_sync(0xFFFFFFFFu, wiped)) continue;
-        const uint32_t kchild = d < K ? key * (uint32_t)N + v : key;      // the key stops growing at depth k
-        if (A.part_count > 1 && d + 1 == own_depth && (kchild % (uint32_t)A.part_count) != (uint32_t)A.part_rank) continue;
+        const unsigned long long kchild = d < K ? key * (unsigned long long)N + v : key;      // the key stops growing at depth k
+        if (A.part_count > 1 && d + 1 == own_depth && (uint32_t)(kchild % (unsigned long long)A.part_count) != (uint32_t)A.part_rank) continue;
         if (lane == d) { fa = a; fl = l; fr = r; fc = cand; fkey = key; fv = v; }
         if (d == N - 2) {
             if (lane == N - 1) fv = (uint32_t)__ffs((int)(full & ~(na | nl | nr))) - 1u;
             if (lane < N) A.first_out[lane] = (uint8_t)fv;
-            if (lane == 0) *A.best_key = (unsigned long long)kchild;
+            if (lane == 0) *A.best_key = kchild;
             return;
         }
         a = na; l = nl; r = nr; cand = full & ~(na | nl | nr); key = kchild;

@@ -1,0 +1,16 @@
+"""17-Queens: per-partition kernel time at split depths 7 and 8, for 1 and 8 partitions emulated on one GPU."""
+import sys, os
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from dequan_b200 import api
+from dequan_b200.model import nqueens
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 17
+m = api.Model(nqueens(n))
+for k in (7, 8, 9):
+    for world in (1, 8):
+        tot_s = tot_n = 0; times = []; srch = []
+        for r in range(world):
+            m.solve_tree("count", part_rank=r, part_count=world, split_depth=k)
+            x = m.solve_tree("count", part_rank=r, part_count=world, split_depth=k, time_kernels=True)
+            tot_s += x.solutions; tot_n += x.nodes; times.append(x.kernel_ms); srch.append(x.search_kernel_ms)
+        print(f"K={k} used={x.split_depth} parts={world} sols={tot_s} nodes={tot_n} max_ms={max(times):.3f} mean_ms={sum(times)/world:.3f} search_max={max(srch):.3f} records={x.n_prefixes}", flush=True)
