@@ -397,6 +397,12 @@ static int solve_queens_lane(dq_model* m, const dq_tree_opts* opts, dq_tree_resu
             for (int l = head; l < K; l++) {
                 const int grid = (int)std::min<double>(std::max(estimate(l) * N / kQueensBlock, 1.0), (double)m->sm_count * 8);
                 const int count_nodes = (l > part_level || opts->part_rank == 0) ? 1 : 0;
+                // wide frontiers: lane per record (k_queens_level_wide); narrow ones: lane per (record, value) pair
+                if (use_buckets && estimate(l) >= 150000.0) {      // (below that the pair kernel's single trip has the shorter latency)
+                    const int wgrid = (int)std::min<double>(std::max(estimate(l) / kQueensBlock, 1.0), (double)m->sm_count * 8);
+                    k_queens_level_wide<<<wgrid, kQueensBlock, 0, m->stream>>>(A, l, buf[l & 1], ctrl + 8 + l, buf[(l + 1) & 1], ctrl + 8 + l + 1,
+                                                                                count_nodes, (l == part_level && opts->part_count > 1) ? 1 : 0);
+                } else
                 k_queens_level<<<grid, kQueensBlock, 0, m->stream>>>(A, l, buf[l & 1], ctrl + 8 + l, buf[(l + 1) & 1], ctrl + 8 + l + 1,
                                                                        count_nodes, (l == part_level && opts->part_count > 1) ? 1 : 0);
             }

@@ -130,6 +130,75 @@ k_queens_level(QueensLaneArgs A, int level, const uint4* __restrict__ in, const 
     queens_level_body<true>(A, level, in, *n_in_ptr, out, n_out_ptr, count_nodes, filter_partition, s_cnt, &s_base);
 }
 
+// The same level step for WIDE frontiers (tens of thousands of records and more): one lane per RECORD instead of one
+// per (record, value) pair — with N = 17 only about three of a record's seventeen values are in its domain, so the
+// pair layout idles four lanes in five.  Pass 1 forward-checks the record's candidate values one per trip (the trip
+// count is the warp's largest domain) and keeps the survivors as a bit mask; the CTA then reserves its output range
+// with ONE atomic; pass 2 writes the children trip-major, so that each trip's stores are contiguous.
+__global__ void __launch_bounds__(kQueensBlock)
+k_queens_level_wide(QueensLaneArgs A, int level, const uint4* __restrict__ in, const unsigned long long* __restrict__ n_in_ptr,
+                    uint4* __restrict__ out, unsigned long long* __restrict__ n_out_ptr, int count_nodes, int filter_partition) {
+    __shared__ uint32_t s_cnt[kQueensBlock / 32];
+    __shared__ unsigned long long s_base;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint32_t lt = (1u << lane) - 1u;
+    const int N = A.n;
+    const uint32_t full = (1u << N) - 1u;
+    const int last = N - 2 - level;
+    const unsigned long long n_in = min(*n_in_ptr, A.record_cap);
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    unsigned long long tot_nodes = 0;
+    for (unsigned long long tile = (unsigned long long)blockIdx.x * blockDim.x; tile < n_in; tile += stride) {   // CTA-uniform trip count
+        const unsigned long long rix = tile + threadIdx.x;
+        uint4 rec = make_uint4(0u, 0xFFFFFFFFu, 0u, 0u);
+        if (rix < n_in) rec = __ldg(in + rix);
+        const uint32_t ah = rec.y | ~full;
+        uint32_t cand = ~(ah | rec.z | rec.w);
+        tot_nodes += __popc(cand);                                          // every value of the domain is a node
+        uint32_t surv = 0;
+        while (__any_sync(0xFFFFFFFFu, cand != 0u)) {
+            const uint32_t bit = cand & (0u - cand);
+            cand ^= bit;
+            const uint32_t na = ah | bit, nl = (rec.z | bit) << 1, nr = (rec.w | bit) >> 1;
+            uint32_t worst = 0;
+            for (int j = 0; j <= last; j++) worst = max(worst, na | (nl << j) | (nr >> j));
+            bool ok = bit != 0u && worst != 0xFFFFFFFFu;
+            if (ok && filter_partition)
+                ok = ((rec.x * (uint32_t)N + ((uint32_t)__ffs((int)bit) - 1u)) % (uint32_t)A.part_count) == (uint32_t)A.part_rank;
+            if (ok) surv |= bit;
+        }
+        // one atomic per CTA and tile
+        uint32_t mine = __popc(surv), incl = mine;
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) s_cnt[wib] = incl;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t tot = 0;
+#pragma unroll
+            for (int w = 0; w < kQueensBlock / 32; w++) { const uint32_t c = s_cnt[w]; s_cnt[w] = tot; tot += c; }
+            s_base = tot ? atomicAdd(n_out_ptr, (unsigned long long)tot) : 0ull;
+        }
+        __syncthreads();
+        unsigned long long slot0 = s_base + s_cnt[wib];
+        while (__any_sync(0xFFFFFFFFu, surv != 0u)) {
+            const uint32_t bit = surv & (0u - surv);
+            surv ^= bit;
+            const uint32_t m = __ballot_sync(0xFFFFFFFFu, bit != 0u);
+            if (bit) {
+                const unsigned long long slot = slot0 + __popc(m & lt);
+                if (slot < A.record_cap)
+                    out[slot] = make_uint4(rec.x * (uint32_t)N + ((uint32_t)__ffs((int)bit) - 1u), rec.y | bit, (rec.z | bit) << 1, (rec.w | bit) >> 1);
+            }
+            slot0 += __popc(m);
+        }
+        __syncthreads();
+    }
+    if (count_nodes) {
+        for (int o = 16; o > 0; o >>= 1) tot_nodes += __shfl_down_sync(0xFFFFFFFFu, tot_nodes, o);
+        if (lane == 0 && tot_nodes) atomicAdd(A.totals + 1, tot_nodes);
+    }
+}
+
 // The first levels hold a handful of records (1, N, about N^2 / 1.2): ONE CTA walks levels 0 .. n_levels-1 back to back
 // instead of one launch each (a launch costs more than these levels' work).  buf0 / buf1 alternate as in the host loop,
 // sizes[l] is the frontier size at depth l.
