@@ -25,7 +25,7 @@ def add(g, name, ns):
 
 buf = []
 for name, ns in seq:
-    if name in ("dq::k_queens_level", "dq::k_queens_first_warp"):
+    if name in ("dq::k_queens_level", "dq::k_queens_level_wide", "dq::k_queens_levels_head", "dq::k_queens_first_warp"):
         buf.append((name, ns))          # belongs to the bucket launch that follows
     elif name == "dq::k_queens_bucket":
         g = "17-Queens count-all (main workload)" if ns > 5e6 else "14-Queens count-all (extra.nqueens14_1gpu)"
