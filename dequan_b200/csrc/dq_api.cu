@@ -325,9 +325,10 @@ static int solve_queens_lane(dq_model* m, const dq_tree_opts* opts, dq_tree_resu
     if (opts->split_depth > 0) K = std::min(opts->split_depth, std::min(N - 2, 12));
     else {
         K = std::max(std::min(N - 7, N <= 15 ? 6 : 7), 0);
-        // a partition of a strongly scaled solve (multi-GPU) holds 1/parts of the records: one level deeper keeps the
-        // bucket pools fed to the end (17-Queens, 8 partitions: 2.57 -> 2.46 ms each; scripts/parts_k.py)
-        if (opts->part_count >= 4 && N >= 17 && !(getenv("DQ_QUEENS_ENGINE") && !strcmp(getenv("DQ_QUEENS_ENGINE"), "lane"))) K = 8;
+        // one level deeper keeps the bucket pools fed to the end: from 18 queens on (132 -> 121 ms), and for the partitions
+        // of a strongly scaled 17-Queens solve, which hold 1/parts of the records each (8 partitions: 2.43 -> 2.28 ms;
+        // scripts/parts_k.py)
+        if ((N >= 18 || (N == 17 && opts->part_count >= 4)) && !(getenv("DQ_QUEENS_ENGINE") && !strcmp(getenv("DQ_QUEENS_ENGINE"), "lane"))) K = 8;
     }
     auto key_space = [&](int k) { double keys = 1; for (int i = 0; i < k; i++) keys *= N; return keys; };
     // the lane engine reads 32-bit prefix keys from its records; the bucket search reads none (its first-solution warp
@@ -344,7 +345,7 @@ static int solve_queens_lane(dq_model* m, const dq_tree_opts* opts, dq_tree_resu
     const int ctas = occ * m->sm_count;
     DQ_CUDA(m->q_first.reserve(32));
     DQ_CUDA(m->d_ctrl.reserve(32));
-    size_t cap = std::max<size_t>(m->q_records.cap, (size_t)std::min(std::max(2.0 * estimate(K), 1024.0), 64.0 * 1024 * 1024));
+    size_t cap = std::max<size_t>(m->q_records.cap, (size_t)std::min(std::max(2.5 * estimate(K), 1024.0), 512.0 * 1024 * 1024));
     // control words live in pinned host memory that outlives the call: the queue below may be replayed as a CUDA graph
     unsigned long long* h_init = m->pin;              // [32] initial control block
     uint4* h_root = reinterpret_cast<uint4*>(m->pin + 32);
