@@ -314,8 +314,7 @@ static int max_ctas_per_sm(K kernel, int threads, size_t smem, int* out) {
 // kernel queued back to back, one host synchronisation at the end.
 static int solve_queens_lane(dq_model* m, const dq_tree_opts* opts, dq_tree_result* res, int32_t* first_solution) {
     const int N = m->cm.queens_n;
-    // Split depth.  Measured on B200 (scripts/sweep_k.py, profiles/r1_queens_split_depth.txt): subtrees of a few
-    // hundred nodes keep the lanes busy without flooding the record list; that is depth 6 up to N=15 and 7 above.
+    // Split depth: measured per board size on B200 (scripts/sweep_k.py, profiles/r1_queens_split_depth.txt), see below.
     int K = 0;
     auto dfs_smem = [&](int k) { return (size_t)std::max(N - 2 - k, 1) * kQueensBlock * sizeof(uint4); };
     // estimated FC-surviving prefixes per depth (sizes the record lists): each level multiplies by about N - 2.2*depth
@@ -324,11 +323,18 @@ static int solve_queens_lane(dq_model* m, const dq_tree_opts* opts, dq_tree_resu
     int rc = DQ_OK;
     if (opts->split_depth > 0) K = std::min(opts->split_depth, std::min(N - 2, 12));
     else {
-        K = std::max(std::min(N - 7, N <= 15 ? 6 : 7), 0);
-        // one level deeper keeps the bucket pools fed to the end: from 18 queens on (132 -> 121 ms), and for the partitions
-        // of a strongly scaled 17-Queens solve, which hold 1/parts of the records each (8 partitions: 2.43 -> 2.28 ms;
-        // scripts/parts_k.py)
-        if ((N >= 18 || (N == 17 && opts->part_count >= 4)) && !(getenv("DQ_QUEENS_ENGINE") && !strcmp(getenv("DQ_QUEENS_ENGINE"), "lane"))) K = 8;
+        K = std::max(std::min(N - 7, N <= 15 ? 6 : 7), 0);          // the lane-per-subtree engine's depths
+        if (!(getenv("DQ_QUEENS_ENGINE") && !strcmp(getenv("DQ_QUEENS_ENGINE"), "lane"))) {
+            // bucket search, measured per N (scripts/sweep_k.py, profiles/r1_queens_split_depth.txt): small boards are bound
+            // by the launches of the levels, large ones by keeping the pools fed to the end (18 queens: 132 -> 121 ms at
+            // depth 8); the partitions of a strongly scaled 17-Queens solve hold 1/parts of the records each and split one
+            // level deeper as well (8 partitions: 2.43 -> 2.28 ms, scripts/parts_k.py)
+            if (N <= 13) K = std::max(N - 8, 0);
+            else if (N <= 15) K = 7;
+            else if (N == 16) K = 8;
+            else if (N == 17) K = opts->part_count >= 4 ? 8 : 7;
+            else K = 8;
+        }
     }
     auto key_space = [&](int k) { double keys = 1; for (int i = 0; i < k; i++) keys *= N; return keys; };
     // the lane engine reads 32-bit prefix keys from its records; the bucket search reads none (its first-solution warp
