@@ -360,10 +360,10 @@ def roofline_queens(n, world, nodes, frontier_nodes, records, lane_ms, int_peak,
             "note": "not HBM- or tensor-bound: no dense contraction on this path, one 16 B record per subtree from HBM"}
 
 
-# ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum summed over the seven kernels of one 1 M-puzzle pipeline pass
-# (profiles/r1_ncu_sudoku_1M.txt): 869 MB read + 687 MB written, of which 288 B per puzzle are the digest (written once, a
-# local-memory spill in k_sudoku_digest doubles that write) and the rest task / snapshot records of the counting stage
-NCU_SUDOKU_TRAFFIC_1M = 869624832 + 687312384
+# ncu, dram__bytes_read.sum + dram__bytes_write.sum summed over the seven kernels of one 1 M-puzzle pipeline pass
+# (profiles/r1_ncu_sudoku_traffic.txt): 856 MB read + 366 MB written, of which 288 B per puzzle are the digest (written
+# once, read by k_sudoku_first and again per counting task) and the rest task / snapshot records of the counting stage
+NCU_SUDOKU_TRAFFIC_1M = 856_260_000 + 366_400_000
 
 
 def sudoku_rooflines(out, hbm_peak, peak_src, int_peak):

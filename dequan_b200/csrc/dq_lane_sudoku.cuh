@@ -162,12 +162,22 @@ k_sudoku_digest(const uint8_t* __restrict__ cells, long long n, int stride, Sudo
             if ((row[r] | col[c] | box[(r / 3) * 3 + c / 3]) == 0x1FFu) defer = true;  // a blank wiped out by the givens
             w[19 + r * 3 + c / 3] |= 0x1FFu << (10 * (c % 3));
             w[67 + (c * 9 + r) / 32] |= 1u << ((c * 9 + r) % 32);
-            // cell id of this search level, one byte per level (dynamic index: the only non-static store of the pass)
-            const uint32_t sh = (uint32_t)(level & 3) * 8;
-#pragma unroll
-            for (int q = 0; q < 21; q++) if ((level >> 2) == q) w[46 + q] |= (uint32_t)p << sh;
             ++level;
         }
+    // cell id of every search level, one byte per level: the L-th blank cell is the L-th set bit of the blank bitmap
+    // (all indices static: the table stays in registers — the level-indexed store this replaces put it in local memory
+    // and doubled the pass's DRAM writes)
+    {
+        const int c0 = __popc(blank[0]), c1 = c0 + __popc(blank[1]);
+#pragma unroll
+        for (int L = 0; L < 81; L++) {
+            uint32_t p = 0;
+            if (L < c0) p = __fns(blank[0], 0, L + 1);
+            else if (L < c1) p = 32u + __fns(blank[1], 0, L - c0 + 1);
+            else if (L < level) p = 64u + __fns(blank[2], 0, L - c1 + 1);
+            w[46 + (L >> 2)] |= p << ((L & 3) * 8);
+        }
+    }
     w[0] = blank[0]; w[1] = blank[1]; w[2] = blank[2];
     w[3] = (uint32_t)level | (defer ? 0x80000000u : 0u);
 #pragma unroll
