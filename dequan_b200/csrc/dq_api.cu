@@ -318,7 +318,7 @@ static int solve_queens_lane(dq_model* m, const dq_tree_opts* opts, dq_tree_resu
     int K = 0;
     auto dfs_smem = [&](int k) { return (size_t)std::max(N - 2 - k, 1) * kQueensBlock * sizeof(uint4); };
     // estimated FC-surviving prefixes per depth (sizes the record lists): each level multiplies by about N - 2.2*depth
-    auto estimate = [&](int k) { double e = 1; for (int i = 0; i < k; i++) e *= std::max(N - 2.2 * i, 2.0); return e; };
+    auto estimate = [&](int k) { double e = 1; for (int i = 0; i < k; i++) e *= std::max(N - 2.2 * i, 3.6); return e; };
     int occ = 0;
     int rc = DQ_OK;
     if (opts->split_depth > 0) K = std::min(opts->split_depth, std::min(N - 2, 12));
@@ -332,7 +332,7 @@ static int solve_queens_lane(dq_model* m, const dq_tree_opts* opts, dq_tree_resu
             if (N <= 13) K = std::max(N - 8, 0);
             else if (N <= 15) K = 7;
             else if (N == 16) K = 8;
-            else if (N == 17) K = opts->part_count >= 4 ? 8 : 7;
+            else if (N == 17) K = 9;                   // 124 M records (2 GB per list): 16.7 -> 15.3 ms; partitions 2.25 -> 2.04 ms
             else K = 8;
         }
     }
@@ -343,10 +343,26 @@ static int solve_queens_lane(dq_model* m, const dq_tree_opts* opts, dq_tree_resu
     while (K > 0 && !deep_ok && key_space(K) > 4.0e9) K--;   // (res->split_depth_used reports K)
     // the search kernel: depth-bucketed warp pools (default) or the older lane-per-subtree stacks (DQ_QUEENS_ENGINE=lane)
     static const bool use_buckets = !(getenv("DQ_QUEENS_ENGINE") && !strcmp(getenv("DQ_QUEENS_ENGINE"), "lane"));
-    const size_t smem = use_buckets ? (size_t)(kQueensBucketBlock / 32) * (N - 1 - K) * kQueensBucketCap * sizeof(uint4) : dfs_smem(K);
-    if (smem > 200 * 1024) { g_err = "board too large for the shared-memory stack"; return DQ_ERR_UNSUPPORTED; }
-    rc = use_buckets ? max_ctas_per_sm(k_queens_bucket, kQueensBucketBlock, smem, &occ) : max_ctas_per_sm(k_queens_lane, kQueensBlock, smem, &occ);
-    if (rc != DQ_OK) return rc;
+    // bucket search: warps per CTA chosen so that the pools (buckets x 128 frames x 16 B per warp) pack an SM's shared memory best
+    int bucket_warps = 4;
+    size_t smem = dfs_smem(K);
+    if (use_buckets) {
+        const size_t per_warp = (size_t)(N - 1 - K) * kQueensBucketCap * sizeof(uint4);
+        int best = 0;
+        for (int w = 2; w <= kQueensBucketMaxWarps; w++) {
+            if (per_warp * w > 200 * 1024) break;
+            int o = 0;
+            rc = max_ctas_per_sm(k_queens_bucket, w * 32, per_warp * w, &o);
+            if (rc != DQ_OK) return rc;
+            if (o * w > best) { best = o * w; bucket_warps = w; occ = o; }
+        }
+        if (best == 0) { g_err = "board too large for the shared-memory pools"; return DQ_ERR_UNSUPPORTED; }
+        smem = per_warp * bucket_warps;
+    } else {
+        if (smem > 200 * 1024) { g_err = "board too large for the shared-memory stack"; return DQ_ERR_UNSUPPORTED; }
+        rc = max_ctas_per_sm(k_queens_lane, kQueensBlock, smem, &occ);
+        if (rc != DQ_OK) return rc;
+    }
     if (occ < 1) { g_err = "kernel does not fit an SM"; return DQ_ERR_UNSUPPORTED; }
     const int ctas = occ * m->sm_count;
     DQ_CUDA(m->q_first.reserve(32));
@@ -415,7 +431,7 @@ static int solve_queens_lane(dq_model* m, const dq_tree_opts* opts, dq_tree_resu
             }
             if (with_events) DQ_CUDA(cudaEventRecord(m->ev2, m->stream));
             if (use_buckets) {
-                k_queens_bucket<<<ctas, kQueensBucketBlock, smem, m->stream>>>(A);
+                k_queens_bucket<<<ctas, bucket_warps * 32, smem, m->stream>>>(A);
                 if (with_events) DQ_CUDA(cudaEventRecord(m->ev3, m->stream));
                 DQ_CUDA(cudaStreamWaitEvent(m->stream, m->ev_join, 0));
             } else {

@@ -431,17 +431,20 @@ __global__ void k_queens_first(QueensLaneArgs A) {
 // Depth-bucketed warp search (COUNT_ALL).  The lane-per-subtree kernel above pays for SIMT twice: its forward-check
 // loop runs to the row count of the SHALLOWEST lane of the warp (about 9 rows per trip when a node needs 4.3 on
 // average, N=17), and lanes idle while their mates finish a subtree.  Here a warp owns a pool of open frames
-// {a, l, r, untried} in shared memory, bucketed by depth, and every trip takes up to 32 frames of ONE depth:
+// {a, l, r, untried} in shared memory, bucketed by depth, and every trip takes up to 64 frames of ONE depth, two per
+// lane:
 //   * the row count of the forward check is warp-uniform and exact (no max over lanes, uniform shift amounts);
-//   * each lane tries the lowest untried value of its frame (one node, dequan.h:416-423); frames that still hold
-//     untried values go back to the bucket, surviving children go to the next bucket, both compacted with a ballot;
-//   * the bucket is chosen deepest-first among those holding a full warp of frames, which bounds every bucket below
-//     64 frames (a bucket is only fed while it holds fewer than 32); with no full bucket the warp pulls 32 more
-//     records from the frontier list, and once that is empty widens from the shallowest bucket.
+//   * each lane tries the lowest untried value of each of its two frames (one node each, dequan.h:416-423); frames
+//     that still hold untried values go back to the bucket, surviving children go to the next bucket, both
+//     compacted with ballots; the bucket choice, the counts and the loop are paid once per 64 nodes and the two
+//     dependency chains interleave;
+//   * the bucket is chosen deepest-first among those holding 64 frames, which bounds every bucket below 128 frames
+//     (a bucket is only fed, by at most 64, while it holds fewer than 64); with no full bucket the warp pulls 64
+//     more records from the frontier list, and once that is empty widens from the shallowest bucket.
 // Node and solution counts do not depend on the visiting order; the DFS-first solution is found separately by
 // queens_first_owned.  Bucket sizes live in registers, lane i holding the size of bucket i.
-constexpr int kQueensBucketBlock = 128;
-constexpr int kQueensBucketCap = 64;
+constexpr int kQueensBucketMaxWarps = 6;              // warps per CTA: the host picks what packs an SM's shared memory best
+constexpr int kQueensBucketCap = 128;
 
 // DFS-first solution of the part of the tree this partition owns, and the depth-k key of its prefix
 // (ForwardCheckingStep's own order, dequan.h:494-571).  Run by one warp in a kernel of its own, on a second stream
@@ -497,7 +500,7 @@ __device__ __forceinline__ uint32_t queens_rows_occupied(uint32_t na, uint32_t n
 
 __global__ void __launch_bounds__(32) k_queens_first_warp(QueensLaneArgs A) { queens_first_owned(A, (int)threadIdx.x); }
 
-__global__ void __launch_bounds__(kQueensBucketBlock)
+__global__ void __launch_bounds__(kQueensBucketMaxWarps * 32)
 k_queens_bucket(QueensLaneArgs A) {
     extern __shared__ uint4 qb_frames[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -508,8 +511,8 @@ k_queens_bucket(QueensLaneArgs A) {
     const uint32_t bbase = (uint32_t)__cvta_generic_to_shared(qb_frames + (size_t)wib * L * kQueensBucketCap);
     const unsigned long long n_found = *A.n_records;
     const unsigned long long n_rec = n_found < A.record_cap ? n_found : A.record_cap;   // overflow: the host grows the list and reruns
-    const unsigned long long total_warps = (unsigned long long)gridDim.x * (kQueensBucketBlock / 32);
-    const uint32_t fair_share = (uint32_t)min((n_rec + total_warps - 1) / total_warps, 32ull);
+    const unsigned long long total_warps = (unsigned long long)gridDim.x * (blockDim.x >> 5);
+    const uint32_t fair_share = (uint32_t)min((n_rec + total_warps - 1) / total_warps, 64ull);
 
 
     uint32_t cnt = 0;                                            // lane i: frames in bucket i
@@ -519,7 +522,7 @@ k_queens_bucket(QueensLaneArgs A) {
     bool exhausted = false;
 
     for (;;) {
-        const uint32_t big = __ballot_sync(0xFFFFFFFFu, cnt >= 32u);
+        const uint32_t big = __ballot_sync(0xFFFFFFFFu, cnt >= 64u);
         int lvl;
         if (big) lvl = 31 - __clz((int)big);
         else {
@@ -541,12 +544,14 @@ k_queens_bucket(QueensLaneArgs A) {
                 }
                 if (!exhausted) {
                     const uint32_t c0 = __shfl_sync(0xFFFFFFFFu, cnt, 0);
-                    const uint32_t n_take = (uint32_t)min(chunk_end - chunk_pos, 32ull);
-                    if ((uint32_t)lane < n_take) {
-                        const uint4 rec = __ldg(A.records + chunk_pos + lane);
-                        const uint32_t a = rec.y | hi;
-                        sts128(bbase + ((c0 + lane) << 4), a, rec.z, rec.w, ~(a | rec.z | rec.w));
-                    }
+                    const uint32_t n_take = (uint32_t)min(chunk_end - chunk_pos, 64ull);
+#pragma unroll
+                    for (int h = 0; h < 2; h++)
+                        if ((uint32_t)lane + 32u * h < n_take) {
+                            const uint4 rec = __ldg(A.records + chunk_pos + lane + 32 * h);
+                            const uint32_t a = rec.y | hi;
+                            sts128(bbase + ((c0 + lane + 32 * h) << 4), a, rec.z, rec.w, ~(a | rec.z | rec.w));
+                        }
                     if (lane == 0) cnt = c0 + n_take;
                     chunk_pos += n_take;
                     if (nodes >= 0x40000000u) { tot_nodes += nodes; tot_sols += sols; nodes = 0; sols = 0; }
@@ -559,40 +564,49 @@ k_queens_bucket(QueensLaneArgs A) {
             lvl = __ffs((int)any) - 1;
         }
         const uint32_t c = __shfl_sync(0xFFFFFFFFu, cnt, lvl);
-        const uint32_t n = min(c, 32u);
+        const uint32_t n = min(c, 64u);
         const uint32_t keep_base = c - n;
-        const bool act = (uint32_t)lane < n;
         const uint32_t row = bbase + (uint32_t)lvl * (kQueensBucketCap * 16u);
-        uint32_t a = 0xFFFFFFFFu, l = 0, r = 0, cand = 0;
-        if (act) { const uint4 f = lds128(row + ((keep_base + lane) << 4)); a = f.x; l = f.y; r = f.z; cand = f.w; }
-        const uint32_t bit = cand & (0u - cand);
-        cand ^= bit;
-        const uint32_t na = a | bit, nl = (l | bit) << 1, nr = (r | bit) >> 1;
+        // two frames per lane and trip: the bucket choice, the counts and the loop are paid once for 64 nodes, and the two
+        // dependency chains interleave
+        const bool actA = (uint32_t)lane < n, actB = (uint32_t)lane + 32u < n;
+        uint32_t aA = 0xFFFFFFFFu, lA = 0, rA = 0, cA = 0, aB = 0xFFFFFFFFu, lB = 0, rB = 0, cB = 0;
+        if (actA) { const uint4 f = lds128(row + ((keep_base + lane) << 4)); aA = f.x; lA = f.y; rA = f.z; cA = f.w; }
+        if (actB) { const uint4 f = lds128(row + ((keep_base + 32u + lane) << 4)); aB = f.x; lB = f.y; rB = f.z; cB = f.w; }
+        const uint32_t bitA = cA & (0u - cA), bitB = cB & (0u - cB);
+        cA ^= bitA; cB ^= bitB;
+        const uint32_t naA = aA | bitA, nlA = (lA | bitA) << 1, nrA = (rA | bitA) >> 1;
+        const uint32_t naB = aB | bitB, nlB = (lB | bitB) << 1, nrB = (rB | bitB) >> 1;
         const int last = L - 1 - lvl;
-        // the row count is warp-uniform: one jump into straight-line code with immediate shift amounts
-        uint32_t occ_max = 0;                                    // all ones <=> some later domain is empty
+        uint32_t occA = 0, occB = 0;                             // all ones <=> some later domain is empty
         switch (last) {
-#define DQ_QROWS(J) case J: occ_max = queens_rows_occupied<J + 1>(na, nl, nr); break;
+#define DQ_QROWS(J) case J: occA = queens_rows_occupied<J + 1>(naA, nlA, nrA); occB = queens_rows_occupied<J + 1>(naB, nlB, nrB); break;
             DQ_QROWS(0) DQ_QROWS(1) DQ_QROWS(2) DQ_QROWS(3) DQ_QROWS(4) DQ_QROWS(5) DQ_QROWS(6) DQ_QROWS(7) DQ_QROWS(8) DQ_QROWS(9)
             DQ_QROWS(10) DQ_QROWS(11) DQ_QROWS(12) DQ_QROWS(13) DQ_QROWS(14) DQ_QROWS(15) DQ_QROWS(16) DQ_QROWS(17) DQ_QROWS(18) DQ_QROWS(19)
             DQ_QROWS(20) DQ_QROWS(21) DQ_QROWS(22) DQ_QROWS(23) DQ_QROWS(24) DQ_QROWS(25) DQ_QROWS(26) DQ_QROWS(27) DQ_QROWS(28)
 #undef DQ_QROWS
-            default: occ_max = queens_rows_occupied<30>(na, nl, nr); break;
+            default: occA = queens_rows_occupied<30>(naA, nlA, nrA); occB = queens_rows_occupied<30>(naB, nlB, nrB); break;
         }
-        const bool pass = act && occ_max != 0xFFFFFFFFu;
-        nodes += act ? 1u : 0u;
-        const uint32_t keep = __ballot_sync(0xFFFFFFFFu, cand != 0u);
-        if (cand) sts128(row + ((keep_base + __popc(keep & lt)) << 4), a, l, r, cand);
-        const uint32_t c_new = keep_base + __popc(keep);
+        const bool passA = actA && occA != 0xFFFFFFFFu, passB = actB && occB != 0xFFFFFFFFu;
+        nodes += (actA ? 1u : 0u) + (actB ? 1u : 0u);
+        const uint32_t keepA = __ballot_sync(0xFFFFFFFFu, cA != 0u), keepB = __ballot_sync(0xFFFFFFFFu, cB != 0u);
+        const uint32_t nkA = __popc(keepA);
+        if (cA) sts128(row + ((keep_base + __popc(keepA & lt)) << 4), aA, lA, rA, cA);
+        if (cB) sts128(row + ((keep_base + nkA + __popc(keepB & lt)) << 4), aB, lB, rB, cB);
+        const uint32_t c_new = keep_base + nkA + __popc(keepB);
         if (last == 0) {
-            if (pass) { const uint32_t pc = __popc(~(na | nl | nr)); nodes += pc; sols += pc; }
+            if (passA) { const uint32_t pc = __popc(~(naA | nlA | nrA)); nodes += pc; sols += pc; }
+            if (passB) { const uint32_t pc = __popc(~(naB | nlB | nrB)); nodes += pc; sols += pc; }
             if (lane == lvl) cnt = c_new;
         } else {
-            const uint32_t kids = __ballot_sync(0xFFFFFFFFu, pass);
+            const uint32_t kidsA = __ballot_sync(0xFFFFFFFFu, passA), kidsB = __ballot_sync(0xFFFFFFFFu, passB);
             const uint32_t c1 = __shfl_sync(0xFFFFFFFFu, cnt, lvl + 1);
-            if (pass) sts128(row + kQueensBucketCap * 16u + ((c1 + __popc(kids & lt)) << 4), na, nl, nr, ~(na | nl | nr));
+            const uint32_t nA = __popc(kidsA);
+            const uint32_t nrow = row + kQueensBucketCap * 16u;
+            if (passA) sts128(nrow + ((c1 + __popc(kidsA & lt)) << 4), naA, nlA, nrA, ~(naA | nlA | nrA));
+            if (passB) sts128(nrow + ((c1 + nA + __popc(kidsB & lt)) << 4), naB, nlB, nrB, ~(naB | nlB | nrB));
             if (lane == lvl) cnt = c_new;
-            if (lane == lvl + 1) cnt = c1 + __popc(kids);
+            if (lane == lvl + 1) cnt = c1 + nA + __popc(kidsB);
         }
         __syncwarp();
     }

@@ -6,7 +6,7 @@ from dequan_b200 import api
 from dequan_b200.model import nqueens
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 17
 m = api.Model(nqueens(n))
-for k in (7, 8):
+for k in (8, 9):
     for world in (tuple(int(x) for x in sys.argv[2].split(",")) if len(sys.argv) > 2 else (1, 8)):
         tot_s = tot_n = 0; times = []; srch = []
         for r in range(world):

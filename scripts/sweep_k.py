@@ -3,7 +3,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from dequan_b200 import api
 from dequan_b200.model import nqueens
-for n in (13, 14, 15, 16, 17):
+for n in (13, 14, 15, 16):
     m = api.Model(nqueens(n))
     for k in (5, 6, 7, 8, 9):
         if (n >= 17 and k < 4) or k > n - 3: continue

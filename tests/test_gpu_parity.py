@@ -628,13 +628,13 @@ def test_queens_graph_replay_and_recapture(product_lib):
 
 
 def test_17_queens_in_four_partitions(product_lib):
-    """BASELINE config C5 at full size, the way four GPUs split it (partitions of a 17-Queens solve use split depth 8):
+    """BASELINE config C5 at full size, the way four GPUs split it (split depth 9):
     the partitions' counts add up to OEIS A000170(17) and the reference's node count, and the lowest first-solution key
     belongs to the reference's first solution."""
     csp = nqueens(17)
     m = api.Model(csp)
     parts = [m.solve_tree("count", part_rank=k, part_count=4) for k in range(4)]
-    assert all(p.split_depth == 8 for p in parts)
+    assert all(p.split_depth == 9 for p in parts)
     assert sum(p.solutions for p in parts) == 95815104 and sum(p.nodes for p in parts) == 5474619051
     best = min(parts, key=lambda p: p.first_key)
     assert best.first == O.solve(csp, "first").first
