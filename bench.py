@@ -337,7 +337,7 @@ def main():
 
 
 # ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of k_queens_bucket (profiles/r1_ncu_queens14_bucket.txt, r1_ncu_queens17_bucket.txt)
-NCU_TRAFFIC = {(14, 1): 3895040, (17, 1): 126753792 + 6595328}
+NCU_TRAFFIC = {(14, 1): 13093120 + 256, (17, 1): 1982841000 + 5133824}
 
 
 def roofline_queens(n, world, nodes, frontier_nodes, records, lane_ms, int_peak, hbm_peak, peak_src):
