@@ -49,11 +49,12 @@ class dq_batch_opts(C.Structure):
 
 class dq_batch_stats(C.Structure):
     _fields_ = [("n_sat", C.c_uint64), ("n_unsat", C.c_uint64), ("n_budget", C.c_uint64), ("total_nodes", C.c_uint64),
-                ("kernel_ms", C.c_double), ("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+                ("kernel_ms", C.c_double), ("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
+                ("search_kernel_ms", C.c_double)]
 
 
 EXPORTS = ["dq_device_info", "dq_set_device", "dq_compile", "dq_free", "dq_model_info", "dq_model_order", "dq_model_table_bytes", "dq_solve_tree",
-           "dq_tree_nodes_upto", "dq_enumerate_solutions", "dq_solve_batch_cells", "dq_solve_batch_cells_dev", "dq_solve_batch_graphs",
+           "dq_tree_nodes_upto", "dq_enumerate_solutions", "dq_solve_batch_cells", "dq_solve_batch_cells_dev", "dq_solve_batch_graphs", "dq_solve_batch_graphs_dev",
            "dq_measure_int_peak", "dq_last_error", "dq_version", "dq_parse_sudoku_lines", "dq_parse_dimacs_col"]
 
 _lib = None
@@ -84,6 +85,8 @@ def lib():
     L.dq_solve_batch_cells_dev.argtypes = L.dq_solve_batch_cells.argtypes
     L.dq_solve_batch_graphs.argtypes = [C.c_int32, C.c_int32, C.c_void_p, u8p, C.c_int64, C.POINTER(dq_batch_opts),
                                         u8p, u64p, u8p, C.POINTER(dq_batch_stats)]
+    L.dq_solve_batch_graphs_dev.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, u8p, C.c_int64, C.POINTER(dq_batch_opts),
+                                            u8p, u64p, u8p, C.POINTER(dq_batch_stats)]
     L.dq_measure_int_peak.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.dq_parse_sudoku_lines.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
     L.dq_parse_dimacs_col.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_int32), C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
@@ -147,6 +150,7 @@ class BatchResult:
     launches: int
     h2d_bytes: int
     d2h_bytes: int
+    search_kernel_ms: float = 0.0
 
 
 class Model:
@@ -261,7 +265,24 @@ def solve_batch_graphs(n_vertices: int, k: int, edge_off: np.ndarray, edges: np.
     _check(lib().dq_solve_batch_graphs(n_vertices, k, edge_off.ctypes.data, edges.ctypes.data, n, C.byref(o),
                                        col.ctypes.data, nodes.ctypes.data, status.ctypes.data, C.byref(st)))
     return BatchResult(col, nodes, status, st.n_sat, st.n_unsat, st.n_budget, st.total_nodes, st.kernel_ms,
-                       st.kernel_launches, st.h2d_bytes, st.d2h_bytes)
+                       st.kernel_launches, st.h2d_bytes, st.d2h_bytes, st.search_kernel_ms)
+
+
+def solve_batch_graphs_ptr(n_vertices: int, k: int, edge_off: np.ndarray, edge_off_dev: int, edges_ptr: int, col_ptr: int,
+                           nodes_ptr: int, status_ptr: int, node_budget: int = 0, engine: str = "auto", device: bool = True):
+    """Raw-pointer form: device=True -> dq_solve_batch_graphs_dev (HBM-resident edge lists and outputs; `edge_off` is the
+    host copy of the offsets), device=False -> dq_solve_batch_graphs on (pinned) host buffers."""
+    assert edge_off.dtype == np.int64
+    n = len(edge_off) - 1
+    o = dq_batch_opts(node_budget, ENGINE[engine], 0)
+    st = dq_batch_stats()
+    if device:
+        _check(lib().dq_solve_batch_graphs_dev(n_vertices, k, edge_off.ctypes.data, edge_off_dev, edges_ptr, n, C.byref(o),
+                                               col_ptr, nodes_ptr, status_ptr, C.byref(st)))
+    else:
+        _check(lib().dq_solve_batch_graphs(n_vertices, k, edge_off.ctypes.data, edges_ptr, n, C.byref(o),
+                                           col_ptr, nodes_ptr, status_ptr, C.byref(st)))
+    return st
 
 
 def parse_sudoku_lines(text: str) -> np.ndarray:

@@ -13,6 +13,7 @@
 #include "dq_lane_queens.cuh"
 #include "dq_lane_sudoku.cuh"
 #include "dq_reg_graphs.cuh"
+#include "dq_group_graphs.cuh"
 #include "dq_small_tree.cuh"
 #include "dq_model.hpp"
 
@@ -1101,6 +1102,151 @@ int dq_solve_batch_cells(dq_model* m, const uint8_t* cells, int64_t n, int32_t s
     return DQ_OK;
 }
 
+}  // extern "C"
+
+// Batches of k-colouring instances.  Device-level runner shared by the host-buffer and the device-buffer entry points:
+// engine choice, scratch, kernels, totals.  `edge_off` is the HOST copy of the offsets (sizes the adjacency records).
+struct GraphBatchDev {
+    const long long* off; const uint8_t* edges; long long edge_bytes;    // edge_bytes: 2 * total rounded up to 16, readable
+    uint8_t* colours; unsigned long long* nodes; uint8_t* status;
+};
+
+template <int G>
+static int launch_graphs_group(const GroupGraphsArgs& A, int sms, cudaStream_t s) {
+    const size_t per_warp = graphs_group_warp_bytes(A.nvp, A.stride, G);
+    int wpc = kGroupWarpsPerCta;
+    while (wpc > 1 && per_warp * wpc > 200 * 1024) wpc >>= 1;
+    if (per_warp * wpc > 200 * 1024) { g_err = "instance state exceeds shared memory"; return DQ_ERR_UNSUPPORTED; }
+    int occ = 0;
+    int rc = max_ctas_per_sm(k_graphs_group<G>, wpc * 32, per_warp * wpc, &occ);
+    if (rc != DQ_OK) return rc;
+    if (occ < 1) { g_err = "kernel does not fit an SM"; return DQ_ERR_UNSUPPORTED; }
+    const long long groups_per_cta = (long long)wpc * (32 / G);
+    const long long ctas = std::max<long long>(1, std::min<long long>((A.n + groups_per_cta - 1) / groups_per_cta, (long long)occ * sms));
+    k_graphs_group<G><<<(unsigned)ctas, wpc * 32, per_warp * wpc, s>>>(A);
+    return DQ_OK;
+}
+
+static int run_batch_graphs(int nv, int k, const int64_t* edge_off, const GraphBatchDev& B, int64_t n, const dq_batch_opts* opts,
+                            dq_batch_stats* stats) {
+    DeviceCtx* ctx = nullptr;
+    DQ_CUDA(device_ctx(&ctx));
+    cudaStream_t s = ctx->stream;
+    const int sms = ctx->sm_count;
+    const long long total = edge_off[n];
+    const int engine = opts ? opts->engine : DQ_ENGINE_AUTO;
+    if (engine == DQ_ENGINE_LANE && k > 4) { g_err = "the lane-group engine serves k <= 4"; return DQ_ERR_UNSUPPORTED; }
+    if (engine == DQ_ENGINE_REG && k > 4) { g_err = "the register engine serves k <= 4"; return DQ_ERR_UNSUPPORTED; }
+    const bool group_engine = k <= 4 && (engine == DQ_ENGINE_AUTO || engine == DQ_ENGINE_LANE);
+    const bool reg_engine = k <= 4 && engine == DQ_ENGINE_REG;                       // register-resident warp engine (dq_reg_graphs.cuh)
+    DevBuf<uint32_t> d_ent_off, d_ent; DevBuf<uint8_t> d_adj;
+    DevBuf<unsigned long long> d_ctrl;
+    struct Guard {                                       // buffers go back to the block cache only after the queue has drained
+        cudaStream_t s; DevBuf<uint32_t>&a, &b; DevBuf<uint8_t>& c; DevBuf<unsigned long long>& d;
+        ~Guard() { cudaStreamSynchronize(s); a.release(); b.release(); c.release(); d.release(); }
+    } guard{s, d_ent_off, d_ent, d_adj, d_ctrl};
+    DQ_CUDA(d_ctrl.reserve(8));
+    DQ_CUDA(cudaMemsetAsync(d_ctrl.p, 0, 8 * sizeof(unsigned long long), s));
+    unsigned long long launches = 0;
+    float ms = 0, ms_search = 0;
+    if (group_engine) {
+        long long max_m = 0;
+        for (int64_t i = 0; i < n; i++) max_m = std::max<long long>(max_m, edge_off[i + 1] - edge_off[i]);
+        GroupGraphsArgs A;
+        A.nv = nv; A.k = k; A.nvp = (nv + 15) & ~15;
+        A.stride = A.nvp + (int)((max_m + 15) & ~15ll);
+        A.edge_off = B.off; A.edges = B.edges; A.edge_bytes = B.edge_bytes; A.n = n;
+        A.budget = opts ? opts->node_budget : 0; A.cursor = d_ctrl.p; A.colours = B.colours; A.nodes = B.nodes; A.status = B.status;
+        A.totals = d_ctrl.p + 1;
+        DQ_CUDA(d_adj.reserve((size_t)n * A.stride));
+        A.adj = d_adj.p;
+        const int stage_cap = (int)(((2 * max_m + 15) & ~15ll) + 32);
+        const size_t adj_warp = (graphs_adj_warp_bytes(A.nvp, A.stride, stage_cap) + 127) & ~(size_t)127;
+        if (adj_warp * kAdjWarpsPerCta > 200 * 1024) { g_err = "edge list exceeds shared memory"; return DQ_ERR_UNSUPPORTED; }
+        int occ_a = 0;
+        int rc = max_ctas_per_sm(k_graphs_adjacency, kAdjWarpsPerCta * 32, adj_warp * kAdjWarpsPerCta, &occ_a);
+        if (rc != DQ_OK) return rc;
+        if (occ_a < 1) { g_err = "kernel does not fit an SM"; return DQ_ERR_UNSUPPORTED; }
+        // lanes per instance: as few as still give every SM a dozen warps (a trip of the search loop costs the same
+        // number of instructions whatever the group size); DQ_GRAPHS_GROUP overrides (sweeps)
+        int G = 1;
+        while (G < 8 && (double)n * G / 32.0 < 12.0 * sms) G <<= 1;
+        if (const char* e = getenv("DQ_GRAPHS_GROUP")) G = atoi(e);
+        DQ_CUDA(cudaMemsetAsync(B.status, 0, (size_t)n, s));
+        DQ_CUDA(cudaEventRecord(ctx->ev0, s));
+        const long long actas = std::max<long long>(1, std::min<long long>((n + kAdjWarpsPerCta - 1) / kAdjWarpsPerCta, (long long)occ_a * sms));
+        k_graphs_adjacency<<<(unsigned)actas, kAdjWarpsPerCta * 32, adj_warp * kAdjWarpsPerCta, s>>>(A, stage_cap);
+        DQ_CUDA(cudaEventRecord(ctx->ev2, s));
+        switch (G) {
+            case 1: rc = launch_graphs_group<1>(A, sms, s); break;
+            case 2: rc = launch_graphs_group<2>(A, sms, s); break;
+            case 4: rc = launch_graphs_group<4>(A, sms, s); break;
+            case 8: rc = launch_graphs_group<8>(A, sms, s); break;
+            case 16: rc = launch_graphs_group<16>(A, sms, s); break;
+            case 32: rc = launch_graphs_group<32>(A, sms, s); break;
+            default: g_err = "DQ_GRAPHS_GROUP must be 1, 2, 4, 8, 16 or 32"; rc = DQ_ERR_INVALID; break;
+        }
+        if (rc != DQ_OK) return rc;
+        DQ_CUDA(cudaEventRecord(ctx->ev3, s));
+        launches = 2;
+    } else {
+        BatchGraphsArgs A;
+        A.nv = nv; A.k = k; A.edge_off = B.off; A.edges = B.edges; A.n = n;
+        A.budget = opts ? opts->node_budget : 0; A.cursor = d_ctrl.p; A.colours = B.colours; A.nodes = B.nodes;
+        A.status = B.status; A.totals = d_ctrl.p + 1;
+        A.trail = nv * k + 32;
+        DQ_CUDA(cudaEventRecord(ctx->ev0, s));
+        if (reg_engine) {
+            RegGraphsArgs R;
+            R.nv = nv; R.k = k; R.edge_off = B.off; R.edges = B.edges; R.n = n; R.budget = A.budget; R.cursor = d_ctrl.p;
+            R.colours = B.colours; R.nodes = B.nodes; R.status = B.status; R.totals = d_ctrl.p + 1;
+            const size_t rsmem = reg_graphs_warp_bytes(nv, k) * kRegWarpsPerCta;
+            int rocc = 0;
+            int rc = max_ctas_per_sm(k_batch_graphs_reg, kRegWarpsPerCta * 32, rsmem, &rocc);
+            if (rc != DQ_OK) return rc;
+            const long long rctas = std::min<long long>((n + kRegWarpsPerCta - 1) / kRegWarpsPerCta, (long long)std::max(rocc, 1) * sms);
+            DQ_CUDA(cudaEventRecord(ctx->ev2, s));
+            k_batch_graphs_reg<<<(unsigned)rctas, kRegWarpsPerCta * 32, rsmem, s>>>(R);
+            launches = 1;
+        } else {
+            const size_t smem = warp_state_bytes(nv, A.trail) * kWarpsPerCta;
+            if (smem > 200 * 1024) { g_err = "instance state exceeds shared memory"; return DQ_ERR_UNSUPPORTED; }
+            int occ = 0;
+            int rc = max_ctas_per_sm(k_batch_graphs, kWarpsPerCta * 32, smem, &occ);
+            if (rc != DQ_OK) return rc;
+            DQ_CUDA(d_ent_off.reserve((size_t)n * (nv + 1))); DQ_CUDA(d_ent.reserve(2 * (size_t)std::max<long long>(total, 1)));
+            A.ent_off = d_ent_off.p; A.ent = d_ent.p;
+            k_graphs_build<<<(unsigned)((n + kWarpsPerCta - 1) / kWarpsPerCta), kWarpsPerCta * 32, (size_t)kWarpsPerCta * (nv + 1) * 4, s>>>(A);
+            long long ctas = std::min<long long>((n + kWarpsPerCta - 1) / kWarpsPerCta, (long long)std::max(occ, 1) * sms);
+            DQ_CUDA(cudaEventRecord(ctx->ev2, s));
+            k_batch_graphs<<<(unsigned)ctas, kWarpsPerCta * 32, smem, s>>>(A);
+            launches = 2;
+        }
+        DQ_CUDA(cudaEventRecord(ctx->ev3, s));
+    }
+    DQ_CUDA(cudaGetLastError());
+    DQ_CUDA(cudaEventRecord(ctx->ev1, s));
+    unsigned long long* h = ctx->pin + 128 - 8;          // (pinned: the copy is asynchronous)
+    DQ_CUDA(cudaMemcpyAsync(h, d_ctrl.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    DQ_CUDA(cudaStreamSynchronize(s));
+    DQ_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    DQ_CUDA(cudaEventElapsedTime(&ms_search, ctx->ev2, ctx->ev3));
+    if (h[5]) { g_err = "an instance has an edge endpoint out of range, a self-loop, or more than 255 later neighbours of one vertex"; return DQ_ERR_UNSUPPORTED; }
+    if (stats) {
+        stats->n_sat = h[1]; stats->n_unsat = h[2]; stats->n_budget = h[3]; stats->total_nodes = h[4];
+        stats->kernel_ms = ms; stats->search_kernel_ms = ms_search; stats->kernel_launches = launches;
+    }
+    return DQ_OK;
+}
+
+static int check_edge_off(const int64_t* edge_off, int64_t n) {
+    if (edge_off[0] != 0) { g_err = "edge_off[0] must be 0"; return DQ_ERR_INVALID; }
+    for (int64_t i = 0; i < n; i++) if (edge_off[i + 1] < edge_off[i]) { g_err = "edge_off must be non-decreasing"; return DQ_ERR_INVALID; }
+    return DQ_OK;
+}
+
+extern "C" {
+
 int dq_solve_batch_graphs(int32_t nv, int32_t k, const int64_t* edge_off, const uint8_t* edges, int64_t n,
                           const dq_batch_opts* opts, uint8_t* colours, uint64_t* nodes, uint8_t* status,
                           dq_batch_stats* stats) {
@@ -1108,70 +1254,55 @@ int dq_solve_batch_graphs(int32_t nv, int32_t k, const int64_t* edge_off, const 
     if (stats) memset(stats, 0, sizeof *stats);
     if (n == 0) return DQ_OK;
     if (!edge_off || !colours || !nodes || !status) { g_err = "null buffer"; return DQ_ERR_INVALID; }
+    int rc = check_edge_off(edge_off, n);
+    if (rc != DQ_OK) return rc;
     const long long total = edge_off[n];
+    if (total && !edges) { g_err = "null edge buffer"; return DQ_ERR_INVALID; }
     for (long long e = 0; e < 2 * total; e++) if (edges[e] >= nv) { g_err = "edge endpoint out of range"; return DQ_ERR_INVALID; }
     for (long long e = 0; e < total; e++) if (edges[2 * e] == edges[2 * e + 1]) { g_err = "edge with u == v"; return DQ_ERR_UNSUPPORTED; }
-    const bool reg_engine = k <= 4 && !(opts && opts->engine == DQ_ENGINE_WARP);       // register-resident warp engine (dq_reg_graphs.cuh)
-    if (opts && opts->engine == DQ_ENGINE_LANE) { g_err = "no lane engine for graph batches"; return DQ_ERR_UNSUPPORTED; }
-    int dev = 0, sms = 0;
-    DQ_CUDA(cudaGetDevice(&dev));
-    DQ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    DevBuf<long long> d_off; DevBuf<uint8_t> d_edges, d_col, d_status; DevBuf<uint32_t> d_ent_off; DevBuf<uint32_t> d_ent;
-    DevBuf<unsigned long long> d_nodes, d_ctrl;
-    auto cleanup = [&]() { d_off.release(); d_edges.release(); d_col.release(); d_status.release(); d_ent_off.release(); d_ent.release(); d_nodes.release(); d_ctrl.release(); };
-    struct Guard { decltype(cleanup)& f; ~Guard() { f(); } } guard{cleanup};
-    DQ_CUDA(d_off.reserve(n + 1)); DQ_CUDA(d_edges.reserve(2 * total)); DQ_CUDA(d_col.reserve((size_t)n * nv));
-    DQ_CUDA(d_status.reserve(n)); DQ_CUDA(d_ent_off.reserve((size_t)n * (nv + 1))); DQ_CUDA(d_ent.reserve(2 * total));
-    DQ_CUDA(d_nodes.reserve(n)); DQ_CUDA(d_ctrl.reserve(8));
-    cudaStream_t s = nullptr;
-    cudaEvent_t e0, e1;
-    DQ_CUDA(cudaEventCreate(&e0)); DQ_CUDA(cudaEventCreate(&e1));
+    if (opts && opts->engine == DQ_ENGINE_LANE && k > 4) { g_err = "the lane-group engine serves k <= 4"; return DQ_ERR_UNSUPPORTED; }
+    DeviceCtx* ctx = nullptr;
+    DQ_CUDA(device_ctx(&ctx));
+    cudaStream_t s = ctx->stream;
+    DevBuf<long long> d_off; DevBuf<uint8_t> d_edges, d_col, d_status; DevBuf<unsigned long long> d_nodes;
+    struct Guard {
+        cudaStream_t s; DevBuf<long long>& a; DevBuf<uint8_t>&b, &c, &d; DevBuf<unsigned long long>& e;
+        ~Guard() { cudaStreamSynchronize(s); a.release(); b.release(); c.release(); d.release(); e.release(); }
+    } guard{s, d_off, d_edges, d_col, d_status, d_nodes};
+    const long long edge_bytes = (2 * total + 15) & ~15ll;
+    DQ_CUDA(d_off.reserve(n + 1)); DQ_CUDA(d_edges.reserve(std::max<long long>(edge_bytes, 16))); DQ_CUDA(d_col.reserve((size_t)n * nv));
+    DQ_CUDA(d_status.reserve(n)); DQ_CUDA(d_nodes.reserve(n));
     DQ_CUDA(cudaMemcpyAsync(d_off.p, edge_off, (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, s));
     if (total) DQ_CUDA(cudaMemcpyAsync(d_edges.p, edges, 2 * total, cudaMemcpyHostToDevice, s));
-    DQ_CUDA(cudaMemsetAsync(d_ctrl.p, 0, 8 * sizeof(unsigned long long), s));
-    BatchGraphsArgs A;
-    A.nv = nv; A.k = k; A.edge_off = d_off.p; A.edges = d_edges.p; A.n = n; A.ent_off = d_ent_off.p; A.ent = d_ent.p;
-    A.budget = opts ? opts->node_budget : 0; A.cursor = d_ctrl.p; A.colours = d_col.p; A.nodes = d_nodes.p;
-    A.status = d_status.p; A.totals = d_ctrl.p + 1;
-    A.trail = nv * k + 32;
-    const size_t smem = warp_state_bytes(nv, A.trail) * kWarpsPerCta;
-    if (smem > 200 * 1024) { g_err = "instance state exceeds shared memory"; return DQ_ERR_UNSUPPORTED; }
-    int occ = 0;
-    int rc = max_ctas_per_sm(k_batch_graphs, kWarpsPerCta * 32, smem, &occ);
+    GraphBatchDev B{d_off.p, d_edges.p, edge_bytes, d_col.p, d_nodes.p, d_status.p};
+    rc = run_batch_graphs(nv, k, edge_off, B, n, opts, stats);
     if (rc != DQ_OK) return rc;
-    DQ_CUDA(cudaEventRecord(e0, s));
-    if (reg_engine) {
-        RegGraphsArgs R;
-        R.nv = nv; R.k = k; R.edge_off = d_off.p; R.edges = d_edges.p; R.n = n; R.budget = A.budget; R.cursor = d_ctrl.p;
-        R.colours = d_col.p; R.nodes = d_nodes.p; R.status = d_status.p; R.totals = d_ctrl.p + 1;
-        const size_t rsmem = reg_graphs_warp_bytes(nv, k) * kRegWarpsPerCta;
-        int rocc = 0;
-        rc = max_ctas_per_sm(k_batch_graphs_reg, kRegWarpsPerCta * 32, rsmem, &rocc);
-        if (rc != DQ_OK) return rc;
-        const long long rctas = std::min<long long>((n + kRegWarpsPerCta - 1) / kRegWarpsPerCta, (long long)std::max(rocc, 1) * sms);
-        k_batch_graphs_reg<<<(unsigned)rctas, kRegWarpsPerCta * 32, rsmem, s>>>(R);
-    } else {
-        k_graphs_build<<<(unsigned)((n + kWarpsPerCta - 1) / kWarpsPerCta), kWarpsPerCta * 32, (size_t)kWarpsPerCta * (nv + 1) * 4, s>>>(A);
-        long long ctas = std::min<long long>((n + kWarpsPerCta - 1) / kWarpsPerCta, (long long)std::max(occ, 1) * sms);
-        k_batch_graphs<<<(unsigned)ctas, kWarpsPerCta * 32, smem, s>>>(A);
-    }
-    DQ_CUDA(cudaGetLastError());
-    DQ_CUDA(cudaEventRecord(e1, s));
-    unsigned long long h[8];
-    DQ_CUDA(cudaMemcpyAsync(h, d_ctrl.p, sizeof h, cudaMemcpyDeviceToHost, s));
     DQ_CUDA(cudaMemcpyAsync(colours, d_col.p, (size_t)n * nv, cudaMemcpyDeviceToHost, s));
     DQ_CUDA(cudaMemcpyAsync(nodes, d_nodes.p, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
     DQ_CUDA(cudaMemcpyAsync(status, d_status.p, (size_t)n, cudaMemcpyDeviceToHost, s));
     DQ_CUDA(cudaStreamSynchronize(s));
-    if (stats) {
-        float ms = 0;
-        DQ_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-        stats->n_sat = h[1]; stats->n_unsat = h[2]; stats->n_budget = h[3]; stats->total_nodes = h[4];
-        stats->kernel_ms = ms; stats->kernel_launches = reg_engine ? 1 : 2;
-        stats->h2d_bytes = (size_t)(n + 1) * 8 + 2 * (size_t)total; stats->d2h_bytes = (size_t)n * (nv + 9);
-    }
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (stats) { stats->h2d_bytes = (size_t)(n + 1) * 8 + 2 * (size_t)total; stats->d2h_bytes = (size_t)n * (nv + 9); }
     return DQ_OK;
+}
+
+int dq_solve_batch_graphs_dev(int32_t nv, int32_t k, const int64_t* edge_off, const int64_t* edge_off_dev, const uint8_t* edges_dev,
+                              int64_t n, const dq_batch_opts* opts, uint8_t* colours_dev, uint64_t* nodes_dev, uint8_t* status_dev,
+                              dq_batch_stats* stats) {
+    if (nv < 1 || nv > kMaxGraphVertices || k < 1 || k > 32 || n < 0) { g_err = "bad argument"; return DQ_ERR_INVALID; }
+    if (stats) memset(stats, 0, sizeof *stats);
+    if (n == 0) return DQ_OK;
+    if (!edge_off || !edge_off_dev || !colours_dev || !nodes_dev || !status_dev) { g_err = "null buffer"; return DQ_ERR_INVALID; }
+    int rc = check_edge_off(edge_off, n);
+    if (rc != DQ_OK) return rc;
+    if (edge_off[n] && !edges_dev) { g_err = "null edge buffer"; return DQ_ERR_INVALID; }
+    if (((uintptr_t)edges_dev & 15) != 0) { g_err = "edges_dev must be 16-byte aligned"; return DQ_ERR_INVALID; }
+    // the edge lists cannot be validated on the host here: only the lane-group engine checks them on the device
+    if (k > 4 || (opts && opts->engine != DQ_ENGINE_AUTO && opts->engine != DQ_ENGINE_LANE)) {
+        g_err = "device-resident graph batches run on the lane-group engine (k <= 4) only"; return DQ_ERR_UNSUPPORTED;
+    }
+    GraphBatchDev B{(const long long*)edge_off_dev, edges_dev, (2 * (long long)edge_off[n] + 15) & ~15ll, colours_dev,
+                    (unsigned long long*)nodes_dev, status_dev};
+    return run_batch_graphs(nv, k, edge_off, B, n, opts, stats);
 }
 
 int dq_measure_int_peak(double* lane_ops_per_s, double* ms_out) {

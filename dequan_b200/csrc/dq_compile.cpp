@@ -375,6 +375,9 @@ int compile_model(const dq_model_desc* d, CompiledModel& M, std::string& err) {
                 }
             }
         }
+        // the class engine searches the variables in id order (all domains have N values: Reset's order is the identity);
+        // a caller-supplied assign_order that differs from it changes node counts and the first solution: generic engine
+        for (int p = 0; p < nv && queens; p++) queens = M.order[p] == p;
         if (queens && nv >= 2) { M.model_class = CLASS_QUEENS; M.queens_n = nv; }
     }
     // 9x9 Sudoku template: every variable on 1..9 (ascending), every arc a plain "different value", and the

@@ -106,7 +106,9 @@ enum dq_engine {
     DQ_ENGINE_AUTO  = 0,     /* fastest engine the compiled model qualifies for     */
     DQ_ENGINE_WARP  = 1,     /* generic warp-cooperative DFS (any supported model)  */
     DQ_ENGINE_LANE  = 2,     /* lane-per-subtree / lane-per-instance closed-form DFS
-                                (N-Queens class trees, 9x9 Sudoku class batches)    */
+                                (N-Queens class trees, 9x9 Sudoku class batches,
+                                colouring batches with k <= 4: a group of 1..32 lanes
+                                per instance)                                       */
     DQ_ENGINE_REG   = 3      /* register-resident warp DFS: trees of models with at
                                 most 32 variables, colouring batches with k <= 4     */
 };
@@ -160,6 +162,7 @@ typedef struct dq_batch_stats {
     double   kernel_ms;
     uint64_t kernel_launches;
     uint64_t h2d_bytes, d2h_bytes;
+    double   search_kernel_ms; /* graph batches: device time of the search kernel alone    */
 } dq_batch_stats;
 
 typedef struct dq_model dq_model;   /* compiled model: flat tables, host + HBM copies */
@@ -231,6 +234,16 @@ int dq_solve_batch_graphs(int32_t n_vertices, int32_t k, const int64_t *edge_off
                           const uint8_t *edges, int64_t n, const dq_batch_opts *opts,
                           uint8_t *colours, uint64_t *nodes, uint8_t *status,
                           dq_batch_stats *stats);
+
+/* Same, with the edge lists and the outputs resident in device memory (bench "value" leg).
+ * edge_off is the HOST copy of the offsets (it sizes the per-instance adjacency records),
+ * edge_off_dev / edges_dev the device copies; edges_dev must be 16-byte aligned and readable up
+ * to the next multiple of 16 bytes (the lists are fetched with 16-byte bulk copies).  k <= 4;
+ * edge endpoints are checked on the device (DQ_ERR_UNSUPPORTED if an instance is malformed).    */
+int dq_solve_batch_graphs_dev(int32_t n_vertices, int32_t k, const int64_t *edge_off,
+                              const int64_t *edge_off_dev, const uint8_t *edges_dev, int64_t n,
+                              const dq_batch_opts *opts, uint8_t *colours_dev, uint64_t *nodes_dev,
+                              uint8_t *status_dev, dq_batch_stats *stats);
 
 /* On-disk instance formats for the batch entry points (host-side parsing only).
  * Sudoku: one puzzle per line, 81 characters, '1'..'9' givens, '0' '.' '_' '*' blank; blank

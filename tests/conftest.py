@@ -21,6 +21,14 @@ def golden():
 
 
 @pytest.fixture(scope="session")
+def golden_large():
+    """Minutes-of-CPU runs of the unmodified reference (tests/golden/make_golden_large.py): 15/16/17-Queens,
+    config C4 as stated (G(200, c/199), k=3/4), the first 10 000 puzzles of the 1 M Sudoku batch."""
+    with open(os.path.join(ROOT, "tests", "golden", "reference_large.json")) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="session")
 def product_lib():
     """The CUDA library must exist (built by __graft_entry__.build()); building needs only nvcc."""
     from dequan_b200 import api

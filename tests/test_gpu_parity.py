@@ -251,11 +251,25 @@ def test_lane_engine_rejects_other_models(product_lib):
 
 
 @pytest.mark.parametrize("n,k", [(15, 0), (16, 0), (12, 1), (12, 7), (13, 10)])
-def test_lane_engine_larger_boards(product_lib, n, k):
-    """N=15/16 counts are OEIS A000170 + the node counts of SURVEY.md section 10 (cross-checked by the warp engine)."""
-    known = {12: (14200, 641974), 13: (73712, 3456855), 15: (2279184, 121498513), 16: (14772512, 795563572)}
+def test_lane_engine_larger_boards(golden, golden_large, product_lib, n, k):
+    """N <= 14: tests/golden/reference.json; N = 15, 16: tests/golden/reference_large.json — both are outputs of the
+    unmodified reference (solutions, stats.assigned_vars, DFS-first solution)."""
+    g = (golden if n <= 14 else golden_large)["nqueens"][str(n)]["count"]
     r = api.Model(nqueens(n)).solve_tree("count", engine="lane", split_depth=k)
-    assert (r.solutions, r.nodes) == known[n] and r.engine == "lane"
+    assert (r.solutions, r.nodes, r.first) == (g["solutions"], g["nodes"], g["first"]) and r.engine == "lane"
+
+
+@pytest.mark.parametrize("n", [15, 16])
+def test_first_value_subtrees_vs_reference(golden_large, product_lib, n):
+    """The reference's per-first-row-value runs (variable 0 fixed to v by a singleton domain: SURVEY.md section 8c) against
+    the same models here: the fixed variable leaves the N-Queens class, so this is the generic path at 10^7-node size."""
+    per = golden_large["nqueens"][str(n)]["per_first_value"]
+    assert len(per) == n
+    for v in (0, n // 2, n - 1):
+        csp = nqueens(n)
+        csp.domains[0] = type(csp.domains[0])(0, [v])          # Domain(Values, {v})
+        r = api.Model(csp).solve_tree("count")
+        assert (r.solutions, r.nodes) == (per[v]["solutions"], per[v]["nodes"]), (n, v, r)
 
 
 def test_int_peak_microbenchmark(product_lib):
@@ -275,6 +289,27 @@ def test_caller_supplied_assign_order_vs_oracle(product_lib):
         assert m.order() == order
         for mode in ("first", "count"):
             _cmp_tree(m.solve_tree(mode), O.solve(csp, mode), (seed, mode))
+
+
+def test_queens_with_caller_order_leaves_the_class_engine(product_lib):
+    """The N-Queens class engine walks the variables in id order: a model whose caller-supplied assign_order is
+    anything else must count through the generic engine, and agree with the oracle (node counts depend on the order)."""
+    import random
+    for n, seed in ((7, 1), (8, 2), (9, 3)):
+        csp = nqueens(n)
+        order = list(range(n))
+        random.Random(seed).shuffle(order)
+        csp.assign_order = order
+        m = api.Model(csp)
+        assert m.order() == order and m.info()["model_class"] != "queens"
+        for mode in ("first", "count"):
+            _cmp_tree(m.solve_tree(mode), O.solve(csp, mode), (n, mode))
+        with pytest.raises(api.DequanError):
+            m.solve_tree("count", engine="lane")
+    csp = nqueens(8)
+    csp.assign_order = list(range(8))                    # the identity, spelled out, still qualifies
+    m = api.Model(csp)
+    assert m.info()["model_class"] == "queens" and m.solve_tree("count").engine == "lane"
 
 
 # ---- lane-per-instance Sudoku engine (dq_lane_sudoku.cuh): task splitting must not change any result ----
@@ -428,21 +463,96 @@ def test_maximum_sizes_and_limits(product_lib):
     _same_batch(tmpl.solve_batch_cells(few), tmpl.solve_batch_cells(few, engine="warp"), "seven instances")
 
 
-@pytest.mark.parametrize("nv,k,c,budget", [(200, 3, 4.2, 30000), (200, 4, 7.0, 30000), (60, 3, 3.5, 0), (33, 2, 1.2, 0), (1, 3, 0.0, 0),
-                                           (254, 4, 6.0, 5000), (64, 1, 0.5, 0)])
-def test_colouring_register_engine_equals_warp_engine(product_lib, nv, k, c, budget):
-    """dq_reg_graphs.cuh (one register per lane) against the generic warp engine, itself pinned to the reference."""
-    lists = [G.colouring_instance(nv, c, 4242, i) if nv > 1 else np.zeros((0, 2), dtype=np.uint8) for i in range(96)]
+def _graph_lists(nv, c, count, seed=4242):
+    lists = [G.colouring_instance(nv, c, seed, i) if nv > 1 else np.zeros((0, 2), dtype=np.uint8) for i in range(count)]
     off = np.zeros(len(lists) + 1, dtype=np.int64)
     for i, e in enumerate(lists):
         off[i + 1] = off[i] + len(e)
     edges = np.ascontiguousarray(np.concatenate(lists, axis=0).astype(np.uint8)) if off[-1] else np.zeros((0, 2), dtype=np.uint8)
-    a = api.solve_batch_graphs(nv, k, off, edges, node_budget=budget)
+    return off, edges
+
+
+def _with_group(g, fn):
+    """Runs fn() with the lane-group engine forced to g lanes per instance (DQ_GRAPHS_GROUP; None = the library's choice)."""
+    old = os.environ.pop("DQ_GRAPHS_GROUP", None)
+    try:
+        if g is not None:
+            os.environ["DQ_GRAPHS_GROUP"] = str(g)
+        return fn()
+    finally:
+        os.environ.pop("DQ_GRAPHS_GROUP", None)
+        if old is not None:
+            os.environ["DQ_GRAPHS_GROUP"] = old
+
+
+@pytest.mark.parametrize("nv,k,c,budget", [(200, 3, 4.2, 30000), (200, 4, 7.0, 30000), (60, 3, 3.5, 0), (33, 2, 1.2, 0), (1, 3, 0.0, 0),
+                                           (254, 4, 6.0, 5000), (64, 1, 0.5, 0), (2, 2, 1.0, 0), (17, 4, 9.0, 0)])
+def test_colouring_engines_agree(product_lib, nv, k, c, budget):
+    """The lane-group engine (dq_group_graphs.cuh, every group size) and the register-resident warp engine
+    (dq_reg_graphs.cuh) against the generic warp engine, itself pinned to the reference."""
+    off, edges = _graph_lists(nv, c, 96)
     b = api.solve_batch_graphs(nv, k, off, edges, node_budget=budget, engine="warp")
-    _same_batch(a, b, (nv, k, c, budget))
-    assert a.launches == 1 and b.launches == 2
+    for g in (None, 1, 2, 4, 8, 16, 32):
+        a = _with_group(g, lambda: api.solve_batch_graphs(nv, k, off, edges, node_budget=budget))
+        _same_batch(a, b, (nv, k, c, budget, "group", g))
+        assert a.launches == 2
+    r = api.solve_batch_graphs(nv, k, off, edges, node_budget=budget, engine="reg")
+    _same_batch(r, b, (nv, k, c, budget, "reg"))
+    assert r.launches == 1 and b.launches == 2
     with pytest.raises(api.DequanError):        # a self-loop has no lowering (the reference would fail every value of that vertex)
         api.solve_batch_graphs(3, 3, np.array([0, 1], dtype=np.int64), np.array([[1, 1]], dtype=np.uint8))
+
+
+@pytest.mark.parametrize("group", [None, 1, 4, 8])
+def test_colouring_c4_vs_reference(golden_large, product_lib, group):
+    """BASELINE config C4 as stated — G(200, c/199), k=3 c in {4.0, 4.2, 4.4, 4.69}, k=4 c in {6, 7}, 64 instances each,
+    budget 100 000 nodes — against what the unmodified reference returns (tests/golden/make_golden_large.py):
+    status, node count and colours per instance."""
+    assert len(golden_large["colouring200"]) == 6
+    for case in golden_large["colouring200"]:
+        off, edges = G.colouring_batch(case["count"], case["n_vertices"], case["c"])
+        assert hashlib.sha256(edges.tobytes()).hexdigest() == case["sha256"]
+        r = _with_group(group, lambda: api.solve_batch_graphs(case["n_vertices"], case["k"], off, edges, node_budget=case["budget"]))
+        assert [api.OUTCOME[s] for s in r.status] == case["status"], (case["k"], case["c"])
+        assert r.nodes.tolist() == case["nodes"], (case["k"], case["c"])
+        for i, first in enumerate(case["first"]):
+            if first is not None:
+                assert r.solution[i].tolist() == first
+            else:
+                assert (r.solution[i] == 0xFF).all()
+        assert (r.n_sat, r.n_unsat, r.n_budget) == tuple(case["status"].count(x) for x in ("sat", "unsat", "budget"))
+        assert r.total_nodes == sum(case["nodes"])
+
+
+def test_colouring_group_engine_odd_inputs(product_lib):
+    """Duplicate edges, reversed endpoints, empty instances between full ones, a ragged batch that ends in an empty graph."""
+    rng = np.random.default_rng(5)
+    lists = []
+    for i in range(40):
+        if i % 7 == 3:
+            lists.append(np.zeros((0, 2), dtype=np.uint8))
+            continue
+        e = G.colouring_instance(40, 3.2, 77, i).astype(np.uint8)
+        e = np.concatenate([e, e[: len(e) // 3][:, ::-1]], axis=0)          # duplicates, endpoints swapped
+        lists.append(e[rng.permutation(len(e))])
+    lists.append(np.zeros((0, 2), dtype=np.uint8))
+    off = np.zeros(len(lists) + 1, dtype=np.int64)
+    for i, e in enumerate(lists):
+        off[i + 1] = off[i] + len(e)
+    edges = np.ascontiguousarray(np.concatenate(lists, axis=0))
+    b = api.solve_batch_graphs(40, 3, off, edges, engine="warp")
+    for g in (1, 2, 8, 32):
+        _same_batch(_with_group(g, lambda: api.solve_batch_graphs(40, 3, off, edges)), b, ("odd", g))
+    for i in (3, 40):
+        assert b.status[i] == 1 and b.nodes[i] == 40 and (b.solution[i] == 0).all()
+    # budgets on the boundary: an instance that needs exactly B nodes is solved with budget B, and busts with B - 1
+    need = int(b.nodes[0])
+    one = (off[:2].copy(), edges[: off[1]])
+    for budget in (need, need - 1, 1):
+        _same_batch(api.solve_batch_graphs(40, 3, *one, node_budget=budget), api.solve_batch_graphs(40, 3, *one, node_budget=budget, engine="warp"), budget)
+    assert api.solve_batch_graphs(40, 3, *one, node_budget=need).status[0] == b.status[0]
+    r = api.solve_batch_graphs(40, 3, *one, node_budget=need - 1)
+    assert r.status[0] == 2 and r.nodes[0] == need and (r.solution[0] == 0xFF).all()
 
 
 def test_register_tree_engine_equals_generic_engine(product_lib):
@@ -627,16 +737,32 @@ def test_queens_graph_replay_and_recapture(product_lib):
     assert m.solve_tree("count").search_kernel_ms == 0          # replayed: the graph is timed from outside only
 
 
-def test_17_queens_in_four_partitions(product_lib):
-    """BASELINE config C5 at full size, the way four GPUs split it (split depth 9):
-    the partitions' counts add up to OEIS A000170(17) and the reference's node count, and the lowest first-solution key
-    belongs to the reference's first solution."""
+def test_17_queens_in_four_partitions(golden_large, product_lib):
+    """BASELINE config C5 at full size, the way four GPUs split it (split depth 9): the partitions' counts add up to what
+    the unmodified reference returns for 17-Queens (tests/golden/reference_large.json: 17 single-threaded runs of
+    oracle/_ref/dequan_ref, one per first-row value), and the lowest first-solution key belongs to its first solution."""
+    g = golden_large["nqueens"]["17"]["count"]
+    assert g["solutions"] == 95815104                      # OEIS A000170(17), for the record
     csp = nqueens(17)
     m = api.Model(csp)
     parts = [m.solve_tree("count", part_rank=k, part_count=4) for k in range(4)]
-    assert all(p.split_depth == 9 for p in parts)
-    assert sum(p.solutions for p in parts) == 95815104 and sum(p.nodes for p in parts) == 5474619051
+    assert sum(p.solutions for p in parts) == g["solutions"] and sum(p.nodes for p in parts) == g["nodes"]
     best = min(parts, key=lambda p: p.first_key)
-    assert best.first == O.solve(csp, "first").first
+    assert best.first == g["first"] == O.solve(csp, "first").first
     whole = m.solve_tree("count")
-    assert (whole.solutions, whole.nodes, whole.first) == (95815104, 5474619051, best.first)
+    assert (whole.solutions, whole.nodes, whole.first) == (g["solutions"], g["nodes"], g["first"])
+
+
+def test_sudoku_10k_vs_reference(golden_large, product_lib):
+    """The first 10 000 puzzles of the 1 M batch (config C3): node count and solution of every puzzle against the
+    unmodified reference (810 binary NotEqual constraints, tests/golden/make_golden_large.py)."""
+    g = golden_large["sudoku10k"]
+    cells = G.sudoku_batch(g["n"], givens=g["givens"])
+    assert hashlib.sha256(cells.tobytes()).hexdigest() == g["sha256"]
+    tmpl = api.Model(sudoku_template())
+    for engine in ("auto", "warp"):
+        r = tmpl.solve_batch_cells(cells, engine=engine)
+        assert (r.status == 1).all()
+        assert r.nodes.tolist() == g["nodes"], engine
+        got = "".join(map(str, r.solution.reshape(-1).tolist()))
+        assert hashlib.sha256(got.encode()).hexdigest() == g["solutions_sha256"] and got == g["solutions"], engine
