@@ -1111,19 +1111,62 @@ struct GraphBatchDev {
     uint8_t* colours; unsigned long long* nodes; uint8_t* status;
 };
 
-template <int G>
-static int launch_graphs_group(const GroupGraphsArgs& A, int sms, cudaStream_t s) {
-    const size_t per_warp = graphs_group_warp_bytes(A.nvp, A.stride, G);
-    int wpc = kGroupWarpsPerCta;
-    while (wpc > 1 && per_warp * wpc > 200 * 1024) wpc >>= 1;
-    if (per_warp * wpc > 200 * 1024) { g_err = "instance state exceeds shared memory"; return DQ_ERR_UNSUPPORTED; }
+// Lane-per-instance engine (dq_group_graphs.cuh): two passes of k_graphs_adjacency (overflow statistics, records),
+// then the search.  DQ_ERR_UNSUPPORTED when the per-warp state does not fit an SM's shared memory.
+static int run_graphs_lane(int nv, int k, const int64_t* edge_off, const GraphBatchDev& B, int64_t n, unsigned long long budget,
+                           DeviceCtx* ctx, DevBuf<uint8_t>& d_adj, unsigned long long* d_ctrl) {
+    cudaStream_t s = ctx->stream;
+    const int sms = ctx->sm_count;
+    long long max_m = 0;
+    for (int64_t i = 0; i < n; i++) max_m = std::max<long long>(max_m, edge_off[i + 1] - edge_off[i]);
+    GroupGraphsArgs A;
+    A.nv = nv; A.k = k; A.nvp = (nv + 16) & ~15;
+    A.rw = kGraphRow; A.over_cap = 0;
+    A.stride = graphs_record_bytes(A.nvp, A.rw, 0);
+    A.edge_off = B.off; A.edges = B.edges; A.edge_bytes = B.edge_bytes; A.n = n;
+    A.budget = budget; A.cursor = d_ctrl; A.colours = B.colours; A.nodes = B.nodes; A.status = B.status;
+    A.totals = d_ctrl + 1;
+    A.adj = nullptr;
+    const int stage_cap = (int)(((2 * max_m + 15) & ~15ll) + 32);
+    // worst case of the record size: every edge of the largest instance in the overflow list
+    if (graphs_adj_warp_bytes(A.nvp, graphs_record_bytes(A.nvp, A.rw, (int)std::min<long long>(max_m + 256, 65535)), stage_cap) * kAdjWarpsPerCta > 200 * 1024) {
+        g_err = "edge list exceeds shared memory"; return DQ_ERR_UNSUPPORTED;
+    }
+    int occ_a = 0;
+    int rc = max_ctas_per_sm(k_graphs_adjacency<true>, kAdjWarpsPerCta * 32, graphs_adj_warp_bytes(A.nvp, A.stride, stage_cap) * kAdjWarpsPerCta, &occ_a);
+    if (rc != DQ_OK) return rc;
+    if (occ_a < 1) { g_err = "kernel does not fit an SM"; return DQ_ERR_UNSUPPORTED; }
+    DQ_CUDA(cudaMemsetAsync(B.status, 0, (size_t)n, s));
+    DQ_CUDA(cudaEventRecord(ctx->ev0, s));
+    // pass 1 over the edge lists: how long an overflow list do rows of 8 slots leave behind?  (one 8-byte read-back)
+    long long actas = std::max<long long>(1, std::min<long long>((n + kAdjWarpsPerCta - 1) / kAdjWarpsPerCta, (long long)occ_a * sms));
+    k_graphs_adjacency<true><<<(unsigned)actas, kAdjWarpsPerCta * 32, graphs_adj_warp_bytes(A.nvp, A.stride, stage_cap) * kAdjWarpsPerCta, s>>>(A, stage_cap);
+    unsigned long long* h_over = ctx->pin + 128 - 9;
+    DQ_CUDA(cudaMemcpyAsync(h_over, d_ctrl + 6, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    DQ_CUDA(cudaStreamSynchronize(s));
+    if (*h_over > 65535) { g_err = "an instance leaves more than 65535 edges outside its neighbour rows"; return DQ_ERR_UNSUPPORTED; }
+    A.over_cap = (int)((*h_over + 1) & ~1ull);
+    A.stride = graphs_record_bytes(A.nvp, A.rw, A.over_cap);
+    const size_t lane_smem = graphs_lane_warp_bytes(A.nvp, A.stride, A.over_cap);
+    if (lane_smem > 220 * 1024) { g_err = "instance state exceeds shared memory"; return DQ_ERR_UNSUPPORTED; }
+    DQ_CUDA(d_adj.reserve((size_t)n * A.stride));
+    A.adj = d_adj.p;
+    // pass 2: the records
+    const size_t adj_warp = graphs_adj_warp_bytes(A.nvp, A.stride, stage_cap);
+    rc = max_ctas_per_sm(k_graphs_adjacency<false>, kAdjWarpsPerCta * 32, adj_warp * kAdjWarpsPerCta, &occ_a);
+    if (rc != DQ_OK) return rc;
+    if (occ_a < 1) { g_err = "kernel does not fit an SM"; return DQ_ERR_UNSUPPORTED; }
+    actas = std::max<long long>(1, std::min<long long>((n + kAdjWarpsPerCta - 1) / kAdjWarpsPerCta, (long long)occ_a * sms));
+    k_graphs_adjacency<false><<<(unsigned)actas, kAdjWarpsPerCta * 32, adj_warp * kAdjWarpsPerCta, s>>>(A, stage_cap);
+    DQ_CUDA(cudaEventRecord(ctx->ev2, s));
+    // the search: one warp per CTA, as many CTAs per SM as their state lets in
     int occ = 0;
-    int rc = max_ctas_per_sm(k_graphs_group<G>, wpc * 32, per_warp * wpc, &occ);
+    rc = max_ctas_per_sm(k_graphs_lane, 32, lane_smem, &occ);
     if (rc != DQ_OK) return rc;
     if (occ < 1) { g_err = "kernel does not fit an SM"; return DQ_ERR_UNSUPPORTED; }
-    const long long groups_per_cta = (long long)wpc * (32 / G);
-    const long long ctas = std::max<long long>(1, std::min<long long>((A.n + groups_per_cta - 1) / groups_per_cta, (long long)occ * sms));
-    k_graphs_group<G><<<(unsigned)ctas, wpc * 32, per_warp * wpc, s>>>(A);
+    const long long ctas = std::max<long long>(1, std::min<long long>((n + 31) / 32, (long long)occ * sms));
+    k_graphs_lane<<<(unsigned)ctas, 32, lane_smem, s>>>(A);
+    DQ_CUDA(cudaEventRecord(ctx->ev3, s));
     return DQ_OK;
 }
 
@@ -1135,10 +1178,12 @@ static int run_batch_graphs(int nv, int k, const int64_t* edge_off, const GraphB
     const int sms = ctx->sm_count;
     const long long total = edge_off[n];
     const int engine = opts ? opts->engine : DQ_ENGINE_AUTO;
-    if (engine == DQ_ENGINE_LANE && k > 4) { g_err = "the lane-group engine serves k <= 4"; return DQ_ERR_UNSUPPORTED; }
+    if (engine == DQ_ENGINE_LANE && k > 4) { g_err = "the lane engine serves k <= 4"; return DQ_ERR_UNSUPPORTED; }
     if (engine == DQ_ENGINE_REG && k > 4) { g_err = "the register engine serves k <= 4"; return DQ_ERR_UNSUPPORTED; }
-    const bool group_engine = k <= 4 && (engine == DQ_ENGINE_AUTO || engine == DQ_ENGINE_LANE);
-    const bool reg_engine = k <= 4 && engine == DQ_ENGINE_REG;                       // register-resident warp engine (dq_reg_graphs.cuh)
+    // measured on B200 (scripts/colour_sweep.py, G(200, 4.2/199), 100 k-node budget): the lane engine needs a few
+    // thousand instances to fill its 32-instance warps (1 024 instances: 41 ms against 23 ms for one warp per instance,
+    // 8 192: 50 against 83 ms, 65 536: 146 against 588 ms)
+    bool lane_engine = k <= 4 && (engine == DQ_ENGINE_LANE || (engine == DQ_ENGINE_AUTO && n >= 4096));
     DevBuf<uint32_t> d_ent_off, d_ent; DevBuf<uint8_t> d_adj;
     DevBuf<unsigned long long> d_ctrl;
     struct Guard {                                       // buffers go back to the block cache only after the queue has drained
@@ -1149,47 +1194,17 @@ static int run_batch_graphs(int nv, int k, const int64_t* edge_off, const GraphB
     DQ_CUDA(cudaMemsetAsync(d_ctrl.p, 0, 8 * sizeof(unsigned long long), s));
     unsigned long long launches = 0;
     float ms = 0, ms_search = 0;
-    if (group_engine) {
-        long long max_m = 0;
-        for (int64_t i = 0; i < n; i++) max_m = std::max<long long>(max_m, edge_off[i + 1] - edge_off[i]);
-        GroupGraphsArgs A;
-        A.nv = nv; A.k = k; A.nvp = (nv + 15) & ~15;
-        A.stride = A.nvp + (int)((max_m + 15) & ~15ll);
-        A.edge_off = B.off; A.edges = B.edges; A.edge_bytes = B.edge_bytes; A.n = n;
-        A.budget = opts ? opts->node_budget : 0; A.cursor = d_ctrl.p; A.colours = B.colours; A.nodes = B.nodes; A.status = B.status;
-        A.totals = d_ctrl.p + 1;
-        DQ_CUDA(d_adj.reserve((size_t)n * A.stride));
-        A.adj = d_adj.p;
-        const int stage_cap = (int)(((2 * max_m + 15) & ~15ll) + 32);
-        const size_t adj_warp = (graphs_adj_warp_bytes(A.nvp, A.stride, stage_cap) + 127) & ~(size_t)127;
-        if (adj_warp * kAdjWarpsPerCta > 200 * 1024) { g_err = "edge list exceeds shared memory"; return DQ_ERR_UNSUPPORTED; }
-        int occ_a = 0;
-        int rc = max_ctas_per_sm(k_graphs_adjacency, kAdjWarpsPerCta * 32, adj_warp * kAdjWarpsPerCta, &occ_a);
-        if (rc != DQ_OK) return rc;
-        if (occ_a < 1) { g_err = "kernel does not fit an SM"; return DQ_ERR_UNSUPPORTED; }
-        // lanes per instance: as few as still give every SM a dozen warps (a trip of the search loop costs the same
-        // number of instructions whatever the group size); DQ_GRAPHS_GROUP overrides (sweeps)
-        int G = 1;
-        while (G < 8 && (double)n * G / 32.0 < 12.0 * sms) G <<= 1;
-        if (const char* e = getenv("DQ_GRAPHS_GROUP")) G = atoi(e);
-        DQ_CUDA(cudaMemsetAsync(B.status, 0, (size_t)n, s));
-        DQ_CUDA(cudaEventRecord(ctx->ev0, s));
-        const long long actas = std::max<long long>(1, std::min<long long>((n + kAdjWarpsPerCta - 1) / kAdjWarpsPerCta, (long long)occ_a * sms));
-        k_graphs_adjacency<<<(unsigned)actas, kAdjWarpsPerCta * 32, adj_warp * kAdjWarpsPerCta, s>>>(A, stage_cap);
-        DQ_CUDA(cudaEventRecord(ctx->ev2, s));
-        switch (G) {
-            case 1: rc = launch_graphs_group<1>(A, sms, s); break;
-            case 2: rc = launch_graphs_group<2>(A, sms, s); break;
-            case 4: rc = launch_graphs_group<4>(A, sms, s); break;
-            case 8: rc = launch_graphs_group<8>(A, sms, s); break;
-            case 16: rc = launch_graphs_group<16>(A, sms, s); break;
-            case 32: rc = launch_graphs_group<32>(A, sms, s); break;
-            default: g_err = "DQ_GRAPHS_GROUP must be 1, 2, 4, 8, 16 or 32"; rc = DQ_ERR_INVALID; break;
-        }
-        if (rc != DQ_OK) return rc;
-        DQ_CUDA(cudaEventRecord(ctx->ev3, s));
-        launches = 2;
-    } else {
+    if (lane_engine) {
+        const int rc = run_graphs_lane(nv, k, edge_off, B, n, opts ? opts->node_budget : 0, ctx, d_adj, d_ctrl.p);
+        if (rc == DQ_ERR_UNSUPPORTED && engine == DQ_ENGINE_AUTO) {       // (graphs too dense for the lane state: the warp engine below)
+            lane_engine = false;
+            DQ_CUDA(cudaStreamSynchronize(s));
+            DQ_CUDA(cudaMemsetAsync(d_ctrl.p, 0, 8 * sizeof(unsigned long long), s));
+        } else if (rc != DQ_OK) return rc;
+        launches = 3;
+    }
+    const bool reg_engine = !lane_engine && k <= 4 && engine != DQ_ENGINE_WARP;   // register-resident warp engine (dq_reg_graphs.cuh)
+    if (!lane_engine) {
         BatchGraphsArgs A;
         A.nv = nv; A.k = k; A.edge_off = B.off; A.edges = B.edges; A.n = n;
         A.budget = opts ? opts->node_budget : 0; A.cursor = d_ctrl.p; A.colours = B.colours; A.nodes = B.nodes;
@@ -1231,7 +1246,7 @@ static int run_batch_graphs(int nv, int k, const int64_t* edge_off, const GraphB
     DQ_CUDA(cudaStreamSynchronize(s));
     DQ_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     DQ_CUDA(cudaEventElapsedTime(&ms_search, ctx->ev2, ctx->ev3));
-    if (h[5]) { g_err = "an instance has an edge endpoint out of range, a self-loop, or more than 255 later neighbours of one vertex"; return DQ_ERR_UNSUPPORTED; }
+    if (h[5]) { g_err = "an instance has an edge endpoint out of range or a self-loop"; return DQ_ERR_UNSUPPORTED; }
     if (stats) {
         stats->n_sat = h[1]; stats->n_unsat = h[2]; stats->n_budget = h[3]; stats->total_nodes = h[4];
         stats->kernel_ms = ms; stats->search_kernel_ms = ms_search; stats->kernel_launches = launches;
@@ -1260,7 +1275,7 @@ int dq_solve_batch_graphs(int32_t nv, int32_t k, const int64_t* edge_off, const 
     if (total && !edges) { g_err = "null edge buffer"; return DQ_ERR_INVALID; }
     for (long long e = 0; e < 2 * total; e++) if (edges[e] >= nv) { g_err = "edge endpoint out of range"; return DQ_ERR_INVALID; }
     for (long long e = 0; e < total; e++) if (edges[2 * e] == edges[2 * e + 1]) { g_err = "edge with u == v"; return DQ_ERR_UNSUPPORTED; }
-    if (opts && opts->engine == DQ_ENGINE_LANE && k > 4) { g_err = "the lane-group engine serves k <= 4"; return DQ_ERR_UNSUPPORTED; }
+    if (opts && opts->engine == DQ_ENGINE_LANE && k > 4) { g_err = "the lane engine serves k <= 4"; return DQ_ERR_UNSUPPORTED; }
     DeviceCtx* ctx = nullptr;
     DQ_CUDA(device_ctx(&ctx));
     cudaStream_t s = ctx->stream;
@@ -1298,11 +1313,13 @@ int dq_solve_batch_graphs_dev(int32_t nv, int32_t k, const int64_t* edge_off, co
     if (((uintptr_t)edges_dev & 15) != 0) { g_err = "edges_dev must be 16-byte aligned"; return DQ_ERR_INVALID; }
     // the edge lists cannot be validated on the host here: only the lane-group engine checks them on the device
     if (k > 4 || (opts && opts->engine != DQ_ENGINE_AUTO && opts->engine != DQ_ENGINE_LANE)) {
-        g_err = "device-resident graph batches run on the lane-group engine (k <= 4) only"; return DQ_ERR_UNSUPPORTED;
+        g_err = "device-resident graph batches run on the lane engine (k <= 4) only"; return DQ_ERR_UNSUPPORTED;
     }
     GraphBatchDev B{(const long long*)edge_off_dev, edges_dev, (2 * (long long)edge_off[n] + 15) & ~15ll, colours_dev,
                     (unsigned long long*)nodes_dev, status_dev};
-    return run_batch_graphs(nv, k, edge_off, B, n, opts, stats);
+    dq_batch_opts o = opts ? *opts : dq_batch_opts{0, 0, 0};
+    o.engine = DQ_ENGINE_LANE;                           // (no fall-back to an engine that trusts the edge lists)
+    return run_batch_graphs(nv, k, edge_off, B, n, &o, stats);
 }
 
 int dq_measure_int_peak(double* lane_ops_per_s, double* ms_out) {

@@ -1,38 +1,50 @@
-// dq_group_graphs.cuh — lane-group engine for batches of k-colouring instances (BASELINE config C4: one graph per
-// instance, variables AddIntVar(0,k), one OpConstraint(u, v, NotEqual, 0) per edge; k <= 4, <= 254 vertices).
+// dq_group_graphs.cuh — lane-per-instance engine for batches of k-colouring instances (BASELINE config C4: one graph
+// per instance, variables AddIntVar(0,k), one OpConstraint(u, v, NotEqual, 0) per edge; k <= 4, <= 254 vertices).
 //
-// G lanes (1, 2, 4, 8, 16 or 32: the host picks by batch size) own ONE instance, so a warp searches 32/G
-// instances at once and every instruction of the search loop advances all of them: the register-resident warp
-// engine (dq_reg_graphs.cuh) spends ~100 warp instructions per node on a graph where a vertex has two or three
-// later neighbours, i.e. 29 of its 32 lanes have nothing to filter.
+// One LANE owns one instance, so a warp searches 32 instances at once and every instruction of the search loop
+// advances all of them (the register-resident warp engine, dq_reg_graphs.cuh, spends ~100 warp instructions per
+// node on a graph where a vertex has two or three later neighbours: 29 of its 32 lanes have nothing to filter).
+// What keeps a lane fast is instruction-level parallelism: the eight neighbour slots of a level are eight
+// INDEPENDENT load -> test chains, issued back to back.
 //
-// State of one instance, all in shared memory:
-//   S[q]      one 32-bit word per vertex, byte c = "who took colour c away from q": 0 = still in q's domain, d+2 =
-//             removed by the assignment of vertex d (OpConstraint::AplyArcConsistency -> Domain::Exclude,
-//             /root/reference/dequan.h:631-694, 985-1031), 1 = q itself is assigned colour c, 0xFE = c >= k.
-//             The current domain of q is the set of zero bytes; undoing the assignment of d
-//             (Assignment::RestoreSavedDomainStep, dequan.h:431-440) clears exactly the bytes that hold d+2 — no
-//             trail, no per-level record.
-//   adj       deg[nvp] (later-neighbour count per vertex) followed by the later neighbours of vertex 0, 1, ...:
-//             the static order is the vertex id (all domains have k values, Assignment::Reset ties by id,
-//             dequan.h:384-394), so "unassigned neighbour" = neighbour with a larger id.  Built once per batch by
-//             k_graphs_adjacency and brought in with ONE bulk copy (cp.async.bulk + mbarrier) per instance.
+// State of one instance, in shared memory, every array interleaved over the 32 lanes ([index][lane]: conflict-free):
+//   S[q]      one 32-bit word per vertex, byte c = "who took colour c away from q": 0 = still in q's domain, 254-u =
+//             removed by the assignment of vertex u (OpConstraint::AplyArcConsistency -> Domain::Exclude,
+//             /root/reference/dequan.h:631-694, 985-1031), 255 = c >= k.  At level d a byte below 255-d is either 0 or the
+//             mark of a vertex that is no longer assigned, so the current domain of q is the set of bytes < 255-d:
+//             backtracking (Assignment::RestoreSavedDomainStep, dequan.h:431-440) stores NOTHING — stale marks are
+//             ignored, and wiped when the vertex that could have left them is assigned again (its trip rewrites the
+//             words of all its later neighbours).  S[nv] is a dummy (all 255) that the padding of the neighbour rows
+//             points at: it never looks like a singleton and is never written.
+//   rows[d]   8 bytes: the first eight later neighbours of vertex d, padded with nv; a vertex with more has 0xFF in the
+//             last slot and the rest in a short (vertex, neighbour) list, walked by a cold path.  The static order
+//             is the vertex id (all domains have k values, Assignment::Reset ties by id, dequan.h:384-394), so
+//             "unassigned neighbour" = neighbour with a larger id.
+//   co[i]     two bytes: col[i], the colour vertex i holds (written on the way down, read on the way back and for
+//             the result), and open[i], the stack of the levels that still have untried colours: a failed level
+//             returns straight to the top one — the levels in between have nothing left to try and, with no undo
+//             to do, need no visit (they are four fifths of all returns on G(200, 4.2/199)).
+// The per-instance records (rows + overflow list) are built once per batch by k_graphs_adjacency (bulk-copy staged
+// edge lists in, bulk store out) and fetched by the search kernel with one bulk copy (cp.async.bulk + mbarrier) each.
 // One trip of the search loop handles a whole LEVEL: the forward check of every candidate colour of vertex d at
 // once — colour c wipes out a later neighbour q exactly when q's domain is {c} (dequan.h:663-668), so one pass
 // over the later neighbours yields the set F of failing colours; the first colour of the domain outside F is
 // the one the reference descends with, the colours it tried before that one are nodes that failed their check
-// (one AssignVar each, dequan.h:416-423), all counted.  A trip that returns to a level undoes the level's old
-// assignment and retries with the colours above it in the same pass over the neighbours.
+// (one AssignVar each, dequan.h:416-423), all counted.  The trip is straight-line predicated code; everything rare —
+// fetching the next instance, overflow neighbours, finishing an instance — sits behind one warp vote.
 #pragma once
 #include <cstdint>
+#include <type_traits>
 #include <cuda_runtime.h>
 
 namespace dq {
 
 struct GroupGraphsArgs {
     int nv, k;
-    int nvp;                    // nv rounded up to a multiple of 16
-    int stride;                 // bytes of one adjacency record (multiple of 16): deg[nvp] + later neighbours
+    int nvp;                    // (nv + 16) & ~15: room for the dummy word S[nv]
+    int rw;                     // neighbour slots per row (8)
+    int over_cap;               // (vertex, neighbour) pairs the overflow list of one record can hold
+    int stride;                 // bytes of one adjacency record (16 x an odd number)
     const long long* edge_off;  // [n+1]                                  (k_graphs_adjacency)
     const uint8_t* edges;       // [total][2], 16-byte aligned, readable up to the next multiple of 16 bytes
     long long edge_bytes;       // 2 * total rounded up to 16
@@ -43,10 +55,18 @@ struct GroupGraphsArgs {
     uint8_t* colours;           // [n][nv]
     unsigned long long* nodes;
     uint8_t* status;
-    unsigned long long* totals; // [0]=sat [1]=unsat [2]=budget [3]=nodes [4]=instances the adjacency kernel refused
+    unsigned long long* totals; // [0]=sat [1]=unsat [2]=budget [3]=nodes [4]=instances the adjacency kernel refused [5]=longest overflow list
 };
 
-constexpr int kGroupWarpsPerCta = 4;
+// record layout: rows[nvp][rw] | xflag[nvp] | u16 n_over, 14 bytes unused | over[over_cap][2]
+__host__ __device__ inline int graphs_record_bytes(int nvp, int rw, int over_cap) {
+    int b = nvp * rw + nvp + 16 + 2 * over_cap;
+    b = (b + 15) & ~15;
+    if (((b >> 4) & 1) == 0) b += 16;           // 16 x odd: the records of a warp's instances start in different banks
+    return b;
+}
+
+constexpr int kGraphRow = 8;          // neighbour slots per vertex row
 constexpr int kAdjWarpsPerCta = 4;
 
 // ---- bulk-copy (TMA) + mbarrier primitives: SASS UBLKCP / SYNCS ----
@@ -78,23 +98,29 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 
 // ---------------------------------------------------------------------------------------------------------------
 // Adjacency records.  One warp per instance, instances dealt round-robin; the raw edge list of the NEXT instance is
-// in flight (bulk copy into the other staging buffer) while the current one is counted, scanned and scattered in
-// shared memory; the finished record leaves with one bulk store.
+// in flight (bulk copy into the other staging buffer) while the current one is scattered into its rows in shared
+// memory; the finished record leaves with one bulk store.
 __host__ __device__ inline size_t graphs_adj_warp_bytes(int nvp, int stride, int stage_cap) {
-    return (size_t)2 * stage_cap + (size_t)stride + (size_t)nvp * 4 * 2 + 16;
+    return (((size_t)2 * stage_cap + (size_t)stride + (size_t)nvp * 4 + 32) + 127) & ~(size_t)127;
 }
 
+// STATS_ONLY: the same pass over the edge lists, but all it produces is the largest overflow list any instance of
+// the batch needs for rows of A.rw slots (totals[5], atomicMax) — the host sizes the records with it.
+template <bool STATS_ONLY>
 __global__ void __launch_bounds__(kAdjWarpsPerCta * 32)
 k_graphs_adjacency(GroupGraphsArgs A, int stage_cap) {
     extern __shared__ __align__(128) unsigned char ga_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int nvp = A.nvp;
-    unsigned char* base = ga_raw + (size_t)wib * ((graphs_adj_warp_bytes(nvp, A.stride, stage_cap) + 127) & ~(size_t)127);
+    const int nv = A.nv, nvp = A.nvp, rw = A.rw;
+    unsigned char* base = ga_raw + (size_t)wib * graphs_adj_warp_bytes(nvp, A.stride, stage_cap);
     auto stage = [&](int b) { return base + (size_t)b * stage_cap; };
     unsigned char* rec = base + 2 * (size_t)stage_cap;
+    unsigned char* xflag = rec + (size_t)nvp * rw;
+    unsigned char* hdr = xflag + nvp;
+    unsigned char* over = hdr + 16;
     uint32_t* cnt = reinterpret_cast<uint32_t*>(rec + A.stride);
-    uint32_t* pos = cnt + nvp;
-    const uint32_t mbar0 = smem_u32(pos + nvp);
+    uint32_t* n_over = cnt + nvp;
+    const uint32_t mbar0 = smem_u32(cnt + nvp + 2);
     if (lane == 0) { mbar_init(mbar0, 1); mbar_init(mbar0 + 8, 1); mbar_init_fence(); }
     __syncwarp();
     const long long total_warps = (long long)gridDim.x * kAdjWarpsPerCta;
@@ -125,42 +151,47 @@ k_graphs_adjacency(GroupGraphsArgs A, int stage_cap) {
         long long a0; uint32_t bytes, head;
         span(i, &a0, &bytes, &head);
         const uint32_t m = (uint32_t)(A.edge_off[i + 1] - A.edge_off[i]);
-        bool bad = bytes > (uint32_t)stage_cap || (uint32_t)nvp + m > (uint32_t)A.stride;
+        bool bad = bytes > (uint32_t)stage_cap;
         if (bytes && bytes <= (uint32_t)stage_cap) { mbar_wait(mbar0 + 8 * b, (parity >> b) & 1u); parity ^= 1u << b; }
         const unsigned char* e = stage(b) + head;
-        for (int q = lane; q < nvp; q += 32) cnt[q] = 0;
+        for (int q = lane; q < nvp; q += 32) { cnt[q] = 0; xflag[q] = 0; }
+        if (!STATS_ONLY)
+            for (int x = lane; x < nvp * rw; x += 32) rec[x] = (unsigned char)nv;      // padding: the dummy vertex
+        if (lane == 0) *n_over = 0;
         __syncwarp();
         if (!bad)
             for (uint32_t x = lane; x < m; x += 32) {
                 const int u = e[2 * x], v = e[2 * x + 1];
-                if (u >= A.nv || v >= A.nv || u == v) bad = true;      // (the host-buffer entry point has refused these already)
-                else atomicAdd(&cnt[min(u, v)], 1u);
+                if (u >= nv || v >= nv || u == v) { bad = true; continue; }     // (the host-buffer entry point has refused these already)
+                const int lo = min(u, v), hi = max(u, v);
+                const uint32_t slot = atomicAdd(&cnt[lo], 1u);
+                if (slot < (uint32_t)rw) { if (!STATS_ONLY) rec[lo * rw + slot] = (unsigned char)hi; }
+                else {
+                    const uint32_t o = atomicAdd(n_over, 1u);
+                    if (!STATS_ONLY && o < (uint32_t)A.over_cap) { over[2 * o] = (unsigned char)lo; over[2 * o + 1] = (unsigned char)hi; }
+                }
             }
-        bad = __any_sync(0xFFFFFFFFu, bad);
         __syncwarp();
-        // exclusive scan of the per-vertex counts: lane l owns vertices 8l .. 8l+7 (nvp <= 256)
-        uint32_t c[8], sum = 0;
-#pragma unroll
-        for (int j = 0; j < 8; j++) { const int q = lane * 8 + j; c[j] = q < nvp ? cnt[q] : 0u; sum += c[j]; }
-        uint32_t incl = sum;
-        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += t; }
-        uint32_t run = incl - sum;
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const int q = lane * 8 + j;
-            if (q < nvp) { pos[q] = run; rec[q] = (unsigned char)c[j]; if (c[j] > 255u) bad = true; }
-            run += c[j];
+        // a vertex with more neighbours than slots: its last slot becomes the marker 0xFF (the search kernel's cue to walk
+        // the overflow list), the neighbour that sat there joins the list
+        for (int q = lane; q < nvp; q += 32)
+            if (cnt[q] > (uint32_t)rw) {
+                const uint32_t o = atomicAdd(n_over, 1u);
+                if (!STATS_ONLY) {
+                    if (o < (uint32_t)A.over_cap) { over[2 * o] = (unsigned char)q; over[2 * o + 1] = rec[q * rw + rw - 1]; }
+                    rec[q * rw + rw - 1] = 0xFF;
+                    xflag[q] = 1;
+                }
+            }
+        __syncwarp();
+        if (STATS_ONLY) {
+            if (lane == 0 && *n_over) atomicMax(A.totals + 5, (unsigned long long)*n_over);
+            __syncwarp();
+            continue;
         }
-        bad = __any_sync(0xFFFFFFFFu, bad);
-        __syncwarp();
-        if (!bad)
-            for (uint32_t x = lane; x < m; x += 32) {
-                const int u = e[2 * x], v = e[2 * x + 1];
-                const uint32_t slot = atomicAdd(&pos[min(u, v)], 1u);
-                rec[nvp + slot] = (unsigned char)max(u, v);
-            }
-        if (bad) {                                       // the search kernel sees an edgeless record and the status says why
-            for (int q = lane; q < nvp; q += 32) rec[q] = 0;
+        bad = __any_sync(0xFFFFFFFFu, bad) || *n_over > (uint32_t)A.over_cap;
+        if (lane == 0) { hdr[0] = (unsigned char)(*n_over & 0xFF); hdr[1] = (unsigned char)(*n_over >> 8); }
+        if (bad) {                                       // the search kernel skips the instance and the status says why
             if (lane == 0) { A.status[i] = 0xFE; refused++; }
         }
         __syncwarp();
@@ -177,185 +208,218 @@ k_graphs_adjacency(GroupGraphsArgs A, int stage_cap) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// bit 7 of every zero byte of w (exact, no borrow artefacts)
-__device__ __forceinline__ uint32_t zero_bytes(uint32_t w) { return ~(((w & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | w | 0x7F7F7F7Fu); }
-__device__ __forceinline__ uint32_t byte_of(uint32_t w, uint32_t c) { return __byte_perm(w, 0u, 0x4440u | c); }
+// bit 7 of every byte of x that is (unsigned) below the byte replicated in y; yl = y & 0x7F7F7F7F
+__device__ __forceinline__ uint32_t bytes_below(uint32_t x, uint32_t y, uint32_t yl) {
+    const uint32_t t = (x | 0x80808080u) - yl;                // per byte, no borrow across bytes: bit 7 = (low 7 bits of x >= those of y)
+    return ((~x & y) | (~(x ^ y) & ~t)) & 0x80808080u;
+}
 __device__ __forceinline__ void sts8(uint32_t addr, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 __device__ __forceinline__ uint32_t lds32(uint32_t addr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory"); return v; }
+__device__ __forceinline__ uint32_t lds16(uint32_t addr) { uint32_t v; asm volatile("{\n\t.reg .u16 t;\n\tld.shared.u16 t, [%1];\n\tcvt.u32.u16 %0, t;\n\t}" : "=r"(v) : "r"(addr) : "memory"); return v; }
 __device__ __forceinline__ uint32_t lds8(uint32_t addr) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr) : "memory"); return v; }
 
-// per-warp shared memory of k_graphs_group: S words interleaved over the warp's instances, one adjacency record and
-// one mbarrier per instance
-__host__ __device__ inline size_t graphs_group_warp_bytes(int nvp, int stride, int g) {
-    const int ipw = 32 / g;
-    return (size_t)ipw * ((size_t)nvp * 4 + (size_t)stride + 16);
+__device__ __forceinline__ void lds64(uint32_t addr, uint32_t& lo, uint32_t& hi) {
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void sts64(uint32_t addr, uint32_t lo, uint32_t hi) {
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(lo), "r"(hi) : "memory");
+}
+__device__ __forceinline__ void sts16(uint32_t addr, uint32_t v) {
+    asm volatile("{\n\t.reg .u16 t;\n\tcvt.u16.u32 t, %1;\n\tst.shared.u16 [%0], t;\n\t}" ::"r"(addr), "r"(v) : "memory");
 }
 
-// OR of `fail` (bits 7, 15, 23, 31 only) over the G lanes of each group, every lane of the warp taking part: group g
-// parks its four bits at 7-g, 15-g, 23-g, 31-g, so ONE warp-wide REDUX.OR serves all (at most 8) groups of the warp.
-template <int G>
-__device__ __forceinline__ uint32_t group_or_fail(uint32_t fail, int g) {
-    if (G == 1) return fail;
-    if (G == 2) return fail | __shfl_xor_sync(0xFFFFFFFFu, fail, 1);
-    const uint32_t all = __reduce_or_sync(0xFFFFFFFFu, fail >> g);
-    return (all << g) & 0x80808080u;
+// shared memory of one warp (= one CTA) of k_graphs_lane
+__host__ __device__ inline size_t graphs_lane_warp_bytes(int nvp, int stride, int over_cap) {
+    return (size_t)nvp * (128 + 64) + (size_t)over_cap * 64 + (size_t)stride + 16;
 }
 
-// The loop is warp-synchronous: every trip, each group that holds an instance handles one level of it; groups without
-// one fetch the next instance of the batch; the warp leaves when the batch is empty and every group is done.
-template <int G>
-__global__ void __launch_bounds__(kGroupWarpsPerCta * 32)
-k_graphs_group(GroupGraphsArgs A) {
-    extern __shared__ __align__(128) unsigned char gg_raw[];
-    constexpr int IPW = 32 / G;
+__global__ void __launch_bounds__(32)
+k_graphs_lane(GroupGraphsArgs A) {
+    extern __shared__ __align__(128) unsigned char gl_raw[];
     constexpr uint32_t FULL = 0xFFFFFFFFu;
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int g = lane / G, lg = lane % G;
+    constexpr int kLeftCap = 0x7FFF0000;
+    const uint32_t lane = threadIdx.x;
     const int nv = A.nv, nvp = A.nvp;
-    unsigned char* wbase = gg_raw + (size_t)wib * graphs_group_warp_bytes(nvp, A.stride, G);
-    // S[q][instance of the warp]: lanes of different groups never share a bank on the same q
-    const uint32_t s_base = smem_u32(wbase) + 4u * (uint32_t)g;
-    const uint32_t adj_s = smem_u32(wbase + (size_t)IPW * nvp * 4 + (size_t)g * A.stride);
-    const uint32_t mbar = smem_u32(wbase + (size_t)IPW * ((size_t)nvp * 4 + A.stride) + (size_t)g * 16);
-    auto S = [&](uint32_t q) { return s_base + q * (4u * IPW); };
-    if (lg == 0) { mbar_init(mbar, 1); mbar_init_fence(); }
+    const uint32_t base_s = smem_u32(gl_raw);
+    const uint32_t s_s = base_s + 4u * lane;                                  // S[q]    at s_s + q * 128
+    const uint32_t co_s = base_s + (uint32_t)nvp * 128u + 2u * lane;          // co[i]   at co_s + i * 64: byte 0 col[i], byte 1 open[i]
+    const uint32_t over_s = base_s + (uint32_t)nvp * 192u + 2u * lane;        // over[p] at over_s + p * 64: (vertex, neighbour)
+    const uint32_t stage_s = base_s + (uint32_t)nvp * 192u + (uint32_t)A.over_cap * 64u;
+    // the neighbour rows stay in the record (HBM, L2- and L1-resident while the search is around that depth): 8 bytes per
+    // level and lane, the next level's row fetched a trip ahead
+    const uint2* rows_g = reinterpret_cast<const uint2*>(A.adj);
+    uint2 row_cur = make_uint2(0u, 0u);                 // rows[d] when row_ok
+    bool row_ok = false;
+    const uint32_t mbar = stage_s + (uint32_t)A.stride;
+    // lanes without an instance run the trip on whatever their slots hold: start from zeros (vertex 0, no neighbours)
+    for (uint32_t x = 4u * lane; x < (uint32_t)graphs_lane_warp_bytes(nvp, A.stride, A.over_cap); x += 128u) sts32(base_s + x, 0u);
+    __syncwarp();
+    if (lane == 0) { mbar_init(mbar, 1); mbar_init_fence(); }
     __syncwarp();
     uint32_t parity = 0;
-    const uint32_t init_word = A.k >= 4 ? 0u : (0xFEFEFEFEu << (8 * A.k));
+    const uint32_t init_word = A.k >= 4 ? 0u : (FULL << (8 * A.k));
     const unsigned long long budget = A.budget ? A.budget : ~0ull;
     unsigned long long t_sat = 0, t_unsat = 0, t_budget = 0, t_nodes = 0;
 
-    // state of the group's instance (identical in its G lanes)
-    bool have = false, idle = false, ret = false;
+    // state of the lane's instance
+    bool have = false, idle = false, pend = false, ret = false;
     long long inst = 0;
-    unsigned long long nodes = 0;
-    int d = 0;
-    uint32_t off = 0;
+    unsigned long long nodes_base = 0;                   // nodes counted before `left` was last set
+    int left = 0, left0 = 0;                             // nodes the budget still allows (32-bit window of it) / its start value
+    int code = 0;                                        // why the trip stopped the instance: bit 0 a solution, bit 1 tree exhausted (neither: `left` ran out)
+    uint32_t d = 0, sp = 0, n_over = 0;
 
     for (;;) {
-        const bool need = !have && !idle;
-        if (__any_sync(FULL, need)) {
-            long long i_new = 0;
-            if (need && lg == 0) i_new = (long long)atomicAdd(A.cursor, 1ull);
-            i_new = __shfl_sync(FULL, i_new, g * G);
-            bool fresh = false;
-            if (need) {
-                if (i_new >= A.n) idle = true;
-                else {
-                    inst = i_new;
-                    fresh = true;
-                    if (lg == 0) {
-                        mbar_expect_tx(mbar, (uint32_t)A.stride);
-                        bulk_g2s(adj_s, A.adj + (size_t)inst * A.stride, (uint32_t)A.stride, mbar);
-                    }
-                    for (int q = lg; q < nvp; q += G) asm volatile("st.shared.u32 [%0], %1;" ::"r"(S(q)), "r"(init_word) : "memory");
-                    nodes = 0; d = 0; off = 0; ret = false;
-                }
-            }
-            if (fresh) {
-                mbar_wait(mbar, parity);
-                parity ^= 1;
-                have = true;
-                if (A.status[inst] == 0xFE) {             // k_graphs_adjacency could not build this instance's record
-                    if (lg == 0) { A.nodes[inst] = 0; A.status[inst] = 3; }
-                    for (int v = lg; v < nv; v += G) A.colours[(size_t)inst * nv + v] = 0xFF;
-                    have = false;
-                }
-            }
-            __syncwarp();
-            if (__all_sync(FULL, idle)) break;
-        }
-
         // ---- one trip = one level entered or re-entered (ForwardCheckingStep, dequan.h:494-571), level d = vertex d ----
-        uint32_t fail = 0, cand = 0, c_old = 0, deg = 0, q0 = 0, w0 = FULL;
-        const uint32_t undo_id = (uint32_t)d + 2u;
-        const bool last = d == nv - 1;
-        bool has0 = false;
-        if (have) {
-            uint32_t wd = lds32(S(d));
-            if (ret) {
-                // back at level d: its assignment (the byte that reads 1) is undone, the colours above it are left
-                const uint32_t mk = zero_bytes(wd ^ 0x01010101u);
-                c_old = (31u - (uint32_t)__clz((int)mk)) >> 3;
-                wd &= ~(0xFFu << (8 * c_old));
-                if (lg == 0) sts8(S(d) + c_old, 0u);
-                cand = zero_bytes(wd) & ~(mk | (mk - 1u));
-            } else cand = zero_bytes(wd);
-            if (!last) {
-                deg = lds8(adj_s + d);
-                // first pass over the later neighbours: one per lane, kept in registers for the write-back
-                has0 = (uint32_t)lg < deg;
-                if (has0) {
-                    q0 = lds8(adj_s + nvp + off + lg);
-                    w0 = lds32(S(q0));
-                    if (ret && byte_of(w0, c_old) == undo_id) { w0 &= ~(0xFFu << (8 * c_old)); sts8(S(q0) + c_old, 0u); }
-                    const uint32_t t = zero_bytes(w0);
-                    if (__popc(t) == 1) fail |= t;
-                }
-                for (uint32_t j = lg + G; j < deg; j += G) {
-                    const uint32_t q = lds8(adj_s + nvp + off + j);
-                    uint32_t w = lds32(S(q));
-                    if (ret && byte_of(w, c_old) == undo_id) { w &= ~(0xFFu << (8 * c_old)); sts8(S(q) + c_old, 0u); }
-                    const uint32_t t = zero_bytes(w);
-                    if (__popc(t) == 1) fail |= t;
-                }
-            }
+        const uint32_t wd = lds32(s_s + d * 128u);
+        if (!row_ok) { row_cur = __ldg(rows_g + d); row_ok = true; }
+        const uint2 row_next = __ldg(rows_g + d + 1u);
+        uint32_t r_lo = row_cur.x, r_hi = row_cur.y;
+        const uint32_t c_old = lds8(co_s + d * 64u);                 // (meaningful when ret)
+        const uint32_t d_pop = lds8(co_s + sp * 64u - 63u);          // open[sp - 1] (meaningful when sp > 0)
+        const bool more = (r_hi >> 24) == 0xFFu;                     // the row goes on in the overflow list
+        if (more) r_hi = (r_hi & 0x00FFFFFFu) | ((uint32_t)nv << 24);   // (the marker is not a vertex: look at the dummy instead)
+        const uint32_t y = (255u - d) * 0x01010101u, yl = y & 0x7F7F7F7Fu;     // bytes below 255-d: in the domain
+        const uint32_t mark = 254u - d;
+        uint32_t a[8], w[8], f[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const uint32_t q = ((j < 4 ? r_lo : r_hi) >> (8 * (j & 3))) & 0xFFu;
+            a[j] = s_s + q * 128u;
+            w[j] = lds32(a[j]);
         }
-        fail = group_or_fail<G>(fail, g);
-        if (have) {
-            // colour c wipes out a later neighbour exactly when that neighbour's domain is {c} (dequan.h:663-668): the
-            // colours of `cand` up to the first one outside `fail` are the nodes the reference visits at this level
-            const uint32_t pass = cand & ~fail;
-            const uint32_t bit = pass & (0u - pass);
-            const uint32_t tried = pass ? cand & (bit | (bit - 1u)) : cand;
-            nodes += last ? 1u : (uint32_t)__popc(tried);
-            int outcome = -1;
-            uint32_t last_col = 0;
-            if (nodes > budget) outcome = 2;
-            else if (last) { outcome = 1; last_col = (31u - (uint32_t)__clz((int)(cand & (0u - cand)))) >> 3; }
-            else if (pass == 0u) {
-                if (d == 0) outcome = 0;
-                else { --d; off -= lds8(adj_s + d); ret = true; }
-            } else {
-                const uint32_t c = (31u - (uint32_t)__clz((int)bit)) >> 3;
-                if (has0 && (w0 & (0xFFu << (8 * c))) == 0u) sts8(S(q0) + c, undo_id);
-                for (uint32_t j = lg + G; j < deg; j += G) {
-                    const uint32_t q = lds8(adj_s + nvp + off + j);
-                    if (lds8(S(q) + c) == 0u) sts8(S(q) + c, undo_id);
-                }
-                if (lg == 0) sts8(S(d) + c, 1u);
-                off += deg;
-                ++d;
-                ret = false;
-            }
-            if (outcome >= 0) {
-                if (outcome == 2) nodes = budget + 1;
-                uint8_t* out = A.colours + (size_t)inst * nv;
-                for (int v = lg; v < nv; v += G) {
-                    uint32_t col = 0xFFu;
-                    if (outcome == 1) {
-                        const uint32_t mk = zero_bytes(lds32(S(v)) ^ 0x01010101u);
-                        col = v == nv - 1 ? last_col : (31u - (uint32_t)__clz((int)mk)) >> 3;
+        uint32_t fail = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            f[j] = bytes_below(w[j], y, yl);
+            fail |= (f[j] & (f[j] - 1u)) ? 0u : f[j];                // a neighbour down to one colour forbids it
+        }
+        // cold work pending in this warp?  (a lane without an instance, an instance that just ended, overflow neighbours)
+        if (__any_sync(FULL, pend || (!have && !idle) || (have && more))) {
+            if (__any_sync(FULL, pend || (!have && !idle))) {
+                // ---- results out ----
+                if (pend) {
+                    unsigned long long nodes = nodes_base + (unsigned long long)(left0 - left);
+                    if (code == 0 && nodes <= budget) {            // only the 32-bit window ran out: open the next one
+                        nodes_base = nodes;
+                        left0 = left = (int)min(budget - nodes, (unsigned long long)kLeftCap);
+                        have = true;
+                    } else {
+                        const int outcome = nodes > budget ? 2 : ((code & 1) ? 1 : 0);
+                        if (outcome == 2) nodes = budget + 1;
+                        uint8_t* out = A.colours + (size_t)inst * nv;
+                        for (int v = 0; v < nv; v++) out[v] = outcome == 1 ? (uint8_t)lds8(co_s + (uint32_t)v * 64u) : (uint8_t)0xFF;
+                        A.nodes[inst] = nodes;
+                        A.status[inst] = (uint8_t)outcome;
+                        t_nodes += nodes;
+                        t_sat += outcome == 1; t_unsat += outcome == 0; t_budget += outcome == 2;
+                        d = 0; sp = 0; ret = false; row_ok = false;
                     }
-                    out[v] = (uint8_t)col;
+                    pend = false;
                 }
-                if (lg == 0) {
-                    A.nodes[inst] = nodes;
-                    A.status[inst] = (uint8_t)outcome;
-                    t_nodes += nodes;
-                    t_sat += outcome == 1; t_unsat += outcome == 0; t_budget += outcome == 2;
+                // ---- next instances in: one bulk copy per record into the staging buffer, then into the lane's columns ----
+                uint32_t needy = __ballot_sync(FULL, !have && !idle);
+                while (needy) {
+                    const int t = __ffs((int)needy) - 1;
+                    needy &= needy - 1u;
+                    long long i_new = 0;
+                    if (lane == 0) i_new = (long long)atomicAdd(A.cursor, 1ull);
+                    i_new = __shfl_sync(FULL, i_new, 0);
+                    if (i_new >= A.n) {                            // the batch is empty: this lane and the remaining ones are done
+                        if ((int)lane == t || ((needy >> lane) & 1u)) idle = true;
+                        break;
+                    }
+                    if (lane == 0) {
+                        mbar_expect_tx(mbar, (uint32_t)A.stride);
+                        bulk_g2s(stage_s, A.adj + (size_t)i_new * A.stride, (uint32_t)A.stride, mbar);
+                    }
+                    const bool refused = A.status[i_new] == 0xFE;  // k_graphs_adjacency could not build this instance's record
+                    mbar_wait(mbar, parity);
+                    parity ^= 1;
+                    if (refused) {
+                        if (lane == 0) { A.nodes[i_new] = 0; A.status[i_new] = 3; }
+                        for (int v = lane; v < nv; v += 32) A.colours[(size_t)i_new * nv + v] = 0xFF;
+                        needy |= 1u << t;                          // the lane still needs an instance
+                    } else {
+                        for (uint32_t q = lane; q < (uint32_t)nvp; q += 32)
+                            sts32(base_s + q * 128u + 4u * t, q == (uint32_t)nv ? FULL : init_word);
+                        const uint32_t n_ov = lds16(stage_s + (uint32_t)nvp * 9u);
+                        for (uint32_t p = lane; p < (uint32_t)A.over_cap; p += 32)
+                            sts16(base_s + (uint32_t)nvp * 192u + p * 64u + 2u * t, p < n_ov ? lds16(stage_s + (uint32_t)nvp * 9u + 16u + 2u * p) : 0xFFFFu);
+                        if ((int)lane == t) {
+                            inst = i_new; have = true; n_over = n_ov;
+                            rows_g = reinterpret_cast<const uint2*>(A.adj + (size_t)i_new * A.stride);
+                            row_ok = false;
+                            nodes_base = 0; d = 0; sp = 0; ret = false;
+                            left0 = left = (int)min(budget, (unsigned long long)kLeftCap);
+                        }
+                    }
+                    __syncwarp();                                  // the staging buffer is free again
                 }
-                have = false;
+                if (__all_sync(FULL, idle)) break;
+                continue;                                          // (the loads above are stale: start the trip over)
             }
+            // ---- the neighbours of d beyond its row ----
+            if (have && more)
+                for (uint32_t p = 0; p < n_over; p++) {
+                    const uint32_t pr = lds16(over_s + p * 64u);
+                    if ((pr & 0xFFu) != d) continue;
+                    const uint32_t fo = bytes_below(lds32(s_s + (pr >> 8) * 128u), y, yl);
+                    if ((fo & (fo - 1u)) == 0u) fail |= fo;
+                }
         }
-        __syncwarp();
+        // colour c wipes out a later neighbour exactly when that neighbour's domain is {c} (dequan.h:663-668): the
+        // colours of `cand` up to the first one outside `fail` are the nodes the reference visits at this level
+        uint32_t cand = bytes_below(wd, y, yl);
+        if (ret) cand &= ~((0x100u << (8u * c_old)) - 1u);       // back at this level: the colours above the old one are left
+        const uint32_t pass = cand & ~fail;
+        const uint32_t bit = pass & (0u - pass);
+        const bool descend = pass != 0u;
+        const bool last = d == (uint32_t)(nv - 1);
+        const uint32_t upto = bit | (bit - 1u);
+        const uint32_t tried = descend ? cand & upto : cand;
+        const uint32_t n_tried = last ? 1u : (((tried >> 7) * 0x01010101u) >> 24);   // the last variable's first value completes a solution
+        const uint32_t unit = bit >> 7;                          // 1 << 8c
+        const uint32_t put = unit * mark;
+        const bool act = have && descend;
+        // the neighbours' words: stale marks out, this vertex's mark in (where the colour was still there)
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const uint32_t m = (f[j] >> 7) * 255u;
+            if (act && f[j] != 0u) sts32(a[j], (w[j] & ~m) | (put & m));
+        }
+        if (act) {
+            sts8(co_s + d * 64u, (unit * 0x00010203u) >> 24);
+            sts8(co_s + sp * 64u + 1u, d);
+            if (more)
+                for (uint32_t p = 0; p < n_over; p++) {
+                    const uint32_t pr = lds16(over_s + p * 64u);
+                    if ((pr & 0xFFu) != d) continue;
+                    const uint32_t ao = s_s + (pr >> 8) * 128u;
+                    const uint32_t wo = lds32(ao);
+                    const uint32_t m = (bytes_below(wo, y, yl) >> 7) * 255u;
+                    sts32(ao, (wo & ~m) | (put & m));
+                }
+        }
+        // down, back to the deepest level with colours left (return false, dequan.h:569-570), or done
+        const bool rest = (cand & ~upto) != 0u;
+        if (have) {
+            left -= (int)n_tried;
+            const bool sat = descend && last, unsat = !descend && sp == 0u;
+            code = (sat ? 1 : 0) | (unsat ? 2 : 0);
+            sp = descend ? sp + (rest ? 1u : 0u) : sp - 1u;
+            d = descend ? d + 1u : d_pop;
+            ret = !descend;
+            row_ok = descend;
+            row_cur = row_next;
+            if (sat || unsat || left < 0) { have = false; pend = true; if (unsat) { d = 0; sp = 0; row_ok = false; } }
+        }
     }
-    if (lg == 0) {
-        if (t_sat) atomicAdd(A.totals + 0, t_sat);
-        if (t_unsat) atomicAdd(A.totals + 1, t_unsat);
-        if (t_budget) atomicAdd(A.totals + 2, t_budget);
-        if (t_nodes) atomicAdd(A.totals + 3, t_nodes);
-    }
+    if (t_sat) atomicAdd(A.totals + 0, t_sat);
+    if (t_unsat) atomicAdd(A.totals + 1, t_unsat);
+    if (t_budget) atomicAdd(A.totals + 2, t_budget);
+    if (t_nodes) atomicAdd(A.totals + 3, t_nodes);
 }
 
 }  // namespace dq

@@ -101,9 +101,42 @@ def colouring_instance(n: int, c: float, seed: int, index: int, renumber: bool =
     return edges.astype(np.uint8 if n <= 256 else np.int32)
 
 
-def colouring_batch(count: int, n: int, c: float, seed: int = 20261018, start: int = 0) -> Tuple[np.ndarray, np.ndarray]:
-    """CSR batch: edge_off int64[count+1], edges uint8[total,2]."""
-    lists = [colouring_instance(n, c, seed, start + i) for i in range(count)]
+def colouring_batch(count: int, n: int, c: float, seed: int = 20261018, start: int = 0, chunk: int = 1024) -> Tuple[np.ndarray, np.ndarray]:
+    """CSR batch: edge_off int64[count+1], edges uint8[total,2].  Instance i is `colouring_instance(n, c, seed, start + i)`;
+    the maximum-cardinality numbering runs on `chunk` instances at a time (dense adjacency, vectorised over the chunk)."""
+    assert n <= 256
+    iu, ju = np.triu_indices(n, 1)
+    p = c / (n - 1) if n > 1 else 0.0
+    thresh = np.uint64(int(p * 2.0**64)) if p < 1.0 else _M64
+    lists: List[np.ndarray] = []
+    for c0 in range(0, count, chunk):
+        m = min(chunk, count - c0)
+        if iu.size == 0:
+            lists.extend(np.zeros((0, 2), dtype=np.uint8) for _ in range(m))
+            continue
+        idx = np.arange(start + c0, start + c0 + m, dtype=np.uint64)
+        sel = _keys(seed, idx, 21, iu.size) < thresh                      # [m, n(n-1)/2]
+        adj = np.zeros((m, n, n), dtype=bool)
+        adj[:, iu, ju] = sel
+        adj |= adj.transpose(0, 2, 1)
+        # maximum-cardinality search on all m graphs at once: pick the unnumbered vertex with most numbered neighbours
+        # (ties -> smallest id, np.argmax returns the first maximum)
+        weight = np.zeros((m, n), dtype=np.int64)
+        done = np.zeros((m, n), dtype=bool)
+        new_id = np.zeros((m, n), dtype=np.int64)
+        rows = np.arange(m)
+        for step in range(n):
+            u = np.argmax(np.where(done, -1, weight), axis=1)
+            done[rows, u] = True
+            new_id[rows, u] = step
+            weight += adj[rows, u]
+        for i in range(m):
+            e = np.stack([iu[sel[i]], ju[sel[i]]], axis=1)
+            if e.size:
+                e = new_id[i][e]
+                e = np.stack([e.min(axis=1), e.max(axis=1)], axis=1)
+                e = e[np.lexsort((e[:, 1], e[:, 0]))]
+            lists.append(e.astype(np.uint8))
     off = np.zeros(count + 1, dtype=np.int64)
     for i, e in enumerate(lists):
         off[i + 1] = off[i] + len(e)

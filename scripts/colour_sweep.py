@@ -12,7 +12,7 @@ c = float(sys.argv[1]) if len(sys.argv) > 1 else 4.2
 k = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 budget = int(sys.argv[3]) if len(sys.argv) > 3 else 100_000
 counts = [int(x) for x in sys.argv[4].split(",")] if len(sys.argv) > 4 else [1024, 8192]
-groups = sys.argv[5].split(",") if len(sys.argv) > 5 else ["1", "2", "4", "8", "16", "32", "reg"]
+groups = sys.argv[5].split(",") if len(sys.argv) > 5 else ["lane", "reg"]
 base = min(max(counts), 8192)
 t = time.time()
 off0, edges0 = G.colouring_batch(base, 200, c)
@@ -25,12 +25,7 @@ for count in counts:
         edges = np.ascontiguousarray(np.tile(edges0, (reps, 1)))
         off = np.concatenate([[0], (np.arange(reps)[:, None] * off0[-1] + off0[1:][None, :]).ravel()]).astype(np.int64)
     for g in groups:
-        os.environ.pop("DQ_GRAPHS_GROUP", None)
-        engine = "auto"
-        if g == "reg":
-            engine = "reg"
-        elif g != "auto":
-            os.environ["DQ_GRAPHS_GROUP"] = g
+        engine = g
         best = None
         for rep in range(3):
             r = api.solve_batch_graphs(200, k, off, edges, node_budget=budget, engine=engine)

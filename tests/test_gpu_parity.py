@@ -472,30 +472,17 @@ def _graph_lists(nv, c, count, seed=4242):
     return off, edges
 
 
-def _with_group(g, fn):
-    """Runs fn() with the lane-group engine forced to g lanes per instance (DQ_GRAPHS_GROUP; None = the library's choice)."""
-    old = os.environ.pop("DQ_GRAPHS_GROUP", None)
-    try:
-        if g is not None:
-            os.environ["DQ_GRAPHS_GROUP"] = str(g)
-        return fn()
-    finally:
-        os.environ.pop("DQ_GRAPHS_GROUP", None)
-        if old is not None:
-            os.environ["DQ_GRAPHS_GROUP"] = old
-
-
 @pytest.mark.parametrize("nv,k,c,budget", [(200, 3, 4.2, 30000), (200, 4, 7.0, 30000), (60, 3, 3.5, 0), (33, 2, 1.2, 0), (1, 3, 0.0, 0),
                                            (254, 4, 6.0, 5000), (64, 1, 0.5, 0), (2, 2, 1.0, 0), (17, 4, 9.0, 0)])
 def test_colouring_engines_agree(product_lib, nv, k, c, budget):
-    """The lane-group engine (dq_group_graphs.cuh, every group size) and the register-resident warp engine
-    (dq_reg_graphs.cuh) against the generic warp engine, itself pinned to the reference."""
+    """The lane-per-instance engine (dq_group_graphs.cuh) and the register-resident warp engine (dq_reg_graphs.cuh)
+    against the generic warp engine, itself pinned to the reference."""
     off, edges = _graph_lists(nv, c, 96)
     b = api.solve_batch_graphs(nv, k, off, edges, node_budget=budget, engine="warp")
-    for g in (None, 1, 2, 4, 8, 16, 32):
-        a = _with_group(g, lambda: api.solve_batch_graphs(nv, k, off, edges, node_budget=budget))
-        _same_batch(a, b, (nv, k, c, budget, "group", g))
-        assert a.launches == 2
+    a = api.solve_batch_graphs(nv, k, off, edges, node_budget=budget, engine="lane")
+    _same_batch(a, b, (nv, k, c, budget, "lane"))
+    assert a.launches == 3
+    _same_batch(api.solve_batch_graphs(nv, k, off, edges, node_budget=budget), b, (nv, k, c, budget, "auto"))
     r = api.solve_batch_graphs(nv, k, off, edges, node_budget=budget, engine="reg")
     _same_batch(r, b, (nv, k, c, budget, "reg"))
     assert r.launches == 1 and b.launches == 2
@@ -503,8 +490,8 @@ def test_colouring_engines_agree(product_lib, nv, k, c, budget):
         api.solve_batch_graphs(3, 3, np.array([0, 1], dtype=np.int64), np.array([[1, 1]], dtype=np.uint8))
 
 
-@pytest.mark.parametrize("group", [None, 1, 4, 8])
-def test_colouring_c4_vs_reference(golden_large, product_lib, group):
+@pytest.mark.parametrize("engine", ["lane", "reg"])
+def test_colouring_c4_vs_reference(golden_large, product_lib, engine):
     """BASELINE config C4 as stated — G(200, c/199), k=3 c in {4.0, 4.2, 4.4, 4.69}, k=4 c in {6, 7}, 64 instances each,
     budget 100 000 nodes — against what the unmodified reference returns (tests/golden/make_golden_large.py):
     status, node count and colours per instance."""
@@ -512,7 +499,7 @@ def test_colouring_c4_vs_reference(golden_large, product_lib, group):
     for case in golden_large["colouring200"]:
         off, edges = G.colouring_batch(case["count"], case["n_vertices"], case["c"])
         assert hashlib.sha256(edges.tobytes()).hexdigest() == case["sha256"]
-        r = _with_group(group, lambda: api.solve_batch_graphs(case["n_vertices"], case["k"], off, edges, node_budget=case["budget"]))
+        r = api.solve_batch_graphs(case["n_vertices"], case["k"], off, edges, node_budget=case["budget"], engine=engine)
         assert [api.OUTCOME[s] for s in r.status] == case["status"], (case["k"], case["c"])
         assert r.nodes.tolist() == case["nodes"], (case["k"], case["c"])
         for i, first in enumerate(case["first"]):
@@ -541,17 +528,17 @@ def test_colouring_group_engine_odd_inputs(product_lib):
         off[i + 1] = off[i] + len(e)
     edges = np.ascontiguousarray(np.concatenate(lists, axis=0))
     b = api.solve_batch_graphs(40, 3, off, edges, engine="warp")
-    for g in (1, 2, 8, 32):
-        _same_batch(_with_group(g, lambda: api.solve_batch_graphs(40, 3, off, edges)), b, ("odd", g))
+    _same_batch(api.solve_batch_graphs(40, 3, off, edges, engine="lane"), b, "odd")
+    _same_batch(api.solve_batch_graphs(40, 3, off, edges), b, "odd, auto")
     for i in (3, 40):
         assert b.status[i] == 1 and b.nodes[i] == 40 and (b.solution[i] == 0).all()
     # budgets on the boundary: an instance that needs exactly B nodes is solved with budget B, and busts with B - 1
     need = int(b.nodes[0])
     one = (off[:2].copy(), edges[: off[1]])
     for budget in (need, need - 1, 1):
-        _same_batch(api.solve_batch_graphs(40, 3, *one, node_budget=budget), api.solve_batch_graphs(40, 3, *one, node_budget=budget, engine="warp"), budget)
-    assert api.solve_batch_graphs(40, 3, *one, node_budget=need).status[0] == b.status[0]
-    r = api.solve_batch_graphs(40, 3, *one, node_budget=need - 1)
+        _same_batch(api.solve_batch_graphs(40, 3, *one, node_budget=budget, engine="lane"), api.solve_batch_graphs(40, 3, *one, node_budget=budget, engine="warp"), budget)
+    assert api.solve_batch_graphs(40, 3, *one, node_budget=need, engine="lane").status[0] == b.status[0]
+    r = api.solve_batch_graphs(40, 3, *one, node_budget=need - 1, engine="lane")
     assert r.status[0] == 2 and r.nodes[0] == need and (r.solution[0] == 0xFF).all()
 
 
