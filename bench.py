@@ -7,19 +7,18 @@ puzzles/sec, on 1/2/4/8 B200, next to the reference dequan timed on the host cor
 
 One "step" = one complete solve of the workload through the C ABI.  The workload is the same at every N, so that the
 1/2/4/8-GPU series is a strong-scaling series of ONE job: BASELINE config C5, 17-Queens all-solutions (95 815 104
-solutions / 5 474 619 051 nodes; 24 ms on one B200 — the largest single-tree configuration and the one the north star
-names), FC-surviving prefixes dealt to the ranks by key, {solutions, nodes} summed with NCCL.  The line also carries
-`sudoku` (config C3, 1M puzzles, sharded over the ranks), and at N == 1 `extra.nqueens14_1gpu` (config C2, 14-Queens:
-value, e2e and roofline of its own) and `extra.colouring_*` (config C4).
+solutions / 5 474 619 051 nodes, tests/golden/reference_large.json; about 15 ms on one B200), FC-surviving prefixes
+dealt to the ranks by key, {solutions, nodes} summed with NCCL.  The line also carries `sudoku` (config C3, 1M puzzles,
+sharded over the ranks) and, at N == 1, `extra.nqueens14_1gpu` (config C2) and `extra.colouring` (config C4), each
+with value / e2e / roofline / cpu_baseline of its own.
 `value`  : inputs/tables already resident in HBM (compiled model re-used), whole-job nodes/s.
 `e2e`    : the same through the host-facing C-ABI calls with HOST buffers, every step: dq_compile of the flat
            model descriptor (CSP::FinalizeModel + Assignment::Reset), table upload, solve, result read-back, dq_free.
-Every result of every step is checked against the known answers; a mismatch aborts the bench.
+Every result of every step is checked against the reference's answers; a mismatch aborts the bench.
 """
 from __future__ import annotations
 
 import argparse
-import ctypes
 import json
 import os
 import subprocess
@@ -32,20 +31,41 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
-QUEENS = {  # OEIS A000170 + node counts pinned by tests/golden (N<=14) and the engine parity runs
-    14: (365596, 19787662), 15: (2279184, 121498513), 16: (14772512, 795563572), 17: (95815104, 5474619051),
-}
 # forward-checking domain updates per node (A) -> algorithmic lane-ops/node = 5A+4 (queens), 2A+4 (!=,0)
 QUEENS_A = {14: 79143794 / 19787662, 15: 498817896 / 121498513, 16: 3342155422 / 795563572, 17: 23537105544 / 5474619051}
+# colouring, G(200, 4.2/199), k=3, 100 k-node budget: later neighbours of the assigned vertex, averaged over the nodes of
+# the first 12 instances (3 000 013 updates / 1 100 407 nodes)
+COLOURING_A = 2.726
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "dequan_ref")
+
+
+def golden_queens():
+    """(solutions, nodes) per board size from the runs of the unmodified reference under tests/golden/."""
+    out = {}
+    for name in ("reference.json", "reference_large.json"):
+        with open(os.path.join(ROOT, "tests", "golden", name)) as f:
+            for n, g in json.load(f)["nqueens"].items():
+                out[int(n)] = (g["count"]["solutions"], g["count"]["nodes"])
+    return out
 
 
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
-        d = json.load(open(p))
-        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(key):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch, from profiles/r2_traffic.json (written by
+    scripts/ncu_traffic.py out of an `ncu --set full` report, with the commit it was measured at); None if absent."""
+    p = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    e = json.load(open(p)).get(key)
+    if not e:
+        return None, None
+    return int(e["dram_bytes_read"] + e["dram_bytes_write"]), f"profiles/r2_traffic.json[{key}]@{e.get('commit', '?')[:9]}"
 
 
 class ClockSampler:
@@ -78,8 +98,7 @@ class ClockSampler:
         mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i] == "Active" for r in self.rows)]
-        # the busiest half of the samples = "under load"
-        load = sm[len(sm) // 2:] if sm else []
+        load = sm[len(sm) // 2:] if sm else []          # the busiest half of the samples = "under load"
         return {"sm_mhz": load[len(load) // 2] if load else None, "sm_max_mhz": max(mx) if mx else None,
                 "samples": len(sm), "reasons": reasons}
 
@@ -97,19 +116,19 @@ def cpu_threads():
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_baseline_queens(n_gpus: int):
+def cpu_baseline_queens():
     """Reference dequan on the host cores, bounded sample of the same workload."""
     thr = cpu_threads()
     if not os.path.exists(REF_BIN):
-        return cpu_baseline_port_queens(n_gpus)
+        return cpu_baseline_port_queens()
     t = time.time()
     o = run_ref(["nqueens", 17, "count", thr, 8, 3])[0]
     wall = time.time() - t
     return {"value": o["nodes"] / o["seconds"], "unit": "nodes/s", "cores": min(thr, 17), "kind": "reference",
-            "sample": f"17-Queens subtree under prefix (8,3), one depth-3 subtree per thread ({o['nodes']} nodes, {wall:.1f}s wall)"}
+            "sample": f"17-Queens subtree under prefix (8,3), one depth-3 subtree per thread ({o['nodes']} nodes, {wall:.1f}s)"}
 
 
-def cpu_baseline_port_queens(n_gpus: int):
+def cpu_baseline_port_queens():
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib
     from dequan_b200.model import nqueens
@@ -123,8 +142,7 @@ def cpu_baseline_port_queens(n_gpus: int):
 
 def reference_arm(args):
     """--impl reference: the reference's own CPU implementation, all host threads, same metric/config."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return
     thr = cpu_threads()
     n = 17
@@ -136,7 +154,7 @@ def reference_arm(args):
             o = run_ref(cmd)[0]
             dt, nd = o["seconds"], o["nodes"]
         else:
-            b = cpu_baseline_port_queens(args.gpus)
+            b = cpu_baseline_port_queens()
             nd = 1
             dt = 1.0 / b["value"]
         if i >= args.warmup:
@@ -156,12 +174,9 @@ def reference_arm(args):
 
 
 def workload_config(n_gpus, n):
-    which = {17: "BASELINE config C5 (the same job at every N: strong scaling; C2 = 14-Queens is reported in extra.nqueens14_1gpu)",
-             14: "BASELINE config C2"}.get(n, "")
-    return {"workload": f"nqueens{n}_count_all", "baseline_config": which,
-            "model": "N vars AddIntVar(0,N), 3 OpConstraint NotEqual per pair (main-test.cpp:36-49)",
-            "parallelism": "single tree, FC-surviving prefixes in DFS order" + (f", dealt by key to {n_gpus} GPUs, NCCL sum" if n_gpus > 1 else ""),
-            "l2": "flushed between steps (256 MiB write, untimed)"}
+    return {"workload": f"nqueens{n}_count_all", "baseline_config": {17: "C5", 14: "C2"}.get(n, ""),
+            "parallelism": "prefix split" + (f", keys dealt to {n_gpus} GPUs, NCCL sum" if n_gpus > 1 else ""),
+            "l2": "flushed between steps"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -174,6 +189,7 @@ def main():
     ap.add_argument("--engine", default="auto")
     ap.add_argument("--sudoku-n", type=int, default=1_000_000)
     ap.add_argument("--givens", type=int, default=30)
+    ap.add_argument("--colouring-n", type=int, default=32768)
     ap.add_argument("--no-sudoku", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
@@ -190,15 +206,15 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N > 1")
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N > 1")
     torch.cuda.set_device(local)
     api.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    QUEENS = golden_queens()
 
     def sync_all():
         if world > 1:
@@ -218,11 +234,8 @@ def main():
             g = multi.reduce_tree(loc, m.nodes_upto, "count", n, device=dev)
             return loc, g.solutions, g.nodes
 
-        dom = {"ms": 0.0, "frontier_nodes": 0, "records": 0}
-
         def timed_steps(step_fn, k, w):
             tot, kern, launches = 0.0, 0.0, 0
-            dom["ms"] = 0.0
             for i in range(w + k):
                 flush.fill_(i & 0xFF)
                 sync_all()
@@ -243,16 +256,15 @@ def main():
 
         tot, kern_ms, launches = timed_steps(lambda: solve_step(model), steps, warmup)
         # roofline leg: the search kernel's own duration from CUDA events on its stream (DQ_TREE_TIME_KERNELS; the steps
-        # above replay the solve as one CUDA graph, whose inner events cannot be read back)
-        dom["ms"] = 0.0
+        # above replay the solve as one CUDA graph, whose inner events cannot be read back); this rank's own node count
+        dom_ms, dom_nodes, dom_records = 0.0, 0, 0
         for i in range(steps):
             flush.fill_(i & 0xFF)
             sync_all()
             loc = model.solve_tree("count", part_rank=rank, part_count=world, engine=args.engine, time_kernels=True)
             assert (loc.solutions, loc.nodes) == (want_sols, want_nodes) or world > 1
-            dom["ms"] += loc.search_kernel_ms
-            dom["frontier_nodes"], dom["records"] = loc.frontier_nodes, loc.n_prefixes
-        dom_ms, dom_frontier, dom_records = dom["ms"], dom["frontier_nodes"], dom["records"]
+            dom_ms += loc.search_kernel_ms
+            dom_nodes, dom_records = loc.nodes - loc.frontier_nodes, loc.n_prefixes
         desc_keep = csp.desc()          # the host-side flat descriptor: the input buffers of the C-ABI call
 
         def e2e_step():
@@ -262,21 +274,30 @@ def main():
             return r
         e_tot, _, _ = timed_steps(e2e_step, steps, warmup)
         return {"n": n, "nodes": want_nodes, "steps": steps, "tot": tot, "kern_ms": kern_ms, "launches": launches, "e_tot": e_tot,
-                "dom_ms": dom_ms, "dom_frontier": dom_frontier, "dom_records": dom_records, "table_bytes": model.table_bytes(),
+                "dom_ms": dom_ms, "dom_nodes": dom_nodes, "dom_records": dom_records, "table_bytes": model.table_bytes(),
                 "engine": model.solve_tree("count", part_rank=rank, part_count=world, engine=args.engine).engine}
+
+    def queens_block(q, int_peak, hbm_peak, peak_src):
+        n, steps = q["n"], q["steps"]
+        return {"value": q["nodes"] * steps / q["tot"], "unit": "nodes/s", "ms_per_step": 1e3 * q["tot"] / steps,
+                "kernel_ms_per_step": q["kern_ms"] / steps,
+                "e2e": {"value": q["nodes"] * steps / q["e_tot"], "unit": "nodes/s", "h2d_bytes_per_step": q["table_bytes"] + 64,
+                        "d2h_bytes_per_step": 64 + 4 * n + 8 * 64, "ms_per_step": 1e3 * q["e_tot"] / steps},
+                "gpu_launches": q["launches"], "engine": q["engine"],
+                "roofline": roofline_queens(n, world, q["dom_nodes"], q["dom_records"], q["dom_ms"] / steps, int_peak, hbm_peak, peak_src)}
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     n = 17
     Q = measure_queens(n, args.steps, args.warmup)
-    want_nodes, tot, kern_ms, launches, e_tot = Q["nodes"], Q["tot"], Q["kern_ms"], Q["launches"], Q["e_tot"]
-    dom_ms, dom_frontier, dom_records, table_bytes, engine_used = Q["dom_ms"], Q["dom_frontier"], Q["dom_records"], Q["table_bytes"], Q["engine"]
     Q14 = measure_queens(14, max(args.steps, 10), args.warmup) if world == 1 and not args.no_extra else None
-
     sudoku = None
     if not args.no_sudoku:
         sudoku = sudoku_section(args, torch, api, dev, world, rank, dist, flush)      # still inside the clock-sampling window
+    colouring = None
+    if world == 1 and not args.no_extra:
+        colouring = colouring_section(args, torch, api, dev, flush)
 
     if rank != 0:
         if world > 1:
@@ -285,50 +306,24 @@ def main():
         return
     clocks = sampler.stop()
     int_peak, _ = api.measure_int_peak()
-    value = want_nodes * args.steps / tot
-    kernel_nodes_per_s = want_nodes * args.steps / (kern_ms * 1e-3)
-    ops_per_node = 5 * QUEENS_A[n] + 4
     hbm_peak, peak_src = peaks()
+    qb = queens_block(Q, int_peak, hbm_peak, peak_src)
     line = {
-        "metric": "search_nodes_per_sec", "value": value, "unit": "nodes/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True, "scaling": "strong",
+        "metric": "search_nodes_per_sec", "value": qb["value"], "unit": "nodes/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": qb["ms_per_step"], "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": workload_config(world, n),
-        "clocks": clocks,
-        "e2e": {"value": want_nodes * args.steps / e_tot, "unit": "nodes/s", "h2d_bytes_per_step": table_bytes + 64,
-                "d2h_bytes_per_step": 64 + 4 * n + 8 * 64, "ms_per_step": 1e3 * e_tot / args.steps},
-        "gpu_launches": launches,
-        "engine": engine_used,
-        "kernel_ms_per_step": kern_ms / args.steps,
-        "roofline": roofline_queens(n, world, want_nodes, dom_frontier, dom_records, dom_ms / args.steps, int_peak, hbm_peak, peak_src),
+        "clocks": clocks, "e2e": qb["e2e"], "gpu_launches": qb["gpu_launches"], "engine": qb["engine"],
+        "kernel_ms_per_step": qb["kernel_ms_per_step"], "roofline": qb["roofline"],
     }
     if not args.no_cpu:
-        line["cpu_baseline"] = cpu_baseline_queens(world)
-    extra = {}
-    if world == 1 and not args.no_extra:
-        # BASELINE config C2: 14-Queens all-solutions on one B200 (365 596 solutions / 19 787 662 nodes)
-        q = Q14
-        extra["nqueens14_1gpu"] = {
-            "config": workload_config(1, 14), "value": q["nodes"] * q["steps"] / q["tot"], "unit": "nodes/s",
-            "ms_per_step": 1e3 * q["tot"] / q["steps"], "kernel_ms_per_step": q["kern_ms"] / q["steps"], "steps": q["steps"],
-            "e2e": {"value": q["nodes"] * q["steps"] / q["e_tot"], "unit": "nodes/s", "ms_per_step": 1e3 * q["e_tot"] / q["steps"],
-                    "h2d_bytes_per_step": q["table_bytes"] + 64, "d2h_bytes_per_step": 64 + 4 * 14 + 8 * 64},
-            "gpu_launches": q["launches"], "engine": q["engine"],
-            "roofline": roofline_queens(14, 1, q["nodes"], q["dom_frontier"], q["dom_records"], q["dom_ms"] / q["steps"], int_peak, hbm_peak, peak_src)}
-        # BASELINE config C4: G(200, c/199) 3-colouring near the phase transition, batched, node budget per instance
-        from dequan_b200 import generators as G
-        # 1 024 instances leave 7 warps per SM (one warp per instance): a latency-bound launch; 8 192 fill the machine
-        off_all, edges_all = G.colouring_batch(8192, 200, 4.2)
-        for count in (1024, 8192):
-            off, edges = off_all[:count + 1], edges_all[:off_all[count]]
-            cr = api.solve_batch_graphs(200, 3, off, edges, node_budget=100_000)
-            cr = api.solve_batch_graphs(200, 3, off, edges, node_budget=100_000)
-            extra[f"colouring_g200_c4.2_k3_{count}"] = {"instances": count, "node_budget": 100_000, "kernel_ms": cr.kernel_ms,
-                                                        "instances_per_sec": count / (cr.kernel_ms * 1e-3),
-                                                        "nodes_per_sec": cr.total_nodes / (cr.kernel_ms * 1e-3),
-                                                        "sat": cr.n_sat, "unsat": cr.n_unsat, "budget": cr.n_budget,
-                                                        "engine": "register-resident warp engine (dq_reg_graphs.cuh)"}
+        line["cpu_baseline"] = cpu_baseline_queens()
     if sudoku is not None:
         line["sudoku"] = sudoku_rooflines(sudoku, hbm_peak, peak_src, int_peak)
+    extra = {}
+    if Q14 is not None:
+        extra["nqueens14_1gpu"] = dict(config=workload_config(1, 14), steps=Q14["steps"], **queens_block(Q14, int_peak, hbm_peak, peak_src))
+    if colouring is not None:
+        extra["colouring"] = colouring_rooflines(colouring, int_peak, hbm_peak, peak_src)
     line["extra"] = extra
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -336,45 +331,30 @@ def main():
         dist.destroy_process_group()
 
 
-# ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of k_queens_bucket (profiles/r1_ncu_queens14_bucket.txt, r1_ncu_queens17_bucket.txt)
-NCU_TRAFFIC = {(14, 1): 13093120 + 256, (17, 1): 1982841000 + 5133824}
-
-
-def roofline_queens(n, world, nodes, frontier_nodes, records, lane_ms, int_peak, hbm_peak, peak_src):
-    """Roofline of the dominant kernel, k_queens_bucket (depth-bucketed subtree search; profiles/r1_launch_shares.txt).
-    It is integer-issue bound: algorithmic work = (5A+4) lane-ops per node, A = forward-checking domain
-    updates per node; the peak is the LOP3 rate measured in this run.  Its HBM side is shown next to it: one 16-byte
-    record read per subtree."""
+def roofline_queens(n, world, lane_nodes, records, lane_ms, int_peak, hbm_peak, peak_src):
+    """Roofline of the dominant kernel, k_queens_bucket (depth-bucketed subtree search).  It is integer-issue bound
+    (SURVEY.md §8d): algorithmic work = (5A+4) lane-ops per node, A = forward-checking domain updates per node; the peak
+    is the LOP3 rate measured in this run.  nodes_per_launch is what THIS rank's launch searched."""
     ops_per_node = 5 * QUEENS_A[n] + 4
-    lane_nodes = (nodes - frontier_nodes) if world == 1 else None          # N>1: this rank's share is not split out
-    per_gpu_nodes = (nodes / world) if lane_nodes is None else lane_nodes
-    achieved = per_gpu_nodes * ops_per_node / (lane_ms * 1e-3) if lane_ms else 0.0
-    algo_bytes = records * 16 if world == 1 else None
+    achieved = lane_nodes * ops_per_node / (lane_ms * 1e-3) if lane_ms else 0.0
+    traffic, src = ncu_traffic(f"k_queens_bucket/nqueens{n}") if world == 1 else (None, None)
     return {"bound": "int32-alu", "kernel": "k_queens_bucket", "achieved": achieved / 1e12, "peak": int_peak / 1e12,
             "unit": "Tlane-op/s per GPU", "frac": achieved / int_peak, "kernel_ms": lane_ms,
-            "nodes_per_launch": per_gpu_nodes, "ops_per_node": ops_per_node,
-            "peak_source": "LOP3 microbenchmark (dq_measure_int_peak), this run",
-            "traffic": NCU_TRAFFIC.get((n, world)), "algorithmic_bytes": algo_bytes,
-            "hbm": {"achieved": (algo_bytes / (lane_ms * 1e-3) / 1e9) if algo_bytes and lane_ms else None, "peak": hbm_peak,
-                    "unit": "GB/s", "peak_source": peak_src},
-            "note": "not HBM- or tensor-bound: no dense contraction on this path, one 16 B record per subtree from HBM"}
-
-
-# ncu, dram__bytes_read.sum + dram__bytes_write.sum summed over the seven kernels of one 1 M-puzzle pipeline pass
-# (profiles/r1_ncu_sudoku_traffic.txt): 856 MB read + 366 MB written, of which 288 B per puzzle are the digest (written
-# once, read by k_sudoku_first and again per counting task) and the rest task / snapshot records of the counting stage
-NCU_SUDOKU_TRAFFIC_1M = 856_260_000 + 366_400_000
+            "nodes_per_launch": lane_nodes, "ops_per_node": ops_per_node, "peak_source": "LOP3 microbenchmark, this run",
+            "traffic": traffic, "traffic_source": src, "algorithmic_bytes": records * 16,
+            "hbm": {"achieved": records * 16 / (lane_ms * 1e-3) / 1e9 if lane_ms else None, "peak": hbm_peak, "unit": "GB/s",
+                    "peak_source": peak_src}}
 
 
 def sudoku_rooflines(out, hbm_peak, peak_src, int_peak):
     kpps, nps = out.pop("_kernel_pps"), out["nodes_per_sec"]
+    traffic, src = ncu_traffic("sudoku_pipeline/1M_g30") if out.get("shard", out["n"]) == 1_000_000 else (None, None)
+    out["roofline_int"] = {"bound": "int32-alu", "ops_per_node": 2 * 10 + 4, "achieved": nps * 24 / 1e12, "peak": int_peak / 1e12,
+                           "unit": "Tlane-op/s", "frac": nps * 24 / int_peak}
     out["roofline"] = {"bound": "hbm", "achieved": kpps * 174 / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                       "frac": kpps * 174 / 1e9 / hbm_peak,
-                       "traffic": NCU_SUDOKU_TRAFFIC_1M if out.get("shard", out["n"]) == 1_000_000 else None,
-                       "algorithmic_bytes": 174 * out.get("shard", out["n"]), "bytes_per_puzzle": 174, "peak_source": peak_src,
-                       "note": "instance stream only; the search itself is integer-issue bound (see roofline_int)"}
-    out["roofline_int"] = {"ops_per_node": 2 * 10 + 4, "achieved": nps * 24 / 1e12, "peak": int_peak / 1e12, "unit": "Tlane-op/s",
-                           "frac": nps * 24 / int_peak}
+                       "frac": kpps * 174 / 1e9 / hbm_peak, "traffic": traffic, "traffic_source": src,
+                       "algorithmic_bytes": 174 * out.get("shard", out["n"]), "peak_source": peak_src,
+                       "note": "instance stream; the search is integer-issue bound (roofline_int)"}
     return out
 
 
@@ -382,9 +362,9 @@ def sudoku_section(args, torch, api, dev, world=1, rank=0, dist=None, flush=None
     """BASELINE config C3: batch of synthetic 9x9 Sudoku (810 binary != arcs), first solution each.  With N GPUs the
     batch is cut into N contiguous shards, one per rank; the only collective is the final sum of {solved, nodes}."""
     from dequan_b200 import generators as G
+    from dequan_b200 import multi
     from dequan_b200.model import sudoku_template
     n_total = args.sudoku_n
-    from dequan_b200 import multi
     lo, hi = multi.shard_range(n_total, rank, world)
     n = hi - lo
     cells = G.sudoku_batch(n, givens=args.givens, start=lo)
@@ -455,15 +435,12 @@ def sudoku_section(args, torch, api, dev, world=1, rank=0, dist=None, flush=None
     pps = n * steps / tot
     kpps = n * steps / (kern * 1e-3)
     out = {"metric": "sudoku_puzzles_per_sec", "value": pps, "unit": "puzzles/s", "n": n, "givens": args.givens, "n_gpus": world,
-           "scaling": "strong", "shard": n_shard,
-           "steps": steps, "ms_per_step": 1e3 * tot / steps, "kernel_ms_per_step": kern / steps,
+           "scaling": "strong", "shard": n_shard, "steps": steps, "ms_per_step": 1e3 * tot / steps, "kernel_ms_per_step": kern / steps,
            "nodes_per_puzzle": total_nodes / n, "nodes_per_sec": total_nodes * steps / (kern * 1e-3),
-           "config": {"workload": f"sudoku_1M_g{args.givens}" if n == 1_000_000 else f"sudoku_{n}_g{args.givens}",
-                      "l2": "flushed between steps (256 MiB write, untimed); inputs+outputs are 171 B per puzzle"},
+           "config": {"workload": f"sudoku_1M_g{args.givens}" if n == 1_000_000 else f"sudoku_{n}_g{args.givens}", "l2": "flushed between steps"},
            "e2e": {"value": n * steps / e_tot, "unit": "puzzles/s", "h2d_bytes_per_step": n * 81, "d2h_bytes_per_step": n * 90,
                    "ms_per_step": 1e3 * e_tot / steps},
-           "gpu_launches": launches, "engine": "lane pipeline (digest, first, strong, walk, count, finish)",
-           "_kernel_pps": kpps}
+           "gpu_launches": launches, "_kernel_pps": kpps}
     if not args.no_cpu and os.path.exists(REF_BIN):
         sample = min(n_shard, 16000)
         path = "/tmp/dq_bench_sudoku.txt"
@@ -475,9 +452,95 @@ def sudoku_section(args, torch, api, dev, world=1, rank=0, dist=None, flush=None
         assert int(h_nodes.numpy()[:sample].sum()) == int(o["nodes"]), ("sudoku node total differs from the reference",
                                                                       int(h_nodes.numpy()[:sample].sum()), o["nodes"])
         out["cpu_baseline"] = {"value": o["puzzles"] / o["wall_seconds"], "unit": "puzzles/s", "cores": thr, "kind": "reference",
-                               "sample": f"first {sample} puzzles of the same batch, one puzzle per thread, model build included "
-                                         f"(solve-only {o['puzzles'] / o['solve_seconds_sum'] * thr:.0f} puzzles/s)",
+                               "sample": f"first {sample} puzzles, one per thread, model build included",
                                "nodes_per_sec": o["nodes"] / o["wall_seconds"]}
+    return out
+
+
+def colouring_section(args, torch, api, dev, flush):
+    """BASELINE config C4: batch of G(200, 4.2/199) 3-colouring instances near the phase transition (vertices in
+    maximum-cardinality order), first solution under a 100 000-node budget each, tri-state result."""
+    from dequan_b200 import generators as G
+    n, nv, k, c, budget = args.colouring_n, 200, 3, 4.2, 100_000
+    off, edges = G.colouring_batch(n, nv, c)
+    steps, warm = 3, 3
+    pad = (-2 * int(off[-1])) % 16
+    d_edges = torch.from_numpy(np.concatenate([edges.reshape(-1), np.zeros(pad, dtype=np.uint8)])).to(dev)
+    d_off = torch.from_numpy(off).to(dev)
+    d_col = torch.empty((n, nv), dtype=torch.uint8, device=dev)
+    d_nodes = torch.empty(n, dtype=torch.int64, device=dev)
+    d_status = torch.empty(n, dtype=torch.uint8, device=dev)
+    tot = kern = search = 0.0
+    launches = 0
+    for i in range(warm + steps):
+        flush.fill_(i & 0xFF)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        st = api.solve_batch_graphs_ptr(nv, k, off, d_off.data_ptr(), d_edges.data_ptr(), d_col.data_ptr(), d_nodes.data_ptr(),
+                                        d_status.data_ptr(), node_budget=budget, device=True)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if i >= warm:
+            tot += dt; kern += st.kernel_ms; search += st.search_kernel_ms; launches += st.kernel_launches
+    total_nodes = st.total_nodes
+    h_edges = torch.from_numpy(edges.reshape(-1).copy()).pin_memory()
+    h_col = torch.empty((n, nv), dtype=torch.uint8).pin_memory()
+    h_nodes = torch.empty(n, dtype=torch.int64).pin_memory()
+    h_status = torch.empty(n, dtype=torch.uint8).pin_memory()
+    e_tot = 0.0
+    for i in range(warm + steps):
+        flush.fill_(i & 0xFF)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        st2 = api.solve_batch_graphs_ptr(nv, k, off, 0, h_edges.data_ptr(), h_col.data_ptr(), h_nodes.data_ptr(), h_status.data_ptr(),
+                                         node_budget=budget, device=False)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if i >= warm:
+            e_tot += dt
+    # checks: both legs agree; every returned colouring is proper
+    col, status = h_col.numpy(), h_status.numpy()
+    assert (d_col.cpu().numpy() == col).all() and (d_nodes.cpu().numpy() == h_nodes.numpy()).all() and (d_status.cpu().numpy() == status).all()
+    for i in np.nonzero(status == 1)[0][:2000]:
+        e = edges[off[i]:off[i + 1]]
+        assert (col[i][e[:, 0]] != col[i][e[:, 1]]).all() and col[i].max() < k
+    out = {"metric": "colouring_nodes_per_sec", "value": total_nodes * steps / tot, "unit": "nodes/s", "instances": n,
+           "instances_per_sec": n * steps / tot, "node_budget": budget, "steps": steps, "ms_per_step": 1e3 * tot / steps,
+           "kernel_ms_per_step": kern / steps, "search_kernel_ms": search / steps, "nodes": total_nodes,
+           "sat": st.n_sat, "unsat": st.n_unsat, "budget": st.n_budget,
+           "config": {"workload": f"colouring_g200_c{c}_k{k}_{n}", "baseline_config": "C4", "l2": "flushed between steps"},
+           "e2e": {"value": total_nodes * steps / e_tot, "unit": "nodes/s", "instances_per_sec": n * steps / e_tot,
+                   "h2d_bytes_per_step": int(st2.h2d_bytes), "d2h_bytes_per_step": int(st2.d2h_bytes), "ms_per_step": 1e3 * e_tot / steps},
+           "gpu_launches": launches, "engine": "lane per instance (k_graphs_adjacency x2, k_graphs_lane)",
+           "_bytes_in": int(2 * off[-1] + 8 * (n + 1))}
+    if not args.no_cpu and os.path.exists(REF_BIN):
+        sample = min(n, 256)
+        path = "/tmp/dq_bench_graphs.txt"
+        with open(path, "w") as f:
+            f.write("\n".join(G.graph_lines(off[:sample + 1], edges, nv)) + "\n")
+        thr = cpu_threads()
+        o = run_ref(["color", path, k, budget, thr, "quiet"])[-1]
+        # parity at scale against the unmodified reference: the node total of the sample must be the reference's
+        assert int(h_nodes.numpy()[:sample].sum()) == int(o["nodes"]), ("colouring node total differs from the reference",
+                                                                      int(h_nodes.numpy()[:sample].sum()), o["nodes"])
+        out["cpu_baseline"] = {"value": o["nodes"] / o["wall_seconds"], "unit": "nodes/s", "cores": thr, "kind": "reference",
+                               "sample": f"first {sample} instances, one per thread, model build included",
+                               "instances_per_sec": sample / o["wall_seconds"]}
+    return out
+
+
+def colouring_rooflines(out, int_peak, hbm_peak, peak_src):
+    ops = 2 * COLOURING_A + 4
+    bytes_in = out.pop("_bytes_in")
+    ms = out["search_kernel_ms"]
+    achieved = out["nodes"] * ops / (ms * 1e-3)
+    traffic, src = ncu_traffic(f"k_graphs_lane/{out['config']['workload']}")
+    algo = bytes_in + out["instances"] * (200 + 9)
+    out["roofline"] = {"bound": "int32-alu", "kernel": "k_graphs_lane", "achieved": achieved / 1e12, "peak": int_peak / 1e12,
+                       "unit": "Tlane-op/s", "frac": achieved / int_peak, "kernel_ms": ms, "nodes_per_launch": out["nodes"],
+                       "ops_per_node": ops, "peak_source": "LOP3 microbenchmark, this run", "traffic": traffic, "traffic_source": src,
+                       "algorithmic_bytes": algo,
+                       "hbm": {"achieved": algo / (out["kernel_ms_per_step"] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s", "peak_source": peak_src}}
     return out
 
 

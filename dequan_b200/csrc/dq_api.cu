@@ -1109,6 +1109,7 @@ int dq_solve_batch_cells(dq_model* m, const uint8_t* cells, int64_t n, int32_t s
 struct GraphBatchDev {
     const long long* off; const uint8_t* edges; long long edge_bytes;    // edge_bytes: 2 * total rounded up to 16, readable
     uint8_t* colours; unsigned long long* nodes; uint8_t* status;
+    const uint8_t* host_edges;                                           // host copy of the lists, if the caller has one
 };
 
 // Lane-per-instance engine (dq_group_graphs.cuh): two passes of k_graphs_adjacency (overflow statistics, records),
@@ -1196,7 +1197,12 @@ static int run_batch_graphs(int nv, int k, const int64_t* edge_off, const GraphB
     float ms = 0, ms_search = 0;
     if (lane_engine) {
         const int rc = run_graphs_lane(nv, k, edge_off, B, n, opts ? opts->node_budget : 0, ctx, d_adj, d_ctrl.p);
-        if (rc == DQ_ERR_UNSUPPORTED && engine == DQ_ENGINE_AUTO) {       // (graphs too dense for the lane state: the warp engine below)
+        if (rc == DQ_ERR_UNSUPPORTED && engine == DQ_ENGINE_AUTO && B.host_edges) {       // (graphs too dense for the lane state: the warp engine below)
+            for (long long e = 0; e < total; e++) {                   // ... which trusts the lists
+                const uint8_t u = B.host_edges[2 * e], v = B.host_edges[2 * e + 1];
+                if (u >= nv || v >= nv) { g_err = "edge endpoint out of range"; return DQ_ERR_INVALID; }
+                if (u == v) { g_err = "edge with u == v"; return DQ_ERR_UNSUPPORTED; }
+            }
             lane_engine = false;
             DQ_CUDA(cudaStreamSynchronize(s));
             DQ_CUDA(cudaMemsetAsync(d_ctrl.p, 0, 8 * sizeof(unsigned long long), s));
@@ -1273,9 +1279,15 @@ int dq_solve_batch_graphs(int32_t nv, int32_t k, const int64_t* edge_off, const 
     if (rc != DQ_OK) return rc;
     const long long total = edge_off[n];
     if (total && !edges) { g_err = "null edge buffer"; return DQ_ERR_INVALID; }
-    for (long long e = 0; e < 2 * total; e++) if (edges[e] >= nv) { g_err = "edge endpoint out of range"; return DQ_ERR_INVALID; }
-    for (long long e = 0; e < total; e++) if (edges[2 * e] == edges[2 * e + 1]) { g_err = "edge with u == v"; return DQ_ERR_UNSUPPORTED; }
     if (opts && opts->engine == DQ_ENGINE_LANE && k > 4) { g_err = "the lane engine serves k <= 4"; return DQ_ERR_UNSUPPORTED; }
+    // the lane engine checks the lists on the device (k_graphs_adjacency); the others trust them: one pass on the host
+    const int engine = opts ? opts->engine : DQ_ENGINE_AUTO;
+    if (!(k <= 4 && (engine == DQ_ENGINE_LANE || (engine == DQ_ENGINE_AUTO && n >= 4096))))
+        for (long long e = 0; e < total; e++) {
+            const uint8_t u = edges[2 * e], v = edges[2 * e + 1];
+            if (u >= nv || v >= nv) { g_err = "edge endpoint out of range"; return DQ_ERR_INVALID; }
+            if (u == v) { g_err = "edge with u == v"; return DQ_ERR_UNSUPPORTED; }
+        }
     DeviceCtx* ctx = nullptr;
     DQ_CUDA(device_ctx(&ctx));
     cudaStream_t s = ctx->stream;
@@ -1289,7 +1301,7 @@ int dq_solve_batch_graphs(int32_t nv, int32_t k, const int64_t* edge_off, const 
     DQ_CUDA(d_status.reserve(n)); DQ_CUDA(d_nodes.reserve(n));
     DQ_CUDA(cudaMemcpyAsync(d_off.p, edge_off, (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, s));
     if (total) DQ_CUDA(cudaMemcpyAsync(d_edges.p, edges, 2 * total, cudaMemcpyHostToDevice, s));
-    GraphBatchDev B{d_off.p, d_edges.p, edge_bytes, d_col.p, d_nodes.p, d_status.p};
+    GraphBatchDev B{d_off.p, d_edges.p, edge_bytes, d_col.p, d_nodes.p, d_status.p, edges};
     rc = run_batch_graphs(nv, k, edge_off, B, n, opts, stats);
     if (rc != DQ_OK) return rc;
     DQ_CUDA(cudaMemcpyAsync(colours, d_col.p, (size_t)n * nv, cudaMemcpyDeviceToHost, s));
@@ -1316,7 +1328,7 @@ int dq_solve_batch_graphs_dev(int32_t nv, int32_t k, const int64_t* edge_off, co
         g_err = "device-resident graph batches run on the lane engine (k <= 4) only"; return DQ_ERR_UNSUPPORTED;
     }
     GraphBatchDev B{(const long long*)edge_off_dev, edges_dev, (2 * (long long)edge_off[n] + 15) & ~15ll, colours_dev,
-                    (unsigned long long*)nodes_dev, status_dev};
+                    (unsigned long long*)nodes_dev, status_dev, nullptr};
     dq_batch_opts o = opts ? *opts : dq_batch_opts{0, 0, 0};
     o.engine = DQ_ENGINE_LANE;                           // (no fall-back to an engine that trusts the edge lists)
     return run_batch_graphs(nv, k, edge_off, B, n, &o, stats);

@@ -511,6 +511,32 @@ def test_colouring_c4_vs_reference(golden_large, product_lib, engine):
         assert r.total_nodes == sum(case["nodes"])
 
 
+def test_colouring_device_resident_entry(product_lib):
+    """dq_solve_batch_graphs_dev (edge lists and outputs in HBM) against the host-buffer entry point; malformed lists
+    are refused by the device-side check."""
+    import torch
+    off, edges = _graph_lists(60, 3.5, 300)
+    want = api.solve_batch_graphs(60, 3, off, edges, node_budget=5000, engine="warp")
+    dev = torch.device("cuda", 0)
+    pad = (-edges.size) % 16
+    d_edges = torch.from_numpy(np.concatenate([edges.reshape(-1), np.zeros(pad, dtype=np.uint8)])).to(dev)
+    d_off = torch.from_numpy(off).to(dev)
+    d_col = torch.zeros((300, 60), dtype=torch.uint8, device=dev)
+    d_nodes = torch.zeros(300, dtype=torch.int64, device=dev)
+    d_status = torch.zeros(300, dtype=torch.uint8, device=dev)
+    st = api.solve_batch_graphs_ptr(60, 3, off, d_off.data_ptr(), d_edges.data_ptr(), d_col.data_ptr(), d_nodes.data_ptr(),
+                                    d_status.data_ptr(), node_budget=5000, device=True)
+    torch.cuda.synchronize()
+    assert (d_col.cpu().numpy() == want.solution).all() and (d_nodes.cpu().numpy().astype(np.uint64) == want.nodes).all()
+    assert (d_status.cpu().numpy() == want.status).all()
+    assert (st.n_sat, st.n_unsat, st.n_budget, st.total_nodes) == (want.n_sat, want.n_unsat, want.n_budget, want.total_nodes)
+    bad = d_edges.clone()
+    bad[3] = 77                                           # vertex 77 of 60
+    with pytest.raises(api.DequanError):
+        api.solve_batch_graphs_ptr(60, 3, off, d_off.data_ptr(), bad.data_ptr(), d_col.data_ptr(), d_nodes.data_ptr(),
+                                   d_status.data_ptr(), node_budget=5000, device=True)
+
+
 def test_colouring_group_engine_odd_inputs(product_lib):
     """Duplicate edges, reversed endpoints, empty instances between full ones, a ragged batch that ends in an empty graph."""
     rng = np.random.default_rng(5)
