@@ -60,9 +60,8 @@ struct BlockCache {
         }
         return e;
     }
-    void give(void* p, size_t bytes) {
-        int dev = 0;
-        cudaGetDevice(&dev);
+    void give(void* p, size_t bytes, int dev) {
+        if (dev < 0) cudaGetDevice(&dev);
         free_blocks.push_back(Block{p, bytes, dev});
         cached_bytes += bytes;
         if (cached_bytes > (size_t)8 << 30) trim();               // keep at most 8 GiB parked
@@ -80,16 +79,17 @@ template <class T>
 struct DevBuf {
     T* p = nullptr;
     size_t cap = 0, bytes = 0;
+    int dev = -1;                                        // the device the block lives on
     cudaError_t reserve(size_t n) {
         if (n <= cap) return cudaSuccess;
         release();
         const size_t want = std::max<size_t>(n, 1) * sizeof(T);
         cudaError_t e = g_cache.take(want, (void**)&p);
-        if (e == cudaSuccess) { cap = n; bytes = want; }
+        if (e == cudaSuccess) { cap = n; bytes = want; cudaGetDevice(&dev); }
         else p = nullptr;
         return e;
     }
-    void release() { if (p) g_cache.give(p, bytes); p = nullptr; cap = 0; bytes = 0; }
+    void release() { if (p) g_cache.give(p, bytes, dev); p = nullptr; cap = 0; bytes = 0; }
 };
 
 // Stream + timing events are per thread and device, shared by every handle.
@@ -138,6 +138,7 @@ using namespace dq;
 struct dq_model {
     CompiledModel cm;
     bool uploaded = false;
+    int device = -1;                            // the CUDA device the handle was first solved on
     cudaStream_t stream = nullptr, stream2 = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, ev_fork = nullptr, ev_join = nullptr;
     unsigned long long* pin = nullptr;          // pinned control words (DeviceCtx)
@@ -185,9 +186,14 @@ struct dq_model {
 namespace dq {
 
 static int upload(dq_model* m) {
-    if (m->uploaded) return DQ_OK;
     int dev = 0;
     DQ_CUDA(cudaGetDevice(&dev));
+    if (m->uploaded) {
+        // a handle is bound to the device (and thread) of its first solve: its stream, events and cached blocks live there
+        if (dev != m->device) { g_err = "model handle is bound to CUDA device " + std::to_string(m->device) + " (dq_set_device before the first solve)"; return DQ_ERR_INVALID; }
+        return DQ_OK;
+    }
+    m->device = dev;
     DeviceCtx* ctx = nullptr;
     DQ_CUDA(device_ctx(&ctx));
     m->sm_count = ctx->sm_count; m->stream = ctx->stream; m->ev0 = ctx->ev0; m->ev1 = ctx->ev1; m->ev2 = ctx->ev2; m->ev3 = ctx->ev3;
@@ -493,7 +499,8 @@ static int solve_queens_lane(dq_model* m, const dq_tree_opts* opts, dq_tree_resu
         for (int l = 0; l <= K; l++) biggest = std::max(biggest, h_ctrl[8 + l]);
         if (biggest <= rcap) break;
         // a frontier overflowed its list: grow (the last level's count is exact only if the earlier ones fitted) and rerun
-        cap = (size_t)std::max<unsigned long long>(biggest, 2 * rcap);
+        if (biggest > 512ull * 1024 * 1024) { g_err = "frontier of more than 2^29 records: lower split_depth"; return DQ_ERR_UNSUPPORTED; }
+        cap = (size_t)std::min<unsigned long long>(std::max<unsigned long long>(biggest, 2 * rcap), 512ull * 1024 * 1024);
         if (attempt == 2) { g_err = "internal: record list overflow persists"; return DQ_ERR_INTERNAL; }
     }
     res->kernel_ms = ms_total;

@@ -1,6 +1,7 @@
 // dq_formats.cpp — host-side readers for the on-disk instance formats of the batch entry points
 // (SURVEY.md §8f-3): 81-character Sudoku lines and DIMACS .col graphs.  Pure parsing: the solve
 // itself is dq_solve_batch_cells / dq_solve_batch_graphs.
+#include <cstdio>
 #include <cctype>
 #include <cstdlib>
 #include <cstring>

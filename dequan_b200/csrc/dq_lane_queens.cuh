@@ -79,8 +79,8 @@ __device__ __forceinline__ void queens_level_body(const QueensLaneArgs& A, int l
         bool valid = p < pairs;
         uint32_t key = 0, a = 0, l = 0, r = 0;
         if (valid) {
-            const uint32_t rix = (uint32_t)p / (uint32_t)N;                    // pairs < 2^32 (host caps the record list)
-            const uint32_t v = (uint32_t)p - rix * N;
+            const unsigned long long rix = p / (unsigned long long)N;          // (the host caps the list at 2^29 records: pairs may pass 2^32)
+            const uint32_t v = (uint32_t)(p - rix * N);
             // (the fused head kernel reads records it wrote itself one level earlier: no read-only cache path there)
             const uint4 rec = IN_IS_READ_ONLY ? __ldg(in + rix) : __ldcg(in + rix);
             const uint32_t bit = 1u << v;
@@ -563,6 +563,7 @@ k_queens_bucket(QueensLaneArgs A) {
             if (!any) break;
             lvl = __ffs((int)any) - 1;
         }
+        if (nodes >= 0x40000000u) { tot_nodes += nodes; tot_sols += sols; nodes = 0; sols = 0; }   // (a warp that never refills still flushes its 32-bit counts)
         const uint32_t c = __shfl_sync(0xFFFFFFFFu, cnt, lvl);
         const uint32_t n = min(c, 64u);
         const uint32_t keep_base = c - n;

@@ -54,6 +54,9 @@
 #define DEQUAN_Array_Reserve(a, s)          a.reserve(s)
 #define DEQUAN_Array_Back(a)                a.back()
 #define DEQUAN_Array_PopBack(a)             a.pop_back()
+#define DEQUAN_Array_Insert(a, idx, val)    a.insert(a.begin() + (idx), val)
+#define DEQUAN_Array_Erase(a, first, last)  a.erase(a.begin() + (first), a.begin() + (last));
+#define DEQUAN_Array_Sort(a, lambda)        std::sort(a.begin(), a.end(), lambda)
 
 namespace dequan {
 
@@ -667,22 +670,79 @@ inline void CSP::Flatten(const Assignment& a, b200::Lowering& low, std::vector<i
                          std::vector<int32_t>& dom_off, std::vector<int32_t>& dom_vals) const {
     if (scopes_.size() != constraints.size())
         throw b200::Error(DQ_ERR_INVALID, "FinalizeModel() must be called after the last AddConstraint()");
+    // A partially assigned Assignment (the reference resumes at assign_order[assigned_var_count], dequan.h:411-414,
+    // 504): the assigned variables become singleton domains at the head of the order, and because the reference never
+    // filtered from them, every constraint between an assigned and an unassigned variable is lowered CHECK-ONLY (the
+    // value pairs its Evaluate accepts: the unassigned side's values are still visited and fail validation, exactly as
+    // in the reference); a constraint among assigned variables only is never evaluated again and is dropped.
+    const int p = a.assigned_var_count;
+    std::vector<char> pre(vars.size(), 0);
+    for (int i = 0; i < p; i++) pre[a.assign_order[i]] = 1;
     dom_off.assign(1, 0);
-    for (const Domain& d : a.current_domains) {
-        dom_type.push_back(d.type == DomainType::Ranges ? DQ_DOM_RANGES : DQ_DOM_VALUES);
-        dom_vals.insert(dom_vals.end(), d.values.begin(), d.values.end());
+    for (size_t v = 0; v < a.current_domains.size(); v++) {
+        const Domain& d = a.current_domains[v];
+        if (pre[v]) {
+            dom_type.push_back(DQ_DOM_VALUES);
+            dom_vals.push_back(a.inst_vars[v].value);
+        } else {
+            dom_type.push_back(d.type == DomainType::Ranges ? DQ_DOM_RANGES : DQ_DOM_VALUES);
+            dom_vals.insert(dom_vals.end(), d.values.begin(), d.values.end());
+        }
         dom_off.push_back((int32_t)dom_vals.size());
     }
-    for (size_t c = 0; c < constraints.size(); c++)
-        if (!constraints[c].get()->LowerB200(low)) {
-            if (scopes_[c].size() > 2 || scopes_[c].empty()) {
-                // built-in ternary/4-ary constraints land here too
-                throw b200::Error(DQ_ERR_UNSUPPORTED, "constraint #" + std::to_string(c) + " links " +
-                                                          std::to_string(scopes_[c].size()) +
-                                                          " variables; the device engine lowers unary-free binary constraints and AllDifferent only");
+    auto expand = [](const Domain& d) {
+        Array<int> out;
+        if (d.type == DomainType::Values) out = d.values;
+        else
+            for (size_t i = 0; i + 1 < d.values.size(); i += 2)
+                for (int v = d.values[i]; v < d.values[i + 1]; v++) out.push_back(v);
+        return out;
+    };
+    for (size_t c = 0; c < constraints.size(); c++) {
+        const std::vector<VarId>& scope = scopes_[c];
+        size_t n_pre = 0;
+        for (VarId v : scope) n_pre += pre[v];
+        Constraint* con = const_cast<GenericConstraint&>(constraints[c]).get();
+        if (n_pre == 0) {
+            if (!con->LowerB200(low)) {
+                if (scope.size() > 2 || scope.empty()) {
+                    // built-in ternary/4-ary constraints land here too
+                    throw b200::Error(DQ_ERR_UNSUPPORTED, "constraint #" + std::to_string(c) + " links " + std::to_string(scope.size()) +
+                                                              " variables; the device engine lowers unary-free binary constraints and AllDifferent only");
+                }
+                TabulateUserConstraint(c, low);
             }
-            TabulateUserConstraint(c, low);
+            continue;
         }
+        if (n_pre == scope.size()) continue;
+        if (const AllDifferentConstraint* ad = dynamic_cast<const AllDifferentConstraint*>(con)) {
+            std::vector<int32_t> open;
+            for (VarId v : ad->alldiff_vars) if (!pre[v]) open.push_back(v);
+            if (open.size() >= 2) low.Row(DQ_CON_ALLDIFF, open.data(), open.size());
+            for (VarId pv : ad->alldiff_vars) {
+                if (!pre[pv]) continue;
+                const int held = a.inst_vars[pv].value;
+                for (VarId x : open) {
+                    std::vector<int32_t> row{pv, x};
+                    for (int xv : expand(a.current_domains[x])) if (xv != held) { row.push_back(held); row.push_back(xv); }
+                    low.Row(DQ_CON_TABLE, row.data(), row.size());
+                }
+            }
+            continue;
+        }
+        if (scope.size() != 2)
+            throw b200::Error(DQ_ERR_UNSUPPORTED, "constraint #" + std::to_string(c) + " links " + std::to_string(scope.size()) + " variables");
+        const VarId x = pre[scope[0]] ? scope[1] : scope[0];          // the endpoint still to assign
+        Array<InstVar> iv = a.inst_vars;
+        std::vector<int32_t> row{scope[0], scope[1]};
+        for (int xv : expand(a.current_domains[x])) {
+            iv[x].value = xv;
+            if (con->Evaluate(iv, x) == Constraint::Eval::Failed) continue;
+            row.push_back(iv[scope[0]].value);
+            row.push_back(iv[scope[1]].value);
+        }
+        low.Row(DQ_CON_TABLE, row.data(), row.size());
+    }
 }
 
 /* Lowers the CSP with the Assignment's domains and order and compiles it, unless the cached handle was built from the
@@ -725,8 +785,10 @@ inline bool CSP::SolveB200(Assignment& a, int mode, const b200::SolveOptions& op
     const int nv = (int)vars.size();
     if ((int)a.inst_vars.size() != nv || (int)a.current_domains.size() != nv || (int)a.assign_order.size() != nv)
         throw b200::Error(DQ_ERR_INVALID, "Assignment does not belong to this CSP: call a.Reset(csp) first");
-    if (a.assigned_var_count != 0)
-        throw b200::Error(DQ_ERR_UNSUPPORTED, "resuming a partially assigned Assignment is not supported; Reset() it");
+    const int resumed = a.assigned_var_count;            // a prefix of assign_order the caller assigned by hand (dequan.h:504)
+    for (int i = 0; i < nv; i++)
+        if ((a.inst_vars[a.assign_order[i]].value != InstVar::UNASSIGNED) != (i < resumed))
+            throw b200::Error(DQ_ERR_UNSUPPORTED, "the assigned variables must be the first assigned_var_count entries of assign_order");
 
     const bool fresh = CompileB200(a);
 
@@ -741,15 +803,16 @@ inline bool CSP::SolveB200(Assignment& a, int mode, const b200::SolveOptions& op
     const int rc = dq_solve_tree(cache_.handle, &o, &r, first.data());
     if (rc != DQ_OK) throw b200::Error(rc, dq_last_error());
     if (rep) { rep->tree = r; rep->compiled_fresh = fresh; }
+    if (rep) rep->tree.n_nodes -= (uint64_t)resumed;     // (the device visits each pre-assigned singleton once; the reference does not)
 #ifdef DEQUAN_WITH_STATS
-    a.stats.assigned_vars += r.n_nodes;
+    a.stats.assigned_vars += r.n_nodes - (uint64_t)resumed;
 #endif
     const bool have = r.first_key != UINT64_MAX && (nv == 0 || first[0] != InstVar::UNASSIGNED);
     if (!have) return false;
 
     // Leave the Assignment as the reference's recursion leaves it on success: walk the one solution
     // path, one saved-domain frame per depth, each linked constraint filtering in link order.
-    for (int d = 0; d < nv; d++) {
+    for (int d = resumed; d < nv; d++) {
         const VarId vid = a.assign_order[d];
         a.saved_domains.emplace_back();
         a.inst_vars[vid].value = first[vid];

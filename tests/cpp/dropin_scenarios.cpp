@@ -220,6 +220,83 @@ static void user_constraint(const char* name, int gap) {
     report(name, ok, csp, a);
 }
 
+// A partially assigned Assignment: the caller assigns the first variables of assign_order by hand (AssignVar, no
+// filtering) and the solve resumes at assign_order[assigned_var_count] (reference dequan.h:411-414, 504).
+static void resume(const char* name, CSP& csp, const int* vals, int k) {
+    Assignment a;
+    a.Reset(csp);
+    for (int i = 0; i < k; i++) a.AssignVar(a.assign_order[i], vals[i]);
+    bool ok = csp.ForwardCheckingStep(a);
+    report(name, ok, csp, a);
+}
+
+static void queens_resume(const char* name, int n, const int* vals, int k) {
+    CSP csp;
+    queens_model(csp, n);
+    resume(name, csp, vals, k);
+}
+
+static void mixed_resume(const char* name, const int* vals, int k) {
+    CSP csp;
+    int d0[] = {4, -2, 7, 1, 0}, d1[] = {3, 9, -1, 5}, d2[] = {6, 2, 8};
+    VarId a0 = csp.AddIntVar(Domain(DomainType::Values, Array<int>(d0, d0 + 5)));
+    VarId a1 = csp.AddIntVar(Domain(DomainType::Values, Array<int>(d1, d1 + 4)));
+    VarId a2 = csp.AddIntVar(Domain(DomainType::Values, Array<int>(d2, d2 + 3)));
+    VarId a3 = csp.AddIntVar(-3, 6);
+    VarId a4 = csp.AddIntVar(-2, 5);
+    VarId a5 = csp.AddBoolVar();
+    csp.AddConstraint(OpConstraint(a0, a1, OpConstraint::Op::Inf, -2));
+    csp.AddConstraint(OpConstraint(a2, a0, OpConstraint::Op::SupEqual, 5));
+    csp.AddConstraint(OpConstraint(a3, a4, OpConstraint::Op::Equal, -1));
+    csp.AddConstraint(EqualityConstraint(a5, a3));
+    csp.AddConstraint(OrRangeConstraint(a4, a2, 6, 9));
+    csp.AddConstraint(GapConstraint(a1, a2, 1));
+    Array<VarId> ad;
+    ad.push_back(a0); ad.push_back(a3); ad.push_back(a4); ad.push_back(a5);
+    csp.AddConstraint(AllDifferentConstraint(ad));
+    csp.FinalizeModel();
+    resume(name, csp, vals, k);
+}
+
+static void sudoku_resume(const char* name, int k) {     // the first k givens assigned by hand instead of by the search
+    CSP csp;
+    Array<VarId> cell(81);
+    for (int i = 0; i < 81; i++) cell[i] = kGrid[i] ? csp.AddFixedVar(kGrid[i]) : csp.AddIntVar(1, 10);
+    for (int r = 0; r < 9; r++) { Array<VarId> g; for (int c = 0; c < 9; c++) g.push_back(cell[r * 9 + c]); csp.AddConstraint(AllDifferentConstraint(g)); }
+    for (int c = 0; c < 9; c++) { Array<VarId> g; for (int r = 0; r < 9; r++) g.push_back(cell[r * 9 + c]); csp.AddConstraint(AllDifferentConstraint(g)); }
+    for (int b = 0; b < 9; b++) {
+        Array<VarId> g;
+        for (int j = 0; j < 9; j++) g.push_back(cell[(b / 3 * 3 + j / 3) * 9 + (b % 3 * 3 + j % 3)]);
+        csp.AddConstraint(AllDifferentConstraint(g));
+    }
+    csp.FinalizeModel();
+    Assignment a;
+    a.Reset(csp);
+    for (int i = 0; i < k; i++) a.AssignVar(a.assign_order[i], csp.domains[a.assign_order[i]].values[0]);
+    bool ok = csp.ForwardCheckingStep(a);
+    report(name, ok, csp, a);
+}
+
+// The array macros of the reference's std::vector mode (dequan.h:32-42) in user code.
+static void array_macros() {
+    Array<int> vals;
+    DEQUAN_Array_PushBack(vals, 5); DEQUAN_Array_PushBack(vals, 3); DEQUAN_Array_PushBack(vals, 9); DEQUAN_Array_PushBack(vals, 7);
+    DEQUAN_Array_Sort(vals, [](int x, int y) { return x < y; });     // 3 5 7 9
+    DEQUAN_Array_Insert(vals, 1, 4);                                  // 3 4 5 7 9
+    DEQUAN_Array_Erase(vals, 3, 4)                                    // 3 4 5 9 (the macro brings its own semicolon)
+    CSP csp;
+    VarId x = csp.AddIntVar(Domain(DomainType::Values, vals));
+    VarId y = csp.AddIntVar(Domain(DomainType::Values, vals));
+    VarId z = csp.AddIntVar(Domain(DomainType::Values, vals));
+    csp.AddConstraint(OpConstraint(x, y, OpConstraint::Op::Sup, 1));
+    csp.AddConstraint(OpConstraint(z, x, OpConstraint::Op::Sup, 3));
+    csp.FinalizeModel();
+    Assignment a;
+    a.Reset(csp);
+    bool ok = csp.ForwardCheckingStep(a);
+    report("array_macros", ok && DEQUAN_Array_Size(vals) == 4 && DEQUAN_Array_Back(vals) == 9, csp, a);
+}
+
 static void empty_model() {
     CSP csp;
     csp.FinalizeModel();
@@ -291,5 +368,18 @@ int main(int argc, char** argv) {
     wide_domains("wide_domains_sat", 10, false);
     wide_domains("wide_domains_shift40", 40, false);
     wide_domains("wide_domains_unsat", 10, true);
+    { const int v[] = {3}; queens_resume("resume_queens8_first3", 8, v, 1); }
+    { const int v[] = {0, 2, 4}; queens_resume("resume_queens8_prefix024", 8, v, 3); }
+    { const int v[] = {0, 1}; queens_resume("resume_queens8_conflicting_prefix", 8, v, 2); }   // never checked against each other
+    { const int v[] = {5, 5}; queens_resume("resume_queens6_same_row", 6, v, 2); }
+    { const int v[] = {100}; queens_resume("resume_queens6_foreign_value", 6, v, 1); }
+    { const int v[] = {1}; queens_resume("resume_queens3_unsat", 3, v, 1); }
+    { const int v[] = {0, 1, 2, 3, 4, 5}; queens_resume("resume_queens6_all_assigned", 6, v, 6); }
+    { const int v[] = {1, 8}; mixed_resume("resume_mixed_two", v, 2); }
+    { const int v[] = {0, 6, 9}; mixed_resume("resume_mixed_three", v, 3); }
+    { const int v[] = {1, 2, 3, 0}; mixed_resume("resume_mixed_unsat", v, 4); }
+    sudoku_resume("resume_sudoku_10_givens", 10);
+    sudoku_resume("resume_sudoku_all_givens", 32);
+    array_macros();
     return 0;
 }
