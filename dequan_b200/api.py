@@ -54,7 +54,7 @@ class dq_batch_stats(C.Structure):
 
 
 EXPORTS = ["dq_device_info", "dq_set_device", "dq_compile", "dq_free", "dq_model_info", "dq_model_order", "dq_model_table_bytes", "dq_solve_tree",
-           "dq_tree_nodes_upto", "dq_enumerate_solutions", "dq_solve_batch_cells", "dq_solve_batch_cells_dev", "dq_solve_batch_graphs", "dq_solve_batch_graphs_dev",
+           "dq_solve_tree_multi", "dq_tree_nodes_upto", "dq_enumerate_solutions", "dq_solve_batch_cells", "dq_solve_batch_cells_dev", "dq_solve_batch_graphs", "dq_solve_batch_graphs_dev",
            "dq_measure_int_peak", "dq_last_error", "dq_version", "dq_parse_sudoku_lines", "dq_parse_dimacs_col"]
 
 _lib = None
@@ -78,6 +78,7 @@ def lib():
     L.dq_model_order.argtypes = [vp, i32p]
     L.dq_model_table_bytes.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.dq_solve_tree.argtypes = [vp, C.POINTER(dq_tree_opts), C.POINTER(dq_tree_result), i32p]
+    L.dq_solve_tree_multi.argtypes = [vp, C.POINTER(dq_tree_opts), C.c_int32, i32p, C.POINTER(dq_tree_result), i32p]
     L.dq_tree_nodes_upto.argtypes = [vp, C.c_uint64, C.POINTER(C.c_uint64)]
     L.dq_enumerate_solutions.argtypes = [vp, C.POINTER(dq_tree_opts), C.POINTER(dq_tree_result), i32p, C.c_uint64, C.POINTER(C.c_uint64)]
     L.dq_solve_batch_cells.argtypes = [vp, u8p, C.c_int64, C.c_int32, C.POINTER(dq_batch_opts), u8p, u64p, u8p,
@@ -195,6 +196,21 @@ class Model:
         r = dq_tree_result()
         first = np.zeros(max(self.n_vars, 1), dtype=np.int32)
         _check(lib().dq_solve_tree(self._h, C.byref(o), C.byref(r), first.ctypes.data_as(C.POINTER(C.c_int32))))
+        have = r.first_key != U64_MAX and (self.n_vars == 0 or first[0] != UNASSIGNED)
+        return TreeResult(OUTCOME[r.outcome], r.n_solutions, r.n_nodes, first[:self.n_vars].tolist() if have else None,
+                          r.first_key, r.n_prefixes, r.split_depth_used, r.kernel_ms,
+                          ENGINE_NAME.get(r.engine_used, "?"), r.kernel_launches, r.search_kernel_ms, r.frontier_nodes)
+
+    def solve_tree_multi(self, mode: str = "first", devices=(0,), split_depth: int = 0, engine: str = "auto",
+                         time_kernels: bool = False) -> TreeResult:
+        """dq_solve_tree_multi: one process, one partition of the prefix-split tree per entry of `devices`."""
+        o = dq_tree_opts(DQ_MODE_COUNT_ALL if mode == "count" else DQ_MODE_FIRST, split_depth, 0, 1, 0, ENGINE[engine],
+                         1 if time_kernels else 0)
+        r = dq_tree_result()
+        first = np.zeros(max(self.n_vars, 1), dtype=np.int32)
+        devs = np.array(list(devices), dtype=np.int32)
+        _check(lib().dq_solve_tree_multi(self._h, C.byref(o), len(devs), devs.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(r),
+                                         first.ctypes.data_as(C.POINTER(C.c_int32))))
         have = r.first_key != U64_MAX and (self.n_vars == 0 or first[0] != UNASSIGNED)
         return TreeResult(OUTCOME[r.outcome], r.n_solutions, r.n_nodes, first[:self.n_vars].tolist() if have else None,
                           r.first_key, r.n_prefixes, r.split_depth_used, r.kernel_ms,

@@ -2,10 +2,14 @@
 // Host orchestration only: table upload, frontier expansion loop, kernel launches, result
 // gathering.  No search runs on the CPU; every solve needs a CUDA device.
 #include <algorithm>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "dequan_b200.h"
@@ -135,6 +139,9 @@ struct LevelArrays {               // kept per expansion level for FIRST-mode no
 
 using namespace dq;
 
+struct MultiCtx;
+static void multi_destroy(MultiCtx* mc);
+
 struct dq_model {
     CompiledModel cm;
     bool uploaded = false;
@@ -181,6 +188,8 @@ struct dq_model {
     DevBuf<uint4> s_snaps;
     DevBuf<int> s_deferred;
     unsigned long long s_tasks_used = 0;
+    // dq_solve_tree_multi: one worker thread + one clone of the compiled model per device
+    struct MultiCtx* multi = nullptr;
 };
 
 namespace dq {
@@ -557,6 +566,7 @@ int dq_compile(const dq_model_desc* desc, dq_model** out) {
 
 void dq_free(dq_model* m) {
     if (!m) return;
+    if (m->multi) { multi_destroy(m->multi); m->multi = nullptr; }
     if (m->q_exec) { cudaGraphExecDestroy(m->q_exec); m->q_exec = nullptr; }
     if (m->uploaded) {
         m->d_blob.release(); m->d_ctrl.release();
@@ -922,6 +932,124 @@ int dq_tree_nodes_upto(dq_model* m, uint64_t key, uint64_t* nodes) {
         }
     }
     *nodes = total;
+    return DQ_OK;
+}
+
+}  // extern "C"
+
+// ---- single-process multi-GPU tree solve (SURVEY.md par. 8e) ----
+// One worker thread per device (streams, events and the block cache of this library are per thread and device), each
+// with its own clone of the compiled model; partition i of the prefix-split tree goes to worker i.  What comes back
+// per device is three 64-bit words and one value per variable; the tail — solution-count and node-count sums, lowest
+// first-solution key with its solution attached — is reduced on the calling thread.
+struct MultiWorker {
+    int dev = 0;
+    dq_model* clone = nullptr;
+    std::thread th;
+    std::mutex mu;
+    std::condition_variable cv;
+    int job = 0;                      // 0 idle, 1 solve, 2 nodes_upto, 3 quit
+    bool done = false;
+    dq_tree_opts opts{};
+    dq_tree_result res{};
+    std::vector<int32_t> first;
+    uint64_t key = 0, upto = 0;
+    int rc = DQ_OK;
+    std::string err;
+    void loop() {
+        if (cudaSetDevice(dev) != cudaSuccess) { (void)cudaGetLastError(); }
+        for (;;) {
+            int j;
+            { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return job != 0; }); j = job; }
+            if (j == 3) { dq_free(clone); clone = nullptr; g_cache.trim(); return; }
+            if (j == 1) rc = solve_tree_impl(clone, &opts, &res, first.data(), nullptr);
+            else rc = dq_tree_nodes_upto(clone, key, &upto);
+            err = g_err;
+            { std::lock_guard<std::mutex> lk(mu); job = 0; done = true; }
+            cv.notify_all();
+        }
+    }
+    void post(int j) { { std::lock_guard<std::mutex> lk(mu); job = j; done = false; } cv.notify_all(); }
+    void wait() { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return done; }); }
+};
+struct MultiCtx {
+    std::vector<int> devices;
+    std::vector<std::unique_ptr<MultiWorker>> w;
+};
+static void multi_destroy(MultiCtx* mc) {
+    for (auto& w : mc->w) { w->post(3); if (w->th.joinable()) w->th.join(); }
+    delete mc;
+}
+
+extern "C" {
+
+int dq_solve_tree_multi(dq_model* m, const dq_tree_opts* opts, int32_t n_devices, const int32_t* devices, dq_tree_result* res,
+                        int32_t* first_solution) {
+    if (!m || !opts || !res) { g_err = "null argument"; return DQ_ERR_INVALID; }
+    if (n_devices < 1 || n_devices > 64) { g_err = "bad device count"; return DQ_ERR_INVALID; }
+    if (opts->part_count > 1 || opts->part_rank != 0) { g_err = "dq_solve_tree_multi partitions the tree itself: part_rank / part_count must be 0 / 1"; return DQ_ERR_INVALID; }
+    int have = 0;
+    DQ_CUDA(cudaGetDeviceCount(&have));
+    std::vector<int> devs(n_devices);
+    for (int i = 0; i < n_devices; i++) {
+        devs[i] = devices ? devices[i] : i;
+        if (devs[i] < 0 || devs[i] >= have) { g_err = "no CUDA device " + std::to_string(devs[i]); return DQ_ERR_INVALID; }
+    }
+    const int nv = m->cm.nv;
+    if (!m->multi || m->multi->devices != devs) {
+        if (m->multi) multi_destroy(m->multi);
+        m->multi = new MultiCtx();
+        m->multi->devices = devs;
+        for (int i = 0; i < n_devices; i++) {
+            std::unique_ptr<MultiWorker> w(new MultiWorker());
+            w->dev = devs[i];
+            w->clone = new dq_model();
+            w->clone->cm = m->cm;
+            w->first.assign(std::max(nv, 1), 0);
+            MultiWorker* raw = w.get();
+            w->th = std::thread([raw] { raw->loop(); });
+            m->multi->w.push_back(std::move(w));
+        }
+    }
+    MultiCtx* mc = m->multi;
+    for (int i = 0; i < n_devices; i++) {
+        MultiWorker& w = *mc->w[i];
+        w.opts = *opts;
+        w.opts.part_rank = i;
+        w.opts.part_count = n_devices;
+        w.post(1);
+    }
+    for (auto& w : mc->w) w->wait();
+    for (auto& w : mc->w) if (w->rc != DQ_OK) { g_err = "device " + std::to_string(w->dev) + ": " + w->err; return w->rc; }
+    // the tail: sums, and the solution of the lowest DFS key (keys of different partitions never tie)
+    const bool count_all = opts->mode == DQ_MODE_COUNT_ALL;
+    int owner = 0;
+    for (int i = 1; i < n_devices; i++) if (mc->w[i]->res.first_key < mc->w[owner]->res.first_key) owner = i;
+    const uint64_t key = mc->w[owner]->res.first_key;
+    *res = mc->w[0]->res;
+    res->first_key = key;
+    res->n_solutions = 0; res->n_nodes = 0; res->kernel_launches = 0; res->frontier_nodes = 0;
+    for (auto& w : mc->w) {
+        res->kernel_ms = std::max(res->kernel_ms, w->res.kernel_ms);
+        res->search_kernel_ms = std::max(res->search_kernel_ms, w->res.search_kernel_ms);
+        res->kernel_launches += w->res.kernel_launches;
+        res->frontier_nodes += w->res.frontier_nodes;
+        if (count_all) { res->n_solutions += w->res.n_solutions; res->n_nodes += w->res.n_nodes; }
+    }
+    if (!count_all) {
+        // nodes of the reference's sequential search up to the first solution: every partition's share below the GLOBAL key
+        for (auto& w : mc->w) { w->key = key; w->post(2); }
+        for (auto& w : mc->w) w->wait();
+        for (auto& w : mc->w) {
+            if (w->rc != DQ_OK) { g_err = "device " + std::to_string(w->dev) + ": " + w->err; return w->rc; }
+            res->n_nodes += w->upto;
+        }
+        res->n_solutions = key != KEY_NONE ? 1 : 0;
+        res->nodes_before_first = res->n_nodes;
+    }
+    res->outcome = res->n_solutions ? DQ_SAT : DQ_UNSAT;
+    if (first_solution)
+        for (int v = 0; v < nv; v++) first_solution[v] = key != KEY_NONE ? mc->w[owner]->first[v] : -2147483647;
     return DQ_OK;
 }
 

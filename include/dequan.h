@@ -505,8 +505,9 @@ namespace b200 {
 struct SolveOptions {
     int engine = DQ_ENGINE_AUTO;
     int split_depth = 0;        // <= 0: automatic
-    int part_rank = 0;          // multi-GPU: this process' partition of the prefix-split tree
+    int part_rank = 0;          // one process per GPU: this process' partition of the prefix-split tree
     int part_count = 1;
+    int n_gpus = 1;             // > 1: this one call deals the tree to CUDA devices 0..n_gpus-1 (dq_solve_tree_multi)
 };
 
 /* What a device solve reports beyond the Assignment. */
@@ -800,7 +801,8 @@ inline bool CSP::SolveB200(Assignment& a, int mode, const b200::SolveOptions& op
     o.engine = opt.engine;
     dq_tree_result r{};
     std::vector<int32_t> first((size_t)std::max(nv, 1), InstVar::UNASSIGNED);
-    const int rc = dq_solve_tree(cache_.handle, &o, &r, first.data());
+    const int rc = opt.n_gpus > 1 ? dq_solve_tree_multi(cache_.handle, &o, opt.n_gpus, nullptr, &r, first.data())
+                                  : dq_solve_tree(cache_.handle, &o, &r, first.data());
     if (rc != DQ_OK) throw b200::Error(rc, dq_last_error());
     if (rep) { rep->tree = r; rep->compiled_fresh = fresh; }
     if (rep) rep->tree.n_nodes -= (uint64_t)resumed;     // (the device visits each pre-assigned singleton once; the reference does not)

@@ -195,6 +195,14 @@ int dq_model_table_bytes(const dq_model *m, uint64_t *bytes);
 int dq_solve_tree(dq_model *m, const dq_tree_opts *opts,
                   dq_tree_result *res, int32_t *first_solution);
 
+/* The same solve on `n_devices` GPUs of this process: the prefix-split tree is dealt to the devices (partition i ->
+ * devices[i]; NULL = ordinals 0..n_devices-1; an ordinal may repeat), one worker thread per device, and the tail —
+ * solution-count and node-count sums, lexicographic-min first solution — is reduced here.  opts->part_rank /
+ * part_count must be 0 / 1.  res: sums over the devices; kernel_ms = the slowest device.  One call, one answer: what
+ * `a.Reset(csp); csp.ForwardCheckingStep(a)` (dequan.h:292, 347) is on one thread of the reference.            */
+int dq_solve_tree_multi(dq_model *m, const dq_tree_opts *opts, int32_t n_devices, const int32_t *devices,
+                        dq_tree_result *res, int32_t *first_solution);
+
 /* FIRST-mode node accounting across partitions (multi-GPU): after dq_solve_tree, the number of
  * nodes (AssignVar calls, dequan.h:416-423) the reference's sequential search would have visited
  * up to and including the solution inside prefix `key`, restricted to the subtrees this

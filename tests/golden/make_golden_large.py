@@ -2,7 +2,7 @@
 (oracle/_ref/dequan_ref, built from /root/reference/dequan.h by oracle/Makefile) on the
 BASELINE.json shapes that make_golden.py leaves out because they take minutes of CPU:
 
-  * N-Queens N = 15, 16, 17 all-solutions (solutions, nodes = stats.assigned_vars, DFS-first solution);
+  * N-Queens N = 15, 16, 17 (and, section queens18, 18) all-solutions (solutions, nodes = stats.assigned_vars, DFS-first solution);
     the tree is split on the first variable's value with singleton domains, one reference solve per
     value (SURVEY.md §8c "parallel CPU split"), and the per-value results are kept as well;
   * config C4 as stated: G(200, c/199), k=3 c in {4.0, 4.2, 4.4, 4.69}, k=4 c in {6, 7}, 64 instances
@@ -11,7 +11,7 @@ BASELINE.json shapes that make_golden.py leaves out because they take minutes of
 
 Run in the build container only (the GPU box has no /root/reference):
     make -C oracle ref && python tests/golden/make_golden_large.py [section ...]
-Sections: queens colouring sudoku (default: all).  An existing file is updated section by section.
+Sections: queens colouring sudoku (default: all), queens18 (18-Queens, about two hours on six cores).  An existing file is updated section by section.
 """
 import hashlib
 import json
@@ -41,10 +41,10 @@ def run(args):
     return [json.loads(line) for line in out.splitlines()]
 
 
-def queens(gold):
+def queens(gold, sizes=(15, 16, 17)):
     from concurrent.futures import ThreadPoolExecutor
     gold.setdefault("nqueens", {})
-    for n in (15, 16, 17):
+    for n in sizes:
         # one single-threaded reference solve per first-row value v (variable 0 gets the singleton domain {v},
         # stays first in assign_order): nodes = 1 + the subtree below, so the sum over v is the whole tree.
         def task(v):
@@ -111,7 +111,7 @@ def main():
             gold.update(json.load(f))
     sections = sys.argv[1:] or ["colouring", "sudoku", "queens"]
     for s in sections:
-        {"queens": queens, "colouring": colouring, "sudoku": sudoku}[s](gold)
+        {"queens": queens, "queens18": lambda g: queens(g, (18,)), "colouring": colouring, "sudoku": sudoku}[s](gold)
     print("wrote", OUT, os.path.getsize(OUT))
 
 

@@ -766,6 +766,33 @@ def test_17_queens_in_four_partitions(golden_large, product_lib):
     assert (whole.solutions, whole.nodes, whole.first) == (g["solutions"], g["nodes"], g["first"])
 
 
+def test_single_process_multi_device_solve(golden, product_lib):
+    """dq_solve_tree_multi: one call deals the prefix-split tree to several devices (worker thread + model clone each)
+    and reduces the tail itself.  A device may be named more than once, so the partition / reduction logic is
+    exercised on a one-GPU box too; with two or more GPUs the same list of checks runs across real devices."""
+    import torch
+    lists = [(0,), (0, 0), (0, 0, 0)]
+    if torch.cuda.device_count() >= 2:
+        lists += [(0, 1), tuple(range(torch.cuda.device_count()))]
+    for n in (8, 12):
+        g = golden["nqueens"][str(n)]
+        m = api.Model(nqueens(n))
+        for devs in lists:
+            c = m.solve_tree_multi("count", devs)
+            assert (c.solutions, c.nodes, c.first) == (g["count"]["solutions"], g["count"]["nodes"], g["count"]["first"]), (n, devs, c)
+            f = m.solve_tree_multi("first", devs)
+            assert (f.status, f.nodes, f.first) == (g["first"]["status"], g["first"]["nodes"], g["first"]["first"]), (n, devs, f)
+    for seed in range(9100, 9130):
+        csp = random_model(seed, n_vars=10, n_cons=15, max_dom=6)
+        m = api.Model(csp)
+        for mode in ("first", "count"):
+            want = O.solve(csp, mode)
+            for devs in lists[1:]:
+                _cmp_tree(m.solve_tree_multi(mode, devs, split_depth=2), want, (seed, mode, devs))
+    with pytest.raises(api.DequanError):
+        api.Model(nqueens(6)).solve_tree_multi("count", (0, 99))
+
+
 def test_sudoku_10k_vs_reference(golden_large, product_lib):
     """The first 10 000 puzzles of the 1 M batch (config C3): node count and solution of every puzzle against the
     unmodified reference (810 binary NotEqual constraints, tests/golden/make_golden_large.py)."""
