@@ -544,5 +544,14 @@ def colouring_rooflines(out, int_peak, hbm_peak, peak_src):
     return out
 
 
+def _quiet_stdout():
+    """The driver reads ONE JSON line from stdout: native libraries that print there (the NCCL version banner) are sent
+    to stderr, and `print` keeps the real stdout."""
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real
+
+
 if __name__ == "__main__":
+    _quiet_stdout()
     main()

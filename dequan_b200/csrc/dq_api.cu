@@ -332,38 +332,28 @@ static int solve_queens_lane(dq_model* m, const dq_tree_opts* opts, dq_tree_resu
     const int N = m->cm.queens_n;
     // Split depth: measured per board size on B200 (scripts/sweep_k.py, profiles/r1_queens_split_depth.txt), see below.
     int K = 0;
-    auto dfs_smem = [&](int k) { return (size_t)std::max(N - 2 - k, 1) * kQueensBlock * sizeof(uint4); };
     // estimated FC-surviving prefixes per depth (sizes the record lists): each level multiplies by about N - 2.2*depth
     auto estimate = [&](int k) { double e = 1; for (int i = 0; i < k; i++) e *= std::max(N - 2.2 * i, 3.6); return e; };
     int occ = 0;
     int rc = DQ_OK;
     if (opts->split_depth > 0) K = std::min(opts->split_depth, std::min(N - 2, 12));
     else {
-        K = std::max(std::min(N - 7, N <= 15 ? 6 : 7), 0);          // the lane-per-subtree engine's depths
-        if (!(getenv("DQ_QUEENS_ENGINE") && !strcmp(getenv("DQ_QUEENS_ENGINE"), "lane"))) {
-            // bucket search, measured per N (scripts/sweep_k.py, profiles/r1_queens_split_depth.txt): small boards are bound
-            // by the launches of the levels, large ones by keeping the pools fed to the end (18 queens: 132 -> 121 ms at
-            // depth 8); the partitions of a strongly scaled 17-Queens solve hold 1/parts of the records each and split one
-            // level deeper as well (8 partitions: 2.43 -> 2.28 ms, scripts/parts_k.py)
-            if (N <= 13) K = std::max(N - 8, 0);
-            else if (N <= 15) K = 7;
-            else if (N == 16) K = 8;
-            else if (N == 17) K = 9;                   // 124 M records (2 GB per list): 16.7 -> 15.3 ms; partitions 2.25 -> 2.04 ms
-            else K = 8;
-        }
+        // measured per N (scripts/sweep_k.py, profiles/r1_queens_split_depth.txt): small boards are bound by the launches of
+        // the levels, large ones by keeping the pools fed to the end (18 queens: 132 -> 121 ms at depth 8); the partitions
+        // of a strongly scaled 17-Queens solve hold 1/parts of the records each and split one level deeper as well
+        // (8 partitions: 2.43 -> 2.28 ms, scripts/parts_k.py)
+        if (N <= 13) K = std::max(N - 8, 0);
+        else if (N <= 15) K = 7;
+        else if (N == 16) K = 8;
+        else if (N == 17) K = 9;                   // 124 M records (2 GB per list): 16.7 -> 15.3 ms; partitions 2.25 -> 2.04 ms
+        else K = 8;
     }
-    auto key_space = [&](int k) { double keys = 1; for (int i = 0; i < k; i++) keys *= N; return keys; };
-    // the lane engine reads 32-bit prefix keys from its records; the bucket search reads none (its first-solution warp
-    // computes 64-bit keys, and the partition deal happens at depth <= 5), so its split may go deeper
-    const bool deep_ok = !(getenv("DQ_QUEENS_ENGINE") && !strcmp(getenv("DQ_QUEENS_ENGINE"), "lane"));
-    while (K > 0 && !deep_ok && key_space(K) > 4.0e9) K--;   // (res->split_depth_used reports K)
-    // the search kernel: depth-bucketed warp pools (default) or the older lane-per-subtree stacks (DQ_QUEENS_ENGINE=lane)
-    static const bool use_buckets = !(getenv("DQ_QUEENS_ENGINE") && !strcmp(getenv("DQ_QUEENS_ENGINE"), "lane"));
-    // bucket search: warps per CTA chosen so that the pools (buckets x 128 frames x 16 B per warp) pack an SM's shared memory best
+    // (the bucket search reads no prefix keys from its records — its first-solution warp computes 64-bit keys, and the
+    // partition deal happens at depth <= 5 — so the split may go deeper than 32-bit keys would allow)
+    // warps per CTA chosen so that the pools (buckets x 128 frames x 16 B + the staging buffer, per warp) pack an SM's shared memory best
     int bucket_warps = 4;
-    size_t smem = dfs_smem(K);
-    if (use_buckets) {
-        const size_t per_warp = (size_t)(N - 1 - K) * kQueensBucketCap * sizeof(uint4);
+    const size_t per_warp = (size_t)(N - 1 - K) * kQueensBucketCap * sizeof(uint4) + kQueensStageBytes;
+    {
         int best = 0;
         for (int w = 2; w <= kQueensBucketMaxWarps; w++) {
             if (per_warp * w > 200 * 1024) break;
@@ -373,12 +363,8 @@ static int solve_queens_lane(dq_model* m, const dq_tree_opts* opts, dq_tree_resu
             if (o * w > best) { best = o * w; bucket_warps = w; occ = o; }
         }
         if (best == 0) { g_err = "board too large for the shared-memory pools"; return DQ_ERR_UNSUPPORTED; }
-        smem = per_warp * bucket_warps;
-    } else {
-        if (smem > 200 * 1024) { g_err = "board too large for the shared-memory stack"; return DQ_ERR_UNSUPPORTED; }
-        rc = max_ctas_per_sm(k_queens_lane, kQueensBlock, smem, &occ);
-        if (rc != DQ_OK) return rc;
     }
+    const size_t smem = per_warp * bucket_warps;
     if (occ < 1) { g_err = "kernel does not fit an SM"; return DQ_ERR_UNSUPPORTED; }
     const int ctas = occ * m->sm_count;
     DQ_CUDA(m->q_first.reserve(32));
@@ -395,7 +381,7 @@ static int solve_queens_lane(dq_model* m, const dq_tree_opts* opts, dq_tree_resu
     const char* env_pl = getenv("DQ_QUEENS_PART_LEVEL");
     const int part_level = std::min(K - 1, env_pl ? atoi(env_pl) : 4);     // measured: depth-5 keys balance 2/4/8 partitions within 3 %
     // levels 0 .. head-1 in one single-CTA launch (a few hundred records at most, all above the partition level)
-    const int head = use_buckets ? std::max(0, std::min(std::min(K, part_level), 3)) : 0;
+    const int head = std::max(0, std::min(std::min(K, part_level), 3));
     static const bool use_graph = getenv("DQ_NO_GRAPH") == nullptr;
     for (int attempt = 0; attempt < 3; attempt++) {
         DQ_CUDA(m->q_records.reserve(cap));
@@ -424,20 +410,18 @@ static int solve_queens_lane(dq_model* m, const dq_tree_opts* opts, dq_tree_resu
             if (with_events) DQ_CUDA(cudaEventRecord(m->ev0, m->stream));
             DQ_CUDA(cudaMemcpyAsync(ctrl, h_init, 32 * sizeof(unsigned long long), cudaMemcpyHostToDevice, m->stream));
             DQ_CUDA(cudaMemcpyAsync(buf[0], h_root, sizeof(uint4), cudaMemcpyHostToDevice, m->stream));
-            if (use_buckets) {
-                // the DFS-first solution needs nothing from the frontier: one warp looks for it on the side stream
-                DQ_CUDA(cudaEventRecord(m->ev_fork, m->stream));
-                DQ_CUDA(cudaStreamWaitEvent(m->stream2, m->ev_fork, 0));
-                k_queens_first_warp<<<1, 32, 0, m->stream2>>>(A);
-                DQ_CUDA(cudaEventRecord(m->ev_join, m->stream2));
-            }
+            // the DFS-first solution needs nothing from the frontier: one warp looks for it on the side stream
+            DQ_CUDA(cudaEventRecord(m->ev_fork, m->stream));
+            DQ_CUDA(cudaStreamWaitEvent(m->stream2, m->ev_fork, 0));
+            k_queens_first_warp<<<1, 32, 0, m->stream2>>>(A);
+            DQ_CUDA(cudaEventRecord(m->ev_join, m->stream2));
             if (head > 0)
                 k_queens_levels_head<<<1, kQueensBlock, 0, m->stream>>>(A, head, buf[0], buf[1], ctrl + 8, opts->part_rank == 0 ? 1 : 0);
             for (int l = head; l < K; l++) {
                 const int grid = (int)std::min<double>(std::max(estimate(l) * N / kQueensBlock, 1.0), (double)m->sm_count * 8);
                 const int count_nodes = (l > part_level || opts->part_rank == 0) ? 1 : 0;
                 // wide frontiers: lane per record (k_queens_level_wide); narrow ones: lane per (record, value) pair
-                if (use_buckets && estimate(l) >= 150000.0) {      // (below that the pair kernel's single trip has the shorter latency)
+                if (estimate(l) >= 150000.0) {      // (below that the pair kernel's single trip has the shorter latency)
                     const int wgrid = (int)std::min<double>(std::max(estimate(l) / kQueensBlock, 1.0), (double)m->sm_count * 8);
                     k_queens_level_wide<<<wgrid, kQueensBlock, 0, m->stream>>>(A, l, buf[l & 1], ctrl + 8 + l, buf[(l + 1) & 1], ctrl + 8 + l + 1,
                                                                                 count_nodes, (l == part_level && opts->part_count > 1) ? 1 : 0);
@@ -446,28 +430,22 @@ static int solve_queens_lane(dq_model* m, const dq_tree_opts* opts, dq_tree_resu
                                                                        count_nodes, (l == part_level && opts->part_count > 1) ? 1 : 0);
             }
             if (with_events) DQ_CUDA(cudaEventRecord(m->ev2, m->stream));
-            if (use_buckets) {
-                k_queens_bucket<<<ctas, bucket_warps * 32, smem, m->stream>>>(A);
-                if (with_events) DQ_CUDA(cudaEventRecord(m->ev3, m->stream));
-                DQ_CUDA(cudaStreamWaitEvent(m->stream, m->ev_join, 0));
-            } else {
-                k_queens_lane<<<ctas, kQueensBlock, smem, m->stream>>>(A);
-                if (with_events) DQ_CUDA(cudaEventRecord(m->ev3, m->stream));
-                k_queens_first<<<1, 32, 0, m->stream>>>(A);
-            }
+            k_queens_bucket<<<ctas, bucket_warps * 32, smem, m->stream>>>(A);
+            if (with_events) DQ_CUDA(cudaEventRecord(m->ev3, m->stream));
+            DQ_CUDA(cudaStreamWaitEvent(m->stream, m->ev_join, 0));
             DQ_CUDA(cudaGetLastError());
             DQ_CUDA(cudaMemcpyAsync(h_ctrl, ctrl, 32 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, m->stream));
             DQ_CUDA(cudaMemcpyAsync(h_first, m->q_first.p, 32, cudaMemcpyDeviceToHost, m->stream));
             if (with_events) DQ_CUDA(cudaEventRecord(m->ev1, m->stream));
             return DQ_OK;
         };
-        launches += (use_buckets ? (K - head) + (head > 0 ? 1 : 0) + 2 : K + 2);
+        launches += (K - head) + (head > 0 ? 1 : 0) + 2;
 
         // One graph launch instead of ~20 API calls (a 14-Queens solve is 0.16 ms of kernels): the queue is captured once
         // per (model, split, partition, buffers) and replayed; anything that changes one of those re-captures it.
         bool queued = false;
         const bool time_kernels = (opts->flags & DQ_TREE_TIME_KERNELS) != 0;
-        if (use_graph && use_buckets && !time_kernels) {
+        if (use_graph && !time_kernels) {
             const unsigned long long key[6] = {(unsigned long long)K | ((unsigned long long)opts->part_rank << 16) | ((unsigned long long)opts->part_count << 32),
                                                (unsigned long long)rcap, (unsigned long long)(uintptr_t)buf[0], (unsigned long long)(uintptr_t)buf[1],
                                                (unsigned long long)(uintptr_t)ctrl, (unsigned long long)(uintptr_t)m->q_first.p};
@@ -1149,7 +1127,14 @@ static int run_batch_sudoku(dq_model* m, const uint8_t* cells_dev, int64_t n, in
     const long long sms = m->sm_count;
     DQ_CUDA(cudaEventRecord(m->ev0, m->stream));
     mark(0);
-    k_sudoku_digest<<<(unsigned)((n + 127) / 128), 128, 128 * 81, m->stream>>>(cells_dev, n, stride, m->s_digest.p);
+    {
+        int occ_d = 0;
+        rc = max_ctas_per_sm(k_sudoku_digest, kDigestTile, kDigestSmem, &occ_d);
+        if (rc != DQ_OK) return rc;
+        const long long tiles = (n + kDigestTile - 1) / kDigestTile;
+        k_sudoku_digest<<<(unsigned)std::max<long long>(1, std::min<long long>(tiles, (long long)std::max(occ_d, 1) * sms)), kDigestTile, kDigestSmem, m->stream>>>(
+            cells_dev, n, stride, m->s_digest.p);
+    }
     mark(1);
     const long long ctas_first = std::max<long long>(1, std::min<long long>(occ_first * sms, (long long)((n + kSudokuBlock - 1) / kSudokuBlock)));
     k_sudoku_first<<<(unsigned)ctas_first, kSudokuBlock, smem, m->stream>>>(A);

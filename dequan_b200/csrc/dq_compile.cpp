@@ -157,6 +157,10 @@ int compile_model(const dq_model_desc* d, CompiledModel& M, std::string& err) {
             case DQ_CON_EQ:      if (k.n != 2) { err = "EQ payload"; return DQ_ERR_INVALID; } break;
             case DQ_CON_ORRANGE: if (k.n != 4) { err = "ORRANGE payload"; return DQ_ERR_INVALID; } break;
             case DQ_CON_TABLE:   if (k.n < 2 || (k.n % 2)) { err = "TABLE payload"; return DQ_ERR_INVALID; } break;
+            case DQ_CON_FILTER:
+                if (k.n < 5 || k.data[2] < 0 || k.data[3] < 0 || k.data[4] < 0 ||
+                    (long long)k.n != 5 + 2 * ((long long)k.data[2] + k.data[3] + k.data[4])) { err = "FILTER payload"; return DQ_ERR_INVALID; }
+                break;
             case DQ_CON_ALLDIFF: break;
             default: err = "constraint kind outside the engine's scope (ternary+ constraints are not lowered)"; return DQ_ERR_UNSUPPORTED;
         }
@@ -263,6 +267,31 @@ int compile_model(const dq_model_desc* d, CompiledModel& M, std::string& err) {
                     m[b] = bad;
                 }
                 push(q, K_CHK, std::move(m));
+            } else if (k.kind == DQ_CON_FILTER) {
+                // a user constraint with its own AplyArcConsistency: what assigning x leaves of q (a plain AND mask, in
+                // link order with the other filters on the pair) + the values of q its Evaluate will reject later
+                const bool x_is_v0 = (k.data[0] == x);
+                const int q = x_is_v0 ? k.data[1] : k.data[0];
+                const int n_allow = k.data[2], n01 = k.data[3], n10 = k.data[4];
+                const int32_t* pr = k.data + 5;
+                std::set<std::pair<int, int>> allowed, keep;
+                for (int i = 0; i < n_allow; i++) allowed.insert({pr[2 * i], pr[2 * i + 1]});
+                const int32_t* kp = pr + 2 * n_allow + (x_is_v0 ? 0 : 2 * n01);
+                for (int i = 0; i < (x_is_v0 ? n01 : n10); i++) keep.insert({kp[2 * i], kp[2 * i + 1]});
+                std::vector<Mask> ma(kx), mc(kx);
+                for (int b = 0; b < kx; b++) {
+                    Mask kept = 0, bad = 0;
+                    for (size_t j = 0; j < M.values[q].size(); j++) {
+                        std::pair<int, int> p2 = x_is_v0 ? std::make_pair((int)xv[b], (int)M.values[q][j])
+                                                         : std::make_pair((int)M.values[q][j], (int)xv[b]);
+                        if (keep.count(p2)) kept |= Mask(1) << j;
+                        if (!allowed.count(p2)) bad |= Mask(1) << j;
+                    }
+                    ma[b] = kept;
+                    mc[b] = bad;
+                }
+                push(q, K_AND, std::move(ma));
+                push(q, K_CHK, std::move(mc));
             }
         }
         // normalise each pair: merge adjacent ANDs, gather all CHKs (they commute) at the end

@@ -25,15 +25,13 @@
 //   k_queens_first_warp : one warp, on a side stream, walks the tree in the reference's order to the
 //                         DFS-first solution of this partition (solution bookkeeping stays out of the
 //                         counting kernel).
-//   k_queens_lane / k_queens_first : the earlier lane-per-subtree search (explicit stack per lane,
-//                         [level][thread] frames in shared memory), kept for comparison
-//                         (DQ_QUEENS_ENGINE=lane; profiles/r1_ncu_queens17_lane_old.txt).
 // Prefixes are dealt to partitions (multi-GPU) by key at depth min(k, 5): partition r owns keys = r (mod parts);
 // the levels above that depth are expanded by every partition and counted by partition 0 only, the levels below
 // it by the owner alone.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
+#include "dq_group_graphs.cuh"     // bulk-copy / mbarrier primitives
 
 namespace dq {
 
@@ -227,210 +225,11 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t x, uint32_t y, ui
 __device__ __forceinline__ uint32_t shl_clamp(uint32_t x, uint32_t n) { uint32_t r; asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(n)); return r; }
 __device__ __forceinline__ uint32_t shr_clamp(uint32_t x, uint32_t n) { uint32_t r; asm("shr.u32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(n)); return r; }
 
-// Phase B: persistent lanes, DFS below each record.  Dynamic shared memory: uint4[levels][256].
-//
-// Register conventions in the hot loop:
-//   a   has every bit >= N permanently set, so a domain is a single ~(a|l|r) with no masking and the
-//       depth is popc(a) - (32 - N);
-//   the forward check walks the later variables from the LAST one backwards (t = 0 is variable N-1):
-//       its distance from the next variable is j = last - t, which goes "negative" for lanes that are
-//       deeper than the warp's shallowest lane; as an unsigned shift amount that clamps both diagonal
-//       terms to 0, so those extra rows see the non-empty ~a and pass — no per-row bounds test;
-//   the wipe-out test is an unsigned max over the rows' occupied masks (all ones <=> some domain is empty).
-__global__ void __launch_bounds__(kQueensBlock)
-k_queens_lane(QueensLaneArgs A) {
-    extern __shared__ uint4 frames[];
-    const int lane = threadIdx.x & 31;
-    const uint32_t lt = (1u << lane) - 1u;
-    const int N = A.n;
-    const uint32_t hi = ~((1u << N) - 1u);                       // bits >= N
-    const int dbias = 32 - N;
-    const unsigned long long n_found = *A.n_records;
-    const unsigned long long n_rec = n_found < A.record_cap ? n_found : A.record_cap;   // overflow: the host grows the list and reruns
-    const uint32_t fbase = (uint32_t)__cvta_generic_to_shared(frames + threadIdx.x);
-    constexpr uint32_t kLevelBytes = kQueensBlock * sizeof(uint4);
-    unsigned long long tot_nodes = 0, tot_sols = 0;
-
-    // per-lane search state
-    uint32_t a = 0xFFFFFFFFu, l = 0, r = 0, cand = 0, key = 0;
-    uint32_t nodes = 0, sols = 0;
-    uint32_t sp = fbase;                                         // shared-memory address of the next free frame
-    bool have = false, item_found = false;
-    uint32_t fb = fbase;                                         // bottom of this lane's stack (rises when a frame is given away)
-    // warp-uniform work-distribution state
-    unsigned long long chunk_pos = 0, chunk_end = 0;
-    bool exhausted = false;
-    const unsigned long long total_warps = (unsigned long long)gridDim.x * (kQueensBlock / 32);
-    // fewer records than lanes: a warp takes no more than its share, its other lanes get work from their mates
-    const uint32_t fair_share = (uint32_t)min((n_rec + total_warps - 1) / total_warps, 32ull);
-
-    for (;;) {
-        // ---- refill: lanes without a subtree take the next records ----
-        // The warp owns a chunk [chunk_pos, chunk_end) of the record list and hands it out lane by lane;
-        // an empty chunk is refilled with ONE atomic whose size follows guided self-scheduling
-        // (remaining / (4 * warps), at most 256), so the shared cursor sees thousands of atomics instead
-        // of one per record while the tail stays balanced.
-        const uint32_t need = __ballot_sync(0xFFFFFFFFu, !have);
-        if (need) {
-            const uint32_t n_need = __popc(need);
-            if (chunk_pos >= chunk_end && !exhausted) {
-                unsigned long long base = 0;
-                uint32_t size = 0;
-                if (lane == 0) {
-                    const unsigned long long cur = *(volatile unsigned long long*)A.cursor;
-                    const unsigned long long remaining = cur < n_rec ? n_rec - cur : 0;
-                    size = (uint32_t)min(max(remaining / (4ull * total_warps), (unsigned long long)min(n_need, fair_share)), 256ull);
-                    base = atomicAdd(A.cursor, (unsigned long long)size);
-                }
-                base = __shfl_sync(0xFFFFFFFFu, base, 0);
-                size = __shfl_sync(0xFFFFFFFFu, size, 0);
-                chunk_pos = base;
-                chunk_end = min(base + size, n_rec);
-                if (base >= n_rec) { exhausted = true; chunk_end = chunk_pos; }
-            }
-            const unsigned long long avail = chunk_end - chunk_pos;
-            if (!have) {
-                const uint32_t rank = __popc(need & lt);
-                if (rank < avail) {
-                    const uint4 rec = __ldg(A.records + chunk_pos + rank);
-                    key = rec.x; a = rec.y | hi; l = rec.z; r = rec.w;
-                    item_found = false;
-                    if (nodes >= 0x40000000u) { tot_nodes += nodes; tot_sols += sols; nodes = 0; sols = 0; }   // 32-bit running counts, flushed rarely
-                    have = true;
-                    sp = fbase; fb = fbase;
-                    cand = ~(a | l | r);
-                }
-            }
-            chunk_pos += min((unsigned long long)n_need, avail);
-            if (exhausted) {
-                // The record list is empty.  Lanes that are still idle take work from lanes of their own warp: the
-                // BOTTOM frame of a busy lane's stack is the largest subtree it has not started (untried values of its
-                // shallowest open level).  The warp runs in lockstep, so the hand-over needs no locking: the donor
-                // raises its stack bottom, the taker reads the frame out of the donor's shared-memory column.
-                const uint32_t idle = __ballot_sync(0xFFFFFFFFu, !have);
-                const uint32_t donors = __ballot_sync(0xFFFFFFFFu, have && sp != fb);
-                if (idle == 0xFFFFFFFFu) break;                      // nobody has anything left
-                if (idle && donors) {
-                    __syncwarp();                                    // the donors' frame stores are visible to the takers
-                    const int n_pairs = min(__popc(idle), __popc(donors));
-                    const int my_idle_rank = __popc(idle & lt), my_donor_rank = __popc(donors & lt);
-                    const bool take = !have && my_idle_rank < n_pairs;
-                    const bool give = have && sp != fb && my_donor_rank < n_pairs;
-                    const int partner = take ? (int)__fns(donors, 0, my_idle_rank + 1) : lane;
-                    const uint32_t p_fb = __shfl_sync(0xFFFFFFFFu, fb, partner);
-                    const uint32_t p_key = __shfl_sync(0xFFFFFFFFu, key, partner);
-                    if (take) {
-                        const uint4 f = lds128(p_fb);
-                        a = f.x; l = f.y; r = f.z; cand = f.w;
-                        key = p_key; item_found = false;
-                        have = true;
-                        sp = fbase; fb = fbase;
-                    }
-                    if (give) fb += kLevelBytes;
-                    __syncwarp();
-                }
-            }
-        }
-
-        // ---- every value tried at this depth: return to the nearest level with untried values ----
-        if (have && cand == 0) {
-            if (sp == fb) {
-                have = false;                                  // subtree exhausted (dequan.h:569-570 at the split depth)
-            } else {
-                sp -= kLevelBytes;
-                const uint4 f = lds128(sp);
-                a = f.x; l = f.y; r = f.z; cand = f.w;
-            }
-        }
-
-        // ---- AssignVar(next value) + forward check, all lanes converged ----
-        const bool trying = have && cand != 0;
-        const uint32_t bit = cand & (0u - cand);
-        const uint32_t na = a | bit, nl = (l | bit) << 1, nr = (r | bit) >> 1;
-        const int last = N - 2 + dbias - __popc(a);              // later variables to check, minus one (d = popc(a) - dbias)
-        const int tmax = __reduce_max_sync(0xFFFFFFFFu, trying ? last : 0);
-        uint32_t occ_max = 0;                                    // max over rows of the occupied mask; all ones <=> an empty domain
-        uint32_t j = (uint32_t)last;
-#pragma unroll 4
-        for (int t = 0; t <= tmax; t++) {
-            occ_max = max(occ_max, na | shl_clamp(nl, j) | shr_clamp(nr, j));
-            --j;
-        }
-        if (trying) {
-            cand ^= bit;
-            ++nodes;
-            if (occ_max != 0xFFFFFFFFu) {
-                if (last == 0) {
-                    // the child is the last variable: its whole domain is nodes, each one a solution
-                    const int pc = __popc(~(na | nl | nr));
-                    nodes += pc;
-                    sols += pc;
-                    if (!item_found) {
-                        item_found = true;
-                        if ((unsigned long long)key < *(volatile unsigned long long*)A.best_key) atomicMin(A.best_key, (unsigned long long)key);
-                    }
-                } else {
-                    if (cand) { sts128(sp, a, l, r, cand); sp += kLevelBytes; }
-                    a = na; l = nl; r = nr;
-                    cand = ~(a | l | r);
-                }
-            }
-        }
-    }
-    // warp-reduce the per-lane totals, one atomic pair per warp
-    tot_nodes += nodes; tot_sols += sols;
-    for (int o = 16; o > 0; o >>= 1) {
-        tot_nodes += __shfl_down_sync(0xFFFFFFFFu, tot_nodes, o);
-        tot_sols += __shfl_down_sync(0xFFFFFFFFu, tot_sols, o);
-    }
-    if (lane == 0) {
-        atomicAdd(A.totals + 0, tot_sols);
-        atomicAdd(A.dfs_nodes, tot_nodes);
-    }
-}
-
-// Phase C: the DFS-first solution lives in the lowest-keyed item that holds any solution; one lane
-// walks that item in value order until its first solution (ForwardCheckingStep's own order).
-__global__ void k_queens_first(QueensLaneArgs A) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    const unsigned long long best = *A.best_key;
-    if (best == 0xFFFFFFFFFFFFFFFFull) return;
-    const int N = A.n, K = A.k;
-    const uint32_t full = (1u << N) - 1u;
-    uint32_t sa[32], sl[32], sr[32], sc[32];
-    uint8_t* out = A.first_out;
-    uint32_t a = 0, l = 0, r = 0, rem = (uint32_t)best;
-    for (int t = K - 1; t >= 0; t--) {
-        const uint32_t q = rem / (uint32_t)N;
-        out[t] = (uint8_t)(rem - q * N);
-        rem = q;
-    }
-    for (int i = 0; i < K; i++) {
-        const uint32_t bit = 1u << out[i];
-        a |= bit; l = (l | bit) << 1; r = (r | bit) >> 1;
-    }
-    int d = K;
-    sa[d] = a; sl[d] = l; sr[d] = r; sc[d] = full & ~(a | l | r);
-    while (d >= K) {
-        if (sc[d] == 0) { --d; continue; }
-        const uint32_t bit = sc[d] & (0u - sc[d]);
-        sc[d] ^= bit;
-        const uint32_t na = sa[d] | bit, nl = (sl[d] | bit) << 1, nr = (sr[d] | bit) >> 1;
-        bool wipe = false;
-        for (int j = 0; j <= N - 2 - d; j++) wipe |= ((na | ~full) | (nl << j) | (nr >> j)) == 0xFFFFFFFFu;
-        if (wipe) continue;
-        out[d] = (uint8_t)(__ffs(bit) - 1);
-        if (d == N - 2) { out[N - 1] = (uint8_t)(__ffs(full & ~(na | nl | nr)) - 1); return; }
-        ++d;
-        sa[d] = na; sl[d] = nl; sr[d] = nr; sc[d] = full & ~(na | nl | nr);
-    }
-}
-
-
 // ---------------------------------------------------------------------------------------------------------------
-// Depth-bucketed warp search (COUNT_ALL).  The lane-per-subtree kernel above pays for SIMT twice: its forward-check
-// loop runs to the row count of the SHALLOWEST lane of the warp (about 9 rows per trip when a node needs 4.3 on
-// average, N=17), and lanes idle while their mates finish a subtree.  Here a warp owns a pool of open frames
+// Depth-bucketed warp search (COUNT_ALL).  A lane-per-subtree search (round 1's first engine: explicit stack per lane;
+// profiles/r1_ncu_queens17_lane_old.txt) pays for SIMT twice: its forward-check loop runs to the row count of the
+// SHALLOWEST lane of the warp (about 9 rows per trip when a node needs 4.3 on average, N=17), and lanes idle while
+// their mates finish a subtree.  Here a warp owns a pool of open frames
 // {a, l, r, untried} in shared memory, bucketed by depth, and every trip takes up to 64 frames of ONE depth, two per
 // lane:
 //   * the row count of the forward check is warp-uniform and exact (no max over lanes, uniform shift amounts);
@@ -445,6 +244,7 @@ __global__ void k_queens_first(QueensLaneArgs A) {
 // queens_first_owned.  Bucket sizes live in registers, lane i holding the size of bucket i.
 constexpr int kQueensBucketMaxWarps = 6;              // warps per CTA: the host picks what packs an SM's shared memory best
 constexpr int kQueensBucketCap = 128;
+constexpr int kQueensStageBytes = 64 * 16 + 16;       // per warp: 64 frontier records in flight (bulk copy) + their mbarrier
 
 // DFS-first solution of the part of the tree this partition owns, and the depth-k key of its prefix
 // (ForwardCheckingStep's own order, dequan.h:494-571).  Run by one warp in a kernel of its own, on a second stream
@@ -508,7 +308,14 @@ k_queens_bucket(QueensLaneArgs A) {
     const int N = A.n;
     const int L = N - 1 - A.k;                                   // buckets: depth k .. N-2
     const uint32_t hi = ~((1u << N) - 1u);
-    const uint32_t bbase = (uint32_t)__cvta_generic_to_shared(qb_frames + (size_t)wib * L * kQueensBucketCap);
+    const uint32_t per_warp = (uint32_t)L * kQueensBucketCap * 16u + kQueensStageBytes;
+    const uint32_t bbase = (uint32_t)__cvta_generic_to_shared(qb_frames) + (uint32_t)wib * per_warp;
+    // the frontier records reach the pools through a 1 KB staging buffer filled by bulk copies (cp.async.bulk +
+    // mbarrier): the next 64 records are in flight while the warp works through the ones it has
+    const uint32_t stage = bbase + (uint32_t)L * kQueensBucketCap * 16u, mbar = stage + 64u * 16u;
+    if (lane == 0) { mbar_init(mbar, 1); mbar_init_fence(); }
+    __syncwarp();
+    uint32_t pf_n = 0, pf_parity = 0;                            // records in the staging buffer (or on their way); mbarrier phase
     const unsigned long long n_found = *A.n_records;
     const unsigned long long n_rec = n_found < A.record_cap ? n_found : A.record_cap;   // overflow: the host grows the list and reruns
     const unsigned long long total_warps = (unsigned long long)gridDim.x * (blockDim.x >> 5);
@@ -526,7 +333,9 @@ k_queens_bucket(QueensLaneArgs A) {
         int lvl;
         if (big) lvl = 31 - __clz((int)big);
         else {
-            if (!exhausted) {
+            // claims the next chunk of the record list if need be and starts the bulk copy of up to 64 records of it
+            auto prefetch = [&]() {
+                if (exhausted) return;
                 if (chunk_pos >= chunk_end) {
                     unsigned long long base = 0;
                     uint32_t size = 0;
@@ -540,24 +349,33 @@ k_queens_bucket(QueensLaneArgs A) {
                     size = __shfl_sync(0xFFFFFFFFu, size, 0);
                     chunk_pos = base;
                     chunk_end = min(base + size, n_rec);
-                    if (base >= n_rec) { exhausted = true; chunk_end = chunk_pos; }
+                    if (base >= n_rec) { exhausted = true; chunk_end = chunk_pos; return; }
                 }
-                if (!exhausted) {
-                    const uint32_t c0 = __shfl_sync(0xFFFFFFFFu, cnt, 0);
-                    const uint32_t n_take = (uint32_t)min(chunk_end - chunk_pos, 64ull);
+                pf_n = (uint32_t)min(chunk_end - chunk_pos, 64ull);
+                if (lane == 0) {
+                    mbar_expect_tx(mbar, pf_n * 16u);
+                    bulk_g2s(stage, A.records + chunk_pos, pf_n * 16u, mbar);
+                }
+                chunk_pos += pf_n;
+            };
+            if (pf_n == 0u) prefetch();
+            if (pf_n != 0u) {
+                mbar_wait(mbar, pf_parity);
+                pf_parity ^= 1u;
+                const uint32_t c0 = __shfl_sync(0xFFFFFFFFu, cnt, 0);
 #pragma unroll
-                    for (int h = 0; h < 2; h++)
-                        if ((uint32_t)lane + 32u * h < n_take) {
-                            const uint4 rec = __ldg(A.records + chunk_pos + lane + 32 * h);
-                            const uint32_t a = rec.y | hi;
-                            sts128(bbase + ((c0 + lane + 32 * h) << 4), a, rec.z, rec.w, ~(a | rec.z | rec.w));
-                        }
-                    if (lane == 0) cnt = c0 + n_take;
-                    chunk_pos += n_take;
-                    if (nodes >= 0x40000000u) { tot_nodes += nodes; tot_sols += sols; nodes = 0; sols = 0; }
-                    __syncwarp();
-                    continue;
-                }
+                for (int h = 0; h < 2; h++)
+                    if ((uint32_t)lane + 32u * h < pf_n) {
+                        const uint4 rec = lds128(stage + (((uint32_t)lane + 32u * h) << 4));
+                        const uint32_t a = rec.y | hi;
+                        sts128(bbase + ((c0 + lane + 32 * h) << 4), a, rec.z, rec.w, ~(a | rec.z | rec.w));
+                    }
+                if (lane == 0) cnt = c0 + pf_n;
+                pf_n = 0;
+                if (nodes >= 0x40000000u) { tot_nodes += nodes; tot_sols += sols; nodes = 0; sols = 0; }
+                __syncwarp();                                    // the staging buffer is free again
+                prefetch();
+                continue;
             }
             const uint32_t any = __ballot_sync(0xFFFFFFFFu, cnt != 0u);
             if (!any) break;

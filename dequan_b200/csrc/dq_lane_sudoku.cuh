@@ -45,6 +45,7 @@
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
+#include "dq_group_graphs.cuh"     // bulk-copy / mbarrier primitives
 
 namespace dq {
 
@@ -117,79 +118,119 @@ struct SudokuArgs {
 };
 
 // ---------------------------------------------------------------------------------------------
-// Pass 0: one thread per instance, inputs staged through shared memory so that HBM reads coalesce.
-__global__ void __launch_bounds__(128)
+// Pass 0: one thread per instance, persistent CTAs over tiles of 128 instances.  The 81-byte cell rows of a tile are
+// one contiguous 10 368-byte span: a single bulk copy (cp.async.bulk + mbarrier) brings it into shared memory while
+// the previous tile is being digested (two staging buffers); the 128 finished 288-byte records are assembled in shared
+// memory and leave with one 36 864-byte bulk store.  (A ragged last tile, a stride other than 81 or a misaligned
+// batch go through plain loads and stores.)
+constexpr int kDigestTile = 128;
+constexpr int kDigestInBytes = kDigestTile * 81;                 // 16 x 648
+constexpr int kDigestOutBytes = kDigestTile * kDigestVec * 16;   // 36 864
+constexpr int kDigestSmem = 2 * kDigestInBytes + kDigestOutBytes + 16;
+
+__global__ void __launch_bounds__(kDigestTile)
 k_sudoku_digest(const uint8_t* __restrict__ cells, long long n, int stride, SudokuDigest* __restrict__ out) {
-    extern __shared__ uint8_t stage[];                       // [128][81]
-    const long long first = (long long)blockIdx.x * 128;
-    const int here = (int)min((long long)128, n - first);
-    if (stride == 81) {
-        const uint8_t* src = cells + first * 81;
-        for (int i = threadIdx.x; i < here * 81; i += 128) stage[i] = src[i];
-    } else {
-        for (int i = threadIdx.x; i < here * 81; i += 128) stage[i] = cells[(first + i / 81) * stride + i % 81];
-    }
+    extern __shared__ __align__(128) uint8_t dg_raw[];           // in[2][10368] | records[128][288] | two mbarriers
+    uint8_t* recs = dg_raw + 2 * kDigestInBytes;
+    const uint32_t in_s = smem_u32(dg_raw), recs_s = smem_u32(recs), mbar = recs_s + kDigestOutBytes;
+    const long long tiles = (n + kDigestTile - 1) / kDigestTile;
+    const bool bulk_ok = stride == 81 && ((size_t)cells & 15) == 0 && ((size_t)out & 15) == 0;
+    if (threadIdx.x == 0) { mbar_init(mbar, 1); mbar_init(mbar + 8, 1); mbar_init_fence(); }
     __syncthreads();
-    if ((int)threadIdx.x >= here) return;
-    const uint8_t* g = stage + threadIdx.x * 81;
-    uint32_t row[9], col[9], box[9], blank[3] = {0, 0, 0};
-#pragma unroll
-    for (int i = 0; i < 9; i++) { row[i] = 0; col[i] = 0; box[i] = 0; }
-    bool defer = false;
-#pragma unroll
-    for (int r = 0; r < 9; r++)
-#pragma unroll
-        for (int c = 0; c < 9; c++) {
-            const int p = r * 9 + c;
-            const uint32_t v = g[p];
-            if (v == 0) { blank[p >> 5] |= 1u << (p & 31); continue; }
-            if (v > 9) { defer = true; continue; }           // not a value of the template domain
-            const uint32_t bit = 1u << (v - 1);
-            const int b = (r / 3) * 3 + c / 3;
-            if ((row[r] | col[c] | box[b]) & bit) defer = true;   // two givens clash: the exact node count is the generic engine's job
-            row[r] |= bit; col[c] |= bit; box[b] |= bit;
+    auto full = [&](long long t) { return bulk_ok && (t + 1) * kDigestTile <= n; };
+    auto issue = [&](long long t, int b) {                       // (thread 0) the whole tile in one copy
+        mbar_expect_tx(mbar + 8 * b, kDigestInBytes);
+        bulk_g2s(in_s + b * kDigestInBytes, cells + t * kDigestInBytes, kDigestInBytes, mbar + 8 * b);
+    };
+    uint32_t parity = 0;
+    int b = 0;
+    long long t = blockIdx.x;
+    if (t < tiles && full(t) && threadIdx.x == 0) issue(t, 0);
+    bool store_in_flight = false;
+    for (; t < tiles; t += gridDim.x, b ^= 1) {
+        const long long nxt = t + gridDim.x;
+        if (nxt < tiles && full(nxt) && threadIdx.x == 0) issue(nxt, b ^ 1);
+        const long long first = t * kDigestTile;
+        const int here = (int)min((long long)kDigestTile, n - first);
+        uint8_t* stage = dg_raw + b * kDigestInBytes;
+        if (full(t)) { mbar_wait(mbar + 8 * b, (parity >> b) & 1u); parity ^= 1u << b; }
+        else {
+            for (int i = threadIdx.x; i < here * 81; i += kDigestTile) stage[i] = cells[(first + i / 81) * stride + i % 81];
+            __syncthreads();
         }
-    uint32_t w[kDigestVec * 4];
-#pragma unroll
-    for (int i = 0; i < kDigestVec * 4; i++) w[i] = 0;
-    int level = 0;
-#pragma unroll
-    for (int r = 0; r < 9; r++)
-#pragma unroll
-        for (int c = 0; c < 9; c++) {
-            const int p = r * 9 + c;
-            if (!((blank[p >> 5] >> (p & 31)) & 1u)) continue;
-            if ((row[r] | col[c] | box[(r / 3) * 3 + c / 3]) == 0x1FFu) defer = true;  // a blank wiped out by the givens
-            w[19 + r * 3 + c / 3] |= 0x1FFu << (10 * (c % 3));
-            w[67 + (c * 9 + r) / 32] |= 1u << ((c * 9 + r) % 32);
-            ++level;
+        if (store_in_flight) {                                   // the previous tile's records have left shared memory
+            if (threadIdx.x == 0) bulk_wait_read0();
+            __syncthreads();
+            store_in_flight = false;
         }
-    // cell id of every search level, one byte per level: the L-th blank cell is the L-th set bit of the blank bitmap
-    // (all indices static: the table stays in registers — the level-indexed store this replaces put it in local memory
-    // and doubled the pass's DRAM writes)
-    {
-        const int c0 = __popc(blank[0]), c1 = c0 + __popc(blank[1]);
+        if ((int)threadIdx.x < here) {
+            const uint8_t* g = stage + threadIdx.x * 81;
+            uint32_t row[9], col[9], box[9], blank[3] = {0, 0, 0};
 #pragma unroll
-        for (int L = 0; L < 81; L++) {
-            uint32_t p = 0;
-            if (L < c0) p = __fns(blank[0], 0, L + 1);
-            else if (L < c1) p = 32u + __fns(blank[1], 0, L - c0 + 1);
-            else if (L < level) p = 64u + __fns(blank[2], 0, L - c1 + 1);
-            w[46 + (L >> 2)] |= p << ((L & 3) * 8);
+            for (int i = 0; i < 9; i++) { row[i] = 0; col[i] = 0; box[i] = 0; }
+            bool defer = false;
+#pragma unroll
+            for (int r = 0; r < 9; r++)
+#pragma unroll
+                for (int c = 0; c < 9; c++) {
+                    const int p = r * 9 + c;
+                    const uint32_t v = g[p];
+                    if (v == 0) { blank[p >> 5] |= 1u << (p & 31); continue; }
+                    if (v > 9) { defer = true; continue; }           // not a value of the template domain
+                    const uint32_t bit = 1u << (v - 1);
+                    const int bx = (r / 3) * 3 + c / 3;
+                    if ((row[r] | col[c] | box[bx]) & bit) defer = true;   // two givens clash: the exact node count is the generic engine's job
+                    row[r] |= bit; col[c] |= bit; box[bx] |= bit;
+                }
+            uint32_t w[kDigestVec * 4];
+#pragma unroll
+            for (int i = 0; i < kDigestVec * 4; i++) w[i] = 0;
+            int level = 0;
+#pragma unroll
+            for (int r = 0; r < 9; r++)
+#pragma unroll
+                for (int c = 0; c < 9; c++) {
+                    const int p = r * 9 + c;
+                    if (!((blank[p >> 5] >> (p & 31)) & 1u)) continue;
+                    if ((row[r] | col[c] | box[(r / 3) * 3 + c / 3]) == 0x1FFu) defer = true;  // a blank wiped out by the givens
+                    w[19 + r * 3 + c / 3] |= 0x1FFu << (10 * (c % 3));
+                    w[67 + (c * 9 + r) / 32] |= 1u << ((c * 9 + r) % 32);
+                    ++level;
+                }
+            w[0] = blank[0]; w[1] = blank[1]; w[2] = blank[2];
+            w[3] = (uint32_t)level | (defer ? 0x80000000u : 0u);
+#pragma unroll
+            for (int i = 0; i < 9; i++) w[10 + i] = box[i] * SK_ONES;
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                w[4 + i] = row[3 * i] | (row[3 * i + 1] << 10) | (row[3 * i + 2] << 20);
+                w[7 + i] = col[3 * i] | (col[3 * i + 1] << 10) | (col[3 * i + 2] << 20);
+            }
+            uint32_t* rw = reinterpret_cast<uint32_t*>(recs + threadIdx.x * (kDigestVec * 16));
+#pragma unroll
+            for (int i = 0; i < kDigestVec * 4; i++) rw[i] = w[i];           // (w[46..66] are zero here)
+            // cell id of every search level, one byte per level: the set bits of the blank bitmap in ascending order,
+            // written straight into the record (the 81 x __fns of the all-register version were most of this pass)
+            uint8_t* tab = recs + threadIdx.x * (kDigestVec * 16) + 46 * 4;
+            int L = 0;
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+                for (uint32_t bits = blank[k]; bits; bits &= bits - 1u) tab[L++] = (uint8_t)(32 * k + __ffs((int)bits) - 1);
+        }
+        if (full(t)) {
+            fence_async_smem();
+            __syncthreads();
+            if (threadIdx.x == 0) { bulk_s2g(out + first, recs_s, kDigestOutBytes); bulk_commit(); }
+            store_in_flight = true;
+        } else {
+            __syncthreads();
+            const uint4* src = reinterpret_cast<const uint4*>(recs);
+            uint4* dst = reinterpret_cast<uint4*>(out + first);
+            for (int i = threadIdx.x; i < here * kDigestVec; i += kDigestTile) dst[i] = src[i];
+            __syncthreads();
         }
     }
-    w[0] = blank[0]; w[1] = blank[1]; w[2] = blank[2];
-    w[3] = (uint32_t)level | (defer ? 0x80000000u : 0u);
-#pragma unroll
-    for (int i = 0; i < 9; i++) w[10 + i] = box[i] * SK_ONES;
-#pragma unroll
-    for (int i = 0; i < 3; i++) {
-        w[4 + i] = row[3 * i] | (row[3 * i + 1] << 10) | (row[3 * i + 2] << 20);
-        w[7 + i] = col[3 * i] | (col[3 * i + 1] << 10) | (col[3 * i + 2] << 20);
-    }
-    uint4* o = reinterpret_cast<uint4*>(out + first + threadIdx.x);
-#pragma unroll
-    for (int i = 0; i < kDigestVec; i++) o[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+    if (store_in_flight && threadIdx.x == 0) bulk_wait_read0();
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -587,7 +587,7 @@ private:
     bool CompileB200(const Assignment& a) const;
     void Flatten(const Assignment& a, b200::Lowering& low, std::vector<int32_t>& dom_type, std::vector<int32_t>& dom_off,
                  std::vector<int32_t>& dom_vals) const;
-    void TabulateUserConstraint(size_t c, b200::Lowering& low) const;
+    void TabulateUserConstraint(size_t c, b200::Lowering& low, const Assignment& a) const;
 
     std::vector<std::vector<VarId>> scopes_;        // per constraint: the variables LinkVars attached it to
     mutable b200::ModelCache cache_;
@@ -607,10 +607,14 @@ inline void Assignment::Reset(const CSP& csp) {
     std::stable_sort(assign_order.begin(), assign_order.end(), [&size](VarId x, VarId y) { return size[x] < size[y]; });
 }
 
-/* A user-defined constraint becomes a DQ_CON_TABLE row: the (v0,v1) value pairs its Evaluate does
- * not reject.  Requirements, each checked: exactly two variables in scope; Evaluate does not fail
- * with only one of them assigned; AplyArcConsistency leaves the domains alone (check-only). */
-inline void CSP::TabulateUserConstraint(size_t c, b200::Lowering& low) const {
+/* A user-defined constraint becomes a DQ_CON_TABLE row — the (v0,v1) value pairs its Evaluate does not reject — or,
+ * when it overrides AplyArcConsistency (reference dequan.h:145-147) with a step that filters the other endpoint's
+ * domain, a DQ_CON_FILTER row that adds, per direction, the value pairs the filter keeps.  Requirements, each checked
+ * on the Assignment's current domains: exactly two variables in scope; Evaluate does not fail with only one of them
+ * assigned; the filter touches only the unassigned endpoint of the pair, answers false exactly when it leaves that
+ * domain empty (what ForwardCheckingStep takes for a wipe-out, dequan.h:514-518), and removes a value whatever
+ * else the domain holds (it is run on the full domain and on every other value of it: the answers must agree). */
+inline void CSP::TabulateUserConstraint(size_t c, b200::Lowering& low, const Assignment& a) const {
     const std::vector<VarId>& scope = scopes_[c];
     if (scope.size() != 2)
         throw b200::Error(DQ_ERR_UNSUPPORTED, "constraint #" + std::to_string(c) + " links " + std::to_string(scope.size()) +
@@ -625,46 +629,89 @@ inline void CSP::TabulateUserConstraint(size_t c, b200::Lowering& low) const {
                 for (int v = d.values[i]; v < d.values[i + 1]; v++) out.push_back(v);
         return out;
     };
-    const Array<int> xs = expand(domains[x]), ys = expand(domains[y]);
+    const Array<int> xs = expand(a.current_domains[x]), ys = expand(a.current_domains[y]);
     Array<InstVar> iv(vars.size());
-    std::vector<int32_t> row{x, y};
-    for (int a : xs) {
-        iv[x].value = a;
+    std::vector<int32_t> allow;
+    for (int av : xs) {
+        iv[x].value = av;
         if (con->Evaluate(iv, x) == Constraint::Eval::Failed)
             throw b200::Error(DQ_ERR_UNSUPPORTED, "user constraint fails with a single variable assigned (unary part)");
-        for (int b : ys) {
-            iv[y].value = b;
+        for (int bv : ys) {
+            iv[y].value = bv;
             if (con->Evaluate(iv, y) != Constraint::Eval::Failed && con->Evaluate(iv, x) != Constraint::Eval::Failed) {
-                row.push_back(a);
-                row.push_back(b);
+                allow.push_back(av);
+                allow.push_back(bv);
             }
         }
         iv[y].value = InstVar::UNASSIGNED;
     }
     iv[x].value = InstVar::UNASSIGNED;
-    for (int b : ys) {
-        iv[y].value = b;
+    for (int bv : ys) {
+        iv[y].value = bv;
         if (con->Evaluate(iv, y) == Constraint::Eval::Failed)
             throw b200::Error(DQ_ERR_UNSUPPORTED, "user constraint fails with a single variable assigned (unary part)");
     }
-    // check-only? run its filter once per value of either endpoint on a scratch state
-    Assignment scratch;
-    scratch.Reset(*this);
-    scratch.saved_domains.emplace_back();
+    // its AplyArcConsistency, once per value of either endpoint on a scratch state
+    std::vector<int32_t> keep[2];
+    bool filters = false;
     for (int side = 0; side < 2; side++) {
-        const VarId from = side ? y : x;
-        for (int v : (side ? ys : xs)) {
-            scratch.inst_vars[from].value = v;
-            scratch.assigned_var_count = 1;
-            const bool ok = con->AplyArcConsistency(scratch, from);
-            if (!ok || scratch.current_domains[x] != domains[x] || scratch.current_domains[y] != domains[y])
-                throw b200::Error(DQ_ERR_UNSUPPORTED, "user constraint overrides AplyArcConsistency with a filtering step; only "
-                                                      "check-only user constraints are lowered");
-            scratch.saved_domains.back().domains.clear();
+        const VarId from = side ? y : x, to = side ? x : y;
+        const Array<int>& from_vals = side ? ys : xs;
+        const Array<int>& to_vals = side ? xs : ys;
+        for (int v : from_vals) {
+            std::vector<char> kept_full(to_vals.size(), 0);
+            for (int pass = 0; pass < 3; pass++) {               // the full domain, then its even / odd positions only
+                Assignment scratch;
+                scratch.inst_vars.assign(vars.size(), InstVar());
+                scratch.current_domains = a.current_domains;
+                scratch.assign_order = a.assign_order;
+                scratch.saved_domains.emplace_back();
+                if (pass) {
+                    Array<int> sub;
+                    for (size_t i = 0; i < to_vals.size(); i++) if ((int)(i & 1) == pass - 1) sub.push_back(to_vals[i]);
+                    scratch.current_domains[to] = Domain(DomainType::Values, sub);
+                }
+                const Array<Domain> before = scratch.current_domains;
+                scratch.inst_vars[from].value = v;
+                scratch.assigned_var_count = 1;
+                const bool ok = con->AplyArcConsistency(scratch, from);
+                for (size_t u = 0; u < vars.size(); u++)
+                    if ((VarId)u != to && scratch.current_domains[u] != before[u])
+                        throw b200::Error(DQ_ERR_UNSUPPORTED, "user constraint's AplyArcConsistency changes a domain other than its unassigned endpoint's");
+                const Array<int> left = expand(scratch.current_domains[to]);
+                if (ok == left.empty())
+                    throw b200::Error(DQ_ERR_UNSUPPORTED, "user constraint's AplyArcConsistency must answer false exactly when it empties the domain");
+                if (scratch.current_domains[to] != before[to]) filters = true;
+                for (size_t i = 0; i < to_vals.size(); i++) {
+                    const bool in_start = pass == 0 || (int)(i & 1) == pass - 1;
+                    if (!in_start) continue;
+                    const bool kept = std::find(left.begin(), left.end(), to_vals[i]) != left.end();
+                    if (pass == 0) kept_full[i] = kept;
+                    else if (kept != (bool)kept_full[i])
+                        throw b200::Error(DQ_ERR_UNSUPPORTED, "user constraint's AplyArcConsistency depends on the other values of the domain it filters");
+                }
+                for (int lv : left)
+                    if (std::find(to_vals.begin(), to_vals.end(), lv) == to_vals.end())
+                        throw b200::Error(DQ_ERR_UNSUPPORTED, "user constraint's AplyArcConsistency adds values to a domain");
+            }
+            for (size_t i = 0; i < to_vals.size(); i++)
+                if (kept_full[i]) {
+                    keep[side].push_back(side ? to_vals[i] : v);          // pairs are (value of scope[0], value of scope[1])
+                    keep[side].push_back(side ? v : to_vals[i]);
+                }
         }
-        scratch.inst_vars[from].value = InstVar::UNASSIGNED;
     }
-    low.Row(DQ_CON_TABLE, row.data(), row.size());
+    if (!filters) {
+        std::vector<int32_t> row{x, y};
+        row.insert(row.end(), allow.begin(), allow.end());
+        low.Row(DQ_CON_TABLE, row.data(), row.size());
+        return;
+    }
+    std::vector<int32_t> row{x, y, (int32_t)(allow.size() / 2), (int32_t)(keep[0].size() / 2), (int32_t)(keep[1].size() / 2)};
+    row.insert(row.end(), allow.begin(), allow.end());
+    row.insert(row.end(), keep[0].begin(), keep[0].end());
+    row.insert(row.end(), keep[1].begin(), keep[1].end());
+    low.Row(DQ_CON_FILTER, row.data(), row.size());
 }
 
 inline void CSP::Flatten(const Assignment& a, b200::Lowering& low, std::vector<int32_t>& dom_type,
@@ -711,7 +758,7 @@ inline void CSP::Flatten(const Assignment& a, b200::Lowering& low, std::vector<i
                     throw b200::Error(DQ_ERR_UNSUPPORTED, "constraint #" + std::to_string(c) + " links " + std::to_string(scope.size()) +
                                                               " variables; the device engine lowers unary-free binary constraints and AllDifferent only");
                 }
-                TabulateUserConstraint(c, low);
+                TabulateUserConstraint(c, low, a);
             }
             continue;
         }

@@ -73,10 +73,17 @@ enum dq_con_kind {
     DQ_CON_EQ      = 1,  /* EqualityConstraint  data = {v0, v1}                  (dequan.h:200-211) */
     DQ_CON_ALLDIFF = 2,  /* AllDifferentConstraint data = {vars...}              (dequan.h:257-268) */
     DQ_CON_ORRANGE = 3,  /* OrRangeConstraint   data = {v0, v1, min, max}        (dequan.h:242-254) */
-    DQ_CON_TABLE   = 4   /* user-defined binary Constraint, tabulated Evaluate:
+    DQ_CON_TABLE   = 4,  /* user-defined binary Constraint, tabulated Evaluate:
                             data = {v0, v1, a0, b0, a1, b1, ...} allowed (v0,v1)
                             value pairs; check-only (default AplyArcConsistency,
                             dequan.h:147)                                         */
+    DQ_CON_FILTER  = 5   /* user-defined binary Constraint that overrides
+                            AplyArcConsistency (dequan.h:145-147), tabulated:
+                            data = {v0, v1, n_allow, n_keep01, n_keep10, then
+                            n_allow pairs Evaluate accepts, n_keep01 pairs (a,b):
+                            assigning v0=a leaves b in v1's domain, n_keep10 pairs
+                            (a,b): assigning v1=b leaves a in v0's domain}; all
+                            pairs are (value of v0, value of v1)                  */
 };
 
 typedef struct dq_model_desc {

@@ -36,6 +36,37 @@ struct GapConstraint : public Constraint {
     int gap;
 };
 
+// A user-defined constraint WITH its own filtering step (AplyArcConsistency, reference dequan.h:145-147): x + gap <= y.
+struct OrderedConstraint : public Constraint {
+    OrderedConstraint(VarId a, VarId b, int g) : x(a), y(b), gap(g) {}
+    virtual void LinkVars(Array<Var>& vars) {
+        vars[x].linked_constraints.push_back(this);
+        vars[y].linked_constraints.push_back(this);
+    }
+    virtual Eval Evaluate(const Array<InstVar>& iv, VarId) {
+        if (iv[x].value == InstVar::UNASSIGNED || iv[y].value == InstVar::UNASSIGNED) return Eval::NA;
+        return iv[x].value + gap <= iv[y].value ? Eval::Passed : Eval::Failed;
+    }
+    virtual bool AplyArcConsistency(Assignment& a, VarId) {
+        const int xv = a.inst_vars[x].value, yv = a.inst_vars[y].value;
+        if (xv != InstVar::UNASSIGNED && yv == InstVar::UNASSIGNED) {
+            Domain& d = a.current_domains[y];
+            a.EnsureSavedDomain(y, d);
+            d.ExcludeInf(xv + gap);
+            return d.Size() > 0;
+        }
+        if (yv != InstVar::UNASSIGNED && xv == InstVar::UNASSIGNED) {
+            Domain& d = a.current_domains[x];
+            a.EnsureSavedDomain(x, d);
+            d.ExcludeSup(yv - gap + 1);
+            return d.Size() > 0;
+        }
+        return true;
+    }
+    VarId x, y;
+    int gap;
+};
+
 static void print_ints(const Array<int>& v) {
     printf("[");
     for (size_t i = 0; i < v.size(); i++) printf("%s%d", i ? "," : "", v[i]);
@@ -297,6 +328,30 @@ static void array_macros() {
     report("array_macros", ok && DEQUAN_Array_Size(vals) == 4 && DEQUAN_Array_Back(vals) == 9, csp, a);
 }
 
+// Filtering user constraints next to built-in ones: a chain v0 + g <= v1 + ... with an all-different on top and a
+// check-only gap constraint; `reverse_domains` lists the Values domains in descending order (iteration order matters).
+static void user_filter(const char* name, int n, int g, bool reverse_domains, int extra_gap) {
+    CSP csp;
+    Array<VarId> v(n);
+    for (int i = 0; i < n; i++) {
+        if (i % 2 == 0) v[i] = csp.AddIntVar(0, n + 3);
+        else {
+            Array<int> vals;
+            for (int k = 0; k < n + 3; k++) vals.push_back(reverse_domains ? n + 2 - k : k);
+            v[i] = csp.AddIntVar(Domain(DomainType::Values, vals));
+        }
+    }
+    for (int i = 0; i + 1 < n; i++) csp.AddConstraint(OrderedConstraint(v[i], v[i + 1], (i % 2) ? g : 1));
+    csp.AddConstraint(AllDifferentConstraint(v));
+    if (extra_gap) csp.AddConstraint(GapConstraint(v[0], v[n - 1], extra_gap));
+    csp.AddConstraint(OpConstraint(v[1], v[n - 2], OpConstraint::Op::NotEqual, -3));
+    csp.FinalizeModel();
+    Assignment a;
+    a.Reset(csp);
+    bool ok = csp.ForwardCheckingStep(a);
+    report(name, ok, csp, a);
+}
+
 static void empty_model() {
     CSP csp;
     csp.FinalizeModel();
@@ -381,5 +436,9 @@ int main(int argc, char** argv) {
     sudoku_resume("resume_sudoku_10_givens", 10);
     sudoku_resume("resume_sudoku_all_givens", 32);
     array_macros();
+    user_filter("user_filter_sat", 5, 2, false, 0);
+    user_filter("user_filter_reversed_domains", 6, 1, true, 4);
+    user_filter("user_filter_unsat", 6, 3, false, 0);
+    user_filter("user_filter_gap", 5, 1, true, 6);
     return 0;
 }

@@ -706,27 +706,6 @@ def test_domains_up_to_64_values(product_lib):
         api.Model(tmpl).solve_batch_cells(np.zeros((2, 4), dtype=np.uint8))
 
 
-def test_previous_queens_engine_still_agrees(product_lib):
-    """DQ_QUEENS_ENGINE=lane selects the earlier lane-per-subtree search (kept for comparison); it is read once per
-    process, hence the subprocess."""
-    import subprocess
-    import sys
-    code = ("import sys; sys.path.insert(0, %r); from dequan_b200 import api; from dequan_b200.model import nqueens\n"
-            "for n in (6, 10, 13):\n"
-            "    r = api.Model(nqueens(n)).solve_tree('count'); print(n, r.solutions, r.nodes, r.first, r.engine, r.launches)\n"
-            % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-    outs = []
-    for env_engine in ("lane", "bucket"):
-        env = dict(os.environ, DQ_QUEENS_ENGINE=env_engine)
-        outs.append(subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, check=True, timeout=300).stdout.splitlines())
-    for a, b in zip(*outs):
-        assert a.split()[:-1] == b.split()[:-1], (a, b)          # same counts, nodes, first solution, engine name
-    for line in outs[1]:
-        n = int(line.split()[0])
-        g = O.solve(nqueens(n), "count")
-        assert line.startswith(f"{n} {g.solutions} {g.nodes} {g.first}"), line
-
-
 def test_queens_graph_replay_and_recapture(product_lib):
     """The N-Queens solve queue is replayed as a CUDA graph from the second identical solve on; a change of split depth
     or partition re-captures it.  Every call returns the same exact counts."""
