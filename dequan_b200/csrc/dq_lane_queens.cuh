@@ -244,7 +244,7 @@ __device__ __forceinline__ uint32_t shr_clamp(uint32_t x, uint32_t n) { uint32_t
 // queens_first_owned.  Bucket sizes live in registers, lane i holding the size of bucket i.
 constexpr int kQueensBucketMaxWarps = 6;              // warps per CTA: the host picks what packs an SM's shared memory best
 constexpr int kQueensBucketCap = 128;
-constexpr int kQueensStageBytes = 64 * 16 + 16;       // per warp: 64 frontier records in flight (bulk copy) + their mbarrier
+constexpr int kQueensStageBytes = 0;                  // (the pools fill an SM's shared memory to the byte at 17 queens: see the refill)
 
 // DFS-first solution of the part of the tree this partition owns, and the depth-k key of its prefix
 // (ForwardCheckingStep's own order, dequan.h:494-571).  Run by one warp in a kernel of its own, on a second stream
@@ -310,12 +310,8 @@ k_queens_bucket(QueensLaneArgs A) {
     const uint32_t hi = ~((1u << N) - 1u);
     const uint32_t per_warp = (uint32_t)L * kQueensBucketCap * 16u + kQueensStageBytes;
     const uint32_t bbase = (uint32_t)__cvta_generic_to_shared(qb_frames) + (uint32_t)wib * per_warp;
-    // the frontier records reach the pools through a 1 KB staging buffer filled by bulk copies (cp.async.bulk +
-    // mbarrier): the next 64 records are in flight while the warp works through the ones it has
-    const uint32_t stage = bbase + (uint32_t)L * kQueensBucketCap * 16u, mbar = stage + 64u * 16u;
-    if (lane == 0) { mbar_init(mbar, 1); mbar_init_fence(); }
-    __syncwarp();
-    uint32_t pf_n = 0, pf_parity = 0;                            // records in the staging buffer (or on their way); mbarrier phase
+    uint32_t pf_n = 0;                                           // records prefetched into pf0 / pf1 (in flight or landed)
+    uint4 pf0 = make_uint4(0u, 0u, 0u, 0u), pf1 = pf0;
     const unsigned long long n_found = *A.n_records;
     const unsigned long long n_rec = n_found < A.record_cap ? n_found : A.record_cap;   // overflow: the host grows the list and reruns
     const unsigned long long total_warps = (unsigned long long)gridDim.x * (blockDim.x >> 5);
@@ -333,7 +329,8 @@ k_queens_bucket(QueensLaneArgs A) {
         int lvl;
         if (big) lvl = 31 - __clz((int)big);
         else {
-            // claims the next chunk of the record list if need be and starts the bulk copy of up to 64 records of it
+            // claims the next chunk of the record list if need be and starts the loads of up to 64 records of it: they
+            // stay in flight (two uint4 registers per lane) while the warp works through the records it has
             auto prefetch = [&]() {
                 if (exhausted) return;
                 if (chunk_pos >= chunk_end) {
@@ -352,28 +349,19 @@ k_queens_bucket(QueensLaneArgs A) {
                     if (base >= n_rec) { exhausted = true; chunk_end = chunk_pos; return; }
                 }
                 pf_n = (uint32_t)min(chunk_end - chunk_pos, 64ull);
-                if (lane == 0) {
-                    mbar_expect_tx(mbar, pf_n * 16u);
-                    bulk_g2s(stage, A.records + chunk_pos, pf_n * 16u, mbar);
-                }
+                if ((uint32_t)lane < pf_n) pf0 = __ldg(A.records + chunk_pos + lane);
+                if ((uint32_t)lane + 32u < pf_n) pf1 = __ldg(A.records + chunk_pos + lane + 32);
                 chunk_pos += pf_n;
             };
             if (pf_n == 0u) prefetch();
             if (pf_n != 0u) {
-                mbar_wait(mbar, pf_parity);
-                pf_parity ^= 1u;
                 const uint32_t c0 = __shfl_sync(0xFFFFFFFFu, cnt, 0);
-#pragma unroll
-                for (int h = 0; h < 2; h++)
-                    if ((uint32_t)lane + 32u * h < pf_n) {
-                        const uint4 rec = lds128(stage + (((uint32_t)lane + 32u * h) << 4));
-                        const uint32_t a = rec.y | hi;
-                        sts128(bbase + ((c0 + lane + 32 * h) << 4), a, rec.z, rec.w, ~(a | rec.z | rec.w));
-                    }
+                if ((uint32_t)lane < pf_n) { const uint32_t a = pf0.y | hi; sts128(bbase + ((c0 + lane) << 4), a, pf0.z, pf0.w, ~(a | pf0.z | pf0.w)); }
+                if ((uint32_t)lane + 32u < pf_n) { const uint32_t a = pf1.y | hi; sts128(bbase + ((c0 + lane + 32) << 4), a, pf1.z, pf1.w, ~(a | pf1.z | pf1.w)); }
                 if (lane == 0) cnt = c0 + pf_n;
                 pf_n = 0;
                 if (nodes >= 0x40000000u) { tot_nodes += nodes; tot_sols += sols; nodes = 0; sols = 0; }
-                __syncwarp();                                    // the staging buffer is free again
+                __syncwarp();
                 prefetch();
                 continue;
             }
