@@ -15,7 +15,15 @@ namespace {
 struct PairOp {
     EntryKind kind;
     std::vector<Mask> m;      // one mask per value index of x
+    bool first = false;       // K_AND that erases only the first present position of m (duplicate values, ENT_FIRST)
 };
+
+// positions of q's value list that hold value t
+Mask positions_of(const std::vector<int32_t>& qvals, int64_t t) {
+    Mask m = 0;
+    for (size_t j = 0; j < qvals.size(); j++) if ((int64_t)qvals[j] == t) m |= Mask(1) << j;
+    return m;
+}
 
 // How assigning x = a filters q through one OpConstraint-style test "y (op) t"
 // (DoCheck, dequan.h:636-669): returns the mask over q's value list.
@@ -81,9 +89,7 @@ int compile_model(const dq_model_desc* d, CompiledModel& M, std::string& err) {
         if (hi < lo) { err = "dom_off not monotone"; return DQ_ERR_INVALID; }
         std::vector<int32_t>& vals = M.values[v];
         if (d->dom_type[v] == DQ_DOM_VALUES) {
-            vals.assign(d->dom_vals + lo, d->dom_vals + hi);
-            std::set<int32_t> uniq(vals.begin(), vals.end());
-            if (uniq.size() != vals.size()) { err = "duplicate values in a Values domain (SURVEY Q2) are not supported"; return DQ_ERR_UNSUPPORTED; }
+            vals.assign(d->dom_vals + lo, d->dom_vals + hi);     // (may list a value more than once: SURVEY.md Q2, see has_dup)
         } else if (d->dom_type[v] == DQ_DOM_RANGES) {
             if ((hi - lo) % 2) { err = "odd-length Ranges domain"; return DQ_ERR_INVALID; }
             int64_t prev_max = INT64_MIN;
@@ -107,6 +113,12 @@ int compile_model(const dq_model_desc* d, CompiledModel& M, std::string& err) {
         bool run = !vals.empty();
         for (size_t j = 1; j < vals.size() && run; j++) run = (int64_t)vals[j] == (int64_t)vals[j - 1] + 1;
         is_run[v] = run;
+    }
+    // Values domains that list a value twice: iteration visits both copies, Exclude erases the first one only
+    std::vector<char> has_dup(nv, 0);
+    for (int v = 0; v < nv; v++) {
+        std::set<int32_t> uniq(M.values[v].begin(), M.values[v].end());
+        has_dup[v] = uniq.size() != M.values[v].size();
     }
     auto mask_of = [&](int q, int op, int64_t t) -> Mask {
         return is_run[q] ? op_mask_run(M.values[q][0], (int)M.values[q].size(), op, t) : op_mask(M.values[q], op, t);
@@ -201,10 +213,11 @@ int compile_model(const dq_model_desc* d, CompiledModel& M, std::string& err) {
         std::vector<std::vector<PairOp>>& ops = ops_buf;
         for (int q : qorder) ops[q].clear();           // left over from the previous x
         qorder.clear();
-        auto push = [&](int q, EntryKind kind, std::vector<Mask>&& m) {
+        auto push = [&](int q, EntryKind kind, std::vector<Mask>&& m, bool first = false) {
             if (ops[q].empty()) qorder.push_back(q);
+            if (first) { ops[q].push_back(PairOp{kind, std::move(m), true}); return; }
             // consecutive AND filters on the same pair compose into one (the normalisation below would do it anyway)
-            if (kind == K_AND && !ops[q].empty() && ops[q].back().kind == K_AND) {
+            if (kind == K_AND && !ops[q].empty() && ops[q].back().kind == K_AND && !ops[q].back().first) {
                 std::vector<Mask>& acc = ops[q].back().m;
                 for (int b = 0; b < kx; b++) acc[b] &= m[b];
                 return;
@@ -225,7 +238,11 @@ int compile_model(const dq_model_desc* d, CompiledModel& M, std::string& err) {
                     const int64_t t = x_is_v0 ? (int64_t)xv[b] - off : (int64_t)xv[b] + off;
                     return mask_of(q, op, t);
                 };
-                if (kind == K_AND && !ops[q].empty() && ops[q].back().kind == K_AND) {
+                if (op == DQ_OP_NOTEQUAL && has_dup[q]) {                  // Exclude(t) on a list with duplicates: the first match only
+                    std::vector<Mask> m(kx);
+                    for (int b = 0; b < kx; b++) m[b] = positions_of(M.values[q], x_is_v0 ? (int64_t)xv[b] - off : (int64_t)xv[b] + off);
+                    push(q, K_AND, std::move(m), true);
+                } else if (kind == K_AND && !ops[q].empty() && ops[q].back().kind == K_AND && !ops[q].back().first) {
                     std::vector<Mask>& acc = ops[q].back().m;              // compose in place, no temporary
                     for (int b = 0; b < kx; b++) acc[b] &= mask_at(b);
                 } else {
@@ -238,6 +255,11 @@ int compile_model(const dq_model_desc* d, CompiledModel& M, std::string& err) {
                     int q = k.data[i];
                     if (q == x) continue;
                     std::vector<Mask> m(kx);
+                    if (has_dup[q]) {
+                        for (int b = 0; b < kx; b++) m[b] = positions_of(M.values[q], xv[b]);
+                        push(q, K_AND, std::move(m), true);
+                        continue;
+                    }
                     for (int b = 0; b < kx; b++) m[b] = mask_of(q, DQ_OP_NOTEQUAL, xv[b]);
                     push(q, K_AND, std::move(m));
                 }
@@ -308,19 +330,20 @@ int compile_model(const dq_model_desc* d, CompiledModel& M, std::string& err) {
             bool have_chk = false;
             for (PairOp& o : seq) {
                 if (o.kind == K_CHK) { have_chk = true; for (int b = 0; b < kx; b++) chk.m[b] |= o.m[b]; }
-                else if (o.kind == K_AND && !norm.empty() && norm.back().kind == K_AND) { for (int b = 0; b < kx; b++) norm.back().m[b] &= o.m[b]; }
+                else if (o.kind == K_AND && !o.first && !norm.empty() && norm.back().kind == K_AND && !norm.back().first) { for (int b = 0; b < kx; b++) norm.back().m[b] &= o.m[b]; }
                 else norm.push_back(std::move(o));
             }
             if (have_chk) norm.push_back(std::move(chk));
             // K_AND that is exactly "clear the same bit index" -> K_NE_SAME (no table needed)
             for (PairOp& o : norm) {
-                if (o.kind != K_AND || M.values[q].size() != (size_t)kx) continue;
+                if (o.kind != K_AND || o.first || M.values[q].size() != (size_t)kx) continue;
                 bool same = true;
                 for (int b = 0; b < kx && same; b++) same = (o.m[b] == (M.dom0[q] & ~(Mask(1) << b)));
                 if (same) o.kind = K_NE_SAME;
             }
             if (norm.size() > 1) multi_pairs++;
             n_pass = std::max(n_pass, norm.size());
+            for (const PairOp& o : norm) if (o.first) small_try = false;      // (the register engine's tables are plain AND masks)
             if (small_try) {
                 size_t i = 0;
                 const PairOp *pa = nullptr, *pw = nullptr, *pc = nullptr;
@@ -355,6 +378,7 @@ int compile_model(const dq_model_desc* d, CompiledModel& M, std::string& err) {
                 uint32_t w = (uint32_t)q | ((uint32_t)o.kind << ENT_KIND_SHIFT);
                 const size_t cnt = op_count[q];
                 if (cnt > 1) w |= (p == 0) ? (ENT_FORCE_D | ENT_FORCE_F) : (ENT_NOTRAIL_D | ENT_NOTRAIL_F);
+                if (o.first) w |= ENT_FIRST;
                 if (o.kind == K_WEQ || o.kind == K_CHK) M.has_f = true;
                 if (o.kind != K_NE_SAME) {
                     M.has_table = true;

@@ -40,7 +40,10 @@ constexpr uint32_t ENT_FORCE_F   = 1u << 19;
 constexpr uint32_t ENT_NOTRAIL_D = 1u << 20;  // later entry on the same q: the first one already trailed it
 constexpr uint32_t ENT_NOTRAIL_F = 1u << 21;
 constexpr uint32_t ENT_SKIP      = 1u << 22;  // padding so that same-q entries land in different 32-lane passes
-constexpr uint32_t ENT_FLAGS     = ENT_FORCE_D | ENT_FORCE_F | ENT_NOTRAIL_D | ENT_NOTRAIL_F | ENT_SKIP;
+constexpr uint32_t ENT_FIRST     = 1u << 23;  // K_AND on a value list with duplicates: mask[b] = the positions that hold the
+                                              // excluded value, and only the FIRST one still present goes
+                                              // (Domain::Exclude erases the first match, dequan.h:989-996)
+constexpr uint32_t ENT_FLAGS     = ENT_FORCE_D | ENT_FORCE_F | ENT_NOTRAIL_D | ENT_NOTRAIL_F | ENT_SKIP | ENT_FIRST;
 
 enum ModelClass : int32_t {
     CLASS_GENERIC = 0,     // anything the entry table can express

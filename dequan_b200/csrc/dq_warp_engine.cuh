@@ -24,7 +24,7 @@ constexpr uint32_t D_K_NE_SAME = 0, D_K_AND = 1, D_K_WEQ = 2, D_K_CHK = 3;
 constexpr uint32_t D_Q_MASK = 0xFFFFu;
 constexpr int D_KIND_SHIFT = 16;
 constexpr uint32_t D_FORCE_D = 1u << 18, D_FORCE_F = 1u << 19, D_NOTRAIL_D = 1u << 20, D_NOTRAIL_F = 1u << 21,
-                   D_SKIP = 1u << 22;
+                   D_SKIP = 1u << 22, D_FIRST = 1u << 23;
 constexpr uint32_t FULL = 0xFFFFFFFFu;
 constexpr uint32_t TRAIL_F = 0x8000;  // trail entry refers to F[q], not D[q]
 
@@ -125,9 +125,12 @@ __device__ __forceinline__ bool fc_apply(const DevTablesT<W>& T, const WarpState
             if (!HAS_TABLE || kind == D_K_NE_SAME) newD = oldD & ~(W(1) << b);
             else {
                 const W m = __ldg(T.masks + __ldg(T.ent_moff + e) + b);
-                if (kind == D_K_AND) newD = oldD & m;
-                else if (HAS_F) {
-                    if (kind == D_K_WEQ) { if (oldD & m) newD = oldD & m; else newF = ~W(0); }
+                if (kind == D_K_AND) {
+                    if (w & D_FIRST) { const W t = oldD & m; newD = oldD & ~(t & (W(0) - t)); }   // erase the first match only (duplicate values)
+                    else newD = oldD & m;
+                } else if (HAS_F) {
+                    // Domain::Intersect(val) leaves ONE copy of val (dequan.h:957-984), or the domain alone if val is absent
+                    if (kind == D_K_WEQ) { const W t = oldD & m; if (t) newD = t & (W(0) - t); else newF = ~W(0); }
                     else newF = oldF | m;
                 }
             }

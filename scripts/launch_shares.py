@@ -35,11 +35,11 @@ for name, ns in seq:
         add(g, name, ns)
     elif name.startswith("dq::k_sudoku"):
         add("1 M Sudoku batch (sudoku)", name, ns)
-    elif name.startswith("dq::k_batch_graphs") or name.startswith("dq::k_graphs"):
+    elif "k_batch_graphs" in name or "k_graphs" in name:
         add("G(200) 3-colouring batches (extra.colouring_*)", name, ns)
     else:
         add("other", name, ns)
-out = ["# ncu --metrics gpu__time_duration.sum --clock-control none -c 600 : python bench.py --steps 2 --warmup 3",
+out = ["# ncu --metrics gpu__time_duration.sum --clock-control none -c 600 : python bench.py --steps 2 --warmup 3 --no-cpu",
        "# per-launch times are cold-cache and SERIALISED (k_queens_first_warp runs on a side stream next to the level and",
        "# bucket kernels in a real step; under ncu it is timed alone).  What must agree with bench.py is each kernel's SHARE."]
 for g, d in groups.items():

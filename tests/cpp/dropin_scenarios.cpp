@@ -352,6 +352,30 @@ static void user_filter(const char* name, int n, int g, bool reverse_domains, in
     report(name, ok, csp, a);
 }
 
+// Values domains that list a value more than once (every copy is visited; Exclude erases the first copy only).
+static void duplicate_values(const char* name, bool with_equal) {
+    CSP csp;
+    int d0[] = {3, 1, 3, 2, 1}, d1[] = {2, 2, 3, 1}, d2[] = {1, 3, 3, 3, 2, 2};
+    VarId a0 = csp.AddIntVar(Domain(DomainType::Values, Array<int>(d0, d0 + 5)));
+    VarId a1 = csp.AddIntVar(Domain(DomainType::Values, Array<int>(d1, d1 + 4)));
+    VarId a2 = csp.AddIntVar(Domain(DomainType::Values, Array<int>(d2, d2 + 6)));
+    VarId a3 = csp.AddIntVar(1, 4);
+    csp.AddConstraint(OpConstraint(a0, a1, OpConstraint::Op::NotEqual, 0));
+    csp.AddConstraint(OpConstraint(a1, a2, OpConstraint::Op::NotEqual, 1));
+    csp.AddConstraint(OpConstraint(a0, a2, OpConstraint::Op::NotEqual, 0));
+    csp.AddConstraint(OpConstraint(a0, a2, OpConstraint::Op::NotEqual, 0));      // the same exclusion twice: two copies go
+    Array<VarId> ad;
+    ad.push_back(a1); ad.push_back(a2); ad.push_back(a3);
+    csp.AddConstraint(AllDifferentConstraint(ad));
+    if (with_equal) csp.AddConstraint(EqualityConstraint(a3, a0));
+    csp.AddConstraint(OpConstraint(a3, a2, OpConstraint::Op::Sup, 0));
+    csp.FinalizeModel();
+    Assignment a;
+    a.Reset(csp);
+    bool ok = csp.ForwardCheckingStep(a);
+    report(name, ok, csp, a);
+}
+
 static void empty_model() {
     CSP csp;
     csp.FinalizeModel();
@@ -440,5 +464,7 @@ int main(int argc, char** argv) {
     user_filter("user_filter_reversed_domains", 6, 1, true, 4);
     user_filter("user_filter_unsat", 6, 3, false, 0);
     user_filter("user_filter_gap", 5, 1, true, 6);
+    duplicate_values("duplicate_values", false);
+    duplicate_values("duplicate_values_equal", true);
     return 0;
 }

@@ -7,11 +7,12 @@ BASELINE.json shapes that make_golden.py leaves out because they take minutes of
     value (SURVEY.md §8c "parallel CPU split"), and the per-value results are kept as well;
   * config C4 as stated: G(200, c/199), k=3 c in {4.0, 4.2, 4.4, 4.69}, k=4 c in {6, 7}, 64 instances
     each, node budget 100 000 (status, nodes, colours per instance);
-  * config C3 per-instance: the first 10 000 puzzles of the 1 M batch (30 givens): nodes + solution.
+  * config C3 per-instance: the first 10 000 puzzles of the 1 M batch (30 givens): nodes + solution;
+  * 150 random models whose Values domains list values more than once (SURVEY.md par. 9 Q2), first + count.
 
 Run in the build container only (the GPU box has no /root/reference):
     make -C oracle ref && python tests/golden/make_golden_large.py [section ...]
-Sections: queens colouring sudoku (default: all), queens18 (18-Queens, about two hours on six cores).  An existing file is updated section by section.
+Sections: queens colouring sudoku (default: all), dups, queens18 (18-Queens, about two hours on six cores).  An existing file is updated section by section.
 """
 import hashlib
 import json
@@ -99,6 +100,26 @@ def sudoku(gold):
     save(gold)
 
 
+def dups(gold):
+    """Random models whose Values domains list values more than once (SURVEY.md par. 9 Q2), first and count modes."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from randmodels import dup_suite
+    suite = dup_suite(150)
+    txt = "".join(c.to_text() for c in suite)
+    keep = ("status", "solutions", "nodes", "first", "order")
+    out = {}
+    for mode in ("first", "count"):
+        res = subprocess.run([REF, "solve", mode, "0"], input=txt, capture_output=True, text=True, check=True).stdout
+        rows = [json.loads(line) for line in res.splitlines()]
+        assert len(rows) == len(suite)
+        out[mode] = [{k: r[k] for k in keep} for r in rows]
+    dup = {"generated_by": "tests/golden/make_golden_large.py dups", "reference": "nsweb/dequan dequan.h (unmodified)",
+           "duplicate_values": {"n": 150, "seed0": 5000, "sha256": hashlib.sha256(txt.encode()).hexdigest(), **out}}
+    with open(os.path.join(ROOT, "tests", "golden", "reference_dups.json"), "w") as f:     # (a file of its own)
+        json.dump(dup, f, separators=(",", ":"))
+    print("dups", sum(r["nodes"] for r in out["count"]), flush=True)
+
+
 def save(gold):
     with open(OUT, "w") as f:
         json.dump(gold, f, separators=(",", ":"))
@@ -111,7 +132,7 @@ def main():
             gold.update(json.load(f))
     sections = sys.argv[1:] or ["colouring", "sudoku", "queens"]
     for s in sections:
-        {"queens": queens, "queens18": lambda g: queens(g, (18,)), "colouring": colouring, "sudoku": sudoku}[s](gold)
+        {"queens": queens, "queens18": lambda g: queens(g, (18,)), "colouring": colouring, "sudoku": sudoku, "dups": dups}[s](gold)
     print("wrote", OUT, os.path.getsize(OUT))
 
 

@@ -62,3 +62,23 @@ def model_suite(n: int = 200, seed0: int = 1000) -> List[CSP]:
         nc = rng.randint(1, 14)
         out.append(random_model(seed0 + i, nv, nc, rng.randint(2, 7), "ne" if i % 5 == 0 else "all"))
     return out
+
+
+def random_model_dups(seed: int, n_vars: int = 6, n_cons: int = 9, max_dom: int = 5) -> CSP:
+    """random_model with Values domains that list some values more than once (SURVEY.md par. 9 Q2: iteration visits every
+    copy, Domain::Exclude erases the first match only, Domain::Intersect leaves one copy)."""
+    csp = random_model(seed, n_vars, n_cons, max_dom)
+    rng = random.Random(seed * 7919 + 13)
+    for d in csp.domains:
+        if d.type == DomainType.Values and rng.random() < 0.7:
+            for _ in range(rng.randint(1, 3)):
+                d.values.insert(rng.randint(0, len(d.values)), rng.choice(d.values))
+    return csp
+
+
+def dup_suite(n: int = 150, seed0: int = 5000) -> List[CSP]:
+    out = []
+    for i in range(n):
+        rng = random.Random(seed0 + i)
+        out.append(random_model_dups(seed0 + i, rng.randint(2, 8), rng.randint(2, 12), rng.randint(2, 5)))
+    return out

@@ -772,6 +772,22 @@ def test_single_process_multi_device_solve(golden, product_lib):
         api.Model(nqueens(6)).solve_tree_multi("count", (0, 99))
 
 
+def test_duplicate_values_vs_reference(product_lib):
+    """Values domains that list a value more than once (SURVEY.md par. 9 Q2): every copy is a position of the domain
+    word, Exclude erases the first copy still present, Intersect leaves one — against the unmodified reference."""
+    import json
+    from randmodels import dup_suite
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_dups.json")))["duplicate_values"]
+    suite = dup_suite(g["n"], g["seed0"])
+    for mode in ("first", "count"):
+        for i, (csp, want) in enumerate(zip(suite, g[mode])):
+            m = api.Model(csp)
+            assert m.order() == want["order"]
+            for engine in ("auto", "warp"):
+                r = m.solve_tree(mode, engine=engine)
+                assert (r.status, r.solutions, r.nodes, r.first) == (want["status"], want["solutions"], want["nodes"], want["first"]), (mode, i, engine, r)
+
+
 def test_sudoku_10k_vs_reference(golden_large, product_lib):
     """The first 10 000 puzzles of the 1 M batch (config C3): node count and solution of every puzzle against the
     unmodified reference (810 binary NotEqual constraints, tests/golden/make_golden_large.py)."""

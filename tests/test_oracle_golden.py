@@ -119,3 +119,21 @@ def test_oracle_enumeration_matches_reference():
         assert total == g["solutions"], name
         assert sols == g["all"], name
         assert O.solve(csp, "count").nodes == g["nodes"], name
+
+
+def test_oracle_duplicate_values_vs_reference():
+    """Values domains that list a value more than once (SURVEY.md par. 9 Q2): the C restatement against the unmodified
+    reference on 150 random models, both modes."""
+    import hashlib
+    import json
+    import os
+    from randmodels import dup_suite
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    g = json.load(open(os.path.join(root, "tests", "golden", "reference_dups.json")))["duplicate_values"]
+    suite = dup_suite(g["n"], g["seed0"])
+    assert hashlib.sha256("".join(c.to_text() for c in suite).encode()).hexdigest() == g["sha256"]
+    for mode in ("first", "count"):
+        for i, (csp, want) in enumerate(zip(suite, g[mode])):
+            got = O.solve(csp, mode)
+            assert (got.status, got.solutions, got.nodes, got.first, got.order) == \
+                   (want["status"], want["solutions"], want["nodes"], want["first"], want["order"]), (mode, i)
