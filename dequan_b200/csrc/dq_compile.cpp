@@ -197,6 +197,7 @@ int compile_model(const dq_model_desc* d, CompiledModel& M, std::string& err) {
     int forced_total = 0;
     // small-model tables (filled while the pairs are normalised below; dropped if some pair does not fit the pattern)
     bool small_try = nv >= 1 && nv <= 32 && M.kmax <= 32 && (size_t)nv * M.kmax * 32 * 4 * 3 + 40 * 1024 <= 200 * 1024;   // three tables + four warps of frames fit one CTA
+    for (int v = 0; v < nv; v++) if (has_dup[v]) small_try = false;      // (first-match Exclude / one-copy Intersect: warp engine only)
     if (small_try) {
         M.small_and.assign((size_t)nv * M.kmax * 32, 0xFFFFFFFFu);
         M.small_weq_on.assign((size_t)nv * M.kmax, 0u);       // the WEQ / CHK tables are created when the first such op shows up
@@ -241,7 +242,9 @@ int compile_model(const dq_model_desc* d, CompiledModel& M, std::string& err) {
                 if (op == DQ_OP_NOTEQUAL && has_dup[q]) {                  // Exclude(t) on a list with duplicates: the first match only
                     std::vector<Mask> m(kx);
                     for (int b = 0; b < kx; b++) m[b] = positions_of(M.values[q], x_is_v0 ? (int64_t)xv[b] - off : (int64_t)xv[b] + off);
+                    std::vector<Mask> again = m;                             // the copies that stay are still visited, and fail Evaluate
                     push(q, K_AND, std::move(m), true);
+                    push(q, K_CHK, std::move(again));
                 } else if (kind == K_AND && !ops[q].empty() && ops[q].back().kind == K_AND && !ops[q].back().first) {
                     std::vector<Mask>& acc = ops[q].back().m;              // compose in place, no temporary
                     for (int b = 0; b < kx; b++) acc[b] &= mask_at(b);
@@ -257,7 +260,9 @@ int compile_model(const dq_model_desc* d, CompiledModel& M, std::string& err) {
                     std::vector<Mask> m(kx);
                     if (has_dup[q]) {
                         for (int b = 0; b < kx; b++) m[b] = positions_of(M.values[q], xv[b]);
+                        std::vector<Mask> again = m;
                         push(q, K_AND, std::move(m), true);
+                        push(q, K_CHK, std::move(again));
                         continue;
                     }
                     for (int b = 0; b < kx; b++) m[b] = mask_of(q, DQ_OP_NOTEQUAL, xv[b]);
