@@ -19,6 +19,8 @@ for r in rows[2:]:
     rd_i, wr_i = float(r[ri]) * scale[units[ri]], float(r[wi]) * scale[units[wi]]
     t_i = float(r[ti]) * {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(units[ti], 1e-6)
     if do_sum:
+        if r[ki][:60] in names:
+            continue                       # one launch per kernel: a pipeline pass
         rd, wr, ms = rd + rd_i, wr + wr_i, ms + t_i
         names.append(r[ki][:60])
     else:
