@@ -19,6 +19,7 @@
 #include "dq_reg_graphs.cuh"
 #include "dq_group_graphs.cuh"
 #include "dq_small_tree.cuh"
+#include "dq_lane_tree.cuh"
 #include "dq_model.hpp"
 
 namespace dq {
@@ -624,7 +625,18 @@ static int solve_tree_generic(dq_model* m, const dq_tree_opts* opts, dq_tree_res
     const long long resident_warps = (long long)occ * m->sm_count * wpc;
     const int max_depth = nv - 1;
     const int want_depth = opts->split_depth > 0 ? std::min(opts->split_depth, max_depth) : -1;
-    const long long want_prefixes = resident_warps * 24 * opts->part_count;
+    // lane-per-subtree counting (dq_lane_tree.cuh) for small models whose pair filters are plain AND masks
+    bool lanes = count_all && !er && sizeof(W) == 4 && m->cm.small_ok && !m->cm.has_f && m->cm.kmax <= kLaneTreeMaxDom &&
+                 lane_tree_smem(nv, m->cm.kmax) <= 200 * 1024 && (opts->engine == DQ_ENGINE_AUTO || opts->engine == DQ_ENGINE_LANE);
+    if (opts->engine == DQ_ENGINE_LANE && !lanes) { g_err = "the lane engine counts the trees of small models with plain AND filters (or the N-Queens class)"; return DQ_ERR_UNSUPPORTED; }
+    int occ_l = 0;
+    if (lanes) {
+        rc = max_ctas_per_sm(k_tree_lanes, kLaneTreeThreads, lane_tree_smem(nv, m->cm.kmax), &occ_l);
+        if (rc != DQ_OK) return rc;
+        if (occ_l < 1) lanes = false;
+    }
+    // enough prefixes for 24 rounds of the resident warps — or, one subtree per lane, 6 rounds of the resident lanes
+    const long long want_prefixes = (lanes ? (long long)(occ_l * m->sm_count * kLaneTreeThreads * env_ull("DQ_LANE_TREE_ROUNDS", 1)) : resident_warps * 24) * opts->part_count;
 
     if (er) {
         DQ_CUDA(m->e_out.reserve(std::max<size_t>((size_t)er->cap * nv, 1)));
@@ -658,8 +670,9 @@ static int solve_tree_generic(dq_model* m, const dq_tree_opts* opts, dq_tree_res
     }
     auto launch_dfs = [&](int at_depth, unsigned long long n_prefix, int part_rank, int part_count, unsigned long long node_budget) -> int {
         const unsigned long long mine = (n_prefix + part_count - 1 - part_rank) / part_count;
-        const long long per_sm = small ? socc : occ;
-        const int w_cta = small ? kWarpsPerCta : wpc;
+        const bool by_lane = lanes && !node_budget && mine >= 2048;          // (a handful of prefixes: the warp-cooperative engines)
+        const long long per_sm = by_lane ? occ_l : (small ? socc : occ);
+        const int w_cta = by_lane ? kLaneTreeThreads : (small ? kWarpsPerCta : wpc);     // result slots per CTA: lanes or warps
         const long long ctas = std::max<long long>(1, std::min<long long>((long long)((mine + w_cta - 1) / w_cta), per_sm * m->sm_count));
         n_warps = ctas * w_cta;
         DQ_CUDA(m->d_sub_nodes.reserve(n_prefix));
@@ -675,7 +688,13 @@ static int solve_tree_generic(dq_model* m, const dq_tree_opts* opts, dq_tree_res
         A.node_budget = node_budget; A.gave_up = ctrl + 6;
         A.enum_out = er ? m->e_out.p : nullptr; A.enum_prefix = m->e_prefix.p; A.enum_seq = m->e_seq.p;
         A.enum_count = ctrl + 7; A.enum_cap = er ? er->cap : 0;
-        if (small) {
+        if (by_lane) {
+            SmallTablesDev ST;
+            ST.nv = nv; ST.kmax = m->cm.kmax; ST.t_and = m->t_s_and; ST.t_weq = m->t_s_weq; ST.t_weq_on = m->t_s_weq_on;
+            ST.t_chk = m->t_s_chk; ST.dom0_pos = m->t_s_dom0; ST.order = m->t_order;
+            k_tree_lanes<<<(int)ctas, kLaneTreeThreads, lane_tree_smem(nv, m->cm.kmax), m->stream>>>(ST, A);
+            res->engine_used = DQ_ENGINE_LANE;
+        } else if (small) {
             SmallTablesDev ST;
             ST.nv = nv; ST.kmax = m->cm.kmax; ST.t_and = m->t_s_and; ST.t_weq = m->t_s_weq; ST.t_weq_on = m->t_s_weq_on;
             ST.t_chk = m->t_s_chk; ST.dom0_pos = m->t_s_dom0; ST.order = m->t_order;
@@ -745,8 +764,10 @@ static int solve_tree_generic(dq_model* m, const dq_tree_opts* opts, dq_tree_res
 
     // ---- subtree DFS ----
     if (n_prefix && !probed) {
+        DQ_CUDA(cudaEventRecord(m->ev2, m->stream));
         rc = launch_dfs(depth, n_prefix, opts->part_rank, opts->part_count, 0ull);
         if (rc != DQ_OK) return rc;
+        DQ_CUDA(cudaEventRecord(m->ev3, m->stream));
     }
     if (!probed) {
         DQ_CUDA(cudaEventRecord(m->ev1, m->stream));
@@ -757,6 +778,10 @@ static int solve_tree_generic(dq_model* m, const dq_tree_opts* opts, dq_tree_res
     DQ_CUDA(cudaEventElapsedTime(&ms, m->ev0, m->ev1));
     res->kernel_ms = ms;
     res->kernel_launches = launches;
+    if (n_prefix && !probed) {                            // the subtree search alone (the frontier levels are the rest)
+        DQ_CUDA(cudaEventElapsedTime(&ms, m->ev2, m->ev3));
+        res->search_kernel_ms = ms;
+    }
 
     const unsigned long long best = h_ctrl[3];
     res->first_key = best;
@@ -822,10 +847,12 @@ static int solve_tree_impl(dq_model* m, const dq_tree_opts* opts, dq_tree_result
     const bool count_all = opts->mode == DQ_MODE_COUNT_ALL;
     if (er && !count_all) { g_err = "enumeration is a COUNT_ALL solve"; return DQ_ERR_INVALID; }
     if (er && opts->engine == DQ_ENGINE_LANE) { g_err = "the lane engine counts; enumeration runs on the warp or register engine"; return DQ_ERR_UNSUPPORTED; }
-    if (opts->engine == DQ_ENGINE_LANE && !(count_all && m->cm.model_class == CLASS_QUEENS)) {
-        g_err = "the lane engine serves COUNT_ALL on N-Queens-class models only"; return DQ_ERR_UNSUPPORTED;
+    if (opts->engine == DQ_ENGINE_LANE && !count_all) {
+        g_err = "the lane engines serve COUNT_ALL only"; return DQ_ERR_UNSUPPORTED;
     }
-    if (!er && count_all && m->cm.model_class == CLASS_QUEENS && m->cm.queens_n <= kQueensMaxN && opts->engine != DQ_ENGINE_WARP && opts->engine != DQ_ENGINE_REG)
+    // DQ_NO_CLASS=1 (measurements, tests): no structural class engine, every model takes the generic path
+    static const bool no_class = getenv("DQ_NO_CLASS") != nullptr;
+    if (!no_class && !er && count_all && m->cm.model_class == CLASS_QUEENS && m->cm.queens_n <= kQueensMaxN && opts->engine != DQ_ENGINE_WARP && opts->engine != DQ_ENGINE_REG)
         return solve_queens_lane(m, opts, res, first_solution);
     if (m->cm.wide()) {
         if (opts->engine == DQ_ENGINE_REG || opts->engine == DQ_ENGINE_LANE) { g_err = "domains of more than 32 values run on the generic warp engine only"; return DQ_ERR_UNSUPPORTED; }

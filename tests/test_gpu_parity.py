@@ -55,16 +55,14 @@ def test_reference_scenarios(golden, product_lib):
 def test_nqueens_count_and_first(golden, product_lib, engine, n):
     g = golden["nqueens"][str(n)]
     m = api.Model(nqueens(n))
-    if engine == "lane" and n < 2:
-        with pytest.raises(api.DequanError):   # a single variable has no queens structure to recognise
-            m.solve_tree("count", engine=engine)
-        return
     c = m.solve_tree("count", engine=engine)
     assert (c.solutions, c.nodes, c.first) == (g["count"]["solutions"], g["count"]["nodes"], g["count"]["first"]), c
     if engine == "lane":
         if n >= 2:
             assert c.engine == "lane"
-        return  # the lane engine serves COUNT_ALL only; FIRST runs on the warp engine
+        with pytest.raises(api.DequanError):   # the lane engines serve COUNT_ALL only; FIRST runs on the warp engines
+            m.solve_tree("first", engine=engine)
+        return
     f = m.solve_tree("first", engine=engine)
     assert (f.status, f.nodes, f.first) == (g["first"]["status"], g["first"]["nodes"], g["first"]["first"]), f
 
@@ -304,8 +302,7 @@ def test_queens_with_caller_order_leaves_the_class_engine(product_lib):
         assert m.order() == order and m.info()["model_class"] != "queens"
         for mode in ("first", "count"):
             _cmp_tree(m.solve_tree(mode), O.solve(csp, mode), (n, mode))
-        with pytest.raises(api.DequanError):
-            m.solve_tree("count", engine="lane")
+        _cmp_tree(m.solve_tree("count", engine="lane"), O.solve(csp, "count"), (n, "generic lane engine"))
     csp = nqueens(8)
     csp.assign_order = list(range(8))                    # the identity, spelled out, still qualifies
     m = api.Model(csp)
@@ -786,6 +783,52 @@ def test_duplicate_values_vs_reference(product_lib):
             for engine in ("auto", "warp"):
                 r = m.solve_tree(mode, engine=engine)
                 assert (r.status, r.solutions, r.nodes, r.first) == (want["status"], want["solutions"], want["nodes"], want["first"]), (mode, i, engine, r)
+
+
+def _queens_plus(n, extra):
+    """N-Queens with one more constraint: no longer the structure the class engine recognises."""
+    csp = nqueens(n)
+    csp.constraints = list(csp.constraints)
+    csp.AddConstraint(extra)
+    csp.FinalizeModel()
+    return csp
+
+
+@pytest.mark.parametrize("n", [9, 11, 12])
+def test_generic_lane_tree_engine(product_lib, n):
+    """dq_lane_tree.cuh (lane per prefix subtree, small models with plain AND filters): COUNT_ALL against the oracle and
+    against the warp-cooperative engines on models just outside the N-Queens class."""
+    for extra in (OpConstraint(0, n - 1, Op.Inf, 0), OpConstraint(1, 2, Op.NotEqual, 3), OpConstraint(0, 3, Op.SupEqual, -2)):
+        csp = _queens_plus(n, extra)
+        m = api.Model(csp)
+        assert m.info()["model_class"] != "queens"
+        want = O.solve(csp, "count")
+        for engine, depth in (("auto", 0), ("lane", 0), ("lane", 4), ("reg", 0), ("warp", 0)):
+            got = m.solve_tree("count", engine=engine, split_depth=depth)
+            _cmp_tree(got, want, (n, engine, depth))
+        if n >= 12:
+            assert m.solve_tree("count", engine="lane").engine == "lane"
+        parts = [m.solve_tree("count", engine="lane", part_rank=r, part_count=3) for r in range(3)]
+        assert (sum(p.solutions for p in parts), sum(p.nodes for p in parts)) == (want.solutions, want.nodes)
+        assert min(parts, key=lambda p: p.first_key).first == want.first
+
+
+def test_generic_path_on_the_queens_class(golden, product_lib):
+    """DQ_NO_CLASS=1 sends the N-Queens model itself down the generic path (lane tree engine): same counts as the
+    reference.  The variable is read once per process, hence the subprocess."""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r); from dequan_b200 import api; from dequan_b200.model import nqueens\n"
+            "for n in (10, 13):\n"
+            "    r = api.Model(nqueens(n)).solve_tree('count'); print(n, r.solutions, r.nodes, r.first, r.engine)\n"
+            % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, DQ_NO_CLASS="1"), capture_output=True, text=True,
+                         check=True, timeout=300).stdout.splitlines()
+    for line in out:
+        n = int(line.split()[0])
+        g = golden["nqueens"][str(n)]["count"]
+        want_engine = "lane" if n >= 13 else line.split()[-1]      # (a tree of a few thousand prefixes stays on the warp-cooperative engines)
+        assert line == f"{n} {g['solutions']} {g['nodes']} {g['first']} {want_engine}", line
 
 
 def test_sudoku_10k_vs_reference(golden_large, product_lib):
