@@ -85,6 +85,8 @@ struct DevBuf {
     T* p = nullptr;
     size_t cap = 0, bytes = 0;
     int dev = -1;                                        // the device the block lives on
+    bool view = false;                                   // points into somebody else's block (never handed to the cache)
+    void set_view(T* q, size_t n) { release(); p = q; cap = n; bytes = 0; view = true; }
     cudaError_t reserve(size_t n) {
         if (n <= cap) return cudaSuccess;
         release();
@@ -94,7 +96,7 @@ struct DevBuf {
         else p = nullptr;
         return e;
     }
-    void release() { if (p) g_cache.give(p, bytes, dev); p = nullptr; cap = 0; bytes = 0; }
+    void release() { if (p && !view) g_cache.give(p, bytes, dev); p = nullptr; cap = 0; bytes = 0; view = false; }
 };
 
 // Stream + timing events are per thread and device, shared by every handle.
@@ -170,6 +172,9 @@ struct dq_model {
     DevBuf<unsigned long long> d_ctrl;          // cursor, totals[2], best_key, scan totals[2], misc
     DevBuf<unsigned long long> d_sub_nodes, d_sol_key;
     DevBuf<uint8_t> d_sol;
+    DevBuf<uint8_t> d_lvl_ptrs;                 // dq_tree_nodes_upto: 8-byte result + the per-level array pointers
+    DevBuf<uint8_t> d_head;                     // k_expand_head: the first levels' arrays (views in `levels`) + its pointer table
+    int head_levels = 0;                        // levels whose arrays live in d_head
     DevBuf<uint8_t> e_out;                      // dq_enumerate_solutions: [cap][nv] value indices
     DevBuf<unsigned long long> e_prefix, e_seq; // ... and their place in the DFS order
     int last_depth = 0;
@@ -549,7 +554,7 @@ void dq_free(dq_model* m) {
     if (m->q_exec) { cudaGraphExecDestroy(m->q_exec); m->q_exec = nullptr; }
     if (m->uploaded) {
         m->d_blob.release(); m->d_ctrl.release();
-        m->d_sub_nodes.release(); m->d_sol_key.release(); m->d_sol.release();
+        m->d_sub_nodes.release(); m->d_sol_key.release(); m->d_sol.release(); m->d_lvl_ptrs.release();
         m->e_out.release(); m->e_prefix.release(); m->e_seq.release();
         m->q_records.release(); m->q_records2.release(); m->q_first.release();
         m->b_cells.release(); m->b_solution.release(); m->b_status.release(); m->b_nodes.release();
@@ -559,6 +564,7 @@ void dq_free(dq_model* m) {
             l.dmask.release(); l.surv.release(); l.dmask64.release(); l.surv64.release(); l.child_off.release(); l.parent_of.release();
             l.node_off.release(); l.prefixes.release();
         }
+        m->d_head.release();
     }
     delete m;
 }
@@ -608,7 +614,7 @@ static int solve_tree_generic(dq_model* m, const dq_tree_opts* opts, dq_tree_res
                               const bool count_all) {
     const int nv = m->cm.nv;
     int rc = DQ_OK;
-    const TreeModelDevT<W> M = dev_model_t<W>(m);
+    TreeModelDevT<W> M = dev_model_t<W>(m);
     m->last_wide = sizeof(W) == 8;
     const size_t wbytes = warp_state_bytes(nv, M.trail, sizeof(W));
     // warps per CTA: four, fewer when the per-warp state (domains + trail) of a large model would not fit a CTA
@@ -727,8 +733,81 @@ static int solve_tree_generic(dq_model* m, const dq_tree_opts* opts, dq_tree_res
         }
     }
 
+    // ---- the forced head of the tree (one prefix per level) in one launch (k_expand_head) ----
+    constexpr int kHeadCap = 1, kHeadMaxLevels = 96;
+    static const bool use_head = getenv("DQ_NO_HEAD") == nullptr;
+    if (!probed && use_head && max_depth > 0) {
+        const int head_max = std::min(std::min(max_depth, kHeadMaxLevels), want_depth >= 0 ? want_depth : max_depth);
+        // one slab: per level dmask, surv (W), child_off, parent_of (u32), node_off (u64), prefixes (cap x level bytes); then the table
+        const size_t per_level = (size_t)kHeadCap * (2 * sizeof(W) + 4 + 4 + 8);
+        size_t bytes = 0;
+        std::vector<size_t> off_lvl(head_max + 2), off_pre(head_max + 2);
+        for (int l = 0; l <= head_max; l++) { off_lvl[l] = bytes; bytes += per_level; off_pre[l] = bytes; bytes += ((size_t)kHeadCap * l + 15) & ~(size_t)15; }
+        const size_t off_tab = bytes;
+        bytes += (size_t)(head_max + 1) * sizeof(HeadLevel<W>);
+        const size_t off_base = (bytes + 15) & ~(size_t)15;
+        bytes = off_base + 2 * (size_t)nv * sizeof(W);
+        if (m->d_head.cap < bytes || m->head_levels < head_max + 1) {
+            for (auto& L : m->levels) {                       // views of the old slab go first
+                if (L.dmask.view) L.dmask.release();
+                if (L.surv.view) L.surv.release();
+                if (L.dmask64.view) L.dmask64.release();
+                if (L.surv64.view) L.surv64.release();
+                if (L.child_off.view) L.child_off.release();
+                if (L.parent_of.view) L.parent_of.release();
+                if (L.node_off.view) L.node_off.release();
+                if (L.prefixes.view) L.prefixes.release();
+            }
+            DQ_CUDA(cudaStreamSynchronize(m->stream));
+            DQ_CUDA(m->d_head.reserve(bytes));
+            m->head_levels = head_max + 1;
+        }
+        std::vector<HeadLevel<W>> tab(head_max + 1);
+        for (int l = 0; l <= head_max; l++) {
+            uint8_t* b0 = m->d_head.p + off_lvl[l];
+            LevelArrays& L = m->levels[l];
+            HeadLevel<W>& H = tab[l];
+            H.node_off = reinterpret_cast<unsigned long long*>(b0);
+            H.dmask = reinterpret_cast<W*>(b0 + (size_t)kHeadCap * 8);
+            H.surv = H.dmask + kHeadCap;
+            H.child_off = reinterpret_cast<uint32_t*>(H.surv + kHeadCap);
+            H.parent_of = H.child_off + kHeadCap;
+            H.prefixes = m->d_head.p + off_pre[l];
+            // the level arrays of `levels` become views of the slab unless they already own something at least as large
+            if (LevelWords<W>::dmask(L).cap < (size_t)kHeadCap || LevelWords<W>::dmask(L).view) LevelWords<W>::dmask(L).set_view(H.dmask, kHeadCap); else H.dmask = LevelWords<W>::dmask(L).p;
+            if (LevelWords<W>::surv(L).cap < (size_t)kHeadCap || LevelWords<W>::surv(L).view) LevelWords<W>::surv(L).set_view(H.surv, kHeadCap); else H.surv = LevelWords<W>::surv(L).p;
+            if (L.child_off.cap < (size_t)kHeadCap || L.child_off.view) L.child_off.set_view(H.child_off, kHeadCap); else H.child_off = L.child_off.p;
+            if (L.parent_of.cap < (size_t)kHeadCap || L.parent_of.view) L.parent_of.set_view(H.parent_of, kHeadCap); else H.parent_of = L.parent_of.p;
+            if (L.node_off.cap < (size_t)kHeadCap || L.node_off.view) L.node_off.set_view(H.node_off, kHeadCap); else H.node_off = L.node_off.p;
+            if (L.prefixes.cap < (size_t)kHeadCap * std::max(l, 1) || L.prefixes.view) L.prefixes.set_view(H.prefixes, (size_t)kHeadCap * std::max(l, 1)); else H.prefixes = L.prefixes.p;
+        }
+        HeadLevel<W>* d_tab = reinterpret_cast<HeadLevel<W>*>(m->d_head.p + off_tab);
+        DQ_CUDA(cudaMemcpyAsync(d_tab, tab.data(), tab.size() * sizeof(HeadLevel<W>), cudaMemcpyHostToDevice, m->stream));
+        DQ_CUDA(m->d_lvl_ptrs.reserve((size_t)(kHeadMaxLevels + 8) * 8 + 4096));
+        unsigned long long* d_out = reinterpret_cast<unsigned long long*>(m->d_lvl_ptrs.p);
+        int occ_h = 0;
+        rc = DQ_OCCUPANCY_W(m, W, k_expand_head, 32, wbytes, &occ_h);      // (also lifts the 48 KB dynamic shared-memory limit)
+        if (rc != DQ_OK) return rc;
+        W* base_D = reinterpret_cast<W*>(m->d_head.p + off_base);
+        DQ_DISPATCH_W(m, W, k_expand_head, 1, 32, wbytes, m->stream, M, d_tab, head_max, base_D, base_D + nv, d_out);
+        launches++;
+        unsigned long long* h_out = m->pin + 80;             // (pinned; 40 words are free there: [80, 119))
+        const int n_read = std::min(4 + head_max + 1, 38);
+        DQ_CUDA(cudaMemcpyAsync(h_out, d_out, (size_t)n_read * 8, cudaMemcpyDeviceToHost, m->stream));
+        std::vector<unsigned long long> h_all;
+        if (4 + head_max + 1 > n_read) { h_all.resize(4 + head_max + 1); DQ_CUDA(cudaMemcpyAsync(h_all.data(), d_out, h_all.size() * 8, cudaMemcpyDeviceToHost, m->stream)); }
+        DQ_CUDA(cudaStreamSynchronize(m->stream));
+        DQ_CUDA(cudaGetLastError());
+        const unsigned long long* ho = h_all.empty() ? h_out : h_all.data();
+        depth = (int)ho[0];
+        shallow_nodes += ho[1];
+        for (int l = 0; l <= depth; l++) m->levels[l].n = (int)ho[4 + l];
+        if (ho[2]) empty = true;
+        if (depth > 0) { M.base_D = base_D; M.base_F = base_D + nv; M.base_depth = depth; }    // prefixes are replayed from the chain's end
+    }
+
     // ---- frontier expansion, level by level, children kept in DFS order ----
-  if (!probed) {
+  if (!probed && !empty) {
     while (depth < max_depth && (want_depth >= 0 ? depth < want_depth : m->levels[depth].n < want_prefixes)) {
         LevelArrays& L = m->levels[depth];
         const int n = L.n;
@@ -739,8 +818,8 @@ static int solve_tree_generic(dq_model* m, const dq_tree_opts* opts, dq_tree_res
         DQ_DISPATCH_W(m, W, k_expand, grid, wpc * 32, smem, m->stream, M, L.prefixes.p, depth, n, Ldmask.p, Lsurv.p);
         k_scan_level<W><<<1, 1024, 0, m->stream>>>(Ldmask.p, Lsurv.p, n, L.child_off.p, L.node_off.p, ctrl + 4);
         launches += 2;
-        unsigned long long tot[2];
-        DQ_CUDA(cudaMemcpyAsync(tot, ctrl + 4, sizeof tot, cudaMemcpyDeviceToHost, m->stream));
+        unsigned long long* tot = m->pin + 76;              // (pinned: a pageable target costs a staging copy per level)
+        DQ_CUDA(cudaMemcpyAsync(tot, ctrl + 4, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, m->stream));
         DQ_CUDA(cudaStreamSynchronize(m->stream));
         shallow_nodes += tot[1];
         if (tot[0] == 0) { empty = true; depth++; m->levels[depth].n = 0; break; }
@@ -919,21 +998,24 @@ int dq_tree_nodes_upto(dq_model* m, uint64_t key, uint64_t* nodes) {
                 DQ_CUDA(read_dmask(L, (size_t)L.n - 1, &dm));
                 total += off + __builtin_popcountll(dm);
             }
-        } else {
-            std::vector<uint8_t> pre(std::max(depth, 1));
-            if (depth) DQ_CUDA(cudaMemcpy(pre.data(), m->levels[depth].prefixes.p + key * (size_t)depth, depth, cudaMemcpyDeviceToHost));
-            unsigned long long idx = key;
-            for (int l = depth - 1; l >= 0; l--) {
-                uint32_t par = 0;
-                DQ_CUDA(cudaMemcpy(&par, m->levels[l + 1].parent_of.p + idx, sizeof par, cudaMemcpyDeviceToHost));
+        } else if (depth > 0) {
+            // the parent chain of prefix `key`, walked on the device (k_nodes_upto): one launch, one read-back
+            std::vector<LevelPtrs> lp(depth + 1);
+            for (int l = 0; l <= depth; l++) {
                 const LevelArrays& L = m->levels[l];
-                unsigned long long off = 0, dm = 0;
-                DQ_CUDA(cudaMemcpy(&off, L.node_off.p + par, sizeof off, cudaMemcpyDeviceToHost));
-                DQ_CUDA(read_dmask(L, par, &dm));
-                const unsigned long long upto_bit = pre[l] >= 63 ? ~0ull : (2ull << pre[l]) - 1ull;
-                total += off + __builtin_popcountll(dm & upto_bit);
-                idx = par;
+                lp[l].parent_of = L.parent_of.p;
+                lp[l].node_off = L.node_off.p;
+                lp[l].dmask = wide ? (const void*)L.dmask64.p : (const void*)L.dmask.p;
             }
+            DQ_CUDA(m->d_lvl_ptrs.reserve((size_t)(depth + 1) * sizeof(LevelPtrs) + 8));
+            DQ_CUDA(cudaMemcpyAsync(m->d_lvl_ptrs.p + 8, lp.data(), lp.size() * sizeof(LevelPtrs), cudaMemcpyHostToDevice, m->stream));
+            k_nodes_upto<<<1, 32, 0, m->stream>>>(reinterpret_cast<const LevelPtrs*>(m->d_lvl_ptrs.p + 8), depth, key,
+                                                  m->levels[depth].prefixes.p + key * (size_t)depth, wide ? 1 : 0,
+                                                  reinterpret_cast<unsigned long long*>(m->d_lvl_ptrs.p));
+            unsigned long long above = 0;
+            DQ_CUDA(cudaMemcpyAsync(&above, m->d_lvl_ptrs.p, sizeof above, cudaMemcpyDeviceToHost, m->stream));
+            DQ_CUDA(cudaStreamSynchronize(m->stream));
+            total += above;
         }
     }
     *nodes = total;

@@ -15,14 +15,19 @@ struct TreeModelDevT {
     const uint16_t* __restrict__ order;  // [nv]
     const uint16_t* __restrict__ pos;    // [nv]
     int trail;                           // trail capacity per warp
+    // the state k_expand_head left at the end of the forced chain (domains / fails-validation words by var id): prefixes
+    // are replayed from there instead of from the root.  base_depth == 0: no chain.
+    const W* base_D = nullptr;
+    const W* base_F = nullptr;
+    int base_depth = 0;
 };
 typedef TreeModelDevT<uint32_t> TreeModelDev;
 
 template <typename W>
 __device__ __forceinline__ void load_root_state(const TreeModelDevT<W>& M, const WarpStateT<W>& S, int lane) {
     for (int v = lane; v < M.T.nv; v += 32) {
-        S.D[v] = __ldg(M.dom0 + v);
-        S.F[v] = 0;
+        S.D[v] = M.base_depth ? __ldg(M.base_D + v) : __ldg(M.dom0 + v);
+        S.F[v] = M.base_depth ? __ldg(M.base_F + v) : W(0);
         S.order[v] = __ldg(M.order + v);
         S.pos[v] = __ldg(M.pos + v);
     }
@@ -30,14 +35,16 @@ __device__ __forceinline__ void load_root_state(const TreeModelDevT<W>& M, const
 }
 
 // Re-apply a prefix (value indices for depths 0..depth-1) to the root state.
-template <bool HAS_F, bool HAS_TABLE, typename W>
+// (COHERENT: the prefix was written by this very launch — k_expand_head — so no read-only cache path)
+template <bool HAS_F, bool HAS_TABLE, typename W, bool COHERENT = false>
 __device__ __forceinline__ void replay_prefix(const TreeModelDevT<W>& M, const WarpStateT<W>& S, const uint8_t* __restrict__ prefix,
                                               int depth, int lane) {
     load_root_state(M, S, lane);
     int top = 0;
     for (int i = 0; i < depth; i++) {
-        const int b = __ldg(prefix + i);
+        const int b = COHERENT ? (int)*(const volatile uint8_t*)(prefix + i) : (int)__ldg(prefix + i);
         if (lane == 0) S.val[i] = (uint8_t)b;
+        if (i < M.base_depth) continue;               // (the forced chain is already in the base state)
         fc_apply<HAS_F, HAS_TABLE>(M.T, S, S.order[i], b, i, top, lane);
         top = 0;                                      // nothing above the split depth is ever undone
     }
@@ -128,6 +135,68 @@ __global__ void k_write_children(const uint8_t* __restrict__ prefixes, int depth
         parent_of[o] = (uint32_t)i;
         ++o;
     }
+}
+
+// ---- the forced head of the tree in ONE launch -------------------------------------------------------------------
+// Givens and other singleton domains at the head of the static order (Assignment::Reset puts them first, dequan.h:384-394),
+// and every level where forward checking leaves a single passing value, keep the frontier at ONE prefix — often for
+// dozens of levels (the reference's SudokuTest: 32 givens) — and each such level is a microsecond of work behind three
+// launches and a host round trip.  One warp walks that chain: per level exactly what k_expand / k_scan_level /
+// k_write_children produce (domain mask, surviving values, offsets, the child prefix, its parent), with the state
+// carried along instead of replayed, until a level has no child or more than one; the host carries on from there.
+template <typename W>
+struct HeadLevel {
+    uint8_t* prefixes;                 // [1][level]
+    W* dmask;                          // [1]
+    W* surv;                           // [1]
+    uint32_t* child_off;               // [1]
+    unsigned long long* node_off;      // [1]
+    uint32_t* parent_of;               // [1] index into the previous level
+};
+// out[0] = levels completed (the frontier at that depth is materialised), out[1] = nodes of those levels,
+// out[2] = 1 if the frontier died out, out[4 + l] = frontier size at depth l
+template <bool HAS_F, bool HAS_TABLE, typename W = uint32_t>
+__global__ void __launch_bounds__(32)
+k_expand_head(TreeModelDevT<W> M, const HeadLevel<W>* __restrict__ lv, int max_levels, W* __restrict__ base_D, W* __restrict__ base_F,
+              unsigned long long* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x;
+    WarpStateT<W> S = carve_warp_state_t<W>(smem, M.T.nv, M.trail);
+    load_root_state(M, S, lane);
+    int done = 0, top = 0;
+    unsigned long long nodes = 0;
+    bool died = false;
+    if (lane == 0) out[4] = 1;
+    for (int l = 0; l < max_levels; l++) {
+        const HeadLevel<W> L = lv[l];
+        const int x = S.order[l];
+        const W dm = S.D[x];
+        W c = HAS_F ? (dm & ~S.F[x]) : dm, sv = 0;
+        while (c) {
+            const int b = dq_ffs(c) - 1;
+            c &= c - 1;
+            const bool wiped = fc_apply<HAS_F, HAS_TABLE>(M.T, S, x, b, l, top, lane);
+            trail_undo<HAS_F>(S, 0, top, lane);
+            if (!wiped) sv |= W(1) << b;
+        }
+        const int kids = dq_popc(sv);
+        if (kids > 1) break;                                         // the tree fans out: this level is the host's
+        if (lane == 0) { L.dmask[0] = dm; L.surv[0] = sv; L.child_off[0] = 0; L.node_off[0] = 0; out[4 + l + 1] = (unsigned long long)kids; }
+        nodes += dq_popc(dm);
+        done = l + 1;
+        if (kids == 0) { died = true; break; }
+        const int b = dq_ffs(sv) - 1;
+        if (lane == 0) S.val[l] = (uint8_t)b;
+        __syncwarp();
+        const HeadLevel<W> C = lv[l + 1];
+        for (int j = lane; j <= l; j += 32) C.prefixes[j] = S.val[j];
+        if (lane == 0) C.parent_of[0] = 0;
+        fc_apply<HAS_F, HAS_TABLE>(M.T, S, x, b, l, top, lane);      // for good: nothing above the split is ever undone
+        top = 0;
+    }
+    __syncwarp();
+    for (int v = lane; v < M.T.nv; v += 32) { base_D[v] = S.D[v]; base_F[v] = S.F[v]; }      // the state after `done` levels
+    if (lane == 0) { out[0] = (unsigned long long)done; out[1] = nodes; out[2] = died ? 1ull : 0ull; }
 }
 
 // ---- persistent subtree DFS: warps pull prefix indices from an atomic cursor -------------------
@@ -417,6 +486,31 @@ __global__ void __launch_bounds__(1024) k_int_peak(uint32_t* out, int iters) {
         }
     }
     out[blockIdx.x * blockDim.x + threadIdx.x] = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
+}
+
+// FIRST-mode node accounting above the split (dq_tree_nodes_upto): one thread walks the parent chain of prefix `key`
+// from the split depth to the root and adds, per level, the nodes the reference visits there up to the value that leads
+// on (node_off of the parent + the values of its domain up to that one).  One launch and one 8-byte read-back instead
+// of three synchronous copies per level.
+struct LevelPtrs {
+    const uint32_t* parent_of;           // [n of level l+1] -> index in level l   (stored with level l+1's entry)
+    const unsigned long long* node_off;  // [n of level l]
+    const void* dmask;                   // [n of level l], 32- or 64-bit words
+};
+__global__ void k_nodes_upto(const LevelPtrs* __restrict__ lv, int depth, unsigned long long key, const uint8_t* __restrict__ prefix,
+                             int wide, unsigned long long* __restrict__ out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    unsigned long long total = 0, idx = key;
+    for (int l = depth - 1; l >= 0; l--) {
+        const uint32_t par = lv[l + 1].parent_of[idx];
+        const unsigned long long dm = wide ? reinterpret_cast<const unsigned long long*>(lv[l].dmask)[par]
+                                           : (unsigned long long)reinterpret_cast<const uint32_t*>(lv[l].dmask)[par];
+        const int v = prefix[l];
+        const unsigned long long upto_bit = v >= 63 ? ~0ull : (2ull << v) - 1ull;
+        total += lv[l].node_off[par] + (unsigned long long)__popcll(dm & upto_bit);
+        idx = par;
+    }
+    *out = total;
 }
 
 }  // namespace dq
