@@ -284,7 +284,8 @@ def main():
                 "e2e": {"value": q["nodes"] * steps / q["e_tot"], "unit": "nodes/s", "h2d_bytes_per_step": q["table_bytes"] + 64,
                         "d2h_bytes_per_step": 64 + 4 * n + 8 * 64, "ms_per_step": 1e3 * q["e_tot"] / steps},
                 "gpu_launches": q["launches"], "engine": q["engine"],
-                "roofline": roofline_queens(n, world, q["dom_nodes"], q["dom_records"], q["dom_ms"] / steps, int_peak, hbm_peak, peak_src)}
+                "roofline": roofline_queens(n, world, q["dom_nodes"], q["dom_records"], q["dom_ms"] / steps, int_peak, hbm_peak, peak_src,
+                                            q["table_bytes"])}
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -331,7 +332,7 @@ def main():
         dist.destroy_process_group()
 
 
-def roofline_queens(n, world, lane_nodes, records, lane_ms, int_peak, hbm_peak, peak_src):
+def roofline_queens(n, world, lane_nodes, records, lane_ms, int_peak, hbm_peak, peak_src, table_bytes=0):
     """Roofline of the dominant kernel, k_queens_bucket (depth-bucketed subtree search).  It is integer-issue bound
     (SURVEY.md §8d): algorithmic work = (5A+4) lane-ops per node, A = forward-checking domain updates per node; the peak
     is the LOP3 rate measured in this run.  nodes_per_launch is what THIS rank's launch searched."""
@@ -341,9 +342,11 @@ def roofline_queens(n, world, lane_nodes, records, lane_ms, int_peak, hbm_peak, 
     return {"bound": "int32-alu", "kernel": "k_queens_bucket", "achieved": achieved / 1e12, "peak": int_peak / 1e12,
             "unit": "Tlane-op/s per GPU", "frac": achieved / int_peak, "kernel_ms": lane_ms,
             "nodes_per_launch": lane_nodes, "ops_per_node": ops_per_node, "peak_source": "LOP3 microbenchmark, this run",
-            "traffic": traffic, "traffic_source": src, "algorithmic_bytes": records * 16,
+            # the job's true input is the model table (a few KB); what the kernel streams from HBM is the ENGINE'S OWN frontier:
+            # one 16-byte record per depth-k subtree, written by the level kernels before it
+            "traffic": traffic, "traffic_source": src, "algorithmic_bytes": table_bytes, "frontier_bytes": records * 16,
             "hbm": {"achieved": records * 16 / (lane_ms * 1e-3) / 1e9 if lane_ms else None, "peak": hbm_peak, "unit": "GB/s",
-                    "peak_source": peak_src}}
+                    "peak_source": peak_src, "what": "frontier records read by the launch"}}
 
 
 def sudoku_rooflines(out, hbm_peak, peak_src, int_peak):

@@ -1227,7 +1227,7 @@ static int run_batch_sudoku(dq_model* m, const uint8_t* cells_dev, int64_t n, in
     const char* env_q = getenv("DQ_SUDOKU_POP_QUORUM");
     A.pop_quorum = env_q ? atoi(env_q) : kPopQuorum;
     const char* env_fb = getenv("DQ_SUDOKU_FIRST_BUDGET");
-    A.first_budget = env_fb ? (unsigned)atoi(env_fb) : (n >= 400000 ? 2048u : 1024u);   // measured: flat 1536-3072 at 1M, 1024 best for 125-250 k shards
+    A.first_budget = env_fb ? (unsigned)atoi(env_fb) : (n >= 400000 ? 3072u : 1024u);   // measured at 1 M: 1024 -> 32.7 ms, 2048 -> 30.3, 3072 -> 29.5; 125 k shards: flat 512-1024 (7.2 ms), 1536 -> 7.6
     if (A.force_donate) A.first_budget = std::min(A.first_budget, 4u * A.force_donate);       // tests: push work through the task path
     const bool trace = getenv("DQ_TRACE") != nullptr;
     cudaEvent_t ev[7] = {nullptr};
