@@ -319,8 +319,8 @@ k_queens_bucket(QueensLaneArgs A) {
 
 
     uint32_t cnt = 0;                                            // lane i: frames in bucket i
-    uint32_t nodes = 0, sols = 0;
-    unsigned long long tot_nodes = 0, tot_sols = 0;
+    unsigned long long trip_nodes = 0;                           // warp-uniform: one node per frame taken (AssignVar of its next value)
+    unsigned long long tot_sols = 0;                             // per lane: values of the last variable (a node and a solution each)
     unsigned long long chunk_pos = 0, chunk_end = 0;
     bool exhausted = false;
 
@@ -360,7 +360,6 @@ k_queens_bucket(QueensLaneArgs A) {
                 if ((uint32_t)lane + 32u < pf_n) { const uint32_t a = pf1.y | hi; sts128(bbase + ((c0 + lane + 32) << 4), a, pf1.z, pf1.w, ~(a | pf1.z | pf1.w)); }
                 if (lane == 0) cnt = c0 + pf_n;
                 pf_n = 0;
-                if (nodes >= 0x40000000u) { tot_nodes += nodes; tot_sols += sols; nodes = 0; sols = 0; }
                 __syncwarp();
                 prefetch();
                 continue;
@@ -369,19 +368,24 @@ k_queens_bucket(QueensLaneArgs A) {
             if (!any) break;
             lvl = __ffs((int)any) - 1;
         }
-        if (nodes >= 0x40000000u) { tot_nodes += nodes; tot_sols += sols; nodes = 0; sols = 0; }   // (a warp that never refills still flushes its 32-bit counts)
         const uint32_t c = __shfl_sync(0xFFFFFFFFu, cnt, lvl);
-        const uint32_t n = min(c, 64u);
-        const uint32_t keep_base = c - n;
         const uint32_t row = bbase + (uint32_t)lvl * (kQueensBucketCap * 16u);
+        uint32_t keep_base = c - 64u;
+        if (c < 64u) {
+            // a short trip (the tail of the warp's work): pads the bucket to 64 with frames that hold no value — every
+            // trip is then a full one, with no per-lane "is this slot in use" anywhere below
+            if ((uint32_t)lane >= c) sts128(row + ((uint32_t)lane << 4), 0xFFFFFFFFu, 0u, 0u, 0u);
+            if ((uint32_t)lane + 32u >= c) sts128(row + (((uint32_t)lane + 32u) << 4), 0xFFFFFFFFu, 0u, 0u, 0u);
+            keep_base = 0u;
+            __syncwarp();
+        }
+        trip_nodes += min(c, 64u);
         // two frames per lane and trip: the bucket choice, the counts and the loop are paid once for 64 nodes, and the two
         // dependency chains interleave
-        const bool actA = (uint32_t)lane < n, actB = (uint32_t)lane + 32u < n;
-        uint32_t aA = 0xFFFFFFFFu, lA = 0, rA = 0, cA = 0, aB = 0xFFFFFFFFu, lB = 0, rB = 0, cB = 0;
-        if (actA) { const uint4 f = lds128(row + ((keep_base + lane) << 4)); aA = f.x; lA = f.y; rA = f.z; cA = f.w; }
-        if (actB) { const uint4 f = lds128(row + ((keep_base + 32u + lane) << 4)); aB = f.x; lB = f.y; rB = f.z; cB = f.w; }
-        const uint32_t bitA = cA & (0u - cA), bitB = cB & (0u - cB);
-        cA ^= bitA; cB ^= bitB;
+        const uint4 fA = lds128(row + ((keep_base + lane) << 4)), fB = lds128(row + ((keep_base + 32u + lane) << 4));
+        const uint32_t aA = fA.x, lA = fA.y, rA = fA.z, aB = fB.x, lB = fB.y, rB = fB.z;
+        const uint32_t bitA = fA.w & (0u - fA.w), bitB = fB.w & (0u - fB.w);      // (0 for a frame without values: its child below is "wiped")
+        const uint32_t cA = fA.w ^ bitA, cB = fB.w ^ bitB;
         const uint32_t naA = aA | bitA, nlA = (lA | bitA) << 1, nrA = (rA | bitA) >> 1;
         const uint32_t naB = aB | bitB, nlB = (lB | bitB) << 1, nrB = (rB | bitB) >> 1;
         const int last = L - 1 - lvl;
@@ -394,37 +398,33 @@ k_queens_bucket(QueensLaneArgs A) {
 #undef DQ_QROWS
             default: occA = queens_rows_occupied<30>(naA, nlA, nrA); occB = queens_rows_occupied<30>(naB, nlB, nrB); break;
         }
-        const bool passA = actA && occA != 0xFFFFFFFFu, passB = actB && occB != 0xFFFFFFFFu;
-        nodes += (actA ? 1u : 0u) + (actB ? 1u : 0u);
+        // (a padding frame has a = all ones: "wiped" whatever the rows say)
+        const bool passA = occA != 0xFFFFFFFFu, passB = occB != 0xFFFFFFFFu;
         const uint32_t keepA = __ballot_sync(0xFFFFFFFFu, cA != 0u), keepB = __ballot_sync(0xFFFFFFFFu, cB != 0u);
         const uint32_t nkA = __popc(keepA);
         if (cA) sts128(row + ((keep_base + __popc(keepA & lt)) << 4), aA, lA, rA, cA);
         if (cB) sts128(row + ((keep_base + nkA + __popc(keepB & lt)) << 4), aB, lB, rB, cB);
         const uint32_t c_new = keep_base + nkA + __popc(keepB);
+        const uint32_t dA = ~(naA | nlA | nrA), dB = ~(naB | nlB | nrB);
         if (last == 0) {
-            if (passA) { const uint32_t pc = __popc(~(naA | nlA | nrA)); nodes += pc; sols += pc; }
-            if (passB) { const uint32_t pc = __popc(~(naB | nlB | nrB)); nodes += pc; sols += pc; }
+            tot_sols += (passA ? __popc(dA) : 0) + (passB ? __popc(dB) : 0);
             if (lane == lvl) cnt = c_new;
         } else {
             const uint32_t kidsA = __ballot_sync(0xFFFFFFFFu, passA), kidsB = __ballot_sync(0xFFFFFFFFu, passB);
             const uint32_t c1 = __shfl_sync(0xFFFFFFFFu, cnt, lvl + 1);
             const uint32_t nA = __popc(kidsA);
             const uint32_t nrow = row + kQueensBucketCap * 16u;
-            if (passA) sts128(nrow + ((c1 + __popc(kidsA & lt)) << 4), naA, nlA, nrA, ~(naA | nlA | nrA));
-            if (passB) sts128(nrow + ((c1 + nA + __popc(kidsB & lt)) << 4), naB, nlB, nrB, ~(naB | nlB | nrB));
+            if (passA) sts128(nrow + ((c1 + __popc(kidsA & lt)) << 4), naA, nlA, nrA, dA);
+            if (passB) sts128(nrow + ((c1 + nA + __popc(kidsB & lt)) << 4), naB, nlB, nrB, dB);
             if (lane == lvl) cnt = c_new;
             if (lane == lvl + 1) cnt = c1 + nA + __popc(kidsB);
         }
         __syncwarp();
     }
-    tot_nodes += nodes; tot_sols += sols;
-    for (int o = 16; o > 0; o >>= 1) {
-        tot_nodes += __shfl_down_sync(0xFFFFFFFFu, tot_nodes, o);
-        tot_sols += __shfl_down_sync(0xFFFFFFFFu, tot_sols, o);
-    }
+    for (int o = 16; o > 0; o >>= 1) tot_sols += __shfl_down_sync(0xFFFFFFFFu, tot_sols, o);
     if (lane == 0) {
         atomicAdd(A.totals + 0, tot_sols);
-        atomicAdd(A.dfs_nodes, tot_nodes);
+        atomicAdd(A.dfs_nodes, tot_sols + trip_nodes);
     }
 }
 
