@@ -342,7 +342,7 @@ static int solve_queens_lane(dq_model* m, const dq_tree_opts* opts, dq_tree_resu
     auto estimate = [&](int k) { double e = 1; for (int i = 0; i < k; i++) e *= std::max(N - 2.2 * i, 3.6); return e; };
     int occ = 0;
     int rc = DQ_OK;
-    if (opts->split_depth > 0) K = std::min(opts->split_depth, std::min(N - 2, 12));
+    if (opts->split_depth > 0) K = std::min(opts->split_depth, std::min(N - 3, 12));
     else {
         // measured per N (scripts/sweep_k.py, profiles/r1_queens_split_depth.txt): small boards are bound by the launches of
         // the levels, large ones by keeping the pools fed to the end (18 queens: 132 -> 121 ms at depth 8); the partitions
@@ -358,7 +358,7 @@ static int solve_queens_lane(dq_model* m, const dq_tree_opts* opts, dq_tree_resu
     // partition deal happens at depth <= 5 — so the split may go deeper than 32-bit keys would allow)
     // warps per CTA chosen so that the pools (buckets x 128 frames x 16 B + the staging buffer, per warp) pack an SM's shared memory best
     int bucket_warps = 4;
-    const size_t per_warp = (size_t)(N - 1 - K) * kQueensBucketCap * sizeof(uint4) + kQueensStageBytes;
+    const size_t per_warp = (size_t)(N - 2 - K) * kQueensBucketCap * sizeof(uint4) + kQueensStageBytes;
     {
         int best = 0;
         for (int w = 2; w <= kQueensBucketMaxWarps; w++) {
@@ -931,7 +931,7 @@ static int solve_tree_impl(dq_model* m, const dq_tree_opts* opts, dq_tree_result
     }
     // DQ_NO_CLASS=1 (measurements, tests): no structural class engine, every model takes the generic path
     static const bool no_class = getenv("DQ_NO_CLASS") != nullptr;
-    if (!no_class && !er && count_all && m->cm.model_class == CLASS_QUEENS && m->cm.queens_n <= kQueensMaxN && opts->engine != DQ_ENGINE_WARP && opts->engine != DQ_ENGINE_REG)
+    if (!no_class && !er && count_all && m->cm.model_class == CLASS_QUEENS && m->cm.queens_n >= 3 && m->cm.queens_n <= kQueensMaxN && opts->engine != DQ_ENGINE_WARP && opts->engine != DQ_ENGINE_REG)
         return solve_queens_lane(m, opts, res, first_solution);
     if (m->cm.wide()) {
         if (opts->engine == DQ_ENGINE_REG || opts->engine == DQ_ENGINE_LANE) { g_err = "domains of more than 32 values run on the generic warp engine only"; return DQ_ERR_UNSUPPORTED; }

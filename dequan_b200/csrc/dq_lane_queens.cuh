@@ -242,7 +242,7 @@ __device__ __forceinline__ uint32_t shr_clamp(uint32_t x, uint32_t n) { uint32_t
 //     more records from the frontier list, and once that is empty widens from the shallowest bucket.
 // Node and solution counts do not depend on the visiting order; the DFS-first solution is found separately by
 // queens_first_owned.  Bucket sizes live in registers, lane i holding the size of bucket i.
-constexpr int kQueensBucketMaxWarps = 6;              // warps per CTA: the host picks what packs an SM's shared memory best
+constexpr int kQueensBucketMaxWarps = 12;             // warps per CTA: the host picks what packs an SM's shared memory best
 constexpr int kQueensBucketCap = 128;
 constexpr int kQueensStageBytes = 0;                  // (the pools fill an SM's shared memory to the byte at 17 queens: see the refill)
 
@@ -306,7 +306,7 @@ k_queens_bucket(QueensLaneArgs A) {
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t lt = (1u << lane) - 1u;
     const int N = A.n;
-    const int L = N - 1 - A.k;                                   // buckets: depth k .. N-2
+    const int L = N - 2 - A.k;                                   // buckets: depth k .. N-3 (frames of depth N-2 never reach a bucket: see below)
     const uint32_t hi = ~((1u << N) - 1u);
     const uint32_t per_warp = (uint32_t)L * kQueensBucketCap * 16u + kQueensStageBytes;
     const uint32_t bbase = (uint32_t)__cvta_generic_to_shared(qb_frames) + (uint32_t)wib * per_warp;
@@ -321,6 +321,7 @@ k_queens_bucket(QueensLaneArgs A) {
     uint32_t cnt = 0;                                            // lane i: frames in bucket i
     unsigned long long trip_nodes = 0;                           // warp-uniform: one node per frame taken (AssignVar of its next value)
     unsigned long long tot_sols = 0;                             // per lane: values of the last variable (a node and a solution each)
+    unsigned long long tot_lane_nodes = 0;                       // per lane: values tried for variable N-2
     unsigned long long chunk_pos = 0, chunk_end = 0;
     bool exhausted = false;
 
@@ -388,7 +389,7 @@ k_queens_bucket(QueensLaneArgs A) {
         const uint32_t cA = fA.w ^ bitA, cB = fB.w ^ bitB;
         const uint32_t naA = aA | bitA, nlA = (lA | bitA) << 1, nrA = (rA | bitA) >> 1;
         const uint32_t naB = aB | bitB, nlB = (lB | bitB) << 1, nrB = (rB | bitB) >> 1;
-        const int last = L - 1 - lvl;
+        const int last = L - lvl;                                // later variables to check, minus one (>= 1)
         uint32_t occA = 0, occB = 0;                             // all ones <=> some later domain is empty
         switch (last) {
 #define DQ_QROWS(J) case J: occA = queens_rows_occupied<J + 1>(naA, nlA, nrA); occB = queens_rows_occupied<J + 1>(naB, nlB, nrB); break;
@@ -406,8 +407,17 @@ k_queens_bucket(QueensLaneArgs A) {
         if (cB) sts128(row + ((keep_base + nkA + __popc(keepB & lt)) << 4), aB, lB, rB, cB);
         const uint32_t c_new = keep_base + nkA + __popc(keepB);
         const uint32_t dA = ~(naA | nlA | nrA), dB = ~(naB | nlB | nrB);
-        if (last == 0) {
-            tot_sols += (passA ? __popc(dA) : 0) + (passB ? __popc(dB) : 0);
+        if (last == 1) {
+            // The children hold variable N-2.  Two columns are free there, so a child has at most two values: both are
+            // tried right here instead of going through a bucket of their own.  Each value is a node; what it leaves
+            // to the last variable (at most the other free column) is a node and a solution per value.
+            const uint32_t eA = passA ? dA : 0u, eB = passB ? dB : 0u;
+            const uint32_t bA1 = eA & (0u - eA), bA2 = eA ^ bA1, bB1 = eB & (0u - eB), bB2 = eB ^ bB1;
+            const uint32_t fA1 = ~(naA | bA1 | ((nlA | bA1) << 1) | ((nrA | bA1) >> 1)), fA2 = ~(naA | bA2 | ((nlA | bA2) << 1) | ((nrA | bA2) >> 1));
+            const uint32_t fB1 = ~(naB | bB1 | ((nlB | bB1) << 1) | ((nrB | bB1) >> 1)), fB2 = ~(naB | bB2 | ((nlB | bB2) << 1) | ((nrB | bB2) >> 1));
+            const uint32_t s = (bA1 ? __popc(fA1) : 0) + (bA2 ? __popc(fA2) : 0) + (bB1 ? __popc(fB1) : 0) + (bB2 ? __popc(fB2) : 0);
+            tot_sols += s;
+            tot_lane_nodes += __popc(eA) + __popc(eB);
             if (lane == lvl) cnt = c_new;
         } else {
             const uint32_t kidsA = __ballot_sync(0xFFFFFFFFu, passA), kidsB = __ballot_sync(0xFFFFFFFFu, passB);
@@ -421,10 +431,13 @@ k_queens_bucket(QueensLaneArgs A) {
         }
         __syncwarp();
     }
-    for (int o = 16; o > 0; o >>= 1) tot_sols += __shfl_down_sync(0xFFFFFFFFu, tot_sols, o);
+    for (int o = 16; o > 0; o >>= 1) {
+        tot_sols += __shfl_down_sync(0xFFFFFFFFu, tot_sols, o);
+        tot_lane_nodes += __shfl_down_sync(0xFFFFFFFFu, tot_lane_nodes, o);
+    }
     if (lane == 0) {
         atomicAdd(A.totals + 0, tot_sols);
-        atomicAdd(A.dfs_nodes, tot_sols + trip_nodes);
+        atomicAdd(A.dfs_nodes, tot_sols + tot_lane_nodes + trip_nodes);
     }
 }
 
