@@ -359,12 +359,18 @@ static int solve_queens_lane(dq_model* m, const dq_tree_opts* opts, dq_tree_resu
     // warps per CTA chosen so that the pools (buckets x 128 frames x 16 B + the staging buffer, per warp) pack an SM's shared memory best
     int bucket_warps = 4;
     const size_t per_warp = (size_t)(N - 2 - K) * kQueensBucketCap * sizeof(uint4) + kQueensStageBytes;
+    // up to eight buckets: the kernel compiled for exactly that many (static levels, packed counts); more: the general one
+    typedef void (*BucketKernel)(QueensLaneArgs);
+    static const BucketKernel kBucketKernels[9] = {nullptr, k_queens_bucket_t<1>, k_queens_bucket_t<2>, k_queens_bucket_t<3>, k_queens_bucket_t<4>,
+                                                   k_queens_bucket_t<5>, k_queens_bucket_t<6>, k_queens_bucket_t<7>, k_queens_bucket_t<8>};
+    static const bool general_only = getenv("DQ_QUEENS_GENERAL") != nullptr;
+    const BucketKernel bucket_kernel = (N - 2 - K <= 8 && !general_only) ? kBucketKernels[N - 2 - K] : k_queens_bucket;
     {
         int best = 0;
         for (int w = 2; w <= kQueensBucketMaxWarps; w++) {
             if (per_warp * w > 200 * 1024) break;
             int o = 0;
-            rc = max_ctas_per_sm(k_queens_bucket, w * 32, per_warp * w, &o);
+            rc = max_ctas_per_sm(bucket_kernel, w * 32, per_warp * w, &o);
             if (rc != DQ_OK) return rc;
             if (o * w > best) { best = o * w; bucket_warps = w; occ = o; }
         }
@@ -436,7 +442,7 @@ static int solve_queens_lane(dq_model* m, const dq_tree_opts* opts, dq_tree_resu
                                                                        count_nodes, (l == part_level && opts->part_count > 1) ? 1 : 0);
             }
             if (with_events) DQ_CUDA(cudaEventRecord(m->ev2, m->stream));
-            k_queens_bucket<<<ctas, bucket_warps * 32, smem, m->stream>>>(A);
+            bucket_kernel<<<ctas, bucket_warps * 32, smem, m->stream>>>(A);
             if (with_events) DQ_CUDA(cudaEventRecord(m->ev3, m->stream));
             DQ_CUDA(cudaStreamWaitEvent(m->stream, m->ev_join, 0));
             DQ_CUDA(cudaGetLastError());

@@ -441,4 +441,167 @@ k_queens_bucket(QueensLaneArgs A) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// The same search with the number of buckets L (<= 8) a template parameter.  Everything the kernel above finds out per
+// trip is then a compile-time constant of the code that serves one level: the bucket's address, the number of later
+// variables to check (no second dispatch for the rows), which count it updates.  The counts live packed, a byte per
+// bucket, in two warp-uniform words (bit 6 of a byte = "holds 64 frames"), so choosing the level and all the count
+// arithmetic run on the uniform datapath with no shuffle in the trip's dependency chain.
+struct QueensTripState {
+    uint32_t pk_lo, pk_hi;                 // frames per bucket, a byte each: buckets 0-3, 4-7
+    unsigned long long trip_nodes;         // warp-uniform: one node per frame taken (AssignVar of its next value)
+    unsigned long long tot_sols;           // per lane: values of the last variable (a node and a solution each)
+    unsigned long long tot_lane_nodes;     // per lane: values tried for variable N-2
+};
+
+__device__ __forceinline__ uint32_t nor3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0x01;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+template <int L, int LVL>
+__device__ __forceinline__ void queens_trip(QueensTripState& S, const uint32_t bbase, const uint32_t lane, const uint32_t lt) {
+    constexpr uint32_t kRow = (uint32_t)LVL * kQueensBucketCap * 16u;
+    constexpr int SH = (LVL & 3) * 8;
+    uint32_t& pk = LVL < 4 ? S.pk_lo : S.pk_hi;
+    const uint32_t c = (pk >> SH) & 0xFFu;
+    const uint32_t row = bbase + kRow;
+    uint32_t keep_base = c - 64u;
+    if (c < 64u) {
+        // a short trip (the tail of the warp's work): pads the bucket to 64 with frames that hold no value — every
+        // trip is then a full one, with no per-lane "is this slot in use" anywhere below
+        if (lane >= c) sts128(row + (lane << 4), 0xFFFFFFFFu, 0u, 0u, 0u);
+        if (lane + 32u >= c) sts128(row + ((lane + 32u) << 4), 0xFFFFFFFFu, 0u, 0u, 0u);
+        keep_base = 0u;
+        __syncwarp();
+    }
+    S.trip_nodes += min(c, 64u);
+    const uint32_t top = row + (keep_base << 4);
+    const uint4 fA = lds128(top + (lane << 4)), fB = lds128(top + (lane << 4) + 512u);
+    const uint32_t aA = fA.x, lA = fA.y, rA = fA.z, aB = fB.x, lB = fB.y, rB = fB.z;
+    const uint32_t bitA = fA.w & (0u - fA.w), bitB = fB.w & (0u - fB.w);      // (0 for a frame without values: its child below is "wiped")
+    const uint32_t cA = fA.w ^ bitA, cB = fB.w ^ bitB;
+    const uint32_t naA = aA | bitA, nlA = (lA | bitA) << 1, nrA = (rA | bitA) >> 1;
+    const uint32_t naB = aB | bitB, nlB = (lB | bitB) << 1, nrB = (rB | bitB) >> 1;
+    // forward check over the L - LVL + 1 later variables; all ones <=> some domain is empty (a padding frame has a = all ones)
+    const bool passA = queens_rows_occupied<L - LVL + 1>(naA, nlA, nrA) != 0xFFFFFFFFu;
+    const bool passB = queens_rows_occupied<L - LVL + 1>(naB, nlB, nrB) != 0xFFFFFFFFu;
+    const uint32_t keepA = __ballot_sync(0xFFFFFFFFu, cA != 0u), keepB = __ballot_sync(0xFFFFFFFFu, cB != 0u);
+    const uint32_t nkA = __popc(keepA);
+    if (cA) sts128(top + (__popc(keepA & lt) << 4), aA, lA, rA, cA);
+    if (cB) sts128(top + (nkA << 4) + (__popc(keepB & lt) << 4), aB, lB, rB, cB);
+    const uint32_t c_new = keep_base + nkA + __popc(keepB);
+    const uint32_t dA = nor3(naA, nlA, nrA), dB = nor3(naB, nlB, nrB);
+    if constexpr (LVL == L - 1) {
+        // The children hold variable N-2.  Two columns are free there, so a child has at most two values: both are
+        // tried right here instead of going through a bucket of their own.  Each value is a node; what it leaves
+        // to the last variable (at most the other free column) is a node and a solution per value.
+        const uint32_t eA = passA ? dA : 0u, eB = passB ? dB : 0u;
+        const uint32_t bA1 = eA & (0u - eA), bA2 = eA ^ bA1, bB1 = eB & (0u - eB), bB2 = eB ^ bB1;
+        const uint32_t fA1 = nor3(naA | bA1, (nlA | bA1) << 1, (nrA | bA1) >> 1), fA2 = nor3(naA | bA2, (nlA | bA2) << 1, (nrA | bA2) >> 1);
+        const uint32_t fB1 = nor3(naB | bB1, (nlB | bB1) << 1, (nrB | bB1) >> 1), fB2 = nor3(naB | bB2, (nlB | bB2) << 1, (nrB | bB2) >> 1);
+        S.tot_sols += (bA1 ? __popc(fA1) : 0) + (bA2 ? __popc(fA2) : 0) + (bB1 ? __popc(fB1) : 0) + (bB2 ? __popc(fB2) : 0);
+        S.tot_lane_nodes += __popc(eA) + __popc(eB);
+        pk += (c_new - c) << SH;
+    } else {
+        constexpr int SH1 = ((LVL + 1) & 3) * 8;
+        const uint32_t kidsA = __ballot_sync(0xFFFFFFFFu, passA), kidsB = __ballot_sync(0xFFFFFFFFu, passB);
+        uint32_t& pk1 = LVL + 1 < 4 ? S.pk_lo : S.pk_hi;
+        pk += (c_new - c) << SH;                                   // (before pk1 is read: the two may be the same word)
+        const uint32_t c1 = (pk1 >> SH1) & 0xFFu;
+        const uint32_t nA = __popc(kidsA);
+        const uint32_t ntop = row + kQueensBucketCap * 16u + (c1 << 4);
+        if (passA) sts128(ntop + (__popc(kidsA & lt) << 4), naA, nlA, nrA, dA);
+        if (passB) sts128(ntop + (nA << 4) + (__popc(kidsB & lt) << 4), naB, nlB, nrB, dB);
+        pk1 += (nA + __popc(kidsB)) << SH1;
+    }
+    __syncwarp();
+}
+
+template <int L>
+__global__ void __launch_bounds__(kQueensBucketMaxWarps * 32)
+k_queens_bucket_t(QueensLaneArgs A) {
+    static_assert(L >= 1 && L <= 8, "a byte per bucket in two words");
+    extern __shared__ uint4 qb_frames[];
+    const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint32_t lt = (1u << lane) - 1u;
+    const uint32_t hi = ~((1u << A.n) - 1u);
+    constexpr uint32_t per_warp = (uint32_t)L * kQueensBucketCap * 16u;
+    const uint32_t bbase = (uint32_t)__cvta_generic_to_shared(qb_frames) + wib * per_warp;
+    uint32_t pf_n = 0;                                           // records prefetched into pf0 / pf1 (in flight or landed)
+    uint4 pf0 = make_uint4(0u, 0u, 0u, 0u), pf1 = pf0;
+    const unsigned long long n_found = *A.n_records;
+    const unsigned long long n_rec = n_found < A.record_cap ? n_found : A.record_cap;   // overflow: the host grows the list and reruns
+    const unsigned long long total_warps = (unsigned long long)gridDim.x * (blockDim.x >> 5);
+    const uint32_t fair_share = (uint32_t)min((n_rec + total_warps - 1) / total_warps, 64ull);
+    QueensTripState S = {0u, 0u, 0ull, 0ull, 0ull};
+    unsigned long long chunk_pos = 0, chunk_end = 0;
+    bool exhausted = false;
+
+    for (;;) {
+        // deepest bucket that holds 64 frames
+        const uint32_t big_hi = L > 4 ? (S.pk_hi & 0x40404040u) : 0u, big_lo = S.pk_lo & 0x40404040u;
+        int lvl;
+        if (big_hi) lvl = 4 + ((31 - __clz((int)big_hi)) >> 3);
+        else if (big_lo) lvl = (31 - __clz((int)big_lo)) >> 3;
+        else {
+            // claims the next chunk of the record list if need be and starts the loads of up to 64 records of it: they
+            // stay in flight (two uint4 registers per lane) while the warp works through the records it has
+            auto prefetch = [&]() {
+                if (exhausted) return;
+                if (chunk_pos >= chunk_end) {
+                    unsigned long long base = 0;
+                    uint32_t size = 0;
+                    if (lane == 0) {
+                        const unsigned long long cur = *(volatile unsigned long long*)A.cursor;
+                        const unsigned long long remaining = cur < n_rec ? n_rec - cur : 0;
+                        size = (uint32_t)min(max(remaining / (4ull * total_warps), (unsigned long long)max(fair_share, 1u)), 256ull);
+                        base = atomicAdd(A.cursor, (unsigned long long)size);
+                    }
+                    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                    size = __shfl_sync(0xFFFFFFFFu, size, 0);
+                    chunk_pos = base;
+                    chunk_end = min(base + size, n_rec);
+                    if (base >= n_rec) { exhausted = true; chunk_end = chunk_pos; return; }
+                }
+                pf_n = (uint32_t)min(chunk_end - chunk_pos, 64ull);
+                if (lane < pf_n) pf0 = __ldg(A.records + chunk_pos + lane);
+                if (lane + 32u < pf_n) pf1 = __ldg(A.records + chunk_pos + lane + 32);
+                chunk_pos += pf_n;
+            };
+            if (pf_n == 0u) prefetch();
+            if (pf_n != 0u) {
+                const uint32_t c0 = S.pk_lo & 0xFFu;
+                if (lane < pf_n) { const uint32_t a = pf0.y | hi; sts128(bbase + ((c0 + lane) << 4), a, pf0.z, pf0.w, ~(a | pf0.z | pf0.w)); }
+                if (lane + 32u < pf_n) { const uint32_t a = pf1.y | hi; sts128(bbase + ((c0 + lane + 32) << 4), a, pf1.z, pf1.w, ~(a | pf1.z | pf1.w)); }
+                S.pk_lo += pf_n;
+                pf_n = 0;
+                __syncwarp();
+                prefetch();
+                continue;
+            }
+            // the record list is spent: widen from the shallowest bucket that holds anything
+            if (S.pk_lo) lvl = (__ffs((int)S.pk_lo) - 1) >> 3;
+            else if (L > 4 && S.pk_hi) lvl = 4 + ((__ffs((int)S.pk_hi) - 1) >> 3);
+            else break;
+        }
+        switch (lvl) {
+#define DQ_QTRIP(V) case V: if constexpr (V < L) queens_trip<L, V>(S, bbase, lane, lt); break;
+            DQ_QTRIP(0) DQ_QTRIP(1) DQ_QTRIP(2) DQ_QTRIP(3) DQ_QTRIP(4) DQ_QTRIP(5) DQ_QTRIP(6) DQ_QTRIP(7)
+#undef DQ_QTRIP
+            default: break;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        S.tot_sols += __shfl_down_sync(0xFFFFFFFFu, S.tot_sols, o);
+        S.tot_lane_nodes += __shfl_down_sync(0xFFFFFFFFu, S.tot_lane_nodes, o);
+    }
+    if (lane == 0) {
+        atomicAdd(A.totals + 0, S.tot_sols);
+        atomicAdd(A.dfs_nodes, S.tot_sols + S.tot_lane_nodes + S.trip_nodes);
+    }
+}
+
+
 }  // namespace dq
