@@ -361,10 +361,16 @@ static int solve_queens_lane(dq_model* m, const dq_tree_opts* opts, dq_tree_resu
     const size_t per_warp = (size_t)(N - 2 - K) * kQueensBucketCap * sizeof(uint4) + kQueensStageBytes;
     // up to eight buckets: the kernel compiled for exactly that many (static levels, packed counts); more: the general one
     typedef void (*BucketKernel)(QueensLaneArgs);
-    static const BucketKernel kBucketKernels[9] = {nullptr, k_queens_bucket_t<1>, k_queens_bucket_t<2>, k_queens_bucket_t<3>, k_queens_bucket_t<4>,
-                                                   k_queens_bucket_t<5>, k_queens_bucket_t<6>, k_queens_bucket_t<7>, k_queens_bucket_t<8>};
+    // [0]: plain rows; [1]: rows in shifted frames (left shifts only), exact while N + 2 (buckets) <= 32
+    static const BucketKernel kBucketKernels[2][9] = {
+        {nullptr, k_queens_bucket_t<1, false>, k_queens_bucket_t<2, false>, k_queens_bucket_t<3, false>, k_queens_bucket_t<4, false>,
+         k_queens_bucket_t<5, false>, k_queens_bucket_t<6, false>, k_queens_bucket_t<7, false>, k_queens_bucket_t<8, false>},
+        {nullptr, k_queens_bucket_t<1, true>, k_queens_bucket_t<2, true>, k_queens_bucket_t<3, true>, k_queens_bucket_t<4, true>,
+         k_queens_bucket_t<5, true>, k_queens_bucket_t<6, true>, k_queens_bucket_t<7, true>, k_queens_bucket_t<8, true>}};
     static const bool general_only = getenv("DQ_QUEENS_GENERAL") != nullptr;
-    const BucketKernel bucket_kernel = (N - 2 - K <= 8 && !general_only) ? kBucketKernels[N - 2 - K] : k_queens_bucket;
+    static const bool plain_rows = getenv("DQ_QUEENS_PLAIN_ROWS") != nullptr;
+    const int n_buckets = N - 2 - K;
+    const BucketKernel bucket_kernel = (n_buckets <= 8 && !general_only) ? kBucketKernels[(N + 2 * n_buckets <= 32 && !plain_rows) ? 1 : 0][n_buckets] : k_queens_bucket;
     {
         int best = 0;
         for (int w = 2; w <= kQueensBucketMaxWarps; w++) {

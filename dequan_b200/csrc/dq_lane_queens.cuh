@@ -460,10 +460,33 @@ __device__ __forceinline__ uint32_t nor3(uint32_t a, uint32_t b, uint32_t c) {
     return d;
 }
 
-template <int L, int LVL>
-__device__ __forceinline__ void queens_trip(QueensTripState& S, const uint32_t bbase, const uint32_t lane, const uint32_t lt) {
+// The forward check with every row in its own shifted frame: row j (the variable j+1 places on) is full when
+//     (na << j | 2^j - 1)  |  nl << 2j  |  nr        is all ones
+// — the same test as na | nl << j | nr >> j moved j bits up, so that no operand shifts right: the two left shifts are
+// multiplications by constants (IMAD, the FMA pipe) and the ALU pipe, the one that bounds this kernel, is left with one
+// LOP3 per row and the maximum.  Exact while no board bit of nl << 2j leaves the word: N + 2 (ROWS - 1) <= 32.
+// ls = l | value bit (nl before its shift).
+// The low ones are the addend of the first multiplication; they come in registers the compiler cannot see through
+// (QueensLowOnes), or it would split the addition off as one more LOP3.
+struct QueensLowOnes { uint32_t v[9]; };
+__device__ __forceinline__ uint32_t mad_lo(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+template <int ROWS>
+__device__ __forceinline__ uint32_t queens_rows_occupied_up(uint32_t na, uint32_t ls, uint32_t nr, const QueensLowOnes& ones) {
+    uint32_t m = na | (ls * 2u) | nr;
+#pragma unroll
+    for (int j = 1; j < ROWS; j++) m = max(m, mad_lo(na, 1u << j, ones.v[j]) | (ls * (2u << (2 * j))) | nr);
+    return m;
+}
+
+template <int L, int LVL, bool UP>
+__device__ __forceinline__ void queens_trip(QueensTripState& S, const uint32_t bbase, const uint32_t lane, const uint32_t rank_mul, const QueensLowOnes& ones) {
     constexpr uint32_t kRow = (uint32_t)LVL * kQueensBucketCap * 16u;
     constexpr int SH = (LVL & 3) * 8;
+    constexpr int ROWS = L - LVL + 1;                            // later variables to check
     uint32_t& pk = LVL < 4 ? S.pk_lo : S.pk_hi;
     const uint32_t c = (pk >> SH) & 0xFFu;
     const uint32_t row = bbase + kRow;
@@ -481,16 +504,19 @@ __device__ __forceinline__ void queens_trip(QueensTripState& S, const uint32_t b
     const uint4 fA = lds128(top + (lane << 4)), fB = lds128(top + (lane << 4) + 512u);
     const uint32_t aA = fA.x, lA = fA.y, rA = fA.z, aB = fB.x, lB = fB.y, rB = fB.z;
     const uint32_t bitA = fA.w & (0u - fA.w), bitB = fB.w & (0u - fB.w);      // (0 for a frame without values: its child below is "wiped")
-    const uint32_t cA = fA.w ^ bitA, cB = fB.w ^ bitB;
-    const uint32_t naA = aA | bitA, nlA = (lA | bitA) << 1, nrA = (rA | bitA) >> 1;
-    const uint32_t naB = aB | bitB, nlB = (lB | bitB) << 1, nrB = (rB | bitB) >> 1;
-    // forward check over the L - LVL + 1 later variables; all ones <=> some domain is empty (a padding frame has a = all ones)
-    const bool passA = queens_rows_occupied<L - LVL + 1>(naA, nlA, nrA) != 0xFFFFFFFFu;
-    const bool passB = queens_rows_occupied<L - LVL + 1>(naB, nlB, nrB) != 0xFFFFFFFFu;
+    // the value is in none of a, l, r (it came out of their complement): the unions are sums (IMAD, not LOP3)
+    const uint32_t cA = fA.w - bitA, cB = fB.w - bitB;
+    const uint32_t naA = aA + bitA, lsA = lA + bitA, nrA = (rA + bitA) >> 1;
+    const uint32_t naB = aB + bitB, lsB = lB + bitB, nrB = (rB + bitB) >> 1;
+    const uint32_t nlA = lsA * 2u, nlB = lsB * 2u;
+    // all ones <=> some later domain is empty (a padding frame has a = all ones)
+    const bool passA = (UP ? queens_rows_occupied_up<ROWS>(naA, lsA, nrA, ones) : queens_rows_occupied<ROWS>(naA, nlA, nrA)) != 0xFFFFFFFFu;
+    const bool passB = (UP ? queens_rows_occupied_up<ROWS>(naB, lsB, nrB, ones) : queens_rows_occupied<ROWS>(naB, nlB, nrB)) != 0xFFFFFFFFu;
+    // rank of a lane among the set lanes of a ballot: popc(ballot << (32 - lane)), the shift a multiplication (rank_mul = 2^(32-lane), 0 for lane 0)
     const uint32_t keepA = __ballot_sync(0xFFFFFFFFu, cA != 0u), keepB = __ballot_sync(0xFFFFFFFFu, cB != 0u);
     const uint32_t nkA = __popc(keepA);
-    if (cA) sts128(top + (__popc(keepA & lt) << 4), aA, lA, rA, cA);
-    if (cB) sts128(top + (nkA << 4) + (__popc(keepB & lt) << 4), aB, lB, rB, cB);
+    if (cA) sts128(top + (__popc(keepA * rank_mul) << 4), aA, lA, rA, cA);
+    if (cB) sts128(top + (nkA << 4) + (__popc(keepB * rank_mul) << 4), aB, lB, rB, cB);
     const uint32_t c_new = keep_base + nkA + __popc(keepB);
     const uint32_t dA = nor3(naA, nlA, nrA), dB = nor3(naB, nlB, nrB);
     if constexpr (LVL == L - 1) {
@@ -498,9 +524,9 @@ __device__ __forceinline__ void queens_trip(QueensTripState& S, const uint32_t b
         // tried right here instead of going through a bucket of their own.  Each value is a node; what it leaves
         // to the last variable (at most the other free column) is a node and a solution per value.
         const uint32_t eA = passA ? dA : 0u, eB = passB ? dB : 0u;
-        const uint32_t bA1 = eA & (0u - eA), bA2 = eA ^ bA1, bB1 = eB & (0u - eB), bB2 = eB ^ bB1;
-        const uint32_t fA1 = nor3(naA | bA1, (nlA | bA1) << 1, (nrA | bA1) >> 1), fA2 = nor3(naA | bA2, (nlA | bA2) << 1, (nrA | bA2) >> 1);
-        const uint32_t fB1 = nor3(naB | bB1, (nlB | bB1) << 1, (nrB | bB1) >> 1), fB2 = nor3(naB | bB2, (nlB | bB2) << 1, (nrB | bB2) >> 1);
+        const uint32_t bA1 = eA & (0u - eA), bA2 = eA - bA1, bB1 = eB & (0u - eB), bB2 = eB - bB1;
+        const uint32_t fA1 = nor3(naA + bA1, (nlA + bA1) * 2u, (nrA + bA1) >> 1), fA2 = nor3(naA + bA2, (nlA + bA2) * 2u, (nrA + bA2) >> 1);
+        const uint32_t fB1 = nor3(naB + bB1, (nlB + bB1) * 2u, (nrB + bB1) >> 1), fB2 = nor3(naB + bB2, (nlB + bB2) * 2u, (nrB + bB2) >> 1);
         S.tot_sols += (bA1 ? __popc(fA1) : 0) + (bA2 ? __popc(fA2) : 0) + (bB1 ? __popc(fB1) : 0) + (bB2 ? __popc(fB2) : 0);
         S.tot_lane_nodes += __popc(eA) + __popc(eB);
         pk += (c_new - c) << SH;
@@ -512,20 +538,20 @@ __device__ __forceinline__ void queens_trip(QueensTripState& S, const uint32_t b
         const uint32_t c1 = (pk1 >> SH1) & 0xFFu;
         const uint32_t nA = __popc(kidsA);
         const uint32_t ntop = row + kQueensBucketCap * 16u + (c1 << 4);
-        if (passA) sts128(ntop + (__popc(kidsA & lt) << 4), naA, nlA, nrA, dA);
-        if (passB) sts128(ntop + (nA << 4) + (__popc(kidsB & lt) << 4), naB, nlB, nrB, dB);
+        if (passA) sts128(ntop + (__popc(kidsA * rank_mul) << 4), naA, nlA, nrA, dA);
+        if (passB) sts128(ntop + (nA << 4) + (__popc(kidsB * rank_mul) << 4), naB, nlB, nrB, dB);
         pk1 += (nA + __popc(kidsB)) << SH1;
     }
     __syncwarp();
 }
 
-template <int L>
+template <int L, bool UP>
 __global__ void __launch_bounds__(kQueensBucketMaxWarps * 32)
 k_queens_bucket_t(QueensLaneArgs A) {
     static_assert(L >= 1 && L <= 8, "a byte per bucket in two words");
     extern __shared__ uint4 qb_frames[];
     const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const uint32_t lt = (1u << lane) - 1u;
+    const uint32_t rank_mul = lane ? 1u << (32u - lane) : 0u;
     const uint32_t hi = ~((1u << A.n) - 1u);
     constexpr uint32_t per_warp = (uint32_t)L * kQueensBucketCap * 16u;
     const uint32_t bbase = (uint32_t)__cvta_generic_to_shared(qb_frames) + wib * per_warp;
@@ -536,6 +562,9 @@ k_queens_bucket_t(QueensLaneArgs A) {
     const unsigned long long total_warps = (unsigned long long)gridDim.x * (blockDim.x >> 5);
     const uint32_t fair_share = (uint32_t)min((n_rec + total_warps - 1) / total_warps, 64ull);
     QueensTripState S = {0u, 0u, 0ull, 0ull, 0ull};
+    QueensLowOnes ones;
+#pragma unroll
+    for (int j = 0; j < 9; j++) asm volatile("mov.u32 %0, %1;" : "=r"(ones.v[j]) : "r"((1u << j) - 1u));
     unsigned long long chunk_pos = 0, chunk_end = 0;
     bool exhausted = false;
 
@@ -559,8 +588,10 @@ k_queens_bucket_t(QueensLaneArgs A) {
                         size = (uint32_t)min(max(remaining / (4ull * total_warps), (unsigned long long)max(fair_share, 1u)), 256ull);
                         base = atomicAdd(A.cursor, (unsigned long long)size);
                     }
-                    base = __shfl_sync(0xFFFFFFFFu, base, 0);
-                    size = __shfl_sync(0xFFFFFFFFu, size, 0);
+                    // (lane 0's values to every lane through warp reductions: their results are warp-uniform for the compiler
+                    // too, which keeps the bucket counts that pf_n feeds on the uniform datapath)
+                    base = (unsigned long long)__reduce_or_sync(0xFFFFFFFFu, (uint32_t)base) | ((unsigned long long)__reduce_or_sync(0xFFFFFFFFu, (uint32_t)(base >> 32)) << 32);
+                    size = __reduce_or_sync(0xFFFFFFFFu, size);
                     chunk_pos = base;
                     chunk_end = min(base + size, n_rec);
                     if (base >= n_rec) { exhausted = true; chunk_end = chunk_pos; return; }
@@ -587,7 +618,7 @@ k_queens_bucket_t(QueensLaneArgs A) {
             else break;
         }
         switch (lvl) {
-#define DQ_QTRIP(V) case V: if constexpr (V < L) queens_trip<L, V>(S, bbase, lane, lt); break;
+#define DQ_QTRIP(V) case V: if constexpr (V < L) queens_trip<L, V, UP>(S, bbase, lane, rank_mul, ones); break;
             DQ_QTRIP(0) DQ_QTRIP(1) DQ_QTRIP(2) DQ_QTRIP(3) DQ_QTRIP(4) DQ_QTRIP(5) DQ_QTRIP(6) DQ_QTRIP(7)
 #undef DQ_QTRIP
             default: break;
