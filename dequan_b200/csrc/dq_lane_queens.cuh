@@ -442,13 +442,19 @@ k_queens_bucket(QueensLaneArgs A) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// The same search with the number of buckets L (<= 8) a template parameter.  Everything the kernel above finds out per
-// trip is then a compile-time constant of the code that serves one level: the bucket's address, the number of later
-// variables to check (no second dispatch for the rows), which count it updates.  The counts live packed, a byte per
-// bucket, in two warp-uniform words (bit 6 of a byte = "holds 64 frames"), so choosing the level and all the count
-// arithmetic run on the uniform datapath with no shuffle in the trip's dependency chain.
+// The same search with the number of buckets L (<= 8) a template parameter, which makes everything the kernel above
+// finds out per trip a compile-time constant of the code that serves one level: the bucket's address, its count (a
+// register of its own), the number of later variables to check (no dispatch on it).  The deepest-first rule becomes
+// control flow: after a trip at level v only bucket v+1 can have reached 64 frames, so the code of level v falls
+// into the code of level v+1 when it has, and repeats itself while its own bucket still holds 64 (queens_run_from) —
+// no level choice, no jump table, no shuffle in the trip's dependency chain.
+//
+// This kernel is bound by the ALU pipe (LOP3 / SHF / ISETP / VIMNMX: 16 lanes per clock and SM quarter, the INT32
+// roofline of bench.py), with the FMA pipe's integer multiply-add (IMAD, another 16 lanes per clock) idle next to it.
+// So what can be a multiplication is one: left shifts, the rank of a lane in a ballot (popc(ballot * 2^(32-lane))),
+// and unions of disjoint masks (sums).
 struct QueensTripState {
-    uint32_t pk_lo, pk_hi;                 // frames per bucket, a byte each: buckets 0-3, 4-7
+    uint32_t cnt[8];                       // frames per bucket (warp-uniform)
     unsigned long long trip_nodes;         // warp-uniform: one node per frame taken (AssignVar of its next value)
     unsigned long long tot_sols;           // per lane: values of the last variable (a node and a solution each)
     unsigned long long tot_lane_nodes;     // per lane: values tried for variable N-2
@@ -459,65 +465,64 @@ __device__ __forceinline__ uint32_t nor3(uint32_t a, uint32_t b, uint32_t c) {
     asm("lop3.b32 %0, %1, %2, %3, 0x01;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     return d;
 }
-
-// The forward check with every row in its own shifted frame: row j (the variable j+1 places on) is full when
-//     (na << j | 2^j - 1)  |  nl << 2j  |  nr        is all ones
-// — the same test as na | nl << j | nr >> j moved j bits up, so that no operand shifts right: the two left shifts are
-// multiplications by constants (IMAD, the FMA pipe) and the ALU pipe, the one that bounds this kernel, is left with one
-// LOP3 per row and the maximum.  Exact while no board bit of nl << 2j leaves the word: N + 2 (ROWS - 1) <= 32.
-// ls = l | value bit (nl before its shift).
-// The low ones are the addend of the first multiplication; they come in registers the compiler cannot see through
-// (QueensLowOnes), or it would split the addition off as one more LOP3.
-struct QueensLowOnes { uint32_t v[9]; };
 __device__ __forceinline__ uint32_t mad_lo(uint32_t a, uint32_t b, uint32_t c) {
     uint32_t d;
     asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     return d;
 }
+
+// The forward check with every row in its own shifted frame: row j (the variable j+1 places on) is full when
+//     (na << j | 2^j - 1)  |  nl << 2j  |  nr        is all ones
+// — the same test as na | nl << j | nr >> j moved j bits up, so that no operand shifts right: the two left shifts are
+// multiplications, and the ALU pipe is left with one LOP3 per row and the maximum.  Exact while no board bit of
+// nl << 2j leaves the word: N + 2 (ROWS - 1) <= 32.  ls = l | value bit (nl before its shift).
+// The powers of two and the low ones of the first product come in registers whose values the compiler cannot see
+// (QueensRowConsts): knowing them it turns the multiply-add back into a shift-add (LEA) plus a LOP3 on the ALU pipe.
+struct QueensRowConsts { uint32_t pow[9], ones[9]; };
 template <int ROWS>
-__device__ __forceinline__ uint32_t queens_rows_occupied_up(uint32_t na, uint32_t ls, uint32_t nr, const QueensLowOnes& ones) {
+__device__ __forceinline__ uint32_t queens_rows_occupied_up(uint32_t na, uint32_t ls, uint32_t nr, const QueensRowConsts& rc) {
     uint32_t m = na | (ls * 2u) | nr;
 #pragma unroll
-    for (int j = 1; j < ROWS; j++) m = max(m, mad_lo(na, 1u << j, ones.v[j]) | (ls * (2u << (2 * j))) | nr);
+    for (int j = 1; j < ROWS; j++) m = max(m, mad_lo(na, rc.pow[j], rc.ones[j]) | (ls * (2u << (2 * j))) | nr);
     return m;
 }
 
-template <int L, int LVL, bool UP>
-__device__ __forceinline__ void queens_trip(QueensTripState& S, const uint32_t bbase, const uint32_t lane, const uint32_t rank_mul, const QueensLowOnes& ones) {
+template <int L, int LVL, bool UP, bool FULL>
+__device__ __forceinline__ void queens_trip(QueensTripState& S, const uint32_t bbase, const uint32_t lane, const uint32_t rank_mul, const QueensRowConsts& rc) {
     constexpr uint32_t kRow = (uint32_t)LVL * kQueensBucketCap * 16u;
-    constexpr int SH = (LVL & 3) * 8;
     constexpr int ROWS = L - LVL + 1;                            // later variables to check
-    uint32_t& pk = LVL < 4 ? S.pk_lo : S.pk_hi;
-    const uint32_t c = (pk >> SH) & 0xFFu;
+    const uint32_t c = S.cnt[LVL];
     const uint32_t row = bbase + kRow;
     uint32_t keep_base = c - 64u;
-    if (c < 64u) {
-        // a short trip (the tail of the warp's work): pads the bucket to 64 with frames that hold no value — every
-        // trip is then a full one, with no per-lane "is this slot in use" anywhere below
-        if (lane >= c) sts128(row + (lane << 4), 0xFFFFFFFFu, 0u, 0u, 0u);
-        if (lane + 32u >= c) sts128(row + ((lane + 32u) << 4), 0xFFFFFFFFu, 0u, 0u, 0u);
-        keep_base = 0u;
-        __syncwarp();
+    if constexpr (FULL) S.trip_nodes += 64u;
+    else {
+        if (c < 64u) {
+            // a short trip (the tail of the warp's work): pads the bucket to 64 with frames that hold no value — every
+            // trip is then a full one, with no per-lane "is this slot in use" anywhere below
+            if (lane >= c) sts128(row + (lane << 4), 0xFFFFFFFFu, 0u, 0u, 0u);
+            if (lane + 32u >= c) sts128(row + ((lane + 32u) << 4), 0xFFFFFFFFu, 0u, 0u, 0u);
+            keep_base = 0u;
+            __syncwarp();
+        }
+        S.trip_nodes += min(c, 64u);
     }
-    S.trip_nodes += min(c, 64u);
     const uint32_t top = row + (keep_base << 4);
     const uint4 fA = lds128(top + (lane << 4)), fB = lds128(top + (lane << 4) + 512u);
     const uint32_t aA = fA.x, lA = fA.y, rA = fA.z, aB = fB.x, lB = fB.y, rB = fB.z;
     const uint32_t bitA = fA.w & (0u - fA.w), bitB = fB.w & (0u - fB.w);      // (0 for a frame without values: its child below is "wiped")
-    // the value is in none of a, l, r (it came out of their complement): the unions are sums (IMAD, not LOP3)
+    // the value is in none of a, l, r (it came out of their complement): the unions are sums
     const uint32_t cA = fA.w - bitA, cB = fB.w - bitB;
     const uint32_t naA = aA + bitA, lsA = lA + bitA, nrA = (rA + bitA) >> 1;
     const uint32_t naB = aB + bitB, lsB = lB + bitB, nrB = (rB + bitB) >> 1;
     const uint32_t nlA = lsA * 2u, nlB = lsB * 2u;
     // all ones <=> some later domain is empty (a padding frame has a = all ones)
-    const bool passA = (UP ? queens_rows_occupied_up<ROWS>(naA, lsA, nrA, ones) : queens_rows_occupied<ROWS>(naA, nlA, nrA)) != 0xFFFFFFFFu;
-    const bool passB = (UP ? queens_rows_occupied_up<ROWS>(naB, lsB, nrB, ones) : queens_rows_occupied<ROWS>(naB, nlB, nrB)) != 0xFFFFFFFFu;
-    // rank of a lane among the set lanes of a ballot: popc(ballot << (32 - lane)), the shift a multiplication (rank_mul = 2^(32-lane), 0 for lane 0)
+    const bool passA = (UP ? queens_rows_occupied_up<ROWS>(naA, lsA, nrA, rc) : queens_rows_occupied<ROWS>(naA, nlA, nrA)) != 0xFFFFFFFFu;
+    const bool passB = (UP ? queens_rows_occupied_up<ROWS>(naB, lsB, nrB, rc) : queens_rows_occupied<ROWS>(naB, nlB, nrB)) != 0xFFFFFFFFu;
     const uint32_t keepA = __ballot_sync(0xFFFFFFFFu, cA != 0u), keepB = __ballot_sync(0xFFFFFFFFu, cB != 0u);
     const uint32_t nkA = __popc(keepA);
     if (cA) sts128(top + (__popc(keepA * rank_mul) << 4), aA, lA, rA, cA);
     if (cB) sts128(top + (nkA << 4) + (__popc(keepB * rank_mul) << 4), aB, lB, rB, cB);
-    const uint32_t c_new = keep_base + nkA + __popc(keepB);
+    S.cnt[LVL] = keep_base + nkA + __popc(keepB);
     const uint32_t dA = nor3(naA, nlA, nrA), dB = nor3(naB, nlB, nrB);
     if constexpr (LVL == L - 1) {
         // The children hold variable N-2.  Two columns are free there, so a child has at most two values: both are
@@ -529,26 +534,34 @@ __device__ __forceinline__ void queens_trip(QueensTripState& S, const uint32_t b
         const uint32_t fB1 = nor3(naB + bB1, (nlB + bB1) * 2u, (nrB + bB1) >> 1), fB2 = nor3(naB + bB2, (nlB + bB2) * 2u, (nrB + bB2) >> 1);
         S.tot_sols += (bA1 ? __popc(fA1) : 0) + (bA2 ? __popc(fA2) : 0) + (bB1 ? __popc(fB1) : 0) + (bB2 ? __popc(fB2) : 0);
         S.tot_lane_nodes += __popc(eA) + __popc(eB);
-        pk += (c_new - c) << SH;
     } else {
-        constexpr int SH1 = ((LVL + 1) & 3) * 8;
         const uint32_t kidsA = __ballot_sync(0xFFFFFFFFu, passA), kidsB = __ballot_sync(0xFFFFFFFFu, passB);
-        uint32_t& pk1 = LVL + 1 < 4 ? S.pk_lo : S.pk_hi;
-        pk += (c_new - c) << SH;                                   // (before pk1 is read: the two may be the same word)
-        const uint32_t c1 = (pk1 >> SH1) & 0xFFu;
+        const uint32_t c1 = S.cnt[LVL + 1];
         const uint32_t nA = __popc(kidsA);
         const uint32_t ntop = row + kQueensBucketCap * 16u + (c1 << 4);
         if (passA) sts128(ntop + (__popc(kidsA * rank_mul) << 4), naA, nlA, nrA, dA);
         if (passB) sts128(ntop + (nA << 4) + (__popc(kidsB * rank_mul) << 4), naB, nlB, nrB, dB);
-        pk1 += (nA + __popc(kidsB)) << SH1;
+        S.cnt[LVL + 1] = c1 + nA + __popc(kidsB);
     }
     __syncwarp();
+}
+
+// Entered with 64 frames or more in bucket LVL and fewer in every deeper one; returns once no bucket from LVL down
+// holds 64.
+template <int L, int LVL, bool UP>
+__device__ __forceinline__ void queens_run_from(QueensTripState& S, const uint32_t bbase, const uint32_t lane, const uint32_t rank_mul, const QueensRowConsts& rc) {
+    do {
+        queens_trip<L, LVL, UP, true>(S, bbase, lane, rank_mul, rc);
+        if constexpr (LVL + 1 < L) {
+            if (S.cnt[LVL + 1] >= 64u) queens_run_from<L, LVL + 1, UP>(S, bbase, lane, rank_mul, rc);
+        }
+    } while (S.cnt[LVL] >= 64u);
 }
 
 template <int L, bool UP>
 __global__ void __launch_bounds__(kQueensBucketMaxWarps * 32)
 k_queens_bucket_t(QueensLaneArgs A) {
-    static_assert(L >= 1 && L <= 8, "a byte per bucket in two words");
+    static_assert(L >= 1 && L <= 8, "one count register per bucket");
     extern __shared__ uint4 qb_frames[];
     const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t rank_mul = lane ? 1u << (32u - lane) : 0u;
@@ -561,64 +574,67 @@ k_queens_bucket_t(QueensLaneArgs A) {
     const unsigned long long n_rec = n_found < A.record_cap ? n_found : A.record_cap;   // overflow: the host grows the list and reruns
     const unsigned long long total_warps = (unsigned long long)gridDim.x * (blockDim.x >> 5);
     const uint32_t fair_share = (uint32_t)min((n_rec + total_warps - 1) / total_warps, 64ull);
-    QueensTripState S = {0u, 0u, 0ull, 0ull, 0ull};
-    QueensLowOnes ones;
+    QueensTripState S;
 #pragma unroll
-    for (int j = 0; j < 9; j++) asm volatile("mov.u32 %0, %1;" : "=r"(ones.v[j]) : "r"((1u << j) - 1u));
+    for (int i = 0; i < 8; i++) S.cnt[i] = 0u;
+    S.trip_nodes = 0ull; S.tot_sols = 0ull; S.tot_lane_nodes = 0ull;
+    QueensRowConsts rc;
+    const uint32_t zero = (uint32_t)A.n >> 8;                    // 0, but not to the compiler
+#pragma unroll
+    for (int j = 0; j < 9; j++) { rc.pow[j] = (1u << j) + zero; rc.ones[j] = rc.pow[j] - 1u; }
     unsigned long long chunk_pos = 0, chunk_end = 0;
     bool exhausted = false;
 
     for (;;) {
-        // deepest bucket that holds 64 frames
-        const uint32_t big_hi = L > 4 ? (S.pk_hi & 0x40404040u) : 0u, big_lo = S.pk_lo & 0x40404040u;
-        int lvl;
-        if (big_hi) lvl = 4 + ((31 - __clz((int)big_hi)) >> 3);
-        else if (big_lo) lvl = (31 - __clz((int)big_lo)) >> 3;
-        else {
-            // claims the next chunk of the record list if need be and starts the loads of up to 64 records of it: they
-            // stay in flight (two uint4 registers per lane) while the warp works through the records it has
-            auto prefetch = [&]() {
-                if (exhausted) return;
-                if (chunk_pos >= chunk_end) {
-                    unsigned long long base = 0;
-                    uint32_t size = 0;
-                    if (lane == 0) {
-                        const unsigned long long cur = *(volatile unsigned long long*)A.cursor;
-                        const unsigned long long remaining = cur < n_rec ? n_rec - cur : 0;
-                        size = (uint32_t)min(max(remaining / (4ull * total_warps), (unsigned long long)max(fair_share, 1u)), 256ull);
-                        base = atomicAdd(A.cursor, (unsigned long long)size);
-                    }
-                    // (lane 0's values to every lane through warp reductions: their results are warp-uniform for the compiler
-                    // too, which keeps the bucket counts that pf_n feeds on the uniform datapath)
-                    base = (unsigned long long)__reduce_or_sync(0xFFFFFFFFu, (uint32_t)base) | ((unsigned long long)__reduce_or_sync(0xFFFFFFFFu, (uint32_t)(base >> 32)) << 32);
-                    size = __reduce_or_sync(0xFFFFFFFFu, size);
-                    chunk_pos = base;
-                    chunk_end = min(base + size, n_rec);
-                    if (base >= n_rec) { exhausted = true; chunk_end = chunk_pos; return; }
+        if (S.cnt[0] >= 64u) { queens_run_from<L, 0, UP>(S, bbase, lane, rank_mul, rc); continue; }
+        // No bucket holds 64 frames.
+        // claims the next chunk of the record list if need be and starts the loads of up to 64 records of it: they
+        // stay in flight (two uint4 registers per lane) while the warp works through the records it has
+        auto prefetch = [&]() {
+            if (exhausted) return;
+            if (chunk_pos >= chunk_end) {
+                unsigned long long base = 0;
+                uint32_t size = 0;
+                if (lane == 0) {
+                    const unsigned long long cur = *(volatile unsigned long long*)A.cursor;
+                    const unsigned long long remaining = cur < n_rec ? n_rec - cur : 0;
+                    size = (uint32_t)min(max(remaining / (4ull * total_warps), (unsigned long long)max(fair_share, 1u)), 256ull);
+                    base = atomicAdd(A.cursor, (unsigned long long)size);
                 }
-                pf_n = (uint32_t)min(chunk_end - chunk_pos, 64ull);
-                if (lane < pf_n) pf0 = __ldg(A.records + chunk_pos + lane);
-                if (lane + 32u < pf_n) pf1 = __ldg(A.records + chunk_pos + lane + 32);
-                chunk_pos += pf_n;
-            };
-            if (pf_n == 0u) prefetch();
-            if (pf_n != 0u) {
-                const uint32_t c0 = S.pk_lo & 0xFFu;
-                if (lane < pf_n) { const uint32_t a = pf0.y | hi; sts128(bbase + ((c0 + lane) << 4), a, pf0.z, pf0.w, ~(a | pf0.z | pf0.w)); }
-                if (lane + 32u < pf_n) { const uint32_t a = pf1.y | hi; sts128(bbase + ((c0 + lane + 32) << 4), a, pf1.z, pf1.w, ~(a | pf1.z | pf1.w)); }
-                S.pk_lo += pf_n;
-                pf_n = 0;
-                __syncwarp();
-                prefetch();
-                continue;
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                size = __shfl_sync(0xFFFFFFFFu, size, 0);
+                chunk_pos = base;
+                chunk_end = min(base + size, n_rec);
+                if (base >= n_rec) { exhausted = true; chunk_end = chunk_pos; return; }
             }
-            // the record list is spent: widen from the shallowest bucket that holds anything
-            if (S.pk_lo) lvl = (__ffs((int)S.pk_lo) - 1) >> 3;
-            else if (L > 4 && S.pk_hi) lvl = 4 + ((__ffs((int)S.pk_hi) - 1) >> 3);
-            else break;
+            pf_n = (uint32_t)min(chunk_end - chunk_pos, 64ull);
+            if (lane < pf_n) pf0 = __ldg(A.records + chunk_pos + lane);
+            if (lane + 32u < pf_n) pf1 = __ldg(A.records + chunk_pos + lane + 32);
+            chunk_pos += pf_n;
+        };
+        if (pf_n == 0u) prefetch();
+        if (pf_n != 0u) {
+            const uint32_t c0 = S.cnt[0];
+            if (lane < pf_n) { const uint32_t a = pf0.y | hi; sts128(bbase + ((c0 + lane) << 4), a, pf0.z, pf0.w, ~(a | pf0.z | pf0.w)); }
+            if (lane + 32u < pf_n) { const uint32_t a = pf1.y | hi; sts128(bbase + ((c0 + lane + 32) << 4), a, pf1.z, pf1.w, ~(a | pf1.z | pf1.w)); }
+            S.cnt[0] = c0 + pf_n;
+            pf_n = 0;
+            __syncwarp();
+            prefetch();
+            continue;
         }
+        // The record list is spent: the deepest bucket that holds 64 frames, else the shallowest that holds anything
+        // (short trips; this is the tail of the warp's work).
+        int lvl = -1;
+#pragma unroll
+        for (int v = L - 1; v >= 0; v--) if (lvl < 0 && S.cnt[v] >= 64u) lvl = v;
+        if (lvl < 0) {
+#pragma unroll
+            for (int v = 0; v < L; v++) if (lvl < 0 && S.cnt[v] != 0u) lvl = v;
+        }
+        if (lvl < 0) break;
         switch (lvl) {
-#define DQ_QTRIP(V) case V: if constexpr (V < L) queens_trip<L, V, UP>(S, bbase, lane, rank_mul, ones); break;
+#define DQ_QTRIP(V) case V: if constexpr (V < L) queens_trip<L, V, UP, false>(S, bbase, lane, rank_mul, rc); break;
             DQ_QTRIP(0) DQ_QTRIP(1) DQ_QTRIP(2) DQ_QTRIP(3) DQ_QTRIP(4) DQ_QTRIP(5) DQ_QTRIP(6) DQ_QTRIP(7)
 #undef DQ_QTRIP
             default: break;
@@ -633,6 +649,5 @@ k_queens_bucket_t(QueensLaneArgs A) {
         atomicAdd(A.dfs_nodes, S.tot_sols + S.tot_lane_nodes + S.trip_nodes);
     }
 }
-
 
 }  // namespace dq
