@@ -358,10 +358,10 @@ static int solve_queens_lane(dq_model* m, const dq_tree_opts* opts, dq_tree_resu
     // partition deal happens at depth <= 5 — so the split may go deeper than 32-bit keys would allow)
     // warps per CTA chosen so that the pools (buckets x 128 frames x 16 B + the staging buffer, per warp) pack an SM's shared memory best
     int bucket_warps = 4;
-    const size_t per_warp = (size_t)(N - 2 - K) * kQueensBucketCap * sizeof(uint4) + kQueensStageBytes;
-    // up to eight buckets: the kernel compiled for exactly that many (static levels, packed counts); more: the general one
+    // up to eight buckets (variables k+1 .. N-3; the records themselves stay in registers): the kernel compiled for exactly
+    // that many; more: the general one (variables k .. N-3)
     typedef void (*BucketKernel)(QueensLaneArgs);
-    // [0]: plain rows; [1]: rows in shifted frames (left shifts only), exact while N + 2 (buckets) <= 32
+    // [0]: plain rows; [1]: rows in shifted frames (left shifts only), exact while N + 2 (buckets + 1) <= 32
     static const BucketKernel kBucketKernels[2][9] = {
         {nullptr, k_queens_bucket_t<1, false>, k_queens_bucket_t<2, false>, k_queens_bucket_t<3, false>, k_queens_bucket_t<4, false>,
          k_queens_bucket_t<5, false>, k_queens_bucket_t<6, false>, k_queens_bucket_t<7, false>, k_queens_bucket_t<8, false>},
@@ -369,8 +369,10 @@ static int solve_queens_lane(dq_model* m, const dq_tree_opts* opts, dq_tree_resu
          k_queens_bucket_t<5, true>, k_queens_bucket_t<6, true>, k_queens_bucket_t<7, true>, k_queens_bucket_t<8, true>}};
     static const bool general_only = getenv("DQ_QUEENS_GENERAL") != nullptr;
     static const bool plain_rows = getenv("DQ_QUEENS_PLAIN_ROWS") != nullptr;
-    const int n_buckets = N - 2 - K;
-    const BucketKernel bucket_kernel = (n_buckets <= 8 && !general_only) ? kBucketKernels[(N + 2 * n_buckets <= 32 && !plain_rows) ? 1 : 0][n_buckets] : k_queens_bucket;
+    const bool compiled = N - 3 - K >= 1 && N - 3 - K <= 8 && !general_only;
+    const int n_buckets = compiled ? N - 3 - K : N - 2 - K;
+    const BucketKernel bucket_kernel = compiled ? kBucketKernels[(N + 2 * (n_buckets + 1) <= 32 && !plain_rows) ? 1 : 0][n_buckets] : k_queens_bucket;
+    const size_t per_warp = (size_t)n_buckets * kQueensBucketCap * sizeof(uint4) + kQueensStageBytes;
     {
         int best = 0;
         for (int w = 2; w <= kQueensBucketMaxWarps; w++) {

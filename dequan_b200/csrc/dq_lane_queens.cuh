@@ -478,7 +478,7 @@ __device__ __forceinline__ uint32_t mad_lo(uint32_t a, uint32_t b, uint32_t c) {
 // nl << 2j leaves the word: N + 2 (ROWS - 1) <= 32.  ls = l | value bit (nl before its shift).
 // The powers of two and the low ones of the first product come in registers whose values the compiler cannot see
 // (QueensRowConsts): knowing them it turns the multiply-add back into a shift-add (LEA) plus a LOP3 on the ALU pipe.
-struct QueensRowConsts { uint32_t pow[9], ones[9]; };
+struct QueensRowConsts { uint32_t pow[10], ones[10]; };
 template <int ROWS>
 __device__ __forceinline__ uint32_t queens_rows_occupied_up(uint32_t na, uint32_t ls, uint32_t nr, const QueensRowConsts& rc) {
     uint32_t m = na | (ls * 2u) | nr;
@@ -546,6 +546,32 @@ __device__ __forceinline__ void queens_trip(QueensTripState& S, const uint32_t b
     __syncwarp();
 }
 
+// The records themselves (depth k, variable k) never enter a bucket: a lane holds two of them in registers and tries
+// one value of each per trip until the warp's 64 are spent — no load, nothing to put back, children to bucket 0.
+// A spent record has no value bit: its "child" is nobody's.  (The nodes of this level are counted when the records
+// are taken: every value of a record's domain is tried exactly once.)
+struct QueensRecordRegs { uint32_t aA, lA, rA, cA, aB, lB, rB, cB; };
+
+template <int L, bool UP>
+__device__ __forceinline__ void queens_record_trip(QueensTripState& S, QueensRecordRegs& R, const uint32_t bbase, const uint32_t rank_mul, const QueensRowConsts& rc) {
+    constexpr int ROWS = L + 2;                                  // later variables to check
+    const uint32_t bitA = R.cA & (0u - R.cA), bitB = R.cB & (0u - R.cB);
+    R.cA -= bitA; R.cB -= bitB;
+    const uint32_t naA = R.aA + bitA, lsA = R.lA + bitA, nrA = (R.rA + bitA) >> 1;
+    const uint32_t naB = R.aB + bitB, lsB = R.lB + bitB, nrB = (R.rB + bitB) >> 1;
+    const uint32_t nlA = lsA * 2u, nlB = lsB * 2u;
+    const bool passA = bitA != 0u && (UP ? queens_rows_occupied_up<ROWS>(naA, lsA, nrA, rc) : queens_rows_occupied<ROWS>(naA, nlA, nrA)) != 0xFFFFFFFFu;
+    const bool passB = bitB != 0u && (UP ? queens_rows_occupied_up<ROWS>(naB, lsB, nrB, rc) : queens_rows_occupied<ROWS>(naB, nlB, nrB)) != 0xFFFFFFFFu;
+    const uint32_t kidsA = __ballot_sync(0xFFFFFFFFu, passA), kidsB = __ballot_sync(0xFFFFFFFFu, passB);
+    const uint32_t c0 = S.cnt[0];
+    const uint32_t nA = __popc(kidsA);
+    const uint32_t ntop = bbase + (c0 << 4);
+    if (passA) sts128(ntop + (__popc(kidsA * rank_mul) << 4), naA, nlA, nrA, nor3(naA, nlA, nrA));
+    if (passB) sts128(ntop + (nA << 4) + (__popc(kidsB * rank_mul) << 4), naB, nlB, nrB, nor3(naB, nlB, nrB));
+    S.cnt[0] = c0 + nA + __popc(kidsB);
+    __syncwarp();
+}
+
 // Entered with 64 frames or more in bucket LVL and fewer in every deeper one; returns once no bucket from LVL down
 // holds 64.
 template <int L, int LVL, bool UP>
@@ -581,48 +607,54 @@ k_queens_bucket_t(QueensLaneArgs A) {
     QueensRowConsts rc;
     const uint32_t zero = (uint32_t)A.n >> 8;                    // 0, but not to the compiler
 #pragma unroll
-    for (int j = 0; j < 9; j++) { rc.pow[j] = (1u << j) + zero; rc.ones[j] = rc.pow[j] - 1u; }
+    for (int j = 0; j < 10; j++) { rc.pow[j] = (1u << j) + zero; rc.ones[j] = rc.pow[j] - 1u; }
     unsigned long long chunk_pos = 0, chunk_end = 0;
     bool exhausted = false;
 
-    for (;;) {
-        if (S.cnt[0] >= 64u) { queens_run_from<L, 0, UP>(S, bbase, lane, rank_mul, rc); continue; }
-        // No bucket holds 64 frames.
-        // claims the next chunk of the record list if need be and starts the loads of up to 64 records of it: they
-        // stay in flight (two uint4 registers per lane) while the warp works through the records it has
-        auto prefetch = [&]() {
-            if (exhausted) return;
-            if (chunk_pos >= chunk_end) {
-                unsigned long long base = 0;
-                uint32_t size = 0;
-                if (lane == 0) {
-                    const unsigned long long cur = *(volatile unsigned long long*)A.cursor;
-                    const unsigned long long remaining = cur < n_rec ? n_rec - cur : 0;
-                    size = (uint32_t)min(max(remaining / (4ull * total_warps), (unsigned long long)max(fair_share, 1u)), 256ull);
-                    base = atomicAdd(A.cursor, (unsigned long long)size);
-                }
-                base = __shfl_sync(0xFFFFFFFFu, base, 0);
-                size = __shfl_sync(0xFFFFFFFFu, size, 0);
-                chunk_pos = base;
-                chunk_end = min(base + size, n_rec);
-                if (base >= n_rec) { exhausted = true; chunk_end = chunk_pos; return; }
+    QueensRecordRegs R = {0xFFFFFFFFu, 0u, 0u, 0u, 0xFFFFFFFFu, 0u, 0u, 0u};
+    // claims the next chunk of the record list if need be and starts the loads of up to 64 records of it: they
+    // stay in flight (two uint4 registers per lane) while the warp works through the records it has
+    auto prefetch = [&]() {
+        if (exhausted) return;
+        if (chunk_pos >= chunk_end) {
+            unsigned long long base = 0;
+            uint32_t size = 0;
+            if (lane == 0) {
+                const unsigned long long cur = *(volatile unsigned long long*)A.cursor;
+                const unsigned long long remaining = cur < n_rec ? n_rec - cur : 0;
+                size = (uint32_t)min(max(remaining / (4ull * total_warps), (unsigned long long)max(fair_share, 1u)), 256ull);
+                base = atomicAdd(A.cursor, (unsigned long long)size);
             }
-            pf_n = (uint32_t)min(chunk_end - chunk_pos, 64ull);
-            if (lane < pf_n) pf0 = __ldg(A.records + chunk_pos + lane);
-            if (lane + 32u < pf_n) pf1 = __ldg(A.records + chunk_pos + lane + 32);
-            chunk_pos += pf_n;
-        };
-        if (pf_n == 0u) prefetch();
-        if (pf_n != 0u) {
-            const uint32_t c0 = S.cnt[0];
-            if (lane < pf_n) { const uint32_t a = pf0.y | hi; sts128(bbase + ((c0 + lane) << 4), a, pf0.z, pf0.w, ~(a | pf0.z | pf0.w)); }
-            if (lane + 32u < pf_n) { const uint32_t a = pf1.y | hi; sts128(bbase + ((c0 + lane + 32) << 4), a, pf1.z, pf1.w, ~(a | pf1.z | pf1.w)); }
-            S.cnt[0] = c0 + pf_n;
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            size = __shfl_sync(0xFFFFFFFFu, size, 0);
+            chunk_pos = base;
+            chunk_end = min(base + size, n_rec);
+            if (base >= n_rec) { exhausted = true; chunk_end = chunk_pos; return; }
+        }
+        pf_n = (uint32_t)min(chunk_end - chunk_pos, 64ull);
+        if (lane < pf_n) pf0 = __ldg(A.records + chunk_pos + lane);
+        if (lane + 32u < pf_n) pf1 = __ldg(A.records + chunk_pos + lane + 32);
+        chunk_pos += pf_n;
+    };
+    prefetch();
+    for (;;) {
+        // (here no bucket holds 64 frames)
+        if (!__any_sync(0xFFFFFFFFu, (R.cA | R.cB) != 0u)) {
+            // the warp's records are spent: the next 64 (already loaded), and the loads of the 64 after them
+            if (pf_n == 0u) prefetch();
+            if (pf_n == 0u) break;                               // the list is spent as well
+            R.aA = 0xFFFFFFFFu; R.cA = 0u; R.aB = 0xFFFFFFFFu; R.cB = 0u;
+            if (lane < pf_n) { R.aA = pf0.y | hi; R.lA = pf0.z; R.rA = pf0.w; R.cA = ~(R.aA | R.lA | R.rA); }
+            if (lane + 32u < pf_n) { R.aB = pf1.y | hi; R.lB = pf1.z; R.rB = pf1.w; R.cB = ~(R.aB | R.lB | R.rB); }
+            S.tot_lane_nodes += __popc(R.cA) + __popc(R.cB);
             pf_n = 0;
-            __syncwarp();
             prefetch();
             continue;
         }
+        queens_record_trip<L, UP>(S, R, bbase, rank_mul, rc);
+        if (S.cnt[0] >= 64u) queens_run_from<L, 0, UP>(S, bbase, lane, rank_mul, rc);
+    }
+    for (;;) {
         // The record list is spent: the deepest bucket that holds 64 frames, else the shallowest that holds anything
         // (short trips; this is the tail of the warp's work).
         int lvl = -1;
