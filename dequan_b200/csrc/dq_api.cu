@@ -349,9 +349,9 @@ static int solve_queens_lane(dq_model* m, const dq_tree_opts* opts, dq_tree_resu
         // of a strongly scaled 17-Queens solve hold 1/parts of the records each and split one level deeper as well
         // (8 partitions: 2.43 -> 2.28 ms, scripts/parts_k.py)
         if (N <= 13) K = std::max(N - 8, 0);
-        else if (N <= 15) K = 7;
-        else if (N == 16) K = 8;
-        else if (N == 17) K = 9;                   // 124 M records (2 GB per list): 16.7 -> 15.3 ms; partitions 2.25 -> 2.04 ms
+        else if (N == 14) K = 5;                   // 0.172 ms (depth 7: 0.179)
+        else if (N <= 16) K = 7;                   // 15: 0.34 ms (depth 6 / 8: 0.40 / 0.38); 16: 1.51 ms (depth 8: 1.55)
+        else if (N == 17) K = 8;                   // 35 M records: 9.65 ms (depth 7 / 9: 9.68 / 10.24; the levels cost 0.16 / 0.44 / 1.44 ms)
         else K = 8;
     }
     // (the bucket search reads no prefix keys from its records — its first-solution warp computes 64-bit keys, and the
@@ -361,17 +361,18 @@ static int solve_queens_lane(dq_model* m, const dq_tree_opts* opts, dq_tree_resu
     // up to eight buckets (variables k+1 .. N-3; the records themselves stay in registers): the kernel compiled for exactly
     // that many; more: the general one (variables k .. N-3)
     typedef void (*BucketKernel)(QueensLaneArgs);
-    // [0]: plain rows; [1]: rows in shifted frames (left shifts only), exact while N + 2 (buckets + 1) <= 32
-    static const BucketKernel kBucketKernels[2][9] = {
-        {nullptr, k_queens_bucket_t<1, false>, k_queens_bucket_t<2, false>, k_queens_bucket_t<3, false>, k_queens_bucket_t<4, false>,
-         k_queens_bucket_t<5, false>, k_queens_bucket_t<6, false>, k_queens_bucket_t<7, false>, k_queens_bucket_t<8, false>},
-        {nullptr, k_queens_bucket_t<1, true>, k_queens_bucket_t<2, true>, k_queens_bucket_t<3, true>, k_queens_bucket_t<4, true>,
-         k_queens_bucket_t<5, true>, k_queens_bucket_t<6, true>, k_queens_bucket_t<7, true>, k_queens_bucket_t<8, true>}};
+    // rows 1 .. 5 of the forward check in shifted frames (left shifts only, the FMA pipe), the rest plain (the ALU pipe):
+    // the mix that balances the two pipes (measured: 0 / 3 / 4 / 5 / 6 / 7 / all rows shifted give 12.6 / 9.98 / 10.11 /
+    // 9.65 / 9.79 / 9.80 / 9.81 ms on 17-Queens at split depth 8); exact while N + 2 * 5 <= 32
+#define DQ_QB_ROW(J) {nullptr, k_queens_bucket_t<1, J>, k_queens_bucket_t<2, J>, k_queens_bucket_t<3, J>, k_queens_bucket_t<4, J>, \
+                      k_queens_bucket_t<5, J>, k_queens_bucket_t<6, J>, k_queens_bucket_t<7, J>, k_queens_bucket_t<8, J>}
+    static const BucketKernel kBucketKernels[2][9] = {DQ_QB_ROW(0), DQ_QB_ROW(5)};
+#undef DQ_QB_ROW
     static const bool general_only = getenv("DQ_QUEENS_GENERAL") != nullptr;
     static const bool plain_rows = getenv("DQ_QUEENS_PLAIN_ROWS") != nullptr;
     const bool compiled = N - 3 - K >= 1 && N - 3 - K <= 8 && !general_only;
     const int n_buckets = compiled ? N - 3 - K : N - 2 - K;
-    const BucketKernel bucket_kernel = compiled ? kBucketKernels[(N + 2 * (n_buckets + 1) <= 32 && !plain_rows) ? 1 : 0][n_buckets] : k_queens_bucket;
+    const BucketKernel bucket_kernel = compiled ? kBucketKernels[(N + 10 <= 32 && !plain_rows) ? 1 : 0][n_buckets] : k_queens_bucket;
     const size_t per_warp = (size_t)n_buckets * kQueensBucketCap * sizeof(uint4) + kQueensStageBytes;
     {
         int best = 0;

@@ -475,19 +475,23 @@ __device__ __forceinline__ uint32_t mad_lo(uint32_t a, uint32_t b, uint32_t c) {
 //     (na << j | 2^j - 1)  |  nl << 2j  |  nr        is all ones
 // — the same test as na | nl << j | nr >> j moved j bits up, so that no operand shifts right: the two left shifts are
 // multiplications, and the ALU pipe is left with one LOP3 per row and the maximum.  Exact while no board bit of
-// nl << 2j leaves the word: N + 2 (ROWS - 1) <= 32.  ls = l | value bit (nl before its shift).
+// nl << 2j leaves the word: N + 2j <= 32, i.e. for the rows j <= JUP = (32 - N) / 2; the others keep the plain form.
+// ls = l | value bit (nl before its shift).
 // The powers of two and the low ones of the first product come in registers whose values the compiler cannot see
 // (QueensRowConsts): knowing them it turns the multiply-add back into a shift-add (LEA) plus a LOP3 on the ALU pipe.
 struct QueensRowConsts { uint32_t pow[10], ones[10]; };
-template <int ROWS>
+template <int ROWS, int JUP>
 __device__ __forceinline__ uint32_t queens_rows_occupied_up(uint32_t na, uint32_t ls, uint32_t nr, const QueensRowConsts& rc) {
-    uint32_t m = na | (ls * 2u) | nr;
+    const uint32_t nl = ls * 2u;
+    uint32_t m = na | nl | nr;
 #pragma unroll
-    for (int j = 1; j < ROWS; j++) m = max(m, mad_lo(na, rc.pow[j], rc.ones[j]) | (ls * (2u << (2 * j))) | nr);
+    for (int j = 1; j < ROWS; j++)
+        m = max(m, j <= JUP ? (mad_lo(na, rc.pow[j], rc.ones[j]) | (ls * (2u << (2 * j))) | nr)      // rows whose shifted frame fits the word
+                            : (na | (nl << j) | (nr >> j)));
     return m;
 }
 
-template <int L, int LVL, bool UP, bool FULL>
+template <int L, int LVL, int JUP, bool FULL>
 __device__ __forceinline__ void queens_trip(QueensTripState& S, const uint32_t bbase, const uint32_t lane, const uint32_t rank_mul, const QueensRowConsts& rc) {
     constexpr uint32_t kRow = (uint32_t)LVL * kQueensBucketCap * 16u;
     constexpr int ROWS = L - LVL + 1;                            // later variables to check
@@ -516,8 +520,8 @@ __device__ __forceinline__ void queens_trip(QueensTripState& S, const uint32_t b
     const uint32_t naB = aB + bitB, lsB = lB + bitB, nrB = (rB + bitB) >> 1;
     const uint32_t nlA = lsA * 2u, nlB = lsB * 2u;
     // all ones <=> some later domain is empty (a padding frame has a = all ones)
-    const bool passA = (UP ? queens_rows_occupied_up<ROWS>(naA, lsA, nrA, rc) : queens_rows_occupied<ROWS>(naA, nlA, nrA)) != 0xFFFFFFFFu;
-    const bool passB = (UP ? queens_rows_occupied_up<ROWS>(naB, lsB, nrB, rc) : queens_rows_occupied<ROWS>(naB, nlB, nrB)) != 0xFFFFFFFFu;
+    const bool passA = queens_rows_occupied_up<ROWS, JUP>(naA, lsA, nrA, rc) != 0xFFFFFFFFu;
+    const bool passB = queens_rows_occupied_up<ROWS, JUP>(naB, lsB, nrB, rc) != 0xFFFFFFFFu;
     const uint32_t keepA = __ballot_sync(0xFFFFFFFFu, cA != 0u), keepB = __ballot_sync(0xFFFFFFFFu, cB != 0u);
     const uint32_t nkA = __popc(keepA);
     if (cA) sts128(top + (__popc(keepA * rank_mul) << 4), aA, lA, rA, cA);
@@ -552,7 +556,7 @@ __device__ __forceinline__ void queens_trip(QueensTripState& S, const uint32_t b
 // are taken: every value of a record's domain is tried exactly once.)
 struct QueensRecordRegs { uint32_t aA, lA, rA, cA, aB, lB, rB, cB; };
 
-template <int L, bool UP>
+template <int L, int JUP>
 __device__ __forceinline__ void queens_record_trip(QueensTripState& S, QueensRecordRegs& R, const uint32_t bbase, const uint32_t rank_mul, const QueensRowConsts& rc) {
     constexpr int ROWS = L + 2;                                  // later variables to check
     const uint32_t bitA = R.cA & (0u - R.cA), bitB = R.cB & (0u - R.cB);
@@ -560,8 +564,8 @@ __device__ __forceinline__ void queens_record_trip(QueensTripState& S, QueensRec
     const uint32_t naA = R.aA + bitA, lsA = R.lA + bitA, nrA = (R.rA + bitA) >> 1;
     const uint32_t naB = R.aB + bitB, lsB = R.lB + bitB, nrB = (R.rB + bitB) >> 1;
     const uint32_t nlA = lsA * 2u, nlB = lsB * 2u;
-    const bool passA = bitA != 0u && (UP ? queens_rows_occupied_up<ROWS>(naA, lsA, nrA, rc) : queens_rows_occupied<ROWS>(naA, nlA, nrA)) != 0xFFFFFFFFu;
-    const bool passB = bitB != 0u && (UP ? queens_rows_occupied_up<ROWS>(naB, lsB, nrB, rc) : queens_rows_occupied<ROWS>(naB, nlB, nrB)) != 0xFFFFFFFFu;
+    const bool passA = bitA != 0u && queens_rows_occupied_up<ROWS, JUP>(naA, lsA, nrA, rc) != 0xFFFFFFFFu;
+    const bool passB = bitB != 0u && queens_rows_occupied_up<ROWS, JUP>(naB, lsB, nrB, rc) != 0xFFFFFFFFu;
     const uint32_t kidsA = __ballot_sync(0xFFFFFFFFu, passA), kidsB = __ballot_sync(0xFFFFFFFFu, passB);
     const uint32_t c0 = S.cnt[0];
     const uint32_t nA = __popc(kidsA);
@@ -574,17 +578,17 @@ __device__ __forceinline__ void queens_record_trip(QueensTripState& S, QueensRec
 
 // Entered with 64 frames or more in bucket LVL and fewer in every deeper one; returns once no bucket from LVL down
 // holds 64.
-template <int L, int LVL, bool UP>
+template <int L, int LVL, int JUP>
 __device__ __forceinline__ void queens_run_from(QueensTripState& S, const uint32_t bbase, const uint32_t lane, const uint32_t rank_mul, const QueensRowConsts& rc) {
     do {
-        queens_trip<L, LVL, UP, true>(S, bbase, lane, rank_mul, rc);
+        queens_trip<L, LVL, JUP, true>(S, bbase, lane, rank_mul, rc);
         if constexpr (LVL + 1 < L) {
-            if (S.cnt[LVL + 1] >= 64u) queens_run_from<L, LVL + 1, UP>(S, bbase, lane, rank_mul, rc);
+            if (S.cnt[LVL + 1] >= 64u) queens_run_from<L, LVL + 1, JUP>(S, bbase, lane, rank_mul, rc);
         }
     } while (S.cnt[LVL] >= 64u);
 }
 
-template <int L, bool UP>
+template <int L, int JUP>
 __global__ void __launch_bounds__(kQueensBucketMaxWarps * 32)
 k_queens_bucket_t(QueensLaneArgs A) {
     static_assert(L >= 1 && L <= 8, "one count register per bucket");
@@ -651,8 +655,8 @@ k_queens_bucket_t(QueensLaneArgs A) {
             prefetch();
             continue;
         }
-        queens_record_trip<L, UP>(S, R, bbase, rank_mul, rc);
-        if (S.cnt[0] >= 64u) queens_run_from<L, 0, UP>(S, bbase, lane, rank_mul, rc);
+        queens_record_trip<L, JUP>(S, R, bbase, rank_mul, rc);
+        if (S.cnt[0] >= 64u) queens_run_from<L, 0, JUP>(S, bbase, lane, rank_mul, rc);
     }
     for (;;) {
         // The record list is spent: the deepest bucket that holds 64 frames, else the shallowest that holds anything
@@ -666,7 +670,7 @@ k_queens_bucket_t(QueensLaneArgs A) {
         }
         if (lvl < 0) break;
         switch (lvl) {
-#define DQ_QTRIP(V) case V: if constexpr (V < L) queens_trip<L, V, UP, false>(S, bbase, lane, rank_mul, rc); break;
+#define DQ_QTRIP(V) case V: if constexpr (V < L) queens_trip<L, V, JUP, false>(S, bbase, lane, rank_mul, rc); break;
             DQ_QTRIP(0) DQ_QTRIP(1) DQ_QTRIP(2) DQ_QTRIP(3) DQ_QTRIP(4) DQ_QTRIP(5) DQ_QTRIP(6) DQ_QTRIP(7)
 #undef DQ_QTRIP
             default: break;
