@@ -333,13 +333,14 @@ def main():
 
 
 def roofline_queens(n, world, lane_nodes, records, lane_ms, int_peak, hbm_peak, peak_src, table_bytes=0):
-    """Roofline of the dominant kernel, k_queens_bucket (depth-bucketed subtree search).  It is integer-issue bound
+    """Roofline of the dominant kernel, k_queens_bucket_t (depth-bucketed subtree search).  It is integer-issue bound
     (SURVEY.md §8d): algorithmic work = (5A+4) lane-ops per node, A = forward-checking domain updates per node; the peak
-    is the LOP3 rate measured in this run.  nodes_per_launch is what THIS rank's launch searched."""
+    is the LOP3 rate measured in this run, i.e. the ALU pipe alone (16 lanes per clock and SM quarter) — the kernel also
+    issues integer multiply-adds on the FMA pipe next to it.  nodes_per_launch is what THIS rank's launch searched."""
     ops_per_node = 5 * QUEENS_A[n] + 4
     achieved = lane_nodes * ops_per_node / (lane_ms * 1e-3) if lane_ms else 0.0
     traffic, src = ncu_traffic(f"k_queens_bucket/nqueens{n}") if world == 1 else (None, None)
-    return {"bound": "int32-alu", "kernel": "k_queens_bucket", "achieved": achieved / 1e12, "peak": int_peak / 1e12,
+    return {"bound": "int32-alu", "kernel": "k_queens_bucket_t", "achieved": achieved / 1e12, "peak": int_peak / 1e12,
             "unit": "Tlane-op/s per GPU", "frac": achieved / int_peak, "kernel_ms": lane_ms,
             "nodes_per_launch": lane_nodes, "ops_per_node": ops_per_node, "peak_source": "LOP3 microbenchmark, this run",
             # the job's true input is the model table (a few KB); what the kernel streams from HBM is the ENGINE'S OWN frontier:

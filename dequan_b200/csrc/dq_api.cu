@@ -320,7 +320,9 @@ template <> struct LevelWords<W64> {
 
 template <class K>
 static int max_ctas_per_sm(K kernel, int threads, size_t smem, int* out) {
-    if (smem > 48 * 1024) DQ_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // (always the device's full opt-in size, never the size asked for: several host threads may be sizing launches of the
+    // same kernel at once — dq_solve_tree_multi — and the attribute is per kernel, not per launch)
+    if (smem > 48 * 1024) DQ_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     DQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, kernel, threads, smem));
     return DQ_OK;
 }
@@ -349,8 +351,7 @@ static int solve_queens_lane(dq_model* m, const dq_tree_opts* opts, dq_tree_resu
         // of a strongly scaled 17-Queens solve hold 1/parts of the records each and split one level deeper as well
         // (8 partitions: 2.43 -> 2.28 ms, scripts/parts_k.py)
         if (N <= 13) K = std::max(N - 8, 0);
-        else if (N == 14) K = 5;                   // 0.172 ms (depth 7: 0.179)
-        else if (N <= 16) K = 7;                   // 15: 0.34 ms (depth 6 / 8: 0.40 / 0.38); 16: 1.51 ms (depth 8: 1.55)
+        else if (N <= 16) K = 7;                   // 14: 0.179 ms (depth 5: 0.172 with a bucket kernel twice as long: the step is bound by the first-solution warp either way);                   // 15: 0.34 ms (depth 6 / 8: 0.40 / 0.38); 16: 1.51 ms (depth 8: 1.55)
         else if (N == 17) K = 8;                   // 35 M records: 9.65 ms (depth 7 / 9: 9.68 / 10.24; the levels cost 0.16 / 0.44 / 1.44 ms)
         else K = 8;
     }

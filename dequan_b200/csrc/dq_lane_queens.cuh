@@ -252,6 +252,9 @@ constexpr int kQueensStageBytes = 0;                  // (the pools fill an SM's
 // search loop is warp-uniform, and with it the uniform datapath: 18.0 -> 21.6 ms on 17-Queens).  The search state is
 // warp-uniform, lane j tests the domain of the j-th later variable (one vote per
 // node), and lane d keeps the frame of depth d in its registers (a pop is four shuffles, nothing touches memory).
+// (Measured and dropped: a whole level per step — lane v forward-checks value v in a row loop of its own, one ballot per
+// level.  Fewer steps but three times the instructions, and this warp shares its SM quarter with the bucket kernel's
+// warps: the 14-Queens solve went from 0.179 to 0.238 ms.)
 __device__ __forceinline__ void queens_first_owned(const QueensLaneArgs& A, int lane) {
     const int N = A.n, K = A.k;
     const uint32_t full = (1u << N) - 1u;

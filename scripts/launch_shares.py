@@ -27,8 +27,8 @@ buf = []
 for name, ns in seq:
     if name in ("dq::k_queens_level", "dq::k_queens_level_wide", "dq::k_queens_levels_head", "dq::k_queens_first_warp"):
         buf.append((name, ns))          # belongs to the bucket launch that follows
-    elif name == "dq::k_queens_bucket":
-        g = "17-Queens count-all (main workload)" if ns > 5e6 else "14-Queens count-all (extra.nqueens14_1gpu)"
+    elif "k_queens_bucket" in name:
+        g = "17-Queens count-all (main workload)" if ns > 3e6 else "14-Queens count-all (extra.nqueens14_1gpu)"
         for n2, t2 in buf:
             add(g, n2, t2)
         buf = []
