@@ -248,10 +248,12 @@ def test_lane_engine_rejects_other_models(product_lib):
         api.Model(sudoku(REFERENCE_SUDOKU)).solve_tree("count", engine="lane")
 
 
-@pytest.mark.parametrize("n,k", [(15, 0), (16, 0), (12, 1), (12, 7), (13, 10)])
+@pytest.mark.parametrize("n,k", [(15, 0), (16, 0), (18, 0), (12, 1), (12, 7), (13, 10), (13, 1), (14, 2), (16, 11)])
 def test_lane_engine_larger_boards(golden, golden_large, product_lib, n, k):
-    """N <= 14: tests/golden/reference.json; N = 15, 16: tests/golden/reference_large.json — both are outputs of the
-    unmodified reference (solutions, stats.assigned_vars, DFS-first solution)."""
+    """N <= 14: tests/golden/reference.json; N = 15 .. 18: tests/golden/reference_large.json — both are outputs of the
+    unmodified reference (solutions, stats.assigned_vars, DFS-first solution).  k = 0: the engine's own split depth (the
+    bucket kernel compiled for its bucket count); (13, 1), (14, 2): nine buckets and (13, 10): none of its own, i.e. the
+    general bucket kernel; (12, 7), (16, 11): two buckets."""
     g = (golden if n <= 14 else golden_large)["nqueens"][str(n)]["count"]
     r = api.Model(nqueens(n)).solve_tree("count", engine="lane", split_depth=k)
     assert (r.solutions, r.nodes, r.first) == (g["solutions"], g["nodes"], g["first"]) and r.engine == "lane"
@@ -829,6 +831,26 @@ def test_generic_path_on_the_queens_class(golden, product_lib):
         g = golden["nqueens"][str(n)]["count"]
         want_engine = "lane" if n >= 13 else line.split()[-1]      # (a tree of a few thousand prefixes stays on the warp-cooperative engines)
         assert line == f"{n} {g['solutions']} {g['nodes']} {g['first']} {want_engine}", line
+
+
+@pytest.mark.parametrize("var", ["DQ_QUEENS_PLAIN_ROWS", "DQ_QUEENS_GENERAL"])
+def test_queens_bucket_kernel_variants(golden, product_lib, var):
+    """The bucket kernels a 17-Queens solve does not pick: forward-check rows all in plain form (what boards of 23 and
+    more queens get) and the general kernel (bucket count at run time) on boards that normally get a compiled one.
+    The variables are read once per process, hence the subprocess."""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r); from dequan_b200 import api; from dequan_b200.model import nqueens\n"
+            "for n in (5, 9, 12, 14):\n"
+            "    r = api.Model(nqueens(n)).solve_tree('count'); print(n, r.solutions, r.nodes, r.first, r.engine)\n"
+            % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **{var: "1"}), capture_output=True, text=True,
+                         check=True, timeout=300).stdout.splitlines()
+    assert len(out) == 4
+    for line in out:
+        n = int(line.split()[0])
+        g = golden["nqueens"][str(n)]["count"]
+        assert line == f"{n} {g['solutions']} {g['nodes']} {g['first']} lane", line
 
 
 def test_sudoku_10k_vs_reference(golden_large, product_lib):
