@@ -1393,7 +1393,8 @@ static int run_graphs_lane(int nv, int k, const int64_t* edge_off, const GraphBa
     if (*h_over > 65535) { g_err = "an instance leaves more than 65535 edges outside its neighbour rows"; return DQ_ERR_UNSUPPORTED; }
     A.over_cap = (int)((*h_over + 1) & ~1ull);
     A.stride = graphs_record_bytes(A.nvp, A.rw, A.over_cap);
-    const size_t lane_smem = graphs_lane_warp_bytes(A.nvp, A.stride, A.over_cap);
+    const bool packed = k <= 3 && getenv("DQ_GRAPHS_K4_LAYOUT") == nullptr;      // (byte 3 of the state words is free below four colours)
+    const size_t lane_smem = graphs_lane_warp_bytes(A.nv, A.nvp, A.over_cap, packed);
     if (lane_smem > 220 * 1024) { g_err = "instance state exceeds shared memory"; return DQ_ERR_UNSUPPORTED; }
     DQ_CUDA(d_adj.reserve((size_t)n * A.stride));
     A.adj = d_adj.p;
@@ -1407,11 +1408,12 @@ static int run_graphs_lane(int nv, int k, const int64_t* edge_off, const GraphBa
     DQ_CUDA(cudaEventRecord(ctx->ev2, s));
     // the search: one warp per CTA, as many CTAs per SM as their state lets in
     int occ = 0;
-    rc = max_ctas_per_sm(k_graphs_lane, 32, lane_smem, &occ);
+    rc = packed ? max_ctas_per_sm(k_graphs_lane<true>, 32, lane_smem, &occ) : max_ctas_per_sm(k_graphs_lane<false>, 32, lane_smem, &occ);
     if (rc != DQ_OK) return rc;
     if (occ < 1) { g_err = "kernel does not fit an SM"; return DQ_ERR_UNSUPPORTED; }
     const long long ctas = std::max<long long>(1, std::min<long long>((n + 31) / 32, (long long)occ * sms));
-    k_graphs_lane<<<(unsigned)ctas, 32, lane_smem, s>>>(A);
+    if (packed) k_graphs_lane<true><<<(unsigned)ctas, 32, lane_smem, s>>>(A);
+    else k_graphs_lane<false><<<(unsigned)ctas, 32, lane_smem, s>>>(A);
     DQ_CUDA(cudaEventRecord(ctx->ev3, s));
     return DQ_OK;
 }

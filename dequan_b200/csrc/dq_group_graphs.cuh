@@ -229,11 +229,19 @@ __device__ __forceinline__ void sts16(uint32_t addr, uint32_t v) {
     asm volatile("{\n\t.reg .u16 t;\n\tcvt.u16.u32 t, %1;\n\tst.shared.u16 [%0], t;\n\t}" ::"r"(addr), "r"(v) : "memory");
 }
 
-// shared memory of one warp (= one CTA) of k_graphs_lane
-__host__ __device__ inline size_t graphs_lane_warp_bytes(int nvp, int stride, int over_cap) {
-    return (size_t)nvp * (128 + 64) + (size_t)over_cap * 64 + (size_t)stride + 16;
+// shared memory of one warp (= one CTA) of k_graphs_lane.
+// Per level (= vertex) and lane: the S word, and what the search keeps about the level — the colour it took and the
+// stack of open levels (levels that still hold untried colours).  K4 (four colours): a byte each, next to S.
+// Up to three colours (PACKED): byte 3 of the S words is free — the domain test never looks at it — and holds the open
+// levels as a linked list (S[d].byte3 = the open level below d), and the colours go 16 to a word: 136 bytes per level and
+// warp instead of 192, i.e. 8 warps per SM instead of 5 at 200 vertices.
+// (At 200 vertices and three colours: 201 S words + 13 colour words + the overflow pairs = 27.4 KB per warp, the most
+// that still lets 8 warps share an SM's 228 KB; a staging buffer for the record would cost the eighth.)
+__host__ __device__ inline size_t graphs_lane_warp_bytes(int nv, int nvp, int over_cap, bool packed) {
+    return (size_t)(nv + 1) * 128 + (packed ? (size_t)((nv + 15) / 16) * 128 : (size_t)nvp * 64) + (size_t)over_cap * 64 + 16;
 }
 
+template <bool PACKED>
 __global__ void __launch_bounds__(32)
 k_graphs_lane(GroupGraphsArgs A) {
     extern __shared__ __align__(128) unsigned char gl_raw[];
@@ -243,21 +251,17 @@ k_graphs_lane(GroupGraphsArgs A) {
     const int nv = A.nv, nvp = A.nvp;
     const uint32_t base_s = smem_u32(gl_raw);
     const uint32_t s_s = base_s + 4u * lane;                                  // S[q]    at s_s + q * 128
-    const uint32_t co_s = base_s + (uint32_t)nvp * 128u + 2u * lane;          // co[i]   at co_s + i * 64: byte 0 col[i], byte 1 open[i]
-    const uint32_t over_s = base_s + (uint32_t)nvp * 192u + 2u * lane;        // over[p] at over_s + p * 64: (vertex, neighbour)
-    const uint32_t stage_s = base_s + (uint32_t)nvp * 192u + (uint32_t)A.over_cap * 64u;
+    const uint32_t co_s = base_s + (uint32_t)(nv + 1) * 128u + (PACKED ? 4u : 2u) * lane;   // K4: co[i] at co_s + i * 64: byte 0 col[i], byte 1 open[i]; PACKED: colours of levels 16j .. 16j+15 at co_s + j * 128
+    const uint32_t over_base = base_s + (uint32_t)(nv + 1) * 128u + (PACKED ? (uint32_t)((nv + 15) / 16) * 128u : (uint32_t)nvp * 64u);
+    const uint32_t over_s = over_base + 2u * lane;                            // over[p] at over_s + p * 64: (vertex, neighbour)
     // the neighbour rows stay in the record (HBM, L2- and L1-resident while the search is around that depth): 8 bytes per
     // level and lane, the next level's row fetched a trip ahead
     const uint2* rows_g = reinterpret_cast<const uint2*>(A.adj);
     uint2 row_cur = make_uint2(0u, 0u);                 // rows[d] when row_ok
     bool row_ok = false;
-    const uint32_t mbar = stage_s + (uint32_t)A.stride;
     // lanes without an instance run the trip on whatever their slots hold: start from zeros (vertex 0, no neighbours)
-    for (uint32_t x = 4u * lane; x < (uint32_t)graphs_lane_warp_bytes(nvp, A.stride, A.over_cap); x += 128u) sts32(base_s + x, 0u);
+    for (uint32_t x = 4u * lane; x < (uint32_t)graphs_lane_warp_bytes(nv, nvp, A.over_cap, PACKED); x += 128u) sts32(base_s + x, 0u);
     __syncwarp();
-    if (lane == 0) { mbar_init(mbar, 1); mbar_init_fence(); }
-    __syncwarp();
-    uint32_t parity = 0;
     const uint32_t init_word = A.k >= 4 ? 0u : (FULL << (8 * A.k));
     const unsigned long long budget = A.budget ? A.budget : ~0ull;
     unsigned long long t_sat = 0, t_unsat = 0, t_budget = 0, t_nodes = 0;
@@ -269,6 +273,9 @@ k_graphs_lane(GroupGraphsArgs A) {
     int left = 0, left0 = 0;                             // nodes the budget still allows (32-bit window of it) / its start value
     int code = 0;                                        // why the trip stopped the instance: bit 0 a solution, bit 1 tree exhausted (neither: `left` ran out)
     uint32_t d = 0, sp = 0, n_over = 0;
+    uint32_t top = 0xFFu;                                // PACKED: the deepest open level (0xFF: none)
+    // bytes of an S word that are colours (the domain test ignores the others)
+    const uint32_t ymul = A.k >= 4 ? 0x01010101u : (0x01010101u & ((1u << (8 * A.k)) - 1u));
 
     for (;;) {
         // ---- one trip = one level entered or re-entered (ForwardCheckingStep, dequan.h:494-571), level d = vertex d ----
@@ -276,11 +283,19 @@ k_graphs_lane(GroupGraphsArgs A) {
         if (!row_ok) { row_cur = __ldg(rows_g + d); row_ok = true; }
         const uint2 row_next = __ldg(rows_g + d + 1u);
         uint32_t r_lo = row_cur.x, r_hi = row_cur.y;
-        const uint32_t c_old = lds8(co_s + d * 64u);                 // (meaningful when ret)
-        const uint32_t d_pop = lds8(co_s + sp * 64u - 63u);          // open[sp - 1] (meaningful when sp > 0)
+        uint32_t c_old, d_pop, cw = 0;                               // colour taken here before (meaningful when ret); level to go back to
+        if constexpr (PACKED) {
+            cw = lds32(co_s + (d >> 4) * 128u);
+            c_old = (cw >> (2u * (d & 15u))) & 3u;
+            if (ret) top = wd >> 24;                                 // back at an open level: it leaves the list (and rejoins below if colours are left)
+            d_pop = top;
+        } else {
+            c_old = lds8(co_s + d * 64u);
+            d_pop = lds8(co_s + sp * 64u - 63u);                     // open[sp - 1] (meaningful when sp > 0)
+        }
         const bool more = (r_hi >> 24) == 0xFFu;                     // the row goes on in the overflow list
         if (more) r_hi = (r_hi & 0x00FFFFFFu) | ((uint32_t)nv << 24);   // (the marker is not a vertex: look at the dummy instead)
-        const uint32_t y = (255u - d) * 0x01010101u, yl = y & 0x7F7F7F7Fu;     // bytes below 255-d: in the domain
+        const uint32_t y = (255u - d) * ymul, yl = y & 0x7F7F7F7Fu;           // bytes below 255-d: in the domain
         const uint32_t mark = 254u - d;
         uint32_t a[8], w[8], f[8];
 #pragma unroll
@@ -309,16 +324,21 @@ k_graphs_lane(GroupGraphsArgs A) {
                         const int outcome = nodes > budget ? 2 : ((code & 1) ? 1 : 0);
                         if (outcome == 2) nodes = budget + 1;
                         uint8_t* out = A.colours + (size_t)inst * nv;
-                        for (int v = 0; v < nv; v++) out[v] = outcome == 1 ? (uint8_t)lds8(co_s + (uint32_t)v * 64u) : (uint8_t)0xFF;
+                        for (int v = 0; v < nv; v++) {
+                            uint32_t cv;
+                            if constexpr (PACKED) cv = (lds32(co_s + ((uint32_t)v >> 4) * 128u) >> (2u * ((uint32_t)v & 15u))) & 3u;
+                            else cv = lds8(co_s + (uint32_t)v * 64u);
+                            out[v] = outcome == 1 ? (uint8_t)cv : (uint8_t)0xFF;
+                        }
                         A.nodes[inst] = nodes;
                         A.status[inst] = (uint8_t)outcome;
                         t_nodes += nodes;
                         t_sat += outcome == 1; t_unsat += outcome == 0; t_budget += outcome == 2;
-                        d = 0; sp = 0; ret = false; row_ok = false;
+                        d = 0; sp = 0; top = 0xFFu; ret = false; row_ok = false;
                     }
                     pend = false;
                 }
-                // ---- next instances in: one bulk copy per record into the staging buffer, then into the lane's columns ----
+                // ---- next instances in ----
                 uint32_t needy = __ballot_sync(FULL, !have && !idle);
                 while (needy) {
                     const int t = __ffs((int)needy) - 1;
@@ -330,32 +350,29 @@ k_graphs_lane(GroupGraphsArgs A) {
                         if ((int)lane == t || ((needy >> lane) & 1u)) idle = true;
                         break;
                     }
-                    if (lane == 0) {
-                        mbar_expect_tx(mbar, (uint32_t)A.stride);
-                        bulk_g2s(stage_s, A.adj + (size_t)i_new * A.stride, (uint32_t)A.stride, mbar);
-                    }
                     const bool refused = A.status[i_new] == 0xFE;  // k_graphs_adjacency could not build this instance's record
-                    mbar_wait(mbar, parity);
-                    parity ^= 1;
                     if (refused) {
                         if (lane == 0) { A.nodes[i_new] = 0; A.status[i_new] = 3; }
                         for (int v = lane; v < nv; v += 32) A.colours[(size_t)i_new * nv + v] = 0xFF;
                         needy |= 1u << t;                          // the lane still needs an instance
                     } else {
-                        for (uint32_t q = lane; q < (uint32_t)nvp; q += 32)
+                        // the lane's columns: the state words, and the few neighbour pairs its rows of 8 had no room for
+                        // (straight from the record: its rows are read from there level by level anyway)
+                        for (uint32_t q = lane; q <= (uint32_t)nv; q += 32)
                             sts32(base_s + q * 128u + 4u * t, q == (uint32_t)nv ? FULL : init_word);
-                        const uint32_t n_ov = lds16(stage_s + (uint32_t)nvp * 9u);
+                        const uint16_t* tail = reinterpret_cast<const uint16_t*>(A.adj + (size_t)i_new * A.stride + (size_t)nvp * 9u);
+                        const uint32_t n_ov = __ldg(tail);
                         for (uint32_t p = lane; p < (uint32_t)A.over_cap; p += 32)
-                            sts16(base_s + (uint32_t)nvp * 192u + p * 64u + 2u * t, p < n_ov ? lds16(stage_s + (uint32_t)nvp * 9u + 16u + 2u * p) : 0xFFFFu);
+                            sts16(over_base + p * 64u + 2u * t, p < n_ov ? (uint32_t)__ldg(tail + 8 + p) : 0xFFFFu);
                         if ((int)lane == t) {
                             inst = i_new; have = true; n_over = n_ov;
                             rows_g = reinterpret_cast<const uint2*>(A.adj + (size_t)i_new * A.stride);
                             row_ok = false;
-                            nodes_base = 0; d = 0; sp = 0; ret = false;
+                            nodes_base = 0; d = 0; sp = 0; top = 0xFFu; ret = false;
                             left0 = left = (int)min(budget, (unsigned long long)kLeftCap);
                         }
                     }
-                    __syncwarp();                                  // the staging buffer is free again
+                    __syncwarp();
                 }
                 if (__all_sync(FULL, idle)) break;
                 continue;                                          // (the loads above are stale: start the trip over)
@@ -389,9 +406,16 @@ k_graphs_lane(GroupGraphsArgs A) {
             const uint32_t m = (f[j] >> 7) * 255u;
             if (act && f[j] != 0u) sts32(a[j], (w[j] & ~m) | (put & m));
         }
+        const bool rest = (cand & ~upto) != 0u;
         if (act) {
-            sts8(co_s + d * 64u, (unit * 0x00010203u) >> 24);
-            sts8(co_s + sp * 64u + 1u, d);
+            if constexpr (PACKED) {
+                const uint32_t sh = 2u * (d & 15u);
+                sts32(co_s + (d >> 4) * 128u, (cw & ~(3u << sh)) | (((unit * 0x00010203u) >> 24) << sh));
+                if (rest) sts8(s_s + d * 128u + 3u, top);            // joins the open levels
+            } else {
+                sts8(co_s + d * 64u, (unit * 0x00010203u) >> 24);
+                sts8(co_s + sp * 64u + 1u, d);
+            }
             if (more)
                 for (uint32_t p = 0; p < n_over; p++) {
                     const uint32_t pr = lds16(over_s + p * 64u);
@@ -403,17 +427,17 @@ k_graphs_lane(GroupGraphsArgs A) {
                 }
         }
         // down, back to the deepest level with colours left (return false, dequan.h:569-570), or done
-        const bool rest = (cand & ~upto) != 0u;
         if (have) {
             left -= (int)n_tried;
-            const bool sat = descend && last, unsat = !descend && sp == 0u;
+            const bool sat = descend && last, unsat = !descend && (PACKED ? top == 0xFFu : sp == 0u);
             code = (sat ? 1 : 0) | (unsat ? 2 : 0);
-            sp = descend ? sp + (rest ? 1u : 0u) : sp - 1u;
+            if constexpr (PACKED) { if (descend && rest) top = d; }
+            else sp = descend ? sp + (rest ? 1u : 0u) : sp - 1u;
             d = descend ? d + 1u : d_pop;
             ret = !descend;
             row_ok = descend;
             row_cur = row_next;
-            if (sat || unsat || left < 0) { have = false; pend = true; if (unsat) { d = 0; sp = 0; row_ok = false; } }
+            if (sat || unsat || left < 0) { have = false; pend = true; if (unsat) { d = 0; sp = 0; top = 0xFFu; row_ok = false; } }
         }
     }
     if (t_sat) atomicAdd(A.totals + 0, t_sat);
