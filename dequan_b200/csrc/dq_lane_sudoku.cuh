@@ -93,6 +93,7 @@ enum SkCtrl { SKC_FRESH = 0,        // k_sudoku_first: next fresh instance
               SKC_SNAP = 5,         // snapshots reserved
               SKC_HEAD = 6,         // tickets drawn by consumers (may run ahead of SKC_RESERVE: lanes waiting for work)
               SKC_OUTSTANDING = 7,  // tasks published and not finished yet
+              SKC_MAX_BLANK = 8,    // k_sudoku_digest: the most blanks any instance of the batch has (sizes the lanes' stacks)
               SKC_ERROR = 9,        // bit 0: a warp gave up waiting; bit 1: task pool overflow; bit 2: a counted subtree held a solution
               SKC_TOTALS = 12 };    // [12..15] sat, unsat, budget, nodes
 
@@ -129,7 +130,7 @@ constexpr int kDigestOutBytes = kDigestTile * kDigestVec * 16;   // 36 864
 constexpr int kDigestSmem = 2 * kDigestInBytes + kDigestOutBytes + 16;
 
 __global__ void __launch_bounds__(kDigestTile)
-k_sudoku_digest(const uint8_t* __restrict__ cells, long long n, int stride, SudokuDigest* __restrict__ out) {
+k_sudoku_digest(const uint8_t* __restrict__ cells, long long n, int stride, SudokuDigest* __restrict__ out, unsigned long long* __restrict__ max_blank) {
     extern __shared__ __align__(128) uint8_t dg_raw[];           // in[2][10368] | records[128][288] | two mbarriers
     uint8_t* recs = dg_raw + 2 * kDigestInBytes;
     const uint32_t in_s = smem_u32(dg_raw), recs_s = smem_u32(recs), mbar = recs_s + kDigestOutBytes;
@@ -144,6 +145,7 @@ k_sudoku_digest(const uint8_t* __restrict__ cells, long long n, int stride, Sudo
     };
     uint32_t parity = 0;
     int b = 0;
+    int most_blanks = 0;
     long long t = blockIdx.x;
     if (t < tiles && full(t) && threadIdx.x == 0) issue(t, 0);
     bool store_in_flight = false;
@@ -199,6 +201,7 @@ k_sudoku_digest(const uint8_t* __restrict__ cells, long long n, int stride, Sudo
                 }
             w[0] = blank[0]; w[1] = blank[1]; w[2] = blank[2];
             w[3] = (uint32_t)level | (defer ? 0x80000000u : 0u);
+            most_blanks = max(most_blanks, level);
 #pragma unroll
             for (int i = 0; i < 9; i++) w[10 + i] = box[i] * SK_ONES;
 #pragma unroll
@@ -231,6 +234,8 @@ k_sudoku_digest(const uint8_t* __restrict__ cells, long long n, int stride, Sudo
         }
     }
     if (store_in_flight && threadIdx.x == 0) bulk_wait_read0();
+    most_blanks = __reduce_max_sync(0xFFFFFFFFu, most_blanks);
+    if ((threadIdx.x & 31) == 0 && most_blanks) atomicMax(max_blank, (unsigned long long)most_blanks);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -242,6 +247,7 @@ struct SudokuSmem {
     uint32_t blk[27][kSudokuBlock];     // (row, stack) -> 0x1FF in the fields of blank cells
     uint32_t cellw[21][kSudokuBlock];   // blank cell ids in search order, four levels per word
     uint16_t stk[81][kSudokuBlock];     // per level: passing values not tried yet | chosen value index << 9
+                                        // (LAST member: a batch whose instances have at most B blanks launches with B levels of it)
 };
 
 __device__ __forceinline__ uint32_t sk_rep(uint32_t x9) { return x9 * SK_ONES; }
