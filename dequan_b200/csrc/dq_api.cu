@@ -1208,11 +1208,7 @@ static int run_batch_cells(dq_model* m, const uint8_t* cells_dev, int64_t n, int
 // engine afterwards.
 static int run_batch_sudoku(dq_model* m, const uint8_t* cells_dev, int64_t n, int32_t stride, const dq_batch_opts* opts,
                             uint8_t* sol_dev, unsigned long long* nodes_dev, uint8_t* status_dev, dq_batch_stats* st) {
-    const size_t smem_strong = sizeof(StrongSmem);
-    int occ_strong = 0;
-    int rc = max_ctas_per_sm(k_sudoku_strong, 128, smem_strong, &occ_strong);
-    if (rc != DQ_OK) return rc;
-    if (occ_strong < 1) { g_err = "kernel does not fit an SM"; return DQ_ERR_UNSUPPORTED; }
+    int rc = DQ_OK;
     // the number of pieces handed over at the tail does not shrink with the batch: generous floors (64 MB + 192 MB)
     const unsigned long long task_cap = std::max<unsigned long long>(1u << 22, std::min<unsigned long long>(8ull * n, 1ull << 25));
     const unsigned long long snap_cap = std::max<unsigned long long>(1u << 20, std::min<unsigned long long>(2ull * n, 1ull << 23));
@@ -1267,12 +1263,15 @@ static int run_batch_sudoku(dq_model* m, const uint8_t* cells_dev, int64_t n, in
     static const bool full_stack = getenv("DQ_SUDOKU_FULL_STACK") != nullptr;
     const int levels = full_stack ? 81 : (int)std::min<unsigned long long>(std::max<unsigned long long>(*h_blank, 1), 81);
     const size_t smem = offsetof(SudokuSmem, stk) + (size_t)levels * kSudokuBlock * sizeof(uint16_t);
-    int occ_first = 0, occ_count = 0, occ_walk = 0;
+    const size_t smem_strong = sudoku_strong_smem(levels);       // (30 givens: 36 KB per CTA, 24 warps per SM instead of 16)
+    A.stack_levels = levels;
+    int occ_first = 0, occ_count = 0, occ_walk = 0, occ_strong = 0;
     rc = max_ctas_per_sm(k_sudoku_first, kSudokuBlock, smem, &occ_first);
     if (rc == DQ_OK) rc = max_ctas_per_sm(k_sudoku_count, kSudokuBlock, smem, &occ_count);
     if (rc == DQ_OK) rc = max_ctas_per_sm(k_sudoku_walk, kSudokuBlock, smem, &occ_walk);
+    if (rc == DQ_OK) rc = max_ctas_per_sm(k_sudoku_strong, 128, smem_strong, &occ_strong);
     if (rc != DQ_OK) return rc;
-    if (occ_first < 1 || occ_count < 1 || occ_walk < 1) { g_err = "kernel does not fit an SM"; return DQ_ERR_UNSUPPORTED; }
+    if (occ_first < 1 || occ_count < 1 || occ_walk < 1 || occ_strong < 1) { g_err = "kernel does not fit an SM"; return DQ_ERR_UNSUPPORTED; }
     const long long ctas_first = std::max<long long>(1, std::min<long long>(occ_first * sms, (long long)((n + kSudokuBlock - 1) / kSudokuBlock)));
     k_sudoku_first<<<(unsigned)ctas_first, kSudokuBlock, smem, m->stream>>>(A);
     mark(2);

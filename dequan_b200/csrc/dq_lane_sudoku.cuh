@@ -115,6 +115,7 @@ struct SudokuArgs {
     unsigned donate_min, donate_gap;       // k_sudoku_count: a task gives a level away only when it is this old / this long after the last time
     unsigned strong_hidden_after;          // k_sudoku_strong: value tries after which hidden-single propagation joins in
     int pop_quorum;                        // extra step-back rounds run while at least this many lanes still stand on an exhausted level
+    int stack_levels;                      // the most blanks any instance of the batch has: levels of the lanes' (and k_sudoku_strong's) stacks
     unsigned force_donate;                 // test knob: donate whenever a task is this many nodes old, hungry lanes or not (0 = off)
 };
 
@@ -622,9 +623,11 @@ constexpr unsigned kStrongHiddenAfter = 400;   // value tries after which an ins
 
 struct StrongSmem {
     uint32_t peer[81][32];               // peer[x][lane]: bit 10*f set iff cell lane+32f is a peer of x
-    uint32_t saved[4][81][32];           // per warp, per level: the registers before the level's first value
-    uint16_t rest[4][81];                // per warp, per level: values still to try (0: forced level)
+    // followed, for `levels` = the most blanks of any instance in the batch (SudokuArgs::stack_levels), by
+    //   uint32_t saved[4][levels][32]   per warp, per level: the registers before the level's first value
+    //   uint16_t rest[4][levels]        per warp, per level: values still to try (0: forced level)
 };
+__host__ __device__ inline size_t sudoku_strong_smem(int levels) { return sizeof(StrongSmem) + (size_t)4 * levels * (32 * 4 + 2) + 16; }
 
 // Hidden singles: a value that only one cell of a row, column or box can still take goes to that cell; a value no
 // cell of the unit can take is a contradiction.  Lane u < 27 owns unit u (its three 32-bit cell masks u0..u2 in the
@@ -689,6 +692,8 @@ k_sudoku_strong(SudokuArgs A) {
     extern __shared__ __align__(16) unsigned char sk_raw[];
     StrongSmem& M = *reinterpret_cast<StrongSmem*>(sk_raw);
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    uint32_t* const saved = reinterpret_cast<uint32_t*>(sk_raw + sizeof(StrongSmem)) + (size_t)wib * A.stack_levels * 32 + lane;   // [level * 32]
+    uint16_t* const rest = reinterpret_cast<uint16_t*>(sk_raw + sizeof(StrongSmem) + (size_t)4 * A.stack_levels * 128) + wib * A.stack_levels;
     // peer table, once per CTA
     for (int i = threadIdx.x; i < 81 * 32; i += blockDim.x) {
         const int x = i >> 5, l = i & 31;
@@ -753,31 +758,31 @@ k_sudoku_strong(SudokuArgs A) {
             if (!back) {
                 const uint32_t w = __shfl_sync(0xFFFFFFFFu, D, owner) >> (10 * f);
                 if (w & 0x200u) {                          // forced: its single value is already everywhere
-                    if (lane == 0) M.rest[wib][l] = 0;
+                    if (lane == 0) rest[l] = 0;
                     __syncwarp();
                     ++l;
                     continue;
                 }
                 d = w & 0x1FF;
-                M.saved[wib][l][lane] = D;
-            } else d = M.rest[wib][l];
+                saved[l * 32] = D;
+            } else d = rest[l];
             bool ok = false;
             while (d) {                                    // the level's values in ascending order, each from the saved state
                 const uint32_t v = d & (0u - d);
                 d ^= v;
-                D = M.saved[wib][l][lane];
+                D = saved[l * 32];
                 if (lane == owner) D = (D & ~(0x3FFu << (10 * f))) | ((v | 0x200u) << (10 * f));
                 D &= ~(M.peer[p][lane] * v);
                 ++tries;
                 if (sk_propagate(D, M, lane, valid3, tries > A.strong_hidden_after, u0, u1, u2)) { ok = true; break; }
             }
             __syncwarp();
-            if (lane == 0) M.rest[wib][l] = (uint16_t)d;
+            if (lane == 0) rest[l] = (uint16_t)d;
             __syncwarp();
             if (ok) { ++l; back = false; }
             else {
                 --l;
-                while (l >= 0 && M.rest[wib][l] == 0) --l;
+                while (l >= 0 && rest[l] == 0) --l;
                 back = true;
             }
         }
