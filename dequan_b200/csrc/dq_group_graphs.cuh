@@ -293,6 +293,9 @@ k_graphs_lane(GroupGraphsArgs A) {
             c_old = lds8(co_s + d * 64u);
             d_pop = lds8(co_s + sp * 64u - 63u);                     // open[sp - 1] (meaningful when sp > 0)
         }
+        // the row of the level a dead end here goes back to, a trip ahead like the next level's (half of all trips end
+        // that way, and a row loaded on arrival leaves its L2 latency exposed)
+        const uint2 row_back = __ldg(rows_g + min(d_pop, (uint32_t)nv));
         const bool more = (r_hi >> 24) == 0xFFu;                     // the row goes on in the overflow list
         if (more) r_hi = (r_hi & 0x00FFFFFFu) | ((uint32_t)nv << 24);   // (the marker is not a vertex: look at the dummy instead)
         const uint32_t y = (255u - d) * ymul, yl = y & 0x7F7F7F7Fu;           // bytes below 255-d: in the domain
@@ -435,8 +438,8 @@ k_graphs_lane(GroupGraphsArgs A) {
             else sp = descend ? sp + (rest ? 1u : 0u) : sp - 1u;
             d = descend ? d + 1u : d_pop;
             ret = !descend;
-            row_ok = descend;
-            row_cur = row_next;
+            row_ok = true;
+            row_cur = descend ? row_next : row_back;
             if (sat || unsat || left < 0) { have = false; pend = true; if (unsat) { d = 0; sp = 0; top = 0xFFu; row_ok = false; } }
         }
     }
