@@ -161,6 +161,8 @@ struct dq_model {
     std::vector<uint8_t> h_blob;                // its host image (kept while the copy may be in flight)
     uint32_t *t_ent_off = nullptr, *t_ent_moff = nullptr, *t_masks = nullptr, *t_dom0 = nullptr;   // masks / dom0: 64-bit words when cm.wide()
     bool last_wide = false;
+    bool last_queens_first = false;                 // the last solve was solve_queens_first (dq_tree_nodes_upto answers from its count)
+    unsigned long long last_queens_first_nodes = 0;
     uint32_t* t_ent = nullptr;
     uint16_t *t_order = nullptr, *t_pos = nullptr;
     uint8_t* t_cell_lut = nullptr;
@@ -333,6 +335,45 @@ static int max_ctas_per_sm(K kernel, int threads, size_t smem, int* out) {
                    : ((m)->cm.has_table ? max_ctas_per_sm(KERNEL<false, true>, threads, smem, out) \
                                         : max_ctas_per_sm(KERNEL<false, false>, threads, smem, out)))
 
+
+// FIRST mode on a CLASS_QUEENS model, whole tree in one partition, no node budget: one warp walks the reference's own
+// DFS (k_queens_first_nodes) — the solution, and every value tried on the way counted as the node it is.  One launch, one
+// synchronisation; the generic path's prefix split searches the winning subtree with one warp as well, after paying for
+// the frontier and for the subtrees that hold nothing (20-Queens: 43 ms there).
+static int solve_queens_first(dq_model* m, dq_tree_result* res, int32_t* first_solution) {
+    const int N = m->cm.queens_n;
+    DQ_CUDA(m->q_first.reserve(32));
+    DQ_CUDA(m->d_ctrl.reserve(32));
+    unsigned long long* ctrl = m->d_ctrl.p;
+    unsigned long long* h = m->pin;                  // [0] best key [1] nodes, [8..11] the solution bytes
+    h[0] = KEY_NONE; h[1] = 0;
+    QueensLaneArgs A;
+    A.n = N; A.k = 0; A.part_rank = 0; A.part_count = 1; A.part_level = -1;
+    A.records = nullptr; A.record_cap = 0; A.n_records = nullptr; A.cursor = nullptr; A.totals = nullptr; A.dfs_nodes = nullptr;
+    A.best_key = ctrl + 3; A.first_out = m->q_first.p;
+    DQ_CUDA(cudaEventRecord(m->ev0, m->stream));
+    DQ_CUDA(cudaMemcpyAsync(ctrl + 3, h, 2 * sizeof(unsigned long long), cudaMemcpyHostToDevice, m->stream));
+    k_queens_first_nodes<<<1, 32, 0, m->stream>>>(A, ctrl + 4);
+    DQ_CUDA(cudaGetLastError());
+    DQ_CUDA(cudaMemcpyAsync(h, ctrl + 3, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, m->stream));
+    DQ_CUDA(cudaMemcpyAsync(h + 8, m->q_first.p, 32, cudaMemcpyDeviceToHost, m->stream));
+    DQ_CUDA(cudaEventRecord(m->ev1, m->stream));
+    DQ_CUDA(cudaStreamSynchronize(m->stream));
+    float ms = 0;
+    DQ_CUDA(cudaEventElapsedTime(&ms, m->ev0, m->ev1));
+    const bool found = h[0] != KEY_NONE;
+    res->kernel_ms = ms; res->search_kernel_ms = 0; res->kernel_launches = 1; res->frontier_nodes = 0;
+    res->engine_used = DQ_ENGINE_LANE; res->split_depth_used = 0; res->n_prefixes = 1;
+    res->n_solutions = found ? 1 : 0; res->n_nodes = h[1]; res->first_key = found ? 0 : KEY_NONE;
+    res->outcome = found ? DQ_SAT : DQ_UNSAT;
+    if (found && first_solution) {
+        const uint8_t* sol = reinterpret_cast<const uint8_t*>(h + 8);
+        for (int i = 0; i < N; i++) first_solution[i] = m->cm.values[i][sol[i]];
+    }
+    m->last_queens_first = true; m->last_queens_first_nodes = h[1];
+    m->last_n_prefix = 0; m->last_depth = 0;
+    return DQ_OK;
+}
 
 // COUNT_ALL on a CLASS_QUEENS model with the lane-per-subtree engine: K level kernels + DFS + first-solution
 // kernel queued back to back, one host synchronisation at the end.
@@ -947,6 +988,10 @@ static int solve_tree_impl(dq_model* m, const dq_tree_opts* opts, dq_tree_result
     }
     // DQ_NO_CLASS=1 (measurements, tests): no structural class engine, every model takes the generic path
     static const bool no_class = getenv("DQ_NO_CLASS") != nullptr;
+    m->last_queens_first = false;
+    if (!no_class && !er && !count_all && m->cm.model_class == CLASS_QUEENS && m->cm.queens_n >= 3 && m->cm.queens_n <= kQueensMaxN &&
+        opts->engine == DQ_ENGINE_AUTO && opts->part_count == 1 && opts->node_budget == 0 && opts->split_depth <= 0)
+        return solve_queens_first(m, res, first_solution);
     if (!no_class && !er && count_all && m->cm.model_class == CLASS_QUEENS && m->cm.queens_n >= 3 && m->cm.queens_n <= kQueensMaxN && opts->engine != DQ_ENGINE_WARP && opts->engine != DQ_ENGINE_REG)
         return solve_queens_lane(m, opts, res, first_solution);
     if (m->cm.wide()) {
@@ -985,6 +1030,7 @@ int dq_tree_nodes_upto(dq_model* m, uint64_t key, uint64_t* nodes) {
     if (!m || !nodes) { g_err = "null argument"; return DQ_ERR_INVALID; }
     *nodes = 0;
     if (!m->uploaded) { g_err = "no solve to account for"; return DQ_ERR_INVALID; }
+    if (m->last_queens_first) { *nodes = m->last_queens_first_nodes; return DQ_OK; }     // (one partition: the whole count is its share)
     const int depth = m->last_depth;
     const unsigned long long n_prefix = m->last_n_prefix;
     unsigned long long total = 0;

@@ -255,7 +255,7 @@ constexpr int kQueensStageBytes = 0;                  // (the pools fill an SM's
 // (Measured and dropped: a whole level per step — lane v forward-checks value v in a row loop of its own, one ballot per
 // level.  Fewer steps but three times the instructions, and this warp shares its SM quarter with the bucket kernel's
 // warps: the 14-Queens solve went from 0.179 to 0.238 ms.)
-__device__ __forceinline__ void queens_first_owned(const QueensLaneArgs& A, int lane) {
+__device__ __forceinline__ void queens_first_owned(const QueensLaneArgs& A, int lane, unsigned long long* nodes_out = nullptr) {
     const int N = A.n, K = A.k;
     const uint32_t full = (1u << N) - 1u;
     const int own_depth = A.part_level + 1;              // prefixes of this depth are dealt to the partitions by key
@@ -264,9 +264,10 @@ __device__ __forceinline__ void queens_first_owned(const QueensLaneArgs& A, int 
     unsigned long long fkey = 0, key = 0;                // 64-bit: N^k outgrows 32 bits from k = 8 on (N = 17)
     uint32_t a = 0, l = 0, r = 0, cand = full;
     int d = 0;
+    unsigned long long tries = 0;                        // values tried = AssignVar calls (dequan.h:416-423) on the way
     for (;;) {
         if (cand == 0) {                                 // every value tried at this depth
-            if (d == 0) return;                          // no solution in this partition's share
+            if (d == 0) { if (nodes_out && lane == 0) *nodes_out = tries; return; }   // no solution in this partition's share
             --d;
             a = __shfl_sync(0xFFFFFFFFu, fa, d); l = __shfl_sync(0xFFFFFFFFu, fl, d); r = __shfl_sync(0xFFFFFFFFu, fr, d);
             cand = __shfl_sync(0xFFFFFFFFu, fc, d); key = __shfl_sync(0xFFFFFFFFu, fkey, d);
@@ -274,6 +275,7 @@ __device__ __forceinline__ void queens_first_owned(const QueensLaneArgs& A, int 
         }
         const uint32_t bit = cand & (0u - cand);
         cand ^= bit;
+        ++tries;
         const uint32_t v = (uint32_t)__ffs((int)bit) - 1u;
         const uint32_t na = a | bit, nl = (l | bit) << 1, nr = (r | bit) >> 1;
         const bool wiped = lane < N - 1 - d && ((na | ~full) | (nl << lane) | (nr >> lane)) == 0xFFFFFFFFu;
@@ -285,6 +287,7 @@ __device__ __forceinline__ void queens_first_owned(const QueensLaneArgs& A, int 
             if (lane == N - 1) fv = (uint32_t)__ffs((int)(full & ~(na | nl | nr))) - 1u;
             if (lane < N) A.first_out[lane] = (uint8_t)fv;
             if (lane == 0) *A.best_key = kchild;
+            if (nodes_out && lane == 0) *nodes_out = tries + 1ull;      // ... and the last variable's first value completes the solution
             return;
         }
         a = na; l = nl; r = nr; cand = full & ~(na | nl | nr); key = kchild;
@@ -302,6 +305,9 @@ __device__ __forceinline__ uint32_t queens_rows_occupied(uint32_t na, uint32_t n
 }
 
 __global__ void __launch_bounds__(32) k_queens_first_warp(QueensLaneArgs A) { queens_first_owned(A, (int)threadIdx.x); }
+// FIRST mode on the class (one partition): the same walk IS the reference's search up to its first solution — the values
+// it tries are the nodes.
+__global__ void __launch_bounds__(32) k_queens_first_nodes(QueensLaneArgs A, unsigned long long* nodes) { queens_first_owned(A, (int)threadIdx.x, nodes); }
 
 __global__ void __launch_bounds__(kQueensBucketMaxWarps * 32)
 k_queens_bucket(QueensLaneArgs A) {

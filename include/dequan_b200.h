@@ -110,7 +110,10 @@ enum dq_mode {
 };
 
 enum dq_engine {
-    DQ_ENGINE_AUTO  = 0,     /* fastest engine the compiled model qualifies for     */
+    DQ_ENGINE_AUTO  = 0,     /* fastest engine the compiled model qualifies for
+                                (FIRST mode on the N-Queens class, one partition, no
+                                budget: the class's first-solution warp, reported as
+                                DQ_ENGINE_LANE)                                      */
     DQ_ENGINE_WARP  = 1,     /* generic warp-cooperative DFS (any supported model)  */
     DQ_ENGINE_LANE  = 2,     /* lane-per-subtree / lane-per-instance closed-form DFS
                                 (N-Queens class trees, 9x9 Sudoku class batches,

@@ -67,6 +67,20 @@ def test_nqueens_count_and_first(golden, product_lib, engine, n):
     assert (f.status, f.nodes, f.first) == (g["first"]["status"], g["first"]["nodes"], g["first"]["first"]), f
 
 
+@pytest.mark.parametrize("n", [15, 17, 18, 20, 22])
+def test_queens_first_mode_on_the_class(product_lib, n):
+    """FIRST mode on the N-Queens class: one warp walks the reference's DFS; solution and node count against the oracle
+    (20-Queens: 145 151 nodes).  The count a later dq_tree_nodes_upto reports is the same."""
+    csp = nqueens(n)
+    want = O.solve(csp, "first")
+    m = api.Model(csp)
+    r = m.solve_tree("first")
+    assert (r.status, r.nodes, r.first) == (want.status, want.nodes, want.first) and r.engine == "lane"
+    assert m.nodes_upto(r.first_key) == want.nodes
+    w = m.solve_tree("first", engine="warp")
+    assert (w.status, w.nodes, w.first) == (want.status, want.nodes, want.first)
+
+
 @pytest.mark.parametrize("engine", ENGINES)
 def test_nqueens14_config(golden, product_lib, engine):
     """BASELINE config C2: 365 596 solutions, 19 787 662 nodes, first 0,2,4,6,11,9,12,3,13,8,1,5,7,10."""
@@ -185,6 +199,25 @@ def test_sudoku_batch_budget_and_unsat(product_lib):
     assert (api.OUTCOME[r.status[0]], int(r.nodes[0])) == (o.status, o.nodes) and o.status == "unsat"
     assert r.status[1] == 3
     assert r.status[2] == 1 and r.status[3] == 1
+
+
+def test_sudoku_batch_mixed_blank_counts(product_lib):
+    """The lanes' stacks are sized for the batch's largest number of blanks: an empty grid (81 blanks), a solved grid (none)
+    and a 17-given-like sparse grid next to 30-given puzzles, each against the oracle."""
+    cells = G.sudoku_batch(24, givens=30, seed=3)
+    tmpl = api.Model(sudoku_template())
+    solved = tmpl.solve_batch_cells(cells[:1]).solution[0]
+    cells[0] = 0
+    cells[1] = solved
+    sparse = solved.copy()
+    sparse[np.arange(81) % 4 != 0] = 0          # 21 givens of a valid grid
+    cells[2] = sparse
+    r = tmpl.solve_batch_cells(cells)
+    for i in range(len(cells)):
+        o = O.solve(sudoku(cells[i]), "first", 3_000_000)
+        assert (api.OUTCOME[r.status[i]], int(r.nodes[i])) == (o.status, o.nodes), i
+        assert r.solution[i].tolist() == o.first, i
+    assert int(r.nodes[1]) == 81
 
 
 def test_sudoku_batch_large_properties(product_lib):
