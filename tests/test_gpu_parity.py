@@ -634,8 +634,9 @@ def test_register_tree_engine_equals_generic_engine(product_lib):
     g = O.solve(nqueens(11), "count")
     parts = [m.solve_tree("count", split_depth=3, part_rank=r, part_count=3, engine="reg") for r in range(3)]
     assert (sum(p.solutions for p in parts), sum(p.nodes for p in parts)) == (g.solutions, g.nodes)
-    f = m.solve_tree("first")
-    assert f.engine == "reg" and f.launches == 1 and (f.nodes, f.first) == (O.solve(nqueens(11), "first").nodes, O.solve(nqueens(11), "first").first)
+    for engine, used_engine in (("reg", "reg"), ("auto", "lane")):     # (auto: the class's own first-solution warp)
+        f = m.solve_tree("first", engine=engine)
+        assert f.engine == used_engine and f.launches == 1 and (f.nodes, f.first) == (O.solve(nqueens(11), "first").nodes, O.solve(nqueens(11), "first").first)
     big = CSP()
     for _ in range(40):
         big.AddIntVar(0, 3)
