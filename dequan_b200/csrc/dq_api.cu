@@ -1424,7 +1424,7 @@ static int run_graphs_lane(int nv, int k, const int64_t* edge_off, const GraphBa
     for (int64_t i = 0; i < n; i++) max_m = std::max<long long>(max_m, edge_off[i + 1] - edge_off[i]);
     GroupGraphsArgs A;
     A.nv = nv; A.k = k; A.nvp = (nv + 16) & ~15;
-    A.rw = kGraphRow; A.over_cap = 0;
+    A.rw = kGraphRow; A.over_cap = 0; A.over_smem = 0;
     A.stride = graphs_record_bytes(A.nvp, A.rw, 0);
     A.edge_off = B.off; A.edges = B.edges; A.edge_bytes = B.edge_bytes; A.n = n;
     A.budget = budget; A.cursor = d_ctrl; A.colours = B.colours; A.nodes = B.nodes; A.status = B.status;
@@ -1451,8 +1451,17 @@ static int run_graphs_lane(int nv, int k, const int64_t* edge_off, const GraphBa
     A.over_cap = (int)((*h_over + 1) & ~1ull);
     A.stride = graphs_record_bytes(A.nvp, A.rw, A.over_cap);
     const bool packed = k <= 3 && getenv("DQ_GRAPHS_K4_LAYOUT") == nullptr;      // (byte 3 of the state words is free below four colours)
-    const size_t lane_smem = graphs_lane_warp_bytes(A.nv, A.nvp, A.over_cap, packed);
-    if (lane_smem > 220 * 1024) { g_err = "instance state exceeds shared memory"; return DQ_ERR_UNSUPPORTED; }
+    // the overflow pairs a lane keeps in shared memory: as many as cost no CTA per SM (the rest are read from the record)
+    A.over_smem = 0;
+    {
+        const size_t per_sm = 228 * 1024, cta_tax = 1024;
+        const size_t base = graphs_lane_warp_bytes(A.nv, A.nvp, 0, packed);
+        if (base > 220 * 1024) { g_err = "instance state exceeds shared memory"; return DQ_ERR_UNSUPPORTED; }
+        const size_t ctas_base = std::min<size_t>(per_sm / (base + cta_tax), 32);
+        const size_t room = per_sm / ctas_base - cta_tax - base;                 // bytes a CTA can grow by without losing a neighbour
+        A.over_smem = (int)std::min<size_t>((size_t)A.over_cap, room / 64);
+    }
+    const size_t lane_smem = graphs_lane_warp_bytes(A.nv, A.nvp, A.over_smem, packed);
     DQ_CUDA(d_adj.reserve((size_t)n * A.stride));
     A.adj = d_adj.p;
     // pass 2: the records

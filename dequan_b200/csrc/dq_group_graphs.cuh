@@ -44,6 +44,7 @@ struct GroupGraphsArgs {
     int nvp;                    // (nv + 16) & ~15: room for the dummy word S[nv]
     int rw;                     // neighbour slots per row (8)
     int over_cap;               // (vertex, neighbour) pairs the overflow list of one record can hold
+    int over_smem;              // k_graphs_lane: how many of them a lane keeps in shared memory (the rest are read from the record)
     int stride;                 // bytes of one adjacency record (16 x an odd number)
     const long long* edge_off;  // [n+1]                                  (k_graphs_adjacency)
     const uint8_t* edges;       // [total][2], 16-byte aligned, readable up to the next multiple of 16 bytes
@@ -172,8 +173,9 @@ k_graphs_adjacency(GroupGraphsArgs A, int stage_cap) {
                 }
             }
         __syncwarp();
-        // a vertex with more neighbours than slots: its last slot becomes the marker 0xFF (the search kernel's cue to walk
-        // the overflow list), the neighbour that sat there joins the list
+        // a vertex with more neighbours than slots: its last slot becomes a marker (a byte above nv: the search kernel's
+        // cue to walk the overflow list; which byte says where the vertex's pairs start in the list, sorted by vertex
+        // below), the neighbour that sat there joins the list
         for (int q = lane; q < nvp; q += 32)
             if (cnt[q] > (uint32_t)rw) {
                 const uint32_t o = atomicAdd(n_over, 1u);
@@ -184,6 +186,26 @@ k_graphs_adjacency(GroupGraphsArgs A, int stage_cap) {
                 }
             }
         __syncwarp();
+        if (!STATS_ONLY && !bad && *n_over && *n_over <= (uint32_t)A.over_cap) {
+            const uint32_t no = *n_over;
+            unsigned char* tmp = stage(b);                 // (the edge list has been consumed; 2 * no <= 2 * m bytes fit)
+            for (int q = lane; q < nvp; q += 32)
+                if (xflag[q]) {
+                    uint32_t before = 0;
+                    for (uint32_t x = 0; x < no; x++) before += over[2 * x] < (unsigned char)q;
+                    cnt[q] = before;                       // cursor of the vertex's pairs in the sorted list
+                    // marker 255 - start, kept above nv (a start that does not fit: the walk skips forward from the one that does)
+                    rec[q * rw + rw - 1] = (unsigned char)(255u - min(before, (uint32_t)(254 - nv)));
+                }
+            __syncwarp();
+            for (uint32_t x = lane; x < no; x += 32) {
+                const uint32_t pos = atomicAdd(&cnt[over[2 * x]], 1u);
+                tmp[2 * pos] = over[2 * x]; tmp[2 * pos + 1] = over[2 * x + 1];
+            }
+            __syncwarp();
+            for (uint32_t x = lane; x < 2 * no; x += 32) over[x] = tmp[x];
+            __syncwarp();
+        }
         if (STATS_ONLY) {
             if (lane == 0 && *n_over) atomicMax(A.totals + 5, (unsigned long long)*n_over);
             __syncwarp();
@@ -237,8 +259,8 @@ __device__ __forceinline__ void sts16(uint32_t addr, uint32_t v) {
 // warp instead of 192, i.e. 8 warps per SM instead of 5 at 200 vertices.
 // (At 200 vertices and three colours: 201 S words + 13 colour words + the overflow pairs = 27.4 KB per warp, the most
 // that still lets 8 warps share an SM's 228 KB; a staging buffer for the record would cost the eighth.)
-__host__ __device__ inline size_t graphs_lane_warp_bytes(int nv, int nvp, int over_cap, bool packed) {
-    return (size_t)(nv + 1) * 128 + (packed ? (size_t)((nv + 15) / 16) * 128 : (size_t)nvp * 64) + (size_t)over_cap * 64 + 16;
+__host__ __device__ inline size_t graphs_lane_warp_bytes(int nv, int nvp, int over_smem, bool packed) {
+    return (size_t)(nv + 1) * 128 + (packed ? (size_t)((nv + 15) / 16) * 128 : (size_t)nvp * 64) + (size_t)over_smem * 64 + 16;
 }
 
 template <bool PACKED>
@@ -253,14 +275,16 @@ k_graphs_lane(GroupGraphsArgs A) {
     const uint32_t s_s = base_s + 4u * lane;                                  // S[q]    at s_s + q * 128
     const uint32_t co_s = base_s + (uint32_t)(nv + 1) * 128u + (PACKED ? 4u : 2u) * lane;   // K4: co[i] at co_s + i * 64: byte 0 col[i], byte 1 open[i]; PACKED: colours of levels 16j .. 16j+15 at co_s + j * 128
     const uint32_t over_base = base_s + (uint32_t)(nv + 1) * 128u + (PACKED ? (uint32_t)((nv + 15) / 16) * 128u : (uint32_t)nvp * 64u);
-    const uint32_t over_s = over_base + 2u * lane;                            // over[p] at over_s + p * 64: (vertex, neighbour)
+    const uint32_t over_s = over_base + 2u * lane;                            // over[p] at over_s + p * 64: (vertex | neighbour << 8), sorted by vertex
+    const uint16_t* over_g = reinterpret_cast<const uint16_t*>(A.adj + (size_t)nvp * 9u) + 8;   // ... and in the record, for p >= A.over_smem
+    auto over_pair = [&](uint32_t p) -> uint32_t { return p < (uint32_t)A.over_smem ? lds16(over_s + p * 64u) : (uint32_t)__ldg(over_g + p); };
     // the neighbour rows stay in the record (HBM, L2- and L1-resident while the search is around that depth): 8 bytes per
     // level and lane, the next level's row fetched a trip ahead
     const uint2* rows_g = reinterpret_cast<const uint2*>(A.adj);
     uint2 row_cur = make_uint2(0u, 0u);                 // rows[d] when row_ok
     bool row_ok = false;
     // lanes without an instance run the trip on whatever their slots hold: start from zeros (vertex 0, no neighbours)
-    for (uint32_t x = 4u * lane; x < (uint32_t)graphs_lane_warp_bytes(nv, nvp, A.over_cap, PACKED); x += 128u) sts32(base_s + x, 0u);
+    for (uint32_t x = 4u * lane; x < (uint32_t)graphs_lane_warp_bytes(nv, nvp, A.over_smem, PACKED); x += 128u) sts32(base_s + x, 0u);
     __syncwarp();
     const uint32_t init_word = A.k >= 4 ? 0u : (FULL << (8 * A.k));
     const unsigned long long budget = A.budget ? A.budget : ~0ull;
@@ -296,7 +320,8 @@ k_graphs_lane(GroupGraphsArgs A) {
         // the row of the level a dead end here goes back to, a trip ahead like the next level's (half of all trips end
         // that way, and a row loaded on arrival leaves its L2 latency exposed)
         const uint2 row_back = __ldg(rows_g + min(d_pop, (uint32_t)nv));
-        const bool more = (r_hi >> 24) == 0xFFu;                     // the row goes on in the overflow list
+        const bool more = (r_hi >> 24) > (uint32_t)nv;               // a marker: the row goes on in the overflow list ...
+        const uint32_t over_start = 255u - (r_hi >> 24);             // ... from this position on (the list is sorted by vertex)
         if (more) r_hi = (r_hi & 0x00FFFFFFu) | ((uint32_t)nv << 24);   // (the marker is not a vertex: look at the dummy instead)
         const uint32_t y = (255u - d) * ymul, yl = y & 0x7F7F7F7Fu;           // bytes below 255-d: in the domain
         const uint32_t mark = 254u - d;
@@ -359,17 +384,18 @@ k_graphs_lane(GroupGraphsArgs A) {
                         for (int v = lane; v < nv; v += 32) A.colours[(size_t)i_new * nv + v] = 0xFF;
                         needy |= 1u << t;                          // the lane still needs an instance
                     } else {
-                        // the lane's columns: the state words, and the few neighbour pairs its rows of 8 had no room for
+                        // the lane's columns: the state words, and the few neighbour pairs its rows had no room for
                         // (straight from the record: its rows are read from there level by level anyway)
                         for (uint32_t q = lane; q <= (uint32_t)nv; q += 32)
                             sts32(base_s + q * 128u + 4u * t, q == (uint32_t)nv ? FULL : init_word);
                         const uint16_t* tail = reinterpret_cast<const uint16_t*>(A.adj + (size_t)i_new * A.stride + (size_t)nvp * 9u);
                         const uint32_t n_ov = __ldg(tail);
-                        for (uint32_t p = lane; p < (uint32_t)A.over_cap; p += 32)
+                        for (uint32_t p = lane; p < (uint32_t)A.over_smem; p += 32)
                             sts16(over_base + p * 64u + 2u * t, p < n_ov ? (uint32_t)__ldg(tail + 8 + p) : 0xFFFFu);
                         if ((int)lane == t) {
                             inst = i_new; have = true; n_over = n_ov;
                             rows_g = reinterpret_cast<const uint2*>(A.adj + (size_t)i_new * A.stride);
+                            over_g = tail + 8;
                             row_ok = false;
                             nodes_base = 0; d = 0; sp = 0; top = 0xFFu; ret = false;
                             left0 = left = (int)min(budget, (unsigned long long)kLeftCap);
@@ -381,13 +407,16 @@ k_graphs_lane(GroupGraphsArgs A) {
                 continue;                                          // (the loads above are stale: start the trip over)
             }
             // ---- the neighbours of d beyond its row ----
-            if (have && more)
-                for (uint32_t p = 0; p < n_over; p++) {
-                    const uint32_t pr = lds16(over_s + p * 64u);
-                    if ((pr & 0xFFu) != d) continue;
+            if (have && more) {
+                uint32_t p = over_start;
+                while (p < n_over && (over_pair(p) & 0xFFu) < d) ++p;
+                for (; p < n_over; p++) {
+                    const uint32_t pr = over_pair(p);
+                    if ((pr & 0xFFu) != d) break;
                     const uint32_t fo = bytes_below(lds32(s_s + (pr >> 8) * 128u), y, yl);
                     if ((fo & (fo - 1u)) == 0u) fail |= fo;
                 }
+            }
         }
         // colour c wipes out a later neighbour exactly when that neighbour's domain is {c} (dequan.h:663-668): the
         // colours of `cand` up to the first one outside `fail` are the nodes the reference visits at this level
@@ -419,15 +448,18 @@ k_graphs_lane(GroupGraphsArgs A) {
                 sts8(co_s + d * 64u, (unit * 0x00010203u) >> 24);
                 sts8(co_s + sp * 64u + 1u, d);
             }
-            if (more)
-                for (uint32_t p = 0; p < n_over; p++) {
-                    const uint32_t pr = lds16(over_s + p * 64u);
-                    if ((pr & 0xFFu) != d) continue;
+            if (more) {
+                uint32_t p = over_start;
+                while (p < n_over && (over_pair(p) & 0xFFu) < d) ++p;
+                for (; p < n_over; p++) {
+                    const uint32_t pr = over_pair(p);
+                    if ((pr & 0xFFu) != d) break;
                     const uint32_t ao = s_s + (pr >> 8) * 128u;
                     const uint32_t wo = lds32(ao);
                     const uint32_t m = (bytes_below(wo, y, yl) >> 7) * 255u;
                     sts32(ao, (wo & ~m) | (put & m));
                 }
+            }
         }
         // down, back to the deepest level with colours left (return false, dequan.h:569-570), or done
         if (have) {
