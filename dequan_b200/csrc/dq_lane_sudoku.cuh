@@ -942,6 +942,7 @@ k_sudoku_count(SudokuArgs A) {
             }
         }
         unsigned closed_now = 0;                // tasks this lane took and closed on the spot
+        uint32_t got_info = 0, got_snap = 0;    // the task this lane has just drawn (info != 0, not a null task)
         if (waiting && (poll_now || (iter & 7) == 0) && ticket < A.task_cap) {
             volatile uint32_t* rec = reinterpret_cast<volatile uint32_t*>(A.tasks + ticket);
             const uint32_t info = rec[2];       // the publisher writes `info` last
@@ -949,52 +950,71 @@ k_sudoku_count(SudokuArgs A) {
                 __threadfence();
                 waiting = false;
                 L.puzzle = rec[0];
-                const uint32_t snap_id = rec[1];
                 if (info & SKT_NULL) closed_now = 1;
-                else {
-                    const uint4* dg = A.digest[L.puzzle].v;
-                    L.nblank = (int)(__ldg(dg).w & 0xFF);
-                    sk_load_tables(S, t, dg);
-                    bt = sk_load_blank_t(dg);
-                    L.nodes = 0; L.nodes_hi = 0;
-                    L.passrem = 0; L.dom_rem = 0;
-                    L.have = true;
-                    donate_at = A.force_donate ? A.force_donate : A.donate_min;
-                    split_at = kSplitGap;
-                    if (info & SKT_ROOT) {
-                        // path values at the levels above, then the task's own value at its level
-                        const int l0 = (int)(info & 0xFF);
-                        const uint32_t v0 = (info >> 8) & 0xF;
-                        const uint8_t* sol = A.solution + (size_t)L.puzzle * A.stride;
-                        for (int l = 0; l <= l0; l++) {
-                            const int q = sk_cell_at(S, t, l);
-                            const uint32_t v = l < l0 ? (uint32_t)sol[q] - 1u : v0;
-                            sk_commit(S, t, sk_decode(q), 1u << v);
-                            S.stk[l][t] = (uint16_t)(v << 9);
-                        }
-                        L.sp = l0 + 1; L.base_sp = l0 + 1;
-                        if (L.sp >= L.nblank) { atomicOr(A.ctrl + SKC_ERROR, 4ull); L.have = false; closed_now = 1; }
-                        else { L.p = sk_cell_at(S, t, L.sp); L.enter = true; }
-                    } else {
-                        // resume from the donor's snapshot: re-assign the values chosen at levels 0..hi-1; the untried
-                        // values of levels [lo, hi] are this piece's, everything shallower belongs to other tasks
-                        const int lo = (int)(info & 0xFF), hi = (int)((info >> 8) & 0xFF);
-                        const uint4* sb = A.snaps + (size_t)snap_id * kSnapWords;
-                        for (int l = 0; l < hi; l++) {
-                            const uint32_t e = sk_snap_entry(sb, l);
-                            sk_commit(S, t, sk_decode(sk_cell_at(S, t, l)), 1u << (e >> 9));
-                            S.stk[l][t] = (uint16_t)(l >= lo ? e : (e & 0xFE00u));
-                        }
-                        L.sp = hi; L.base_sp = lo;
-                        L.p = sk_cell_at(S, t, hi);
-                        L.c = sk_decode(L.p);
-                        const uint32_t e = sk_snap_entry(sb, hi);
-                        L.passrem = e & 0x1FF;
-                        if (info & SKT_TOP) L.dom_rem = sk_snap_entry(sb, hi + 1) & 0x1FF;
-                        else L.dom_rem = ~sk_used_at(S, t, L.c) & 0x1FF & ~((2u << (e >> 9)) - 1u);   // the values above the one the donor took here
-                        L.enter = false;
-                    }
-                }
+                else { got_info = info; got_snap = rec[1]; }
+            }
+        }
+        // A drawn task is set up by the WHOLE warp, one task after the other: the instance's tables into the lane's
+        // columns (63 words, two per helper), then the path above the task — the solution's values (root task) or the
+        // donor's (piece), one level per helper, OR-ed into the used masks with shared-memory atomics.  Done by the
+        // lane alone this was a loop of ~40 instructions per level with one lane in 32 active: a third of the kernel.
+        for (uint32_t todo = __ballot_sync(0xFFFFFFFFu, got_info != 0u); todo; todo &= todo - 1u) {
+            const int src = __ffs((int)todo) - 1;
+            const uint32_t pz = __shfl_sync(0xFFFFFFFFu, L.puzzle, src), inf = __shfl_sync(0xFFFFFFFFu, got_info, src);
+            const uint32_t sn = __shfl_sync(0xFFFFFFFFu, got_snap, src);
+            const int ts = (t & ~31) + src;                                // the column of the lane that owns the task
+            const uint32_t* dgw = reinterpret_cast<const uint32_t*>(A.digest[pz].v);
+            uint32_t* tab = &S.rowp[0][0];
+            for (int w = lane; w < kTableWords; w += 32) tab[w * kSudokuBlock + ts] = __ldg(dgw + 4 + w);
+            __syncwarp();
+            const bool root = (inf & SKT_ROOT) != 0u;
+            const int lo = (int)(inf & 0xFF), hi = (int)((inf >> 8) & 0xFF);    // root: the task's level / value (low nibble of hi)
+            const int n_replay = root ? lo + 1 : hi;
+            const uint8_t* sol = A.solution + (size_t)pz * A.stride;
+            const uint4* sb = A.snaps + (size_t)sn * kSnapWords;
+            for (int l = lane; l < n_replay; l += 32) {
+                const int q = sk_cell_at(S, ts, l);
+                uint32_t v, entry;
+                if (root) { v = l < lo ? (uint32_t)sol[q] - 1u : (uint32_t)(hi & 0xF); entry = v << 9; }
+                else { const uint32_t e = sk_snap_entry(sb, l); v = e >> 9; entry = l >= lo ? e : (e & 0xFE00u); }
+                const SkCell k = sk_decode(q);
+                const uint32_t bit = 1u << v;
+                atomicOr(&S.rowp[k.band][ts], bit << (10 * k.rm));
+                atomicOr(&S.boxr[k.box][ts], sk_rep(bit));
+                atomicOr(&S.colp[k.s][ts], bit << (10 * k.f));
+                S.stk[l][ts] = (uint16_t)entry;
+            }
+            __syncwarp();
+        }
+        if (got_info) {
+            const uint32_t info = got_info;
+            const uint4* dg = A.digest[L.puzzle].v;
+            L.nblank = (int)(__ldg(dg).w & 0xFF);
+            bt = sk_load_blank_t(dg);
+            L.nodes = 0; L.nodes_hi = 0;
+            L.passrem = 0; L.dom_rem = 0;
+            L.have = true;
+            donate_at = A.force_donate ? A.force_donate : A.donate_min;
+            split_at = kSplitGap;
+            if (info & SKT_ROOT) {
+                // path values at the levels above, then the task's own value at its level: committed above
+                const int l0 = (int)(info & 0xFF);
+                L.sp = l0 + 1; L.base_sp = l0 + 1;
+                if (L.sp >= L.nblank) { atomicOr(A.ctrl + SKC_ERROR, 4ull); L.have = false; closed_now = 1; }
+                else { L.p = sk_cell_at(S, t, L.sp); L.enter = true; }
+            } else {
+                // resumed from the donor's snapshot: the values chosen at levels 0..hi-1 are committed above; the untried
+                // values of levels [lo, hi] are this piece's, everything shallower belongs to other tasks
+                const int lo = (int)(info & 0xFF), hi = (int)((info >> 8) & 0xFF);
+                const uint4* sb = A.snaps + (size_t)got_snap * kSnapWords;
+                L.sp = hi; L.base_sp = lo;
+                L.p = sk_cell_at(S, t, hi);
+                L.c = sk_decode(L.p);
+                const uint32_t e = sk_snap_entry(sb, hi);
+                L.passrem = e & 0x1FF;
+                if (info & SKT_TOP) L.dom_rem = sk_snap_entry(sb, hi + 1) & 0x1FF;
+                else L.dom_rem = ~sk_used_at(S, t, L.c) & 0x1FF & ~((2u << (e >> 9)) - 1u);   // the values above the one the donor took here
+                L.enter = false;
             }
         }
         poll_now = false;
