@@ -161,6 +161,8 @@ struct dq_model {
     std::vector<uint8_t> h_blob;                // its host image (kept while the copy may be in flight)
     uint32_t *t_ent_off = nullptr, *t_ent_moff = nullptr, *t_masks = nullptr, *t_dom0 = nullptr;   // masks / dom0: 64-bit words when cm.wide()
     bool last_wide = false;
+    uint8_t* early_sol_host = nullptr;             // dq_solve_batch_cells: host buffer the solutions may be copied to as soon as they are final
+    bool early_sol_done = false;
     bool last_queens_first = false;                 // the last solve was solve_queens_first (dq_tree_nodes_upto answers from its count)
     unsigned long long last_queens_first_nodes = 0;
     uint32_t* t_ent = nullptr;
@@ -1324,6 +1326,15 @@ static int run_batch_sudoku(dq_model* m, const uint8_t* cells_dev, int64_t n, in
     // the hard list's length stays on the device: the next three kernels are sized for the machine and find it in ctrl
     k_sudoku_strong<<<(unsigned)(occ_strong * sms), 128, smem_strong, m->stream>>>(A);
     mark(3);
+    // Host-buffer call without a node budget: every solution is final here (what follows only counts nodes), so the
+    // 81 bytes per instance go home on the side stream while the counting stage runs.
+    if (m->early_sol_host && !A.user_budget) {
+        DQ_CUDA(cudaEventRecord(m->ev_fork, m->stream));
+        DQ_CUDA(cudaStreamWaitEvent(m->stream2, m->ev_fork, 0));
+        DQ_CUDA(cudaMemcpyAsync(m->early_sol_host, sol_dev, (size_t)n * stride, cudaMemcpyDeviceToHost, m->stream2));
+        DQ_CUDA(cudaEventRecord(m->ev_join, m->stream2));
+        m->early_sol_done = true;
+    }
     k_sudoku_walk<<<(unsigned)std::min<long long>(occ_walk * sms, (long long)((n + kSudokuBlock - 1) / kSudokuBlock)), kSudokuBlock, smem, m->stream>>>(A);
     mark(4);
     k_sudoku_count<<<(unsigned)(occ_count * sms), kSudokuBlock, smem, m->stream>>>(A);
@@ -1352,7 +1363,9 @@ static int run_batch_sudoku(dq_model* m, const uint8_t* cells_dev, int64_t n, in
     }
     const unsigned long long n_def = hc[10];
     unsigned long long hw[8] = {0};
+    if (m->early_sol_done) DQ_CUDA(cudaStreamWaitEvent(m->stream, m->ev_join, 0));
     if (n_def) {
+        m->early_sol_done = false;                 // (the generic engine is about to write the deferred instances' solutions)
         dq_batch_opts o2 = opts ? *opts : dq_batch_opts{0, 0, 0};
         o2.engine = DQ_ENGINE_WARP;
         rc = run_batch_cells(m, cells_dev, (int64_t)n_def, stride, &o2, sol_dev, nodes_dev, status_dev, nullptr, m->s_deferred.p, false);
@@ -1394,9 +1407,11 @@ int dq_solve_batch_cells(dq_model* m, const uint8_t* cells, int64_t n, int32_t s
     DQ_CUDA(m->b_cells.reserve(bytes)); DQ_CUDA(m->b_solution.reserve(bytes));
     DQ_CUDA(m->b_status.reserve(n)); DQ_CUDA(m->b_nodes.reserve(n));
     DQ_CUDA(cudaMemcpyAsync(m->b_cells.p, cells, bytes, cudaMemcpyHostToDevice, m->stream));
+    m->early_sol_host = solution; m->early_sol_done = false;
     rc = run_batch_cells(m, m->b_cells.p, n, stride, opts, m->b_solution.p, m->b_nodes.p, m->b_status.p, stats);
-    if (rc != DQ_OK) return rc;
-    DQ_CUDA(cudaMemcpyAsync(solution, m->b_solution.p, bytes, cudaMemcpyDeviceToHost, m->stream));
+    m->early_sol_host = nullptr;
+    if (rc != DQ_OK) { cudaStreamSynchronize(m->stream2); return rc; }     // (nothing may still be writing the caller's buffer)
+    if (!m->early_sol_done) DQ_CUDA(cudaMemcpyAsync(solution, m->b_solution.p, bytes, cudaMemcpyDeviceToHost, m->stream));
     DQ_CUDA(cudaMemcpyAsync(nodes, m->b_nodes.p, (size_t)n * 8, cudaMemcpyDeviceToHost, m->stream));
     DQ_CUDA(cudaMemcpyAsync(status, m->b_status.p, (size_t)n, cudaMemcpyDeviceToHost, m->stream));
     DQ_CUDA(cudaStreamSynchronize(m->stream));
