@@ -381,7 +381,7 @@ static int solve_queens_first(dq_model* m, dq_tree_result* res, int32_t* first_s
 // kernel queued back to back, one host synchronisation at the end.
 static int solve_queens_lane(dq_model* m, const dq_tree_opts* opts, dq_tree_result* res, int32_t* first_solution) {
     const int N = m->cm.queens_n;
-    // Split depth: measured per board size on B200 (scripts/sweep_k.py, profiles/r1_queens_split_depth.txt), see below.
+    // Split depth: measured per board size on B200 (scripts/sweep_k.py, profiles/r2_queens_split_depth.txt), see below.
     int K = 0;
     // estimated FC-surviving prefixes per depth (sizes the record lists): each level multiplies by about N - 2.2*depth
     auto estimate = [&](int k) { double e = 1; for (int i = 0; i < k; i++) e *= std::max(N - 2.2 * i, 3.6); return e; };
@@ -389,12 +389,13 @@ static int solve_queens_lane(dq_model* m, const dq_tree_opts* opts, dq_tree_resu
     int rc = DQ_OK;
     if (opts->split_depth > 0) K = std::min(opts->split_depth, std::min(N - 3, 12));
     else {
-        // measured per N (scripts/sweep_k.py, profiles/r1_queens_split_depth.txt): small boards are bound by the launches of
-        // the levels, large ones by keeping the pools fed to the end (18 queens: 132 -> 121 ms at depth 8); the partitions
-        // of a strongly scaled 17-Queens solve hold 1/parts of the records each and split one level deeper as well
-        // (8 partitions: 2.43 -> 2.28 ms, scripts/parts_k.py)
+        // measured per N (scripts/sweep_k.py, profiles/r2_queens_split_depth.txt): small boards are bound by the launches of
+        // the levels, large ones by keeping the pools fed to the end; the same depths serve the partitions of a strongly
+        // scaled solve (scripts/parts_k.py: 17-Queens in 8 partitions, slowest partition 1.52 / 1.38 / 1.43 ms at depth 7 / 8 / 9)
         if (N <= 13) K = std::max(N - 8, 0);
-        else if (N <= 16) K = 7;                   // 14: 0.179 ms (depth 5: 0.172 with a bucket kernel twice as long: the step is bound by the first-solution warp either way);                   // 15: 0.34 ms (depth 6 / 8: 0.40 / 0.38); 16: 1.51 ms (depth 8: 1.55)
+        else if (N <= 16) K = 7;                   // 14: 0.179 ms (depth 5: 0.172 with a bucket kernel twice as long: the step is
+                                                   // bound by the first-solution warp either way); 15: 0.34 ms (depth 6 / 8: 0.40 /
+                                                   // 0.38); 16: 1.51 ms (depth 8: 1.55)
         else if (N == 17) K = 8;                   // 35 M records: 9.65 ms (depth 7 / 9: 9.68 / 10.24; the levels cost 0.16 / 0.44 / 1.44 ms)
         else K = 8;
     }
