@@ -255,7 +255,8 @@ constexpr int kQueensStageBytes = 0;                  // (the pools fill an SM's
 // (Measured and dropped: a whole level per step — lane v forward-checks value v in a row loop of its own, one ballot per
 // level.  Fewer steps but three times the instructions, and this warp shares its SM quarter with the bucket kernel's
 // warps: the 14-Queens solve went from 0.179 to 0.238 ms.  And the two lowest untried values per vote, lanes 0-15 on the
-// rows of the first and 16-31 on the rows of the second: the warp alone 152 -> 205 us on 14-Queens.)
+// rows of the first and 16-31 on the rows of the second: the warp alone 152 -> 205 us on 14-Queens; both values on all
+// lanes, two chains and two votes per step: 187 us — most values pass, so the second verdict is rarely the one needed.)
 __device__ __forceinline__ void queens_first_owned(const QueensLaneArgs& A, int lane, unsigned long long* nodes_out = nullptr) {
     const int N = A.n, K = A.k;
     const uint32_t full = (1u << N) - 1u;
