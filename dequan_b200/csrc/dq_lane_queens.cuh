@@ -262,37 +262,48 @@ __device__ __forceinline__ void queens_first_owned(const QueensLaneArgs& A, int 
     const uint32_t full = (1u << N) - 1u;
     const int own_depth = A.part_level + 1;              // prefixes of this depth are dealt to the partitions by key
     if (A.part_count > 1 && own_depth <= 0 && A.part_rank != 0) return;
-    uint32_t fa = 0, fl = 0, fr = 0, fc = 0, fv = 0;
-    unsigned long long fkey = 0, key = 0;                // 64-bit: N^k outgrows 32 bits from k = 8 on (N = 17)
+    uint32_t fa = 0, fl = 0, fr = 0, fc = 0, fb = 0;     // lane d: the frame of depth d (state before its value, values left, the value's bit)
     uint32_t a = 0, l = 0, r = 0, cand = full;
     int d = 0;
     unsigned long long tries = 0;                        // values tried = AssignVar calls (dequan.h:416-423) on the way
+    // Nothing in the loop needs a value's INDEX or the prefix key (a find-first-set and a 64-bit multiply-add per node
+    // that the in-order issue would wait for): frames keep the value's bit, and keys are folded out of the frames
+    // where they are used — at the level the partitions are dealt at, and once at the end.
+    // base-N number of the values at depths 0 .. upto-1 (frames of lanes 0 .. upto-1), 64-bit: N^k outgrows 32 bits from k = 8 on
+    auto key_of = [&](int upto) {
+        unsigned long long key = 0;
+        for (int i = 0; i < upto; i++) key = key * (unsigned long long)N + ((unsigned)__ffs((int)__shfl_sync(0xFFFFFFFFu, fb, i)) - 1u);
+        return key;
+    };
     for (;;) {
         if (cand == 0) {                                 // every value tried at this depth
             if (d == 0) { if (nodes_out && lane == 0) *nodes_out = tries; return; }   // no solution in this partition's share
             --d;
             a = __shfl_sync(0xFFFFFFFFu, fa, d); l = __shfl_sync(0xFFFFFFFFu, fl, d); r = __shfl_sync(0xFFFFFFFFu, fr, d);
-            cand = __shfl_sync(0xFFFFFFFFu, fc, d); key = __shfl_sync(0xFFFFFFFFu, fkey, d);
+            cand = __shfl_sync(0xFFFFFFFFu, fc, d);
             continue;
         }
         const uint32_t bit = cand & (0u - cand);
         cand ^= bit;
         ++tries;
-        const uint32_t v = (uint32_t)__ffs((int)bit) - 1u;
         const uint32_t na = a | bit, nl = (l | bit) << 1, nr = (r | bit) >> 1;
         const bool wiped = lane < N - 1 - d && ((na | ~full) | (nl << lane) | (nr >> lane)) == 0xFFFFFFFFu;
         if (__any_sync(0xFFFFFFFFu, wiped)) continue;
-        const unsigned long long kchild = d < K ? key * (unsigned long long)N + v : key;      // the key stops growing at depth k
-        if (A.part_count > 1 && d + 1 == own_depth && (uint32_t)(kchild % (unsigned long long)A.part_count) != (uint32_t)A.part_rank) continue;
-        if (lane == d) { fa = a; fl = l; fr = r; fc = cand; fkey = key; fv = v; }
+        if (A.part_count > 1 && d + 1 == own_depth) {
+            const unsigned long long kchild = key_of(d) * (unsigned long long)N + ((unsigned)__ffs((int)bit) - 1u);   // (own_depth <= k)
+            if ((uint32_t)(kchild % (unsigned long long)A.part_count) != (uint32_t)A.part_rank) continue;
+        }
+        if (lane == d) { fa = a; fl = l; fr = r; fc = cand; fb = bit; }
         if (d == N - 2) {
+            uint32_t fv = (uint32_t)__ffs((int)fb) - 1u;
             if (lane == N - 1) fv = (uint32_t)__ffs((int)(full & ~(na | nl | nr))) - 1u;
             if (lane < N) A.first_out[lane] = (uint8_t)fv;
-            if (lane == 0) *A.best_key = kchild;
+            const unsigned long long key = key_of(K < N - 1 ? K : N - 1);       // the key stops growing at depth k
+            if (lane == 0) *A.best_key = key;
             if (nodes_out && lane == 0) *nodes_out = tries + 1ull;      // ... and the last variable's first value completes the solution
             return;
         }
-        a = na; l = nl; r = nr; cand = full & ~(na | nl | nr); key = kchild;
+        a = na; l = nl; r = nr; cand = full & ~(na | nl | nr);
         ++d;
     }
 }
