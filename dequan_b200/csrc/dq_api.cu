@@ -1408,7 +1408,12 @@ int dq_solve_batch_cells(dq_model* m, const uint8_t* cells, int64_t n, int32_t s
     DQ_CUDA(m->b_cells.reserve(bytes)); DQ_CUDA(m->b_solution.reserve(bytes));
     DQ_CUDA(m->b_status.reserve(n)); DQ_CUDA(m->b_nodes.reserve(n));
     DQ_CUDA(cudaMemcpyAsync(m->b_cells.p, cells, bytes, cudaMemcpyHostToDevice, m->stream));
-    m->early_sol_host = solution; m->early_sol_done = false;
+    // (only into page-locked memory: an "asynchronous" copy into pageable memory holds the calling thread until it is
+    // done, which would park the pipeline between its stages)
+    cudaPointerAttributes pa;
+    const bool pinned = cudaPointerGetAttributes(&pa, solution) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+    if (!pinned) cudaGetLastError();
+    m->early_sol_host = pinned ? solution : nullptr; m->early_sol_done = false;
     rc = run_batch_cells(m, m->b_cells.p, n, stride, opts, m->b_solution.p, m->b_nodes.p, m->b_status.p, stats);
     m->early_sol_host = nullptr;
     if (rc != DQ_OK) { cudaStreamSynchronize(m->stream2); return rc; }     // (nothing may still be writing the caller's buffer)
