@@ -196,6 +196,7 @@ struct dq_model {
     DevBuf<uint32_t> s_hard;
     DevBuf<SudokuTask> s_tasks;
     DevBuf<uint4> s_snaps;
+    DevBuf<uint32_t> s_snap_state;
     DevBuf<int> s_deferred;
     unsigned long long s_tasks_used = 0;
     // dq_solve_tree_multi: one worker thread + one clone of the compiled model per device
@@ -618,7 +619,7 @@ void dq_free(dq_model* m) {
         m->e_out.release(); m->e_prefix.release(); m->e_seq.release();
         m->q_records.release(); m->q_records2.release(); m->q_first.release();
         m->b_cells.release(); m->b_solution.release(); m->b_status.release(); m->b_nodes.release();
-        m->s_digest.release(); m->s_ctrl.release(); m->s_hard.release(); m->s_tasks.release(); m->s_snaps.release();
+        m->s_digest.release(); m->s_ctrl.release(); m->s_hard.release(); m->s_tasks.release(); m->s_snaps.release(); m->s_snap_state.release();
         m->s_deferred.release();
         for (auto& l : m->levels) {
             l.dmask.release(); l.surv.release(); l.dmask64.release(); l.surv64.release(); l.child_off.release(); l.parent_of.release();
@@ -1259,20 +1260,21 @@ static int run_batch_sudoku(dq_model* m, const uint8_t* cells_dev, int64_t n, in
                             uint8_t* sol_dev, unsigned long long* nodes_dev, uint8_t* status_dev, dq_batch_stats* st) {
     int rc = DQ_OK;
     // the number of pieces handed over at the tail does not shrink with the batch: generous floors (64 MB + 192 MB)
-    const unsigned long long task_cap = std::max<unsigned long long>(1u << 22, std::min<unsigned long long>(8ull * n, 1ull << 25));
+    const unsigned long long task_cap = std::max<unsigned long long>(1u << 24, std::min<unsigned long long>(8ull * n, 1ull << 26));   // (16 B each; a task per 512 counted nodes and more)
     const unsigned long long snap_cap = std::max<unsigned long long>(1u << 20, std::min<unsigned long long>(2ull * n, 1ull << 23));
     const bool fresh_pool = m->s_tasks.cap < task_cap;
     DQ_CUDA(m->s_digest.reserve(n)); DQ_CUDA(m->s_hard.reserve(2 * (size_t)n)); DQ_CUDA(m->s_ctrl.reserve(16));
-    DQ_CUDA(m->s_tasks.reserve(task_cap)); DQ_CUDA(m->s_snaps.reserve(snap_cap * kSnapWords));
+    DQ_CUDA(m->s_tasks.reserve(task_cap)); DQ_CUDA(m->s_snaps.reserve(snap_cap * kSnapWords)); DQ_CUDA(m->s_snap_state.reserve(snap_cap));
     unsigned long long* ctrl = m->s_ctrl.p;       // SkCtrl words
     DQ_CUDA(cudaMemsetAsync(ctrl, 0, 16 * sizeof(unsigned long long), m->stream));
+    DQ_CUDA(cudaMemsetAsync(m->s_snap_state.p, 0, snap_cap * sizeof(uint32_t), m->stream));
     // task records double as "published" flags: the part the previous call used must read zero again
     const unsigned long long dirty = fresh_pool ? m->s_tasks.cap : std::min<unsigned long long>(m->s_tasks_used, m->s_tasks.cap);
     if (dirty) DQ_CUDA(cudaMemsetAsync(m->s_tasks.p, 0, dirty * sizeof(SudokuTask), m->stream));
     SudokuArgs A;
     A.digest = m->s_digest.p; A.n = n; A.stride = stride; A.cells = cells_dev; A.solution = sol_dev; A.nodes = nodes_dev;
     A.status = status_dev; A.hard = m->s_hard.p; A.tasks = m->s_tasks.p; A.task_cap = task_cap;
-    A.snaps = m->s_snaps.p; A.snap_cap = snap_cap; A.ctrl = ctrl; A.user_budget = opts ? opts->node_budget : 0;
+    A.snaps = m->s_snaps.p; A.snap_cap = snap_cap; A.snap_state = m->s_snap_state.p; A.ctrl = ctrl; A.user_budget = opts ? opts->node_budget : 0;
     A.force_donate = opts && opts->task_nodes > 0 ? (unsigned)opts->task_nodes : 0u;
     const char* env_dd = getenv("DQ_SUDOKU_DONATE_DEPTH");
     A.donate_depth = env_dd ? atoi(env_dd) : 5;     // measured sweep: 1..12, flat optimum around 5
@@ -1280,6 +1282,8 @@ static int run_batch_sudoku(dq_model* m, const uint8_t* cells_dev, int64_t n, in
     const char* env_dg = getenv("DQ_SUDOKU_DONATE_GAP");
     A.donate_min = env_dm ? (unsigned)atoi(env_dm) : kDonateMinNodes;
     A.donate_gap = env_dg ? (unsigned)atoi(env_dg) : kDonateGap;
+    const char* env_sg = getenv("DQ_SUDOKU_SPLIT_GAP");
+    A.split_gap = env_sg ? (unsigned)atoi(env_sg) : kSplitGap;
     const char* env_h = getenv("DQ_SUDOKU_HIDDEN_AFTER");
     A.strong_hidden_after = env_h ? (unsigned)atoi(env_h) : kStrongHiddenAfter;
     const char* env_q = getenv("DQ_SUDOKU_POP_QUORUM");

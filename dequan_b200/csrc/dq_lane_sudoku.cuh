@@ -108,6 +108,7 @@ struct SudokuArgs {
     uint32_t* hard;                        // [n][2] instances k_sudoku_first did not finish: {id, snapshot slot | stack level << 24}
     SudokuTask* tasks;    unsigned long long task_cap;
     uint4* snaps;         unsigned long long snap_cap;       // kSnapWords x uint4 per snapshot
+    uint32_t* snap_state;                  // [snap_cap] 1 while a snapshot is waiting for the task that resumes from it (the pool is a ring)
     unsigned long long* ctrl;              // control block, see SkCtrl
     unsigned long long user_budget;        // per-instance node budget of the API (0 = none)
     unsigned first_budget;                 // nodes k_sudoku_first spends on an instance before calling it hard
@@ -116,6 +117,7 @@ struct SudokuArgs {
     unsigned strong_hidden_after;          // k_sudoku_strong: value tries after which hidden-single propagation joins in
     int pop_quorum;                        // extra step-back rounds run while at least this many lanes still stand on an exhausted level
     int stack_levels;                      // the most blanks any instance of the batch has: levels of the lanes' (and k_sudoku_strong's) stacks
+    unsigned split_gap;                    // k_sudoku_count: a task splits unasked every time it has counted this many nodes
     unsigned force_donate;                 // test knob: donate whenever a task is this many nodes old, hungry lanes or not (0 = off)
 };
 
@@ -599,7 +601,7 @@ k_sudoku_first(SudokuArgs A) {
                 // counting pipeline picks it up exactly where it stands
                 const unsigned long long sslot = atomicAdd(A.ctrl + SKC_SNAP, 1ull);
                 const unsigned long long idx = atomicAdd(A.ctrl + SKC_HARD, 1ull);
-                if (sslot < A.snap_cap) sk_snap_write(A.snaps + (size_t)sslot * kSnapWords, S, t, L.sp, L.passrem, L.dom_rem);
+                if (sslot < A.snap_cap) { sk_snap_write(A.snaps + (size_t)sslot * kSnapWords, S, t, L.sp, L.passrem, L.dom_rem); A.snap_state[sslot] = 1u; }
                 else atomicOr(A.ctrl + SKC_ERROR, 2ull);
                 A.hard[2 * idx] = L.puzzle;
                 A.hard[2 * idx + 1] = (uint32_t)sslot | ((uint32_t)L.sp << 24);
@@ -905,7 +907,7 @@ k_sudoku_walk(SudokuArgs A) {
 constexpr int kDonatePeriod = 32;
 constexpr uint32_t kDonateMinNodes = 48;    // a task younger than this keeps its stack to itself
 constexpr uint32_t kDonateGap = 96;         // ... and so does one that gave a level away fewer nodes ago than this
-constexpr uint32_t kSplitGap = 4096;        // a task splits unasked every time it has counted this many nodes
+constexpr uint32_t kSplitGap = 512;         // a task splits unasked every time it has counted this many nodes (1 M puzzles, count stage: 4096 -> 11.0 ms, 1024 -> 10.2, 512 -> 9.9, 256 -> 10.0, 128 -> 33.8)
 
 __global__ void __launch_bounds__(kSudokuBlock)
 k_sudoku_count(SudokuArgs A) {
@@ -995,7 +997,7 @@ k_sudoku_count(SudokuArgs A) {
             L.passrem = 0; L.dom_rem = 0;
             L.have = true;
             donate_at = A.force_donate ? A.force_donate : A.donate_min;
-            split_at = kSplitGap;
+            split_at = A.split_gap;
             if (info & SKT_ROOT) {
                 // path values at the levels above, then the task's own value at its level: committed above
                 const int l0 = (int)(info & 0xFF);
@@ -1015,6 +1017,8 @@ k_sudoku_count(SudokuArgs A) {
                 if (info & SKT_TOP) L.dom_rem = sk_snap_entry(sb, hi + 1) & 0x1FF;
                 else L.dom_rem = ~sk_used_at(S, t, L.c) & 0x1FF & ~((2u << (e >> 9)) - 1u);   // the values above the one the donor took here
                 L.enter = false;
+                __threadfence();
+                A.snap_state[got_snap] = 0u;                     // the snapshot has been read: its slot is free again
             }
         }
         poll_now = false;
@@ -1029,8 +1033,10 @@ k_sudoku_count(SudokuArgs A) {
             if (lane == 0) out = vctrl[SKC_OUTSTANDING];
             out = __shfl_sync(0xFFFFFFFFu, out, 0);
             if (out == 0) break;
-            __nanosleep(200);
-            if (++spins > 8000000u) { if (lane == 0) atomicOr(A.ctrl + SKC_ERROR, 1ull); break; }
+            __nanosleep(spins < 4096u ? 200u : 2000u);
+            // (a guard against a hang, not a deadline: batches of hard puzzles keep a few lanes busy for seconds while
+            // everybody else waits here — about four minutes of waiting before the warp gives up)
+            if (++spins > 120000000u) { if (lane == 0) atomicOr(A.ctrl + SKC_ERROR, 1ull); break; }
             poll_now = true;
             continue;
         }
@@ -1055,34 +1061,34 @@ k_sudoku_count(SudokuArgs A) {
                     int l = L.base_sp;
                     while (l < L.sp && (S.stk[l][t] & 0x1FF) == 0) ++l;
                     if (l + A.donate_depth <= L.sp) hl = l;                               // a level close to the current one roots a tiny subtree
-                    else if (L.nodes >= split_at) split_at = L.nodes + kSplitGap / 4;     // nothing to give right now: look again soon
+                    else if (L.nodes >= split_at) split_at = L.nodes + A.split_gap / 4;     // nothing to give right now: look again soon
                 }
                 const uint32_t elig = __ballot_sync(0xFFFFFFFFu, hl >= 0);
                 const long long quota = min((long long)8, demand / (long long)total_warps + 1);
                 if (hl >= 0 && (L.nodes >= split_at || (long long)__popc(elig & lt) < quota)) {
-                    atomicAdd(A.ctrl + SKC_OUTSTANDING, 1ull);                 // the piece exists from here on
-                    const unsigned long long slot = atomicAdd(A.ctrl + SKC_RESERVE, 1ull);
-                    const unsigned long long sslot = atomicAdd(A.ctrl + SKC_SNAP, 1ull);
-                    if (slot >= A.task_cap) {                                  // pool full: nobody will ever claim it
-                        atomicAdd(A.ctrl + SKC_OUTSTANDING, 0ull - 1ull);
-                        donate_at = 0xFFFFFFFFu; split_at = 0xFFFFFFFFu;       // ... and this task stops offering
-                    } else if (sslot >= A.snap_cap) {
-                        donate_at = 0xFFFFFFFFu; split_at = 0xFFFFFFFFu;
-                        // publish a null task: whoever claims it closes it
-                        volatile uint32_t* rec = reinterpret_cast<volatile uint32_t*>(A.tasks + slot);
-                        rec[0] = L.puzzle; rec[1] = 0;
-                        __threadfence();
-                        rec[2] = SKT_VALID | SKT_NULL;
+                    // a snapshot slot first (the pool is a ring: a slot is free again once the task that resumes from it has
+                    // read it); none free at this position: no piece this time, the task offers again a little later
+                    const unsigned long long sslot = atomicAdd(A.ctrl + SKC_SNAP, 1ull) % A.snap_cap;
+                    if (atomicCAS(A.snap_state + sslot, 0u, 1u) != 0u) {
+                        donate_at = L.nodes + A.donate_gap; split_at = L.nodes + A.split_gap / 4;
                     } else {
-                        // stack snapshot, levels 0..hl
-                        sk_snap_write(A.snaps + (size_t)sslot * kSnapWords, S, t, hl + 1, 0u, 0u);
-                        volatile uint32_t* rec = reinterpret_cast<volatile uint32_t*>(A.tasks + slot);
-                        rec[0] = L.puzzle; rec[1] = (uint32_t)sslot;
-                        __threadfence();
-                        rec[2] = SKT_VALID | (uint32_t)L.base_sp | ((uint32_t)hl << 8);
-                        L.base_sp = hl + 1;                                      // this task keeps the deeper levels
-                        donate_at = L.nodes + (A.force_donate ? A.force_donate : A.donate_gap);
-                        split_at = L.nodes + kSplitGap;
+                        atomicAdd(A.ctrl + SKC_OUTSTANDING, 1ull);             // the piece exists from here on
+                        const unsigned long long slot = atomicAdd(A.ctrl + SKC_RESERVE, 1ull);
+                        if (slot >= A.task_cap) {                              // task pool full: nobody will ever claim it
+                            atomicAdd(A.ctrl + SKC_OUTSTANDING, 0ull - 1ull);
+                            A.snap_state[sslot] = 0u;
+                            donate_at = 0xFFFFFFFFu; split_at = 0xFFFFFFFFu;   // ... and this task stops offering
+                        } else {
+                            // stack snapshot, levels 0..hl
+                            sk_snap_write(A.snaps + (size_t)sslot * kSnapWords, S, t, hl + 1, 0u, 0u);
+                            volatile uint32_t* rec = reinterpret_cast<volatile uint32_t*>(A.tasks + slot);
+                            rec[0] = L.puzzle; rec[1] = (uint32_t)sslot;
+                            __threadfence();
+                            rec[2] = SKT_VALID | (uint32_t)L.base_sp | ((uint32_t)hl << 8);
+                            L.base_sp = hl + 1;                                  // this task keeps the deeper levels
+                            donate_at = L.nodes + (A.force_donate ? A.force_donate : A.donate_gap);
+                            split_at = L.nodes + A.split_gap;
+                        }
                     }
                 }
             }
@@ -1111,7 +1117,7 @@ k_sudoku_count(SudokuArgs A) {
             sk_enter(S, t, L.c, bt, dom, pass);
             L.dom_rem = dom; L.passrem = pass; L.enter = false;
         }
-        if (L.nodes >= 0x80000000u) { L.nodes_hi += L.nodes; L.nodes = 0; donate_at = 0; split_at = kSplitGap; }
+        if (L.nodes >= 0x80000000u) { L.nodes_hi += L.nodes; L.nodes = 0; donate_at = 0; split_at = A.split_gap; }
 
         // ---------------- closed tasks leave the outstanding count ----------------
         {
