@@ -1261,7 +1261,8 @@ static int run_batch_sudoku(dq_model* m, const uint8_t* cells_dev, int64_t n, in
     int rc = DQ_OK;
     // the number of pieces handed over at the tail does not shrink with the batch: generous floors (64 MB + 192 MB)
     const unsigned long long task_cap = std::max<unsigned long long>(1u << 24, std::min<unsigned long long>(8ull * n, 1ull << 26));   // (16 B each; a task per 512 counted nodes and more)
-    const unsigned long long snap_cap = std::max<unsigned long long>(1u << 20, std::min<unsigned long long>(2ull * n, 1ull << 23));
+    // (one parked snapshot per hard instance stays for the whole call, the rest of the ring recycles; slots are 24-bit in the hard list)
+    const unsigned long long snap_cap = std::min<unsigned long long>(std::max<unsigned long long>(1u << 20, (unsigned long long)n + (1u << 20)), 1ull << 24);
     const bool fresh_pool = m->s_tasks.cap < task_cap;
     DQ_CUDA(m->s_digest.reserve(n)); DQ_CUDA(m->s_hard.reserve(2 * (size_t)n)); DQ_CUDA(m->s_ctrl.reserve(16));
     DQ_CUDA(m->s_tasks.reserve(task_cap)); DQ_CUDA(m->s_snaps.reserve(snap_cap * kSnapWords)); DQ_CUDA(m->s_snap_state.reserve(snap_cap));

@@ -220,6 +220,24 @@ def test_sudoku_batch_mixed_blank_counts(product_lib):
     assert int(r.nodes[1]) == 81
 
 
+def test_sudoku_hard_batch_recycles_snapshots(product_lib):
+    """Hard puzzles (24 givens, 2e4 nodes each on average) split into millions of pieces: the snapshot ring recycles its
+    slots (round 1's linear pool ran out, after which no task could split).  The per-instance node counts do not depend
+    on how the work was cut — default splitting against forced splitting every 64 nodes — and a sample agrees with the
+    oracle."""
+    n = 30_000
+    cells = G.sudoku_batch(n, givens=24, seed=11)
+    tmpl = api.Model(sudoku_template())
+    a = tmpl.solve_batch_cells(cells)
+    b = tmpl.solve_batch_cells(cells, task_nodes=64)
+    assert a.n_sat == n and (a.status == 1).all()
+    assert (a.nodes == b.nodes).all() and (a.solution == b.solution).all() and a.total_nodes == b.total_nodes
+    order = np.argsort(a.nodes)
+    for i in list(order[:3]) + list(order[n // 2: n // 2 + 3]):
+        o = O.solve(sudoku(cells[i]), "first")
+        assert (int(a.nodes[i]), a.solution[i].tolist()) == (o.nodes, o.first)
+
+
 def test_sudoku_batch_large_properties(product_lib):
     """Size-independent properties at a size the oracle cannot cover."""
     n = 200_000
