@@ -238,6 +238,36 @@ def test_sudoku_hard_batch_recycles_snapshots(product_lib):
         assert (int(a.nodes[i]), a.solution[i].tolist()) == (o.nodes, o.first)
 
 
+def test_sudoku_batch_unsolvable_without_clash(product_lib):
+    """One given of each puzzle replaced by a value its row, column and box do not rule out: no clash for the digest to
+    defer, but (mostly) no solution either — the lane pipeline's own unsat / budget paths (exhausted root level in the
+    first stage, "whole parked stack" tasks in the counting stage) against the oracle."""
+    n = 48
+    cells = G.sudoku_batch(n, givens=30, seed=21)
+    rng = np.random.default_rng(5)
+    for i in range(n):
+        g = cells[i].reshape(9, 9)
+        given = np.argwhere(g != 0)
+        for r, c in given[rng.permutation(len(given))]:
+            seen = set(g[r, :]) | set(g[:, c]) | set(g[3 * (r // 3):3 * (r // 3) + 3, 3 * (c // 3):3 * (c // 3) + 3].ravel())
+            free = [v for v in range(1, 10) if v not in seen]
+            if free:
+                g[r, c] = free[0]
+                break
+    budget = 400_000
+    r = api.Model(sudoku_template()).solve_batch_cells(cells, node_budget=budget)
+    seen_status = set()
+    for i in range(n):
+        o = O.solve(sudoku(cells[i]), "first", budget)
+        assert (api.OUTCOME[r.status[i]], int(r.nodes[i])) == (o.status, o.nodes), i
+        if o.status == "sat":
+            assert r.solution[i].tolist() == o.first
+        else:
+            assert not r.solution[i].any()
+        seen_status.add(o.status)
+    assert "unsat" in seen_status
+
+
 def test_sudoku_batch_large_properties(product_lib):
     """Size-independent properties at a size the oracle cannot cover."""
     n = 200_000
