@@ -19,9 +19,13 @@
 //                         i.e. the DFS order of the prefix.  One lane per (record, value) pair: a value
 //                         of the current domain is a node; a surviving child is appended to the next
 //                         frontier with a CTA-aggregated atomic.
-//   k_queens_bucket     : the search below the depth-k records: per-warp pools of open frames
-//                         {a, l, r, untried} in shared memory, bucketed by depth, 32 nodes of ONE depth
-//                         per trip (see the comment above the kernel).  DEFAULT.
+//   k_queens_bucket_t   : the search below the depth-k records: per-warp pools of open frames
+//                         {a, l, r, untried} in shared memory, bucketed by depth, 64 nodes of ONE depth
+//                         per trip; compiled per bucket count (up to 8), levels as static control flow, the
+//                         records in registers and the last variable in the lane (see the comments above
+//                         the kernel).  DEFAULT.
+//   k_queens_bucket     : the same search with the bucket count at run time, for splits that leave more
+//                         than eight buckets.
 //   k_queens_first_warp : one warp, on a side stream, walks the tree in the reference's order to the
 //                         DFS-first solution of this partition (solution bookkeeping stays out of the
 //                         counting kernel).
