@@ -475,9 +475,9 @@ k_queens_bucket(QueensLaneArgs A) {
 // into the code of level v+1 when it has, and repeats itself while its own bucket still holds 64 (queens_run_from) —
 // no level choice, no jump table, no shuffle in the trip's dependency chain.
 //
-// This kernel is bound by the ALU pipe (LOP3 / SHF / ISETP / VIMNMX: 16 lanes per clock and SM quarter, the INT32
-// roofline of bench.py), with the FMA pipe's integer multiply-add (IMAD, another 16 lanes per clock) idle next to it.
-// So what can be a multiplication is one: left shifts, the rank of a lane in a ballot (popc(ballot * 2^(32-lane))),
+// The round-1 kernel was bound by the ALU pipe (LOP3 / SHF / ISETP / VIMNMX: 16 lanes per clock and SM quarter, the
+// INT32 roofline of bench.py), with the FMA pipe's integer multiply-add (IMAD, another 16 lanes per clock) idle next to
+// it.  So what can be a multiplication is one: left shifts, the rank of a lane in a ballot (popc(ballot * 2^(32-lane))),
 // and unions of disjoint masks (sums).
 struct QueensTripState {
     uint32_t cnt[8];                       // frames per bucket (warp-uniform)
@@ -501,7 +501,8 @@ __device__ __forceinline__ uint32_t mad_lo(uint32_t a, uint32_t b, uint32_t c) {
 //     (na << j | 2^j - 1)  |  nl << 2j  |  nr        is all ones
 // — the same test as na | nl << j | nr >> j moved j bits up, so that no operand shifts right: the two left shifts are
 // multiplications, and the ALU pipe is left with one LOP3 per row and the maximum.  Exact while no board bit of
-// nl << 2j leaves the word: N + 2j <= 32, i.e. for the rows j <= JUP = (32 - N) / 2; the others keep the plain form.
+// nl << 2j leaves the word: N + 2j <= 32.  Rows 1 .. JUP take this form and the others the plain one; the host picks
+// JUP = 5 (boards up to 22 queens), the mix that loads the two pipes equally (profiles/r2_queens_split_depth.txt), else 0.
 // ls = l | value bit (nl before its shift).
 // The powers of two and the low ones of the first product come in registers whose values the compiler cannot see
 // (QueensRowConsts): knowing them it turns the multiply-add back into a shift-add (LEA) plus a LOP3 on the ALU pipe.
